@@ -1,0 +1,26 @@
+/*
+ * engine_bridge.h -- host-side glue between the ALiS public structs and the engine C ABI.
+ * See engine_bridge.c.  Internal header (not installed).
+ */
+#ifndef ALIS_ENGINE_BRIDGE_H
+#define ALIS_ENGINE_BRIDGE_H
+
+#include "alis_b200.h"
+
+typedef struct alis_bridge alis_bridge;
+
+alis_bridge  *alis_bridge_create(world W);           /* allocates the engine (fields start at 0) */
+void          alis_bridge_destroy(alis_bridge *B);
+void          alis_bridge_commit(alis_bridge *B);    /* upload coefficients/sources/copies       */
+void          alis_bridge_invalidate(alis_bridge *B);/* setup changed: re-commit before next step */
+void          alis_bridge_step_E(alis_bridge *B);    /* updateE  (update.c:275-299)              */
+void          alis_bridge_step_H(alis_bridge *B);    /* updateH  (update.c:302-341)              */
+alisb_engine *alis_bridge_engine(alis_bridge *B);
+void          alis_bridge_read_field(alis_bridge *B, int set, int comp, int m, float *host);
+void          alis_bridge_write_field(alis_bridge *B, int set, int comp, int m, const float *host);
+
+/* provided by the including side (product host layer or test harness) */
+int alis_source_target(world W, source S, int set, int *comp, int *m);   /* 0 on success */
+int alis_bridge_device(void);                                            /* CUDA ordinal  */
+
+#endif

@@ -1,0 +1,209 @@
+/*
+ * alis_b200.h -- C ABI of the B200 FDTD time-stepping engine.
+ *
+ * This is the boundary between host C code (the ALiS-compatible public API in
+ * include/alis.h, implemented in alis_b200/host/) and the hand-written sm_100a
+ * CUDA kernels in alis_b200/csrc/.  Plain pointers, sizes and POD structs only.
+ *
+ * What each entry point replaces in the reference (hseelab/alis, src/):
+ *   alisb_create / alisb_set_axis_tables   fields+psi allocation and 1-D tables
+ *                                          world.c:164-189 (makeVectorField),
+ *                                          world.c:98-161 (makeCpmlCoeff, makeVFieldCoeff)
+ *   alisb_set_inv_eps                      CE->x/y/z  object.c:168-174,374-398
+ *   alisb_add_dispersive                   ADE boxes  object.c:178-226,290-336
+ *   alisb_add_source                       source lists W->SE/W->SH  source.c:52-75, update.c:161-179
+ *   alisb_add_tfsf                         TFSF list W->S  source.c:269-334, update.c:194-272
+ *   alisb_set_copies                       copyBoundary call lists  update.c:182-191,284-297,311-339
+ *   alisb_step_E / alisb_step_H            updateE / updateH  update.c:275-341
+ *   alisb_phaser_*                         createPhasers/updatePhaser  phaser.c:21-110
+ *   alisb_read_box / alisb_write_box       the host float*** views  world.c:58-70
+ *
+ * Coordinates.  The engine uses ARRAY coordinates: a = i-(iMIN-1), b = j-(jMIN-1),
+ * c = k-(kMIN-1), so a runs 0..nx+1 where 1..nx are the updated cells (iMIN..iMAX) and
+ * 0 / nx+1 are the reference's ghost layer (world.c:170-172).  All boxes are inclusive
+ * [lo,hi] in array coordinates.  Host-side dense blocks are packed like the reference's
+ * makeField blocks: c (z) fastest, then b, then a  (world.c:58-70).
+ * On the device the layout is x fastest / z slowest.
+ *
+ * Errors: every function returns 0 on success, a negative ALISB_E* code otherwise;
+ * alisb_last_error() returns a static description.  There is NO CPU fallback: if no
+ * CUDA device is usable alisb_create fails.
+ */
+#ifndef ALIS_B200_H
+#define ALIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALISB_ABI_VERSION 1
+
+enum { ALISB_OK = 0, ALISB_EINVAL = -1, ALISB_ENOMEM = -2, ALISB_ECUDA = -3, ALISB_ESTATE = -4 };
+
+enum { ALISB_SET_E = 0, ALISB_SET_H = 1 };
+enum { ALISB_X = 0, ALISB_Y = 1, ALISB_Z = 2 };
+enum { ALISB_LO = 0, ALISB_HI = 1 };
+
+/* array identifiers for alisb_read_box / alisb_write_box */
+enum {
+	ALISB_ARR_FIELD   = 0,  /* set, comp, m                                       */
+	ALISB_ARR_INVEPS  = 1,  /* comp                      (E only)                 */
+	ALISB_ARR_PSI     = 2,  /* set, m, axis, side, which (0: comp axis+1, 1: axis+2) */
+	ALISB_ARR_ADE_J   = 3,  /* m, object, pole, comp                              */
+	ALISB_ARR_ADE_K   = 4,  /* m, object, pole, comp                              */
+	ALISB_ARR_ADE_FILL= 5   /* object, comp                                       */
+};
+
+typedef struct alisb_engine alisb_engine;
+typedef struct alisb_phaser alisb_phaser;
+
+/* Grid description (reference struct world, alis_c.h:109-130, index part). */
+typedef struct {
+	int32_t nx, ny, nz;          /* iNUM, jNUM, kNUM: updated cells per axis                  */
+	int32_t complex_field;       /* W->complexField: 1 => a second (imaginary) field set      */
+	float   dt;                  /* W->dt                                                     */
+	/* CPML/ADE-PML slabs, update.c:119-124.  pml[set][axis][side] = {first,last} cell in
+	 * array coordinates (inclusive), or first>last for "no slab".                        */
+	int32_t pml[2][3][2][2];
+	/* z-slab sharding: this engine instance owns global planes
+	 * c = kshard_lo .. kshard_lo+nz-1 of a global grid of nz_global planes.  For a
+	 * single-GPU world kshard_lo = 1 and nz_global = nz.  pml[][Z] and all boxes are
+	 * LOCAL to the shard.                                                               */
+	int32_t kshard_lo, nz_global;
+	int32_t device;              /* CUDA device ordinal                                       */
+	int32_t reserved[5];
+} alisb_grid;
+
+/* Dispersive object: per-object ADE data, reference coeffs (alis_c.h:96-107),
+ * object.c:178-226 (allocation), :290-336 (coefficients), update.c:89-108,128-158. */
+#define ALISB_MAXPOLES 6
+typedef struct {
+	int32_t box[6];              /* a0,a1,b0,b1,c0,c1 inclusive (bbox clipped to updated cells +1) */
+	int32_t nj, nk;              /* NJ (Drude poles), NK (all poles)                           */
+	float   a[3];                /* ax, ay, az loss factors                                    */
+	float   JJ[3][ALISB_MAXPOLES], JK[3][ALISB_MAXPOLES], JE[3][ALISB_MAXPOLES];
+	float   KJ[3][ALISB_MAXPOLES], KK[3][ALISB_MAXPOLES], KE[3][ALISB_MAXPOLES];
+	const float *fill[3];        /* CE->Jx/Jy/Jz[n]: dense host blocks over box, z fastest      */
+} alisb_dispersive;
+
+/* Waveform callback evaluated ON THE HOST with the caller's libm (so that the value
+ * is bit-identical to the reference's S->waveForm(W,S,t,phase), update.c:166-171). */
+typedef float (*alisb_waveform_fn)(void *user, float t, float phase);
+
+/* Soft source (reference struct source, alis_c.h:305-312; update.c:161-179). */
+typedef struct {
+	int32_t set, comp, m;        /* target array: E or H, component, field set (0 real, 1 imag) */
+	int32_t box[6];
+	float   amplitude, phase;    /* scalars used when the arrays below are NULL                 */
+	const float *Amplitude;      /* dense host block over box or NULL                           */
+	const float *Phase;          /* dense host block over box or NULL                           */
+	uint64_t n_active;           /* S->N: source adds while engine step counter n < n_active    */
+	alisb_waveform_fn waveform;
+	void   *user;
+} alisb_source;
+
+/* One TFSF face strip: F[a,b,c] += coef * G_aux[clamp(a+alt)...] (* inv_eps) -- update.c:194-202
+ * with the call lists of update.c:205-272.  The aux array is indexed through the
+ * reference's pointer aliasing (source.c:223-248): aux index = min(index, clamp). */
+typedef struct {
+	int32_t comp;                /* target component of the pass's field set                    */
+	int32_t aux_comp;            /* component of the aux world's OTHER field set                */
+	float   coef;                /* +-dtd?[face]                                                */
+	int32_t box[6];              /* in MAIN array coordinates                                   */
+	int32_t alt[3];              /* iAlt,jAlt,kAlt added before the aux lookup                  */
+	int32_t use_eps;             /* multiply by inv_eps[comp] (E pass with CE->x allocated)     */
+} alisb_strip;
+
+typedef struct {
+	alisb_engine *aux;           /* auxiliary world engine; stepped first (update.c:207,242)    */
+	int32_t offset[3];           /* aux array coord = main array coord + offset                 */
+	int32_t clamp[2][3][2];      /* [aux set][aux comp][0:x,1:y] max aux array coord (aliasing) */
+	const alisb_strip *strips_E; int32_t n_strips_E;   /* applied to every field set m         */
+	const alisb_strip *strips_H; int32_t n_strips_H;
+} alisb_tfsf;
+
+/* One boundary copy (reference copyBoundary, update.c:182-191).  Executed in list order.
+ * real:    F[p] = cosk*F[p+alt]
+ * complex: F0[p] = cosk*F0[p+alt] + sink*F1[p+alt];  F1[p] = cosk*F1[p+alt] - sink*F0[p+alt] */
+typedef struct {
+	int32_t set, comp;
+	float   cosk, sink;
+	int32_t box[6];
+	int32_t alt[3];
+} alisb_copy;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+int  alisb_abi_version(void);
+const char *alisb_last_error(void);
+const char *alisb_backend(void);                 /* "cuda-sm_100a" or "oracle-cpu"            */
+int  alisb_create(const alisb_grid *grid, alisb_engine **out);
+void alisb_destroy(alisb_engine *e);
+int  alisb_set_stream(alisb_engine *e, void *cuda_stream);   /* NULL = engine-owned stream    */
+
+/* ---- coefficients ---------------------------------------------------------------- */
+/* dtd, P, P1, P2: host arrays of n+2 floats in array coordinates (n = nx/ny/nz of the axis).
+ * P/P1/P2 = C->xP,xPy,xPz | yP,yPz,yPx | zP,zPx,zPy (world.c:155-157); NULL if no PML.   */
+int  alisb_set_axis_tables(alisb_engine *e, int set, int axis, const float *dtd,
+                           const float *P, const float *P1, const float *P2);
+/* dense host blocks exactly like the reference's allocations (object.c:168-170):
+ *   cx covers a in [1,nx+1], b in [1,ny],   c in [1,nz]
+ *   cy covers a in [1,nx],   b in [1,ny+1], c in [1,nz]
+ *   cz covers a in [1,nx],   b in [1,ny],   c in [1,nz+1]      (z fastest)
+ * NULL for all three = vacuum (CE->x == NULL, update.c:109,114).                          */
+int  alisb_set_inv_eps(alisb_engine *e, const float *cx, const float *cy, const float *cz);
+int  alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *obj);
+int  alisb_clear_dispersive(alisb_engine *e);    /* removeObjects: ADE boxes and their J/K     */
+int  alisb_add_source(alisb_engine *e, const alisb_source *src);
+int  alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t);
+int  alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops, int n);
+int  alisb_clear_sources(alisb_engine *e);       /* removeSources: sources + tfsf links        */
+
+/* ---- time stepping --------------------------------------------------------------- */
+int  alisb_step_E(alisb_engine *e);              /* updateE, update.c:275-299                 */
+int  alisb_step_H(alisb_engine *e);              /* updateH, update.c:302-341                 */
+int  alisb_run(alisb_engine *e, int steps);      /* steps x (E then H), no host sync between  */
+int  alisb_synchronize(alisb_engine *e);
+int  alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH);
+int  alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH);
+int  alisb_reset_fields(alisb_engine *e);        /* rebootWorld field part, world.c:334-368   */
+
+/* ---- data access (parity dumps, slices, get) -------------------------------------- */
+/* ids: meaning depends on arr (see enum).  box inclusive, host block dense z-fastest.      */
+int  alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host);
+int  alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host);
+
+/* ---- z-slab halo (multi-GPU) -------------------------------------------- */
+/* Buffers (device memory for the CUDA engine) holding one full z-plane incl. ghosts of
+ * component comp (x or y) of field set `set`, copy m:
+ *   send : the owned plane a neighbour needs (E: top plane c=nz -> upper neighbour's c=0;
+ *          H: bottom plane c=1 -> lower neighbour's c=nz+1)     [update.c:110-111]
+ *   recv : the ghost plane filled by the neighbour (E: c=0, H: c=nz+1)
+ * The CUDA engine hands out pointers straight into the field arrays (planes are
+ * contiguous in its x-fastest/z-slowest layout), so pack/unpack are no-ops there.          */
+int  alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes);
+int  alisb_halo_pack(alisb_engine *e, int set);      /* owned planes -> send buffers (on stream) */
+int  alisb_halo_unpack(alisb_engine *e, int set);    /* recv buffers -> ghost planes (on stream) */
+
+/* ---- running DFT (phasers) ---------------------------------------------------------- */
+/* box = interior-clipped monitor box; face_mask bit (axis*2+side) set => that face is
+ * accumulated (phaser.c:57-62).  nfreq accumulator sets.                                  */
+int  alisb_phaser_create(alisb_engine *e, const int32_t box[6], int face_mask, int nfreq, alisb_phaser **out);
+void alisb_phaser_destroy(alisb_phaser *p);
+/* expE/expH: nfreq (re,im) pairs = cexpf(2*pi*i*f*tE), cexpf(2*pi*i*f*tH) from the host.  */
+int  alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const float *expH);
+/* which: 0,1 = E1,E2 ; 2,3 = H1,H2 of that face (phaser.c:57-62 ordering); host gets
+ * (re,im) pairs, dense over the face, z fastest.                                           */
+int  alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *host_complex);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+uint64_t alisb_launch_count(alisb_engine *e);    /* kernels launched by this engine so far   */
+/* CUDA-event time (ms) of the volume kernels of the last alisb_run, and their launch count */
+int  alisb_last_run_kernel_ms(alisb_engine *e, float *ms_total, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIS_B200_H */

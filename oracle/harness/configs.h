@@ -1,0 +1,179 @@
+/*
+ * configs.h -- test configurations written purely against the ALiS public API
+ * (createWorld / putObjects / pointDipole / planewave ...).  The same source is compiled
+ *   - against the unmodified reference (oracle/_ref)            -> golden behaviour
+ *   - against the reference setup + our engine through the bridge -> engine parity
+ *   - against our own host layer + engine (the drop-in)          -> end-to-end parity
+ * Configurations follow reference examples/*.c (cited per function); IDs are "" so that
+ * createWorld does not shell out to `rm -fr` (reference world.c:275-278).
+ */
+#ifndef HARNESS_CONFIGS_H
+#define HARNESS_CONFIGS_H
+#include <string.h>
+
+typedef struct { const char *name; world (*make)(void); int default_steps; int order; } harness_config;
+
+/* examples/Dipole_PML.c:6-13 */
+static world cfg_dipole_pml(void)
+{
+	dom Dom = {{1000}, {1000}, {1000}};
+	res Res = {10, {20}, {1240}};
+	sur Sur = {{SYM, PML}, {SYM, PML}, {SYM, PML}, {24}};
+	world W = createWorld(Dom, Res, Sur, "");
+	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 10000000);
+	return W;
+}
+
+/* SURVEY 8d synthetic config at a small size: all-PML vacuum cube, Num=12 */
+static world cfg_vacuum_cpml(void)
+{
+	dom Dom = {{-250, 240}, {-190, 180}, {-150, 140}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PML, PML}, {PML, PML}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 1);
+	return W;
+}
+
+/* PEC cavity, no PML, off-centre Hy dipole */
+static world cfg_pec_box(void)
+{
+	dom Dom = {{-200, 200}, {-150, 150}, {-100, 100}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PEC, PEC}, {PEC, PEC}, {PEC, PEC}};
+	world W = createWorld(Dom, Res, Sur, "");
+	pointDipole(W, Hy, 30, -20, 10, Sine, 300, 3, 1);
+	return W;
+}
+
+/* periodic (PBC) in x,y + PML in z with a dielectric slab and a Band dipole */
+static world cfg_pbc_slab(void)
+{
+	dom Dom = {{-150, 150}, {-100, 100}, {-300, 300}};
+	res Res = {5, {10}, {1240, 4}};
+	sur Sur = {{PBC}, {PBC}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Slab = {Box, {{-INF, INF}, {-INF, INF}, {-55, 45}}};
+	object Ball1 = {Ball, {{-60, 60}, {-60, 60}, {100, 220}}};
+	putObjects(W, n(2.0), Ball1, n(3.4), Slab, Air);
+	pointDipole(W, Ex, 10, 20, 150, Band, 500, 900, 1);
+	return W;
+}
+
+/* examples/Nanoblock_Scattering.c:6-15 : CPML + Au (Drude + 2 critical points) + substrate
+ * + oblique TFSF plane wave (complex Bloch 2-D auxiliary world) */
+static world cfg_nanoblock(void)
+{
+	dom DTF = {{300}, {300}, {300}};
+	dom DSF = {{400}, {400}, {400}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PML}, {SYM, PML}, {PML}};
+	world W = createWorld(DSF, Res, Sur, "");
+	object Nanoblock = {Box, {{-200, 200}, {-200, 200}, {-200, 200}}};
+	object Substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF,-200}}};
+	putObjects(W, Au, Nanoblock, n(1.5), Substrate, Air);
+	planewave(W, DTF, Ppol, 55, 0, Sine, 500, 20);
+	return W;
+}
+
+/* normal-incidence S-polarised TFSF (1-D auxiliary world) on a lossy + Lorentz particle */
+static world cfg_tfsf_normal(void)
+{
+	dom DTF = {{200}, {200}, {200}};
+	dom DSF = {{300}, {300}, {300}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{SYM, PML}, {SYM, PML}, {PML}};
+	world W = createWorld(DSF, Res, Sur, "");
+	matter Lossy = {{2.25}, {{0, 0.35}, {2.1, 0.3, 1.7}}};
+	object Particle = {Ball, {{-120, 120}, {-120, 120}, {-120, 120}}};
+	putObjects(W, Lossy, Particle, Air);
+	planewave(W, DTF, Spol, 0, 0, Pulse, 600, 900);
+	return W;
+}
+
+/* examples/PhC_Band_Diagram.c:6-24 : Bloch (BBC) in x, hexagonal Bloch (HBC) in y, complex fields */
+static world cfg_phc(void)
+{
+	float kx, ky, k=1.2;
+	if (k<=0 || k>=3) kx = 0, ky = 0;
+	else if (k < 1) kx =   0, ky =   k;
+	else if (k < 2) kx = k-1, ky =   1;
+	else if (k < 3) kx = 3-k, ky = 3-k;
+	dom Dom = {{250}, {0, 250*sqrtf(3)}, {500}};
+	res Res = {5, {10, 5*sqrtf(3), 10}, {1240}};
+	sur Sur = {{BBC, 500*3/kx}, {HBC, 500*sqrtf(3)/ky}, {SYM, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Slab = {Difference, {2}, objects {
+						{Box, {{-INF, INF}, {-INF, INF}, {-100, 100}}},
+						{DLattice, {{500}, {500*sqrtf(3)}}, objects {
+							{RodZ, {{-200, 200}, {-200, 200}, {-INF, INF}}},
+						}},
+					}};
+	putObjects(W, n(3.5), Slab, Air);
+	pointDipole(W, iHz, 200, 100*sqrtf(3), 0, Band, 750, 2000);
+	return W;
+}
+
+/* examples/Metasurface_Farfield.c:6-15 */
+static world cfg_metasurface(void)
+{
+	dom DTF = {{500}, {500}, {300}};
+	dom DSF = {{500}, {500}, {500}};
+	res Res = {10, {20}, {1240}};
+	sur Sur = {{BBC}, {SYM}, {PML}};
+	world W = createWorld(DSF, Res, Sur, "");
+	object Nanoblock = {Lattice, {{500}, {500}}, objects {{Box, {{0, 200}, {-100, 100}, {-100, 100}}}}};
+	object Substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF,-100}}};
+	putObjects(W, n(4), Nanoblock, n(1.5), Substrate, Air);
+	planewave(W, DTF, Ppol, 55, 0, Sine, 530, 5);
+	return W;
+}
+
+/* examples/Dipole_Band.c:6-11 : non-uniform grid, SYM + PML, Band dipole */
+static world cfg_dipole_band(void)
+{
+	dom Dom = {{500}, {500}, {500}};
+	res Res = {10, {20}, {1240}, {{2, 100}, {2, 100}, {2, 100}}};
+	sur Sur = {{SYM, PML}, {SYM, PML}, {SYM, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	pointDipole(W, Ex, 0, 0, 0, Band, 400, 800);
+	return W;
+}
+
+/* anisotropic Drude/critical-point matter (poles consumed in x,y,z triples, object.c:364-370),
+ * two overlapping dispersive objects, conductivity, PML on one side only */
+static world cfg_aniso_ade(void)
+{
+	dom Dom = {{-200, 200}, {-200, 200}, {-200, 200}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PML, PEC}, {PBC}, {PEC, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	matter Aniso = {{2.0, 3.0, 4.0}, {{8.0, 0.05}, {7.0, 0.06}, {6.0, 0.07}, {2.5, 0.3, 0.4, 0.2}, {2.7, 0.25, 0.5, 0.1}, {2.9, 0.2, 0.6, 0.3}}};
+	object A1 = {Box, {{-90, 60}, {-50, 110}, {-100, 20}}};
+	object A2 = {Ball, {{-20, 140}, {-80, 80}, {-40, 120}}};
+	putObjects(W, Ag, A2, Aniso, A1, n(1.2));
+	pointDipole(W, Ey, -120, 10, 130, Pulse, 450, 700, 1);
+	pointDipole(W, Hz, 100, -100, -100, Sine, 500, 4, 1, 30);
+	return W;
+}
+
+static const harness_config harness_configs[] = {
+	{"dipole_pml",  cfg_dipole_pml,  60, 0},
+	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
+	{"pec_box",     cfg_pec_box,     80, 0},
+	{"pbc_slab",    cfg_pbc_slab,    80, 0},
+	{"nanoblock",   cfg_nanoblock,   120, 1},
+	{"tfsf_normal", cfg_tfsf_normal, 120, 0},
+	{"phc",         cfg_phc,         100, 0},
+	{"metasurface", cfg_metasurface, 120, 0},
+	{"dipole_band", cfg_dipole_band, 80, 0},
+	{"aniso_ade",   cfg_aniso_ade,   100, 1},
+	{0, 0, 0, 0}
+};
+
+static const harness_config *harness_find(const char *name)
+{
+	for (const harness_config *c = harness_configs; c->name; c++) if (!strcmp(c->name, name)) return c;
+	return 0;
+}
+#endif
