@@ -1,0 +1,818 @@
+/*
+ * engine.cu -- the B200 FDTD engine behind the C ABI of include/alis_b200.h.
+ *
+ * Host orchestration of one updateE / updateH call (reference update.c:275-341):
+ *   E: [ADE loss, ADE current subtraction] -> fused curl+CPML volume kernel (per field set m)
+ *      -> TFSF (aux engine stepped first, then face strips) -> soft sources -> boundary copies
+ *   H: fused curl+CPML volume kernel -> ADE current update from the final E -> TFSF -> sources
+ *      -> boundary copies
+ * All launches go to one stream; nothing synchronises with the host inside a step.  Waveform
+ * scalars are evaluated on the host with the caller's libm (bit parity with the reference)
+ * and passed as kernel arguments.
+ *
+ * There is no CPU fallback: without a usable CUDA device alisb_create fails.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <vector>
+#include <algorithm>
+#include "alis_b200.h"
+#include "kernels.cuh"
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+	return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALISB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct SubBox { int tile0, ntiles, b0, b1, c0, c1; bool pml; };
+struct ProfRec { size_t ev; int set, sub; };
+
+struct DispObj {
+	alisb_dispersive d;
+	Box full, upd;
+	size_t cnt;
+	float *fill[3];
+	float *J[2][ALISB_MAXPOLES][3], *K[2][ALISB_MAXPOLES][3];
+};
+
+#define SRC_RING 4
+struct SrcObj {
+	alisb_source d;
+	Box B; size_t cnt;
+	float *dAmp;                       /* device dense box (x fastest) or NULL            */
+	std::vector<float> hAmp, hPha;     /* host copies in device order (x fastest)         */
+	float *hvals[SRC_RING], *dvals[SRC_RING]; cudaEvent_t ev[SRC_RING]; int slot;
+};
+
+struct TfsfObj {
+	alisb_tfsf d;
+	std::vector<alisb_strip> sE, sH;
+};
+
+struct alisb_engine {
+	alisb_grid g;
+	int nx, ny, nz, pitch;
+	size_t plane, elems;               /* floats per z-plane / per array (incl. slack)    */
+	float *F[2][2][3];
+	float *eps[3];
+	float *dtd[2][3], *P[2][3], *P1[2][3], *P2[2][3];
+	float *psi[2][2][3][2][2]; size_t psi_elems[2][3][2];
+	int xbase[2][2], xpitch[2][2];     /* [set][side]                                     */
+	std::vector<DispObj*> obj;
+	std::vector<SrcObj*> src[2];
+	std::vector<TfsfObj*> tf;
+	std::vector<alisb_copy> copies[2];
+	cudaStream_t stream; bool own_stream;
+	uint64_t step; float t, tE, tH;
+	uint64_t launches;
+	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
+	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
+	std::vector<ProfRec> prof;         /* one record per profiled volume sub-launch          */
+	float *scratch; size_t scratch_elems;
+};
+
+struct alisb_phaser {
+	alisb_engine *e;
+	int box[6]; int mask, nfreq;
+	Box face[6]; size_t cells[6];
+	float2 *acc[6];
+	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev; bool ev_pending;
+};
+
+extern "C" int alisb_abi_version(void) { return ALISB_ABI_VERSION; }
+extern "C" const char *alisb_last_error(void) { return g_err; }
+extern "C" const char *alisb_backend(void) { return "cuda-sm_100a"; }
+
+static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1)/b); }
+static inline Box mkbox(const int32_t b[6]) { Box B; B.a0=b[0]; B.b0=b[2]; B.c0=b[4]; B.na=b[1]-b[0]+1; B.nb=b[3]-b[2]+1; B.nc=b[5]-b[4]+1; if (B.na<0) B.na=0; if (B.nb<0) B.nb=0; if (B.nc<0) B.nc=0; return B; }
+static inline size_t bcount(const Box &B) { return (size_t)B.na*B.nb*B.nc; }
+
+static int dalloc(float **p, size_t n)
+{
+	*p = 0;
+	if (!n) return ALISB_OK;
+	cudaError_t e = cudaMalloc((void**)p, n*sizeof(float));
+	if (e != cudaSuccess) return fail(ALISB_ENOMEM, "cudaMalloc(%zu floats): %s", n, cudaGetErrorString(e));
+	e = cudaMemset(*p, 0, n*sizeof(float));
+	if (e != cudaSuccess) return fail(ALISB_ECUDA, "cudaMemset: %s", cudaGetErrorString(e));
+	return ALISB_OK;
+}
+#define TRY(call) do { int r_ = (call); if (r_ != ALISB_OK) return r_; } while (0)
+#define DEV(e) CU(cudaSetDevice((e)->g.device))
+
+/* host dense block, z fastest (reference layout)  <->  dense block, x fastest (device order) */
+static void to_xfast(const float *zf, float *xf, const Box &B)
+{
+	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
+		xf[((size_t)c*B.nb + b)*B.na + a] = zf[((size_t)a*B.nb + b)*B.nc + c];
+}
+static void to_zfast(const float *xf, float *zf, const Box &B)
+{
+	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
+		zf[((size_t)a*B.nb + b)*B.nc + c] = xf[((size_t)c*B.nb + b)*B.na + a];
+}
+
+extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
+{
+	if (!g || !out || g->nx < 1 || g->ny < 1 || g->nz < 1) return fail(ALISB_EINVAL, "bad grid");
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev < 1) return fail(ALISB_ECUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(ce));
+	if (g->device < 0 || g->device >= ndev) return fail(ALISB_EINVAL, "device %d out of range (%d devices)", g->device, ndev);
+	CU(cudaSetDevice(g->device));
+	alisb_engine *e = new alisb_engine();
+	e->g = *g; e->nx = g->nx; e->ny = g->ny; e->nz = g->nz;
+	e->pitch = ((ALISB_XO + g->nx + 2) + 31)/32*32;
+	e->plane = (size_t)(g->ny + 2)*e->pitch;
+	e->elems = e->plane*(g->nz + 2) + 64;
+	memset(e->F, 0, sizeof e->F); memset(e->eps, 0, sizeof e->eps); memset(e->psi, 0, sizeof e->psi);
+	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
+	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
+	e->scratch = 0; e->scratch_elems = 0;
+	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
+	for (int s=0; s<2; s++) for (int m=0; m<=g->complex_field; m++) for (int c=0; c<3; c++) TRY(dalloc(&e->F[s][m][c], e->elems));
+	for (int s=0; s<2; s++) {
+		/* tables: x ones are stored shifted by XO (so float4 loads of a quad are aligned) */
+		TRY(dalloc(&e->dtd[s][0], e->pitch + 8)); TRY(dalloc(&e->dtd[s][1], g->ny + 2)); TRY(dalloc(&e->dtd[s][2], g->nz + 2));
+		TRY(dalloc(&e->P[s][0], e->pitch + 8)); TRY(dalloc(&e->P1[s][0], e->pitch + 8)); TRY(dalloc(&e->P2[s][0], e->pitch + 8));
+		TRY(dalloc(&e->P[s][1], g->ny + 2)); TRY(dalloc(&e->P1[s][1], g->ny + 2)); TRY(dalloc(&e->P2[s][1], g->ny + 2));
+		TRY(dalloc(&e->P[s][2], g->nz + 2)); TRY(dalloc(&e->P1[s][2], g->nz + 2)); TRY(dalloc(&e->P2[s][2], g->nz + 2));
+		for (int sd=0; sd<2; sd++) {
+			const int f = g->pml[s][0][sd][0], l = g->pml[s][0][sd][1];
+			e->xbase[s][sd] = 1; e->xpitch[s][sd] = 4;
+			if (f <= l) {
+				e->xbase[s][sd] = sd == 0 ? 1 : 1 + 4*((f - 1)/4);
+				e->xpitch[s][sd] = (l - e->xbase[s][sd] + 1 + 3)/4*4;
+			}
+			for (int ax=0; ax<3; ax++) {
+				const int ff = g->pml[s][ax][sd][0], ll = g->pml[s][ax][sd][1];
+				size_t n = 0;
+				if (ff <= ll) {
+					if (ax == 0) n = (size_t)(g->nz + 2)*(g->ny + 2)*e->xpitch[s][sd];
+					if (ax == 1) n = (size_t)(g->nz + 2)*(ll - ff + 1)*e->pitch;
+					if (ax == 2) n = (size_t)(ll - ff + 1)*(g->ny + 2)*e->pitch;
+					n += 64;
+				}
+				e->psi_elems[s][ax][sd] = n;
+				for (int m=0; m<=g->complex_field; m++) for (int w=0; w<2; w++) TRY(dalloc(&e->psi[s][m][ax][sd][w], n));
+			}
+		}
+	}
+	int nb = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,true>, 256, 0));
+	cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, g->device));
+	e->resident_ctas = std::max(1, nb)*prop.multiProcessorCount;
+	*out = e;
+	return ALISB_OK;
+}
+
+static void free_src(SrcObj *s)
+{
+	if (!s) return;
+	cudaFree(s->dAmp);
+	for (int r=0; r<SRC_RING; r++) { if (s->hvals[r]) cudaFreeHost(s->hvals[r]); cudaFree(s->dvals[r]); if (s->ev[r]) cudaEventDestroy(s->ev[r]); }
+	delete s;
+}
+
+extern "C" int alisb_clear_sources(alisb_engine *e)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	for (int s=0; s<2; s++) { for (SrcObj *o : e->src[s]) free_src(o); e->src[s].clear(); }
+	for (TfsfObj *t : e->tf) delete t;
+	e->tf.clear();
+	return ALISB_OK;
+}
+
+extern "C" int alisb_clear_dispersive(alisb_engine *e)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	for (DispObj *o : e->obj) {
+		for (int c=0; c<3; c++) { cudaFree(o->fill[c]); for (int m=0; m<2; m++) for (int p=0; p<ALISB_MAXPOLES; p++) { cudaFree(o->J[m][p][c]); cudaFree(o->K[m][p][c]); } }
+		delete o;
+	}
+	e->obj.clear();
+	return ALISB_OK;
+}
+
+extern "C" void alisb_destroy(alisb_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->g.device);
+	cudaStreamSynchronize(e->stream);
+	alisb_clear_sources(e);
+	alisb_clear_dispersive(e);
+	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int c=0; c<3; c++) cudaFree(e->F[s][m][c]);
+	for (int c=0; c<3; c++) cudaFree(e->eps[c]);
+	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { cudaFree(e->dtd[s][ax]); cudaFree(e->P[s][ax]); cudaFree(e->P1[s][ax]); cudaFree(e->P2[s][ax]); }
+	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psi[s][m][ax][sd][w]);
+	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+	cudaFree(e->scratch);
+	if (e->own_stream) cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+extern "C" int alisb_set_stream(alisb_engine *e, void *s)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+	if (s) e->stream = (cudaStream_t)s;
+	else { CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+	return ALISB_OK;
+}
+
+static int upload_table(alisb_engine *e, float *dst, const float *src, int n, int shift)
+{
+	std::vector<float> h((size_t)n + 2 + shift, 0.f);
+	if (src) for (int q=0; q<n+2; q++) h[q + shift] = src[q];
+	CU(cudaMemcpyAsync(dst, h.data(), h.size()*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	return ALISB_OK;
+}
+
+extern "C" int alisb_set_axis_tables(alisb_engine *e, int set, int axis, const float *dtd, const float *P, const float *P1, const float *P2)
+{
+	if (set<0 || set>1 || axis<0 || axis>2 || !dtd) return fail(ALISB_EINVAL, "bad tables");
+	DEV(e);
+	const int n = axis==0 ? e->nx : axis==1 ? e->ny : e->nz, shift = axis==0 ? ALISB_XO : 0;
+	TRY(upload_table(e, e->dtd[set][axis], dtd, n, shift));
+	TRY(upload_table(e, e->P[set][axis], P, n, shift));
+	TRY(upload_table(e, e->P1[set][axis], P1, n, shift));
+	TRY(upload_table(e, e->P2[set][axis], P2, n, shift));
+	return ALISB_OK;
+}
+
+extern "C" int alisb_set_inv_eps(alisb_engine *e, const float *cx, const float *cy, const float *cz)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	const float *src[3] = {cx, cy, cz};
+	if (!cx && !cy && !cz) { for (int c=0; c<3; c++) { cudaFree(e->eps[c]); e->eps[c] = 0; } return ALISB_OK; }
+	if (!cx || !cy || !cz) return fail(ALISB_EINVAL, "inv_eps needs all three components");
+	std::vector<float> h(e->elems);
+	for (int c=0; c<3; c++) {
+		if (!e->eps[c]) TRY(dalloc(&e->eps[c], e->elems));
+		int hi[3] = {e->nx, e->ny, e->nz}; hi[c]++;
+		std::fill(h.begin(), h.end(), 0.f);
+		const size_t sb = (size_t)hi[2], sa = (size_t)hi[1]*hi[2];
+		#pragma omp parallel for
+		for (int k=1; k<=hi[2]; k++) for (int b=1; b<=hi[1]; b++) for (int a=1; a<=hi[0]; a++)
+			h[((size_t)k*(e->ny+2) + b)*e->pitch + ALISB_XO + a] = src[c][(size_t)(a-1)*sa + (size_t)(b-1)*sb + (k-1)];
+		CU(cudaMemcpy(e->eps[c], h.data(), e->elems*sizeof(float), cudaMemcpyHostToDevice));
+	}
+	return ALISB_OK;
+}
+
+static int upload_box(float **dst, const float *zfast, const Box &B)
+{
+	const size_t n = bcount(B);
+	TRY(dalloc(dst, n));
+	if (!n) return ALISB_OK;
+	std::vector<float> h(n);
+	to_xfast(zfast, h.data(), B);
+	CU(cudaMemcpy(*dst, h.data(), n*sizeof(float), cudaMemcpyHostToDevice));
+	return ALISB_OK;
+}
+
+extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
+{
+	if (!d || d->nk > ALISB_MAXPOLES || d->nj > d->nk || d->nk < 0) return fail(ALISB_EINVAL, "bad pole counts");
+	DEV(e);
+	DispObj *o = new DispObj();
+	memset(o->fill, 0, sizeof o->fill); memset(o->J, 0, sizeof o->J); memset(o->K, 0, sizeof o->K);
+	o->d = *d;
+	o->full = mkbox(d->box);
+	int32_t u[6] = {std::max(d->box[0],1), std::min(d->box[1],e->nx), std::max(d->box[2],1), std::min(d->box[3],e->ny), std::max(d->box[4],1), std::min(d->box[5],e->nz)};
+	o->upd = mkbox(u);
+	o->cnt = bcount(o->full);
+	for (int c=0; c<3; c++) {
+		TRY(upload_box(&o->fill[c], d->fill[c], o->full));
+		for (int m=0; m<=e->g.complex_field; m++) for (int p=0; p<d->nk; p++) {
+			TRY(dalloc(&o->J[m][p][c], o->cnt));
+			if (p >= d->nj) TRY(dalloc(&o->K[m][p][c], o->cnt));
+		}
+	}
+	e->obj.push_back(o);
+	return ALISB_OK;
+}
+
+extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
+{
+	if (!s || s->set<0 || s->set>1 || s->comp<0 || s->comp>2 || s->m<0 || s->m>e->g.complex_field || !s->waveform) return fail(ALISB_EINVAL, "bad source");
+	DEV(e);
+	SrcObj *o = new SrcObj();
+	o->d = *s; o->B = mkbox(s->box); o->cnt = bcount(o->B); o->dAmp = 0; o->slot = 0;
+	for (int r=0; r<SRC_RING; r++) { o->hvals[r] = 0; o->dvals[r] = 0; o->ev[r] = 0; }
+	if (s->Amplitude) {
+		o->hAmp.resize(o->cnt); to_xfast(s->Amplitude, o->hAmp.data(), o->B);
+		TRY(dalloc(&o->dAmp, o->cnt));
+		CU(cudaMemcpy(o->dAmp, o->hAmp.data(), o->cnt*sizeof(float), cudaMemcpyHostToDevice));
+	}
+	if (s->Phase) {
+		o->hPha.resize(o->cnt); to_xfast(s->Phase, o->hPha.data(), o->B);
+		for (int r=0; r<SRC_RING; r++) {
+			CU(cudaMallocHost((void**)&o->hvals[r], o->cnt*sizeof(float)));
+			TRY(dalloc(&o->dvals[r], o->cnt));
+			CU(cudaEventCreateWithFlags(&o->ev[r], cudaEventDisableTiming));
+		}
+	}
+	o->d.Amplitude = 0; o->d.Phase = 0;
+	e->src[s->set].push_back(o);
+	return ALISB_OK;
+}
+
+extern "C" int alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t)
+{
+	if (!t || !t->aux) return fail(ALISB_EINVAL, "bad tfsf");
+	TfsfObj *o = new TfsfObj();
+	o->d = *t;
+	o->sE.assign(t->strips_E, t->strips_E + t->n_strips_E);
+	o->sH.assign(t->strips_H, t->strips_H + t->n_strips_H);
+	e->tf.push_back(o);
+	return ALISB_OK;
+}
+
+extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops, int n)
+{
+	if (set<0 || set>1 || n<0) return fail(ALISB_EINVAL, "bad copies");
+	e->copies[set].assign(ops, ops + n);
+	return ALISB_OK;
+}
+
+/* ---- one pass ------------------------------------------------------------------------- */
+template <int S>
+static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, bool pml)
+{
+	if (eps) { if (pml) yee_volume<S,true,true><<<grid,block,0,e->stream>>>(p); else yee_volume<S,true,false><<<grid,block,0,e->stream>>>(p); }
+	else     { if (pml) yee_volume<S,false,true><<<grid,block,0,e->stream>>>(p); else yee_volume<S,false,false><<<grid,block,0,e->stream>>>(p); }
+}
+
+/* Region-specialised launches: the interior runs the lean no-PML instantiation, the PML
+ * shell (z slabs, then y slabs of the remaining planes, then the x-edge tiles of what is
+ * left) runs the fused CPML instantiation.  Cells are independent within a pass, so the
+ * split does not change results.                                                        */
+static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
+{
+	L.clear();
+	const int ntile = div_up(e->nx, 128);
+	int lo[3], hi[3];                 /* interior (slab-free) range per axis in array coords */
+	const int n[3] = {e->nx, e->ny, e->nz};
+	for (int ax=0; ax<3; ax++) {
+		lo[ax] = 1; hi[ax] = n[ax];
+		if (e->g.pml[set][ax][0][0] <= e->g.pml[set][ax][0][1]) lo[ax] = e->g.pml[set][ax][0][1] + 1;
+		if (e->g.pml[set][ax][1][0] <= e->g.pml[set][ax][1][1]) hi[ax] = e->g.pml[set][ax][1][0] - 1;
+	}
+	/* (H min-side slabs start at cell 2: cell 1 simply rides along in the slab-side launch) */
+	if (lo[2] > 1)      L.push_back({0, ntile, 1, e->ny, 1, std::min(lo[2]-1, e->nz), true});
+	if (hi[2] < e->nz && hi[2] + 1 >= lo[2]) L.push_back({0, ntile, 1, e->ny, hi[2]+1, e->nz, true});
+	if (lo[2] > hi[2]) return;
+	if (lo[1] > 1)      L.push_back({0, ntile, 1, std::min(lo[1]-1, e->ny), lo[2], hi[2], true});
+	if (hi[1] < e->ny && hi[1] + 1 >= lo[1]) L.push_back({0, ntile, hi[1]+1, e->ny, lo[2], hi[2], true});
+	if (lo[1] > hi[1]) return;
+	/* tiles [t0,t1] are free of x-slab cells */
+	int t0 = 0, t1 = ntile - 1;
+	if (lo[0] > 1)      t0 = std::min((lo[0] - 2)/128 + 1, ntile);   /* tiles holding cells 1..lo-1  */
+	if (hi[0] < e->nx)  t1 = hi[0]/128 - 1;                          /* tiles holding cells hi+1..nx */
+	if (t1 < t0 - 1) t1 = t0 - 1;
+	if (t0 > 0)         L.push_back({0, t0, lo[1], hi[1], lo[2], hi[2], true});
+	if (t1 < ntile - 1) L.push_back({t1 + 1, ntile - (t1 + 1), lo[1], hi[1], lo[2], hi[2], true});
+	if (t0 <= t1)       L.push_back({t0, t1 - t0 + 1, lo[1], hi[1], lo[2], hi[2], false});
+}
+
+static int launch_volume(alisb_engine *e, int set, int m)
+{
+	VolParams p;
+	memset(&p, 0, sizeof p);
+	for (int c=0; c<3; c++) {
+		p.F[c] = e->F[set][m][c]; p.G[c] = e->F[1-set][m][c];
+		p.C[c] = set == ALISB_SET_E ? e->eps[c] : 0;
+		p.dtd[c] = e->dtd[set][c]; p.P[c] = e->P[set][c]; p.P1[c] = e->P1[set][c]; p.P2[c] = e->P2[set][c];
+		for (int sd=0; sd<2; sd++) {
+			p.slab[c][sd][0] = e->g.pml[set][c][sd][0]; p.slab[c][sd][1] = e->g.pml[set][c][sd][1];
+			for (int w=0; w<2; w++) p.psi[c][sd][w] = e->psi[set][m][c][sd][w];
+		}
+	}
+	for (int sd=0; sd<2; sd++) { p.xbase[sd] = e->xbase[set][sd]; p.xpitch[sd] = e->xpitch[set][sd]; }
+	p.nx = e->nx; p.ny = e->ny; p.nz = e->nz; p.pitch = e->pitch; p.plane = e->plane;
+	const bool eps = set == ALISB_SET_E && e->eps[0] && e->eps[1] && e->eps[2];
+	if (e->plan[set].empty()) plan_volume(e, set, e->plan[set]);
+
+	int sub = -1;
+	for (const SubBox &sb : e->plan[set]) {
+		sub++;
+		cudaEvent_t e1 = 0;
+		if (e->profiling) {
+			if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
+			e->prof.push_back({e->ev_used, set, sub});
+			CU(cudaEventRecord(e->ev_pool[e->ev_used++], e->stream));
+			e1 = e->ev_pool[e->ev_used++];
+		}
+		p.tile0 = sb.tile0; p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
+		const int nzs = sb.c1 - sb.c0 + 1, gy = div_up(sb.b1 - sb.b0 + 1, 8);
+		const long tiles = (long)sb.ntiles*gy;
+		long want = (16L*e->resident_ctas + tiles - 1)/tiles;      /* >= ~16 waves of CTAs ...       */
+		long maxc = std::max(1, nzs/32);                           /* ... but chunks of >= 32 planes */
+		int nchunks = (int)std::max(1L, std::min(want, maxc));
+		p.cchunk = div_up(nzs, nchunks);
+		nchunks = div_up(nzs, p.cchunk);
+		dim3 grid(sb.ntiles, gy, nchunks), block(32, 8, 1);
+		if (set == ALISB_SET_E) launch_volume_t<1>(e, p, grid, block, eps, sb.pml);
+		else                    launch_volume_t<-1>(e, p, grid, block, false, sb.pml);
+		e->launches++;
+		if (e->profiling) CU(cudaEventRecord(e1, e->stream));
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+static void fill_ade(alisb_engine *e, DispObj *o, int m, AdeParams &p)
+{
+	memset(&p, 0, sizeof p);
+	for (int c=0; c<3; c++) {
+		p.F[c] = e->F[ALISB_SET_E][m][c]; p.fill[c] = o->fill[c]; p.a[c] = o->d.a[c];
+		for (int s=0; s<ALISB_MAXPOLES; s++) { p.J[s][c] = o->J[m][s][c]; p.K[s][c] = o->K[m][s][c]; }
+	}
+	memcpy(p.JJ, o->d.JJ, sizeof p.JJ); memcpy(p.JK, o->d.JK, sizeof p.JK); memcpy(p.JE, o->d.JE, sizeof p.JE);
+	memcpy(p.KJ, o->d.KJ, sizeof p.KJ); memcpy(p.KK, o->d.KK, sizeof p.KK); memcpy(p.KE, o->d.KE, sizeof p.KE);
+	p.nj = o->d.nj; p.nk = o->d.nk; p.lossy = (o->d.a[0] || o->d.a[1] || o->d.a[2]) ? 1 : 0;
+	p.full = o->full; p.upd = o->upd; p.ny = e->ny; p.pitch = e->pitch;
+}
+
+static int ade_pre(alisb_engine *e, int m)
+{
+	AdeParams p;
+	for (DispObj *o : e->obj) {
+		fill_ade(e, o, m, p);
+		const size_t n = bcount(o->upd);
+		if (!n || !p.lossy) continue;
+		ade_loss<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
+	}
+	for (DispObj *o : e->obj) {
+		fill_ade(e, o, m, p);
+		const size_t n = bcount(o->upd);
+		if (!n || !p.nk) continue;
+		ade_subtract<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+static int ade_post(alisb_engine *e, int m)
+{
+	AdeParams p;
+	for (DispObj *o : e->obj) {
+		fill_ade(e, o, m, p);
+		const size_t n = bcount(o->upd);
+		if (!n || !p.nk) continue;
+		ade_currents<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+static int apply_sources(alisb_engine *e, int set, float t)
+{
+	for (SrcObj *s : e->src[set]) {
+		if (!(e->step < s->d.n_active) || !s->cnt) continue;
+		float *F = e->F[set][s->d.m][s->d.comp];
+		if (!s->hPha.empty()) {
+			const int r = s->slot; s->slot = (s->slot + 1) % SRC_RING;
+			CU(cudaEventSynchronize(s->ev[r]));
+			float *h = s->hvals[r];
+			for (size_t q=0; q<s->cnt; q++)
+				h[q] = (s->hAmp.empty() ? s->d.amplitude : s->hAmp[q]) * s->d.waveform(s->d.user, t, s->hPha[q]);
+			CU(cudaMemcpyAsync(s->dvals[r], h, s->cnt*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+			source_add<<<div_up(s->cnt, 256), 256, 0, e->stream>>>(F, s->B, e->ny, e->pitch, s->dvals[r], 0, 0.f, 0.f);
+			CU(cudaEventRecord(s->ev[r], e->stream));
+		} else {
+			const float f = s->d.waveform(s->d.user, t, s->d.phase);
+			source_add<<<div_up(s->cnt, 256), 256, 0, e->stream>>>(F, s->B, e->ny, e->pitch, 0, s->dAmp, s->d.amplitude, f);
+		}
+		e->launches++;
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+static int apply_tfsf(alisb_engine *e, int set)
+{
+	for (TfsfObj *t : e->tf) {
+		alisb_engine *x = t->d.aux;
+		if (x->stream != e->stream && !x->own_stream) return fail(ALISB_ESTATE, "aux engine on a foreign stream");
+		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; }
+		TRY(set == ALISB_SET_E ? alisb_step_E(x) : alisb_step_H(x));
+		const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
+		for (int m=0; m<=e->g.complex_field; m++) for (const alisb_strip &s : L) {
+			Box B = mkbox(s.box);
+			const size_t n = bcount(B);
+			if (!n) continue;
+			const float *C = s.use_eps ? e->eps[s.comp] : 0;
+			tfsf_strip<<<div_up(n, 128), 128, 0, e->stream>>>(e->F[set][m][s.comp], x->F[1-set][m][s.aux_comp], C, s.coef, B, e->ny, e->pitch,
+				x->ny, x->pitch, s.alt[0] + t->d.offset[0], s.alt[1] + t->d.offset[1], s.alt[2] + t->d.offset[2],
+				t->d.clamp[1-set][s.aux_comp][0], t->d.clamp[1-set][s.aux_comp][1]);
+			e->launches++;
+		}
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+static int apply_copies(alisb_engine *e, int set)
+{
+	for (const alisb_copy &k : e->copies[set]) {
+		Box B = mkbox(k.box);
+		const size_t n = bcount(B);
+		if (!n) continue;
+		float *F = e->F[k.set][0][k.comp], *G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
+		copy_plane<<<div_up(n, 256), 256, 0, e->stream>>>(F, G, k.cosk, k.sink, B, e->ny, e->pitch, k.alt[0], k.alt[1], k.alt[2]);
+		e->launches++;
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+extern "C" int alisb_step_E(alisb_engine *e)
+{
+	DEV(e);
+	for (int m=0; m<=e->g.complex_field; m++) {
+		if (!e->obj.empty()) TRY(ade_pre(e, m));
+		TRY(launch_volume(e, ALISB_SET_E, m));
+	}
+	TRY(apply_tfsf(e, ALISB_SET_E));
+	TRY(apply_sources(e, ALISB_SET_E, e->tH));
+	TRY(apply_copies(e, ALISB_SET_E));
+	e->t = e->tE = ++e->step * e->g.dt;                 /* update.c:298 */
+	return ALISB_OK;
+}
+
+extern "C" int alisb_step_H(alisb_engine *e)
+{
+	DEV(e);
+	for (int m=0; m<=e->g.complex_field; m++) {
+		TRY(launch_volume(e, ALISB_SET_H, m));
+		if (!e->obj.empty()) TRY(ade_post(e, m));
+	}
+	TRY(apply_tfsf(e, ALISB_SET_H));
+	TRY(apply_sources(e, ALISB_SET_H, e->tE));
+	TRY(apply_copies(e, ALISB_SET_H));
+	e->t = e->tH = e->tE + 0.5 * e->g.dt;               /* update.c:340 */
+	return ALISB_OK;
+}
+
+extern "C" int alisb_run(alisb_engine *e, int steps)
+{
+	e->ev_used = 0; e->prof.clear();
+	for (int s=0; s<steps; s++) { TRY(alisb_step_E(e)); TRY(alisb_step_H(e)); }
+	return ALISB_OK;
+}
+
+extern "C" int alisb_synchronize(alisb_engine *e) { DEV(e); CU(cudaStreamSynchronize(e->stream)); return ALISB_OK; }
+extern "C" int alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH) { if (n) *n = e->step; if (t) *t = e->t; if (tE) *tE = e->tE; if (tH) *tH = e->tH; return ALISB_OK; }
+extern "C" int alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH) { e->step = n; e->t = t; e->tE = tE; e->tH = tH; return ALISB_OK; }
+
+extern "C" int alisb_reset_fields(alisb_engine *e)
+{
+	DEV(e);
+	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) {
+		for (int c=0; c<3; c++) CU(cudaMemsetAsync(e->F[s][m][c], 0, e->elems*sizeof(float), e->stream));
+		for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++)
+			if (e->psi[s][m][ax][sd][w]) CU(cudaMemsetAsync(e->psi[s][m][ax][sd][w], 0, e->psi_elems[s][ax][sd]*sizeof(float), e->stream));
+	}
+	for (DispObj *o : e->obj) for (int m=0; m<=e->g.complex_field; m++) for (int p=0; p<o->d.nk; p++) for (int c=0; c<3; c++) {
+		CU(cudaMemsetAsync(o->J[m][p][c], 0, o->cnt*sizeof(float), e->stream));
+		if (o->K[m][p][c]) CU(cudaMemsetAsync(o->K[m][p][c], 0, o->cnt*sizeof(float), e->stream));
+	}
+	return ALISB_OK;
+}
+
+/* ---- data access ------------------------------------------------------------------------- */
+static int need_scratch(alisb_engine *e, size_t n)
+{
+	if (n <= e->scratch_elems) return ALISB_OK;
+	cudaFree(e->scratch); e->scratch = 0; e->scratch_elems = 0;
+	TRY(dalloc(&e->scratch, n));
+	e->scratch_elems = n;
+	return ALISB_OK;
+}
+
+/* resolves to a padded full-grid style array (ny2 rows per plane, row pitch) or a dense box */
+struct ArrRef { float *p; int kind; int ny2; int pitch; int shift; Box dense; };
+static int resolve(alisb_engine *e, int arr, const int32_t ids[6], ArrRef &r)
+{
+	memset(&r, 0, sizeof r);
+	switch (arr) {
+	case ALISB_ARR_FIELD:
+		if (ids[0]<0||ids[0]>1||ids[1]<0||ids[1]>2||ids[2]<0||ids[2]>e->g.complex_field) break;
+		r.p = e->F[ids[0]][ids[2]][ids[1]]; r.kind = 0; return ALISB_OK;
+	case ALISB_ARR_INVEPS:
+		if (ids[0]<0||ids[0]>2||!e->eps[ids[0]]) break;
+		r.p = e->eps[ids[0]]; r.kind = 0; return ALISB_OK;
+	case ALISB_ARR_PSI: {
+		if (ids[0]<0||ids[0]>1||ids[1]<0||ids[1]>e->g.complex_field||ids[2]<0||ids[2]>2||ids[3]<0||ids[3]>1||ids[4]<0||ids[4]>1) break;
+		const int s=ids[0], m=ids[1], ax=ids[2], sd=ids[3];
+		if (!e->psi[s][m][ax][sd][ids[4]]) break;
+		r.p = e->psi[s][m][ax][sd][ids[4]]; r.kind = 1 + ax;
+		r.dense.a0 = e->xbase[s][sd]; r.dense.na = e->xpitch[s][sd];
+		r.dense.b0 = e->g.pml[s][1][sd][0]; r.dense.nb = e->g.pml[s][1][sd][1] - e->g.pml[s][1][sd][0] + 1;
+		r.dense.c0 = e->g.pml[s][2][sd][0]; r.dense.nc = e->g.pml[s][2][sd][1] - e->g.pml[s][2][sd][0] + 1;
+		return ALISB_OK; }
+	case ALISB_ARR_ADE_J: case ALISB_ARR_ADE_K: {
+		if (ids[0]<0||ids[0]>e->g.complex_field||ids[1]<0||ids[1]>=(int)e->obj.size()||ids[2]<0||ids[2]>=e->obj[ids[1]]->d.nk||ids[3]<0||ids[3]>2) break;
+		DispObj *o = e->obj[ids[1]];
+		r.p = arr==ALISB_ARR_ADE_J ? o->J[ids[0]][ids[2]][ids[3]] : o->K[ids[0]][ids[2]][ids[3]];
+		if (!r.p) break;
+		r.kind = 4; r.dense = o->full; return ALISB_OK; }
+	case ALISB_ARR_ADE_FILL:
+		if (ids[0]<0||ids[0]>=(int)e->obj.size()||ids[1]<0||ids[1]>2) break;
+		r.p = e->obj[ids[0]]->fill[ids[1]]; r.kind = 4; r.dense = e->obj[ids[0]]->full; return ALISB_OK;
+	}
+	return fail(ALISB_EINVAL, "bad array id");
+}
+
+/* element offset of (a,b,c) in the resolved array, or -1 if outside */
+static long long arr_offset(alisb_engine *e, const ArrRef &r, int a, int b, int c)
+{
+	switch (r.kind) {
+	case 0: if (a<0||a>e->nx+1||b<0||b>e->ny+1||c<0||c>e->nz+1) return -1;
+	        return ((long long)c*(e->ny+2) + b)*e->pitch + ALISB_XO + a;
+	case 1: if (a<r.dense.a0||a>=r.dense.a0+r.dense.na||b<0||b>e->ny+1||c<0||c>e->nz+1) return -1;
+	        return ((long long)c*(e->ny+2) + b)*r.dense.na + (a - r.dense.a0);
+	case 2: if (a<0||a>e->nx+1||b<r.dense.b0||b>=r.dense.b0+r.dense.nb||c<0||c>e->nz+1) return -1;
+	        return ((long long)c*r.dense.nb + (b - r.dense.b0))*e->pitch + ALISB_XO + a;
+	case 3: if (a<0||a>e->nx+1||b<0||b>e->ny+1||c<r.dense.c0||c>=r.dense.c0+r.dense.nc) return -1;
+	        return ((long long)(c - r.dense.c0)*(e->ny+2) + b)*e->pitch + ALISB_XO + a;
+	case 4: if (a<r.dense.a0||a>=r.dense.a0+r.dense.na||b<r.dense.b0||b>=r.dense.b0+r.dense.nb||c<r.dense.c0||c>=r.dense.c0+r.dense.nc) return -1;
+	        return ((long long)(c - r.dense.c0)*r.dense.nb + (b - r.dense.b0))*r.dense.na + (a - r.dense.a0);
+	}
+	return -1;
+}
+
+static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
+{
+	DEV(e);
+	ArrRef r;
+	TRY(resolve(e, arr, ids, r));
+	Box B = mkbox(box);
+	const size_t n = bcount(B);
+	if (!n) return ALISB_OK;
+	if (arr_offset(e, r, box[0], box[2], box[4]) < 0 || arr_offset(e, r, box[1], box[3], box[5]) < 0) return fail(ALISB_EINVAL, "box outside array");
+	std::vector<float> h(n);
+	if (r.kind == 0) {
+		TRY(need_scratch(e, n));
+		if (write) {
+			to_xfast(host, h.data(), B);
+			CU(cudaMemcpyAsync(e->scratch, h.data(), n*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+			box_scatter<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, e->ny, e->pitch);
+			CU(cudaStreamSynchronize(e->stream));
+		} else {
+			box_gather<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, e->ny, e->pitch);
+			CU(cudaMemcpyAsync(h.data(), e->scratch, n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+			CU(cudaStreamSynchronize(e->stream));
+			to_zfast(h.data(), host, B);
+		}
+		e->launches++;
+		return ALISB_OK;
+	}
+	/* small auxiliary arrays: row-wise copies */
+	CU(cudaStreamSynchronize(e->stream));
+	for (int c=0; c<B.nc; c++) for (int b=0; b<B.nb; b++) {
+		const long long off = arr_offset(e, r, B.a0, B.b0 + b, B.c0 + c);
+		float *row = &h[((size_t)c*B.nb + b)*B.na];
+		if (write) { for (int a=0; a<B.na; a++) row[a] = host[((size_t)a*B.nb + b)*B.nc + c]; CU(cudaMemcpy(r.p + off, row, B.na*sizeof(float), cudaMemcpyHostToDevice)); }
+		else CU(cudaMemcpy(row, r.p + off, B.na*sizeof(float), cudaMemcpyDeviceToHost));
+	}
+	if (!write) to_zfast(h.data(), host, B);
+	return ALISB_OK;
+}
+extern "C" int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, false); }
+extern "C" int alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(e, arr, ids, box, (float*)host, true); }
+
+/* ---- halo: planes are contiguous in this layout, hand out pointers into the arrays -------- */
+extern "C" int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)
+{
+	if (set<0||set>1||m<0||m>e->g.complex_field||comp<0||comp>1) return fail(ALISB_EINVAL, "bad halo id");
+	float *F = e->F[set][m][comp];
+	if (send_ptr) *send_ptr = F + (set == ALISB_SET_E ? (size_t)e->nz*e->plane : e->plane);
+	if (recv_ptr) *recv_ptr = F + (set == ALISB_SET_E ? 0 : (size_t)(e->nz + 1)*e->plane);
+	if (bytes) *bytes = e->plane*sizeof(float);
+	return ALISB_OK;
+}
+extern "C" int alisb_halo_pack(alisb_engine *e, int set) { (void)e; (void)set; return ALISB_OK; }
+extern "C" int alisb_halo_unpack(alisb_engine *e, int set) { (void)e; (void)set; return ALISB_OK; }
+
+/* ---- phasers -------------------------------------------------------------------------------- */
+extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int face_mask, int nfreq, alisb_phaser **out)
+{
+	if (nfreq < 1 || !out) return fail(ALISB_EINVAL, "nfreq");
+	DEV(e);
+	alisb_phaser *p = new alisb_phaser();
+	p->e = e; memcpy(p->box, box, sizeof p->box); p->mask = face_mask; p->nfreq = nfreq; p->ev_pending = false;
+	for (int f=0; f<6; f++) {
+		p->acc[f] = 0; p->cells[f] = 0;
+		if (!(face_mask & (1<<f))) continue;
+		int32_t fb[6]; memcpy(fb, box, sizeof fb);
+		const int ax = f/2, sd = f%2;
+		fb[2*ax] = fb[2*ax+1] = sd ? box[2*ax+1] : box[2*ax];
+		p->face[f] = mkbox(fb); p->cells[f] = bcount(p->face[f]);
+		float *a = 0; TRY(dalloc(&a, p->cells[f]*8*(size_t)nfreq)); p->acc[f] = (float2*)a;
+	}
+	for (int k=0; k<2; k++) {
+		float *d = 0; TRY(dalloc(&d, 2*(size_t)nfreq)); p->dexp[k] = (float2*)d;
+		CU(cudaMallocHost((void**)&p->hexp[k], 2*(size_t)nfreq*sizeof(float)));
+	}
+	CU(cudaEventCreateWithFlags(&p->ev, cudaEventDisableTiming));
+	*out = p;
+	return ALISB_OK;
+}
+
+extern "C" void alisb_phaser_destroy(alisb_phaser *p)
+{
+	if (!p) return;
+	cudaSetDevice(p->e->g.device);
+	cudaStreamSynchronize(p->e->stream);
+	for (int f=0; f<6; f++) cudaFree(p->acc[f]);
+	for (int k=0; k<2; k++) { cudaFree(p->dexp[k]); cudaFreeHost(p->hexp[k]); }
+	cudaEventDestroy(p->ev);
+	delete p;
+}
+
+extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const float *expH)
+{
+	alisb_engine *e = p->e;
+	DEV(e);
+	if (p->ev_pending) CU(cudaEventSynchronize(p->ev));       /* pinned staging buffers free again */
+	memcpy(p->hexp[0], expE, 2*(size_t)p->nfreq*sizeof(float));
+	memcpy(p->hexp[1], expH, 2*(size_t)p->nfreq*sizeof(float));
+	for (int k=0; k<2; k++) CU(cudaMemcpyAsync(p->dexp[k], p->hexp[k], 2*(size_t)p->nfreq*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	CU(cudaEventRecord(p->ev, e->stream)); p->ev_pending = true;
+	for (int f=0; f<6; f++) if (p->acc[f]) {
+		const int ax = f/2, c1 = (ax+1)%3, c2 = (ax+2)%3;
+		const size_t hstep = ax == 0 ? 1 : ax == 1 ? (size_t)e->pitch : e->plane;
+		phaser_face<<<div_up(p->cells[f], 128), 128, 0, e->stream>>>(p->acc[f], e->F[0][0][c1], e->F[0][0][c2], e->F[1][0][c1], e->F[1][0][c2],
+			p->face[f], e->ny, e->pitch, hstep, p->nfreq, p->dexp[0], p->dexp[1]);
+		e->launches++;
+	}
+	CU(cudaGetLastError());
+	return ALISB_OK;
+}
+
+extern "C" int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *host)
+{
+	if (face<0||face>5||which<0||which>3||freq<0||freq>=p->nfreq||!p->acc[face]) return fail(ALISB_EINVAL, "bad phaser id");
+	alisb_engine *e = p->e;
+	DEV(e);
+	const size_t n = p->cells[face];
+	std::vector<float2> h(n);
+	CU(cudaStreamSynchronize(e->stream));
+	CU(cudaMemcpy(h.data(), p->acc[face] + ((size_t)freq*4 + which)*n, n*sizeof(float2), cudaMemcpyDeviceToHost));
+	const Box &B = p->face[face];
+	float2 *o = (float2*)host;
+	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
+		o[((size_t)a*B.nb + b)*B.nc + c] = h[((size_t)c*B.nb + b)*B.na + a];
+	return ALISB_OK;
+}
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+extern "C" uint64_t alisb_launch_count(alisb_engine *e) { return e->launches; }
+extern "C" int alisb_set_profiling(alisb_engine *e, int on) { e->profiling = on != 0; e->ev_used = 0; e->prof.clear(); return ALISB_OK; }
+extern "C" int alisb_last_run_kernel_ms(alisb_engine *e, float *ms_total, int *launches)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	float tot = 0; int n = 0;
+	for (const ProfRec &r : e->prof) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev+1])); tot += ms; n++; }
+	if (ms_total) *ms_total = tot;
+	if (launches) *launches = n;
+	return ALISB_OK;
+}
+
+/* the dominant kernel = the volume sub-launch covering the most cells (the interior, no-PML
+ * instantiation whenever the grid has an interior); bytes per launch = 36 B per cell
+ * (read 3 F + 3 G, write 3 F: SURVEY 8d) for that launch's cells.                          */
+extern "C" int alisb_profile_dominant(alisb_engine *e, float *ms_total, int *launches, double *bytes_per_launch)
+{
+	DEV(e);
+	CU(cudaStreamSynchronize(e->stream));
+	int best[2] = {-1, -1}; double cells[2] = {0, 0};
+	for (int s=0; s<2; s++) for (size_t q=0; q<e->plan[s].size(); q++) {
+		const SubBox &b = e->plan[s][q];
+		const int a0 = 1 + 128*b.tile0, a1 = std::min(e->nx, 128*(b.tile0 + b.ntiles));
+		const double c = (double)(a1 - a0 + 1)*(b.b1 - b.b0 + 1)*(b.c1 - b.c0 + 1);
+		if (c > cells[s]) { cells[s] = c; best[s] = (int)q; }
+	}
+	float tot = 0; int n = 0;
+	for (const ProfRec &r : e->prof) if (r.sub == best[r.set]) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev+1])); tot += ms; n++; }
+	if (ms_total) *ms_total = tot;
+	if (launches) *launches = n;
+	if (bytes_per_launch) *bytes_per_launch = 36.0*0.5*(cells[0] + cells[1]);
+	return ALISB_OK;
+}

@@ -1,0 +1,401 @@
+/*
+ * kernels.cuh -- hand-written sm_100a kernels of the FDTD time-stepping path.
+ *
+ * Device layout (DESIGN.md "Data layout in HBM"): every scalar array is
+ * [c][b][pitch] with x (a) fastest and z (c) slowest; element (a,b,c) lives at
+ *     ((size_t)c*(ny+2) + b)*pitch + XO + a ,   XO = 31,
+ * so the first updated cell a=1 of every row is 128-byte aligned and one warp reading
+ * float4 per lane covers exactly four 128-byte lines.  z-planes are contiguous, which
+ * makes the multi-GPU halo planes, k-faces and z-phasor faces plain 2-D blocks.
+ *
+ * Arithmetic: fp32, no FMA contraction (the translation unit is compiled with
+ * -fmad=false), IEEE division, and the reference's expression order, so that results are
+ * bit-identical to reference update.c (see the per-kernel citations).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ALISB_XO 31               /* array coordinate a sits at row offset XO + a */
+
+struct VolParams {
+	float       *F[3];            /* field set being updated (E or H), components x,y,z */
+	const float *G[3];            /* the other field set                                */
+	const float *C[3];            /* inverse permittivity (E pass, EPS variant)         */
+	const float *dtd[3];          /* dtdx (stored shifted by XO), dtdy, dtdz            */
+	const float *P[3], *P1[3], *P2[3];   /* CPML tables per axis (x ones shifted by XO) */
+	float       *psi[3][2][2];    /* [axis][side][which]                                */
+	int slab[3][2][2];            /* [axis][side]{first,last} in array coordinates      */
+	int xbase[2], xpitch[2];      /* x-slab psi arrays: slot = a - xbase, row pitch      */
+	int nx, ny, nz, pitch;
+	int tile0;                    /* first 128-cell x tile of this launch                */
+	int b_first, b_last;          /* rows updated by this launch                        */
+	int c_first, c_last;          /* planes updated by this launch                      */
+	int cchunk;                   /* planes per z-chunk (grid.z chunks)                  */
+	size_t plane;                 /* (ny+2)*pitch                                        */
+};
+
+static __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4*>(p); }
+static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+/*
+ * Fused Yee curl + CPML volume kernel: reference updateF (update.c:87-125) without the
+ * ADE pre-pass, i.e. the curl of update.c:109-118 followed by the six psi slabs of
+ * update.c:48-84,119-124 applied in the reference's order, in ONE pass over memory.
+ *
+ *   S = +1 : E pass (forward differences of H),  S = -1 : H pass (backward differences of E)
+ *
+ * Thread mapping: one warp = one x-row segment of 128 cells (float4 per lane), blockDim.y
+ * rows per CTA, and the CTA marches along z (2.5-D blocking) in direction -S so that the
+ * plane c+S needed by the z-differences is the one carried in registers from the previous
+ * iteration.  The y-neighbour row is fetched with a second coalesced load that hits L1
+ * (the warp above/below in the same CTA loads the same line in the same iteration), the
+ * x-neighbour comes from a warp shuffle.
+ */
+template <int S, bool EPS, bool PML>
+__global__ void __launch_bounds__(256)
+yee_volume(const __grid_constant__ VolParams p)
+{
+	const int lane = threadIdx.x;
+	const int a0 = 1 + 4*((blockIdx.x + p.tile0)*32 + lane);
+	const int b  = p.b_first + blockIdx.y*blockDim.y + threadIdx.y;
+	if (b > p.b_last) return;                               /* whole warp leaves */
+	const bool act = a0 <= p.nx;                            /* owns at least one updated cell      */
+	const bool ldg = a0 <= p.nx + 1;                        /* G quad holds data someone needs (ghost a=nx+1) */
+	const bool full = a0 + 3 <= p.nx;
+
+	const int cf = p.c_first + blockIdx.z*p.cchunk;
+	const int cl = min(cf + p.cchunk - 1, p.c_last);
+	if (cf > cl) return;
+	const int nsteps = cl - cf + 1;
+	int c = (S > 0) ? cl : cf;
+
+	const size_t row = (size_t)b*p.pitch + ALISB_XO + a0;    /* offset inside a plane */
+	const ptrdiff_t yn = (ptrdiff_t)S*p.pitch;               /* to row b+S            */
+
+	float *__restrict__ F0 = p.F[0], *__restrict__ F1 = p.F[1], *__restrict__ F2 = p.F[2];
+	const float *__restrict__ G0 = p.G[0], *__restrict__ G1 = p.G[1], *__restrict__ G2 = p.G[2];
+
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4 dx4 = act ? ld4(p.dtd[0] + ALISB_XO + a0) : zero4;
+	const float  dy  = __ldg(p.dtd[1] + b);
+
+	/* loop-invariant slab membership */
+	int ys = -1, xs = -1;
+	float yP = 0.f, yP1 = 0.f, yP2 = 0.f;
+	float4 xP = zero4, xP1 = zero4, xP2 = zero4;
+	unsigned xmask = 0;
+	if (PML) {
+		if (b >= p.slab[1][0][0] && b <= p.slab[1][0][1]) ys = 0;
+		else if (b >= p.slab[1][1][0] && b <= p.slab[1][1][1]) ys = 1;
+		if (ys >= 0) { yP = __ldg(p.P[1] + b); yP1 = __ldg(p.P1[1] + b); yP2 = __ldg(p.P2[1] + b); }
+		if (act) {
+			if (a0 + 3 >= p.slab[0][0][0] && a0 <= p.slab[0][0][1]) xs = 0;
+			else if (a0 + 3 >= p.slab[0][1][0] && a0 <= p.slab[0][1][1]) xs = 1;
+			if (xs >= 0) {
+				#pragma unroll
+				for (int e = 0; e < 4; e++) if (a0 + e >= p.slab[0][xs][0] && a0 + e <= p.slab[0][xs][1]) xmask |= 1u << e;
+				xP = ld4(p.P[0] + ALISB_XO + a0); xP1 = ld4(p.P1[0] + ALISB_XO + a0); xP2 = ld4(p.P2[0] + ALISB_XO + a0);
+			}
+		}
+	}
+
+	/* plane c+S: carried */
+	float4 gxp = zero4, gyp = zero4;
+	if (ldg) {
+		const size_t o = (size_t)(c + S)*p.plane + row;
+		gxp = ld4(G0 + o); gyp = ld4(G1 + o);
+	}
+
+	for (int it = 0; it < nsteps; ++it, c -= S) {
+		const size_t o = (size_t)c*p.plane + row;
+		float4 fx = zero4, fy = zero4, fz = zero4, gx = zero4, gy = zero4, gz = zero4, gxn = zero4, gzn = zero4;
+		float4 cx = zero4, cy = zero4, cz = zero4;
+		if (ldg) { gx = ld4(G0 + o); gy = ld4(G1 + o); gz = ld4(G2 + o); }
+		if (act) {
+			gxn = ld4(G0 + o + yn); gzn = ld4(G2 + o + yn);
+			fx = ld4(F0 + o); fy = ld4(F1 + o); fz = ld4(F2 + o);
+			if (EPS) { cx = ld4(p.C[0] + o); cy = ld4(p.C[1] + o); cz = ld4(p.C[2] + o); }
+		}
+		/* x-neighbour element (a0+4 for S=+1, a0-1 for S=-1) from the adjacent lane */
+		float gye, gze;
+		if (S > 0) {
+			gye = __shfl_down_sync(0xffffffffu, gy.x, 1);
+			gze = __shfl_down_sync(0xffffffffu, gz.x, 1);
+			if (lane == 31 && act) { gye = G1[o + 4]; gze = G2[o + 4]; }
+		} else {
+			gye = __shfl_up_sync(0xffffffffu, gy.w, 1);
+			gze = __shfl_up_sync(0xffffffffu, gz.w, 1);
+			if (lane == 0 && act) { gye = *(G1 + o - 1); gze = *(G2 + o - 1); }
+		}
+		const float dz = __ldg(p.dtd[2] + c);
+
+		/* 5-wide windows along x: self(e) and neighbour(e) = element a+S */
+		float gy5[5], gz5[5];
+		if (S > 0) { gy5[0]=gy.x; gy5[1]=gy.y; gy5[2]=gy.z; gy5[3]=gy.w; gy5[4]=gye;  gz5[0]=gz.x; gz5[1]=gz.y; gz5[2]=gz.z; gz5[3]=gz.w; gz5[4]=gze; }
+		else       { gy5[0]=gye;  gy5[1]=gy.x; gy5[2]=gy.y; gy5[3]=gy.z; gy5[4]=gy.w; gz5[0]=gze;  gz5[1]=gz.x; gz5[2]=gz.y; gz5[3]=gz.z; gz5[4]=gz.w; }
+		constexpr int SELF = (S > 0) ? 0 : 1, NBR = (S > 0) ? 1 : 0;
+
+		float Fx[4] = {fx.x, fx.y, fx.z, fx.w}, Fy[4] = {fy.x, fy.y, fy.z, fy.w}, Fz[4] = {fz.x, fz.y, fz.z, fz.w};
+		const float Gx[4] = {gx.x, gx.y, gx.z, gx.w}, Gy[4] = {gy.x, gy.y, gy.z, gy.w}, Gz[4] = {gz.x, gz.y, gz.z, gz.w};
+		const float Gxn[4] = {gxn.x, gxn.y, gxn.z, gxn.w}, Gzn[4] = {gzn.x, gzn.y, gzn.z, gzn.w};
+		const float Gxp[4] = {gxp.x, gxp.y, gxp.z, gxp.w}, Gyp[4] = {gyp.x, gyp.y, gyp.z, gyp.w};
+		const float Dx[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
+		const float Cx[4] = {cx.x, cx.y, cx.z, cx.w}, Cy[4] = {cy.x, cy.y, cy.z, cy.w}, Cz[4] = {cz.x, cz.y, cz.z, cz.w};
+
+		/* update.c:110-112 / :115-117 */
+		#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			const float ux = dz*(Gy[e] - Gyp[e]) + dy*(Gzn[e] - Gz[e]);
+			const float uy = Dx[e]*(gz5[e+SELF] - gz5[e+NBR]) + dz*(Gxp[e] - Gx[e]);
+			const float uz = dy*(Gx[e] - Gxn[e]) + Dx[e]*(gy5[e+NBR] - gy5[e+SELF]);
+			if (EPS) { Fx[e] += ux*Cx[e]; Fy[e] += uy*Cy[e]; Fz[e] += uz*Cz[e]; }
+			else     { Fx[e] += ux;       Fy[e] += uy;       Fz[e] += uz; }
+		}
+
+		if (PML) {
+			int zs = -1;
+			if (c >= p.slab[2][0][0] && c <= p.slab[2][0][1]) zs = 0;
+			else if (c >= p.slab[2][1][0] && c <= p.slab[2][1][1]) zs = 1;
+			if (act && (xs >= 0 || ys >= 0 || zs >= 0)) {
+				/* psi contributions; slab order x-min,y-min,z-min,x-max,y-max,z-max (update.c:119-124) */
+				float xq0[4] = {0,0,0,0}, xq1[4] = {0,0,0,0};   /* x slab: psi0 -> Fy, psi1 -> Fz */
+				float yq0[4] = {0,0,0,0}, yq1[4] = {0,0,0,0};   /* y slab: psi0 -> Fz, psi1 -> Fx */
+				float zq0[4] = {0,0,0,0}, zq1[4] = {0,0,0,0};   /* z slab: psi0 -> Fx, psi1 -> Fy */
+				if (xs >= 0) {
+					const size_t po = ((size_t)c*(p.ny + 2) + b)*p.xpitch[xs] + (a0 - p.xbase[xs]);
+					float *q0p = p.psi[0][xs][0] + po, *q1p = p.psi[0][xs][1] + po;
+					float4 q0 = ld4(q0p), q1 = ld4(q1p);
+					float v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
+					const float Pq[4] = {xP.x, xP.y, xP.z, xP.w}, Pa[4] = {xP1.x, xP1.y, xP1.z, xP1.w}, Pb[4] = {xP2.x, xP2.y, xP2.z, xP2.w};
+					#pragma unroll
+					for (int e = 0; e < 4; e++) if (xmask & (1u << e)) {
+						v0[e] = Pq[e]*v0[e] + Pa[e]*(gz5[e+SELF] - gz5[e+NBR]);   /* update.c:51 */
+						v1[e] = Pq[e]*v1[e] + Pb[e]*(gy5[e+SELF] - gy5[e+NBR]);   /* update.c:52 */
+						xq0[e] = v0[e]; xq1[e] = v1[e];
+					}
+					st4(q0p, make_float4(v0[0], v0[1], v0[2], v0[3]));
+					st4(q1p, make_float4(v1[0], v1[1], v1[2], v1[3]));
+				}
+				if (ys >= 0) {
+					const int nys = p.slab[1][ys][1] - p.slab[1][ys][0] + 1;
+					const size_t po = ((size_t)c*nys + (b - p.slab[1][ys][0]))*p.pitch + ALISB_XO + a0;
+					float *q0p = p.psi[1][ys][0] + po, *q1p = p.psi[1][ys][1] + po;
+					float4 q0 = ld4(q0p), q1 = ld4(q1p);
+					float v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
+					#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						v0[e] = yP*v0[e] + yP1*(Gx[e] - Gxn[e]);                 /* update.c:64 */
+						v1[e] = yP*v1[e] + yP2*(Gz[e] - Gzn[e]);                 /* update.c:65 */
+						yq0[e] = v0[e]; yq1[e] = v1[e];
+					}
+					st4(q0p, make_float4(v0[0], v0[1], v0[2], v0[3]));
+					st4(q1p, make_float4(v1[0], v1[1], v1[2], v1[3]));
+				}
+				if (zs >= 0) {
+					const float zP = __ldg(p.P[2] + c), zP1 = __ldg(p.P1[2] + c), zP2 = __ldg(p.P2[2] + c);
+					const size_t po = ((size_t)(c - p.slab[2][zs][0])*(p.ny + 2) + b)*p.pitch + ALISB_XO + a0;
+					float *q0p = p.psi[2][zs][0] + po, *q1p = p.psi[2][zs][1] + po;
+					float4 q0 = ld4(q0p), q1 = ld4(q1p);
+					float v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
+					#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						v0[e] = zP*v0[e] + zP1*(Gy[e] - Gyp[e]);                 /* update.c:77 */
+						v1[e] = zP*v1[e] + zP2*(Gx[e] - Gxp[e]);                 /* update.c:78 */
+						zq0[e] = v0[e]; zq1[e] = v1[e];
+					}
+					st4(q0p, make_float4(v0[0], v0[1], v0[2], v0[3]));
+					st4(q1p, make_float4(v1[0], v1[1], v1[2], v1[3]));
+				}
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const bool xin = (xmask >> e) & 1u;
+					#pragma unroll
+					for (int side = 0; side < 2; side++) {
+						if (xs == side && xin) {
+							if (EPS) { Fy[e] += xq0[e]*Cy[e]; Fz[e] += xq1[e]*Cz[e]; } else { Fy[e] += xq0[e]; Fz[e] += xq1[e]; }
+						}
+						if (ys == side) {
+							if (EPS) { Fz[e] += yq0[e]*Cz[e]; Fx[e] += yq1[e]*Cx[e]; } else { Fz[e] += yq0[e]; Fx[e] += yq1[e]; }
+						}
+						if (zs == side) {
+							if (EPS) { Fx[e] += zq0[e]*Cx[e]; Fy[e] += zq1[e]*Cy[e]; } else { Fx[e] += zq0[e]; Fy[e] += zq1[e]; }
+						}
+					}
+				}
+			}
+		}
+
+		if (full) {
+			st4(F0 + o, make_float4(Fx[0], Fx[1], Fx[2], Fx[3]));
+			st4(F1 + o, make_float4(Fy[0], Fy[1], Fy[2], Fy[3]));
+			st4(F2 + o, make_float4(Fz[0], Fz[1], Fz[2], Fz[3]));
+		} else if (act) {
+			#pragma unroll
+			for (int e = 0; e < 4; e++) if (a0 + e <= p.nx) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
+		}
+		gxp = gx; gyp = gy;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Box kernels (regions, planes, strips).  A box is [lo,hi] inclusive in array coordinates,
+ * threads run x fastest.
+ * ------------------------------------------------------------------------------------------ */
+struct Box { int a0, b0, c0, na, nb, nc; };
+
+static __device__ __forceinline__ bool box_cell(const Box &B, size_t t, int &a, int &b, int &c, size_t &q)
+{
+	const size_t n = (size_t)B.na*B.nb*B.nc;
+	if (t >= n) return false;
+	const int ia = (int)(t % B.na); const size_t r = t / B.na;
+	const int ib = (int)(r % B.nb); const int ic = (int)(r / B.nb);
+	a = B.a0 + ia; b = B.b0 + ib; c = B.c0 + ic; q = t;
+	return true;
+}
+#define GIDX(a,b,c) (((size_t)(c)*(ny+2) + (size_t)(b))*pitch + ALISB_XO + (a))
+
+/* reference update.c:89-108: conductivity loss then subtraction of all polarisation currents */
+struct AdeParams {
+	float *F[3];                  /* E components */
+	const float *fill[3];         /* dense box arrays, x fastest */
+	float *J[ALISB_MAXPOLES][3], *K[ALISB_MAXPOLES][3];
+	float a[3];
+	float JJ[3][ALISB_MAXPOLES], JK[3][ALISB_MAXPOLES], JE[3][ALISB_MAXPOLES];
+	float KJ[3][ALISB_MAXPOLES], KK[3][ALISB_MAXPOLES], KE[3][ALISB_MAXPOLES];
+	int nj, nk, lossy;
+	Box full;                     /* allocation box of fill/J/K                         */
+	Box upd;                      /* full clipped to the updated cells 1..n              */
+	int ny, pitch;
+};
+
+__global__ void ade_loss(const __grid_constant__ AdeParams p)
+{
+	const int ny = p.ny, pitch = p.pitch;
+	int a, b, c; size_t q;
+	if (!box_cell(p.upd, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const size_t j = ((size_t)(c - p.full.c0)*p.full.nb + (b - p.full.b0))*p.full.na + (a - p.full.a0);
+	#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const float f = p.fill[k][j];
+		p.F[k][i] = p.F[k][i] * ((1 - p.a[k]*f) / (1 + p.a[k]*f));       /* update.c:94-96 */
+	}
+}
+
+__global__ void ade_subtract(const __grid_constant__ AdeParams p)
+{
+	const int ny = p.ny, pitch = p.pitch;
+	int a, b, c; size_t q;
+	if (!box_cell(p.upd, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const size_t j = ((size_t)(c - p.full.c0)*p.full.nb + (b - p.full.b0))*p.full.na + (a - p.full.a0);
+	#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		float f = p.F[k][i];
+		for (int s = 0; s < p.nk; s++) f -= p.J[s][k][j];                  /* update.c:104-106 */
+		p.F[k][i] = f;
+	}
+}
+
+/* reference update.c:128-158 (updateJ): Drude and critical-point/Lorentz ADE recursions */
+__global__ void ade_currents(const __grid_constant__ AdeParams p)
+{
+	const int ny = p.ny, pitch = p.pitch;
+	int a, b, c; size_t q;
+	if (!box_cell(p.upd, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const size_t j = ((size_t)(c - p.full.c0)*p.full.nb + (b - p.full.b0))*p.full.na + (a - p.full.a0);
+	#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const float F = p.F[k][i], f = p.fill[k][j];
+		for (int s = 0; s < p.nk; s++) {
+			if (s < p.nj) {
+				p.J[s][k][j] = p.JJ[k][s]*p.J[s][k][j] + p.JE[k][s]*f*F;                       /* update.c:135 */
+			} else {
+				const float Kold = p.K[s][k][j];
+				const float Jn = p.JJ[k][s]*p.J[s][k][j] + p.JK[k][s]*Kold + p.JE[k][s]*f*F;   /* update.c:140 */
+				p.J[s][k][j] = Jn;
+				p.K[s][k][j] = p.KJ[k][s]*Jn + p.KK[k][s]*Kold + p.KE[k][s]*f*F;               /* update.c:142 */
+			}
+		}
+	}
+}
+
+/* reference update.c:161-179 (updateS).  vals != 0: per-cell products Amplitude*wave(t,Phase)
+ * evaluated on the host; else amp[q]*f or amplitude*f with the host-evaluated scalar f.   */
+__global__ void source_add(float *F, Box B, int ny, int pitch, const float *vals, const float *amp, float amplitude, float f)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	float v;
+	if (vals) v = vals[q];
+	else v = (amp ? amp[q] : amplitude) * f;
+	F[i] += v;
+}
+
+/* reference update.c:194-202 (update): one TFSF face strip, aux array read through the
+ * aliasing clamp of source.c:223-248 */
+__global__ void tfsf_strip(float *F, const float *G, const float *C, float coef, Box B, int ny, int pitch,
+                           int any, int apitch, int alt0, int alt1, int alt2, int clampa, int clampb)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const int xa = min(a + alt0, clampa), xb = min(b + alt1, clampb), xc = c + alt2;
+	const float g = G[((size_t)xc*(any + 2) + xb)*apitch + ALISB_XO + xa];
+	if (C) F[i] += coef*g*C[i];
+	else   F[i] += coef*g;
+}
+
+/* reference update.c:182-191 (copyBoundary) */
+__global__ void copy_plane(float *F, float *G, float cosk, float sink, Box B, int ny, int pitch, int alt0, int alt1, int alt2)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c), j = GIDX(a + alt0, b + alt1, c + alt2);
+	if (G) {
+		const float f = F[j], g = G[j];
+		F[i] = cosk*f + sink*g;
+		G[i] = cosk*g - sink*f;
+	} else F[i] = cosk*F[j];
+}
+
+/* gather / scatter a box between a padded device array and a dense x-fastest buffer */
+__global__ void box_gather(const float *A, float *buf, Box B, int ny, int pitch)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	buf[q] = A[GIDX(a, b, c)];
+}
+__global__ void box_scatter(float *A, const float *buf, Box B, int ny, int pitch)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	A[GIDX(a, b, c)] = buf[q];
+}
+
+/* reference phaser.c:83-91: running DFT on one face for all frequencies.
+ * acc layout: [freq][which 0..3][cell] float2, cells x fastest over the face box.
+ * The H terms reproduce the reference's promotion to double (0.5 is a double constant). */
+__global__ void phaser_face(float2 *acc, const float *E1, const float *E2, const float *H1, const float *H2,
+                            Box B, int ny, int pitch, size_t hstep, int nfreq, const float2 *expE, const float2 *expH)
+{
+	int a, b, c; size_t q;
+	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t cells = (size_t)B.na*B.nb*B.nc;
+	const size_t i = GIDX(a, b, c);
+	const float e1 = E1[i], e2 = E2[i];
+	const float h1 = H1[i] + H1[i + hstep], h2 = H2[i] + H2[i + hstep];
+	for (int f = 0; f < nfreq; f++) {
+		const float2 wE = expE[f], wH = expH[f];
+		float2 *A = acc + (size_t)f*4*cells + q;
+		float2 v = A[0];       v.x += wE.x*e1; v.y += wE.y*e1; A[0] = v;
+		v = A[cells];          v.x += wE.x*e2; v.y += wE.y*e2; A[cells] = v;
+		v = A[2*cells];
+		v.x = (float)((double)v.x + (double)(wH.x*h1)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h1)*0.5); A[2*cells] = v;
+		v = A[3*cells];
+		v.x = (float)((double)v.x + (double)(wH.x*h2)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h2)*0.5); A[3*cells] = v;
+	}
+}

@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FDTD time-stepping hot path (updateE + updateH) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4]): the synthetic all-PML (CPML Num=12) vacuum
+box with one point dipole, z-slab sharded, WEAK scaling: 2048 x 2048 x 256 cells per GPU, so
+N = 8 is the named 2048^3 cube.  A step = one full Yee step (updateE + updateH) of the whole
+grid.  Metric: Mcells/s (cells incl. PML x steps / second), whole job.
+
+  value     device-resident stepping through the engine C ABI (alisb_step_E/H), CUDA events
+            on the engine's stream, barrier + synchronize on both sides, max over ranks
+  e2e       the same steps driven the way a user's time loop drives them: per step the source
+            sample is produced on the host and a probe value (get(W,Ez,...)) is read back
+            device->host, host wall clock around the loop
+  roofline  the dominant kernel (yee_volume interior instantiation): algorithmic bytes
+            (36 B per cell per half-step pass) / CUDA-event duration of that launch
+  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample
+
+`--impl reference` times the reference CPU implementation (oracle/_ref/bin/bench_cube_ref, the
+reference library built from its own sources; falls back to the oracle port) on a bounded
+z-sub-slab of the same workload.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NY, NZ_PER_GPU, NUM = 2048, 2048, 256, 12
+METRIC, UNIT = "Mcells/s", "Mcells/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--ny", type=int, default=NY)
+    ap.add_argument("--nz-per-gpu", type=int, default=NZ_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(nx, ny, nz, n):
+    return f"synthetic vacuum+CPML(Num={NUM}) box {nx}x{ny}x{nz} cells, point dipole Ez/Pulse, z-slab sharded over {n} GPU(s), {nz // n} planes per GPU"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref)
+# ------------------------------------------------------------------------------------------
+def run_reference_cube(nx, ny, nz, steps, warmup):
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "bench_cube_ref")
+    cores = os.cpu_count() or 1
+    if os.path.exists(exe):
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        out = subprocess.run([exe, str(nx), str(ny), str(nz), str(steps), str(warmup)], env=env, capture_output=True, text=True, timeout=3000).stdout
+        m = re.search(r"seconds=([0-9.]+) mcells_per_s=([0-9.]+) threads=(\d+)", out)
+        if m:
+            return {"value": float(m.group(2)), "seconds": float(m.group(1)), "cores": int(m.group(3)), "kind": "reference"}
+    # fall back to the oracle port (plain-C restatement, OpenMP)
+    from alis_b200 import capi, synthetic
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    w = synthetic.BoxWorld(nx, ny, nz, num=NUM)
+    e = w.make_engine(capi.load_oracle())
+    e.run(warmup)
+    t0 = time.time()
+    e.run(steps)
+    dt = time.time() - t0
+    return {"value": w.cells() * steps / dt * 1e-6, "seconds": dt, "cores": cores, "kind": "port"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nz_total = args.nz_per_gpu * args.gpus
+    sample_nz = 64                                   # bounded z-sub-slab of the workload
+    r = run_reference_cube(args.nx, args.ny, sample_nz, args.steps, args.warmup)
+    sample = f"{args.nx}x{args.ny}x{sample_nz} z-sub-slab of the workload, {args.steps} steps, all host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.nx, args.ny, nz_total, args.gpus), "timed_sample": sample},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=10).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for q, n in enumerate(names) if any(len(s) > 2 + q and s[2 + q].lower() == "active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from alis_b200 import capi, synthetic, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    torch.cuda.set_stream(torch.cuda.Stream())       # a real (non-default) stream shared by the engine, NCCL ordering and the timing events
+    lib = capi.load_engine()
+    nz = args.nz_per_gpu * world
+    w = synthetic.BoxWorld(args.nx, args.ny, nz, num=NUM)
+    eng = w.make_engine(lib, device=local, rank=rank, world=world)
+    runner = sharding.SlabRunner(eng, rank, world, cuda=True)      # engine now runs on torch's current stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    runner.run(args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- device-resident timing --------------------------------------------------------
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        runner.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    kinfo = lib_kernel_stats(eng)
+    eng.set_profiling(False)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = w.cells() * args.steps / (ms * 1e-3) * 1e-6
+
+    # ---- end to end: host-driven loop with a probe read back every step -----------------
+    e2e = None
+    if not args.no_e2e:
+        probe_c = min(max(eng.shard[0], w.ax[2].arr(5)), eng.shard[1]) - (eng.shard[0] - 1)
+        pbox = [w.ax[0].arr(0), w.ax[0].arr(0), w.ax[1].arr(0), w.ax[1].arr(0), probe_c, probe_c]
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(args.steps):
+            runner.step()
+            acc += float(eng.read_box(capi.ARR_FIELD, [0, 2, 0], pbox)[0, 0, 0])   # get(W, Ez, ...): 4 B D2H, syncs
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": w.cells() * args.steps / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4,
+               "note": "FDTD state is device-resident by design: per step the host supplies the two source samples (kernel arguments) and reads one probe value back"}
+
+    clocks = None
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=5)
+        clocks = sampler.summary()
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        roof = None
+        if kinfo:
+            ach = kinfo["bytes_per_launch"] / (kinfo["avg_ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": load_traffic(),
+                    "kernel": "yee_volume (interior, no-PML instantiation)", "avg_launch_ms": kinfo["avg_ms"], "launches_timed": kinfo["n"],
+                    "bytes_per_launch": kinfo["bytes_per_launch"], "peak_source": peak_src,
+                    "whole_step": {"algorithmic_bytes": w.algorithmic_bytes_per_step() / world, "achieved_GBps": w.algorithmic_bytes_per_step() / world / (ms / args.steps * 1e-3) / 1e9}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_reference_cube(256, 256, 256, 100, 3)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": "256^3 all-PML vacuum cube, 100 steps, all host threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.nx, args.ny, nz, world), "l2": "inputs (6 field arrays, >= 26 GB per GPU) are far larger than the 126 MB L2",
+                       "per_gpu_mcells_per_s": value / world},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def lib_kernel_stats(eng):
+    """per-launch CUDA-event times of the dominant kernel, collected by the engine"""
+    avg, n, by = eng.profile_dominant()
+    if n == 0:
+        return None
+    return {"avg_ms": avg, "n": n, "bytes_per_launch": by}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)

@@ -200,8 +200,14 @@ int  alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *ho
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 uint64_t alisb_launch_count(alisb_engine *e);    /* kernels launched by this engine so far   */
-/* CUDA-event time (ms) of the volume kernels of the last alisb_run, and their launch count */
+/* With profiling on, every volume-kernel launch is bracketed by CUDA events on the engine's
+ * stream; alisb_last_run_kernel_ms returns their summed duration (ms) and count for the
+ * last alisb_run (it synchronises the stream).                                             */
+int  alisb_set_profiling(alisb_engine *e, int on);
 int  alisb_last_run_kernel_ms(alisb_engine *e, float *ms_total, int *launches);
+/* the same for the dominant kernel only (the volume launch covering the most cells), with
+ * its algorithmic bytes per launch (36 B per cell per half-step pass)       */
+int  alisb_profile_dominant(alisb_engine *e, float *ms_total, int *launches, double *bytes_per_launch);
 
 #ifdef __cplusplus
 }

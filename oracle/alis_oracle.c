@@ -619,4 +619,6 @@ int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *hos
 }
 
 uint64_t alisb_launch_count(alisb_engine *e) { return e->launches; }
+int alisb_profile_dominant(alisb_engine *e, float *ms, int *n, double *b) { (void)e; if (ms) *ms=0; if (n) *n=0; if (b) *b=0; return ALISB_OK; }
+int alisb_set_profiling(alisb_engine *e, int on) { (void)e; (void)on; return ALISB_OK; }
 int alisb_last_run_kernel_ms(alisb_engine *e, float *ms, int *n) { (void)e; if (ms) *ms=0; if (n) *n=0; return ALISB_OK; }

@@ -1,0 +1,41 @@
+/*
+ * bench_cube.c -- times updateE+updateH of an all-PML vacuum box through the PUBLIC API
+ * (createWorld + pointDipole + the run loop), i.e. the synthetic configuration of SURVEY 8d.
+ *
+ *   bench_cube <nx> <ny> <nz> <steps> <warmup>
+ *
+ * prints one line:  cells=<n> steps=<k> seconds=<s> mcells_per_s=<v> threads=<t> probe=<Ez>
+ * Linked against the unmodified reference it is the CPU baseline (`--impl reference` and
+ * cpu_baseline.kind "reference" in bench.py).
+ */
+#include <alis.h>
+#include <sys/time.h>
+#include <omp.h>
+
+static double now(void) { struct timeval t; gettimeofday(&t, 0); return t.tv_sec + 1e-6*t.tv_usec; }
+
+int main(int argc, char **argv)
+{
+	if (argc < 6) { printf("usage: %s nx ny nz steps warmup\n", argv[0]); return 2; }
+	int n[3] = {atoi(argv[1]), atoi(argv[2]), atoi(argv[3])}, steps = atoi(argv[4]), warm = atoi(argv[5]);
+	float lo[3], hi[3];
+	for (int d=0; d<3; d++) {            /* interior = n-26 cells, centred like alis_b200/synthetic.py */
+		int interior = n[d] - 26;
+		int Min = -(interior/2), Max = Min + interior - 1;
+		lo[d] = 10.f*Min; hi[d] = 10.f*Max;
+	}
+	dom Dom = {{lo[0], hi[0]}, {lo[1], hi[1]}, {lo[2], hi[2]}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PML, PML}, {PML, PML}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	if (W->iNUM != n[0] || W->jNUM != n[1] || W->kNUM != n[2]) { printf("grid mismatch %d %d %d\n", W->iNUM, W->jNUM, W->kNUM); return 1; }
+	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 1);
+	for (int s=0; s<warm; s++) { updateE(W); updateH(W); }
+	double t0 = now();
+	for (int s=0; s<steps; s++) { updateE(W); updateH(W); }
+	double dt = now() - t0;
+	double cells = (double)n[0]*n[1]*n[2];
+	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g\n", cells, steps, dt, cells*steps/dt*1e-6,
+		omp_get_max_threads(), get(W, Ez, 0, 0, 50));
+	return 0;
+}

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/stepdump_hashes.json from the UNMODIFIED reference
+(oracle/_ref/bin/stepdump_ref, built by oracle/build_ref.sh from /root/reference).
+Runs in the build container only (the reference is not present on the GPU box).
+
+For every configuration in oracle/harness/configs.h the complete field state after the
+default number of steps is hashed (sha256 over the raw dump, so parity is bit-exact) and
+per-array L2 norms are recorded for diagnostics.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tests import helpers  # noqa: E402
+
+out = {}
+with tempfile.TemporaryDirectory() as tmp:
+    for cfg in helpers.CONFIGS:
+        path = os.path.join(tmp, cfg + ".bin")
+        log = helpers.run_stepdump("stepdump_ref", cfg, path, cwd=tmp)
+        a = helpers.read_dump(path)
+        out[cfg] = {
+            "sha256": helpers.sha256_file(path),
+            "shape": list(a.shape),
+            "l2": [[[float(np.sqrt((a[m, s, c].astype(np.float64) ** 2).sum())) for c in range(3)] for s in range(2)] for m in range(a.shape[0])],
+            "summary": log.strip().splitlines()[-1],
+        }
+        print(cfg, out[cfg]["sha256"][:16], out[cfg]["summary"])
+with open(os.path.join(helpers.GOLDEN, "stepdump_hashes.json"), "w") as f:
+    json.dump(out, f, indent=1)

@@ -1,0 +1,78 @@
+"""Shared test helpers (test infrastructure; may use the oracle)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CONFIGS = ["dipole_pml", "vacuum_cpml", "pec_box", "pbc_slab", "nanoblock", "tfsf_normal",
+           "phc", "metasurface", "dipole_band", "aniso_ade"]
+
+
+def have_ref_bin(name):
+    return os.path.exists(os.path.join(REF_BIN, name))
+
+
+def run_stepdump(binary, config, out, steps=0, cwd=None):
+    exe = os.path.join(REF_BIN, binary)
+    env = dict(os.environ)
+    env.setdefault("OMP_NUM_THREADS", str(min(8, os.cpu_count() or 1)))
+    r = subprocess.run([exe, config, str(steps), out], cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} {config} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return r.stdout
+
+
+def read_dump(path):
+    b = open(path, "rb").read()
+    assert b[:8] == b"ALISDUMP"
+    nx, ny, nz, cf = np.frombuffer(b[8:24], dtype=np.int32)
+    a = np.frombuffer(b[24:], dtype=np.float32).reshape(cf + 1, 2, 3, nx + 2, ny + 2, nz + 2)
+    return a
+
+
+def sha256_file(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def golden_hashes():
+    with open(os.path.join(GOLDEN, "stepdump_hashes.json")) as f:
+        return json.load(f)
+
+
+def rel_l2(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    d = np.sqrt(((a - b) ** 2).sum())
+    n = np.sqrt((b ** 2).sum())
+    return float(d / n) if n > 0 else float(d)
+
+
+def seed_fields(engines, shape, complex_field=0, seed=12345, scale=1e-3):
+    """Same LCG-seeded dense fields (uniform in +-scale) into every engine."""
+    rng = np.random.RandomState(seed)
+    for m in range(complex_field + 1):
+        for s in range(2):
+            for c in range(3):
+                f = np.zeros(shape, np.float32)
+                f[1:-1, 1:-1, 1:-1] = ((rng.rand(*[n - 2 for n in shape]) * 2 - 1) * scale).astype(np.float32)
+                for e in engines:
+                    e.write_field(s, c, m, f)
+
+
+def assert_fields_identical(e1, e2, what=""):
+    a, b = e1.read_all_fields(), e2.read_all_fields()
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ; first at [m,set,comp,a,b,c]={bad[0].tolist()} "
+                             f"{a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}; rel L2 = {rel_l2(a, b):.3e}")
+    assert np.abs(a).max() > 0, f"{what}: fields are all zero - the test is vacuous"

@@ -1,0 +1,173 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same
+seeded inputs, bit for bit; against the reference goldens for the named configurations; and
+size-independent properties at larger sizes.  All integer/float results are compared exactly:
+the kernels are compiled without FMA contraction and use the reference's expression order."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from alis_b200 import capi, synthetic
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def both(oracle_lib, engine_lib, shape, **kw):
+    w = synthetic.BoxWorld(*shape, **kw)
+    return w, w.make_engine(engine_lib), w.make_engine(oracle_lib)
+
+
+def compare_psi(g, o):
+    for s in range(2):
+        for ax in range(3):
+            for sd in range(2):
+                f, l = g.grid.pml[s][ax][sd][0], g.grid.pml[s][ax][sd][1]
+                if f > l:
+                    continue
+                box = [1, g.nx, 1, g.ny, 1, g.nz]
+                box[2 * ax], box[2 * ax + 1] = f, l
+                for w in range(2):
+                    a = g.read_box(capi.ARR_PSI, [s, 0, ax, sd, w], box)
+                    b = o.read_box(capi.ARR_PSI, [s, 0, ax, sd, w], box)
+                    assert np.array_equal(a, b), f"psi set={s} axis={ax} side={sd} which={w}"
+
+
+@pytest.mark.parametrize("shape,num,steps", [
+    ((76, 64, 56), 12, 40),      # the synthetic config at the golden size
+    ((37, 41, 45), 5, 25),       # odd sizes, ragged quads
+    ((131, 33, 40), 8, 20),      # two x tiles, ragged tail
+    ((260, 30, 29), 6, 12),      # three x tiles
+    ((64, 64, 64), 24, 30),      # Num=24 -> true CPML (kappa 10, alpha 0.01)
+])
+def test_box_world_seeded_bit_exact(oracle_lib, engine_lib, shape, num, steps):
+    w, g, o = both(oracle_lib, engine_lib, shape, num=num)
+    helpers.seed_fields([g, o], tuple(n + 2 for n in shape))
+    for e in (g, o):
+        e.run(steps)
+    assert g.time() == o.time()
+    helpers.assert_fields_identical(g, o, f"box {shape}")
+    compare_psi(g, o)
+
+
+def test_golden_vacuum_cpml_on_gpu(engine_lib):
+    import hashlib
+    w = synthetic.BoxWorld(76, 64, 56)
+    e = w.make_engine(engine_lib)
+    e.run(60)
+    hdr = b"ALISDUMP" + np.array([76, 64, 56, 0], np.int32).tobytes()
+    got = hashlib.sha256(hdr + e.read_all_fields().tobytes()).hexdigest()
+    assert got == helpers.golden_hashes()["vacuum_cpml"]["sha256"]
+    assert e.launch_count() > 0
+
+
+@pytest.mark.skipif(not helpers.have_ref_bin("stepdump_bridge_cuda"), reason="oracle/_ref harness not built")
+@pytest.mark.parametrize("cfg", helpers.CONFIGS)
+def test_named_configs_match_reference_golden(cfg, tmp_path):
+    """reference-built world (unmodified reference setup code) stepped by the CUDA engine"""
+    out = str(tmp_path / "g.bin")
+    helpers.run_stepdump("stepdump_bridge_cuda", cfg, out, cwd=str(tmp_path))
+    gold = helpers.golden_hashes()[cfg]
+    if helpers.sha256_file(out) != gold["sha256"]:
+        ref = str(tmp_path / "o.bin")
+        helpers.run_stepdump("stepdump_bridge_oracle", cfg, ref, cwd=str(tmp_path))
+        a, b = helpers.read_dump(out), helpers.read_dump(ref)
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{cfg}: {len(bad)} values differ from the oracle, first {bad[:1].tolist()}, rel L2 {helpers.rel_l2(a, b):.3e}")
+
+
+def test_read_write_box_roundtrip(engine_lib):
+    w = synthetic.BoxWorld(45, 38, 33, num=3)
+    e = w.make_engine(engine_lib, with_source=False)
+    rng = np.random.RandomState(1)
+    full = rng.rand(47, 40, 35).astype(np.float32)
+    e.write_field(1, 2, 0, full)
+    assert np.array_equal(e.read_field(1, 2, 0), full)
+    box = [3, 9, 0, 39, 5, 5]
+    sub = rng.rand(7, 40, 1).astype(np.float32)
+    e.write_box(capi.ARR_FIELD, [1, 2, 0], box, sub)
+    full[3:10, :, 5:6] = sub
+    assert np.array_equal(e.read_field(1, 2, 0), full)
+    assert np.array_equal(e.read_box(capi.ARR_FIELD, [1, 2, 0], box), sub)
+
+
+def test_linearity_at_scale(engine_lib):
+    """size-independent property at a size the oracle cannot reach in seconds: scaling the
+    source by 2 scales every field value by exactly 2 (power-of-two scaling is exact in fp32)"""
+    shape = (384, 320, 288)
+    w1 = synthetic.BoxWorld(*shape, amplitude=1.0)
+    w2 = synthetic.BoxWorld(*shape, amplitude=2.0)
+    e1, e2 = w1.make_engine(engine_lib), w2.make_engine(engine_lib)
+    for e in (e1, e2):
+        e.run(90)
+    k = w1.ax[2].arr(0)
+    box = [1, shape[0], 1, shape[1], k - 2, k + 3]
+    for s in range(2):
+        for c in range(3):
+            a, b = e1.read_box(capi.ARR_FIELD, [s, c, 0], box), e2.read_box(capi.ARR_FIELD, [s, c, 0], box)
+            assert np.array_equal(2 * a, b)
+    assert np.abs(e1.read_box(capi.ARR_FIELD, [0, 2, 0], box)).max() > 0
+
+
+def _cudart():
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    raise RuntimeError("libcudart not found")
+
+
+def test_two_slabs_on_one_gpu_equal_single(engine_lib):
+    """the multi-GPU decomposition with both slabs on cuda:0 and device-to-device halo copies"""
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    shape, steps = (70, 50, 62), 45
+    w = synthetic.BoxWorld(*shape)
+    single = w.make_engine(engine_lib)
+    single.run(steps)
+    ref = single.read_all_fields()
+    parts = [w.make_engine(engine_lib, rank=r, world=2) for r in range(2)]
+    lo, hi = parts
+
+    def xchg(set_, src, dst):
+        for comp in range(2):
+            sp, _, nb = src.halo_info(set_, 0, comp)
+            _, rp, _ = dst.halo_info(set_, 0, comp)
+            src.synchronize()
+            dst.synchronize()
+            assert rt.cudaMemcpy(rp, sp, nb, 3) == 0
+    for _ in range(steps):
+        for e in parts:
+            e.step_E()
+        xchg(capi.SET_E, lo, hi)
+        for e in parts:
+            e.step_H()
+        xchg(capi.SET_H, hi, lo)
+    got = np.concatenate([e.read_all_fields()[..., 1:-1] for e in parts], axis=-1)
+    assert np.array_equal(got, ref[..., 1:-1])
+    assert np.abs(ref).max() > 0
+
+
+def test_phaser_accumulation_bit_exact(oracle_lib, engine_lib):
+    w, g, o = both(oracle_lib, engine_lib, (48, 44, 40), num=6)
+    helpers.seed_fields([g, o], (50, 46, 42), seed=7)
+    box = [8, 41, 8, 37, 8, 33]
+    freqs = np.array([1 / 400.0, 1 / 520.0, 1 / 650.0], np.float32)
+    pg, po = capi.Phaser(g, box, 0x3F, 3), capi.Phaser(o, box, 0x3F, 3)
+    for step in range(12):
+        for e in (g, o):
+            e.step_E()
+            e.step_H()
+        _, _, tE, tH = g.time()
+        wE = np.exp(2j * np.pi * freqs.astype(np.float64) * tE).astype(np.complex64)
+        wH = np.exp(2j * np.pi * freqs.astype(np.float64) * tH).astype(np.complex64)
+        pg.accumulate(wE, wH)
+        po.accumulate(wE, wH)
+    for f in range(3):
+        for face in range(6):
+            for which in range(4):
+                a, b = pg.read(f, face, which), po.read(f, face, which)
+                assert np.array_equal(a.view(np.float32), b.view(np.float32)), (f, face, which)
+                assert np.abs(a).max() > 0
