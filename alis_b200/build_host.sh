@@ -1,0 +1,38 @@
+#!/bin/sh
+# Builds the host C layer (the ALiS-compatible public API) IN-TREE:
+#   alis_b200/libalis.so        host layer + CUDA engine   (the drop-in product library)
+#   tests/bin/libalis_oracle.so host layer + CPU oracle    (TEST INFRASTRUCTURE: lets the host layer be
+#                                                            validated against the reference without a GPU)
+#   tests/bin/stepdump_mine_*   harness drivers linked against either
+# Same flags as the reference build (gcc -O3 -std=c99, no fast-math) so float/complex expressions
+# compile to the same arithmetic.
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(dirname "$HERE")
+CC=${ALIS_HOST_CC:-gcc}
+OBJ=$HERE/host/obj
+mkdir -p "$OBJ" "$ROOT/tests/bin"
+CFLAGS="-std=c99 -O3 -fopenmp -fPIC -w -I$ROOT/include -I$HERE/host"
+SRCS="world object shapes source update view fields output slices phaser farfld engine_bridge"
+OBJS=""
+for f in $SRCS; do
+	$CC $CFLAGS -c "$HERE/host/$f.c" -o "$OBJ/$f.o"
+	OBJS="$OBJS $OBJ/$f.o"
+done
+if [ -f "$HERE/libalis_b200_engine.so" ]; then
+	$CC -shared -fopenmp -o "$HERE/libalis.so" $OBJS -L"$HERE" -lalis_b200_engine -Wl,-rpath,'$ORIGIN' -lm
+fi
+if [ -f "$ROOT/oracle/liboracle_alis.so" ]; then
+	$CC -shared -fopenmp -o "$ROOT/tests/bin/libalis_oracle.so" $OBJS -L"$ROOT/oracle" -loracle_alis -Wl,-rpath,'$ORIGIN/../../oracle' -lm
+fi
+HARNESS=$ROOT/oracle/harness
+for h in stepdump bench_cube monitors; do
+	[ -f "$HARNESS/$h.c" ] || continue
+	if [ -f "$HERE/libalis.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -DHARNESS_MODE_MINE -I"$ROOT/include" -I"$HARNESS" "$HARNESS/$h.c" -L"$HERE" -lalis -Wl,-rpath,'$ORIGIN/../../alis_b200' -lm -o "$ROOT/tests/bin/${h}_mine_cuda"
+	fi
+	if [ -f "$ROOT/tests/bin/libalis_oracle.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -DHARNESS_MODE_MINE -I"$ROOT/include" -I"$HARNESS" "$HARNESS/$h.c" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/${h}_mine_oracle"
+	fi
+done
+echo "build_host: ok"

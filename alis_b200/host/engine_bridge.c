@@ -26,8 +26,15 @@ struct alis_bridge {
 	alisb_engine *E;
 	struct alis_bridge *aux[8]; int naux;
 	wave_ctx *ctx; int nctx, cap_ctx;
-	int committed;
+	int dirty;                      /* DIRTY_* bits: what must be re-uploaded before the next step */
+	int owns_aux;
 };
+
+enum { DIRTY_TABLES = 1, DIRTY_MATERIALS = 2, DIRTY_SOURCES = 4, DIRTY_COPIES = 8, DIRTY_ALL = 15 };
+
+#ifdef ALIS_B200_HOST
+alis_bridge *alis_host_bridge(world W);        /* host layer: every world owns its bridge */
+#endif
 
 static float wave_trampoline(void *user, float t, float phase)
 {
@@ -267,7 +274,13 @@ static void push_tfsf(alis_bridge *B, tfsf S)
 		add_strip(LH,&nH,W, X,Y, +hz[S->kMax+1], 0, S->iMin,S->iMax, S->jMIN,S->jMAX, S->kMax+1,S->kMax+1, 0,0,-1);
 	}
 
+#ifdef ALIS_B200_HOST
+	alis_bridge *AB = alis_host_bridge(A);      /* owned by the auxiliary world itself */
+	B->owns_aux = 0;
+#else
 	alis_bridge *AB = alis_bridge_create(A);
+	B->owns_aux = 1;
+#endif
 	alis_bridge_commit(AB);
 	if (B->naux >= 8) { printf("alis-b200 engine: too many TFSF regions\n"); exit(1); }
 	B->aux[B->naux++] = AB;
@@ -298,12 +311,13 @@ alis_bridge *alis_bridge_create(world W)
 	CHECK(alisb_create(&g, &B->E));
 	B->cap_ctx = 512;
 	B->ctx = calloc(B->cap_ctx, sizeof(wave_ctx));
+	B->dirty = DIRTY_ALL;
 	return B;
 }
 
 static void drop_aux(alis_bridge *B)
 {
-	for (int q=0; q<B->naux; q++) alis_bridge_destroy(B->aux[q]);
+	if (B->owns_aux) for (int q=0; q<B->naux; q++) alis_bridge_destroy(B->aux[q]);
 	B->naux = 0;
 }
 
@@ -318,23 +332,30 @@ void alis_bridge_destroy(alis_bridge *B)
 
 alisb_engine *alis_bridge_engine(alis_bridge *B) { return B->E; }
 
-/* (re)upload everything except the field state */
+/* (re)upload whatever changed since the last commit; the field state is never touched */
 void alis_bridge_commit(alis_bridge *B)
 {
 	world W = B->W;
-	push_tables(B, ALISB_SET_E, W->CE);
-	push_tables(B, ALISB_SET_H, W->CH);
-	push_materials(B);
-	push_copies(B);
-	CHECK(alisb_clear_sources(B->E));
-	drop_aux(B);
-	B->nctx = 0;
-	for (tfsf S = W->S; S; S = S->S) push_tfsf(B, S);
-	push_source_list(B, W->SE, ALISB_SET_E);
-	push_source_list(B, W->SH, ALISB_SET_H);
+	if (!B->dirty) return;
+	if (B->dirty & DIRTY_TABLES) {
+		push_tables(B, ALISB_SET_E, W->CE);
+		push_tables(B, ALISB_SET_H, W->CH);
+	}
+	if (B->dirty & DIRTY_MATERIALS) push_materials(B);
+	if (B->dirty & (DIRTY_COPIES|DIRTY_SOURCES)) push_copies(B);
+	if (B->dirty & DIRTY_SOURCES) {
+		CHECK(alisb_clear_sources(B->E));
+		drop_aux(B);
+		B->nctx = 0;
+		for (tfsf S = W->S; S; S = S->S) push_tfsf(B, S);
+		push_source_list(B, W->SE, ALISB_SET_E);
+		push_source_list(B, W->SH, ALISB_SET_H);
+	}
 	CHECK(alisb_set_time(B->E, W->n, W->t, W->E->t, W->H->t));
-	B->committed = 1;
+	B->dirty = 0;
 }
+
+void alis_bridge_mark(alis_bridge *B, int mask) { if (B) B->dirty |= mask; }
 
 static void pull_time(alis_bridge *B)
 {
@@ -347,19 +368,19 @@ static void pull_time(alis_bridge *B)
 
 void alis_bridge_step_E(alis_bridge *B)
 {
-	if (!B->committed) alis_bridge_commit(B);
+	if (B->dirty) alis_bridge_commit(B);
 	CHECK(alisb_step_E(B->E));
 	pull_time(B);
 }
 
 void alis_bridge_step_H(alis_bridge *B)
 {
-	if (!B->committed) alis_bridge_commit(B);
+	if (B->dirty) alis_bridge_commit(B);
 	CHECK(alisb_step_H(B->E));
 	pull_time(B);
 }
 
-void alis_bridge_invalidate(alis_bridge *B) { if (B) B->committed = 0; }
+void alis_bridge_invalidate(alis_bridge *B) { alis_bridge_mark(B, DIRTY_ALL); }
 
 /* dense host block (reference layout, incl. ghost layer) of one field component */
 void alis_bridge_read_field(alis_bridge *B, int set, int comp, int m, float *host)

@@ -13,6 +13,7 @@ alis_bridge  *alis_bridge_create(world W);           /* allocates the engine (fi
 void          alis_bridge_destroy(alis_bridge *B);
 void          alis_bridge_commit(alis_bridge *B);    /* upload coefficients/sources/copies       */
 void          alis_bridge_invalidate(alis_bridge *B);/* setup changed: re-commit before next step */
+void          alis_bridge_mark(alis_bridge *B, int dirty_mask);   /* 1 tables, 2 materials, 4 sources, 8 copies */
 void          alis_bridge_step_E(alis_bridge *B);    /* updateE  (update.c:275-299)              */
 void          alis_bridge_step_H(alis_bridge *B);    /* updateH  (update.c:302-341)              */
 alisb_engine *alis_bridge_engine(alis_bridge *B);

@@ -1,0 +1,32 @@
+/*
+ * host_internal.h -- glue shared by the host C layer (not installed).
+ *
+ * Fields live on the device.  The host structs keep
+ *   W->b200_bridge : the engine + descriptor state (engine_bridge.c), created on first use
+ *   W->b200_view   : bookkeeping of the lazily allocated HOST VIEWS W->E[m].x/y/z ... that the
+ *                    monitors (fields.c, output.c, slices.c) read, refreshed per region on demand
+ */
+#ifndef ALIS_HOST_INTERNAL_H
+#define ALIS_HOST_INTERNAL_H
+
+#include "alis_b200.h"
+#include "engine_bridge.h"
+
+enum { ALIS_DIRTY_TABLES = 1, ALIS_DIRTY_MATERIALS = 2, ALIS_DIRTY_SOURCES = 4, ALIS_DIRTY_COPIES = 8, ALIS_DIRTY_ALL = 15 };
+
+void alis_host_attach(world W);                 /* called by createWorld / cloneWorld            */
+void alis_host_detach(world W);                 /* frees bridge + views                          */
+alis_bridge *alis_host_bridge(world W);         /* creates the engine on first use               */
+void alis_host_invalidate(world W);             /* setup changed -> re-commit before next step   */
+void alis_host_dirty(world W, int mask);
+void alis_host_reset_fields(world W);           /* rebootWorld                                   */
+void alis_host_touch(world W);                  /* device state advanced: host views are stale   */
+
+/* host views: make W->E[m].{x,y,z}, W->H[m].{x,y,z} valid on [i0-1..i1+1]x[j0-1..j1+1]x[k0-1..k1+1]
+ * (clipped to the allocation), for every field set m, including TFSF aux worlds */
+void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1);
+void alis_view_need_all(world W);
+void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
+void alis_view_free(world W);
+
+#endif

@@ -1,0 +1,450 @@
+/*
+ * object.c -- rasterises objects into the per-component inverse-permittivity arrays and the
+ * per-dispersive-object ADE data (bounding box, fill factors, Drude / Lorentz / critical-point
+ * recursion coefficients) that the GPU engine consumes (engine_bridge.c: push_materials).
+ *
+ * Shapes are user-extensible host callbacks, so rasterisation stays on the host and the results
+ * are uploaded once.  Numerical behaviour follows reference src/object.c (cited per function):
+ * the same sub-pixel sampling pattern and the same float/complex-float expressions, so that the
+ * uploaded arrays are bit-identical to the reference's.
+ */
+#include <string.h>
+#include "alis_c.h"
+#include "host_internal.h"
+
+typedef struct { int iMin, iMax, jMin, jMax, kMin, kMax; } bounds;
+
+/* ---- ADE coefficient formulas (reference object.c:23-67) ------------------------------------------
+ * pole p of matter M: w (resonance, eV), r (damping), f, g (Lorentz / critical-point weights).
+ * Drude:            J' = a J + b E         a = (1 - pi r dt/eV)/(1 + pi r dt/eV),  b = (2 pi w dt/eV)^2/(1 + pi r dt/eV)
+ * critical point:   complex recursion with Gamma = r + i w and sigma = i (f w - g Gamma)                */
+static float complex pole_gamma(matter M, int p) { return M.P[p].r + I * M.P[p].w; }
+static float complex pole_sigma(matter M, int p) { return I * (M.P[p].f * M.P[p].w - M.P[p].g * pole_gamma(M, p)); }
+
+static float drude_a(world W, matter M, int p)
+{
+	return (1 - PI * M.P[p].r * W->dt / W->eV) / (1 + PI * M.P[p].r * W->dt / W->eV);
+}
+
+static float drude_b(world W, matter M, int p)
+{
+	return sq(2 * PI * M.P[p].w * W->dt / W->eV) / (1 + PI * M.P[p].r * W->dt / W->eV);
+}
+
+static float complex cp_a(world W, matter M, int p)
+{
+	return (1 - PI * pole_gamma(M, p) * W->dt / W->eV) / (1 + PI * pole_gamma(M, p) * W->dt / W->eV);
+}
+
+static float complex cp_b(world W, matter M, int p)
+{
+	return - pole_gamma(M, p) * pole_sigma(M, p) * sq(2 * PI * W->dt / W->eV) / (1 + PI * pole_gamma(M, p) * W->dt / W->eV);
+}
+
+/* static conductivity of component q (0,1,2): pure conductivity poles {0,s} plus the g w part of
+ * critical-point poles; anisotropic matter stores its poles in x,y,z triples */
+static float conductivity(world W, matter M, int q)
+{
+	const int tri = M.e.y || M.e.z ? 1 : 0;
+	float s = 0;
+	for (int p=0; p<MAXPOLES; p+=1+2*tri) {
+		if (!M.P[p+q*tri].w && M.P[p+q*tri].r) s += M.P[p+q*tri].r;
+		if (M.P[p+q*tri].g) s += M.P[p+q*tri].g * M.P[p+q*tri].w;
+	}
+	return s / W->eV;
+}
+
+/* effective eps_inf of component q including the conductivity half-step term */
+static float eps_eff(world W, matter M, int q)
+{
+	return ((q==2 && M.e.z) ? M.e.z : (q==1 && M.e.y) ? M.e.y : M.e.x) + PI * W->dt * conductivity(W, M, q);
+}
+
+/* 2: chi(2) matter, 1: dispersive/lossy matter (needs auxiliary fields), 0: plain dielectric */
+static int needs_aux(matter M)
+{
+	for (int a=0; a<3; a++) for (int b=0; b<6; b++) if (M.d[a][b]) return 2;
+	if (M.P[0].w || M.P[0].r) return 1;
+	return 0;
+}
+
+/* ---- sub-pixel rasterisation (reference object.c:70-121) ---------------------------------------------- */
+
+/* 1 if (i,j,k) (fractional indices) is inside object o and in none of the objects listed before it */
+static float owned_by(world W, object *O, int o, float i, float j, float k)
+{
+	if (!(O[o].S(O[o], W->itox(W, i), W->jtoy(W, j), W->ktoz(W, k)))) return 0;
+	while (o--) if (O[o].S(O[o], W->itox(W, i), W->jtoy(W, j), W->ktoz(W, k))) return 0;
+	return 1;
+}
+
+static float fill_factor(world W, object *O, int o, float i, float j, float k)
+{
+	float centre = owned_by(W, O, o, i, j, k);
+
+	if (W->subN < 2) {
+		if (centre || W->subN >= 0) return centre;
+		/* subN < 0: a component counts as inside if an adjacent pair of nodes is inside */
+		if (floorf(i) < ceilf(i)) {
+			if (owned_by(W, O, o, i-0.5, j-0.5, k) && owned_by(W, O, o, i+0.5, j-0.5, k)) return 1;
+			if (owned_by(W, O, o, i-0.5, j+0.5, k) && owned_by(W, O, o, i+0.5, j+0.5, k)) return 1;
+			if (owned_by(W, O, o, i-0.5, j, k-0.5) && owned_by(W, O, o, i+0.5, j, k-0.5)) return 1;
+			if (owned_by(W, O, o, i-0.5, j, k+0.5) && owned_by(W, O, o, i+0.5, j, k+0.5)) return 1;
+		}
+		else if (floorf(j) < ceilf(j)) {
+			if (owned_by(W, O, o, i-0.5, j-0.5, k) && owned_by(W, O, o, i-0.5, j+0.5, k)) return 1;
+			if (owned_by(W, O, o, i+0.5, j-0.5, k) && owned_by(W, O, o, i+0.5, j+0.5, k)) return 1;
+			if (owned_by(W, O, o, i, j-0.5, k-0.5) && owned_by(W, O, o, i, j+0.5, k-0.5)) return 1;
+			if (owned_by(W, O, o, i, j-0.5, k+0.5) && owned_by(W, O, o, i, j+0.5, k+0.5)) return 1;
+		}
+		else if (floorf(k) < ceilf(k)) {
+			if (owned_by(W, O, o, i-0.5, j, k-0.5) && owned_by(W, O, o, i-0.5, j, k+0.5)) return 1;
+			if (owned_by(W, O, o, i+0.5, j, k-0.5) && owned_by(W, O, o, i+0.5, j, k+0.5)) return 1;
+			if (owned_by(W, O, o, i, j-0.5, k-0.5) && owned_by(W, O, o, i, j-0.5, k+0.5)) return 1;
+			if (owned_by(W, O, o, i, j+0.5, k-0.5) && owned_by(W, O, o, i, j+0.5, k+0.5)) return 1;
+		}
+		return 0;
+	}
+
+	/* quick exit: centre and the eight outermost sub-samples agree -> cell is uniform */
+	float edge = (W->subN-1.0) / (W->subN*2.0);
+	int uniform = 1;
+	for (int c=0; c<8 && uniform; c++) {
+		float s = owned_by(W, O, o, i + (c&4 ? edge : -edge), j + (c&2 ? edge : -edge), k + (c&1 ? edge : -edge));
+		if (s != centre) uniform = 0;
+	}
+	if (uniform) return centre;
+
+	/* subN^3 regular sub-samples */
+	float inside = 0;
+	for (int di=1-W->subN; di<W->subN; di+=2) for (int dj=1-W->subN; dj<W->subN; dj+=2) for (int dk=1-W->subN; dk<W->subN; dk+=2)
+		inside += owned_by(W, O, o, i+0.5*di/W->subN, j+0.5*dj/W->subN, k+0.5*dk/W->subN);
+	return inside / (W->subN * W->subN * W->subN);
+}
+
+/* ---- allocation (reference object.c:124-226) -------------------------------------------------------------- */
+
+static void alloc_material_tables(world W, coeffs *C, float ex, float ey, float ez)
+{
+	for (int m=0; m<=W->complexField; m++) {
+		MALLOC(W->E[m].Jx, 0, C->N); MALLOC(W->E[m].Jy, 0, C->N); MALLOC(W->E[m].Jz, 0, C->N);
+		MALLOC(W->E[m].Kx, 0, C->N); MALLOC(W->E[m].Ky, 0, C->N); MALLOC(W->E[m].Kz, 0, C->N);
+	}
+	MALLOC(C->NJ, 0, C->N); MALLOC(C->NK, 0, C->N);
+	MALLOC(C->iMin, 0, C->N); MALLOC(C->iMax, 0, C->N);
+	MALLOC(C->jMin, 0, C->N); MALLOC(C->jMax, 0, C->N);
+	MALLOC(C->kMin, 0, C->N); MALLOC(C->kMax, 0, C->N);
+	MALLOC(C->Jx, 0, C->N); MALLOC(C->Jy, 0, C->N); MALLOC(C->Jz, 0, C->N);
+	MALLOC(C->ax, 0, C->N); MALLOC(C->ay, 0, C->N); MALLOC(C->az, 0, C->N);
+	float ***tabs[] = { &C->JJx, &C->JJy, &C->JJz, &C->JKx, &C->JKy, &C->JKz, &C->JEx, &C->JEy, &C->JEz,
+	                    &C->KJx, &C->KJy, &C->KJz, &C->KKx, &C->KKy, &C->KKz, &C->KEx, &C->KEy, &C->KEz };
+	for (unsigned q=0; q<sizeof tabs/sizeof *tabs; q++) MALLOC(*tabs[q], 0, C->N);
+
+	/* inverse permittivity: each component is one cell longer along its own axis */
+	C->x = makeField(W->iMIN, W->iMAX+1, W->jMIN, W->jMAX, W->kMIN, W->kMAX);
+	C->y = makeField(W->iMIN, W->iMAX, W->jMIN, W->jMAX+1, W->kMIN, W->kMAX);
+	C->z = makeField(W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX+1);
+	for (int i=W->iMIN; i<=W->iMAX+1; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX; k++) C->x[i][j][k] = 1/ex;
+	for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX+1; j++) for (int k=W->kMIN; k<=W->kMAX; k++) C->y[i][j][k] = 1/ey;
+	for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX+1; k++) C->z[i][j][k] = 1/ez;
+}
+
+static void alloc_dispersive(world W, coeffs *C, int n, bounds B)
+{
+	C->iMin[n] = B.iMin, C->iMax[n] = B.iMax + (B.iMax == W->iMAX ? 1 : 0);
+	C->jMin[n] = B.jMin, C->jMax[n] = B.jMax + (B.jMax == W->jMAX ? 1 : 0);
+	C->kMin[n] = B.kMin, C->kMax[n] = B.kMax + (B.kMax == W->kMAX ? 1 : 0);
+
+	float **all[] = { &C->JJx[n], &C->JJy[n], &C->JJz[n], &C->JKx[n], &C->JKy[n], &C->JKz[n], &C->JEx[n], &C->JEy[n], &C->JEz[n] };
+	float **cp[]  = { &C->KJx[n], &C->KJy[n], &C->KJz[n], &C->KKx[n], &C->KKy[n], &C->KKz[n], &C->KEx[n], &C->KEy[n], &C->KEz[n] };
+	for (int q=0; q<9; q++) MALLOC(*all[q], 0, C->NK[n]);
+	for (int q=0; q<9; q++) MALLOC(*cp[q], C->NJ[n], C->NK[n] - C->NJ[n]);
+
+	C->Jx[n] = makeField(C->iMin[n], C->iMax[n], C->jMin[n], C->jMax[n], C->kMin[n], C->kMax[n]);
+	C->Jy[n] = makeField(C->iMin[n], C->iMax[n], C->jMin[n], C->jMax[n], C->kMin[n], C->kMax[n]);
+	C->Jz[n] = makeField(C->iMin[n], C->iMax[n], C->jMin[n], C->jMax[n], C->kMin[n], C->kMax[n]);
+
+	/* host views of the polarisation currents (device resident; refreshed by alis_view_need_ade) */
+	for (int m=0; m<=W->complexField; m++) {
+		float ******J[3] = { &W->E[m].Jx, &W->E[m].Jy, &W->E[m].Jz };
+		for (int c=0; c<3; c++) {
+			MALLOC((*J[c])[n], 0, C->NK[n]);
+			for (int p=0; p<C->NK[n]; p++) (*J[c])[n][p] = makeField(C->iMin[n], C->iMax[n], C->jMin[n], C->jMax[n], C->kMin[n], C->kMax[n]);
+		}
+	}
+}
+
+/* bounding boxes of every object (the cells whose NODE lies in the object and in no earlier one),
+ * widened by one cell below and two above, clipped to the grid (reference object.c:229-279) */
+static bounds *object_bounds(world W, object *O, int N)
+{
+	bounds *B;
+	MALLOC(B, 0, N);
+	for (int o=0; o<N; o++) {
+		B[o].iMin = W->iMAX, B[o].iMax = W->iMIN;
+		B[o].jMin = W->jMAX, B[o].jMax = W->jMIN;
+		B[o].kMin = W->kMAX, B[o].kMax = W->kMIN;
+	}
+	#pragma omp parallel
+	{
+		bounds *b;
+		MALLOC(b, 0, N);
+		memcpy(b, B, sizeof(bounds)*N);
+		#pragma omp for
+		for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX; k++) {
+			int o = 0;
+			while (O[o].S && !(O[o].S(O[o], W->itox(W, i), W->jtoy(W, j), W->ktoz(W, k)))) o++;
+			if (o < N) {
+				b[o].iMin = MIN(i, b[o].iMin), b[o].iMax = MAX(i, b[o].iMax);
+				b[o].jMin = MIN(j, b[o].jMin), b[o].jMax = MAX(j, b[o].jMax);
+				b[o].kMin = MIN(k, b[o].kMin), b[o].kMax = MAX(k, b[o].kMax);
+			}
+		}
+		#pragma omp critical
+		for (int o=0; o<N; o++) {
+			B[o].iMin = MIN(b[o].iMin, B[o].iMin), B[o].iMax = MAX(b[o].iMax, B[o].iMax);
+			B[o].jMin = MIN(b[o].jMin, B[o].jMin), B[o].jMax = MAX(b[o].jMax, B[o].jMax);
+			B[o].kMin = MIN(b[o].kMin, B[o].kMin), B[o].kMax = MAX(b[o].kMax, B[o].kMax);
+		}
+		free(b);
+	}
+	for (int o=0; o<N; o++) {
+		if (B[o].iMin > B[o].iMax || B[o].jMin > B[o].jMax || B[o].kMin > B[o].kMax) {
+			printf("\rVolume of object %d/%d is zero!\n", o+1, N);
+			exit(0);
+		}
+		B[o].iMin = MAX(B[o].iMin-1, W->iMIN), B[o].iMax = MIN(B[o].iMax+2, W->iMAX);
+		B[o].jMin = MAX(B[o].jMin-1, W->jMIN), B[o].jMax = MIN(B[o].jMax+2, W->jMAX);
+		B[o].kMin = MAX(B[o].kMin-1, W->kMIN), B[o].kMax = MIN(B[o].kMax+2, W->kMAX);
+	}
+	return B;
+}
+
+/* fill factors of the three staggered components + the pole coefficients of dispersive object n
+ * (= list entry o); tri = 1 for anisotropic matter (reference object.c:290-336) */
+static void set_dispersive(world W, coeffs *C, matter *M, object *O, int n, int o, int tri)
+{
+	#pragma omp parallel for schedule(guided)
+	for (int i=C->iMin[n]; i<=C->iMax[n]; i++) for (int j=C->jMin[n]; j<=C->jMax[n]; j++) for (int k=C->kMin[n]; k<=C->kMax[n]; k++) {
+		C->Jx[n][i][j][k] = fill_factor(W, O, o, i-0.5, j, k);
+		C->Jy[n][i][j][k] = fill_factor(W, O, o, i, j-0.5, k);
+		C->Jz[n][i][j][k] = fill_factor(W, O, o, i, j, k-0.5);
+	}
+
+	C->ax[n] = PI * W->dt * conductivity(W, M[o], 0) / (M[o].e.x ? M[o].e.x : M[o].e.x);
+	C->ay[n] = PI * W->dt * conductivity(W, M[o], 1) / (M[o].e.y ? M[o].e.y : M[o].e.x);
+	C->az[n] = PI * W->dt * conductivity(W, M[o], 2) / (M[o].e.z ? M[o].e.z : M[o].e.x);
+
+	float *JJ[3] = { C->JJx[n], C->JJy[n], C->JJz[n] }, *JK[3] = { C->JKx[n], C->JKy[n], C->JKz[n] }, *JE[3] = { C->JEx[n], C->JEy[n], C->JEz[n] };
+	float *KJ[3] = { C->KJx[n], C->KJy[n], C->KJz[n] }, *KK[3] = { C->KKx[n], C->KKy[n], C->KKz[n] }, *KE[3] = { C->KEx[n], C->KEy[n], C->KEz[n] };
+	int drude = 0, cp = C->NJ[n];                 /* Drude poles first, then the two-variable ones */
+	for (int p=0; p<MAXPOLES; p+=1+2*tri) {
+		if (!M[o].P[p].w) continue;
+		if (!M[o].P[p].f && !M[o].P[p].g) {
+			for (int c=0; c<3; c++) {
+				JJ[c][drude] = drude_a(W, M[o], p+c*tri);
+				JE[c][drude] = drude_b(W, M[o], p+c*tri) / eps_eff(W, M[o], c);
+			}
+			drude++;
+		}
+		else {
+			for (int c=0; c<3; c++) {
+				JJ[c][cp] = creal(cp_a(W, M[o], p+c*tri));
+				JK[c][cp] =-cimag(cp_a(W, M[o], p+c*tri));
+				JE[c][cp] = creal(cp_b(W, M[o], p+c*tri)) / eps_eff(W, M[o], c);
+				KJ[c][cp] =-JK[c][cp] / JJ[c][cp];
+				KK[c][cp] = JK[c][cp] * JK[c][cp] / JJ[c][cp] + JJ[c][cp];
+				KE[c][cp] = JE[c][cp] * JK[c][cp] / JJ[c][cp] + cimag(cp_b(W, M[o], p+c*tri)) / eps_eff(W, M[o], c);
+			}
+			cp++;
+		}
+	}
+}
+
+/* eps^-1 <- 1/(1/eps^-1 + d_eps * fill): arithmetic averaging of the permittivity inside a cell */
+#define BLEND(C, de, fill) (C) = 1 / (1 / (C) + (de) * (fill))
+
+/* reference object.c:339-405 */
+void putObjectArray(world W, matter *M, object *O)
+{
+	removeObjects(W);
+	int N;
+	for (N=0; O[N].S; N++) if (needs_aux(M[N])) W->CE->N++;
+	printf("\rPreparing to put %d objects.\n", N);
+	/* sub-pixel sampling defaults: 1 if anything is dispersive, else 12 per axis */
+	W->subN = W->Res.spec.subN = W->Res.spec.subN ? W->Res.spec.subN : W->CE->N ? 1 : 12;
+	bounds *B = object_bounds(W, O, N);
+	coeffs *C = W->CE;
+	alloc_material_tables(W, C, eps_eff(W, M[N], 0), eps_eff(W, M[N], 1), eps_eff(W, M[N], 2));
+	MALLOC(C->O, 0, N+1);
+	MALLOC(C->M, 0, N+1);
+	C->M[N] = M[N];                                 /* background matter */
+
+	/* last object first: earlier list entries take precedence (owned_by) */
+	for (int o=N-1, n=C->N; o>=0; o--) {
+		C->O[o] = O[o];
+		C->M[o] = M[o];
+		float cx = eps_eff(W, M[o], 0) - eps_eff(W, M[N], 0);
+		float cy = eps_eff(W, M[o], 1) - eps_eff(W, M[N], 1);
+		float cz = eps_eff(W, M[o], 2) - eps_eff(W, M[N], 2);
+		const bounds b = B[o];
+
+		printf("\rPutting objects: %d left.", o+1);
+		fflush(stdout);
+
+		if (needs_aux(M[o])) {
+			n--;
+			int tri = M[o].e.y || M[o].e.z ? 1 : 0;
+			for (int p=0; p<MAXPOLES; p++) {
+				if (M[o].P[p].w && !M[o].P[p].f && !M[o].P[p].g) C->NJ[n]++;
+				if (M[o].P[p].w) C->NK[n]++;
+			}
+			if (tri) C->NJ[n] /= 3, C->NK[n] /= 3;
+			alloc_dispersive(W, C, n, b);
+			set_dispersive(W, C, M, O, n, o, tri);
+
+			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
+				BLEND(C->x[i][j][k], cx, C->Jx[n][i][j][k]);
+				BLEND(C->y[i][j][k], cy, C->Jy[n][i][j][k]);
+				BLEND(C->z[i][j][k], cz, C->Jz[n][i][j][k]);
+			}
+			if (b.iMax == W->iMAX) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->x[b.iMax+1][j][k], cx, C->Jx[n][b.iMax+1][j][k]);
+			if (b.jMax == W->jMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->y[i][b.jMax+1][k], cy, C->Jy[n][i][b.jMax+1][k]);
+			if (b.kMax == W->kMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++)
+				BLEND(C->z[i][j][b.kMax+1], cz, C->Jz[n][i][j][b.kMax+1]);
+		}
+		else {
+			#pragma omp parallel for schedule(guided)
+			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
+				BLEND(C->x[i][j][k], cx, fill_factor(W, O, o, i-0.5, j, k));
+				BLEND(C->y[i][j][k], cy, fill_factor(W, O, o, i, j-0.5, k));
+				BLEND(C->z[i][j][k], cz, fill_factor(W, O, o, i, j, k-0.5));
+			}
+			if (b.iMax == W->iMAX) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->x[b.iMax+1][j][k], cx, fill_factor(W, O, o, b.iMax+0.5, j, k));
+			if (b.jMax == W->jMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->y[i][b.jMax+1][k], cy, fill_factor(W, O, o, i, b.jMax+0.5, k));
+			if (b.kMax == W->kMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++)
+				BLEND(C->z[i][j][b.kMax+1], cz, fill_factor(W, O, o, i, j, b.kMax+0.5));
+		}
+	}
+
+	free(B);
+	printf("\rPutting objects: %d done.\n", N);
+	fflush(stdout);
+	alis_host_dirty(W, ALIS_DIRTY_MATERIALS | ALIS_DIRTY_SOURCES);
+}
+
+/* putObjects(W, M1, O1, M2, O2, ..., Mbackground): the macro appends a zeroed object as
+ * terminator; matter and object structs travel by value through the varargs
+ * (reference object.c:408-429) */
+void (putObjects)(world W, ...)
+{
+	int N = 0;
+	va_list ap;
+	matter *M;
+	object *O;
+
+	va_start(ap, W);
+	while (va_arg(ap, matter), va_arg(ap, object).S) N++;
+	va_end(ap);
+	MALLOC(M, 0, N+1);
+	MALLOC(O, 0, N+1);
+	va_start(ap, W);
+	for (int o=0; o<=N; o++) {
+		M[o] = va_arg(ap, matter);
+		O[o] = va_arg(ap, object);
+	}
+	va_end(ap);
+	putObjectArray(W, M, O);
+	free(M);
+	free(O);
+}
+
+/* reference object.c:432-497 */
+void removeObjects(world W)
+{
+	coeffs *C = W->CE;
+	if (!(C->O && C->M)) return;
+	for (int m=0; m<=W->complexField; m++) {
+		float *****J[3] = { W->E[m].Jx, W->E[m].Jy, W->E[m].Jz };
+		for (int n=0; n<C->N; n++) for (int c=0; c<3; c++) {
+			for (int p=0; p<C->NK[n]; p++) removeField(J[c][n][p], C->iMin[n], C->jMin[n], C->kMin[n]);
+			free(J[c][n]);
+		}
+		free(W->E[m].Jx); free(W->E[m].Jy); free(W->E[m].Jz);
+		free(W->E[m].Kx); free(W->E[m].Ky); free(W->E[m].Kz);
+		W->E[m].Jx = W->E[m].Jy = W->E[m].Jz = W->E[m].Kx = W->E[m].Ky = W->E[m].Kz = 0;
+	}
+	for (int n=0; n<C->N; n++) {
+		removeField(C->Jx[n], C->iMin[n], C->jMin[n], C->kMin[n]);
+		removeField(C->Jy[n], C->iMin[n], C->jMin[n], C->kMin[n]);
+		removeField(C->Jz[n], C->iMin[n], C->jMin[n], C->kMin[n]);
+		free(C->JJx[n]); free(C->JKx[n]); free(C->JEx[n]);
+		free(C->JJy[n]); free(C->JKy[n]); free(C->JEy[n]);
+		free(C->JJz[n]); free(C->JKz[n]); free(C->JEz[n]);
+		free(C->KJx[n]+C->NJ[n]); free(C->KKx[n]+C->NJ[n]); free(C->KEx[n]+C->NJ[n]);
+		free(C->KJy[n]+C->NJ[n]); free(C->KKy[n]+C->NJ[n]); free(C->KEy[n]+C->NJ[n]);
+		free(C->KJz[n]+C->NJ[n]); free(C->KKz[n]+C->NJ[n]); free(C->KEz[n]+C->NJ[n]);
+	}
+	removeField(C->x, W->iMIN, W->jMIN, W->kMIN);
+	removeField(C->y, W->iMIN, W->jMIN, W->kMIN);
+	removeField(C->z, W->iMIN, W->jMIN, W->kMIN);
+	free(C->NJ); free(C->NK);
+	free(C->iMin); free(C->iMax); free(C->jMin); free(C->jMax); free(C->kMin); free(C->kMax);
+	free(C->Jx); free(C->Jy); free(C->Jz);
+	free(C->ax); free(C->ay); free(C->az);
+	free(C->JJx); free(C->JKx); free(C->JEx); free(C->KJx); free(C->KKx); free(C->KEx);
+	free(C->JJy); free(C->JKy); free(C->JEy); free(C->KJy); free(C->KKy); free(C->KEy);
+	free(C->JJz); free(C->JKz); free(C->JEz); free(C->KJz); free(C->KKz); free(C->KEz);
+	free(C->O);
+	free(C->M);
+	C->O = 0; C->M = 0; C->N = 0;
+	alis_host_dirty(W, ALIS_DIRTY_MATERIALS);
+}
+
+/* loss scaling of all poles ("low temperature" factor T), reference object.c:500-507 */
+matter LT(matter M, float T)
+{
+	for (int p=0; p<MAXPOLES; p++) {
+		M.P[p].r *= T;
+		M.P[p].g *= T;
+	}
+	return M;
+}
+
+/* constant-(n,k) matter interpolated from a text table of "wavelength n k" rows at wavelength l
+ * (reference object.c:510-549) */
+matter nkFile(char *name, float l, float f)
+{
+	FILE *file = fopen(name, "r");
+	if (!file) {
+		printf("The (n,k) file not found.\n");
+		exit(0);
+	}
+	int rows = 0, cap = 0;
+	float *L = 0, *Nr = 0, *Kr = 0;
+	char line[1024];
+	while (fgets(line, 256, file)) {
+		if (cap <= rows) {
+			cap += 256;
+			L = realloc(L, cap*sizeof(float)); Nr = realloc(Nr, cap*sizeof(float)); Kr = realloc(Kr, cap*sizeof(float));
+		}
+		char *s = line;
+		L[rows] = atof(s);
+		s = strchr(s,'\t') ? strchr(s,'\t')+1 : strchr(s,' ') ? strchr(s,' ')+1 : strchr(s,',')+1;
+		Nr[rows] = atof(s);
+		s = strchr(s,'\t') ? strchr(s,'\t')+1 : strchr(s,' ') ? strchr(s,' ')+1 : strchr(s,',')+1;
+		Kr[rows] = atof(s);
+		rows++;
+	}
+	fclose(file);
+	int q = 1;
+	while (q<rows-1 && l>L[q]) q++;
+	float n = (Nr[q-1]*(L[q]-l) + Nr[q]*(l-L[q-1])) / (L[q]-L[q-1]);
+	float k = (Kr[q-1]*(L[q]-l) + Kr[q]*(l-L[q-1])) / (L[q]-L[q-1]);
+	free(L); free(Nr); free(Kr);
+	return (matter) {{(n)*(n)-(k)*(k)},{0,2*n*k*((float)f)}};
+}

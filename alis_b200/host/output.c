@@ -1,0 +1,438 @@
+/*
+ * output.c -- scalar monitors and text writers: point probes, world maxima / integrals,
+ * time-domain Poynting flux through planes and boxes, per-object absorption, tab-separated text
+ * files and the running-DFT spectrum writer.
+ *
+ * Field data is device resident; every monitor prefetches just the region it integrates over
+ * into the host views (view.c) and then evaluates the reference's sums on the host (round 1; the
+ * device-side reductions are SURVEY.md 8 row f1).  Definitions follow reference src/output.c
+ * (cited per function); sums run in index order, i.e. they equal the reference's result with one
+ * OpenMP thread (its `omp reduction` makes the last digits thread-count dependent).
+ */
+#include <sys/time.h>
+#include <sys/stat.h>
+#include <string.h>
+#include "alis_c.h"
+#include "host_internal.h"
+
+/* ---- per (world, name) registry shared by the writers (reference output.c:14-23,107-128) --------- */
+typedef struct entry {
+	world W;
+	char *name;
+	FILE *file;
+	unsigned long calls;
+	unsigned long long stamp;
+	float complex **spectrum;
+	struct entry *next;
+} entry;
+
+/* finds or creates the entry; rewrites `name` into the full path <W->ID><name>; creates the output
+ * directory when the name starts with '/' and the leaf directory when it ends with '/' */
+static entry *lookup(world W, char *name, entry **list)
+{
+	entry *e = *list;
+	while (e && (e->W != W || strcmp(name, e->name))) e = e->next;
+	if (!e) {
+		e = calloc(1, sizeof *e);
+		e->W = W;
+		e->name = strdup(name);
+		e->next = *list;
+		*list = e;
+		char path[1024];
+		strcat(strcpy(path, W->ID), e->name);
+		if (e->name[0]=='/') mkdir(W->ID, 0755);
+		if (path[0] && path[strlen(path)-1]=='/') mkdir(path, 0755);
+	}
+	char path[1024];
+	strcat(strcpy(path, W->ID), e->name);
+	strcpy(name, path);
+	e->calls++;
+	return e;
+}
+
+/* ---- probes ------------------------------------------------------------------------------------------ */
+float get(world W, field F, float x, float y, float z)
+{
+	return F(W, W->xtoi(W, x), W->ytoj(W, y), W->ztok(W, z));
+}
+
+/* reference output.c:56-74 */
+float worldMax(world W, field F)
+{
+	float best = 0, f;
+	alis_view_need(W, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
+	for (int i=W->iMin; i<W->iMax; i++) for (int j=W->jMin; j<W->jMax; j++) for (int k=W->kMin; k<W->kMax; k++)
+		if (best < (f=fabsf(F(W, i, j, k)))) best = f;
+	return best;
+}
+
+/* trapezoidal volume integral over the interior (reference output.c:77-103) */
+static float column_sum(world W, field F, int i, int j)
+{
+	float s = 0;
+	for (int k=W->kMin+1; k<W->kMax; k++) s += W->CE->dz[k] * F(W, i, j, k);
+	s += 0.5 * W->CE->dz[W->kMin] * F(W, i, j, W->kMin);
+	s += 0.5 * W->CE->dz[W->kMax] * F(W, i, j, W->kMax);
+	return s;
+}
+
+static float sheet_sum(world W, field F, int i)
+{
+	float s = 0;
+	for (int j=W->jMin+1; j<W->jMax; j++) s += W->CE->dy[j] * column_sum(W, F, i, j);
+	s += 0.5 * W->CE->dy[W->jMin] * column_sum(W, F, i, W->jMin);
+	s += 0.5 * W->CE->dy[W->jMax] * column_sum(W, F, i, W->jMax);
+	return s;
+}
+
+float worldSum(world W, field F)
+{
+	float Sum = 0;
+	alis_view_need(W, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
+	for (int i=W->iMin+1; i<W->iMax; i++) Sum += W->CE->dx[i] * sheet_sum(W, F, i);
+	Sum += 0.5 * W->CE->dx[W->iMin] * sheet_sum(W, F, W->iMin);
+	Sum += 0.5 * W->CE->dx[W->iMax] * sheet_sum(W, F, W->iMax);
+	if (W->xMinSur==SYM) Sum *= 2;
+	if (W->yMinSur==SYM) Sum *= 2;
+	if (W->zMinSur==SYM) Sum *= 2;
+	return Sum;
+}
+
+/* ---- text writers (reference output.c:131-174) ------------------------------------------------------ */
+void (writeTxt)(world W, char *format, ...)
+{
+	static entry *files;
+	char str[1024], filename[1024];
+	va_list ap;
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	format = va_arg(ap, char*);
+	vsprintf(str, format, ap);
+	va_end(ap);
+	entry *e = lookup(W, filename, &files);
+	struct timeval tv;
+	gettimeofday(&tv, 0);
+	unsigned long long now = tv.tv_sec * 1000000LL + tv.tv_usec;
+
+	if (!e->stamp) {
+		e->file = fopen(strcat(filename, ".txt"), "w");
+		e->stamp = now;
+		if (!e->file) { printf("alis-b200: cannot open %s\n", filename); exit(0); }
+	}
+	fputs(str, e->file);
+	if (now - e->stamp >= 300*1000000LL) {       /* flush every five minutes, as the reference */
+		fflush(e->file);
+		e->stamp = now;
+	}
+}
+
+/* one row of tab-separated %g values; the macro appends a NaN-boxed sentinel */
+void (writeRow)(world W, char *format, ...)
+{
+	char str[1024], filename[1024];
+	va_list ap;
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	double f = va_arg(ap, double);
+	if (!NAN2INT(f)) {
+		int n = sprintf(str, "%g", f);
+		f = va_arg(ap, double);
+		while (!NAN2INT(f)) {
+			n += sprintf(str+n, "\t%g", f);
+			f = va_arg(ap, double);
+		}
+		sprintf(str+n, "\n");
+		(writeTxt)(W, "%s", filename, "%s", str, "");
+	}
+	va_end(ap);
+}
+
+/* Running DFT of scalar samples between wavelengths LMin..LMax with the resolution of an N-step
+ * record; normalised by the spectrum of the driving source; written on the N-th call
+ * (reference output.c:177-230). */
+void (writeSpectrum)(world W, int N, float LMin, float LMax, char *format, ...)
+{
+	static entry *spectra;
+	char filename[1024];
+	double d;
+	float dL = LMin * LMax / (N * W->dt);
+	int M = 0, nMin = floor(LMin/dL), nMax = ceil(LMax/dL);
+	va_list ap;
+
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	do d = va_arg(ap, double), M++;
+	while (!NAN2INT(d));
+	va_end(ap);
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	entry *e = lookup(W, filename, &spectra);
+	const int bins = 1-nMin+nMax;
+
+	if (!e->spectrum) {
+		/* the source that defines the record length: of this world or of its TFSF auxiliary world */
+		source S = W->SE && W->N==W->SE->N ? W->SE : W->SH && W->N==W->SH->N ? W->SH : 0;
+		for (world w = W; !S && w->S && w->S->W; S = w->SE && W->N==w->SE->N ? w->SE : w->SH && W->N==w->SH->N ? w->SH : 0) w = W->S->W;
+
+		MALLOC(e->spectrum, 0, M);
+		MALLOC(e->spectrum[0], 0, M*bins);
+		for (int m=1; m<M; m++) e->spectrum[m] = e->spectrum[0]+m*bins;
+
+		if (S && W->N) {
+			for (int n=0; n<bins; n++) {
+				float f = (nMax-n) / (dL * nMin * nMax);
+				for (int m=1; m<W->N; m++) e->spectrum[0][n] += S->waveForm(W, S, W->dt*m, S->phase) * cexpf(2*PI*I*f*W->dt*m);
+				if (cabsf(e->spectrum[0][n]) < 1E-3) e->spectrum[0][n] = 0;
+				else if (W->sourceType == 2) e->spectrum[0][n] *= sqrtf(f * S->wavelength);
+				else if (W->sourceType == 3) e->spectrum[0][n] *= f * S->wavelength;
+			}
+		}
+	}
+
+	for (int m=1; m<M; m++) {
+		float t = W->t / (dL * nMin * nMax);
+		d = va_arg(ap, double);
+		for (int n=0; n<bins; n++) e->spectrum[m][n] += (float) d * cexpf(2*PI*I*t*(nMax-n));
+	}
+	va_end(ap);
+
+	if (e->calls == (unsigned long)N) {
+		e->file = fopen(strcat(filename, ".txt"), "w");
+		if (!e->file) { printf("alis-b200: cannot open %s\n", filename); exit(0); }
+		for (int n=0; n<bins; n++) {
+			fprintf(e->file, "%g", (dL * nMin * nMax) / (nMax-n));
+			for (int m=1; m<M; m++) fprintf(e->file, "\t%g", e->spectrum[0][n] ? cabsf(e->spectrum[m][n]/e->spectrum[0][n]) : 0);
+			for (int m=1; m<M; m++) fprintf(e->file, "\t%g", e->spectrum[0][n] ? cargf(e->spectrum[m][n]/e->spectrum[0][n])/PI : 0);
+			fprintf(e->file, "\n");
+		}
+		fclose(e->file);
+	}
+}
+
+/* ---- time-domain Poynting flux (reference output.c:233-362) ------------------------------------------
+ * Flux through the plane normal to axis a at index `at`, over [lo_b,hi_b] x [lo_c,hi_c] with
+ * b = a+1, c = a+2 (cyclic):   S_a = E_b H_c - E_c H_b,  H averaged over the two planes that
+ * flank the E plane, trapezoidal weights in both tangential directions. */
+static inline float pick(float ***A, int a, int at, int b, int ib, int c, int ic)
+{
+	int q[3];
+	q[a] = at; q[b] = ib; q[c] = ic;
+	return A[q[0]][q[1]][q[2]];
+}
+
+static float plane_flux(world W, int a, int at, int bMin, int bMax, int cMin, int cMax)
+{
+	const int b = (a+1)%3, c = (a+2)%3;
+	float ***Eb = b==0 ? W->E->x : b==1 ? W->E->y : W->E->z, ***Ec = c==0 ? W->E->x : c==1 ? W->E->y : W->E->z;
+	float ***Hb = b==0 ? W->H->x : b==1 ? W->H->y : W->H->z, ***Hc = c==0 ? W->H->x : c==1 ? W->H->y : W->H->z;
+	const float *dEb = b==0 ? W->CE->dx : b==1 ? W->CE->dy : W->CE->dz, *dEc = c==0 ? W->CE->dx : c==1 ? W->CE->dy : W->CE->dz;
+	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
+	float Sum = 0;
+	int lo[3], hi[3];
+	lo[a] = at, hi[a] = at+1; lo[b] = bMin, hi[b] = bMax; lo[c] = cMin, hi[c] = cMax;
+	alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+	#define E_H(E, H, ib, ic) (pick(E,a,at,b,ib,c,ic) * (pick(H,a,at,b,ib,c,ic) + pick(H,a,at+1,b,ib,c,ic)))
+
+	for (int ib=bMin+1; ib<=bMax; ib++) {            /* + E_b H_c */
+		float sum = 0;
+		sum += 0.5 * dEc[cMin] * E_H(Eb, Hc, ib, cMin);
+		sum += 0.5 * dEc[cMax] * E_H(Eb, Hc, ib, cMax);
+		for (int ic=cMin+1; ic<cMax; ic++) sum += dEc[ic] * E_H(Eb, Hc, ib, ic);
+		Sum += dHb[ib] * sum;
+	}
+	for (int ic=cMin+1; ic<=cMax; ic++) {            /* - E_c H_b */
+		float sum = 0;
+		sum -= 0.5 * dEb[bMin] * E_H(Ec, Hb, bMin, ic);
+		sum -= 0.5 * dEb[bMax] * E_H(Ec, Hb, bMax, ic);
+		for (int ib=bMin+1; ib<bMax; ib++) sum -= dEb[ib] * E_H(Ec, Hb, ib, ic);
+		Sum += dHc[ic] * sum;
+	}
+	#undef E_H
+	return Sum;
+}
+
+/* index range of a tangential extent: a degenerate extent becomes the two cells around it */
+static void tangential_range(world W, int axis, float lo, float hi, int *iLo, int *iHi)
+{
+	int (*toi)(world, float) = axis==0 ? W->xtoi : axis==1 ? W->ytoj : W->ztok;
+	const int Min = axis==0 ? W->iMin : axis==1 ? W->jMin : W->kMin, Max = axis==0 ? W->iMax : axis==1 ? W->jMax : W->kMax;
+	*iLo = lo==hi ? MAX(Min, toi(W, lo)-1) : MAX(Min, toi(W, lo));
+	*iHi = lo==hi ? MIN(Max, toi(W, hi)+1) : MIN(Max, toi(W, hi));
+}
+
+static float poynting_plane(world W, int a, float pos, float bLo, float bHi, float cLo, float cHi)
+{
+	const int b = (a+1)%3, c = (a+2)%3;
+	const int sur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
+	const int flat[3] = { W->Dom.x.Min==W->Dom.x.Max, W->Dom.y.Min==W->Dom.y.Max, W->Dom.z.Min==W->Dom.z.Max };
+	int (*toi)(world, float) = a==0 ? W->xtoi : a==1 ? W->ytoj : W->ztok;
+	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
+	const int mirrored = pos<0 && sur[a]==SYM;
+	int at = toi(W, mirrored ? -pos : pos);
+	int bMin, bMax, cMin, cMax;
+	tangential_range(W, b, bLo, bHi, &bMin, &bMax);
+	tangential_range(W, c, cLo, cHi, &cMin, &cMax);
+
+	float Sum = plane_flux(W, a, at, bMin, bMax, cMin, cMax);
+	/* per-unit-length normalisation of collapsed (2-D) extents; mirror symmetry doubles the flux.
+	 * Order of the two axes as in the reference: y before z, x before z, x before y. */
+	const int first = MIN(b, c), second = MAX(b, c);
+	for (int pass=0; pass<2; pass++) {
+		const int ax = pass==0 ? first : second;
+		const float lo = ax==b ? bLo : cLo, hi = ax==b ? bHi : cHi;
+		const float *dH = ax==b ? dHb : dHc;
+		const int top = ax==b ? bMax : cMax;
+		if (lo==hi || flat[ax]) Sum /= dH[top]+dH[top-1];
+	}
+	if (sur[first]==SYM) Sum *= 2;
+	if (sur[second]==SYM) Sum *= 2;
+	return (mirrored ? -0.5 : 0.5) * Sum;
+}
+
+float (poyntingX)(world W, float x, float yMin, float yMax, float zMin, float zMax, ...) { return poynting_plane(W, 0, x, yMin, yMax, zMin, zMax); }
+float (poyntingY)(world W, float y, float xMin, float xMax, float zMin, float zMax, ...) { return poynting_plane(W, 1, y, zMin, zMax, xMin, xMax); }
+float (poyntingZ)(world W, float z, float xMin, float xMax, float yMin, float yMax, ...) { return poynting_plane(W, 2, z, xMin, xMax, yMin, yMax); }
+
+/* net outward flux through the faces of a box; faces on Bloch-periodic boundaries cancel
+ * (reference output.c:335-362) */
+float poyntingOut(world W, float xMin, float xMax, float yMin, float yMax, float zMin, float zMax)
+{
+	float fx = 0, fy = 0, fz = 0;
+	/* one prefetch for the whole box: the six face evaluations below then hit the host views */
+	{
+		int lo[3], hi[3];
+		const float bmin[3] = { xMin, yMin, zMin }, bmax[3] = { xMax, yMax, zMax };
+		int (*toi[3])(world, float) = { W->xtoi, W->ytoj, W->ztok };
+		const int Min[3] = { W->iMin, W->jMin, W->kMin }, Max[3] = { W->iMax, W->jMax, W->kMax };
+		const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
+		for (int a=0; a<3; a++) {
+			const int q0 = toi[a](W, bmin[a] < 0 && sym[a] ? -bmin[a] : bmin[a]), q1 = toi[a](W, bmax[a]);
+			lo[a] = MAX(Min[a], MIN(q0, q1)) - 1;
+			hi[a] = MIN(Max[a], MAX(q0, q1)) + 1;
+			if (sym[a]) lo[a] = MIN(lo[a], Min[a]);
+		}
+		alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+	}
+	if (xMin > W->xMin || xMax < W->xMax || W->xMinSur != BBC) {
+		fx = (poyntingX)(W, xMax, yMin, yMax, zMin, zMax);
+		if (xMin < 0 && W->xMinSur==SYM) fx *= 2;
+		else fx -= (poyntingX)(W, xMin, yMin, yMax, zMin, zMax);
+	}
+	if (yMin > W->yMin || yMax < W->yMax || W->yMinSur != BBC) {
+		fy = (poyntingY)(W, yMax, xMin, xMax, zMin, zMax);
+		if (yMin < 0 && W->yMinSur==SYM) fy *= 2;
+		else fy -= (poyntingY)(W, yMin, xMin, xMax, zMin, zMax);
+	}
+	if (zMin > W->zMin || zMax < W->zMax || W->zMinSur != BBC) {
+		fz = (poyntingZ)(W, zMax, xMin, xMax, yMin, yMax);
+		if (zMin < 0 && W->zMinSur==SYM) fz *= 2;
+		else fz -= (poyntingZ)(W, zMin, xMin, xMax, yMin, yMax);
+	}
+	return fx + fy + fz;
+}
+
+/* ---- absorption inside a dispersive object (reference output.c:23-47, 365-435) ---------------------------
+ * integral of E.J over the object's bounding box with trapezoidal end corrections, J = conduction
+ * + polarisation currents scaled back by eps */
+static int same_object(object A, object B)
+{
+	if (A.S != B.S || A.p != B.p) return 0;
+	for (int a=0; a<3; a++) for (int b=0; b<3; b++) if (A.f[a][b] != B.f[a][b]) return 0;
+	return 1;
+}
+
+static int needs_aux(matter M)
+{
+	for (int a=0; a<3; a++) for (int b=0; b<6; b++) if (M.d[a][b]) return 2;
+	if (M.P[0].w || M.P[0].r) return 1;
+	return 0;
+}
+
+static float object_current(world W, int c, int n, int i, int j, int k)
+{
+	coeffs *C = W->CE;
+	float a = c==0 ? C->ax[n] : c==1 ? C->ay[n] : C->az[n];
+	float ***fill = c==0 ? C->Jx[n] : c==1 ? C->Jy[n] : C->Jz[n];
+	float ***E = c==0 ? W->E->x : c==1 ? W->E->y : W->E->z;
+	float ***inv = c==0 ? C->x : c==1 ? C->y : C->z;
+	float ****J = c==0 ? W->E->Jx[n] : c==1 ? W->E->Jy[n] : W->E->Jz[n];
+	float f = 0;
+	if (a) f += 2 * fill[i][j][k] * E[i][j][k] / (1 + 1 / a);
+	for (int p=0; p<C->NK[n]; p++) if (J[p]) f += J[p][i][j][k];
+	return f / inv[i][j][k];
+}
+
+static float column_absorption(world W, int n, int i, int j, float x, float y, float z)
+{
+	coeffs *C = W->CE;
+	float Sum = 0, xs = 0, ys = 0, zs = 0;
+	const int k0 = MAX(W->kMIN, C->kMin[n]), k1 = MIN(W->kMAX, C->kMax[n]);
+
+	for (int k=k0; k<=k1; k++) {
+		if (C->x[i][j][k]) xs += C->dz[k] * W->E->x[i][j][k] * object_current(W, 0, n, i, j, k);
+		if (C->y[i][j][k]) ys += C->dz[k] * W->E->y[i][j][k] * object_current(W, 1, n, i, j, k);
+		if (C->z[i][j][k]) zs += W->CH->dz[k] * W->E->z[i][j][k] * object_current(W, 2, n, i, j, k);
+	}
+	if (k0 == W->kMIN) {
+		const int k = W->kMIN;
+		if (C->x[i][j][k]) xs -= C->dz[k] * W->E->x[i][j][k] * object_current(W, 0, n, i, j, k) * 0.5;
+		if (C->y[i][j][k]) ys -= C->dz[k] * W->E->y[i][j][k] * object_current(W, 1, n, i, j, k) * 0.5;
+		if (C->z[i][j][k]) zs -= W->CH->dz[k] * W->E->z[i][j][k] * object_current(W, 2, n, i, j, k);
+	}
+	if (k1 == W->kMAX) {
+		const int k = W->kMAX;
+		if (C->x[i][j][k]) xs -= C->dz[k] * W->E->x[i][j][k] * object_current(W, 0, n, i, j, k) * 0.5;
+		if (C->y[i][j][k]) ys -= C->dz[k] * W->E->y[i][j][k] * object_current(W, 1, n, i, j, k) * 0.5;
+	}
+	Sum += x * xs * W->CH->dx[i] * C->dy[j];
+	Sum += y * ys * C->dx[i] * W->CH->dy[j];
+	Sum += z * zs * C->dx[i] * C->dy[j];
+	return Sum;
+}
+
+float objectAbsorption(world W, object O)
+{
+	coeffs *C = W->CE;
+	float Sum = 0;
+	int n = 0;
+	for (int o=0; !same_object(O, C->O[o]); o++) if (needs_aux(C->M[o])) n++;
+	const int i0 = MAX(W->iMIN, C->iMin[n]), i1 = MIN(W->iMAX, C->iMax[n]);
+	const int j0 = MAX(W->jMIN, C->jMin[n]), j1 = MIN(W->jMAX, C->jMax[n]);
+	alis_view_need(W, i0, i1, j0, j1, MAX(W->kMIN, C->kMin[n]), MIN(W->kMAX, C->kMax[n]));
+	alis_view_need_ade(W);
+
+	for (int i=i0; i<=i1; i++) {
+		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, i, j, 1, 1, 1);
+		if (j0 == W->jMIN) Sum += column_absorption(W, n, i, W->jMIN,-0.5,-1,-0.5);
+		if (j1 == W->jMAX) Sum += column_absorption(W, n, i, W->jMAX,-0.5, 0,-0.5);
+	}
+	if (i0 == W->iMIN) {
+		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, W->iMIN, j,-1,-0.5,-0.5);
+		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMIN, W->jMIN, 0.5, 0.5, 0.25);
+		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMIN, W->jMAX, 0.5, 0.0, 0.25);
+	}
+	if (i1 == W->iMAX) {
+		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, W->iMAX, j, 0,-0.5,-0.5);
+		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMAX, W->jMIN, 0.0, 0.5, 0.25);
+		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMAX, W->jMAX, 0.0, 0.0, 0.25);
+	}
+
+	if (W->Dom.x.Min==W->Dom.x.Max) Sum /= W->CH->dx[W->iMax]+W->CH->dx[W->iMax-1];
+	if (W->Dom.y.Min==W->Dom.y.Max) Sum /= W->CH->dy[W->jMax]+W->CH->dy[W->jMax-1];
+	if (W->Dom.z.Min==W->Dom.z.Max) Sum /= W->CH->dz[W->kMax]+W->CH->dz[W->kMax-1];
+	if (W->xMinSur==SYM) Sum *= 2;
+	if (W->yMinSur==SYM) Sum *= 2;
+	if (W->zMinSur==SYM) Sum *= 2;
+	return Sum / W->dt;
+}
+
+/* shell helper used by createWorld and drivers (reference output.c:438-445) */
+void exec(char *format, ...)
+{
+	char str[1024];
+	va_list ap;
+	va_start(ap, format);
+	vsprintf(str, format, ap);
+	va_end(ap);
+	if (system(str)) { /* exit status ignored, as in the reference */ }
+}

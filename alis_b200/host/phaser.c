@@ -1,0 +1,292 @@
+/*
+ * phaser.c -- running DFT ("phasers") of the tangential fields on the faces of a box, per
+ * frequency; Poynting flux from the phasors; spectrum writers.
+ *
+ * The accumulators live on the GPU (alisb_phaser_*, kernel phaser_face): updatePhaser computes the
+ * two phase factors per frequency on the host (same cexpf as the reference) and launches ONE
+ * kernel per face for all frequencies.  The host arrays P->zMax.Ex[i][j][k] ... are views that
+ * are refreshed lazily (alisSyncPhaser) when a library routine -- or the user -- needs them.
+ * Definitions follow reference src/phaser.c (cited per function).
+ */
+#include <sys/stat.h>
+#include <string.h>
+#include "alis_c.h"
+#include "host_internal.h"
+
+static alisb_engine *engine_of(world W) { return alis_bridge_engine(alis_host_bridge(W)); }
+static phaser base_of(phaser P) { return P - P->b200_index; }
+
+/* face order used with the engine: 0 xMin, 1 xMax, 2 yMin, 3 yMax, 4 zMin, 5 zMax; the four
+ * accumulators of a face are E(c+1), E(c+2), H(c+1), H(c+2) for face normal c */
+static cfield *face_of(phaser P, int face)
+{
+	cfield *F[6] = { &P->xMin, &P->xMax, &P->yMin, &P->yMax, &P->zMin, &P->zMax };
+	return F[face];
+}
+
+static float complex ****slot_of(cfield *F, int axis, int which)
+{
+	float complex ****E[3] = { &F->Ex, &F->Ey, &F->Ez }, ****H[3] = { &F->Hx, &F->Hy, &F->Hz };
+	const int c = (axis + 1 + (which & 1)) % 3;
+	return which < 2 ? E[c] : H[c];
+}
+
+static void face_box(phaser P, int face, int b[6])
+{
+	b[0] = P->iMin, b[1] = P->iMax, b[2] = P->jMin, b[3] = P->jMax, b[4] = P->kMin, b[5] = P->kMax;
+	const int axis = face/2;
+	b[2*axis] = b[2*axis+1] = (face & 1) ? b[2*axis+1] : b[2*axis];
+}
+
+/* reference phaser.c:21-66 */
+phaser (createPhasers)(world W, float LMin, float LMax, float dL, float xMin, float xMax, float yMin, float yMax, float zMin, float zMax, ...)
+{
+	int nMin = floor(LMin/dL), nMax = ceil(LMax/dL);
+	phaser P;
+	/* the finite source whose duration defines W->N (searched in the TFSF auxiliary world too) */
+	source S = W->SE && W->N==W->SE->N ? W->SE : W->SH && W->N==W->SH->N ? W->SH : 0;
+	for (world w = W; !S && w->S && w->S->W; S = w->SE && W->N==w->SE->N ? w->SE : w->SH && W->N==w->SH->N ? w->SH : 0) w = W->S->W;
+	const int count = 1-nMin+nMax;
+	MALLOC(P, 0, count+1);                       /* zeroed terminator element at the end */
+
+	int mask = 0;
+	for (int n=0; n<count; n++) {
+		phaser p = &P[n];
+		p->W = W;
+		p->N = nMin * nMax * dL / W->dt;
+		p->f = (nMax-n) / (dL * nMin * nMax);
+		p->A = 2.0 / (P->W->N ? P->W->N : P->N);
+		p->iMin = MAX(W->iMin, W->xtoi(W, xMin)), p->iMax = MIN(W->iMax, W->xtoi(W, xMax));
+		p->jMin = MAX(W->jMin, W->ytoj(W, yMin)), p->jMax = MIN(W->jMax, W->ytoj(W, yMax));
+		p->kMin = MAX(W->kMin, W->ztok(W, zMin)), p->kMax = MIN(W->kMax, W->ztok(W, zMax));
+		p->b200_index = n, p->b200_count = count;
+
+		/* normalisation by the source spectrum at this frequency */
+		if (S && W->N) {
+			float complex c = 0;
+			float complex iwdt = 2 * PI * I * p->f * W->dt;
+			for (int q=1; q<W->N; q++) c += S->waveForm(W, S, W->dt*q, S->phase) * cexpf(iwdt*q);
+			p->A = 1 / cabsf(c);
+			if (W->sourceType == 2) p->A /= sqrtf(p->f * S->wavelength);
+			if (W->sourceType == 3) p->A /= p->f * S->wavelength;
+		}
+
+		/* a monitor box wider than a periodic / symmetric world stands for xNUM x yNUM replicas */
+		if ((xMax-xMin < INF && xMin < W->xMin && W->xMax < xMax) && (W->xMaxSur==SYM || W->xMaxSur==PBC || W->xMaxSur==BBC)) {
+			p->xNUM = floor((xMax - xMin) / (W->xMax - W->xMin) + 0.5);
+			p->expikx = (W->xMaxSur==BBC) ? (W->coskx+I*W->sinkx) : 1;
+		}
+		if ((yMax-yMin < INF && yMin < W->yMin && W->yMax < yMax) && (W->yMaxSur==SYM || W->yMaxSur==PBC || W->yMaxSur==BBC)) {
+			p->yNUM = floor((yMax - yMin) / (W->yMax - W->yMin) + 0.5);
+			p->expiky = (W->yMaxSur==BBC) ? (W->cosky+I*W->sinky) : 1;
+		}
+
+		/* faces exist only where the world face is absorbing */
+		const int on[6] = { W->xMinSur==PML && p->iMin != p->iMax, W->xMaxSur==PML,
+		                    W->yMinSur==PML && p->jMin != p->jMax, W->yMaxSur==PML,
+		                    W->zMinSur==PML && p->kMin != p->kMax, W->zMaxSur==PML };
+		mask = 0;
+		for (int face=0; face<6; face++) if (on[face]) {
+			int b[6];
+			face_box(p, face, b);
+			mask |= 1<<face;
+			for (int which=0; which<4; which++)
+				*slot_of(face_of(p, face), face/2, which) = makeComplexField(b[0], b[1], b[2], b[3], b[4], b[5]);
+		}
+	}
+
+	/* one device accumulator set for the whole frequency list */
+	if (mask) {
+		int32_t box[6] = { P->iMin-(W->iMIN-1), P->iMax-(W->iMIN-1), P->jMin-(W->jMIN-1), P->jMax-(W->jMIN-1), P->kMin-(W->kMIN-1), P->kMax-(W->kMIN-1) };
+		alisb_phaser *dev = 0;
+		if (alisb_phaser_create(engine_of(W), box, mask, count, &dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		P->b200_dev = dev;
+	}
+	return P;
+}
+
+phaser (createPhaser)(world W, float L, float xMin, float xMax, float yMin, float yMax, float zMin, float zMax, ...)
+{
+	return (createPhasers)(W, L, L, L, xMin, xMax, yMin, yMax, zMin, zMax);
+}
+
+/* the list is ordered by decreasing frequency; pick the entry closest to 1/wavelength
+ * (reference phaser.c:75-80) */
+phaser choosePhaser(phaser P, float wavelength)
+{
+	do P++;
+	while (1/wavelength < P->f);
+	return (1/wavelength - P->f < (P-1)->f - 1/wavelength) ? P : P-1;
+}
+
+/* reference phaser.c:94-110: one accumulation of every frequency from P to the end of its list */
+void updatePhaser(world W, phaser P)
+{
+	phaser B = base_of(P);
+	if (!B->b200_dev) return;
+	const int count = B->b200_count;
+	float complex *wE = calloc(count, sizeof *wE), *wH = calloc(count, sizeof *wH);
+	for (phaser p = P; p->f; p++) {
+		wE[p->b200_index] = cexpf(2 * PI * I * p->f * W->E->t);
+		wH[p->b200_index] = cexpf(2 * PI * I * p->f * W->H->t);
+	}
+	if (alisb_phaser_accumulate(B->b200_dev, (const float*)wE, (const float*)wH) != ALISB_OK) {
+		printf("alis-b200: %s\n", alisb_last_error());
+		exit(1);
+	}
+	B->b200_stale = 1;
+	free(wE); free(wH);
+}
+
+/* refresh the host views of the whole frequency list */
+void alisSyncPhaser(phaser P)
+{
+	phaser B = base_of(P);
+	if (!B->b200_dev || !B->b200_stale) return;
+	for (phaser p = B; p->f; p++) for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
+		float complex ***A = *slot_of(face_of(p, face), face/2, which);
+		if (!A) continue;
+		int b[6];
+		face_box(p, face, b);
+		if (alisb_phaser_read(B->b200_dev, p->b200_index, face, which, (float*)&A[b[0]][b[2]][b[4]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	}
+	B->b200_stale = 0;
+}
+
+/* reference phaser.c:122-139 */
+void deletePhaser(phaser P)
+{
+	phaser B = base_of(P);
+	if (B->b200_dev) alisb_phaser_destroy(B->b200_dev);
+	for (phaser p = B; p->f; p++) {
+		for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
+			float complex ****slot = slot_of(face_of(p, face), face/2, which);
+			if (*slot) {
+				int b[6];
+				face_box(p, face, b);
+				float complex ***A = *slot;
+				removeField(A, b[0], b[2], b[4]);
+				*slot = 0;
+			}
+		}
+		if (p->dE) free(&p->dE[p->kMIN]);
+		if (p->dH) free(&p->dH[p->kMIN]);
+		if (p->ex) free(&p->ex[p->kMIN]);
+		if (p->ez) free(&p->ez[p->kMIN]);
+	}
+	free(B);
+}
+
+/* ---- flux of the phasors through the monitor box (reference phaser.c:142-245) ---------------------
+ * Re(E x H*) integrated with trapezoidal weights; generic in the face normal a, b = a+1, c = a+2. */
+static inline float complex cpick(float complex ***A, int a, int at, int b, int ib, int c, int ic)
+{
+	int q[3];
+	q[a] = at; q[b] = ib; q[c] = ic;
+	return A[q[0]][q[1]][q[2]];
+}
+
+static float face_flux(phaser P, cfield S, int a, int at)
+{
+	world W = P->W;
+	const int b = (a+1)%3, c = (a+2)%3;
+	float complex ***E[3] = { S.Ex, S.Ey, S.Ez }, ***H[3] = { S.Hx, S.Hy, S.Hz };
+	const float *dE[3] = { W->CE->dx, W->CE->dy, W->CE->dz }, *dH[3] = { W->CH->dx, W->CH->dy, W->CH->dz };
+	const int lo[3] = { P->iMin, P->jMin, P->kMin }, hi[3] = { P->iMax, P->jMax, P->kMax };
+	float Sum = 0;
+
+	if (E[b] && H[c]) {
+		for (int ib=lo[b]+1; ib<=hi[b]; ib++) {
+			float sum = 0;
+			sum += 0.5 * dE[c][lo[c]] * cpick(E[b],a,at,b,ib,c,lo[c]) * conjf(cpick(H[c],a,at,b,ib,c,lo[c]));
+			sum += 0.5 * dE[c][hi[c]] * cpick(E[b],a,at,b,ib,c,hi[c]) * conjf(cpick(H[c],a,at,b,ib,c,hi[c]));
+			for (int ic=lo[c]+1; ic<hi[c]; ic++) sum += dE[c][ic] * cpick(E[b],a,at,b,ib,c,ic) * conjf(cpick(H[c],a,at,b,ib,c,ic));
+			Sum += dH[b][ib] * sum;
+		}
+	}
+	if (E[c] && H[b]) {
+		for (int ic=lo[c]+1; ic<=hi[c]; ic++) {
+			float sum = 0;
+			sum -= 0.5 * dE[b][lo[b]] * cpick(E[c],a,at,b,lo[b],c,ic) * conjf(cpick(H[b],a,at,b,lo[b],c,ic));
+			sum -= 0.5 * dE[b][hi[b]] * cpick(E[c],a,at,b,hi[b],c,ic) * conjf(cpick(H[b],a,at,b,hi[b],c,ic));
+			for (int ib=lo[b]+1; ib<hi[b]; ib++) sum -= dE[b][ib] * cpick(E[c],a,at,b,ib,c,ic) * conjf(cpick(H[b],a,at,b,ib,c,ic));
+			Sum += dH[c][ic] * sum;
+		}
+	}
+	return Sum;
+}
+
+float phaserPoyntingOut(phaser P)
+{
+	world W = P->W;
+	float Sum = 0;
+	alisSyncPhaser(P);
+
+	Sum += face_flux(P, P->xMax, 0, P->iMax) - face_flux(P, P->xMin, 0, P->iMin);
+	Sum += face_flux(P, P->yMax, 1, P->jMax) - face_flux(P, P->yMin, 1, P->jMin);
+	Sum += face_flux(P, P->zMax, 2, P->kMax) - face_flux(P, P->zMin, 2, P->kMin);
+
+	if (W->Dom.x.Min==W->Dom.x.Max) Sum /= W->CH->dx[P->iMax]+W->CH->dx[P->iMax-1];
+	if (W->Dom.y.Min==W->Dom.y.Max) Sum /= W->CH->dy[P->jMax]+W->CH->dy[P->jMax-1];
+	if (W->Dom.z.Min==W->Dom.z.Max) Sum /= W->CH->dz[P->kMax]+W->CH->dz[P->kMax-1];
+
+	if (W->xMinSur==SYM) Sum *= 2;
+	if (W->yMinSur==SYM) Sum *= 2;
+	if (W->zMinSur==SYM) Sum *= 2;
+
+	return Sum * sq(P->A);
+}
+
+float phaserPoynting(phaser P)   { return fabsf(phaserPoyntingOut(P)); }
+float phaserPoyntingIn(phaser P) { return -phaserPoyntingOut(P); }
+
+/* ---- spectra of several phaser lists side by side (reference phaser.c:248-295) ------------------------ */
+void (writePoyntingSpectrum)(world W, char *format, ...)
+{
+	int M = 0;
+	char str[1024], filename[1024];
+	va_list ap;
+	phaser *L;
+
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	for (phaser p=va_arg(ap, phaser); p; M++) p=va_arg(ap, phaser);
+	va_end(ap);
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	MALLOC(L, 0, M);
+	for (int m=0; m<M; m++) L[m] = va_arg(ap, phaser);
+	va_end(ap);
+	for (int n=0; L[0][n].f; n++) {
+		int s = sprintf(str, "%g", 1/L[0][n].f);
+		for (int m=0; m<M; m++) s += sprintf(str+s, "\t%g", phaserPoynting(L[m]+n));
+		sprintf(str+s, "\n");
+		(writeTxt)(W, "%s", filename, "%s", str, "");
+	}
+	free(L);
+}
+
+void (writeFarFieldSpectrum)(world W, tfield pol(phaser,float,float), float theta, float phi, char *format, ...)
+{
+	int M = 0;
+	char str[1024], filename[1024];
+	va_list ap;
+	phaser *L;
+
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	for (phaser p=va_arg(ap, phaser); p; M++) p=va_arg(ap, phaser);
+	va_end(ap);
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	MALLOC(L, 0, M);
+	for (int m=0; m<M; m++) L[m] = va_arg(ap, phaser);
+	va_end(ap);
+	for (int n=0; L[0][n].f; n++) {
+		int s = sprintf(str, "%g", 1/L[0][n].f);
+		for (int m=0; m<M; m++) s += sprintf(str+s, "\t%g", farFieldI(L[m]+n, pol, theta, phi));
+		sprintf(str+s, "\n");
+		(writeTxt)(W, "%s", filename, "%s", str, "");
+	}
+	free(L);
+}

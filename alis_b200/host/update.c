@@ -1,0 +1,125 @@
+/*
+ * update.c -- the run loop entry points.  updateE / updateH hand the step to the B200 engine
+ * (reference update.c:275-341 ran the loops on the CPU); timer() is the progress / loop-condition
+ * helper of reference update.c:14-45.
+ */
+#include <sys/time.h>
+#include <string.h>
+#include "alis_c.h"
+#include "host_internal.h"
+
+int alis_bridge_device(void)
+{
+	const char *s = getenv("ALIS_DEVICE");
+	return s ? atoi(s) : 0;
+}
+
+/* which device array a source adds to (the reference compares S->F with the field pointers,
+ * source.c:59-69; here createSource records the target explicitly) */
+int alis_source_target(world W, source S, int set, int *comp, int *m)
+{
+	(void)W;
+	if (S->b200_set != set) return -1;
+	*comp = S->b200_comp; *m = S->b200_m;
+	return 0;
+}
+
+void alis_host_attach(world W) { W->b200_bridge = 0; W->b200_view = 0; }
+
+alis_bridge *alis_host_bridge(world W)
+{
+	if (!W->b200_bridge) W->b200_bridge = alis_bridge_create(W);
+	return (alis_bridge*)W->b200_bridge;
+}
+
+void alis_host_detach(world W)
+{
+	alis_view_free(W);
+	if (W->b200_bridge) alis_bridge_destroy((alis_bridge*)W->b200_bridge);
+	W->b200_bridge = 0;
+}
+
+void alis_host_dirty(world W, int mask) { if (W->b200_bridge) alis_bridge_mark(W->b200_bridge, mask); }
+void alis_host_invalidate(world W) { alis_host_dirty(W, ALIS_DIRTY_ALL); }
+
+void alis_host_reset_fields(world W)
+{
+	if (!W->b200_bridge) return;                /* never stepped: device state is still zero */
+	if (alisb_reset_fields(alis_bridge_engine(W->b200_bridge)) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	alis_host_touch(W);
+}
+
+void updateE(world W)
+{
+	alis_bridge_step_E(alis_host_bridge(W));
+	alis_host_touch(W);
+}
+
+void updateH(world W)
+{
+	alis_bridge_step_H(alis_host_bridge(W));
+	alis_host_touch(W);
+}
+
+/* Public in the reference (alis_c.h:181-182) and applied there to host arrays.  Fields are device
+ * resident here: the copy is applied to the host views passed in and is NOT written back -- the
+ * engine performs all boundary copies of a step itself (update.c:284-297,311-339). */
+void (copyBoundary)(float ***F, float ***G, float cosk, float sink, int iMin, int iMax, int jMin, int jMax, int kMin, int kMax, int iAlt, int jAlt, int kAlt)
+{
+	if (!F) return;
+	for (int i=iMin; i<=iMax; i++) for (int j=jMin; j<=jMax; j++) for (int k=kMin; k<=kMax; k++) {
+		if (G) {
+			F[i][j][k] = cosk * F[i+iAlt][j+jAlt][k+kAlt] + sink * G[i+iAlt][j+jAlt][k+kAlt];
+			G[i][j][k] = cosk * G[i+iAlt][j+jAlt][k+kAlt] - sink * F[i+iAlt][j+jAlt][k+kAlt];
+		}
+		else F[i][j][k] = cosk * F[i+iAlt][j+jAlt][k+kAlt];
+	}
+}
+
+/* chi(2) three-wave mixing (reference update.c:354-411) is outside the scope of this build
+ * (used by no example). */
+void nonLinearSHG(world WS, world WP, float Alt)
+{
+	(void)WS; (void)WP; (void)Alt;
+	printf("alis-b200: nonLinearSHG is not supported by this build.\n");
+	exit(0);
+}
+
+void nonLinearTWM(world WS, world WP1, world WP2, float Alt)
+{
+	(void)WS; (void)WP1; (void)WP2; (void)Alt;
+	printf("alis-b200: nonLinearTWM is not supported by this build.\n");
+	exit(0);
+}
+
+/* progress line at most once per second; returns n<=N so it can be the loop condition
+ * (reference update.c:14-45) */
+int (timer)(long int n, long int N, char *str, ...)
+{
+	static long int firstStep, lastStep;
+	static unsigned long long firstTime, lastTime;
+	struct timeval tv;
+	gettimeofday(&tv, 0);
+	const unsigned long long now = tv.tv_sec * 1000000LL + tv.tv_usec;
+
+	if (!n || !firstStep) {
+		firstStep = lastStep = n;
+		firstTime = lastTime = now;
+	}
+	else if (n>N || now/1000000LL > lastTime/1000000LL) {
+		unsigned long long elapsed = now - firstTime;
+		unsigned long long total = elapsed + (N-n+1) * (now-lastTime) / (n-lastStep);
+		if (total - elapsed > 3600000000LL) total -= total%60000000LL;
+		lastStep = n;
+		lastTime = now;
+		if (str[0]) printf("\r%s ", str);
+		else printf("\r");
+		printf("[%02lld:%02lld:%02lld/%02lld:%02lld:%02lld] [%ld/%ld: %.1f%%]",
+			elapsed/3600000000LL, elapsed%3600000000LL/60000000LL, elapsed%60000000LL/1000000LL,
+			total/3600000000LL, total%3600000000LL/60000000LL, total%60000000LL/1000000LL,
+			(n-1), N, 100.0*(n-1)/N);
+		fflush(stdout);
+		if (n>N) printf("\n");
+	}
+	return n<=N;
+}

@@ -1,0 +1,140 @@
+/*
+ * view.c -- host views of device-resident fields.
+ *
+ * The reference's monitors read W->E[m].x[i][j][k] directly (reference fields.c:130-291,
+ * output.c:23-47, phaser.c:87-90).  Here those arrays are HOST VIEWS: allocated on first use with
+ * the reference's shape ([iMIN-1..iMAX+1]..., world.c:170-172) and refreshed from the device only
+ * over the region a monitor is about to read (alisb_read_box), so a point probe costs a few
+ * bytes of D2H and a Poynting box six thin slabs -- never a full-field round trip unless the
+ * caller asks for it (alisSyncFields).
+ */
+#include <string.h>
+#include "alis_c.h"
+#include "host_internal.h"
+
+typedef struct {
+	unsigned long version;        /* bumped whenever the device state advances              */
+	unsigned long synced;         /* version the synced box belongs to                      */
+	int box[6], have_box;
+	unsigned long ade_synced; int have_ade;
+} view_state;
+
+static view_state *state(world W)
+{
+	if (!W->b200_view) W->b200_view = calloc(1, sizeof(view_state));
+	return (view_state*)W->b200_view;
+}
+
+void alis_host_touch(world W)
+{
+	state(W)->version++;
+	for (tfsf S = W->S; S; S = S->S) alis_host_touch(S->W);
+}
+
+static void ensure_arrays(world W)
+{
+	for (int m=0; m<=W->complexField; m++) {
+		vfield *V[2] = { &W->E[m], &W->H[m] };
+		for (int s=0; s<2; s++) {
+			if (!V[s]->x) V[s]->x = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
+			if (!V[s]->y) V[s]->y = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
+			if (!V[s]->z) V[s]->z = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
+		}
+	}
+}
+
+static void pull_box(world W, const int b[6])
+{
+	alisb_engine *E = alis_bridge_engine(alis_host_bridge(W));
+	const int ni = b[1]-b[0]+1, nj = b[3]-b[2]+1, nk = b[5]-b[4]+1;
+	int32_t box[6] = { b[0]-(W->iMIN-1), b[1]-(W->iMIN-1), b[2]-(W->jMIN-1), b[3]-(W->jMIN-1), b[4]-(W->kMIN-1), b[5]-(W->kMIN-1) };
+	float *tmp = malloc(sizeof(float)*(size_t)ni*nj*nk);
+	for (int m=0; m<=W->complexField; m++) for (int set=0; set<2; set++) for (int comp=0; comp<3; comp++) {
+		int32_t ids[6] = { set, comp, m, 0, 0, 0 };
+		if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		vfield *V = set == 0 ? &W->E[m] : &W->H[m];
+		float ***A = comp == 0 ? V->x : comp == 1 ? V->y : V->z;
+		size_t q = 0;
+		for (int i=b[0]; i<=b[1]; i++) for (int j=b[2]; j<=b[3]; j++) { memcpy(&A[i][j][b[4]], tmp+q, sizeof(float)*nk); q += nk; }
+	}
+	free(tmp);
+}
+
+void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1)
+{
+	view_state *v = state(W);
+	int b[6] = { MAX(i0-1, W->iMIN-1), MIN(i1+1, W->iMAX+1), MAX(j0-1, W->jMIN-1), MIN(j1+1, W->jMAX+1), MAX(k0-1, W->kMIN-1), MIN(k1+1, W->kMAX+1) };
+	ensure_arrays(W);
+	if (b[0] > b[1] || b[2] > b[3] || b[4] > b[5]) return;
+	if (v->have_box && v->synced == v->version &&
+	    v->box[0] <= b[0] && b[1] <= v->box[1] && v->box[2] <= b[2] && b[3] <= v->box[3] && v->box[4] <= b[4] && b[5] <= v->box[5]) return;
+	/* grow the working set: monitors called every step (probes, flux boxes) ask for the same
+	 * regions again, so fetch the union with the previous request unless that is wasteful */
+	if (v->have_box) {
+		int u[6];
+		for (int a=0; a<3; a++) u[2*a] = MIN(b[2*a], v->box[2*a]), u[2*a+1] = MAX(b[2*a+1], v->box[2*a+1]);
+		const double vu = (double)(u[1]-u[0]+1)*(u[3]-u[2]+1)*(u[5]-u[4]+1);
+		const double vb = (double)(b[1]-b[0]+1)*(b[3]-b[2]+1)*(b[5]-b[4]+1);
+		const double vo = (double)(v->box[1]-v->box[0]+1)*(v->box[3]-v->box[2]+1)*(v->box[5]-v->box[4]+1);
+		if (vu <= 4*(vb+vo) + 4096) memcpy(b, u, sizeof u);
+	}
+	pull_box(W, b);
+	memcpy(v->box, b, sizeof b);
+	v->have_box = 1; v->synced = v->version;
+	/* scattered / source-field monitors read the TFSF auxiliary worlds through the same indices */
+	for (tfsf S = W->S; S; S = S->S) alis_view_need_all(S->W);
+}
+
+void alis_view_need_all(world W)
+{
+	alis_view_need(W, W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
+}
+
+/* host views of the ADE polarisation currents W->E[m].Jx[n][p][i][j][k] (read by rawJ*, jx..jz) */
+void alis_view_need_ade(world W)
+{
+	view_state *v = state(W);
+	coeffs *C = W->CE;
+	if (!C->N) return;
+	if (v->have_ade && v->ade_synced == v->version) return;
+	alisb_engine *E = alis_bridge_engine(alis_host_bridge(W));
+	for (int m=0; m<=W->complexField; m++) {
+		float *****J[3] = { W->E[m].Jx, W->E[m].Jy, W->E[m].Jz };
+		for (int n=0; n<C->N; n++) for (int p=0; p<C->NK[n]; p++) for (int c=0; c<3; c++) {
+			int32_t ids[6] = { m, n, p, c, 0, 0 };
+			int32_t box[6] = { C->iMin[n]-(W->iMIN-1), C->iMax[n]-(W->iMIN-1), C->jMin[n]-(W->jMIN-1), C->jMax[n]-(W->jMIN-1), C->kMin[n]-(W->kMIN-1), C->kMax[n]-(W->kMIN-1) };
+			if (alisb_read_box(E, ALISB_ARR_ADE_J, ids, box, &J[c][n][p][C->iMin[n]][C->jMin[n]][C->kMin[n]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		}
+	}
+	v->have_ade = 1; v->ade_synced = v->version;
+}
+
+void alis_view_free(world W)
+{
+	for (int m=0; m<=W->complexField; m++) {
+		vfield *V[2] = { &W->E[m], &W->H[m] };
+		for (int s=0; s<2; s++) {
+			if (V[s]->x) removeField(V[s]->x, W->iMIN-1, W->jMIN-1, W->kMIN-1);
+			if (V[s]->y) removeField(V[s]->y, W->iMIN-1, W->jMIN-1, W->kMIN-1);
+			if (V[s]->z) removeField(V[s]->z, W->iMIN-1, W->jMIN-1, W->kMIN-1);
+		}
+	}
+	free(W->b200_view);
+	W->b200_view = 0;
+}
+
+/* ---- public extensions --------------------------------------------------------------------------- */
+void alisSyncFields(world W) { alis_view_need_all(W); alis_view_need_ade(W); }
+
+void alisReadField(world W, int set, int comp, int m, float *dense)
+{
+	alis_bridge_read_field(alis_host_bridge(W), set, comp, m, dense);
+}
+
+void alisWriteField(world W, int set, int comp, int m, const float *dense)
+{
+	alis_bridge_write_field(alis_host_bridge(W), set, comp, m, dense);
+	alis_host_touch(W);
+}
+
+const char *alisBackend(void) { return alisb_backend(); }
