@@ -15,6 +15,8 @@
 #include "alis_c.h"
 #include "host_internal.h"
 
+static char *dup_string(const char *s) { char *d = malloc(strlen(s)+1); strcpy(d, s); return d; }   /* (strdup is not ISO C99) */
+
 /* ---- per (world, name) registry shared by the writers (reference output.c:14-23,107-128) --------- */
 typedef struct entry {
 	world W;
@@ -35,7 +37,7 @@ static entry *lookup(world W, char *name, entry **list)
 	if (!e) {
 		e = calloc(1, sizeof *e);
 		e->W = W;
-		e->name = strdup(name);
+		e->name = dup_string(name);
 		e->next = *list;
 		*list = e;
 		char path[1024];
@@ -227,11 +229,13 @@ static float plane_flux(world W, int a, int at, int bMin, int bMax, int cMin, in
 	float ***Hb = b==0 ? W->H->x : b==1 ? W->H->y : W->H->z, ***Hc = c==0 ? W->H->x : c==1 ? W->H->y : W->H->z;
 	const float *dEb = b==0 ? W->CE->dx : b==1 ? W->CE->dy : W->CE->dz, *dEc = c==0 ? W->CE->dx : c==1 ? W->CE->dy : W->CE->dz;
 	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
-	float Sum = 0;
+	/* the reference reduces each of the two terms in its own OpenMP loop and adds the partial
+	 * sums afterwards; keeping the two partials separate reproduces its rounding */
+	float Sum = 0, Sum2 = 0;
 	int lo[3], hi[3];
 	lo[a] = at, hi[a] = at+1; lo[b] = bMin, hi[b] = bMax; lo[c] = cMin, hi[c] = cMax;
 	alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
-	#define E_H(E, H, ib, ic) (pick(E,a,at,b,ib,c,ic) * (pick(H,a,at,b,ib,c,ic) + pick(H,a,at+1,b,ib,c,ic)))
+	#define E_H(E, H, ib, ic) pick(E,a,at,b,ib,c,ic) * (pick(H,a,at,b,ib,c,ic) + pick(H,a,at+1,b,ib,c,ic))   /* no outer parentheses: d * E * (H+H') associates left to right */
 
 	for (int ib=bMin+1; ib<=bMax; ib++) {            /* + E_b H_c */
 		float sum = 0;
@@ -245,9 +249,10 @@ static float plane_flux(world W, int a, int at, int bMin, int bMax, int cMin, in
 		sum -= 0.5 * dEb[bMin] * E_H(Ec, Hb, bMin, ic);
 		sum -= 0.5 * dEb[bMax] * E_H(Ec, Hb, bMax, ic);
 		for (int ib=bMin+1; ib<bMax; ib++) sum -= dEb[ib] * E_H(Ec, Hb, ib, ic);
-		Sum += dHc[ic] * sum;
+		Sum2 += dHc[ic] * sum;
 	}
 	#undef E_H
+	Sum += Sum2;
 	return Sum;
 }
 
@@ -406,13 +411,17 @@ float objectAbsorption(world W, object O)
 		if (j0 == W->jMIN) Sum += column_absorption(W, n, i, W->jMIN,-0.5,-1,-0.5);
 		if (j1 == W->jMAX) Sum += column_absorption(W, n, i, W->jMAX,-0.5, 0,-0.5);
 	}
-	if (i0 == W->iMIN) {
-		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, W->iMIN, j,-1,-0.5,-0.5);
+	if (i0 == W->iMIN) {                         /* (separate partial sums: see plane_flux) */
+		float part = 0;
+		for (int j=j0; j<=j1; j++) part += column_absorption(W, n, W->iMIN, j,-1,-0.5,-0.5);
+		Sum += part;
 		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMIN, W->jMIN, 0.5, 0.5, 0.25);
 		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMIN, W->jMAX, 0.5, 0.0, 0.25);
 	}
 	if (i1 == W->iMAX) {
-		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, W->iMAX, j, 0,-0.5,-0.5);
+		float part = 0;
+		for (int j=j0; j<=j1; j++) part += column_absorption(W, n, W->iMAX, j, 0,-0.5,-0.5);
+		Sum += part;
 		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMAX, W->jMIN, 0.0, 0.5, 0.25);
 		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMAX, W->jMAX, 0.0, 0.0, 0.25);
 	}

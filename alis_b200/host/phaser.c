@@ -193,7 +193,7 @@ static float face_flux(phaser P, cfield S, int a, int at)
 	float complex ***E[3] = { S.Ex, S.Ey, S.Ez }, ***H[3] = { S.Hx, S.Hy, S.Hz };
 	const float *dE[3] = { W->CE->dx, W->CE->dy, W->CE->dz }, *dH[3] = { W->CH->dx, W->CH->dy, W->CH->dz };
 	const int lo[3] = { P->iMin, P->jMin, P->kMin }, hi[3] = { P->iMax, P->jMax, P->kMax };
-	float Sum = 0;
+	float Sum = 0, Sum2 = 0;                     /* two partial sums, added at the end (as the reference's two reduction loops) */
 
 	if (E[b] && H[c]) {
 		for (int ib=lo[b]+1; ib<=hi[b]; ib++) {
@@ -210,9 +210,10 @@ static float face_flux(phaser P, cfield S, int a, int at)
 			sum -= 0.5 * dE[b][lo[b]] * cpick(E[c],a,at,b,lo[b],c,ic) * conjf(cpick(H[b],a,at,b,lo[b],c,ic));
 			sum -= 0.5 * dE[b][hi[b]] * cpick(E[c],a,at,b,hi[b],c,ic) * conjf(cpick(H[b],a,at,b,hi[b],c,ic));
 			for (int ib=lo[b]+1; ib<hi[b]; ib++) sum -= dE[b][ib] * cpick(E[c],a,at,b,ib,c,ic) * conjf(cpick(H[b],a,at,b,ib,c,ic));
-			Sum += dH[c][ic] * sum;
+			Sum2 += dH[c][ic] * sum;
 		}
 	}
+	Sum += Sum2;
 	return Sum;
 }
 

@@ -14,6 +14,8 @@
 #include "alis_c.h"
 #include "host_internal.h"
 
+static char *dup_string(const char *s) { char *d = malloc(strlen(s)+1); strcpy(d, s); return d; }   /* (strdup is not ISO C99) */
+
 /* per (world, writer, name) state (reference slices.c:13-22, 214-239) */
 typedef struct sentry {
 	world W;
@@ -30,7 +32,7 @@ static sentry *lookup(world W, char *name, method M, sentry **list)
 	while (e && (e->W != W || e->M != M || strcmp(name, e->name))) e = e->next;
 	if (!e) {
 		e = calloc(1, sizeof *e);
-		e->W = W; e->M = M; e->name = strdup(name);
+		e->W = W; e->M = M; e->name = dup_string(name);
 		e->next = *list;
 		*list = e;
 		char path[1024];

@@ -1,6 +1,6 @@
 /*
  * alis_api.h -- public C API of alis-b200, source-compatible with the API that the
- * hseelab/alis drivers (reference examples/*.c) are written against (reference src/alis_c.h).
+ * hseelab/alis drivers (the .c files under the reference examples directory) are written against (reference src/alis_c.h).
  *
  * A simulation is a C program: build a `world`, put `object`s in it, add sources, create
  * `slice` / `phaser` monitors and run your own loop of updateE(W); updateH(W);  Here the

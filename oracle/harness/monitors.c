@@ -1,0 +1,78 @@
+/*
+ * monitors.c -- exercises the monitor API (probes, flux boxes, absorption, world integrals,
+ * slices, phasers, phasor flux, far field) on the named configurations and prints every value
+ * with %.9g, one per line.  The same source is linked against the unmodified reference
+ * (golden) and against our library; the two outputs are compared value by value.
+ *
+ *   monitors <config> <steps> [outdir]
+ */
+#include <alis.h>
+#include "configs.h"
+
+static void emit(const char *tag, double v) { printf("%-28s % .9g\n", tag, v); }
+
+int main(int argc, char **argv)
+{
+	if (argc < 3) { printf("usage: %s <config> <steps> [outdir]\n", argv[0]); return 2; }
+	const harness_config *cfg = harness_find(argv[1]);
+	if (!cfg) { printf("unknown config %s\n", argv[1]); return 2; }
+	int steps = atoi(argv[2]);
+	if (steps <= 0) steps = cfg->default_steps;
+	world W = cfg->make();
+	if (argc > 3) strcpy(W->ID, argv[3]);
+
+	const int is_nano = !strcmp(cfg->name, "nanoblock"), is_meta = !strcmp(cfg->name, "metasurface");
+	const int is_band = !strcmp(cfg->name, "dipole_band"), is_phc = !strcmp(cfg->name, "phc");
+	phaser P = 0;
+	if (is_meta) P = createPhaser(W, 500,-2000, 2000,-2000, 2000);
+	if (is_band) P = createPhasers(W, 400, 800, 50);
+	slice XY = createSliceXY(W, 0), XZ = createSliceXZ(W, 0);
+
+	double flux_in = 0, flux_out = 0, probe = 0, absn = 0;
+	object Nanoblock = {Box, {{-200, 200}, {-200, 200}, {-200, 200}}};
+	for (int s=1; s<=steps; s++) {
+		if (cfg->order) updateH(W); else updateE(W);
+		if (is_nano) { flux_in += poyntingIn(W,-250, 250,-250, 250,-250, 250); flux_out += poyntingOut(W,-350, 350,-350, 350,-350, 350); }
+		if (cfg->order) updateE(W); else updateH(W);
+		if (is_nano) { flux_in += poyntingIn(W,-250, 250,-250, 250,-250, 250); flux_out += poyntingOut(W,-350, 350,-350, 350,-350, 350); absn += objectAbsorption(W, Nanoblock); }
+		if (P && steps - s < 40) updatePhaser(W, P);
+		probe += get(W, is_phc ? Hz : Ez, 20, 10, 30);
+	}
+	emit("t", W->t); emit("n", W->n);
+	emit("probe_sum", probe);
+	emit("get_Ex", get(W, Ex, 30, 20, 10)); emit("get_Ey", get(W, Ey, 30, 20, 10)); emit("get_Ez", get(W, Ez, 30, 20, 10));
+	emit("get_Hx", get(W, Hx, 30, 20, 10)); emit("get_Hy", get(W, Hy, 30, 20, 10)); emit("get_Hz", get(W, Hz, 30, 20, 10));
+	emit("get_Ex_mirror", get(W, Ex, -30, -20, -10)); emit("get_Hy_mirror", get(W, Hy, -30, -20, -10));
+	emit("get_iEz", get(W, iEz, 30, 20, 10)); emit("get_iHx", get(W, iHx, 30, 20, 10));
+	emit("get_EE", get(W, EE, 10, 20, 30)); emit("get_HH", get(W, HH, 10, 20, 30)); emit("get_U", get(W, U, 10, 20, 30));
+	emit("get_Sx", get(W, Sx, 10, 20, 30)); emit("get_Sy", get(W, Sy, 10, 20, 30)); emit("get_Sz", get(W, Sz, 10, 20, 30));
+	emit("get_Txx", get(W, Txx, 10, 20, 30)); emit("get_Txy", get(W, Txy, 10, 20, 30)); emit("get_Tyz", get(W, Tyz, 10, 20, 30)); emit("get_Tzx", get(W, Tzx, 10, 20, 30));
+	emit("get_DivE", get(W, DivE, 10, 20, 30)); emit("get_RI", get(W, RI, 10, 20, 30)); emit("get_eEff", get(W, eEff, 10, 20, -150));
+	emit("get_Jx", get(W, Jx, 10, 20, 30)); emit("get_JE", get(W, JE, 10, 20, 30)); emit("get_Fz", get(W, Fz, 10, 20, 30));
+	emit("get_ScEx", get(W, ScEx, 10, 20, 30)); emit("get_ScEE", get(W, ScEE, 10, 20, 30)); emit("get_SoEz", get(W, SoEz, 10, 20, 30)); emit("get_SoEE", get(W, SoEE, 10, 20, 30));
+	emit("worldMax_Ez", worldMax(W, Ez)); emit("worldSum_U", worldSum(W, U));
+	emit("sliceMax_XY_EE", sliceMax(W, EE, XY)); emit("sliceSum_XZ_U", sliceSum(W, U, XZ));
+	emit("poyntingX", poyntingX(W, 100)); emit("poyntingY", poyntingY(W, 50, -100, 100, -80, 120)); emit("poyntingZ", poyntingZ(W, 100, -150, 150));
+	emit("poyntingOut", poyntingOut(W, -120, 120, -120, 120, -100, 140));
+	if (is_nano) { emit("flux_in", flux_in); emit("flux_out", flux_out); emit("absorption", absn); }
+	if (P) {
+		phaser Q = is_band ? choosePhaser(P, 500) : P;
+		emit("phaser_f", Q->f); emit("phaser_A", Q->A); emit("phaser_N", Q->N);
+		emit("phaserPoyntingOut", phaserPoyntingOut(Q));
+		float complex a = farField(Q, Ppol, 20, 30), b = farField(Q, Spol, 140, 250);
+		emit("ff_P_20_30_re", crealf(a)); emit("ff_P_20_30_im", cimagf(a));
+		emit("ff_S_140_250_re", crealf(b)); emit("ff_S_140_250_im", cimagf(b));
+		emit("ffI_unpol_0_0", farFieldI(Q, Unpol, 0, 0)); emit("ffI_P_55_0", farFieldI(Q, Ppol, 55, 0)); emit("ffI_S_89.5_10", farFieldI(Q, Spol, 89.5, 10));
+		emit("ffFlux_30", farFieldFlux(Q, Unpol, 0, 0, 30, 0, 5));
+		double acc = 0;
+		for (int x=0; x<24; x++) for (int y=0; y<12; y++) { float ang[2]; AzimuthalMap(x, y, 24, 12, ang); acc += farFieldI(Q, Unpol, ang[0], ang[1]); }
+		emit("ff_map_sum", acc);
+	}
+	if (argc > 3) {
+		sliceSnap(W, Ez, XY, 0, txt, "/snap-%%");
+		sliceSnap(W, EE, XZ, 0, png(hot,0), "/snap-%%");
+		writeRow(W, "/row", W->t, probe, 2.5);
+		if (P) farFieldTheta(W, is_band ? choosePhaser(P, 500) : P, 0, "/ff-theta");
+	}
+	return 0;
+}

@@ -32,3 +32,12 @@ with tempfile.TemporaryDirectory() as tmp:
         print(cfg, out[cfg]["sha256"][:16], out[cfg]["summary"])
 with open(os.path.join(helpers.GOLDEN, "stepdump_hashes.json"), "w") as f:
     json.dump(out, f, indent=1)
+
+# monitor values (probes, flux, absorption, phasers, far field ...) printed by oracle/harness/monitors.c
+# linked against the reference; one OpenMP thread so that its `omp reduction` sums run in index order
+mon = {}
+for cfg in helpers.MONITOR_CONFIGS:
+    mon[cfg] = helpers.run_monitors("monitors_ref", cfg, threads=1)
+    print(cfg, len(mon[cfg]), "monitor values")
+with open(os.path.join(helpers.GOLDEN, "monitor_values.json"), "w") as f:
+    json.dump(mon, f, indent=1)

@@ -14,6 +14,48 @@ CONFIGS = ["dipole_pml", "vacuum_cpml", "pec_box", "pbc_slab", "nanoblock", "tfs
            "phc", "metasurface", "dipole_band", "aniso_ade"]
 
 
+MONITOR_CONFIGS = ["nanoblock", "metasurface", "dipole_band", "phc", "dipole_pml", "aniso_ade"]
+TEST_BIN = os.path.join(ROOT, "tests", "bin")
+
+
+def have_test_bin(name):
+    return os.path.exists(os.path.join(TEST_BIN, name))
+
+
+def run_monitors(binary, config, threads=None, steps=0):
+    """runs oracle/harness/monitors.c (reference- or own-library build) -> ordered [(tag, text value)]"""
+    exe = os.path.join(REF_BIN if binary.endswith("_ref") else TEST_BIN, binary)
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    r = subprocess.run([exe, config, str(steps)], env=env, capture_output=True, text=True, timeout=1800)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} {config} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    vals = []
+    for line in r.stdout.splitlines():
+        parts = line.split()
+        if len(parts) == 2 and not line.startswith(("Preparing", "Putting")):
+            try:
+                float(parts[1])
+            except ValueError:
+                continue
+            vals.append([parts[0], parts[1]])
+    return vals
+
+
+def run_mine_stepdump(binary, config, out, steps=0, cwd=None):
+    exe = os.path.join(TEST_BIN, binary)
+    r = subprocess.run([exe, config, str(steps), out], cwd=cwd, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} {config} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return r.stdout
+
+
+def golden_monitors():
+    with open(os.path.join(GOLDEN, "monitor_values.json")) as f:
+        return json.load(f)
+
+
 def have_ref_bin(name):
     return os.path.exists(os.path.join(REF_BIN, name))
 

@@ -1,0 +1,25 @@
+"""The drop-in library on the GPU: harness drivers written against the public ALiS API, linked with
+alis_b200/libalis.so (own host layer + CUDA engine), against the reference goldens -- complete
+field state (bit-exact) and every monitor value."""
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", helpers.CONFIGS)
+def test_dropin_fields_bit_exact(cfg, tmp_path):
+    assert helpers.have_test_bin("stepdump_mine_cuda"), "tests/bin/stepdump_mine_cuda missing: run __graft_entry__.build()"
+    out = str(tmp_path / "m.bin")
+    helpers.run_mine_stepdump("stepdump_mine_cuda", cfg, out, cwd=str(tmp_path))
+    assert helpers.sha256_file(out) == helpers.golden_hashes()[cfg]["sha256"]
+
+
+@pytest.mark.parametrize("cfg", helpers.MONITOR_CONFIGS)
+def test_dropin_monitor_values(cfg):
+    got = helpers.run_monitors("monitors_mine_cuda", cfg)
+    want = helpers.golden_monitors()[cfg]
+    assert [g[0] for g in got] == [w[0] for w in want]
+    bad = [(g, w) for g, w in zip(got, want) if g[1] != w[1]]
+    assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
