@@ -73,6 +73,7 @@ struct alisb_engine {
 	uint64_t launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
 	std::vector<ProfRec> prof;         /* one record per profiled volume sub-launch          */
 	float *scratch; size_t scratch_elems;
@@ -166,7 +167,15 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		}
 	}
 	int nb = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,true>, 256, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,true,false>, 256, 0));
+	{
+		const char *s;
+		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 16; e->tune_minchunk = 32;
+		if ((s = getenv("ALISB_BLOCK")) && sscanf(s, "%dx%d", &e->tune_bx, &e->tune_by) == 2) { if (e->tune_bx*e->tune_by*32 > 256 || e->tune_bx < 1 || e->tune_by < 1) { e->tune_bx = 1; e->tune_by = 8; } }
+		if ((s = getenv("ALISB_STREAM"))) e->tune_stream = atoi(s);
+		if ((s = getenv("ALISB_WAVES"))) e->tune_waves = std::max(1, atoi(s));
+		if ((s = getenv("ALISB_MINCHUNK"))) e->tune_minchunk = std::max(1, atoi(s));
+	}
 	cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, g->device));
 	e->resident_ctas = std::max(1, nb)*prop.multiProcessorCount;
 	*out = e;
@@ -349,11 +358,17 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 }
 
 /* ---- one pass ------------------------------------------------------------------------- */
+template <int S, bool STREAM>
+static void launch_volume_ts(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, bool pml)
+{
+	if (eps) { if (pml) yee_volume<S,true,true,STREAM><<<grid,block,0,e->stream>>>(p); else yee_volume<S,true,false,STREAM><<<grid,block,0,e->stream>>>(p); }
+	else     { if (pml) yee_volume<S,false,true,STREAM><<<grid,block,0,e->stream>>>(p); else yee_volume<S,false,false,STREAM><<<grid,block,0,e->stream>>>(p); }
+}
 template <int S>
 static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, bool pml)
 {
-	if (eps) { if (pml) yee_volume<S,true,true><<<grid,block,0,e->stream>>>(p); else yee_volume<S,true,false><<<grid,block,0,e->stream>>>(p); }
-	else     { if (pml) yee_volume<S,false,true><<<grid,block,0,e->stream>>>(p); else yee_volume<S,false,false><<<grid,block,0,e->stream>>>(p); }
+	if (e->tune_stream) launch_volume_ts<S,true>(e, p, grid, block, eps, pml);
+	else                launch_volume_ts<S,false>(e, p, grid, block, eps, pml);
 }
 
 /* Region-specialised launches: the interior runs the lean no-PML instantiation, the PML
@@ -416,15 +431,16 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			CU(cudaEventRecord(e->ev_pool[e->ev_used++], e->stream));
 			e1 = e->ev_pool[e->ev_used++];
 		}
-		p.tile0 = sb.tile0; p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
-		const int nzs = sb.c1 - sb.c0 + 1, gy = div_up(sb.b1 - sb.b0 + 1, 8);
-		const long tiles = (long)sb.ntiles*gy;
-		long want = (16L*e->resident_ctas + tiles - 1)/tiles;      /* >= ~16 waves of CTAs ...       */
-		long maxc = std::max(1, nzs/32);                           /* ... but chunks of >= 32 planes */
+		p.tile0 = sb.tile0; p.ntiles = sb.ntiles; p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
+		const int bx = e->tune_bx, by = e->tune_by;
+		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(sb.ntiles, bx), gy = div_up(sb.b1 - sb.b0 + 1, by);
+		const long tiles = (long)gx*gy;
+		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* >= ~16 waves of CTAs ...       */
+		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* ... but chunks of >= 32 planes */
 		int nchunks = (int)std::max(1L, std::min(want, maxc));
 		p.cchunk = div_up(nzs, nchunks);
 		nchunks = div_up(nzs, p.cchunk);
-		dim3 grid(sb.ntiles, gy, nchunks), block(32, 8, 1);
+		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
 		if (set == ALISB_SET_E) launch_volume_t<1>(e, p, grid, block, eps, sb.pml);
 		else                    launch_volume_t<-1>(e, p, grid, block, false, sb.pml);
 		e->launches++;
@@ -665,32 +681,26 @@ static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t 
 	const size_t n = bcount(B);
 	if (!n) return ALISB_OK;
 	if (arr_offset(e, r, box[0], box[2], box[4]) < 0 || arr_offset(e, r, box[1], box[3], box[5]) < 0) return fail(ALISB_EINVAL, "box outside array");
-	std::vector<float> h(n);
-	if (r.kind == 0) {
-		TRY(need_scratch(e, n));
-		if (write) {
-			to_xfast(host, h.data(), B);
-			CU(cudaMemcpyAsync(e->scratch, h.data(), n*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-			box_scatter<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, e->ny, e->pitch);
-			CU(cudaStreamSynchronize(e->stream));
-		} else {
-			box_gather<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, e->ny, e->pitch);
-			CU(cudaMemcpyAsync(h.data(), e->scratch, n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-			CU(cudaStreamSynchronize(e->stream));
-			to_zfast(h.data(), host, B);
-		}
-		e->launches++;
-		return ALISB_OK;
+	/* strides of the resolved array: element (a,b,c) at c*sC + b*sB + a + off */
+	long long sC, sB, off;
+	switch (r.kind) {
+	case 0:  sB = e->pitch; sC = (long long)(e->ny+2)*e->pitch; off = ALISB_XO; break;
+	case 1:  sB = r.dense.na; sC = (long long)(e->ny+2)*r.dense.na; off = -(long long)r.dense.a0; break;
+	case 2:  sB = e->pitch; sC = (long long)r.dense.nb*e->pitch; off = ALISB_XO - (long long)r.dense.b0*sB; break;
+	case 3:  sB = e->pitch; sC = (long long)(e->ny+2)*e->pitch; off = ALISB_XO - (long long)r.dense.c0*sC; break;
+	default: sB = r.dense.na; sC = (long long)r.dense.nb*r.dense.na; off = -((long long)r.dense.c0*sC + (long long)r.dense.b0*sB + r.dense.a0); break;
 	}
-	/* small auxiliary arrays: row-wise copies */
-	CU(cudaStreamSynchronize(e->stream));
-	for (int c=0; c<B.nc; c++) for (int b=0; b<B.nb; b++) {
-		const long long off = arr_offset(e, r, B.a0, B.b0 + b, B.c0 + c);
-		float *row = &h[((size_t)c*B.nb + b)*B.na];
-		if (write) { for (int a=0; a<B.na; a++) row[a] = host[((size_t)a*B.nb + b)*B.nc + c]; CU(cudaMemcpy(r.p + off, row, B.na*sizeof(float), cudaMemcpyHostToDevice)); }
-		else CU(cudaMemcpy(row, r.p + off, B.na*sizeof(float), cudaMemcpyDeviceToHost));
+	TRY(need_scratch(e, n));
+	if (write) {
+		CU(cudaMemcpyAsync(e->scratch, host, n*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+		box_scatter<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, sC, sB, off);
+		CU(cudaStreamSynchronize(e->stream));
+	} else {
+		box_gather<<<div_up(n, 256), 256, 0, e->stream>>>(r.p, e->scratch, B, sC, sB, off);
+		CU(cudaMemcpyAsync(host, e->scratch, n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+		CU(cudaStreamSynchronize(e->stream));
 	}
-	if (!write) to_zfast(h.data(), host, B);
+	e->launches++;
 	return ALISB_OK;
 }
 extern "C" int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, false); }

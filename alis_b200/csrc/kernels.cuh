@@ -28,7 +28,7 @@ struct VolParams {
 	int slab[3][2][2];            /* [axis][side]{first,last} in array coordinates      */
 	int xbase[2], xpitch[2];      /* x-slab psi arrays: slot = a - xbase, row pitch      */
 	int nx, ny, nz, pitch;
-	int tile0;                    /* first 128-cell x tile of this launch                */
+	int tile0, ntiles;            /* 128-cell x segments [tile0, tile0+ntiles) of this launch */
 	int b_first, b_last;          /* rows updated by this launch                        */
 	int c_first, c_last;          /* planes updated by this launch                      */
 	int cchunk;                   /* planes per z-chunk (grid.z chunks)                  */
@@ -37,6 +37,9 @@ struct VolParams {
 
 static __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4*>(p); }
 static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+/* streaming (evict-first) variants for data that is touched once per pass */
+template <bool STREAM> static __device__ __forceinline__ float4 ld4s(const float *p) { return STREAM ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p); }
+template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, float4 v) { if (STREAM) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v; }
 
 /*
  * Fused Yee curl + CPML volume kernel: reference updateF (update.c:87-125) without the
@@ -52,14 +55,15 @@ static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_ca
  * (the warp above/below in the same CTA loads the same line in the same iteration), the
  * x-neighbour comes from a warp shuffle.
  */
-template <int S, bool EPS, bool PML>
+template <int S, bool EPS, bool PML, bool STREAM>
 __global__ void __launch_bounds__(256)
 yee_volume(const __grid_constant__ VolParams p)
 {
-	const int lane = threadIdx.x;
-	const int a0 = 1 + 4*((blockIdx.x + p.tile0)*32 + lane);
+	const int lane = threadIdx.x & 31;
+	const int seg = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);     /* 128-cell segment within the launch */
+	const int a0 = 1 + 4*((seg + p.tile0)*32 + lane);
 	const int b  = p.b_first + blockIdx.y*blockDim.y + threadIdx.y;
-	if (b > p.b_last) return;                               /* whole warp leaves */
+	if (b > p.b_last || seg >= p.ntiles) return;            /* whole warp leaves */
 	const bool act = a0 <= p.nx;                            /* owns at least one updated cell      */
 	const bool ldg = a0 <= p.nx + 1;                        /* G quad holds data someone needs (ghost a=nx+1) */
 	const bool full = a0 + 3 <= p.nx;
@@ -111,10 +115,10 @@ yee_volume(const __grid_constant__ VolParams p)
 		const size_t o = (size_t)c*p.plane + row;
 		float4 fx = zero4, fy = zero4, fz = zero4, gx = zero4, gy = zero4, gz = zero4, gxn = zero4, gzn = zero4;
 		float4 cx = zero4, cy = zero4, cz = zero4;
-		if (ldg) { gx = ld4(G0 + o); gy = ld4(G1 + o); gz = ld4(G2 + o); }
+		if (ldg) { gx = ld4(G0 + o); gy = ld4s<STREAM>(G1 + o); gz = ld4(G2 + o); }
 		if (act) {
 			gxn = ld4(G0 + o + yn); gzn = ld4(G2 + o + yn);
-			fx = ld4(F0 + o); fy = ld4(F1 + o); fz = ld4(F2 + o);
+			fx = ld4s<STREAM>(F0 + o); fy = ld4s<STREAM>(F1 + o); fz = ld4s<STREAM>(F2 + o);
 			if (EPS) { cx = ld4(p.C[0] + o); cy = ld4(p.C[1] + o); cz = ld4(p.C[2] + o); }
 		}
 		/* x-neighbour element (a0+4 for S=+1, a0-1 for S=-1) from the adjacent lane */
@@ -227,9 +231,9 @@ yee_volume(const __grid_constant__ VolParams p)
 		}
 
 		if (full) {
-			st4(F0 + o, make_float4(Fx[0], Fx[1], Fx[2], Fx[3]));
-			st4(F1 + o, make_float4(Fy[0], Fy[1], Fy[2], Fy[3]));
-			st4(F2 + o, make_float4(Fz[0], Fz[1], Fz[2], Fz[3]));
+			st4s<STREAM>(F0 + o, make_float4(Fx[0], Fx[1], Fx[2], Fx[3]));
+			st4s<STREAM>(F1 + o, make_float4(Fy[0], Fy[1], Fy[2], Fy[3]));
+			st4s<STREAM>(F2 + o, make_float4(Fz[0], Fz[1], Fz[2], Fz[3]));
 		} else if (act) {
 			#pragma unroll
 			for (int e = 0; e < 4; e++) if (a0 + e <= p.nx) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
@@ -362,18 +366,20 @@ __global__ void copy_plane(float *F, float *G, float cosk, float sink, Box B, in
 	} else F[i] = cosk*F[j];
 }
 
-/* gather / scatter a box between a padded device array and a dense x-fastest buffer */
-__global__ void box_gather(const float *A, float *buf, Box B, int ny, int pitch)
+/* gather / scatter a box between any engine array (element (a,b,c) at c*sC + b*sB + a + off) and a
+ * dense buffer in the HOST order (z fastest, reference makeField layout): the transposition is
+ * done here so that the host side is a plain memcpy */
+__global__ void box_gather(const float *A, float *buf, Box B, long long sC, long long sB, long long off)
 {
 	int a, b, c; size_t q;
 	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
-	buf[q] = A[GIDX(a, b, c)];
+	buf[((size_t)(a - B.a0)*B.nb + (b - B.b0))*B.nc + (c - B.c0)] = A[c*sC + b*sB + a + off];
 }
-__global__ void box_scatter(float *A, const float *buf, Box B, int ny, int pitch)
+__global__ void box_scatter(float *A, const float *buf, Box B, long long sC, long long sB, long long off)
 {
 	int a, b, c; size_t q;
 	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
-	A[GIDX(a, b, c)] = buf[q];
+	A[c*sC + b*sB + a + off] = buf[((size_t)(a - B.a0)*B.nb + (b - B.b0))*B.nc + (c - B.c0)];
 }
 
 /* reference phaser.c:83-91: running DFT on one face for all frequencies.

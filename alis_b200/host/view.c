@@ -81,8 +81,6 @@ void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1)
 	pull_box(W, b);
 	memcpy(v->box, b, sizeof b);
 	v->have_box = 1; v->synced = v->version;
-	/* scattered / source-field monitors read the TFSF auxiliary worlds through the same indices */
-	for (tfsf S = W->S; S; S = S->S) alis_view_need_all(S->W);
 }
 
 void alis_view_need_all(world W)
