@@ -20,6 +20,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle_alis.so")
 
 MAXPOLES = 6
 SET_E, SET_H = 0, 1
+PART_ALL, PART_SEND_PLANE, PART_REST = 0, 1, 2
 ARR_FIELD, ARR_INVEPS, ARR_PSI, ARR_ADE_J, ARR_ADE_K, ARR_ADE_FILL = range(6)
 
 f32p = C.POINTER(C.c_float)
@@ -73,6 +74,7 @@ def _declare(lib):
         "alisb_clear_sources": (i, [vp]),
         "alisb_step_E": (i, [vp]),
         "alisb_step_H": (i, [vp]),
+        "alisb_step_part": (i, [vp, i, i]),
         "alisb_run": (i, [vp, i]),
         "alisb_synchronize": (i, [vp]),
         "alisb_get_time": (i, [vp, C.POINTER(u64), C.POINTER(f), C.POINTER(f), C.POINTER(f)]),
@@ -210,6 +212,10 @@ class Engine:
 
     def step_H(self):
         self._ck(self.lib.alisb_step_H(self.h))
+
+    def step_part(self, set_, part):
+        """part: 0 whole pass, 1 only the plane the z-neighbour needs, 2 the rest (see alis_b200.h)"""
+        self._ck(self.lib.alisb_step_part(self.h, set_, part))
 
     def run(self, steps):
         self._ck(self.lib.alisb_run(self.h, steps))

@@ -30,7 +30,7 @@ static int fail(int code, const char *fmt, ...)
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALISB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-struct SubBox { int tile0, ntiles, b0, b1, c0, c1; bool pml; };
+struct SubBox { int tile0, ntiles, b0, b1, c0, c1; int pml; };   /* pml: bit 0/1/2 = may touch x/y/z slabs */
 struct ProfRec { size_t ev; int set, sub; };
 
 struct DispObj {
@@ -74,6 +74,7 @@ struct alisb_engine {
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
 	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
+	int f_lo, f_hi;                    /* plane filter of the current (partial) pass: ops act on c in [f_lo,f_hi] */
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
 	std::vector<ProfRec> prof;         /* one record per profiled volume sub-launch          */
 	float *scratch; size_t scratch_elems;
@@ -94,6 +95,13 @@ extern "C" const char *alisb_backend(void) { return "cuda-sm_100a"; }
 static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1)/b); }
 static inline Box mkbox(const int32_t b[6]) { Box B; B.a0=b[0]; B.b0=b[2]; B.c0=b[4]; B.na=b[1]-b[0]+1; B.nb=b[3]-b[2]+1; B.nc=b[5]-b[4]+1; if (B.na<0) B.na=0; if (B.nb<0) B.nb=0; if (B.nc<0) B.nc=0; return B; }
 static inline size_t bcount(const Box &B) { return (size_t)B.na*B.nb*B.nc; }
+/* clip a box to the plane filter [lo,hi] */
+static inline Box clipc(Box B, int lo, int hi)
+{
+	const int c0 = std::max(B.c0, lo), c1 = std::min(B.c0 + B.nc - 1, hi);
+	B.c0 = c0; B.nc = std::max(0, c1 - c0 + 1);
+	return B;
+}
 
 static int dalloc(float **p, size_t n)
 {
@@ -137,6 +145,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
 	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
+	e->f_lo = 0; e->f_hi = g->nz + 1;
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
 	for (int s=0; s<2; s++) for (int m=0; m<=g->complex_field; m++) for (int c=0; c<3; c++) TRY(dalloc(&e->F[s][m][c], e->elems));
 	for (int s=0; s<2; s++) {
@@ -167,7 +176,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		}
 	}
 	int nb = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,true,false>, 256, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7>, 256, 0));
 	{
 		const char *s;
 		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 16; e->tune_minchunk = 32;
@@ -358,49 +367,71 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 }
 
 /* ---- one pass ------------------------------------------------------------------------- */
-template <int S, bool STREAM>
-static void launch_volume_ts(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, bool pml)
+template <int S, bool EPS>
+static void launch_volume_te(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, int pm)
 {
-	if (eps) { if (pml) yee_volume<S,true,true,STREAM><<<grid,block,0,e->stream>>>(p); else yee_volume<S,true,false,STREAM><<<grid,block,0,e->stream>>>(p); }
-	else     { if (pml) yee_volume<S,false,true,STREAM><<<grid,block,0,e->stream>>>(p); else yee_volume<S,false,false,STREAM><<<grid,block,0,e->stream>>>(p); }
+	switch (pm) {
+	case 0: yee_volume<S,EPS,0><<<grid,block,0,e->stream>>>(p); break;
+	case 1: yee_volume<S,EPS,1><<<grid,block,0,e->stream>>>(p); break;
+	case 2: yee_volume<S,EPS,2><<<grid,block,0,e->stream>>>(p); break;
+	case 3: yee_volume<S,EPS,3><<<grid,block,0,e->stream>>>(p); break;
+	case 4: yee_volume<S,EPS,4><<<grid,block,0,e->stream>>>(p); break;
+	case 5: yee_volume<S,EPS,5><<<grid,block,0,e->stream>>>(p); break;
+	case 6: yee_volume<S,EPS,6><<<grid,block,0,e->stream>>>(p); break;
+	default: yee_volume<S,EPS,7><<<grid,block,0,e->stream>>>(p); break;
+	}
 }
 template <int S>
-static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, bool pml)
+static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm)
 {
-	if (e->tune_stream) launch_volume_ts<S,true>(e, p, grid, block, eps, pml);
-	else                launch_volume_ts<S,false>(e, p, grid, block, eps, pml);
+	if (eps) launch_volume_te<S,true>(e, p, grid, block, pm);
+	else     launch_volume_te<S,false>(e, p, grid, block, pm);
 }
 
-/* Region-specialised launches: the interior runs the lean no-PML instantiation, the PML
- * shell (z slabs, then y slabs of the remaining planes, then the x-edge tiles of what is
- * left) runs the fused CPML instantiation.  Cells are independent within a pass, so the
- * split does not change results.                                                        */
+/* Region-specialised launches.  Per axis the cells split into lo slab / slab-free middle / hi slab
+ * (x in units of 128-cell tiles: tiles that contain slab cells vs. the rest).  Every region runs
+ * the yee_volume instantiation that only carries the PML code (and registers) of the slabs it can
+ * touch: the interior gets the lean PM=0 kernel, the big x-edge columns PM=1, the z-slab planes
+ * away from the x/y edges PM=4, the thin edge/corner regions the full variants.  Cells are
+ * independent within a pass, so the split cannot change results.                          */
 static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 {
 	L.clear();
 	const int ntile = div_up(e->nx, 128);
-	int lo[3], hi[3];                 /* interior (slab-free) range per axis in array coords */
+	int lo[3], hi[3];                 /* slab-free range per axis in array coords */
 	const int n[3] = {e->nx, e->ny, e->nz};
 	for (int ax=0; ax<3; ax++) {
 		lo[ax] = 1; hi[ax] = n[ax];
 		if (e->g.pml[set][ax][0][0] <= e->g.pml[set][ax][0][1]) lo[ax] = e->g.pml[set][ax][0][1] + 1;
 		if (e->g.pml[set][ax][1][0] <= e->g.pml[set][ax][1][1]) hi[ax] = e->g.pml[set][ax][1][0] - 1;
+		if (lo[ax] > hi[ax] + 1) lo[ax] = hi[ax] + 1;
 	}
-	/* (H min-side slabs start at cell 2: cell 1 simply rides along in the slab-side launch) */
-	if (lo[2] > 1)      L.push_back({0, ntile, 1, e->ny, 1, std::min(lo[2]-1, e->nz), true});
-	if (hi[2] < e->nz && hi[2] + 1 >= lo[2]) L.push_back({0, ntile, 1, e->ny, hi[2]+1, e->nz, true});
-	if (lo[2] > hi[2]) return;
-	if (lo[1] > 1)      L.push_back({0, ntile, 1, std::min(lo[1]-1, e->ny), lo[2], hi[2], true});
-	if (hi[1] < e->ny && hi[1] + 1 >= lo[1]) L.push_back({0, ntile, hi[1]+1, e->ny, lo[2], hi[2], true});
-	if (lo[1] > hi[1]) return;
-	/* tiles [t0,t1] are free of x-slab cells */
+	/* x: tiles [0,t0) hold min-slab cells, [t1+1,ntile) max-slab cells, [t0,t1] none */
 	int t0 = 0, t1 = ntile - 1;
-	if (lo[0] > 1)      t0 = std::min((lo[0] - 2)/128 + 1, ntile);   /* tiles holding cells 1..lo-1  */
-	if (hi[0] < e->nx)  t1 = hi[0]/128 - 1;                          /* tiles holding cells hi+1..nx */
+	if (lo[0] > 1)      t0 = std::min((lo[0] - 2)/128 + 1, ntile);
+	if (hi[0] < e->nx)  t1 = hi[0]/128 - 1;
 	if (t1 < t0 - 1) t1 = t0 - 1;
-	if (t0 > 0)         L.push_back({0, t0, lo[1], hi[1], lo[2], hi[2], true});
-	if (t1 < ntile - 1) L.push_back({t1 + 1, ntile - (t1 + 1), lo[1], hi[1], lo[2], hi[2], true});
-	if (t0 <= t1)       L.push_back({t0, t1 - t0 + 1, lo[1], hi[1], lo[2], hi[2], false});
+	struct Range { int a, b, pm; };
+	std::vector<Range> X, Y, Z;
+	if (t0 > 0)          X.push_back({0, t0 - 1, 1});
+	if (t0 <= t1)        X.push_back({t0, t1, 0});
+	if (t1 < ntile - 1)  X.push_back({t1 + 1, ntile - 1, 1});
+	if (lo[1] > 1)       Y.push_back({1, lo[1] - 1, 2});
+	if (lo[1] <= hi[1])  Y.push_back({lo[1], hi[1], 0});
+	if (hi[1] < e->ny)   Y.push_back({hi[1] + 1, e->ny, 2});
+	if (lo[2] > 1)       Z.push_back({1, lo[2] - 1, 4});
+	if (lo[2] <= hi[2])  Z.push_back({lo[2], hi[2], 0});
+	if (hi[2] < e->nz)   Z.push_back({hi[2] + 1, e->nz, 4});
+	for (const Range &z : Z) for (const Range &y : Y) {
+		if (y.pm) {      /* thin y-slab rows: one launch over all tiles with the x code included */
+			L.push_back({0, ntile, y.a, y.b, z.a, z.b, (X.size() > 1 || (X.size() == 1 && X[0].pm) ? 1 : 0) | y.pm | z.pm});
+			continue;
+		}
+		for (const Range &x : X) L.push_back({x.a, x.b - x.a + 1, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm});
+	}
+	/* largest region first (it is also the dominant kernel reported by alisb_profile_dominant) */
+	std::stable_sort(L.begin(), L.end(), [](const SubBox &p, const SubBox &q) {
+		return (double)p.ntiles*(p.b1-p.b0+1)*(p.c1-p.c0+1) > (double)q.ntiles*(q.b1-q.b0+1)*(q.c1-q.c0+1); });
 }
 
 static int launch_volume(alisb_engine *e, int set, int m)
@@ -422,8 +453,11 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	if (e->plan[set].empty()) plan_volume(e, set, e->plan[set]);
 
 	int sub = -1;
-	for (const SubBox &sb : e->plan[set]) {
+	for (const SubBox &sb0 : e->plan[set]) {
 		sub++;
+		SubBox sb = sb0;
+		sb.c0 = std::max(sb.c0, e->f_lo); sb.c1 = std::min(sb.c1, e->f_hi);
+		if (sb.c0 > sb.c1) continue;
 		cudaEvent_t e1 = 0;
 		if (e->profiling) {
 			if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
@@ -460,7 +494,7 @@ static void fill_ade(alisb_engine *e, DispObj *o, int m, AdeParams &p)
 	memcpy(p.JJ, o->d.JJ, sizeof p.JJ); memcpy(p.JK, o->d.JK, sizeof p.JK); memcpy(p.JE, o->d.JE, sizeof p.JE);
 	memcpy(p.KJ, o->d.KJ, sizeof p.KJ); memcpy(p.KK, o->d.KK, sizeof p.KK); memcpy(p.KE, o->d.KE, sizeof p.KE);
 	p.nj = o->d.nj; p.nk = o->d.nk; p.lossy = (o->d.a[0] || o->d.a[1] || o->d.a[2]) ? 1 : 0;
-	p.full = o->full; p.upd = o->upd; p.ny = e->ny; p.pitch = e->pitch;
+	p.full = o->full; p.upd = clipc(o->upd, e->f_lo, e->f_hi); p.ny = e->ny; p.pitch = e->pitch;
 }
 
 static int ade_pre(alisb_engine *e, int m)
@@ -468,13 +502,13 @@ static int ade_pre(alisb_engine *e, int m)
 	AdeParams p;
 	for (DispObj *o : e->obj) {
 		fill_ade(e, o, m, p);
-		const size_t n = bcount(o->upd);
+		const size_t n = bcount(p.upd);
 		if (!n || !p.lossy) continue;
 		ade_loss<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
 	}
 	for (DispObj *o : e->obj) {
 		fill_ade(e, o, m, p);
-		const size_t n = bcount(o->upd);
+		const size_t n = bcount(p.upd);
 		if (!n || !p.nk) continue;
 		ade_subtract<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
 	}
@@ -487,7 +521,7 @@ static int ade_post(alisb_engine *e, int m)
 	AdeParams p;
 	for (DispObj *o : e->obj) {
 		fill_ade(e, o, m, p);
-		const size_t n = bcount(o->upd);
+		const size_t n = bcount(p.upd);
 		if (!n || !p.nk) continue;
 		ade_currents<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
 	}
@@ -499,6 +533,9 @@ static int apply_sources(alisb_engine *e, int set, float t)
 {
 	for (SrcObj *s : e->src[set]) {
 		if (!(e->step < s->d.n_active) || !s->cnt) continue;
+		const Box B = clipc(s->B, e->f_lo, e->f_hi);
+		const size_t nb = bcount(B);
+		if (!nb) continue;
 		float *F = e->F[set][s->d.m][s->d.comp];
 		if (!s->hPha.empty()) {
 			const int r = s->slot; s->slot = (s->slot + 1) % SRC_RING;
@@ -507,11 +544,11 @@ static int apply_sources(alisb_engine *e, int set, float t)
 			for (size_t q=0; q<s->cnt; q++)
 				h[q] = (s->hAmp.empty() ? s->d.amplitude : s->hAmp[q]) * s->d.waveform(s->d.user, t, s->hPha[q]);
 			CU(cudaMemcpyAsync(s->dvals[r], h, s->cnt*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-			source_add<<<div_up(s->cnt, 256), 256, 0, e->stream>>>(F, s->B, e->ny, e->pitch, s->dvals[r], 0, 0.f, 0.f);
+			source_add<<<div_up(nb, 256), 256, 0, e->stream>>>(F, B, s->B, e->ny, e->pitch, s->dvals[r], 0, 0.f, 0.f);
 			CU(cudaEventRecord(s->ev[r], e->stream));
 		} else {
 			const float f = s->d.waveform(s->d.user, t, s->d.phase);
-			source_add<<<div_up(s->cnt, 256), 256, 0, e->stream>>>(F, s->B, e->ny, e->pitch, 0, s->dAmp, s->d.amplitude, f);
+			source_add<<<div_up(nb, 256), 256, 0, e->stream>>>(F, B, s->B, e->ny, e->pitch, 0, s->dAmp, s->d.amplitude, f);
 		}
 		e->launches++;
 	}
@@ -519,16 +556,16 @@ static int apply_sources(alisb_engine *e, int set, float t)
 	return ALISB_OK;
 }
 
-static int apply_tfsf(alisb_engine *e, int set)
+static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 {
 	for (TfsfObj *t : e->tf) {
 		alisb_engine *x = t->d.aux;
 		if (x->stream != e->stream && !x->own_stream) return fail(ALISB_ESTATE, "aux engine on a foreign stream");
 		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; }
-		TRY(set == ALISB_SET_E ? alisb_step_E(x) : alisb_step_H(x));
+		if (step_aux) TRY(set == ALISB_SET_E ? alisb_step_E(x) : alisb_step_H(x));
 		const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
 		for (int m=0; m<=e->g.complex_field; m++) for (const alisb_strip &s : L) {
-			Box B = mkbox(s.box);
+			Box B = clipc(mkbox(s.box), e->f_lo, e->f_hi);
 			const size_t n = bcount(B);
 			if (!n) continue;
 			const float *C = s.use_eps ? e->eps[s.comp] : 0;
@@ -545,7 +582,7 @@ static int apply_tfsf(alisb_engine *e, int set)
 static int apply_copies(alisb_engine *e, int set)
 {
 	for (const alisb_copy &k : e->copies[set]) {
-		Box B = mkbox(k.box);
+		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
 		const size_t n = bcount(B);
 		if (!n) continue;
 		float *F = e->F[k.set][0][k.comp], *G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
@@ -556,33 +593,37 @@ static int apply_copies(alisb_engine *e, int set)
 	return ALISB_OK;
 }
 
-extern "C" int alisb_step_E(alisb_engine *e)
+extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 {
+	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
 	DEV(e);
+	const int send = set == ALISB_SET_E ? e->nz : 1;          /* the plane the z-neighbour needs */
+	e->f_lo = 0; e->f_hi = e->nz + 1;
+	if (part == ALISB_PART_SEND_PLANE) e->f_lo = e->f_hi = send;
+	if (part == ALISB_PART_REST) { if (set == ALISB_SET_E) e->f_hi = send - 1; else e->f_lo = send + 1; }
+	const bool first = part != ALISB_PART_REST, last = part != ALISB_PART_SEND_PLANE;
 	for (int m=0; m<=e->g.complex_field; m++) {
-		if (!e->obj.empty()) TRY(ade_pre(e, m));
-		TRY(launch_volume(e, ALISB_SET_E, m));
+		if (set == ALISB_SET_E) {
+			if (!e->obj.empty()) TRY(ade_pre(e, m));
+			TRY(launch_volume(e, ALISB_SET_E, m));
+		} else {
+			TRY(launch_volume(e, ALISB_SET_H, m));
+			if (!e->obj.empty()) TRY(ade_post(e, m));
+		}
 	}
-	TRY(apply_tfsf(e, ALISB_SET_E));
-	TRY(apply_sources(e, ALISB_SET_E, e->tH));
-	TRY(apply_copies(e, ALISB_SET_E));
-	e->t = e->tE = ++e->step * e->g.dt;                 /* update.c:298 */
+	TRY(apply_tfsf(e, set, first));
+	TRY(apply_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
+	TRY(apply_copies(e, set));
+	e->f_lo = 0; e->f_hi = e->nz + 1;
+	if (last) {
+		if (set == ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;       /* update.c:298 */
+		else e->t = e->tH = e->tE + 0.5 * e->g.dt;                        /* update.c:340 */
+	}
 	return ALISB_OK;
 }
 
-extern "C" int alisb_step_H(alisb_engine *e)
-{
-	DEV(e);
-	for (int m=0; m<=e->g.complex_field; m++) {
-		TRY(launch_volume(e, ALISB_SET_H, m));
-		if (!e->obj.empty()) TRY(ade_post(e, m));
-	}
-	TRY(apply_tfsf(e, ALISB_SET_H));
-	TRY(apply_sources(e, ALISB_SET_H, e->tE));
-	TRY(apply_copies(e, ALISB_SET_H));
-	e->t = e->tH = e->tE + 0.5 * e->g.dt;               /* update.c:340 */
-	return ALISB_OK;
-}
+extern "C" int alisb_step_E(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_E, ALISB_PART_ALL); }
+extern "C" int alisb_step_H(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_H, ALISB_PART_ALL); }
 
 extern "C" int alisb_run(alisb_engine *e, int steps)
 {

@@ -55,8 +55,8 @@ template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, flo
  * (the warp above/below in the same CTA loads the same line in the same iteration), the
  * x-neighbour comes from a warp shuffle.
  */
-template <int S, bool EPS, bool PML, bool STREAM>
-__global__ void __launch_bounds__(256)
+template <int S, bool EPS, int PM>          /* PM: bit 0/1/2 = this launch may touch x / y / z PML slabs */
+__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
 yee_volume(const __grid_constant__ VolParams p)
 {
 	const int lane = threadIdx.x & 31;
@@ -89,10 +89,13 @@ yee_volume(const __grid_constant__ VolParams p)
 	float yP = 0.f, yP1 = 0.f, yP2 = 0.f;
 	float4 xP = zero4, xP1 = zero4, xP2 = zero4;
 	unsigned xmask = 0;
-	if (PML) {
+	constexpr bool STREAM = false;              /* evict-first hints measured slower (profiles/sweep_r01) */
+	if (PM & 2) {
 		if (b >= p.slab[1][0][0] && b <= p.slab[1][0][1]) ys = 0;
 		else if (b >= p.slab[1][1][0] && b <= p.slab[1][1][1]) ys = 1;
 		if (ys >= 0) { yP = __ldg(p.P[1] + b); yP1 = __ldg(p.P1[1] + b); yP2 = __ldg(p.P2[1] + b); }
+	}
+	if (PM & 1) {
 		if (act) {
 			if (a0 + 3 >= p.slab[0][0][0] && a0 <= p.slab[0][0][1]) xs = 0;
 			else if (a0 + 3 >= p.slab[0][1][0] && a0 <= p.slab[0][1][1]) xs = 1;
@@ -157,16 +160,18 @@ yee_volume(const __grid_constant__ VolParams p)
 			else     { Fx[e] += ux;       Fy[e] += uy;       Fz[e] += uz; }
 		}
 
-		if (PML) {
+		if (PM) {
 			int zs = -1;
-			if (c >= p.slab[2][0][0] && c <= p.slab[2][0][1]) zs = 0;
-			else if (c >= p.slab[2][1][0] && c <= p.slab[2][1][1]) zs = 1;
+			if (PM & 4) {
+				if (c >= p.slab[2][0][0] && c <= p.slab[2][0][1]) zs = 0;
+				else if (c >= p.slab[2][1][0] && c <= p.slab[2][1][1]) zs = 1;
+			}
 			if (act && (xs >= 0 || ys >= 0 || zs >= 0)) {
 				/* psi contributions; slab order x-min,y-min,z-min,x-max,y-max,z-max (update.c:119-124) */
 				float xq0[4] = {0,0,0,0}, xq1[4] = {0,0,0,0};   /* x slab: psi0 -> Fy, psi1 -> Fz */
 				float yq0[4] = {0,0,0,0}, yq1[4] = {0,0,0,0};   /* y slab: psi0 -> Fz, psi1 -> Fx */
 				float zq0[4] = {0,0,0,0}, zq1[4] = {0,0,0,0};   /* z slab: psi0 -> Fx, psi1 -> Fy */
-				if (xs >= 0) {
+				if ((PM & 1) && xs >= 0) {
 					const size_t po = ((size_t)c*(p.ny + 2) + b)*p.xpitch[xs] + (a0 - p.xbase[xs]);
 					float *q0p = p.psi[0][xs][0] + po, *q1p = p.psi[0][xs][1] + po;
 					float4 q0 = ld4(q0p), q1 = ld4(q1p);
@@ -181,7 +186,7 @@ yee_volume(const __grid_constant__ VolParams p)
 					st4(q0p, make_float4(v0[0], v0[1], v0[2], v0[3]));
 					st4(q1p, make_float4(v1[0], v1[1], v1[2], v1[3]));
 				}
-				if (ys >= 0) {
+				if ((PM & 2) && ys >= 0) {
 					const int nys = p.slab[1][ys][1] - p.slab[1][ys][0] + 1;
 					const size_t po = ((size_t)c*nys + (b - p.slab[1][ys][0]))*p.pitch + ALISB_XO + a0;
 					float *q0p = p.psi[1][ys][0] + po, *q1p = p.psi[1][ys][1] + po;
@@ -196,7 +201,7 @@ yee_volume(const __grid_constant__ VolParams p)
 					st4(q0p, make_float4(v0[0], v0[1], v0[2], v0[3]));
 					st4(q1p, make_float4(v1[0], v1[1], v1[2], v1[3]));
 				}
-				if (zs >= 0) {
+				if ((PM & 4) && zs >= 0) {
 					const float zP = __ldg(p.P[2] + c), zP1 = __ldg(p.P1[2] + c), zP2 = __ldg(p.P2[2] + c);
 					const size_t po = ((size_t)(c - p.slab[2][zs][0])*(p.ny + 2) + b)*p.pitch + ALISB_XO + a0;
 					float *q0p = p.psi[2][zs][0] + po, *q1p = p.psi[2][zs][1] + po;
@@ -216,13 +221,13 @@ yee_volume(const __grid_constant__ VolParams p)
 					const bool xin = (xmask >> e) & 1u;
 					#pragma unroll
 					for (int side = 0; side < 2; side++) {
-						if (xs == side && xin) {
+						if ((PM & 1) && xs == side && xin) {
 							if (EPS) { Fy[e] += xq0[e]*Cy[e]; Fz[e] += xq1[e]*Cz[e]; } else { Fy[e] += xq0[e]; Fz[e] += xq1[e]; }
 						}
-						if (ys == side) {
+						if ((PM & 2) && ys == side) {
 							if (EPS) { Fz[e] += yq0[e]*Cz[e]; Fx[e] += yq1[e]*Cx[e]; } else { Fz[e] += yq0[e]; Fx[e] += yq1[e]; }
 						}
-						if (zs == side) {
+						if ((PM & 4) && zs == side) {
 							if (EPS) { Fx[e] += zq0[e]*Cx[e]; Fy[e] += zq1[e]*Cy[e]; } else { Fx[e] += zq0[e]; Fy[e] += zq1[e]; }
 						}
 					}
@@ -328,11 +333,12 @@ __global__ void ade_currents(const __grid_constant__ AdeParams p)
 
 /* reference update.c:161-179 (updateS).  vals != 0: per-cell products Amplitude*wave(t,Phase)
  * evaluated on the host; else amp[q]*f or amplitude*f with the host-evaluated scalar f.   */
-__global__ void source_add(float *F, Box B, int ny, int pitch, const float *vals, const float *amp, float amplitude, float f)
+__global__ void source_add(float *F, Box B, Box full, int ny, int pitch, const float *vals, const float *amp, float amplitude, float f)
 {
 	int a, b, c; size_t q;
 	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
 	const size_t i = GIDX(a, b, c);
+	q = ((size_t)(c - full.c0)*full.nb + (b - full.b0))*full.na + (a - full.a0);     /* index into the source's own arrays */
 	float v;
 	if (vals) v = vals[q];
 	else v = (amp ? amp[q] : amplitude) * f;

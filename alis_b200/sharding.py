@@ -38,8 +38,9 @@ def _as_tensor(ptr, nbytes, cuda):
 class SlabRunner:
     """Steps one z-slab engine and exchanges halos with its neighbours."""
 
-    def __init__(self, engine: capi.Engine, rank, world, cuda, complex_field=0):
+    def __init__(self, engine: capi.Engine, rank, world, cuda, complex_field=0, overlap=True):
         self.e, self.rank, self.world, self.cuda = engine, rank, world, cuda
+        self.overlap, self.pending_H = overlap, None
         self.ncf = complex_field + 1
         self.send, self.recv = {}, {}
         for s in range(2):
@@ -52,9 +53,9 @@ class SlabRunner:
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self.exchanged_bytes = 0
 
-    def exchange(self, set_):
-        if self.world == 1:
-            return
+    def _post(self, set_):
+        """post the send of my plane and the receive of the neighbour's plane for field set `set_`;
+        returns the NCCL/gloo work handles (not waited for)"""
         # E planes travel up (to rank+1), H planes travel down (to rank-1)
         dst = self.rank + 1 if set_ == capi.SET_E else self.rank - 1
         src = self.rank - 1 if set_ == capi.SET_E else self.rank + 1
@@ -68,18 +69,62 @@ class SlabRunner:
                     self.exchanged_bytes += self.send[(set_, m, comp)].numel() * 4
                 if 0 <= src < self.world:
                     ops.append(dist.P2POp(dist.irecv, self.recv[(set_, m, comp)], src))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if 0 <= src < self.world:
+        works = dist.batch_isend_irecv(ops) if ops else []
+        return works, (0 <= src < self.world)
+
+    def _finish(self, set_, pending):
+        works, has_src = pending
+        for w in works:
+            w.wait()                      # orders the engine's stream after the transfer (no host sync on CUDA)
+        if has_src:
             self.e.halo_unpack(set_)
 
+    def exchange(self, set_):
+        if self.world > 1:
+            self._finish(set_, self._post(set_))
+
     def step(self):
-        self.e.step_E()
-        self.exchange(capi.SET_E)
-        self.e.step_H()
-        self.exchange(capi.SET_H)
+        """one full step; with overlap=True the plane a neighbour needs is computed first and travels
+        while the rest of the pass runs (the next pass waits for it just before its own send plane)"""
+        if self.world == 1:
+            self.e.step_E()
+            self.e.step_H()
+            return
+        if not self.overlap:
+            self.e.step_E()
+            self.exchange(capi.SET_E)
+            self.e.step_H()
+            self.exchange(capi.SET_H)
+            return
+        up, down = self.rank + 1 < self.world, self.rank > 0
+        # E pass: its top plane needs the H halo posted in the previous H pass
+        if self.pending_H is not None:
+            self._finish(capi.SET_H, self.pending_H)
+            self.pending_H = None
+        if up:
+            self.e.step_part(capi.SET_E, capi.PART_SEND_PLANE)
+            pending_E = self._post(capi.SET_E)
+            self.e.step_part(capi.SET_E, capi.PART_REST)
+        else:
+            pending_E = self._post(capi.SET_E)           # only receives from below
+            self.e.step_E()
+        # H pass: its bottom plane needs the E halo that is in flight
+        self._finish(capi.SET_E, pending_E)
+        if down:
+            self.e.step_part(capi.SET_H, capi.PART_SEND_PLANE)
+            self.pending_H = self._post(capi.SET_H)
+            self.e.step_part(capi.SET_H, capi.PART_REST)
+        else:
+            self.pending_H = self._post(capi.SET_H)      # only receives from above
+            self.e.step_H()
+
+    def flush(self):
+        """complete the halo transfer still in flight (call before reading fields)"""
+        if self.pending_H is not None:
+            self._finish(capi.SET_H, self.pending_H)
+            self.pending_H = None
 
     def run(self, steps):
         for _ in range(steps):
             self.step()
+        self.flush()

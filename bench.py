@@ -177,6 +177,7 @@ def ours(args):
     ev0.record()
     for _ in range(args.steps):
         runner.step()
+    runner.flush()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -199,6 +200,7 @@ def ours(args):
         acc = 0.0
         for _ in range(args.steps):
             runner.step()
+            runner.flush()
             acc += float(eng.read_box(capi.ARR_FIELD, [0, 2, 0], pbox)[0, 0, 0])   # get(W, Ez, ...): 4 B D2H, syncs
         barrier()
         dt = time.perf_counter() - t0

@@ -165,6 +165,13 @@ int  alisb_clear_sources(alisb_engine *e);       /* removeSources: sources + tfs
 int  alisb_step_E(alisb_engine *e);              /* updateE, update.c:275-299                 */
 int  alisb_step_H(alisb_engine *e);              /* updateH, update.c:302-341                 */
 int  alisb_run(alisb_engine *e, int steps);      /* steps x (E then H), no host sync between  */
+/* A pass split in two for communication/computation overlap (multi-GPU):
+ *   ALISB_PART_SEND_PLANE  everything of the pass that lands in the plane the neighbour needs
+ *                          (E: c = nz, H: c = 1): volume update, ADE, TFSF, sources, x/y copies
+ *   ALISB_PART_REST        the rest of the pass (and the time bookkeeping)
+ * SEND_PLANE followed by REST is identical to alisb_step_E / alisb_step_H (= ALISB_PART_ALL). */
+enum { ALISB_PART_ALL = 0, ALISB_PART_SEND_PLANE = 1, ALISB_PART_REST = 2 };
+int  alisb_step_part(alisb_engine *e, int set, int part);
 int  alisb_synchronize(alisb_engine *e);
 int  alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH);
 int  alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH);

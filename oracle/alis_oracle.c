@@ -66,6 +66,7 @@ struct alisb_engine {
 	uint64_t step; float t, tE, tH;
 	float *halo_send[2][2][2], *halo_recv[2][2][2];   /* [set][m][comp x/y] */
 	uint64_t launches;
+	int f_lo, f_hi;                       /* plane filter of the current (partial) pass */
 };
 
 struct alisb_phaser {
@@ -116,9 +117,13 @@ int alisb_create(const alisb_grid *g, alisb_engine **out)
 		e->halo_send[s][m][c] = calloc(plane, sizeof(float));
 		e->halo_recv[s][m][c] = calloc(plane, sizeof(float));
 	}
+	e->f_lo = 0; e->f_hi = g->nz + 1;
 	*out = e;
 	return ALISB_OK;
 }
+
+#define CLO(e,c) ((c) < (e)->f_lo ? (e)->f_lo : (c))
+#define CHI(e,c) ((c) > (e)->f_hi ? (e)->f_hi : (c))
 
 static void free_src(srcobj *s) { if (s) { free(s->Amp); free(s->Pha); free(s); } }
 
@@ -269,7 +274,7 @@ static void psi_slab(alisb_engine *e, int set, int m, int ax, int sd, int Alt)
 	const long off = (long)IDX(e,1,1,1) - (long)IDX(e,1-d[0],1-d[1],1-d[2]);   /* index shift of +Alt along ax */
 	#pragma omp parallel for collapse(2)
 	for (int a=B0->bx.lo[0]; a<=B0->bx.hi[0]; a++) for (int b=B0->bx.lo[1]; b<=B0->bx.hi[1]; b++) {
-		for (int c=B0->bx.lo[2]; c<=B0->bx.hi[2]; c++) {
+		for (int c=CLO(e,B0->bx.lo[2]); c<=CHI(e,B0->bx.hi[2]); c++) {
 			const int q = ax==0 ? a : ax==1 ? b : c;
 			const size_t i = IDX(e,a,b,c), p = bidx(B0,a,b,c);
 			float v0 = B0->v[p] = P[q]*B0->v[p] + Pa[q]*(G2[i] - G2[i+off]);
@@ -297,7 +302,7 @@ static void update_F(alisb_engine *e, int set, int m)
 			if (!(o->a[0] || o->a[1] || o->a[2])) continue;
 			const int a0=o->bx.lo[0]<1?1:o->bx.lo[0], a1=o->bx.hi[0]>nx?nx:o->bx.hi[0];
 			const int b0=o->bx.lo[1]<1?1:o->bx.lo[1], b1=o->bx.hi[1]>ny?ny:o->bx.hi[1];
-			const int c0=o->bx.lo[2]<1?1:o->bx.lo[2], c1=o->bx.hi[2]>nz?nz:o->bx.hi[2];
+			const int c0=CLO(e,o->bx.lo[2]<1?1:o->bx.lo[2]), c1=CHI(e,o->bx.hi[2]>nz?nz:o->bx.hi[2]);
 			#pragma omp parallel for collapse(2)
 			for (int a=a0; a<=a1; a++) for (int b=b0; b<=b1; b++) for (int c=c0; c<=c1; c++) {
 				const size_t i=IDX(e,a,b,c), p=bidx(&o->fill[0],a,b,c);
@@ -311,7 +316,7 @@ static void update_F(alisb_engine *e, int set, int m)
 			dispobj *o = e->obj[n];
 			const int a0=o->bx.lo[0]<1?1:o->bx.lo[0], a1=o->bx.hi[0]>nx?nx:o->bx.hi[0];
 			const int b0=o->bx.lo[1]<1?1:o->bx.lo[1], b1=o->bx.hi[1]>ny?ny:o->bx.hi[1];
-			const int c0=o->bx.lo[2]<1?1:o->bx.lo[2], c1=o->bx.hi[2]>nz?nz:o->bx.hi[2];
+			const int c0=CLO(e,o->bx.lo[2]<1?1:o->bx.lo[2]), c1=CHI(e,o->bx.hi[2]>nz?nz:o->bx.hi[2]);
 			for (int p=0; p<o->nk; p++) {
 				const float *Jx=o->J[m][p][0].v, *Jy=o->J[m][p][1].v, *Jz=o->J[m][p][2].v;
 				#pragma omp parallel for collapse(2)
@@ -327,7 +332,7 @@ static void update_F(alisb_engine *e, int set, int m)
 	const float *Cx = set==ALISB_SET_E ? e->eps[0] : 0, *Cy = set==ALISB_SET_E ? e->eps[1] : 0, *Cz = set==ALISB_SET_E ? e->eps[2] : 0;
 	if (Cx && Cy && Cz) {
 		#pragma omp parallel for collapse(2)
-		for (int a=1; a<=nx; a++) for (int b=1; b<=ny; b++) for (int c=1; c<=nz; c++) {
+		for (int a=1; a<=nx; a++) for (int b=1; b<=ny; b++) for (int c=CLO(e,1); c<=CHI(e,nz); c++) {
 			const size_t i = IDX(e,a,b,c);
 			Fx[i] += (dtdz[c]*(Gy[i]-Gy[i+sc]) + dtdy[b]*(Gz[i+sb]-Gz[i])) * Cx[i];
 			Fy[i] += (dtdx[a]*(Gz[i]-Gz[i+sa]) + dtdz[c]*(Gx[i+sc]-Gx[i])) * Cy[i];
@@ -335,7 +340,7 @@ static void update_F(alisb_engine *e, int set, int m)
 		}
 	} else {
 		#pragma omp parallel for collapse(2)
-		for (int a=1; a<=nx; a++) for (int b=1; b<=ny; b++) for (int c=1; c<=nz; c++) {
+		for (int a=1; a<=nx; a++) for (int b=1; b<=ny; b++) for (int c=CLO(e,1); c<=CHI(e,nz); c++) {
 			const size_t i = IDX(e,a,b,c);
 			Fx[i] += (dtdz[c]*(Gy[i]-Gy[i+sc]) + dtdy[b]*(Gz[i+sb]-Gz[i]));
 			Fy[i] += (dtdx[a]*(Gz[i]-Gz[i+sa]) + dtdz[c]*(Gx[i+sc]-Gx[i]));
@@ -354,7 +359,7 @@ static void update_J(alisb_engine *e, int m)
 		dispobj *o = e->obj[n];
 		const int a0=o->bx.lo[0]<1?1:o->bx.lo[0], a1=o->bx.hi[0]>nx?nx:o->bx.hi[0];
 		const int b0=o->bx.lo[1]<1?1:o->bx.lo[1], b1=o->bx.hi[1]>ny?ny:o->bx.hi[1];
-		const int c0=o->bx.lo[2]<1?1:o->bx.lo[2], c1=o->bx.hi[2]>nz?nz:o->bx.hi[2];
+		const int c0=CLO(e,o->bx.lo[2]<1?1:o->bx.lo[2]), c1=CHI(e,o->bx.hi[2]>nz?nz:o->bx.hi[2]);
 		for (int p=0; p<o->nk; p++) for (int k=0; k<3; k++) {
 			const float *F = e->F[ALISB_SET_E][m][k], *fl = o->fill[k].v;
 			float *J = o->J[m][p][k].v, *K = o->K[m][p][k].v;
@@ -386,24 +391,25 @@ static void apply_sources(alisb_engine *e, int set, float t)
 		float *F = e->F[set][s->d.m][s->d.comp];
 		const int32_t *bx = s->d.box;
 		size_t q = 0;
+		if (CLO(e,bx[4]) > CHI(e,bx[5])) continue;
 		if (s->Pha) {
 			for (int a=bx[0]; a<=bx[1]; a++) for (int b=bx[2]; b<=bx[3]; b++) for (int c=bx[4]; c<=bx[5]; c++, q++)
-				F[IDX(e,a,b,c)] += (s->Amp ? s->Amp[q] : s->d.amplitude) * s->d.waveform(s->d.user, t, s->Pha[q]);
+				if (c >= e->f_lo && c <= e->f_hi) F[IDX(e,a,b,c)] += (s->Amp ? s->Amp[q] : s->d.amplitude) * s->d.waveform(s->d.user, t, s->Pha[q]);
 		} else {
 			const float f = s->d.waveform(s->d.user, t, s->d.phase);
 			for (int a=bx[0]; a<=bx[1]; a++) for (int b=bx[2]; b<=bx[3]; b++) for (int c=bx[4]; c<=bx[5]; c++, q++)
-				F[IDX(e,a,b,c)] += (s->Amp ? s->Amp[q] : s->d.amplitude) * f;
+				if (c >= e->f_lo && c <= e->f_hi) F[IDX(e,a,b,c)] += (s->Amp ? s->Amp[q] : s->d.amplitude) * f;
 		}
 	}
 }
 
 /* reference update.c:194-272 (update, updateTFSFE/H) */
-static void apply_tfsf(alisb_engine *e, int set)
+static void apply_tfsf(alisb_engine *e, int set, int step_aux)
 {
 	for (int n=0; n<e->ntfsf; n++) {
 		tfsfobj *t = e->tf[n];
 		alisb_engine *x = t->d.aux;
-		if (set==ALISB_SET_E) alisb_step_E(x); else alisb_step_H(x);
+		if (step_aux) { if (set==ALISB_SET_E) alisb_step_E(x); else alisb_step_H(x); }
 		const alisb_strip *S = set==ALISB_SET_E ? t->sE : t->sH;
 		const int ns = set==ALISB_SET_E ? t->d.n_strips_E : t->d.n_strips_H;
 		for (int m=0; m<=e->g.complex_field; m++) for (int q=0; q<ns; q++) {
@@ -412,7 +418,7 @@ static void apply_tfsf(alisb_engine *e, int set)
 			const float *G = x->F[1-set][m][s->aux_comp];
 			const float *C = s->use_eps ? e->eps[s->comp] : 0;
 			const int ca = t->d.clamp[1-set][s->aux_comp][0], cb = t->d.clamp[1-set][s->aux_comp][1];
-			for (int a=s->box[0]; a<=s->box[1]; a++) for (int b=s->box[2]; b<=s->box[3]; b++) for (int c=s->box[4]; c<=s->box[5]; c++) {
+			for (int a=s->box[0]; a<=s->box[1]; a++) for (int b=s->box[2]; b<=s->box[3]; b++) for (int c=CLO(e,s->box[4]); c<=CHI(e,s->box[5]); c++) {
 				int xa = a + s->alt[0] + t->d.offset[0], xb = b + s->alt[1] + t->d.offset[1], xc = c + s->alt[2] + t->d.offset[2];
 				if (xa > ca) xa = ca;
 				if (xb > cb) xb = cb;
@@ -430,7 +436,7 @@ static void apply_copies(alisb_engine *e, int set)
 	for (int n=0; n<e->ncopy[set]; n++) {
 		const alisb_copy *k = &e->copy[set][n];
 		float *F = e->F[k->set][0][k->comp], *G = e->g.complex_field ? e->F[k->set][1][k->comp] : 0;
-		for (int a=k->box[0]; a<=k->box[1]; a++) for (int b=k->box[2]; b<=k->box[3]; b++) for (int c=k->box[4]; c<=k->box[5]; c++) {
+		for (int a=k->box[0]; a<=k->box[1]; a++) for (int b=k->box[2]; b<=k->box[3]; b++) for (int c=CLO(e,k->box[4]); c<=CHI(e,k->box[5]); c++) {
 			const size_t i = IDX(e,a,b,c), j = IDX(e,a+k->alt[0],b+k->alt[1],c+k->alt[2]);
 			if (G) {
 				F[i] = k->cosk*F[j] + k->sink*G[j];
@@ -440,27 +446,28 @@ static void apply_copies(alisb_engine *e, int set)
 	}
 }
 
-int alisb_step_E(alisb_engine *e)
+int alisb_step_part(alisb_engine *e, int set, int part)
 {
-	for (int m=0; m<=e->g.complex_field; m++) update_F(e, ALISB_SET_E, m);
-	apply_tfsf(e, ALISB_SET_E);
-	apply_sources(e, ALISB_SET_E, e->tH);
-	apply_copies(e, ALISB_SET_E);
-	e->t = e->tE = ++e->step * e->g.dt;           /* update.c:298 */
+	if (set<0 || set>1 || part<0 || part>2) return fail(ALISB_EINVAL, "bad step part");
+	const int send = set==ALISB_SET_E ? e->n[2] : 1;
+	e->f_lo = 0; e->f_hi = e->n[2]+1;
+	if (part == ALISB_PART_SEND_PLANE) e->f_lo = e->f_hi = send;
+	if (part == ALISB_PART_REST) { if (set==ALISB_SET_E) e->f_hi = send-1; else e->f_lo = send+1; }
+	for (int m=0; m<=e->g.complex_field; m++) { update_F(e, set, m); if (set==ALISB_SET_H) update_J(e, m); }
+	apply_tfsf(e, set, part != ALISB_PART_REST);
+	apply_sources(e, set, set==ALISB_SET_E ? e->tH : e->tE);
+	apply_copies(e, set);
+	e->f_lo = 0; e->f_hi = e->n[2]+1;
+	if (part != ALISB_PART_SEND_PLANE) {
+		if (set==ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;         /* update.c:298 */
+		else e->t = e->tH = e->tE + 0.5 * e->g.dt;                         /* update.c:340 (double arithmetic, then float) */
+	}
 	e->launches++;
 	return ALISB_OK;
 }
 
-int alisb_step_H(alisb_engine *e)
-{
-	for (int m=0; m<=e->g.complex_field; m++) { update_F(e, ALISB_SET_H, m); update_J(e, m); }
-	apply_tfsf(e, ALISB_SET_H);
-	apply_sources(e, ALISB_SET_H, e->tE);
-	apply_copies(e, ALISB_SET_H);
-	e->t = e->tH = e->tE + 0.5 * e->g.dt;         /* update.c:340 (double arithmetic, then float) */
-	e->launches++;
-	return ALISB_OK;
-}
+int alisb_step_E(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_E, ALISB_PART_ALL); }
+int alisb_step_H(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_H, ALISB_PART_ALL); }
 
 int alisb_run(alisb_engine *e, int steps) { for (int i=0; i<steps; i++) { alisb_step_E(e); alisb_step_H(e); } return ALISB_OK; }
 int alisb_synchronize(alisb_engine *e) { (void)e; return ALISB_OK; }

@@ -192,3 +192,19 @@ def test_phaser_accumulation_bit_exact(oracle_lib, engine_lib):
                 a, b = pg.read(f, face, which), po.read(f, face, which)
                 assert np.array_equal(a.view(np.float32), b.view(np.float32)), (f, face, which)
                 assert np.abs(a).max() > 0
+
+
+def test_split_pass_equals_whole_pass_on_gpu(oracle_lib, engine_lib):
+    """the overlap split (send plane first, then the rest) is bit-identical to the whole pass"""
+    w = synthetic.BoxWorld(140, 44, 50, num=6)
+    g, o = w.make_engine(engine_lib), w.make_engine(oracle_lib)
+    helpers.seed_fields([g, o], (142, 46, 52), seed=9)
+    for _ in range(15):
+        o.step_E()
+        o.step_H()
+        for s in (capi.SET_E, capi.SET_H):
+            g.step_part(s, capi.PART_SEND_PLANE)
+            g.step_part(s, capi.PART_REST)
+    assert g.time() == o.time()
+    helpers.assert_fields_identical(g, o, "split pass on GPU")
+    compare_psi(g, o)

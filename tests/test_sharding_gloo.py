@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, steps, outdir):
+def _worker(rank, world, port, shape, steps, outdir, overlap):
     import torch.distributed as dist
     from alis_b200 import sharding
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -27,7 +27,7 @@ def _worker(rank, world, port, shape, steps, outdir):
     lib = capi.load_oracle()
     w = synthetic.BoxWorld(*shape)
     e = w.make_engine(lib, rank=rank, world=world)
-    r = sharding.SlabRunner(e, rank, world, cuda=False)
+    r = sharding.SlabRunner(e, rank, world, cuda=False, overlap=overlap)
     r.run(steps)
     c0, c1 = e.shard
     a = e.read_all_fields()                       # local (nz_local+2) planes
@@ -37,15 +37,15 @@ def _worker(rank, world, port, shape, steps, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape", [(2, (40, 34, 44)), (3, (36, 40, 61))])
-def test_sharded_equals_single(world, shape, tmp_path, oracle_lib):
+@pytest.mark.parametrize("world,shape,overlap", [(2, (40, 34, 44), True), (3, (36, 40, 61), True), (2, (40, 34, 44), False)])
+def test_sharded_equals_single(world, shape, overlap, tmp_path, oracle_lib):
     steps = 40
     w = synthetic.BoxWorld(*shape)
     single = w.make_engine(oracle_lib)
     single.run(steps)
     ref = single.read_all_fields()
     assert np.abs(ref).max() > 0
-    mp.spawn(_worker, args=(world, _free_port(), shape, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, steps, str(tmp_path), overlap), nprocs=world, join=True)
     parts = [np.load(tmp_path / f"r{r}.npy") for r in range(world)]
     got = np.concatenate(parts, axis=-1)
     assert np.array_equal(got, ref[..., 1:-1]), "sharded interior planes differ from the single-domain run"
@@ -54,3 +54,19 @@ def test_sharded_equals_single(world, shape, tmp_path, oracle_lib):
         lo, hi = np.load(tmp_path / f"g{r}.npy"), np.load(tmp_path / f"g{r + 1}.npy")
         assert np.array_equal(lo[0, 1, :2, :, :, -1], hi[0, 1, :2, :, :, 1])      # H ghost of lower == first H plane of upper
         assert np.array_equal(hi[0, 0, :2, :, :, 0], lo[0, 0, :2, :, :, -2])      # E ghost of upper == top E plane of lower
+
+
+def test_split_pass_equals_whole_pass(oracle_lib):
+    """SEND_PLANE followed by REST is the same pass (oracle engine; the CUDA twin is in test_gpu_parity)"""
+    from tests import helpers
+    w = synthetic.BoxWorld(30, 28, 34, num=4)
+    a, b = w.make_engine(oracle_lib), w.make_engine(oracle_lib)
+    helpers.seed_fields([a, b], (32, 30, 36), seed=5)
+    for _ in range(12):
+        a.step_E()
+        a.step_H()
+        for s in (capi.SET_E, capi.SET_H):
+            b.step_part(s, capi.PART_SEND_PLANE)
+            b.step_part(s, capi.PART_REST)
+    assert a.time() == b.time()
+    helpers.assert_fields_identical(a, b, "split pass")
