@@ -169,7 +169,10 @@ int  alisb_run(alisb_engine *e, int steps);      /* steps x (E then H), no host 
  *   ALISB_PART_SEND_PLANE  everything of the pass that lands in the plane the neighbour needs
  *                          (E: c = nz, H: c = 1): volume update, ADE, TFSF, sources, x/y copies
  *   ALISB_PART_REST        the rest of the pass (and the time bookkeeping)
- * SEND_PLANE followed by REST is identical to alisb_step_E / alisb_step_H (= ALISB_PART_ALL). */
+ * SEND_PLANE followed by REST is identical to alisb_step_E / alisb_step_H (= ALISB_PART_ALL) on
+ * the side of a shard that faces a neighbour, i.e. where the plane beyond the send plane is a halo
+ * and not the target/source of a z boundary copy (rank r splits its E pass if it has an upper
+ * neighbour and its H pass if it has a lower one; alis_b200/sharding.py).                      */
 enum { ALISB_PART_ALL = 0, ALISB_PART_SEND_PLANE = 1, ALISB_PART_REST = 2 };
 int  alisb_step_part(alisb_engine *e, int set, int part);
 int  alisb_synchronize(alisb_engine *e);

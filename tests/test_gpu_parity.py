@@ -195,16 +195,21 @@ def test_phaser_accumulation_bit_exact(oracle_lib, engine_lib):
 
 
 def test_split_pass_equals_whole_pass_on_gpu(oracle_lib, engine_lib):
-    """the overlap split (send plane first, then the rest) is bit-identical to the whole pass"""
+    """the overlap split (send plane first, then the rest) is bit-identical to the whole pass, on
+    the side of a shard that faces a neighbour (rank 0: E pass, last rank: H pass)"""
     w = synthetic.BoxWorld(140, 44, 50, num=6)
-    g, o = w.make_engine(engine_lib), w.make_engine(oracle_lib)
-    helpers.seed_fields([g, o], (142, 46, 52), seed=9)
-    for _ in range(15):
-        o.step_E()
-        o.step_H()
-        for s in (capi.SET_E, capi.SET_H):
-            g.step_part(s, capi.PART_SEND_PLANE)
-            g.step_part(s, capi.PART_REST)
-    assert g.time() == o.time()
-    helpers.assert_fields_identical(g, o, "split pass on GPU")
-    compare_psi(g, o)
+    for rank, split_set in ((0, capi.SET_E), (1, capi.SET_H)):
+        g, o = w.make_engine(engine_lib, rank=rank, world=2), w.make_engine(oracle_lib, rank=rank, world=2)
+        helpers.seed_fields([g, o], (142, 46, g.nz + 2), seed=9)
+        for _ in range(15):
+            o.step_E()
+            o.step_H()
+            for s in (capi.SET_E, capi.SET_H):
+                if s == split_set:
+                    g.step_part(s, capi.PART_SEND_PLANE)
+                    g.step_part(s, capi.PART_REST)
+                else:
+                    g.step_part(s, capi.PART_ALL)
+        assert g.time() == o.time()
+        helpers.assert_fields_identical(g, o, f"split pass on GPU, rank {rank}")
+        compare_psi(g, o)

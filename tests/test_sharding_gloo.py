@@ -57,16 +57,22 @@ def test_sharded_equals_single(world, shape, overlap, tmp_path, oracle_lib):
 
 
 def test_split_pass_equals_whole_pass(oracle_lib):
-    """SEND_PLANE followed by REST is the same pass (oracle engine; the CUDA twin is in test_gpu_parity)"""
+    """SEND_PLANE followed by REST is the same pass.  The split is defined for the side of a shard
+    that faces a neighbour (rank 0 splits its E pass, the last rank its H pass); oracle engine,
+    the CUDA twin is in test_gpu_parity."""
     from tests import helpers
     w = synthetic.BoxWorld(30, 28, 34, num=4)
-    a, b = w.make_engine(oracle_lib), w.make_engine(oracle_lib)
-    helpers.seed_fields([a, b], (32, 30, 36), seed=5)
-    for _ in range(12):
-        a.step_E()
-        a.step_H()
-        for s in (capi.SET_E, capi.SET_H):
-            b.step_part(s, capi.PART_SEND_PLANE)
-            b.step_part(s, capi.PART_REST)
-    assert a.time() == b.time()
-    helpers.assert_fields_identical(a, b, "split pass")
+    for rank, split_set in ((0, capi.SET_E), (1, capi.SET_H)):
+        a, b = w.make_engine(oracle_lib, rank=rank, world=2), w.make_engine(oracle_lib, rank=rank, world=2)
+        helpers.seed_fields([a, b], (32, 30, a.nz + 2), seed=5)
+        for _ in range(12):
+            a.step_E()
+            a.step_H()
+            for s in (capi.SET_E, capi.SET_H):
+                if s == split_set:
+                    b.step_part(s, capi.PART_SEND_PLANE)
+                    b.step_part(s, capi.PART_REST)
+                else:
+                    b.step_part(s, capi.PART_ALL)
+        assert a.time() == b.time()
+        helpers.assert_fields_identical(a, b, f"split pass rank {rank}")
