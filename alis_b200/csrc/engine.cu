@@ -30,7 +30,7 @@ static int fail(int code, const char *fmt, ...)
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALISB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-struct SubBox { int tile0, ntiles, b0, b1, c0, c1; int pml; };   /* pml: bit 0/1/2 = may touch x/y/z slabs */
+struct SubBox { int a0, a1, b0, b1, c0, c1; int pml; };   /* cell ranges; pml: bit 0/1/2 = may touch x/y/z slabs */
 struct ProfRec { size_t ev; int set, sub; };
 
 struct DispObj {
@@ -73,6 +73,8 @@ struct alisb_engine {
 	uint64_t launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
+	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
 	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
 	int f_lo, f_hi;                    /* plane filter of the current (partial) pass: ops act on c in [f_lo,f_hi] */
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
@@ -179,9 +181,13 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7>, 256, 0));
 	{
 		const char *s;
-		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 16; e->tune_minchunk = 32;
+		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 100000; e->tune_minchunk = 8;   /* measured: profiles/sweep2_r01, sweep3_r01 */
 		if ((s = getenv("ALISB_BLOCK")) && sscanf(s, "%dx%d", &e->tune_bx, &e->tune_by) == 2) { if (e->tune_bx*e->tune_by*32 > 256 || e->tune_bx < 1 || e->tune_by < 1) { e->tune_bx = 1; e->tune_by = 8; } }
 		if ((s = getenv("ALISB_STREAM"))) e->tune_stream = atoi(s);
+		e->tune_debug = (s = getenv("ALISB_DEBUG")) ? atoi(s) : 0;
+		e->tune_conc = (s = getenv("ALISB_CONC")) ? atoi(s) : 1;
+		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
+		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 		if ((s = getenv("ALISB_WAVES"))) e->tune_waves = std::max(1, atoi(s));
 		if ((s = getenv("ALISB_MINCHUNK"))) e->tune_minchunk = std::max(1, atoi(s));
 	}
@@ -233,6 +239,8 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { cudaFree(e->dtd[s][ax]); cudaFree(e->P[s][ax]); cudaFree(e->P1[s][ax]); cudaFree(e->P2[s][ax]); }
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psi[s][m][ax][sd][w]);
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
+	cudaEventDestroy(e->ev_fork);
 	cudaFree(e->scratch);
 	if (e->own_stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -368,24 +376,24 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 
 /* ---- one pass ------------------------------------------------------------------------- */
 template <int S, bool EPS>
-static void launch_volume_te(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, int pm)
+static void launch_volume_te(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, int pm)
 {
 	switch (pm) {
-	case 0: yee_volume<S,EPS,0><<<grid,block,0,e->stream>>>(p); break;
-	case 1: yee_volume<S,EPS,1><<<grid,block,0,e->stream>>>(p); break;
-	case 2: yee_volume<S,EPS,2><<<grid,block,0,e->stream>>>(p); break;
-	case 3: yee_volume<S,EPS,3><<<grid,block,0,e->stream>>>(p); break;
-	case 4: yee_volume<S,EPS,4><<<grid,block,0,e->stream>>>(p); break;
-	case 5: yee_volume<S,EPS,5><<<grid,block,0,e->stream>>>(p); break;
-	case 6: yee_volume<S,EPS,6><<<grid,block,0,e->stream>>>(p); break;
-	default: yee_volume<S,EPS,7><<<grid,block,0,e->stream>>>(p); break;
+	case 0: yee_volume<S,EPS,0><<<grid,block,0,st>>>(p); break;
+	case 1: yee_volume<S,EPS,1><<<grid,block,0,st>>>(p); break;
+	case 2: yee_volume<S,EPS,2><<<grid,block,0,st>>>(p); break;
+	case 3: yee_volume<S,EPS,3><<<grid,block,0,st>>>(p); break;
+	case 4: yee_volume<S,EPS,4><<<grid,block,0,st>>>(p); break;
+	case 5: yee_volume<S,EPS,5><<<grid,block,0,st>>>(p); break;
+	case 6: yee_volume<S,EPS,6><<<grid,block,0,st>>>(p); break;
+	default: yee_volume<S,EPS,7><<<grid,block,0,st>>>(p); break;
 	}
 }
 template <int S>
-static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm)
+static void launch_volume_t(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm)
 {
-	if (eps) launch_volume_te<S,true>(e, p, grid, block, pm);
-	else     launch_volume_te<S,false>(e, p, grid, block, pm);
+	if (eps) launch_volume_te<S,true>(st, p, grid, block, pm);
+	else     launch_volume_te<S,false>(st, p, grid, block, pm);
 }
 
 /* Region-specialised launches.  Per axis the cells split into lo slab / slab-free middle / hi slab
@@ -397,7 +405,6 @@ static void launch_volume_t(alisb_engine *e, const VolParams &p, dim3 grid, dim3
 static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 {
 	L.clear();
-	const int ntile = div_up(e->nx, 128);
 	int lo[3], hi[3];                 /* slab-free range per axis in array coords */
 	const int n[3] = {e->nx, e->ny, e->nz};
 	for (int ax=0; ax<3; ax++) {
@@ -406,32 +413,41 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 		if (e->g.pml[set][ax][1][0] <= e->g.pml[set][ax][1][1]) hi[ax] = e->g.pml[set][ax][1][0] - 1;
 		if (lo[ax] > hi[ax] + 1) lo[ax] = hi[ax] + 1;
 	}
-	/* x: tiles [0,t0) hold min-slab cells, [t1+1,ntile) max-slab cells, [t0,t1] none */
-	int t0 = 0, t1 = ntile - 1;
-	if (lo[0] > 1)      t0 = std::min((lo[0] - 2)/128 + 1, ntile);
-	if (hi[0] < e->nx)  t1 = hi[0]/128 - 1;
-	if (t1 < t0 - 1) t1 = t0 - 1;
+	/* x: the slab strips are widened to whole 32-cell (128-byte) groups so that every launch starts
+	 * on a sector boundary and on a quad boundary (a = 1 mod 4) */
+	int xl = 0, xh = e->nx + 1;       /* strips [1,xl] and [xh,nx] may hold x-slab cells */
+	if (lo[0] > 1)     xl = std::min(e->nx, (lo[0] - 1 + 31)/32*32);
+	if (hi[0] < e->nx) xh = std::max(xl + 1, hi[0]/32*32 + 1);
 	struct Range { int a, b, pm; };
 	std::vector<Range> X, Y, Z;
-	if (t0 > 0)          X.push_back({0, t0 - 1, 1});
-	if (t0 <= t1)        X.push_back({t0, t1, 0});
-	if (t1 < ntile - 1)  X.push_back({t1 + 1, ntile - 1, 1});
+	const long cells = (long)e->nx*e->ny*e->nz;
+	if (cells < (1L << 21)) {
+		/* small grids are launch-bound: one launch with every slab the grid has */
+		int pm = 0;
+		for (int ax=0; ax<3; ax++) if (lo[ax] > 1 || hi[ax] < n[ax]) pm |= 1 << ax;
+		L.push_back({1, e->nx, 1, e->ny, 1, e->nz, pm});
+		return;
+	}
+	if (xl >= 1)         X.push_back({1, xl, 1});
+	if (xl + 1 <= xh - 1) X.push_back({xl + 1, xh - 1, 0});
+	if (xh <= e->nx)     X.push_back({xh, e->nx, 1});
 	if (lo[1] > 1)       Y.push_back({1, lo[1] - 1, 2});
 	if (lo[1] <= hi[1])  Y.push_back({lo[1], hi[1], 0});
 	if (hi[1] < e->ny)   Y.push_back({hi[1] + 1, e->ny, 2});
 	if (lo[2] > 1)       Z.push_back({1, lo[2] - 1, 4});
 	if (lo[2] <= hi[2])  Z.push_back({lo[2], hi[2], 0});
 	if (hi[2] < e->nz)   Z.push_back({hi[2] + 1, e->nz, 4});
+	const int xany = (xl >= 1 || xh <= e->nx) ? 1 : 0;
 	for (const Range &z : Z) for (const Range &y : Y) {
-		if (y.pm) {      /* thin y-slab rows: one launch over all tiles with the x code included */
-			L.push_back({0, ntile, y.a, y.b, z.a, z.b, (X.size() > 1 || (X.size() == 1 && X[0].pm) ? 1 : 0) | y.pm | z.pm});
+		if (y.pm) {      /* thin y-slab rows: one launch over the whole row with the x code included */
+			L.push_back({1, e->nx, y.a, y.b, z.a, z.b, xany | y.pm | z.pm});
 			continue;
 		}
-		for (const Range &x : X) L.push_back({x.a, x.b - x.a + 1, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm});
+		for (const Range &x : X) L.push_back({x.a, x.b, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm});
 	}
 	/* largest region first (it is also the dominant kernel reported by alisb_profile_dominant) */
 	std::stable_sort(L.begin(), L.end(), [](const SubBox &p, const SubBox &q) {
-		return (double)p.ntiles*(p.b1-p.b0+1)*(p.c1-p.c0+1) > (double)q.ntiles*(q.b1-q.b0+1)*(q.c1-q.c0+1); });
+		return (double)(p.a1-p.a0+1)*(p.b1-p.b0+1)*(p.c1-p.c0+1) > (double)(q.a1-q.a0+1)*(q.b1-q.b0+1)*(q.c1-q.c0+1); });
 }
 
 static int launch_volume(alisb_engine *e, int set, int m)
@@ -452,34 +468,54 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	const bool eps = set == ALISB_SET_E && e->eps[0] && e->eps[1] && e->eps[2];
 	if (e->plan[set].empty()) plan_volume(e, set, e->plan[set]);
 
-	int sub = -1;
+	/* Sub-launches touch disjoint cells, so they may run concurrently: the PML-shell launches are
+	 * spread over three side streams (fork/join with events) so that their ramp-up and tail phases
+	 * overlap; the interior launch runs alone first (tune_conc 1) or concurrently too (2). */
+	int sub = -1, nlaunched = 0, rr = 0;
+	bool forked = false, used[3] = {false, false, false};
+	const bool conc = e->tune_conc > 0 && e->plan[set].size() > 2;
+	if (conc && e->tune_conc == 2) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
 	for (const SubBox &sb0 : e->plan[set]) {
 		sub++;
 		SubBox sb = sb0;
 		sb.c0 = std::max(sb.c0, e->f_lo); sb.c1 = std::min(sb.c1, e->f_hi);
 		if (sb.c0 > sb.c1) continue;
+		cudaStream_t st = e->stream;
+		if (conc && (nlaunched > 0 || e->tune_conc == 2)) {
+			if (!forked) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
+			const int slot = rr++ % 4;                     /* slot 3 = the main stream itself */
+			if (slot < 3) {
+				st = e->side[slot];
+				if (!used[slot]) { CU(cudaStreamWaitEvent(st, e->ev_fork, 0)); used[slot] = true; }
+			}
+		}
+		nlaunched++;
 		cudaEvent_t e1 = 0;
 		if (e->profiling) {
 			if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
 			e->prof.push_back({e->ev_used, set, sub});
-			CU(cudaEventRecord(e->ev_pool[e->ev_used++], e->stream));
+			CU(cudaEventRecord(e->ev_pool[e->ev_used++], st));
 			e1 = e->ev_pool[e->ev_used++];
 		}
-		p.tile0 = sb.tile0; p.ntiles = sb.ntiles; p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
+		p.a_first = sb.a0; p.a_last = sb.a1; p.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
+		p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
 		const int bx = e->tune_bx, by = e->tune_by;
-		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(sb.ntiles, bx), gy = div_up(sb.b1 - sb.b0 + 1, by);
+		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(p.nseg, bx), gy = div_up(sb.b1 - sb.b0 + 1, by);
 		const long tiles = (long)gx*gy;
-		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* >= ~16 waves of CTAs ...       */
-		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* ... but chunks of >= 32 planes */
+		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* many short z-chunks balance best  */
+		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* (the carry preload is an L2 hit)  */
 		int nchunks = (int)std::max(1L, std::min(want, maxc));
 		p.cchunk = div_up(nzs, nchunks);
 		nchunks = div_up(nzs, p.cchunk);
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
-		if (set == ALISB_SET_E) launch_volume_t<1>(e, p, grid, block, eps, sb.pml);
-		else                    launch_volume_t<-1>(e, p, grid, block, false, sb.pml);
+		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] set %d sub %d pm %d cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d (resident %d)\n",
+			set, sub, sb.pml, sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, gx, gy, nchunks, p.cchunk, e->resident_ctas);
+		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, grid, block, eps, sb.pml);
+		else                    launch_volume_t<-1>(st, p, grid, block, false, sb.pml);
 		e->launches++;
-		if (e->profiling) CU(cudaEventRecord(e1, e->stream));
+		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
+	for (int q=0; q<3; q++) if (used[q]) { CU(cudaEventRecord(e->ev_join[q], e->side[q])); CU(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0)); }
 	CU(cudaGetLastError());
 	return ALISB_OK;
 }
@@ -856,8 +892,7 @@ extern "C" int alisb_profile_dominant(alisb_engine *e, float *ms_total, int *lau
 	int best[2] = {-1, -1}; double cells[2] = {0, 0};
 	for (int s=0; s<2; s++) for (size_t q=0; q<e->plan[s].size(); q++) {
 		const SubBox &b = e->plan[s][q];
-		const int a0 = 1 + 128*b.tile0, a1 = std::min(e->nx, 128*(b.tile0 + b.ntiles));
-		const double c = (double)(a1 - a0 + 1)*(b.b1 - b.b0 + 1)*(b.c1 - b.c0 + 1);
+		const double c = (double)(b.a1 - b.a0 + 1)*(b.b1 - b.b0 + 1)*(b.c1 - b.c0 + 1);
 		if (c > cells[s]) { cells[s] = c; best[s] = (int)q; }
 	}
 	float tot = 0; int n = 0;

@@ -28,7 +28,8 @@ struct VolParams {
 	int slab[3][2][2];            /* [axis][side]{first,last} in array coordinates      */
 	int xbase[2], xpitch[2];      /* x-slab psi arrays: slot = a - xbase, row pitch      */
 	int nx, ny, nz, pitch;
-	int tile0, ntiles;            /* 128-cell x segments [tile0, tile0+ntiles) of this launch */
+	int a_first, a_last;          /* x range updated by this launch (a_first = 1 mod 4); a warp covers 128 cells from a_first */
+	int nseg;                     /* number of 128-cell warp segments covering [a_first, a_last]    */
 	int b_first, b_last;          /* rows updated by this launch                        */
 	int c_first, c_last;          /* planes updated by this launch                      */
 	int cchunk;                   /* planes per z-chunk (grid.z chunks)                  */
@@ -61,12 +62,12 @@ yee_volume(const __grid_constant__ VolParams p)
 {
 	const int lane = threadIdx.x & 31;
 	const int seg = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);     /* 128-cell segment within the launch */
-	const int a0 = 1 + 4*((seg + p.tile0)*32 + lane);
+	const int a0 = p.a_first + 4*(seg*32 + lane);
 	const int b  = p.b_first + blockIdx.y*blockDim.y + threadIdx.y;
-	if (b > p.b_last || seg >= p.ntiles) return;            /* whole warp leaves */
-	const bool act = a0 <= p.nx;                            /* owns at least one updated cell      */
-	const bool ldg = a0 <= p.nx + 1;                        /* G quad holds data someone needs (ghost a=nx+1) */
-	const bool full = a0 + 3 <= p.nx;
+	if (b > p.b_last || seg >= p.nseg) return;              /* whole warp leaves */
+	const bool act = a0 <= p.a_last;                        /* owns at least one cell of this launch */
+	const bool ldg = a0 <= p.a_last + 1;                    /* G quad holds data the lane before needs (a_last+1) */
+	const bool full = a0 + 3 <= p.a_last;
 
 	const int cf = p.c_first + blockIdx.z*p.cchunk;
 	const int cl = min(cf + p.cchunk - 1, p.c_last);
@@ -241,7 +242,7 @@ yee_volume(const __grid_constant__ VolParams p)
 			st4s<STREAM>(F2 + o, make_float4(Fz[0], Fz[1], Fz[2], Fz[3]));
 		} else if (act) {
 			#pragma unroll
-			for (int e = 0; e < 4; e++) if (a0 + e <= p.nx) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
+			for (int e = 0; e < 4; e++) if (a0 + e <= p.a_last) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
 		}
 		gxp = gx; gyp = gy;
 	}

@@ -190,26 +190,10 @@ def ours(args):
     ms = float(t.item())
     value = w.cells() * args.steps / (ms * 1e-3) * 1e-6
 
-    # ---- end to end: host-driven loop with a probe read back every step -----------------
+    # ---- end to end: the drop-in C API (createWorld + pointDipole + updateE/updateH + get per step) -----
     e2e = None
     if not args.no_e2e:
-        probe_c = min(max(eng.shard[0], w.ax[2].arr(5)), eng.shard[1]) - (eng.shard[0] - 1)
-        pbox = [w.ax[0].arr(0), w.ax[0].arr(0), w.ax[1].arr(0), w.ax[1].arr(0), probe_c, probe_c]
-        barrier()
-        t0 = time.perf_counter()
-        acc = 0.0
-        for _ in range(args.steps):
-            runner.step()
-            runner.flush()
-            acc += float(eng.read_box(capi.ARR_FIELD, [0, 2, 0], pbox)[0, 0, 0])   # get(W, Ez, ...): 4 B D2H, syncs
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": w.cells() * args.steps / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4,
-               "note": "FDTD state is device-resident by design: per step the host supplies the two source samples (kernel arguments) and reads one probe value back"}
+        e2e = e2e_through_c_api(args, world, rank, local, w, eng, runner, barrier)
 
     clocks = None
     if sampler:
@@ -242,6 +226,48 @@ def ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def e2e_through_c_api(args, world, rank, local, w, eng, runner, barrier):
+    """The metric measured the way a user of the library drives it.  N = 1: a C driver written against
+    the public ALiS API (oracle/harness/bench_cube.c linked with alis_b200/libalis.so: createWorld,
+    pointDipole, then updateE; updateH; get(W,Ez,...) every step), host wall clock around the loop.
+    N > 1: the same loop through the Python binding of the C ABI (the C API is single-process), with
+    the probe read back every step."""
+    import torch
+    import torch.distributed as dist
+    from alis_b200 import capi
+    exe = os.path.join(ROOT, "tests", "bin", "bench_cube_mine_cuda")
+    note = "FDTD state is device-resident by design: per step the host supplies the source samples (kernel arguments, 8 B) and reads one probe value back (4 B)"
+    if world == 1 and os.path.exists(exe):
+        eng_free = getattr(eng, "close", None)
+        del runner
+        eng.close()                                  # give the 27 GB back before the C driver allocates its own world
+        torch.cuda.empty_cache()
+        env = dict(os.environ, ALIS_DEVICE=str(local))
+        out = subprocess.run([exe, str(args.nx), str(args.ny), str(args.nz_per_gpu), str(args.steps), str(args.warmup), "1"],
+                             env=env, capture_output=True, text=True, timeout=3000).stdout
+        m = re.search(r"seconds=([0-9.]+) mcells_per_s=([0-9.]+)", out)
+        if m:
+            return {"value": float(m.group(2)), "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4,
+                    "path": "C driver on the public API: tests/bin/bench_cube_mine_cuda (oracle/harness/bench_cube.c + alis_b200/libalis.so)", "note": note}
+    probe_c = min(max(eng.shard[0], w.ax[2].arr(5)), eng.shard[1]) - (eng.shard[0] - 1)
+    pbox = [w.ax[0].arr(0), w.ax[0].arr(0), w.ax[1].arr(0), w.ax[1].arr(0), probe_c, probe_c]
+    barrier()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(args.steps):
+        runner.step()
+        runner.flush()
+        acc += float(eng.read_box(capi.ARR_FIELD, [0, 2, 0], pbox)[0, 0, 0])   # get(W, Ez, ...): 4 B D2H, syncs
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    return {"value": w.cells() * args.steps / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4,
+            "path": "Python binding of the engine C ABI (alis_b200/capi.py), one process per GPU", "note": note}
 
 
 def lib_kernel_stats(eng):

@@ -2,9 +2,11 @@
  * bench_cube.c -- times updateE+updateH of an all-PML vacuum box through the PUBLIC API
  * (createWorld + pointDipole + the run loop), i.e. the synthetic configuration of SURVEY 8d.
  *
- *   bench_cube <nx> <ny> <nz> <steps> <warmup>
+ *   bench_cube <nx> <ny> <nz> <steps> <warmup> [probe_every_step]
  *
  * prints one line:  cells=<n> steps=<k> seconds=<s> mcells_per_s=<v> threads=<t> probe=<Ez>
+ * With probe_every_step = 1 the loop also reads get(W, Ez, ...) after every step, i.e. the way a
+ * driver with a point monitor runs (one 4-byte device->host read per step in our library).
  * Linked against the unmodified reference it is the CPU baseline (`--impl reference` and
  * cpu_baseline.kind "reference" in bench.py).
  */
@@ -18,6 +20,8 @@ int main(int argc, char **argv)
 {
 	if (argc < 6) { printf("usage: %s nx ny nz steps warmup\n", argv[0]); return 2; }
 	int n[3] = {atoi(argv[1]), atoi(argv[2]), atoi(argv[3])}, steps = atoi(argv[4]), warm = atoi(argv[5]);
+	int every = argc > 6 ? atoi(argv[6]) : 0;
+	double acc = 0;
 	float lo[3], hi[3];
 	for (int d=0; d<3; d++) {            /* interior = n-26 cells, centred like alis_b200/synthetic.py */
 		int interior = n[d] - 26;
@@ -30,12 +34,14 @@ int main(int argc, char **argv)
 	world W = createWorld(Dom, Res, Sur, "");
 	if (W->iNUM != n[0] || W->jNUM != n[1] || W->kNUM != n[2]) { printf("grid mismatch %d %d %d\n", W->iNUM, W->jNUM, W->kNUM); return 1; }
 	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 1);
-	for (int s=0; s<warm; s++) { updateE(W); updateH(W); }
+	for (int s=0; s<warm; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); }
+	acc = get(W, Ez, 0, 0, 50);                       /* (also drains the device queue before the clock starts) */
 	double t0 = now();
-	for (int s=0; s<steps; s++) { updateE(W); updateH(W); }
+	for (int s=0; s<steps; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); }
+	acc += get(W, Ez, 0, 0, 50);                      /* device work is complete when this returns */
 	double dt = now() - t0;
 	double cells = (double)n[0]*n[1]*n[2];
 	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g\n", cells, steps, dt, cells*steps/dt*1e-6,
-		omp_get_max_threads(), get(W, Ez, 0, 0, 50));
+		omp_get_max_threads(), acc);
 	return 0;
 }
