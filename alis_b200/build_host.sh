@@ -35,4 +35,14 @@ for h in stepdump bench_cube monitors; do
 		$CC -std=c99 -O2 -fopenmp -w -DHARNESS_MODE_MINE -I"$ROOT/include" -I"$HARNESS" "$HARNESS/$h.c" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/${h}_mine_oracle"
 	fi
 done
+for ex in "$ROOT"/examples/*.c; do
+	[ -f "$ex" ] || continue
+	b=$(basename "$ex" .c)
+	if [ -f "$HERE/libalis.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$HERE" -lalis -Wl,-rpath,'$ORIGIN/../../alis_b200' -lm -o "$ROOT/tests/bin/${b}_cuda"
+	fi
+	if [ -f "$ROOT/tests/bin/libalis_oracle.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/${b}_oracle"
+	fi
+done
 echo "build_host: ok"
