@@ -82,6 +82,8 @@ def _declare(lib):
         "alisb_reset_fields": (i, [vp]),
         "alisb_read_box": (i, [vp, i, i32p, i32p, f32p]),
         "alisb_write_box": (i, [vp, i, i32p, i32p, f32p]),
+        "alisb_set_spacing": (i, [vp, i, i, f32p]),
+        "alisb_plane_flux": (i, [vp, C.c_void_p, i, C.POINTER(C.c_double)]),
         "alisb_halo_info": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "alisb_halo_pack": (i, [vp, i]),
         "alisb_halo_unpack": (i, [vp, i]),
@@ -275,6 +277,18 @@ class Engine:
     def read_all_fields(self):
         ncf = self.grid.complex_field + 1
         return np.stack([np.stack([np.stack([self.read_field(s, c, m) for c in range(3)]) for s in range(2)]) for m in range(ncf)])
+
+    # --- monitor reductions ------------------------------------------------------------------
+    def set_spacing(self, set_, axis, d):
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        self._ck(self.lib.alisb_set_spacing(self.h, set_, axis, _fp(d)))
+
+    def plane_flux(self, planes):
+        """planes: [(axis, at, b0, b1, c0, c1)] -> array (n, 2) of the two partial sums per plane"""
+        arr = np.ascontiguousarray(np.array(planes, dtype=np.int32).reshape(-1, 6))
+        out = np.zeros((arr.shape[0], 2), np.float64)
+        self._ck(self.lib.alisb_plane_flux(self.h, arr.ctypes.data_as(C.c_void_p), arr.shape[0], out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     # --- halo -----------------------------------------------------------------------------
     def halo_info(self, set_, m, comp):

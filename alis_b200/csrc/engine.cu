@@ -80,6 +80,8 @@ struct alisb_engine {
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
 	std::vector<ProfRec> prof;         /* one record per profiled volume sub-launch          */
 	float *scratch; size_t scratch_elems;
+	float *spacing[2][3];              /* cell sizes per field set and axis (array coords)  */
+	FluxPlane *d_planes; double *d_partial, *d_flux, *h_flux; int flux_cap;
 };
 
 struct alisb_phaser {
@@ -147,6 +149,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
 	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
+	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
 	for (int s=0; s<2; s++) for (int m=0; m<=g->complex_field; m++) for (int c=0; c<3; c++) TRY(dalloc(&e->F[s][m][c], e->elems));
@@ -178,7 +181,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		}
 	}
 	int nb = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7>, 256, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7,32>, 256, 0));
 	{
 		const char *s;
 		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 100000; e->tune_minchunk = 8;   /* measured: profiles/sweep2_r01, sweep3_r01 */
@@ -242,6 +245,8 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
 	cudaFree(e->scratch);
+	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
+	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
 	if (e->own_stream) cudaStreamDestroy(e->stream);
 	delete e;
 }
@@ -376,24 +381,29 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 
 /* ---- one pass ------------------------------------------------------------------------- */
 template <int S, bool EPS>
-static void launch_volume_te(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, int pm)
+static void launch_volume_te(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, int pm, bool narrow)
 {
+	if (narrow) {                     /* 32-cell wide x strips: 8 lanes along x, 4 rows per warp */
+		if (pm == 1) yee_volume<S,EPS,1,8><<<grid,block,0,st>>>(p);
+		else         yee_volume<S,EPS,5,8><<<grid,block,0,st>>>(p);
+		return;
+	}
 	switch (pm) {
-	case 0: yee_volume<S,EPS,0><<<grid,block,0,st>>>(p); break;
-	case 1: yee_volume<S,EPS,1><<<grid,block,0,st>>>(p); break;
-	case 2: yee_volume<S,EPS,2><<<grid,block,0,st>>>(p); break;
-	case 3: yee_volume<S,EPS,3><<<grid,block,0,st>>>(p); break;
-	case 4: yee_volume<S,EPS,4><<<grid,block,0,st>>>(p); break;
-	case 5: yee_volume<S,EPS,5><<<grid,block,0,st>>>(p); break;
-	case 6: yee_volume<S,EPS,6><<<grid,block,0,st>>>(p); break;
-	default: yee_volume<S,EPS,7><<<grid,block,0,st>>>(p); break;
+	case 0: yee_volume<S,EPS,0,32><<<grid,block,0,st>>>(p); break;
+	case 1: yee_volume<S,EPS,1,32><<<grid,block,0,st>>>(p); break;
+	case 2: yee_volume<S,EPS,2,32><<<grid,block,0,st>>>(p); break;
+	case 3: yee_volume<S,EPS,3,32><<<grid,block,0,st>>>(p); break;
+	case 4: yee_volume<S,EPS,4,32><<<grid,block,0,st>>>(p); break;
+	case 5: yee_volume<S,EPS,5,32><<<grid,block,0,st>>>(p); break;
+	case 6: yee_volume<S,EPS,6,32><<<grid,block,0,st>>>(p); break;
+	default: yee_volume<S,EPS,7,32><<<grid,block,0,st>>>(p); break;
 	}
 }
 template <int S>
-static void launch_volume_t(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm)
+static void launch_volume_t(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm, bool narrow)
 {
-	if (eps) launch_volume_te<S,true>(st, p, grid, block, pm);
-	else     launch_volume_te<S,false>(st, p, grid, block, pm);
+	if (eps) launch_volume_te<S,true>(st, p, grid, block, pm, narrow);
+	else     launch_volume_te<S,false>(st, p, grid, block, pm, narrow);
 }
 
 /* Region-specialised launches.  Per axis the cells split into lo slab / slab-free middle / hi slab
@@ -497,10 +507,11 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			CU(cudaEventRecord(e->ev_pool[e->ev_used++], st));
 			e1 = e->ev_pool[e->ev_used++];
 		}
-		p.a_first = sb.a0; p.a_last = sb.a1; p.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
+		const bool narrow = (sb.pml == 1 || sb.pml == 5) && sb.a1 - sb.a0 + 1 <= 64;     /* x-PML strips */
+		p.a_first = sb.a0; p.a_last = sb.a1; p.nseg = div_up(sb.a1 - sb.a0 + 1, narrow ? 32 : 128);
 		p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
-		const int bx = e->tune_bx, by = e->tune_by;
-		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(p.nseg, bx), gy = div_up(sb.b1 - sb.b0 + 1, by);
+		const int bx = narrow ? 1 : e->tune_bx, by = narrow ? 8 : e->tune_by;
+		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(p.nseg, bx), gy = div_up(sb.b1 - sb.b0 + 1, by*(narrow ? 4 : 1));
 		const long tiles = (long)gx*gy;
 		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* many short z-chunks balance best  */
 		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* (the carry preload is an L2 hit)  */
@@ -510,8 +521,8 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
 		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] set %d sub %d pm %d cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d (resident %d)\n",
 			set, sub, sb.pml, sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, gx, gy, nchunks, p.cchunk, e->resident_ctas);
-		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, grid, block, eps, sb.pml);
-		else                    launch_volume_t<-1>(st, p, grid, block, false, sb.pml);
+		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, grid, block, eps, sb.pml, narrow);
+		else                    launch_volume_t<-1>(st, p, grid, block, false, sb.pml, narrow);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
@@ -782,6 +793,52 @@ static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t 
 }
 extern "C" int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, false); }
 extern "C" int alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(e, arr, ids, box, (float*)host, true); }
+
+/* ---- device-side monitor reductions ------------------------------------------------------------- */
+extern "C" int alisb_set_spacing(alisb_engine *e, int set, int axis, const float *d)
+{
+	if (set<0 || set>1 || axis<0 || axis>2 || !d) return fail(ALISB_EINVAL, "bad spacing table");
+	DEV(e);
+	const int n = axis==0 ? e->nx : axis==1 ? e->ny : e->nz;
+	if (!e->spacing[set][axis]) TRY(dalloc(&e->spacing[set][axis], n + 2));
+	CU(cudaMemcpyAsync(e->spacing[set][axis], d, (size_t)(n + 2)*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	return ALISB_OK;
+}
+
+#define FLUX_BLOCKS 64
+extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, double *out)
+{
+	if (n < 1 || !planes || !out) return fail(ALISB_EINVAL, "bad flux request");
+	DEV(e);
+	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) if (!e->spacing[s][ax]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
+	if (n > e->flux_cap) {
+		cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
+		e->flux_cap = std::max(16, n);
+		CU(cudaMalloc((void**)&e->d_planes, sizeof(FluxPlane)*e->flux_cap));
+		CU(cudaMalloc((void**)&e->d_partial, sizeof(double)*2*FLUX_BLOCKS*e->flux_cap));
+		CU(cudaMalloc((void**)&e->d_flux, sizeof(double)*2*e->flux_cap));
+		CU(cudaMallocHost((void**)&e->h_flux, sizeof(double)*2*e->flux_cap + sizeof(FluxPlane)*e->flux_cap));
+	}
+	FluxPlane *hp = (FluxPlane*)(e->h_flux + 2*e->flux_cap);
+	const int N[3] = {e->nx, e->ny, e->nz};
+	for (int q=0; q<n; q++) {
+		const alisb_flux_plane &f = planes[q];
+		if (f.axis<0 || f.axis>2 || f.at<0 || f.at>N[f.axis] || f.b0<0 || f.b1>N[(f.axis+1)%3]+1 || f.c0<0 || f.c1>N[(f.axis+2)%3]+1) return fail(ALISB_EINVAL, "flux plane outside the grid");
+		hp[q].axis = f.axis; hp[q].at = f.at; hp[q].b0 = f.b0; hp[q].b1 = f.b1; hp[q].c0 = f.c0; hp[q].c1 = f.c1;
+	}
+	FluxParams p;
+	for (int c=0; c<3; c++) { p.E[c] = e->F[0][0][c]; p.H[c] = e->F[1][0][c]; p.dE[c] = e->spacing[0][c]; p.dH[c] = e->spacing[1][c]; }
+	p.ny = e->ny; p.pitch = e->pitch;
+	CU(cudaMemcpyAsync(e->d_planes, hp, sizeof(FluxPlane)*n, cudaMemcpyHostToDevice, e->stream));
+	flux_partial<<<dim3(FLUX_BLOCKS, n), 256, 0, e->stream>>>(p, e->d_planes, e->d_partial);
+	flux_finish<<<n, 32, 0, e->stream>>>(e->d_partial, FLUX_BLOCKS, e->d_flux);
+	CU(cudaMemcpyAsync(e->h_flux, e->d_flux, sizeof(double)*2*n, cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	memcpy(out, e->h_flux, sizeof(double)*2*n);
+	e->launches += 2;
+	return ALISB_OK;
+}
 
 /* ---- halo: planes are contiguous in this layout, hand out pointers into the arrays -------- */
 extern "C" int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)

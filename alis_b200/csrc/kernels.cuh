@@ -56,18 +56,24 @@ template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, flo
  * (the warp above/below in the same CTA loads the same line in the same iteration), the
  * x-neighbour comes from a warp shuffle.
  */
-template <int S, bool EPS, int PM>          /* PM: bit 0/1/2 = this launch may touch x / y / z PML slabs */
+/* XL = lanes of a warp along x: 32 (a warp is one 128-cell row segment) or 8 (a warp is a 32-cell
+ * wide, 4-row patch: used for the narrow x-PML strips so that all lanes have work). */
+template <int S, bool EPS, int PM, int XL>  /* PM: bit 0/1/2 = this launch may touch x / y / z PML slabs */
 __global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
 yee_volume(const __grid_constant__ VolParams p)
 {
+	constexpr int RW = 32/XL;                               /* rows per warp */
 	const int lane = threadIdx.x & 31;
-	const int seg = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);     /* 128-cell segment within the launch */
-	const int a0 = p.a_first + 4*(seg*32 + lane);
-	const int b  = p.b_first + blockIdx.y*blockDim.y + threadIdx.y;
-	if (b > p.b_last || seg >= p.nseg) return;              /* whole warp leaves */
-	const bool act = a0 <= p.a_last;                        /* owns at least one cell of this launch */
-	const bool ldg = a0 <= p.a_last + 1;                    /* G quad holds data the lane before needs (a_last+1) */
-	const bool full = a0 + 3 <= p.a_last;
+	const int lx = lane % XL;                               /* lane position along x */
+	const int seg = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);     /* (4*XL)-cell segment within the launch */
+	const int a0 = p.a_first + 4*(seg*XL + lx);
+	const int bw = p.b_first + (blockIdx.y*blockDim.y + threadIdx.y)*RW;   /* first row of this warp */
+	const int b  = bw + lane/XL;
+	if (bw > p.b_last || seg >= p.nseg) return;             /* whole warp leaves */
+	const bool rowok = b <= p.b_last;
+	const bool act = rowok && a0 <= p.a_last;               /* owns at least one cell of this launch */
+	const bool ldg = rowok && a0 <= p.a_last + 1;           /* G quad holds data the lane before needs (a_last+1) */
+	const bool full = rowok && a0 + 3 <= p.a_last;
 
 	const int cf = p.c_first + blockIdx.z*p.cchunk;
 	const int cl = min(cf + p.cchunk - 1, p.c_last);
@@ -83,7 +89,7 @@ yee_volume(const __grid_constant__ VolParams p)
 
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 	const float4 dx4 = act ? ld4(p.dtd[0] + ALISB_XO + a0) : zero4;
-	const float  dy  = __ldg(p.dtd[1] + b);
+	const float  dy  = rowok ? __ldg(p.dtd[1] + b) : 0.f;
 
 	/* loop-invariant slab membership */
 	int ys = -1, xs = -1;
@@ -94,6 +100,7 @@ yee_volume(const __grid_constant__ VolParams p)
 	if (PM & 2) {
 		if (b >= p.slab[1][0][0] && b <= p.slab[1][0][1]) ys = 0;
 		else if (b >= p.slab[1][1][0] && b <= p.slab[1][1][1]) ys = 1;
+		if (!rowok) ys = -1;
 		if (ys >= 0) { yP = __ldg(p.P[1] + b); yP1 = __ldg(p.P1[1] + b); yP2 = __ldg(p.P2[1] + b); }
 	}
 	if (PM & 1) {
@@ -130,11 +137,11 @@ yee_volume(const __grid_constant__ VolParams p)
 		if (S > 0) {
 			gye = __shfl_down_sync(0xffffffffu, gy.x, 1);
 			gze = __shfl_down_sync(0xffffffffu, gz.x, 1);
-			if (lane == 31 && act) { gye = G1[o + 4]; gze = G2[o + 4]; }
+			if (lx == XL-1 && act) { gye = G1[o + 4]; gze = G2[o + 4]; }
 		} else {
 			gye = __shfl_up_sync(0xffffffffu, gy.w, 1);
 			gze = __shfl_up_sync(0xffffffffu, gz.w, 1);
-			if (lane == 0 && act) { gye = *(G1 + o - 1); gze = *(G2 + o - 1); }
+			if (lx == 0 && act) { gye = *(G1 + o - 1); gze = *(G2 + o - 1); }
 		}
 		const float dz = __ldg(p.dtd[2] + c);
 
@@ -410,5 +417,70 @@ __global__ void phaser_face(float2 *acc, const float *E1, const float *E2, const
 		v.x = (float)((double)v.x + (double)(wH.x*h1)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h1)*0.5); A[2*cells] = v;
 		v = A[3*cells];
 		v.x = (float)((double)v.x + (double)(wH.x*h2)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h2)*0.5); A[3*cells] = v;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Poynting flux through rectangles (reference output.c:233-332).  blockIdx.y = plane.  Every
+ * thread accumulates its cells in double, the block reduces with shuffles in a fixed order and
+ * writes one partial per block; flux_finish adds the partials in index order, so the result is
+ * deterministic.
+ * ------------------------------------------------------------------------------------------ */
+struct FluxPlane { int axis, at, b0, b1, c0, c1; };
+struct FluxParams {
+	const float *E[3], *H[3];
+	const float *dE[3], *dH[3];       /* spacing tables in array coordinates */
+	int ny, pitch;
+};
+
+static __device__ __forceinline__ size_t flux_idx(int axis, int at, int ib, int ic, int ny, int pitch)
+{
+	int q[3];
+	q[axis] = at; q[(axis+1)%3] = ib; q[(axis+2)%3] = ic;
+	return GIDX(q[0], q[1], q[2]);
+}
+
+__global__ void flux_partial(const __grid_constant__ FluxParams p, const FluxPlane *planes, double *partial)
+{
+	const FluxPlane P = planes[blockIdx.y];
+	const int a = P.axis, b = (a+1)%3, c = (a+2)%3;
+	const int ny = p.ny, pitch = p.pitch;
+	const int nb = P.b1 - P.b0 + 1, nc = P.c1 - P.c0 + 1;
+	const size_t step = a == 0 ? 1 : a == 1 ? (size_t)pitch : (size_t)(ny+2)*pitch;      /* to plane at+1 */
+	double s1 = 0, s2 = 0;
+	for (size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x; t < (size_t)nb*nc; t += (size_t)gridDim.x*blockDim.x) {
+		/* run fastest along whichever tangential axis is x (contiguous) if any */
+		int ib, ic;
+		if (b == 0) { ib = P.b0 + (int)(t % nb); ic = P.c0 + (int)(t / nb); }
+		else        { ic = P.c0 + (int)(t % nc); ib = P.b0 + (int)(t / nc); }
+		const size_t i = flux_idx(a, P.at, ib, ic, ny, pitch);
+		if (ib > P.b0) {                       /* + E_b (H_c + H_c'), trapezoid along c */
+			const float wc = (ic == P.c0 || ic == P.c1) ? 0.5f : 1.0f;
+			s1 += (double)p.dH[b][ib] * ((double)wc * (double)p.dE[c][ic] * (double)p.E[b][i] * (double)(p.H[c][i] + p.H[c][i + step]));
+		}
+		if (ic > P.c0) {                       /* - E_c (H_b + H_b'), trapezoid along b */
+			const float wb = (ib == P.b0 || ib == P.b1) ? 0.5f : 1.0f;
+			s2 -= (double)p.dH[c][ic] * ((double)wb * (double)p.dE[b][ib] * (double)p.E[c][i] * (double)(p.H[b][i] + p.H[b][i + step]));
+		}
+	}
+	__shared__ double sh[2][32];
+	for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+	const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+	if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; }
+	__syncthreads();
+	if (w == 0) {
+		s1 = l < (blockDim.x >> 5) ? sh[0][l] : 0; s2 = l < (blockDim.x >> 5) ? sh[1][l] : 0;
+		for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+		if (l == 0) { partial[2*((size_t)blockIdx.y*gridDim.x + blockIdx.x)] = s1; partial[2*((size_t)blockIdx.y*gridDim.x + blockIdx.x) + 1] = s2; }
+	}
+}
+
+__global__ void flux_finish(const double *partial, int nblocks, double *out)
+{
+	const int q = blockIdx.x;
+	if (threadIdx.x == 0) {
+		double s1 = 0, s2 = 0;
+		for (int k = 0; k < nblocks; k++) { s1 += partial[2*((size_t)q*nblocks + k)]; s2 += partial[2*((size_t)q*nblocks + k) + 1]; }
+		out[2*q] = s1; out[2*q + 1] = s2;
 	}
 }

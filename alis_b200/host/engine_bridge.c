@@ -80,6 +80,13 @@ static void push_tables(alis_bridge *B, int set, coeffs *C)
 		CHECK(alisb_set_axis_tables(B->E, set, ax, a, b, c, d));
 		free(a); free(b); free(c); free(d);
 	}
+	/* cell sizes, for the device-side flux integrals (reference output.c:233-332) */
+	const float *ds[3] = {C->dx, C->dy, C->dz};
+	for (int ax=0; ax<3; ax++) {
+		float *a = table(ds[ax], MIN[ax], NUM[ax]);
+		CHECK(alisb_set_spacing(B->E, set, ax, a));
+		free(a);
+	}
 }
 
 static void fill_grid(world W, alisb_grid *g)

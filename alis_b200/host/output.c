@@ -214,47 +214,13 @@ void (writeSpectrum)(world W, int N, float LMin, float LMax, char *format, ...)
 /* ---- time-domain Poynting flux (reference output.c:233-362) ------------------------------------------
  * Flux through the plane normal to axis a at index `at`, over [lo_b,hi_b] x [lo_c,hi_c] with
  * b = a+1, c = a+2 (cyclic):   S_a = E_b H_c - E_c H_b,  H averaged over the two planes that
- * flank the E plane, trapezoidal weights in both tangential directions. */
-static inline float pick(float ***A, int a, int at, int b, int ib, int c, int ic)
-{
-	int q[3];
-	q[a] = at; q[b] = ib; q[c] = ic;
-	return A[q[0]][q[1]][q[2]];
-}
-
-static float plane_flux(world W, int a, int at, int bMin, int bMax, int cMin, int cMax)
-{
-	const int b = (a+1)%3, c = (a+2)%3;
-	float ***Eb = b==0 ? W->E->x : b==1 ? W->E->y : W->E->z, ***Ec = c==0 ? W->E->x : c==1 ? W->E->y : W->E->z;
-	float ***Hb = b==0 ? W->H->x : b==1 ? W->H->y : W->H->z, ***Hc = c==0 ? W->H->x : c==1 ? W->H->y : W->H->z;
-	const float *dEb = b==0 ? W->CE->dx : b==1 ? W->CE->dy : W->CE->dz, *dEc = c==0 ? W->CE->dx : c==1 ? W->CE->dy : W->CE->dz;
-	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
-	/* the reference reduces each of the two terms in its own OpenMP loop and adds the partial
-	 * sums afterwards; keeping the two partials separate reproduces its rounding */
-	float Sum = 0, Sum2 = 0;
-	int lo[3], hi[3];
-	lo[a] = at, hi[a] = at+1; lo[b] = bMin, hi[b] = bMax; lo[c] = cMin, hi[c] = cMax;
-	alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
-	#define E_H(E, H, ib, ic) pick(E,a,at,b,ib,c,ic) * (pick(H,a,at,b,ib,c,ic) + pick(H,a,at+1,b,ib,c,ic))   /* no outer parentheses: d * E * (H+H') associates left to right */
-
-	for (int ib=bMin+1; ib<=bMax; ib++) {            /* + E_b H_c */
-		float sum = 0;
-		sum += 0.5 * dEc[cMin] * E_H(Eb, Hc, ib, cMin);
-		sum += 0.5 * dEc[cMax] * E_H(Eb, Hc, ib, cMax);
-		for (int ic=cMin+1; ic<cMax; ic++) sum += dEc[ic] * E_H(Eb, Hc, ib, ic);
-		Sum += dHb[ib] * sum;
-	}
-	for (int ic=cMin+1; ic<=cMax; ic++) {            /* - E_c H_b */
-		float sum = 0;
-		sum -= 0.5 * dEb[bMin] * E_H(Ec, Hb, bMin, ic);
-		sum -= 0.5 * dEb[bMax] * E_H(Ec, Hb, bMax, ic);
-		for (int ib=bMin+1; ib<bMax; ib++) sum -= dEb[ib] * E_H(Ec, Hb, ib, ic);
-		Sum2 += dHc[ic] * sum;
-	}
-	#undef E_H
-	Sum += Sum2;
-	return Sum;
-}
+ * flank the E plane, trapezoidal weights in both tangential directions.  The double sums run ON
+ * THE DEVICE (alisb_plane_flux, kernel flux_partial): only two numbers per plane come back, and a
+ * Poynting box is a single call with one synchronisation. */
+typedef struct {
+	int a, at, bMin, bMax, cMin, cMax, mirrored;
+	float bLo, bHi, cLo, cHi;
+} plane_req;
 
 /* index range of a tangential extent: a degenerate extent becomes the two cells around it */
 static void tangential_range(world W, int axis, float lo, float hi, int *iLo, int *iHi)
@@ -265,33 +231,64 @@ static void tangential_range(world W, int axis, float lo, float hi, int *iLo, in
 	*iHi = lo==hi ? MIN(Max, toi(W, hi)+1) : MIN(Max, toi(W, hi));
 }
 
-static float poynting_plane(world W, int a, float pos, float bLo, float bHi, float cLo, float cHi)
+static plane_req plane_request(world W, int a, float pos, float bLo, float bHi, float cLo, float cHi)
 {
 	const int b = (a+1)%3, c = (a+2)%3;
 	const int sur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
-	const int flat[3] = { W->Dom.x.Min==W->Dom.x.Max, W->Dom.y.Min==W->Dom.y.Max, W->Dom.z.Min==W->Dom.z.Max };
 	int (*toi)(world, float) = a==0 ? W->xtoi : a==1 ? W->ytoj : W->ztok;
-	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
-	const int mirrored = pos<0 && sur[a]==SYM;
-	int at = toi(W, mirrored ? -pos : pos);
-	int bMin, bMax, cMin, cMax;
-	tangential_range(W, b, bLo, bHi, &bMin, &bMax);
-	tangential_range(W, c, cLo, cHi, &cMin, &cMax);
+	plane_req r = { a, 0, 0, 0, 0, 0, pos<0 && sur[a]==SYM, bLo, bHi, cLo, cHi };
+	r.at = toi(W, r.mirrored ? -pos : pos);
+	tangential_range(W, b, bLo, bHi, &r.bMin, &r.bMax);
+	tangential_range(W, c, cLo, cHi, &r.cMin, &r.cMax);
+	return r;
+}
 
-	float Sum = plane_flux(W, a, at, bMin, bMax, cMin, cMax);
+/* the two partial sums of each requested plane, from the device */
+static void plane_sums(world W, const plane_req *r, int n, double *sums)
+{
+	alis_bridge *B = alis_host_bridge(W);
+	alis_bridge_commit(B);
+	alisb_flux_plane P[6];
+	const int org[3] = { W->iMIN-1, W->jMIN-1, W->kMIN-1 };
+	for (int q=0; q<n; q++) {
+		const int a = r[q].a, b = (a+1)%3, c = (a+2)%3;
+		P[q].axis = a; P[q].at = r[q].at - org[a];
+		P[q].b0 = r[q].bMin - org[b]; P[q].b1 = r[q].bMax - org[b];
+		P[q].c0 = r[q].cMin - org[c]; P[q].c1 = r[q].cMax - org[c];
+	}
+	if (alisb_plane_flux(alis_bridge_engine(B), P, n, sums) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+}
+
+static float plane_finish(world W, const plane_req *r, double s1, double s2)
+{
+	const int a = r->a, b = (a+1)%3, c = (a+2)%3;
+	const int sur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
+	const int flat[3] = { W->Dom.x.Min==W->Dom.x.Max, W->Dom.y.Min==W->Dom.y.Max, W->Dom.z.Min==W->Dom.z.Max };
+	const float *dHb = b==0 ? W->CH->dx : b==1 ? W->CH->dy : W->CH->dz, *dHc = c==0 ? W->CH->dx : c==1 ? W->CH->dy : W->CH->dz;
+	/* the reference reduces each term in its own OpenMP loop and then adds the two partial sums */
+	float Sum = (float)s1, Sum2 = (float)s2;
+	Sum += Sum2;
 	/* per-unit-length normalisation of collapsed (2-D) extents; mirror symmetry doubles the flux.
 	 * Order of the two axes as in the reference: y before z, x before z, x before y. */
 	const int first = MIN(b, c), second = MAX(b, c);
 	for (int pass=0; pass<2; pass++) {
 		const int ax = pass==0 ? first : second;
-		const float lo = ax==b ? bLo : cLo, hi = ax==b ? bHi : cHi;
+		const float lo = ax==b ? r->bLo : r->cLo, hi = ax==b ? r->bHi : r->cHi;
 		const float *dH = ax==b ? dHb : dHc;
-		const int top = ax==b ? bMax : cMax;
+		const int top = ax==b ? r->bMax : r->cMax;
 		if (lo==hi || flat[ax]) Sum /= dH[top]+dH[top-1];
 	}
 	if (sur[first]==SYM) Sum *= 2;
 	if (sur[second]==SYM) Sum *= 2;
-	return (mirrored ? -0.5 : 0.5) * Sum;
+	return (r->mirrored ? -0.5 : 0.5) * Sum;
+}
+
+static float poynting_plane(world W, int a, float pos, float bLo, float bHi, float cLo, float cHi)
+{
+	plane_req r = plane_request(W, a, pos, bLo, bHi, cLo, cHi);
+	double s[2];
+	plane_sums(W, &r, 1, s);
+	return plane_finish(W, &r, s[0], s[1]);
 }
 
 float (poyntingX)(world W, float x, float yMin, float yMax, float zMin, float zMax, ...) { return poynting_plane(W, 0, x, yMin, yMax, zMin, zMax); }
@@ -299,41 +296,29 @@ float (poyntingY)(world W, float y, float xMin, float xMax, float zMin, float zM
 float (poyntingZ)(world W, float z, float xMin, float xMax, float yMin, float yMax, ...) { return poynting_plane(W, 2, z, xMin, xMax, yMin, yMax); }
 
 /* net outward flux through the faces of a box; faces on Bloch-periodic boundaries cancel
- * (reference output.c:335-362) */
+ * (reference output.c:335-362).  All faces go to the device in one request. */
 float poyntingOut(world W, float xMin, float xMax, float yMin, float yMax, float zMin, float zMax)
 {
-	float fx = 0, fy = 0, fz = 0;
-	/* one prefetch for the whole box: the six face evaluations below then hit the host views */
-	{
-		int lo[3], hi[3];
-		const float bmin[3] = { xMin, yMin, zMin }, bmax[3] = { xMax, yMax, zMax };
-		int (*toi[3])(world, float) = { W->xtoi, W->ytoj, W->ztok };
-		const int Min[3] = { W->iMin, W->jMin, W->kMin }, Max[3] = { W->iMax, W->jMax, W->kMax };
-		const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
-		for (int a=0; a<3; a++) {
-			const int q0 = toi[a](W, bmin[a] < 0 && sym[a] ? -bmin[a] : bmin[a]), q1 = toi[a](W, bmax[a]);
-			lo[a] = MAX(Min[a], MIN(q0, q1)) - 1;
-			hi[a] = MIN(Max[a], MAX(q0, q1)) + 1;
-			if (sym[a]) lo[a] = MIN(lo[a], Min[a]);
-		}
-		alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+	const float lo[3] = { xMin, yMin, zMin }, hi[3] = { xMax, yMax, zMax };
+	const float wlo[3] = { W->xMin, W->yMin, W->zMin }, whi[3] = { W->xMax, W->yMax, W->zMax };
+	const int sur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
+	plane_req req[6];
+	int n = 0, first[3] = { -1, -1, -1 }, second[3] = { -1, -1, -1 };
+	for (int a=0; a<3; a++) {
+		if (!(lo[a] > wlo[a] || hi[a] < whi[a] || sur[a] != BBC)) continue;
+		const int b = (a+1)%3, c = (a+2)%3;
+		first[a] = n; req[n++] = plane_request(W, a, hi[a], lo[b], hi[b], lo[c], hi[c]);
+		if (!(lo[a] < 0 && sur[a]==SYM)) { second[a] = n; req[n++] = plane_request(W, a, lo[a], lo[b], hi[b], lo[c], hi[c]); }
 	}
-	if (xMin > W->xMin || xMax < W->xMax || W->xMinSur != BBC) {
-		fx = (poyntingX)(W, xMax, yMin, yMax, zMin, zMax);
-		if (xMin < 0 && W->xMinSur==SYM) fx *= 2;
-		else fx -= (poyntingX)(W, xMin, yMin, yMax, zMin, zMax);
+	double sums[12];
+	if (n) plane_sums(W, req, n, sums);
+	float f[3] = { 0, 0, 0 };
+	for (int a=0; a<3; a++) if (first[a] >= 0) {
+		f[a] = plane_finish(W, &req[first[a]], sums[2*first[a]], sums[2*first[a]+1]);
+		if (second[a] < 0) f[a] *= 2;
+		else f[a] -= plane_finish(W, &req[second[a]], sums[2*second[a]], sums[2*second[a]+1]);
 	}
-	if (yMin > W->yMin || yMax < W->yMax || W->yMinSur != BBC) {
-		fy = (poyntingY)(W, yMax, xMin, xMax, zMin, zMax);
-		if (yMin < 0 && W->yMinSur==SYM) fy *= 2;
-		else fy -= (poyntingY)(W, yMin, xMin, xMax, zMin, zMax);
-	}
-	if (zMin > W->zMin || zMax < W->zMax || W->zMinSur != BBC) {
-		fz = (poyntingZ)(W, zMax, xMin, xMax, yMin, yMax);
-		if (zMin < 0 && W->zMinSur==SYM) fz *= 2;
-		else fz -= (poyntingZ)(W, zMin, xMin, xMax, yMin, yMax);
-	}
-	return fx + fy + fz;
+	return f[0] + f[1] + f[2];
 }
 
 /* ---- absorption inside a dispersive object (reference output.c:23-47, 365-435) ---------------------------

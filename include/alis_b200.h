@@ -185,6 +185,19 @@ int  alisb_reset_fields(alisb_engine *e);        /* rebootWorld field part, worl
 int  alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host);
 int  alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host);
 
+/* ---- device-side monitor reductions ------------------------------------------ */
+/* cell sizes C->dx/dy/dz of field set `set` (reference world.c:148-150) in array coordinates,
+ * n+2 floats; needed by the flux integrals                                                   */
+int  alisb_set_spacing(alisb_engine *e, int set, int axis, const float *d);
+/* Time-domain Poynting flux through axis-aligned rectangles (reference output.c:233-332,
+ * poyntingX/Y/Z): plane normal `axis` at array coordinate `at`, tangential index ranges
+ * [b0,b1] x [c0,c1] with b = axis+1, c = axis+2 (cyclic).  out[2*q] = + sum of E_b (H_c + H_c')
+ * with trapezoidal weights, out[2*q+1] = - sum of E_c (H_b + H_b'), exactly the two partial sums of
+ * the reference's two loops, accumulated in double on the device.  One synchronisation for all
+ * n planes (a Poynting box is one call).                                                      */
+typedef struct { int32_t axis, at, b0, b1, c0, c1; } alisb_flux_plane;
+int  alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, double *out);
+
 /* ---- z-slab halo (multi-GPU) -------------------------------------------- */
 /* Buffers (device memory for the CUDA engine) holding one full z-plane incl. ghosts of
  * component comp (x or y) of field set `set`, copy m:

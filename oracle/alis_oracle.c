@@ -67,6 +67,7 @@ struct alisb_engine {
 	float *halo_send[2][2][2], *halo_recv[2][2][2];   /* [set][m][comp x/y] */
 	uint64_t launches;
 	int f_lo, f_hi;                       /* plane filter of the current (partial) pass */
+	float *spacing[2][3];
 };
 
 struct alisb_phaser {
@@ -74,6 +75,7 @@ struct alisb_phaser {
 	block acc[6][4];                      /* per face, E1,E2,H1,H2; v holds nfreq*2*cells floats */
 };
 
+static float *dup_table(const float *src, int n);
 static char g_err[256] = "";
 static int fail(int code, const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
 
@@ -140,7 +142,7 @@ void alisb_destroy(alisb_engine *e)
 	if (!e) return;
 	alisb_clear_sources(e);
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int c=0; c<3; c++) free(e->F[s][m][c]);
-	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { free(e->dtd[s][ax]); free(e->P[s][ax]); free(e->P1[s][ax]); free(e->P2[s][ax]); }
+	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { free(e->dtd[s][ax]); free(e->P[s][ax]); free(e->P1[s][ax]); free(e->P2[s][ax]); free(e->spacing[s][ax]); }
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) free(e->psi[s][m][ax][sd][w].v);
 	for (int c=0; c<3; c++) free(e->eps[c]);
 	alisb_clear_dispersive(e);
@@ -538,6 +540,51 @@ static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t 
 }
 int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, 0); }
 int alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(e, arr, ids, box, (float*)host, 1); }
+
+/* ---- monitor reductions: reference output.c:233-332, same loop order and float arithmetic ---- */
+int alisb_set_spacing(alisb_engine *e, int set, int axis, const float *d)
+{
+	if (set<0 || set>1 || axis<0 || axis>2 || !d) return fail(ALISB_EINVAL, "bad spacing table");
+	free(e->spacing[set][axis]);
+	e->spacing[set][axis] = dup_table(d, e->n[axis]);
+	return ALISB_OK;
+}
+
+static inline float pickf(alisb_engine *e, const float *A, int a, int at, int ib, int ic)
+{
+	int q[3];
+	q[a] = at; q[(a+1)%3] = ib; q[(a+2)%3] = ic;
+	return A[IDX(e, q[0], q[1], q[2])];
+}
+
+int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, double *out)
+{
+	for (int q=0; q<n; q++) {
+		const alisb_flux_plane *P = &planes[q];
+		const int a = P->axis, b = (a+1)%3, c = (a+2)%3;
+		const float *Eb = e->F[0][0][b], *Ec = e->F[0][0][c], *Hb = e->F[1][0][b], *Hc = e->F[1][0][c];
+		const float *dEb = e->spacing[0][b], *dEc = e->spacing[0][c], *dHb = e->spacing[1][b], *dHc = e->spacing[1][c];
+		float S1 = 0, S2 = 0;
+		#define E_H(E, H, ib, ic) pickf(e,E,a,P->at,ib,ic) * (pickf(e,H,a,P->at,ib,ic) + pickf(e,H,a,P->at+1,ib,ic))
+		for (int ib=P->b0+1; ib<=P->b1; ib++) {
+			float sum = 0;
+			sum += 0.5 * dEc[P->c0] * E_H(Eb, Hc, ib, P->c0);
+			sum += 0.5 * dEc[P->c1] * E_H(Eb, Hc, ib, P->c1);
+			for (int ic=P->c0+1; ic<P->c1; ic++) sum += dEc[ic] * E_H(Eb, Hc, ib, ic);
+			S1 += dHb[ib] * sum;
+		}
+		for (int ic=P->c0+1; ic<=P->c1; ic++) {
+			float sum = 0;
+			sum -= 0.5 * dEb[P->b0] * E_H(Ec, Hb, P->b0, ic);
+			sum -= 0.5 * dEb[P->b1] * E_H(Ec, Hb, P->b1, ic);
+			for (int ib=P->b0+1; ib<P->b1; ib++) sum -= dEb[ib] * E_H(Ec, Hb, ib, ic);
+			S2 += dHc[ic] * sum;
+		}
+		#undef E_H
+		out[2*q] = S1; out[2*q+1] = S2;
+	}
+	return ALISB_OK;
+}
 
 /* ---- halo ------------------------------------------------------------------------------ */
 int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)
