@@ -53,7 +53,7 @@ int main(int argc, char **argv)
 	emit("worldMax_Ez", worldMax(W, Ez)); emit("worldSum_U", worldSum(W, U));
 	emit("sliceMax_XY_EE", sliceMax(W, EE, XY)); emit("sliceSum_XZ_U", sliceSum(W, U, XZ));
 	emit("poyntingX", poyntingX(W, 100)); emit("poyntingY", poyntingY(W, 50, -100, 100, -80, 120)); emit("poyntingZ", poyntingZ(W, 100, -150, 150));
-	emit("poyntingOut", poyntingOut(W, -120, 120, -120, 120, -100, 140));
+	emit("poyntingOut", poyntingOut(W, -120, 120, 20, 120, -100, 140));
 	if (is_nano) { emit("flux_in", flux_in); emit("flux_out", flux_out); emit("absorption", absn); }
 	if (P) {
 		phaser Q = is_band ? choosePhaser(P, 500) : P;
