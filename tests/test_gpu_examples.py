@@ -29,7 +29,9 @@ EXAMPLES = {
 def run(exe, args, cwd):
     shutil.copy(exe, os.path.join(cwd, os.path.basename(exe)))
     t0 = time.time()
-    r = subprocess.run(["./" + os.path.basename(exe)] + args, cwd=cwd, capture_output=True, text=True, timeout=1500)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(helpers.ROOT, "alis_b200") + os.pathsep + env.get("LD_LIBRARY_PATH", "")   # the copy's $ORIGIN rpath no longer points there
+    r = subprocess.run(["./" + os.path.basename(exe)] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=1500)
     dt = time.time() - t0
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return dt, r.stdout
