@@ -628,6 +628,28 @@ static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 
 static int apply_copies(alisb_engine *e, int set)
 {
+	/* small planes: the whole ordered list in one single-CTA launch */
+	CopyList L;
+	L.n = 0; L.ny = e->ny; L.pitch = e->pitch;
+	bool small = e->copies[set].size() <= ALISB_MAXCOPIES;
+	size_t total = 0;
+	for (const alisb_copy &k : e->copies[set]) {
+		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
+		const size_t n = bcount(B);
+		if (!n) continue;
+		if (n > 16384) { small = false; break; }
+		total += n;
+		if (small) {
+			CopyOp &o = L.op[L.n++];
+			o.F = e->F[k.set][0][k.comp]; o.G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
+			o.cosk = k.cosk; o.sink = k.sink; o.B = B; o.alt0 = k.alt[0]; o.alt1 = k.alt[1]; o.alt2 = k.alt[2];
+		}
+	}
+	if (small && total <= 131072) {
+		if (L.n) { copy_list<<<1, 1024, 0, e->stream>>>(L); e->launches++; }
+		CU(cudaGetLastError());
+		return ALISB_OK;
+	}
 	for (const alisb_copy &k : e->copies[set]) {
 		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
 		const size_t n = bcount(B);

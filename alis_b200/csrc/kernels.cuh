@@ -380,6 +380,33 @@ __global__ void copy_plane(float *F, float *G, float cosk, float sink, Box B, in
 	} else F[i] = cosk*F[j];
 }
 
+/* The whole ordered copy list of a pass in ONE launch, for grids whose boundary planes are small:
+ * a single CTA walks the list and separates the (order-dependent) copies with __syncthreads().
+ * Cuts a Bloch/hexagonal H pass from 16 tiny launches to one. */
+#define ALISB_MAXCOPIES 24
+struct CopyOp { float *F, *G; float cosk, sink; Box B; int alt0, alt1, alt2; };
+struct CopyList { CopyOp op[ALISB_MAXCOPIES]; int n, ny, pitch; };
+
+__global__ void __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L)
+{
+	const int ny = L.ny, pitch = L.pitch;
+	for (int k = 0; k < L.n; k++) {
+		const CopyOp &o = L.op[k];
+		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
+		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+			int a, b, c; size_t q;
+			box_cell(o.B, t, a, b, c, q);
+			const size_t i = GIDX(a, b, c), j = GIDX(a + o.alt0, b + o.alt1, c + o.alt2);
+			if (o.G) {
+				const float f = o.F[j], g = o.G[j];
+				o.F[i] = o.cosk*f + o.sink*g;
+				o.G[i] = o.cosk*g - o.sink*f;
+			} else o.F[i] = o.cosk*o.F[j];
+		}
+		__syncthreads();
+	}
+}
+
 /* gather / scatter a box between any engine array (element (a,b,c) at c*sC + b*sB + a + off) and a
  * dense buffer in the HOST order (z fastest, reference makeField layout): the transposition is
  * done here so that the host side is a plain memcpy */

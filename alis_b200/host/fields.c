@@ -48,6 +48,8 @@ static inline folded fold_plain(world W, int i, int j, int k)
 }
 
 #define NEED(W,r) alis_view_need(W, (r).i, (r).i+1, (r).j, (r).j+1, (r).k, (r).k+1)
+/* only one array: (set 0 E / 1 H, component, field set m) */
+#define NEED1(W,set,c,m,r) alis_view_need_arr(W, set, c, m, (r).i, (r).i+1, (r).j, (r).j+1, (r).k, (r).k+1)
 
 /* ---- stencils of the Yee cell ---------------------------------------------------------------------- */
 /* two samples of an E component along its own axis c */
@@ -85,7 +87,7 @@ static float raw_component(world W, int isH, int c, int i, int j, int k)
 {
 	const int own = isH ? -1 : 1;
 	folded r = fold_cos(W, i, j, k, 1, SGN(c,0,own), SGN(c,1,own), SGN(c,2,own));
-	NEED(W, r);
+	NEED1(W, isH, c, 0, r);
 	return r.p * (isH ? Hcomp(W,0,c) : Ecomp(W,0,c))[r.i][r.j][r.k];
 }
 float rawEx(world W, int i, int j, int k) { return raw_component(W, 0, 0, i, j, k); }
@@ -100,14 +102,14 @@ static float e_component(world W, int m, int c, int i, int j, int k)
 {
 	if (m && !W->complexField) return 0;
 	folded r = fold_cos(W, i, j, k, 0.5, SGN(c,0,1), SGN(c,1,1), SGN(c,2,1));
-	NEED(W, r);
+	NEED1(W, 0, c, m, r);
 	return r.p * e_pair(Ecomp(W,m,c), c, r.i, r.j, r.k);
 }
 static float h_component(world W, int m, int c, int i, int j, int k)
 {
 	if (m && !W->complexField) return 0;
 	folded r = fold_cos(W, i, j, k, 0.25, SGN(c,0,-1), SGN(c,1,-1), SGN(c,2,-1));
-	NEED(W, r);
+	NEED1(W, 1, c, m, r);
 	return r.p * h_quad(Hcomp(W,m,c), c, r.i, r.j, r.k);
 }
 float Ex(world W, int i, int j, int k)  { return e_component(W, 0, 0, i, j, k); }
@@ -453,3 +455,24 @@ float ScEx(world W, int i, int j, int k) { return scattered_E(W, 0, i, j, k); }
 float ScEy(world W, int i, int j, int k) { return scattered_E(W, 1, i, j, k); }
 float ScEz(world W, int i, int j, int k) { return scattered_E(W, 2, i, j, k); }
 float ScEE(world W, int i, int j, int k) { return sq(ScEx(W,i,j,k))+sq(ScEy(W,i,j,k))+sq(ScEz(W,i,j,k)); }
+
+
+/* ---- which host views a field function reads (bit (m*2+set)*3+comp); used by the region
+ * prefetch of slices and world reductions so that e.g. a slice of Hz moves one array only ---------- */
+unsigned alis_field_arrays(world W, field F)
+{
+	field *Ec[2][3] = { {Ex, Ey, Ez}, {iEx, iEy, iEz} }, *Hc[2][3] = { {Hx, Hy, Hz}, {iHx, iHy, iHz} };
+	field *rawE[3] = { rawEx, rawEy, rawEz }, *rawH[3] = { rawHx, rawHy, rawHz };
+	for (int m=0; m<2; m++) for (int c=0; c<3; c++) {
+		if (F == Ec[m][c]) return 1u << ((m*2+0)*3+c);
+		if (F == Hc[m][c]) return 1u << ((m*2+1)*3+c);
+	}
+	for (int c=0; c<3; c++) {
+		if (F == rawE[c]) return 1u << c;
+		if (F == rawH[c]) return 1u << (3+c);
+	}
+	if (F == EE) return 07;
+	if (F == HH || F == UH) return 070;
+	if (F == RI || F == LogRI || F == ContourRI || F == Contour || F == raweEffx || F == raweEffy || F == raweEffz || F == eEff) return 0;
+	return W->complexField ? 07777 : 077;
+}

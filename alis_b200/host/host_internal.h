@@ -25,7 +25,10 @@ void alis_host_touch(world W);                  /* device state advanced: host v
 /* host views: make W->E[m].{x,y,z}, W->H[m].{x,y,z} valid on [i0-1..i1+1]x[j0-1..j1+1]x[k0-1..k1+1]
  * (clipped to the allocation), for every field set m, including TFSF aux worlds */
 void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1);
+void alis_view_need_arr(world W, int set, int comp, int m, int i0, int i1, int j0, int j1, int k0, int k1);   /* one array only */
 void alis_view_need_all(world W);
+unsigned alis_field_arrays(world W, field F);   /* bit (m*2+set)*3+comp for every host view F reads */
+void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* only the arrays F reads */
 void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
 void alis_view_free(world W);
 

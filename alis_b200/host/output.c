@@ -62,7 +62,7 @@ float get(world W, field F, float x, float y, float z)
 float worldMax(world W, field F)
 {
 	float best = 0, f;
-	alis_view_need(W, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
+	alis_view_need_for(W, F, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
 	for (int i=W->iMin; i<W->iMax; i++) for (int j=W->jMin; j<W->jMax; j++) for (int k=W->kMin; k<W->kMax; k++)
 		if (best < (f=fabsf(F(W, i, j, k)))) best = f;
 	return best;
@@ -90,7 +90,7 @@ static float sheet_sum(world W, field F, int i)
 float worldSum(world W, field F)
 {
 	float Sum = 0;
-	alis_view_need(W, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
+	alis_view_need_for(W, F, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
 	for (int i=W->iMin+1; i<W->iMax; i++) Sum += W->CE->dx[i] * sheet_sum(W, F, i);
 	Sum += 0.5 * W->CE->dx[W->iMin] * sheet_sum(W, F, W->iMin);
 	Sum += 0.5 * W->CE->dx[W->iMax] * sheet_sum(W, F, W->iMax);

@@ -48,7 +48,7 @@ static sentry *lookup(world W, char *name, method M, sentry **list)
 }
 
 /* bring the slice region (mirror images folded back) into the host views */
-static void prefetch(world W, slice S)
+static void prefetch(world W, field F, slice S)
 {
 	int lo[3] = { S->iMin, S->jMin, S->kMin }, hi[3] = { S->iMax, S->jMax, S->kMax };
 	const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
@@ -57,7 +57,7 @@ static void prefetch(world W, slice S)
 		lo[a] = hi[a] < 0 ? -hi[a] : 0;
 		hi[a] = far;
 	}
-	alis_view_need(W, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
+	alis_view_need_for(W, F, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
 }
 
 /* ---- resampling a graded grid onto the uniform raster (reference slices.c:25-64) --------------------- */
@@ -305,7 +305,7 @@ static void expand_name(char *filename, const char *f, const char *s)
 static float sample(world W, field F, slice S, float ***dst)
 {
 	float max = 0;
-	prefetch(W, S);
+	prefetch(W, F, S);
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
 		if (max < fabsf(dst[i][j][k] = F(W, i, j, k))) max = fabsf(dst[i][j][k]);
 	return max;
@@ -363,7 +363,7 @@ void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 	if (N) sprintf(string, "%05ld", e->calls / N), strcat(filename, string);
 
 	if (e->calls == 1) e->F = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
-	prefetch(W, S);
+	prefetch(W, F, S);
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
 		e->F[i][j][k] += F(W, i, j, k);
 
@@ -406,7 +406,7 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 	}
 	float real = cosf(2 * PI * e->calls * W->dt / L);
 	float imag = sinf(2 * PI * e->calls * W->dt / L);
-	prefetch(W, S);
+	prefetch(W, F, S);
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++) {
 		e->F[i][j][k] += F(W, i, j, k) * real;
 		e->G[i][j][k] += F(W, i, j, k) * imag;
@@ -432,7 +432,7 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 float sliceMax(world W, field F, slice S)
 {
 	float best = 0, f;
-	prefetch(W, S);
+	prefetch(W, F, S);
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
 		if (best < (f=fabsf(F(W, i, j, k)))) best = f;
 	return best;
@@ -459,7 +459,7 @@ static float sheet_sum(world W, field F, slice S, int i)
 float sliceSum(world W, field F, slice S)
 {
 	float Sum = 0;
-	prefetch(W, S);
+	prefetch(W, F, S);
 	for (int i=S->iMin+1; i<S->iMax; i++) Sum += W->CE->dx[i] * sheet_sum(W, F, S, i);
 	Sum += 0.5 * W->CE->dx[S->iMin] * sheet_sum(W, F, S, S->iMin);
 	Sum += 0.5 * W->CE->dx[S->iMax] * sheet_sum(W, F, S, S->iMax);

@@ -12,10 +12,11 @@
 #include "alis_c.h"
 #include "host_internal.h"
 
+typedef struct { unsigned long synced; int box[6], have; } arr_state;
+
 typedef struct {
 	unsigned long version;        /* bumped whenever the device state advances              */
-	unsigned long synced;         /* version the synced box belongs to                      */
-	int box[6], have_box;
+	arr_state arr[2][2][3];       /* [m][set][comp]: which box of each host view is current  */
 	unsigned long ade_synced; int have_ade;
 } view_state;
 
@@ -31,56 +32,69 @@ void alis_host_touch(world W)
 	for (tfsf S = W->S; S; S = S->S) alis_host_touch(S->W);
 }
 
-static void ensure_arrays(world W)
+static float ***view_array(world W, int set, int comp, int m)
 {
-	for (int m=0; m<=W->complexField; m++) {
-		vfield *V[2] = { &W->E[m], &W->H[m] };
-		for (int s=0; s<2; s++) {
-			if (!V[s]->x) V[s]->x = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
-			if (!V[s]->y) V[s]->y = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
-			if (!V[s]->z) V[s]->z = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
-		}
-	}
+	vfield *V = set == 0 ? &W->E[m] : &W->H[m];
+	float ****slot = comp == 0 ? &V->x : comp == 1 ? &V->y : &V->z;
+	if (!*slot) *slot = makeField(W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
+	return *slot;
 }
 
-static void pull_box(world W, const int b[6])
+static void pull_box(world W, int set, int comp, int m, const int b[6])
 {
 	alisb_engine *E = alis_bridge_engine(alis_host_bridge(W));
-	const int ni = b[1]-b[0]+1, nj = b[3]-b[2]+1, nk = b[5]-b[4]+1;
+	const int nj = b[3]-b[2]+1, nk = b[5]-b[4]+1;
 	int32_t box[6] = { b[0]-(W->iMIN-1), b[1]-(W->iMIN-1), b[2]-(W->jMIN-1), b[3]-(W->jMIN-1), b[4]-(W->kMIN-1), b[5]-(W->kMIN-1) };
-	float *tmp = malloc(sizeof(float)*(size_t)ni*nj*nk);
-	for (int m=0; m<=W->complexField; m++) for (int set=0; set<2; set++) for (int comp=0; comp<3; comp++) {
-		int32_t ids[6] = { set, comp, m, 0, 0, 0 };
-		if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
-		vfield *V = set == 0 ? &W->E[m] : &W->H[m];
-		float ***A = comp == 0 ? V->x : comp == 1 ? V->y : V->z;
-		size_t q = 0;
-		for (int i=b[0]; i<=b[1]; i++) for (int j=b[2]; j<=b[3]; j++) { memcpy(&A[i][j][b[4]], tmp+q, sizeof(float)*nk); q += nk; }
+	int32_t ids[6] = { set, comp, m, 0, 0, 0 };
+	float ***A = view_array(W, set, comp, m);
+	const int whole_rows = b[4] == W->kMIN-1 && b[5] == W->kMAX+1, whole_sheets = whole_rows && b[2] == W->jMIN-1 && b[3] == W->jMAX+1;
+	if (whole_sheets) {                        /* contiguous in the host view: read straight into it */
+		if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, &A[b[0]][b[2]][b[4]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		return;
 	}
+	float *tmp = malloc(sizeof(float)*(size_t)(b[1]-b[0]+1)*nj*nk);
+	if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	size_t q = 0;
+	for (int i=b[0]; i<=b[1]; i++) for (int j=b[2]; j<=b[3]; j++) { memcpy(&A[i][j][b[4]], tmp+q, sizeof(float)*nk); q += nk; }
 	free(tmp);
 }
 
-void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1)
+/* make host view (set, comp, m) current on [i0-1..i1+1] x [j0-1..j1+1] x [k0-1..k1+1] (clipped) */
+void alis_view_need_arr(world W, int set, int comp, int m, int i0, int i1, int j0, int j1, int k0, int k1)
 {
 	view_state *v = state(W);
+	arr_state *a = &v->arr[m][set][comp];
 	int b[6] = { MAX(i0-1, W->iMIN-1), MIN(i1+1, W->iMAX+1), MAX(j0-1, W->jMIN-1), MIN(j1+1, W->jMAX+1), MAX(k0-1, W->kMIN-1), MIN(k1+1, W->kMAX+1) };
-	ensure_arrays(W);
-	if (b[0] > b[1] || b[2] > b[3] || b[4] > b[5]) return;
-	if (v->have_box && v->synced == v->version &&
-	    v->box[0] <= b[0] && b[1] <= v->box[1] && v->box[2] <= b[2] && b[3] <= v->box[3] && v->box[4] <= b[4] && b[5] <= v->box[5]) return;
-	/* grow the working set: monitors called every step (probes, flux boxes) ask for the same
-	 * regions again, so fetch the union with the previous request unless that is wasteful */
-	if (v->have_box) {
+	if (b[0] > b[1] || b[2] > b[3] || b[4] > b[5]) { view_array(W, set, comp, m); return; }
+	if (a->have && a->synced == v->version &&
+	    a->box[0] <= b[0] && b[1] <= a->box[1] && a->box[2] <= b[2] && b[3] <= a->box[3] && a->box[4] <= b[4] && b[5] <= a->box[5]) return;
+	/* grow the working set: monitors called every step (probes, slices) ask for the same regions
+	 * again, so fetch the union with the previous request unless that is wasteful */
+	if (a->have) {
 		int u[6];
-		for (int a=0; a<3; a++) u[2*a] = MIN(b[2*a], v->box[2*a]), u[2*a+1] = MAX(b[2*a+1], v->box[2*a+1]);
+		for (int q=0; q<3; q++) u[2*q] = MIN(b[2*q], a->box[2*q]), u[2*q+1] = MAX(b[2*q+1], a->box[2*q+1]);
 		const double vu = (double)(u[1]-u[0]+1)*(u[3]-u[2]+1)*(u[5]-u[4]+1);
 		const double vb = (double)(b[1]-b[0]+1)*(b[3]-b[2]+1)*(b[5]-b[4]+1);
-		const double vo = (double)(v->box[1]-v->box[0]+1)*(v->box[3]-v->box[2]+1)*(v->box[5]-v->box[4]+1);
+		const double vo = (double)(a->box[1]-a->box[0]+1)*(a->box[3]-a->box[2]+1)*(a->box[5]-a->box[4]+1);
 		if (vu <= 4*(vb+vo) + 4096) memcpy(b, u, sizeof u);
 	}
-	pull_box(W, b);
-	memcpy(v->box, b, sizeof b);
-	v->have_box = 1; v->synced = v->version;
+	pull_box(W, set, comp, m, b);
+	memcpy(a->box, b, sizeof b);
+	a->have = 1; a->synced = v->version;
+}
+
+/* all components of both field sets (monitors that mix E and H) */
+void alis_view_need(world W, int i0, int i1, int j0, int j1, int k0, int k1)
+{
+	for (int m=0; m<=W->complexField; m++) for (int set=0; set<2; set++) for (int comp=0; comp<3; comp++)
+		alis_view_need_arr(W, set, comp, m, i0, i1, j0, j1, k0, k1);
+}
+
+void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1)
+{
+	const unsigned mask = alis_field_arrays(W, F);
+	for (int m=0; m<=W->complexField; m++) for (int set=0; set<2; set++) for (int comp=0; comp<3; comp++)
+		if (mask & (1u << ((m*2+set)*3+comp))) alis_view_need_arr(W, set, comp, m, i0, i1, j0, j1, k0, k1);
 }
 
 void alis_view_need_all(world W)
