@@ -81,6 +81,7 @@ struct alisb_engine {
 	std::vector<ProfRec> prof;         /* one record per profiled volume sub-launch          */
 	float *scratch; size_t scratch_elems;
 	float *spacing[2][3];              /* cell sizes per field set and axis (array coords)  */
+	float *srcv_h[SRC_RING], *srcv_d[SRC_RING]; cudaEvent_t srcv_ev[SRC_RING]; size_t srcv_cap; int srcv_slot;   /* per-cell source values of one pass */
 	FluxPlane *d_planes; double *d_partial, *d_flux, *h_flux; int flux_cap;
 };
 
@@ -149,6 +150,8 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
 	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
+	for (int r=0; r<SRC_RING; r++) { e->srcv_h[r] = 0; e->srcv_d[r] = 0; e->srcv_ev[r] = 0; }
+	e->srcv_cap = 0; e->srcv_slot = 0;
 	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
@@ -246,6 +249,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	cudaEventDestroy(e->ev_fork);
 	cudaFree(e->scratch);
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
+	for (int r=0; r<SRC_RING; r++) { if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]); cudaFree(e->srcv_d[r]); if (e->srcv_ev[r]) cudaEventDestroy(e->srcv_ev[r]); }
 	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
 	if (e->own_stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -578,6 +582,62 @@ static int ade_post(alisb_engine *e, int m)
 
 static int apply_sources(alisb_engine *e, int set, float t)
 {
+	/* fused path: every active source of the pass in one launch (small boxes only) */
+	{
+		SrcList L;
+		L.n = 0; L.ny = e->ny; L.pitch = e->pitch;
+		size_t nvals = 0;
+		bool ok = true;
+		for (SrcObj *s : e->src[set]) {
+			if (!(e->step < s->d.n_active) || !s->cnt) continue;
+			const Box B = clipc(s->B, e->f_lo, e->f_hi);
+			if (!bcount(B)) continue;
+			if (L.n == ALISB_MAXSRCOPS || s->cnt > 16384) { ok = false; break; }
+			L.n++;
+			if (!s->hPha.empty()) nvals += s->cnt;
+		}
+		if (ok && L.n == 0) return ALISB_OK;
+		if (ok) {
+			float *hv = 0, *dv = 0;
+			int slot = 0;
+			if (nvals) {
+				if (nvals > e->srcv_cap) {
+					CU(cudaStreamSynchronize(e->stream));
+					for (int r=0; r<SRC_RING; r++) {
+						if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]);
+						cudaFree(e->srcv_d[r]);
+						CU(cudaMallocHost((void**)&e->srcv_h[r], nvals*sizeof(float)));
+						TRY(dalloc(&e->srcv_d[r], nvals));
+						if (!e->srcv_ev[r]) CU(cudaEventCreateWithFlags(&e->srcv_ev[r], cudaEventDisableTiming));
+					}
+					e->srcv_cap = nvals;
+				}
+				slot = e->srcv_slot; e->srcv_slot = (e->srcv_slot + 1) % SRC_RING;
+				CU(cudaEventSynchronize(e->srcv_ev[slot]));
+				hv = e->srcv_h[slot]; dv = e->srcv_d[slot];
+			}
+			size_t off = 0;
+			int k = 0;
+			for (SrcObj *s : e->src[set]) {
+				if (!(e->step < s->d.n_active) || !s->cnt) continue;
+				const Box B = clipc(s->B, e->f_lo, e->f_hi);
+				if (!bcount(B)) continue;
+				SrcOp &o = L.op[k++];
+				o.F = e->F[set][s->d.m][s->d.comp]; o.B = B; o.full = s->B; o.vals = 0; o.amp = s->dAmp; o.amplitude = s->d.amplitude; o.f = 0.f;
+				if (!s->hPha.empty()) {
+					for (size_t q=0; q<s->cnt; q++)
+						hv[off + q] = (s->hAmp.empty() ? s->d.amplitude : s->hAmp[q]) * s->d.waveform(s->d.user, t, s->hPha[q]);
+					o.vals = dv + off; off += s->cnt;
+				} else o.f = s->d.waveform(s->d.user, t, s->d.phase);
+			}
+			if (nvals) CU(cudaMemcpyAsync(dv, hv, nvals*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+			source_list<<<1, 1024, 0, e->stream>>>(L);
+			if (nvals) CU(cudaEventRecord(e->srcv_ev[slot], e->stream));
+			e->launches++;
+			CU(cudaGetLastError());
+			return ALISB_OK;
+		}
+	}
 	for (SrcObj *s : e->src[set]) {
 		if (!(e->step < s->d.n_active) || !s->cnt) continue;
 		const Box B = clipc(s->B, e->f_lo, e->f_hi);
@@ -611,6 +671,26 @@ static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; }
 		if (step_aux) TRY(set == ALISB_SET_E ? alisb_step_E(x) : alisb_step_H(x));
 		const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
+		/* small faces: all strips of this TFSF region in one single-CTA launch */
+		{
+			StripList SL;
+			SL.n = 0; SL.ny = e->ny; SL.pitch = e->pitch; SL.any = x->ny; SL.apitch = x->pitch;
+			bool ok = true;
+			for (int m=0; m<=e->g.complex_field && ok; m++) for (const alisb_strip &s : L) {
+				Box B = clipc(mkbox(s.box), e->f_lo, e->f_hi);
+				const size_t n = bcount(B);
+				if (!n) continue;
+				if (n > 16384 || SL.n == ALISB_MAXSTRIPOPS) { ok = false; break; }
+				StripOp &o = SL.op[SL.n++];
+				o.F = e->F[set][m][s.comp]; o.G = x->F[1-set][m][s.aux_comp]; o.C = s.use_eps ? e->eps[s.comp] : 0; o.coef = s.coef; o.B = B;
+				o.alt0 = s.alt[0] + t->d.offset[0]; o.alt1 = s.alt[1] + t->d.offset[1]; o.alt2 = s.alt[2] + t->d.offset[2];
+				o.clampa = t->d.clamp[1-set][s.aux_comp][0]; o.clampb = t->d.clamp[1-set][s.aux_comp][1];
+			}
+			if (ok) {
+				if (SL.n) { strip_list<<<1, 1024, 0, e->stream>>>(SL); e->launches++; }
+				continue;
+			}
+		}
 		for (int m=0; m<=e->g.complex_field; m++) for (const alisb_strip &s : L) {
 			Box B = clipc(mkbox(s.box), e->f_lo, e->f_hi);
 			const size_t n = bcount(B);

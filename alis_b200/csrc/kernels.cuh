@@ -407,6 +407,53 @@ __global__ void __launch_bounds__(1024) copy_list(const __grid_constant__ CopyLi
 	}
 }
 
+/* All soft sources of a pass (reference updateS list, update.c:161-179) and all TFSF strips of a
+ * pass (update.c:205-272) in one single-CTA launch each, in list order (overlapping boxes add in
+ * the reference's order). */
+#define ALISB_MAXSRCOPS 16
+struct SrcOp { float *F; Box B, full; const float *vals, *amp; float amplitude, f; };
+struct SrcList { SrcOp op[ALISB_MAXSRCOPS]; int n, ny, pitch; };
+
+__global__ void __launch_bounds__(1024) source_list(const __grid_constant__ SrcList L)
+{
+	const int ny = L.ny, pitch = L.pitch;
+	for (int k = 0; k < L.n; k++) {
+		const SrcOp &o = L.op[k];
+		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
+		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+			int a, b, c; size_t q;
+			box_cell(o.B, t, a, b, c, q);
+			q = ((size_t)(c - o.full.c0)*o.full.nb + (b - o.full.b0))*o.full.na + (a - o.full.a0);
+			const float v = o.vals ? o.vals[q] : (o.amp ? o.amp[q] : o.amplitude) * o.f;
+			L.op[k].F[GIDX(a, b, c)] += v;
+		}
+		__syncthreads();
+	}
+}
+
+#define ALISB_MAXSTRIPOPS 48
+struct StripOp { float *F; const float *G, *C; float coef; Box B; int alt0, alt1, alt2, clampa, clampb; };
+struct StripList { StripOp op[ALISB_MAXSTRIPOPS]; int n, ny, pitch, any, apitch; };
+
+__global__ void __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L)
+{
+	const int ny = L.ny, pitch = L.pitch;
+	for (int k = 0; k < L.n; k++) {
+		const StripOp &o = L.op[k];
+		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
+		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+			int a, b, c; size_t q;
+			box_cell(o.B, t, a, b, c, q);
+			const size_t i = GIDX(a, b, c);
+			const int xa = min(a + o.alt0, o.clampa), xb = min(b + o.alt1, o.clampb), xc = c + o.alt2;
+			const float g = o.G[((size_t)xc*(L.any + 2) + xb)*L.apitch + ALISB_XO + xa];
+			if (o.C) o.F[i] += o.coef*g*o.C[i];
+			else     o.F[i] += o.coef*g;
+		}
+		__syncthreads();
+	}
+}
+
 /* gather / scatter a box between any engine array (element (a,b,c) at c*sC + b*sB + a + off) and a
  * dense buffer in the HOST order (z fastest, reference makeField layout): the transposition is
  * done here so that the host side is a plain memcpy */
