@@ -520,6 +520,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* many short z-chunks balance best  */
 		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* (the carry preload is an L2 hit)  */
 		int nchunks = (int)std::max(1L, std::min(want, maxc));
+		if (tiles*nchunks < 2L*e->resident_ctas) nchunks = (int)std::min((long)nzs, (2L*e->resident_ctas + tiles - 1)/tiles);   /* small grids: fill the GPU */
 		p.cchunk = div_up(nzs, nchunks);
 		nchunks = div_up(nzs, p.cchunk);
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
@@ -631,7 +632,7 @@ static int apply_sources(alisb_engine *e, int set, float t)
 				} else o.f = s->d.waveform(s->d.user, t, s->d.phase);
 			}
 			if (nvals) CU(cudaMemcpyAsync(dv, hv, nvals*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-			source_list<<<1, 1024, 0, e->stream>>>(L);
+			source_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(L);
 			if (nvals) CU(cudaEventRecord(e->srcv_ev[slot], e->stream));
 			e->launches++;
 			CU(cudaGetLastError());
@@ -687,7 +688,7 @@ static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 				o.clampa = t->d.clamp[1-set][s.aux_comp][0]; o.clampb = t->d.clamp[1-set][s.aux_comp][1];
 			}
 			if (ok) {
-				if (SL.n) { strip_list<<<1, 1024, 0, e->stream>>>(SL); e->launches++; }
+				if (SL.n) { strip_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(SL); e->launches++; }
 				continue;
 			}
 		}
@@ -723,10 +724,25 @@ static int apply_copies(alisb_engine *e, int set)
 			CopyOp &o = L.op[L.n++];
 			o.F = e->F[k.set][0][k.comp]; o.G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
 			o.cosk = k.cosk; o.sink = k.sink; o.B = B; o.alt0 = k.alt[0]; o.alt1 = k.alt[1]; o.alt2 = k.alt[2];
+			o.sync_after = 0;
 		}
 	}
 	if (small && total <= 131072) {
-		if (L.n) { copy_list<<<1, 1024, 0, e->stream>>>(L); e->launches++; }
+		/* a barrier is needed between op q and the ops since the last barrier only if they conflict:
+		 * same array and (target x target, target x source or source x target boxes intersect) */
+		auto hits = [](const Box &A, const Box &B) {
+			return A.a0 < B.a0 + B.na && B.a0 < A.a0 + A.na && A.b0 < B.b0 + B.nb && B.b0 < A.b0 + A.nb && A.c0 < B.c0 + B.nc && B.c0 < A.c0 + A.nc; };
+		auto shifted = [](const CopyOp &o) { Box S = o.B; S.a0 += o.alt0; S.b0 += o.alt1; S.c0 += o.alt2; return S; };
+		int level_start = 0;
+		for (int q=1; q<L.n; q++) {
+			bool conflict = false;
+			for (int r=level_start; r<q && !conflict; r++) {
+				if (L.op[r].F != L.op[q].F) continue;
+				conflict = hits(L.op[r].B, L.op[q].B) || hits(L.op[r].B, shifted(L.op[q])) || hits(shifted(L.op[r]), L.op[q].B);
+			}
+			if (conflict) { L.op[q-1].sync_after = 1; level_start = q; }
+		}
+		if (L.n) { copy_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(L); e->launches++; }
 		CU(cudaGetLastError());
 		return ALISB_OK;
 	}

@@ -384,16 +384,23 @@ __global__ void copy_plane(float *F, float *G, float cosk, float sink, Box B, in
  * a single CTA walks the list and separates the (order-dependent) copies with __syncthreads().
  * Cuts a Bloch/hexagonal H pass from 16 tiny launches to one. */
 #define ALISB_MAXCOPIES 24
-struct CopyOp { float *F, *G; float cosk, sink; Box B; int alt0, alt1, alt2; };
+#define ALISB_LIST_CTAS 8          /* one thread-block cluster walks a list; cluster.sync() separates dependent ops */
+struct CopyOp { float *F, *G; float cosk, sink; Box B; int alt0, alt1, alt2; int sync_after; };
 struct CopyList { CopyOp op[ALISB_MAXCOPIES]; int n, ny, pitch; };
 
-__global__ void __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L)
+static __device__ __forceinline__ void list_sync()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L)
 {
 	const int ny = L.ny, pitch = L.pitch;
+	const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nth = (size_t)gridDim.x*blockDim.x;
 	for (int k = 0; k < L.n; k++) {
 		const CopyOp &o = L.op[k];
 		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
-		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+		for (size_t t = tid; t < cells; t += nth) {
 			int a, b, c; size_t q;
 			box_cell(o.B, t, a, b, c, q);
 			const size_t i = GIDX(a, b, c), j = GIDX(a + o.alt0, b + o.alt1, c + o.alt2);
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(1024) copy_list(const __grid_constant__ CopyLi
 				o.G[i] = o.cosk*g - o.sink*f;
 			} else o.F[i] = o.cosk*o.F[j];
 		}
-		__syncthreads();
+		if (o.sync_after) list_sync();          /* the next op reads or overwrites what this level wrote */
 	}
 }
 
@@ -414,20 +421,21 @@ __global__ void __launch_bounds__(1024) copy_list(const __grid_constant__ CopyLi
 struct SrcOp { float *F; Box B, full; const float *vals, *amp; float amplitude, f; };
 struct SrcList { SrcOp op[ALISB_MAXSRCOPS]; int n, ny, pitch; };
 
-__global__ void __launch_bounds__(1024) source_list(const __grid_constant__ SrcList L)
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) source_list(const __grid_constant__ SrcList L)
 {
 	const int ny = L.ny, pitch = L.pitch;
+	const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nth = (size_t)gridDim.x*blockDim.x;
 	for (int k = 0; k < L.n; k++) {
 		const SrcOp &o = L.op[k];
 		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
-		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+		for (size_t t = tid; t < cells; t += nth) {
 			int a, b, c; size_t q;
 			box_cell(o.B, t, a, b, c, q);
 			q = ((size_t)(c - o.full.c0)*o.full.nb + (b - o.full.b0))*o.full.na + (a - o.full.a0);
 			const float v = o.vals ? o.vals[q] : (o.amp ? o.amp[q] : o.amplitude) * o.f;
 			L.op[k].F[GIDX(a, b, c)] += v;
 		}
-		__syncthreads();
+		if (k + 1 < L.n) list_sync();
 	}
 }
 
@@ -435,13 +443,14 @@ __global__ void __launch_bounds__(1024) source_list(const __grid_constant__ SrcL
 struct StripOp { float *F; const float *G, *C; float coef; Box B; int alt0, alt1, alt2, clampa, clampb; };
 struct StripList { StripOp op[ALISB_MAXSTRIPOPS]; int n, ny, pitch, any, apitch; };
 
-__global__ void __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L)
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L)
 {
 	const int ny = L.ny, pitch = L.pitch;
+	const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nth = (size_t)gridDim.x*blockDim.x;
 	for (int k = 0; k < L.n; k++) {
 		const StripOp &o = L.op[k];
 		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
-		for (size_t t = threadIdx.x; t < cells; t += blockDim.x) {
+		for (size_t t = tid; t < cells; t += nth) {
 			int a, b, c; size_t q;
 			box_cell(o.B, t, a, b, c, q);
 			const size_t i = GIDX(a, b, c);
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(1024) strip_list(const __grid_constant__ Strip
 			if (o.C) o.F[i] += o.coef*g*o.C[i];
 			else     o.F[i] += o.coef*g;
 		}
-		__syncthreads();
+		if (k + 1 < L.n) list_sync();
 	}
 }
 
