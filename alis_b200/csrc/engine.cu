@@ -32,6 +32,16 @@ static int fail(int code, const char *fmt, ...)
 
 struct SubBox { int a0, a1, b0, b1, c0, c1; int pml; };   /* cell ranges; pml: bit 0/1/2 = may touch x/y/z slabs */
 struct ProfRec { size_t ev; int set, sub; };
+struct alisb_engine;
+/* a whole pass (all kernels of updateE or updateH, auxiliary TFSF worlds included) captured once as
+ * a CUDA graph and replayed; the only per-step parameters are the source lists, whose kernel nodes
+ * are updated in place before each launch */
+struct SrcNode { alisb_engine *eng; int set; cudaGraphNode_t node; };
+struct PassGraph { cudaGraphExec_t exec; cudaGraph_t graph; std::vector<SrcNode> nodes; uint64_t version; int nkernels; };
+enum { GMODE_NONE = 0, GMODE_CAPTURE = 1 };
+static thread_local int g_mode = GMODE_NONE;
+static thread_local std::vector<SrcNode> *g_nodes = 0;
+static thread_local int g_nkernels = 0;
 
 struct DispObj {
 	alisb_dispersive d;
@@ -82,6 +92,10 @@ struct alisb_engine {
 	float *scratch; size_t scratch_elems;
 	float *spacing[2][3];              /* cell sizes per field set and axis (array coords)  */
 	float *srcv_h[SRC_RING], *srcv_d[SRC_RING]; cudaEvent_t srcv_ev[SRC_RING]; size_t srcv_cap; int srcv_slot;   /* per-cell source values of one pass */
+	SrcList cur_src[2]; bool cur_src_fused[2]; int cur_src_slot[2];   /* what pass_prepare set up for the pass being issued */
+	uint64_t cfg_version;              /* bumped by every call that changes what a pass launches */
+	bool graph_ok;                     /* CUDA-graph replay of whole passes allowed (ALISB_GRAPH, no per-source fallback path) */
+	PassGraph graph[2][3];             /* [set][part] */
 	FluxPlane *d_planes; double *d_partial, *d_flux, *h_flux; int flux_cap;
 };
 
@@ -151,6 +165,9 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
 	for (int r=0; r<SRC_RING; r++) { e->srcv_h[r] = 0; e->srcv_d[r] = 0; e->srcv_ev[r] = 0; }
+	e->cfg_version = 1; e->cur_src_fused[0] = e->cur_src_fused[1] = false; e->cur_src_slot[0] = e->cur_src_slot[1] = -1;
+	for (int a=0; a<2; a++) for (int b=0; b<3; b++) { e->graph[a][b].exec = 0; e->graph[a][b].graph = 0; e->graph[a][b].version = 0; e->graph[a][b].nkernels = 0; }
+	{ const char *gs = getenv("ALISB_GRAPH"); e->graph_ok = gs ? atoi(gs) != 0 : true; }
 	e->srcv_cap = 0; e->srcv_slot = 0;
 	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
@@ -213,6 +230,7 @@ static void free_src(SrcObj *s)
 
 extern "C" int alisb_clear_sources(alisb_engine *e)
 {
+	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
 	for (int s=0; s<2; s++) { for (SrcObj *o : e->src[s]) free_src(o); e->src[s].clear(); }
@@ -223,6 +241,7 @@ extern "C" int alisb_clear_sources(alisb_engine *e)
 
 extern "C" int alisb_clear_dispersive(alisb_engine *e)
 {
+	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
 	for (DispObj *o : e->obj) {
@@ -244,6 +263,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int c=0; c<3; c++) cudaFree(e->eps[c]);
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { cudaFree(e->dtd[s][ax]); cudaFree(e->P[s][ax]); cudaFree(e->P1[s][ax]); cudaFree(e->P2[s][ax]); }
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psi[s][m][ax][sd][w]);
+	for (int a=0; a<2; a++) for (int b=0; b<3; b++) { if (e->graph[a][b].exec) cudaGraphExecDestroy(e->graph[a][b].exec); if (e->graph[a][b].graph) cudaGraphDestroy(e->graph[a][b].graph); }
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
@@ -257,6 +277,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 
 extern "C" int alisb_set_stream(alisb_engine *e, void *s)
 {
+	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
 	if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
@@ -276,6 +297,7 @@ static int upload_table(alisb_engine *e, float *dst, const float *src, int n, in
 
 extern "C" int alisb_set_axis_tables(alisb_engine *e, int set, int axis, const float *dtd, const float *P, const float *P1, const float *P2)
 {
+	e->cfg_version++;
 	if (set<0 || set>1 || axis<0 || axis>2 || !dtd) return fail(ALISB_EINVAL, "bad tables");
 	DEV(e);
 	const int n = axis==0 ? e->nx : axis==1 ? e->ny : e->nz, shift = axis==0 ? ALISB_XO : 0;
@@ -288,6 +310,7 @@ extern "C" int alisb_set_axis_tables(alisb_engine *e, int set, int axis, const f
 
 extern "C" int alisb_set_inv_eps(alisb_engine *e, const float *cx, const float *cy, const float *cz)
 {
+	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
 	const float *src[3] = {cx, cy, cz};
@@ -320,6 +343,7 @@ static int upload_box(float **dst, const float *zfast, const Box &B)
 
 extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
 {
+	e->cfg_version++;
 	if (!d || d->nk > ALISB_MAXPOLES || d->nj > d->nk || d->nk < 0) return fail(ALISB_EINVAL, "bad pole counts");
 	DEV(e);
 	DispObj *o = new DispObj();
@@ -342,6 +366,7 @@ extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
 
 extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
 {
+	e->cfg_version++;
 	if (!s || s->set<0 || s->set>1 || s->comp<0 || s->comp>2 || s->m<0 || s->m>e->g.complex_field || !s->waveform) return fail(ALISB_EINVAL, "bad source");
 	DEV(e);
 	SrcObj *o = new SrcObj();
@@ -367,6 +392,7 @@ extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
 
 extern "C" int alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t)
 {
+	e->cfg_version++;
 	if (!t || !t->aux) return fail(ALISB_EINVAL, "bad tfsf");
 	TfsfObj *o = new TfsfObj();
 	o->d = *t;
@@ -378,6 +404,7 @@ extern "C" int alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t)
 
 extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops, int n)
 {
+	e->cfg_version++;
 	if (set<0 || set>1 || n<0) return fail(ALISB_EINVAL, "bad copies");
 	e->copies[set].assign(ops, ops + n);
 	return ALISB_OK;
@@ -581,63 +608,80 @@ static int ade_post(alisb_engine *e, int m)
 	return ALISB_OK;
 }
 
-static int apply_sources(alisb_engine *e, int set, float t)
+/* Sources of a pass in three phases so that a pass can be replayed as a CUDA graph:
+ *   prepare_sources  host: waveform samples with the caller's libm, per-cell values uploaded
+ *                    (stream-ordered, before the pass), the SrcList kernel argument filled
+ *   launch_sources   the source_list kernel (its node is the one updated on graph replay)
+ *   finish_sources   ring-buffer bookkeeping                                                */
+static int prepare_sources(alisb_engine *e, int set, float t)
 {
-	/* fused path: every active source of the pass in one launch (small boxes only) */
-	{
-		SrcList L;
-		L.n = 0; L.ny = e->ny; L.pitch = e->pitch;
-		size_t nvals = 0;
-		bool ok = true;
-		for (SrcObj *s : e->src[set]) {
-			if (!(e->step < s->d.n_active) || !s->cnt) continue;
-			const Box B = clipc(s->B, e->f_lo, e->f_hi);
-			if (!bcount(B)) continue;
-			if (L.n == ALISB_MAXSRCOPS || s->cnt > 16384) { ok = false; break; }
-			L.n++;
-			if (!s->hPha.empty()) nvals += s->cnt;
-		}
-		if (ok && L.n == 0) return ALISB_OK;
-		if (ok) {
-			float *hv = 0, *dv = 0;
-			int slot = 0;
-			if (nvals) {
-				if (nvals > e->srcv_cap) {
-					CU(cudaStreamSynchronize(e->stream));
-					for (int r=0; r<SRC_RING; r++) {
-						if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]);
-						cudaFree(e->srcv_d[r]);
-						CU(cudaMallocHost((void**)&e->srcv_h[r], nvals*sizeof(float)));
-						TRY(dalloc(&e->srcv_d[r], nvals));
-						if (!e->srcv_ev[r]) CU(cudaEventCreateWithFlags(&e->srcv_ev[r], cudaEventDisableTiming));
-					}
-					e->srcv_cap = nvals;
-				}
-				slot = e->srcv_slot; e->srcv_slot = (e->srcv_slot + 1) % SRC_RING;
-				CU(cudaEventSynchronize(e->srcv_ev[slot]));
-				hv = e->srcv_h[slot]; dv = e->srcv_d[slot];
+	SrcList &L = e->cur_src[set];
+	L.n = 0; L.ny = e->ny; L.pitch = e->pitch;
+	e->cur_src_slot[set] = -1;
+	e->cur_src_fused[set] = true;
+	size_t nvals = 0;
+	int nact = 0;
+	for (SrcObj *s : e->src[set]) {
+		if (s->cnt > 16384) e->cur_src_fused[set] = false;           /* big planes: per-source launches */
+		if (!(e->step < s->d.n_active) || !s->cnt) continue;
+		const Box B = clipc(s->B, e->f_lo, e->f_hi);
+		if (!bcount(B)) continue;
+		nact++;
+		if (!s->hPha.empty()) nvals += s->cnt;
+	}
+	if (nact > ALISB_MAXSRCOPS) e->cur_src_fused[set] = false;
+	if (!e->cur_src_fused[set] || nact == 0) return ALISB_OK;
+	float *hv = 0, *dv = 0;
+	if (nvals) {
+		if (nvals > e->srcv_cap) {
+			CU(cudaStreamSynchronize(e->stream));
+			for (int r=0; r<SRC_RING; r++) {
+				if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]);
+				cudaFree(e->srcv_d[r]);
+				CU(cudaMallocHost((void**)&e->srcv_h[r], nvals*sizeof(float)));
+				TRY(dalloc(&e->srcv_d[r], nvals));
+				if (!e->srcv_ev[r]) CU(cudaEventCreateWithFlags(&e->srcv_ev[r], cudaEventDisableTiming));
 			}
-			size_t off = 0;
-			int k = 0;
-			for (SrcObj *s : e->src[set]) {
-				if (!(e->step < s->d.n_active) || !s->cnt) continue;
-				const Box B = clipc(s->B, e->f_lo, e->f_hi);
-				if (!bcount(B)) continue;
-				SrcOp &o = L.op[k++];
-				o.F = e->F[set][s->d.m][s->d.comp]; o.B = B; o.full = s->B; o.vals = 0; o.amp = s->dAmp; o.amplitude = s->d.amplitude; o.f = 0.f;
-				if (!s->hPha.empty()) {
-					for (size_t q=0; q<s->cnt; q++)
-						hv[off + q] = (s->hAmp.empty() ? s->d.amplitude : s->hAmp[q]) * s->d.waveform(s->d.user, t, s->hPha[q]);
-					o.vals = dv + off; off += s->cnt;
-				} else o.f = s->d.waveform(s->d.user, t, s->d.phase);
-			}
-			if (nvals) CU(cudaMemcpyAsync(dv, hv, nvals*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-			source_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(L);
-			if (nvals) CU(cudaEventRecord(e->srcv_ev[slot], e->stream));
-			e->launches++;
-			CU(cudaGetLastError());
-			return ALISB_OK;
+			e->srcv_cap = nvals;
 		}
+		const int slot = e->srcv_slot; e->srcv_slot = (e->srcv_slot + 1) % SRC_RING;
+		CU(cudaEventSynchronize(e->srcv_ev[slot]));
+		hv = e->srcv_h[slot]; dv = e->srcv_d[slot];
+		e->cur_src_slot[set] = slot;
+	}
+	size_t off = 0;
+	for (SrcObj *s : e->src[set]) {
+		if (!(e->step < s->d.n_active) || !s->cnt) continue;
+		const Box B = clipc(s->B, e->f_lo, e->f_hi);
+		if (!bcount(B)) continue;
+		SrcOp &o = L.op[L.n++];
+		o.F = e->F[set][s->d.m][s->d.comp]; o.B = B; o.full = s->B; o.vals = 0; o.amp = s->dAmp; o.amplitude = s->d.amplitude; o.f = 0.f;
+		if (!s->hPha.empty()) {
+			for (size_t q=0; q<s->cnt; q++)
+				hv[off + q] = (s->hAmp.empty() ? s->d.amplitude : s->hAmp[q]) * s->d.waveform(s->d.user, t, s->hPha[q]);
+			o.vals = dv + off; off += s->cnt;
+		} else o.f = s->d.waveform(s->d.user, t, s->d.phase);
+	}
+	if (nvals) CU(cudaMemcpyAsync(dv, hv, nvals*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	return ALISB_OK;
+}
+
+static int launch_sources(alisb_engine *e, int set, float t)
+{
+	if (e->src[set].empty()) return ALISB_OK;
+	if (e->cur_src_fused[set]) {
+		/* launched even when no source is active right now, so that the pass has the same kernels
+		 * at every step (graph replay only rewrites this node's argument) */
+		source_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(e->cur_src[set]);
+		e->launches++;
+		if (g_mode == GMODE_CAPTURE) {
+			cudaStreamCaptureStatus st; const cudaGraphNode_t *deps = 0; size_t nd = 0;
+			CU(cudaStreamGetCaptureInfo(e->stream, &st, 0, 0, &deps, &nd));
+			if (nd != 1 || !g_nodes) return fail(ALISB_ECUDA, "graph capture: cannot identify the source node");
+			g_nodes->push_back({e, set, deps[0]});
+		}
+		CU(cudaGetLastError());
+		return ALISB_OK;
 	}
 	for (SrcObj *s : e->src[set]) {
 		if (!(e->step < s->d.n_active) || !s->cnt) continue;
@@ -664,13 +708,20 @@ static int apply_sources(alisb_engine *e, int set, float t)
 	return ALISB_OK;
 }
 
+static int finish_sources(alisb_engine *e, int set)
+{
+	if (e->cur_src_slot[set] >= 0) CU(cudaEventRecord(e->srcv_ev[e->cur_src_slot[set]], e->stream));
+	e->cur_src_slot[set] = -1;
+	return ALISB_OK;
+}
+
+static int pass_launch(alisb_engine *e, int set, int part);
+
 static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 {
 	for (TfsfObj *t : e->tf) {
 		alisb_engine *x = t->d.aux;
-		if (x->stream != e->stream && !x->own_stream) return fail(ALISB_ESTATE, "aux engine on a foreign stream");
-		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; }
-		if (step_aux) TRY(set == ALISB_SET_E ? alisb_step_E(x) : alisb_step_H(x));
+		if (step_aux) TRY(pass_launch(x, set, ALISB_PART_ALL));
 		const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
 		/* small faces: all strips of this TFSF region in one single-CTA launch */
 		{
@@ -758,15 +809,33 @@ static int apply_copies(alisb_engine *e, int set)
 	return ALISB_OK;
 }
 
-extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
+static void set_filter(alisb_engine *e, int set, int part)
 {
-	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
-	DEV(e);
 	const int send = set == ALISB_SET_E ? e->nz : 1;          /* the plane the z-neighbour needs */
 	e->f_lo = 0; e->f_hi = e->nz + 1;
 	if (part == ALISB_PART_SEND_PLANE) e->f_lo = e->f_hi = send;
 	if (part == ALISB_PART_REST) { if (set == ALISB_SET_E) e->f_hi = send - 1; else e->f_lo = send + 1; }
-	const bool first = part != ALISB_PART_REST, last = part != ALISB_PART_SEND_PLANE;
+}
+
+/* host side of a pass (recursively for the TFSF auxiliary worlds that the pass steps first) */
+static int pass_prepare(alisb_engine *e, int set, int part)
+{
+	CU(cudaSetDevice(e->g.device));
+	if (part != ALISB_PART_REST) for (TfsfObj *t : e->tf) {
+		alisb_engine *x = t->d.aux;
+		if (x->stream != e->stream && !x->own_stream) return fail(ALISB_ESTATE, "aux engine on a foreign stream");
+		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; x->cfg_version++; }
+		TRY(pass_prepare(x, set, ALISB_PART_ALL));
+	}
+	set_filter(e, set, part);
+	TRY(prepare_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
+	return ALISB_OK;
+}
+
+/* all kernels of a pass, in the reference's order (update.c:275-341) */
+static int pass_launch(alisb_engine *e, int set, int part)
+{
+	set_filter(e, set, part);
 	for (int m=0; m<=e->g.complex_field; m++) {
 		if (set == ALISB_SET_E) {
 			if (!e->obj.empty()) TRY(ade_pre(e, m));
@@ -776,15 +845,85 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 			if (!e->obj.empty()) TRY(ade_post(e, m));
 		}
 	}
-	TRY(apply_tfsf(e, set, first));
-	TRY(apply_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
+	TRY(apply_tfsf(e, set, part != ALISB_PART_REST));
+	set_filter(e, set, part);
+	TRY(launch_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
 	TRY(apply_copies(e, set));
 	e->f_lo = 0; e->f_hi = e->nz + 1;
-	if (last) {
-		if (set == ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;       /* update.c:298 */
-		else e->t = e->tH = e->tE + 0.5 * e->g.dt;                        /* update.c:340 */
+	return ALISB_OK;
+}
+
+/* bookkeeping after the pass has been issued (times: update.c:298,340) */
+static int pass_finish(alisb_engine *e, int set, int part)
+{
+	if (part != ALISB_PART_REST) for (TfsfObj *t : e->tf) TRY(pass_finish(t->d.aux, set, ALISB_PART_ALL));
+	TRY(finish_sources(e, set));
+	if (part != ALISB_PART_SEND_PLANE) {
+		if (set == ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;
+		else e->t = e->tH = e->tE + 0.5 * e->g.dt;
 	}
 	return ALISB_OK;
+}
+
+static uint64_t config_version(alisb_engine *e)
+{
+	uint64_t v = e->cfg_version*1000003ull;
+	for (TfsfObj *t : e->tf) v = v*31 + config_version(t->d.aux);
+	return v;
+}
+
+static bool graphable(alisb_engine *e, int set)
+{
+	if (!e->graph_ok || e->profiling) return false;
+	if (!e->src[set].empty() && !e->cur_src_fused[set]) return false;
+	for (TfsfObj *t : e->tf) if (!graphable(t->d.aux, set)) return false;
+	return true;
+}
+
+extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
+{
+	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
+	TRY(pass_prepare(e, set, part));
+	if (graphable(e, set)) {
+		PassGraph &G = e->graph[set][part];
+		const uint64_t ver = config_version(e);
+		if (!G.exec || G.version != ver) {
+			/* capture the pass once */
+			if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = 0; }
+			if (G.graph) { cudaGraphDestroy(G.graph); G.graph = 0; }
+			G.nodes.clear();
+			const uint64_t l0 = e->launches;
+			CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+			g_mode = GMODE_CAPTURE; g_nodes = &G.nodes;
+			const int r = pass_launch(e, set, part);
+			g_mode = GMODE_NONE; g_nodes = 0;
+			cudaError_t ce = cudaStreamEndCapture(e->stream, &G.graph);
+			if (r != ALISB_OK || ce != cudaSuccess || !G.graph) {
+				if (G.graph) { cudaGraphDestroy(G.graph); G.graph = 0; }
+				cudaGetLastError();
+				e->graph_ok = false;                      /* fall back to plain launches for good */
+				TRY(pass_launch(e, set, part));
+				return pass_finish(e, set, part);
+			}
+			CU(cudaGraphInstantiate(&G.exec, G.graph, 0));
+			G.version = ver;
+			G.nkernels = (int)(e->launches - l0);
+			e->launches = l0;
+		} else {
+			for (const SrcNode &sn : G.nodes) {
+				cudaKernelNodeParams kp;
+				memset(&kp, 0, sizeof kp);
+				void *args[1] = { (void*)&sn.eng->cur_src[sn.set] };
+				kp.func = (void*)source_list; kp.gridDim = dim3(ALISB_LIST_CTAS); kp.blockDim = dim3(1024); kp.kernelParams = args;
+				CU(cudaGraphExecKernelNodeSetParams(G.exec, sn.node, &kp));
+			}
+		}
+		CU(cudaGraphLaunch(G.exec, e->stream));
+		e->launches += G.nkernels;
+		return pass_finish(e, set, part);
+	}
+	TRY(pass_launch(e, set, part));
+	return pass_finish(e, set, part);
 }
 
 extern "C" int alisb_step_E(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_E, ALISB_PART_ALL); }
@@ -1045,7 +1184,7 @@ extern "C" int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which,
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 extern "C" uint64_t alisb_launch_count(alisb_engine *e) { return e->launches; }
-extern "C" int alisb_set_profiling(alisb_engine *e, int on) { e->profiling = on != 0; e->ev_used = 0; e->prof.clear(); return ALISB_OK; }
+extern "C" int alisb_set_profiling(alisb_engine *e, int on) { e->cfg_version++; e->profiling = on != 0; e->ev_used = 0; e->prof.clear(); return ALISB_OK; }
 extern "C" int alisb_last_run_kernel_ms(alisb_engine *e, float *ms_total, int *launches)
 {
 	DEV(e);
