@@ -83,6 +83,7 @@ struct alisb_engine {
 	uint64_t launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
 	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
 	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
@@ -209,6 +210,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		if ((s = getenv("ALISB_STREAM"))) e->tune_stream = atoi(s);
 		e->tune_debug = (s = getenv("ALISB_DEBUG")) ? atoi(s) : 0;
 		e->tune_conc = (s = getenv("ALISB_CONC")) ? atoi(s) : 1;
+		e->tune_small = (s = getenv("ALISB_SMALL")) ? atol(s) : 3000000L;   /* crossover measured at ~150^3 (profiles/small_grid_probe.py) */
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 		if ((s = getenv("ALISB_WAVES"))) e->tune_waves = std::max(1, atoi(s));
@@ -462,7 +464,7 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 	struct Range { int a, b, pm; };
 	std::vector<Range> X, Y, Z;
 	const long cells = (long)e->nx*e->ny*e->nz;
-	if (cells < (1L << 21)) {
+	if (cells < e->tune_small) {
 		/* small grids are launch-bound: one launch with every slab the grid has */
 		int pm = 0;
 		for (int ax=0; ax<3; ax++) if (lo[ax] > 1 || hi[ax] < n[ax]) pm |= 1 << ax;
@@ -769,7 +771,7 @@ static int apply_copies(alisb_engine *e, int set)
 		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
 		const size_t n = bcount(B);
 		if (!n) continue;
-		if (n > 16384) { small = false; break; }
+		if (n > 32768) { small = false; break; }
 		total += n;
 		if (small) {
 			CopyOp &o = L.op[L.n++];
@@ -778,7 +780,7 @@ static int apply_copies(alisb_engine *e, int set)
 			o.sync_after = 0;
 		}
 	}
-	if (small && total <= 131072) {
+	if (small && total <= 400000) {
 		/* a barrier is needed between op q and the ops since the last barrier only if they conflict:
 		 * same array and (target x target, target x source or source x target boxes intersect) */
 		auto hits = [](const Box &A, const Box &B) {

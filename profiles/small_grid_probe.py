@@ -3,13 +3,13 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alis_b200 import capi, synthetic
 lib = capi.load_engine()
-for shape in ((76, 76, 76), (128, 128, 128), (256, 256, 256)):
+for shape in ((76, 76, 76), (128, 128, 128), (192, 192, 192), (256, 256, 256), (384, 384, 384), (512, 512, 512)):
     w = synthetic.BoxWorld(*shape)
     e = w.make_engine(lib)
-    e.run(200); e.synchronize()
+    e.run(100); e.synchronize()
     l0 = e.launch_count(); t0 = time.perf_counter()
-    e.run(2000); 
+    e.run(500); 
     t_enq = time.perf_counter() - t0
     e.synchronize()
     dt = time.perf_counter() - t0
-    print(shape, "us/step %.1f (host enqueue %.1f)" % (dt/2000*1e6, t_enq/2000*1e6), "launches/step %.1f" % ((e.launch_count()-l0)/2000), "Mcells/s %.0f" % (w.cells()*2000/dt*1e-6))
+    print(shape, "us/step %.1f (host enqueue %.1f)" % (dt/500*1e6, t_enq/500*1e6), "launches/step %.1f" % ((e.launch_count()-l0)/500), "Mcells/s %.0f" % (w.cells()*500/dt*1e-6))
