@@ -31,7 +31,7 @@ static int fail(int code, const char *fmt, ...)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALISB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 struct SubBox { int a0, a1, b0, b1, c0, c1; int pml; };   /* cell ranges; pml: bit 0/1/2 = may touch x/y/z slabs */
-struct ProfRec { size_t ev; int set, sub; };
+struct ProfRec { size_t ev; int set, sub; double cells; };
 struct alisb_engine;
 /* a whole pass (all kernels of updateE or updateH, auxiliary TFSF worlds included) captured once as
  * a CUDA graph and replayed; the only per-step parameters are the source lists, whose kernel nodes
@@ -536,7 +536,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		cudaEvent_t e1 = 0;
 		if (e->profiling) {
 			if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
-			e->prof.push_back({e->ev_used, set, sub});
+			e->prof.push_back({e->ev_used, set, sub, (double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*(sb.c1-sb.c0+1)});
 			CU(cudaEventRecord(e->ev_pool[e->ev_used++], st));
 			e1 = e->ev_pool[e->ev_used++];
 		}
@@ -1053,6 +1053,46 @@ static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t 
 extern "C" int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, false); }
 extern "C" int alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(e, arr, ids, box, (float*)host, true); }
 
+/* ---- second-order mixing between worlds (nonLinearSHG / nonLinearTWM, update.c:344-411) -------- */
+extern "C" int alisb_chi2_couple(alisb_engine *e, int obj, int m, alisb_engine *p1, alisb_engine *p2, const float *d, float alt)
+{
+	if (!e || !p1 || !p2 || !d) return fail(ALISB_EINVAL, "chi2: null argument");
+	if (obj < 0 || obj >= (int)e->obj.size()) return fail(ALISB_EINVAL, "chi2: no such object");
+	if (m < 0 || m > e->g.complex_field || m > p1->g.complex_field || m > p2->g.complex_field) return fail(ALISB_EINVAL, "chi2: no such field set");
+	for (alisb_engine *q : {p1, p2})
+		if (q->nx != e->nx || q->ny != e->ny || q->nz != e->nz || q->pitch != e->pitch || q->g.device != e->g.device)
+			return fail(ALISB_EINVAL, "chi2: the coupled worlds must share one grid and one device");
+	if (!e->eps[0]) return fail(ALISB_EINVAL, "chi2: the signal world has no material arrays");
+	DEV(e);
+	const DispObj *o = e->obj[obj];
+	Chi2Params p;
+	memset(&p, 0, sizeof p);
+	for (int c=0; c<3; c++) {
+		p.F[c] = e->F[ALISB_SET_E][m][c]; p.G1[c] = p1->F[ALISB_SET_E][m][c]; p.G2[c] = p2->F[ALISB_SET_E][m][c];
+		p.eps[c] = e->eps[c]; p.fill[c] = o->fill[c];
+		for (int q=0; q<6; q++) p.d[c][q] = d[c*6 + q];
+	}
+	p.alt = alt; p.full = o->full;
+	p.upd = o->full; p.upd.na--; p.upd.nb--; p.upd.nc--;                  /* iMin..iMax-1 etc. (update.c:359-361) */
+	p.ny = e->ny; p.pitch = e->pitch; p.plane = (long long)e->plane;
+	if (p.upd.na <= 0 || p.upd.nb <= 0 || p.upd.nc <= 0) return ALISB_OK;
+	/* order after whatever the pump worlds have queued, and make them wait for us afterwards */
+	for (alisb_engine *q : {p1, p2}) if (q->stream != e->stream) {
+		CU(cudaEventRecord(q->ev_fork, q->stream)); CU(cudaStreamWaitEvent(e->stream, q->ev_fork, 0));
+	}
+	const size_t n = bcount(p.upd);
+	const int T = 256; const unsigned nb = (unsigned)((n + T - 1)/T);
+	chi2_couple<0><<<nb, T, 0, e->stream>>>(p);
+	chi2_couple<1><<<nb, T, 0, e->stream>>>(p);
+	chi2_couple<2><<<nb, T, 0, e->stream>>>(p);
+	e->launches += 3;
+	CU(cudaGetLastError());
+	for (alisb_engine *q : {p1, p2}) if (q->stream != e->stream) {
+		CU(cudaEventRecord(e->ev_fork, e->stream)); CU(cudaStreamWaitEvent(q->stream, e->ev_fork, 0));
+	}
+	return ALISB_OK;
+}
+
 /* ---- device-side monitor reductions ------------------------------------------------------------- */
 extern "C" int alisb_set_spacing(alisb_engine *e, int set, int axis, const float *d)
 {
@@ -1211,10 +1251,15 @@ extern "C" int alisb_profile_dominant(alisb_engine *e, float *ms_total, int *lau
 		const double c = (double)(b.a1 - b.a0 + 1)*(b.b1 - b.b0 + 1)*(b.c1 - b.c0 + 1);
 		if (c > cells[s]) { cells[s] = c; best[s] = (int)q; }
 	}
-	float tot = 0; int n = 0;
-	for (const ProfRec &r : e->prof) if (r.sub == best[r.set]) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev+1])); tot += ms; n++; }
+	/* launches of the largest region; when a pass is split for overlap (alisb_step_part) only the
+	 * launches that carry at least half of the region count, and the bytes are those of the cells
+	 * they actually processed */
+	float tot = 0; int n = 0; double done = 0;
+	for (const ProfRec &r : e->prof) if (r.sub == best[r.set] && r.cells >= 0.5*cells[r.set]) {
+		float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev+1])); tot += ms; n++; done += r.cells;
+	}
 	if (ms_total) *ms_total = tot;
 	if (launches) *launches = n;
-	if (bytes_per_launch) *bytes_per_launch = 36.0*0.5*(cells[0] + cells[1]);
+	if (bytes_per_launch) *bytes_per_launch = n ? 36.0*done/n : 0;
 	return ALISB_OK;
 }

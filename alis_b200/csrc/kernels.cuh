@@ -339,6 +339,71 @@ __global__ void ade_currents(const __grid_constant__ AdeParams p)
 	}
 }
 
+/* reference update.c:344-391 (coupleTWM): second-order mixing  F.v += 2*Alt*d[v][q]*C.v*fill.v*(G1..*G2..)
+ * inside an object's box.  The reference makes 9 full sweeps per component, each a read-modify-
+ * write of F; one thread replays them for its own cell in the same order.  Field values that do
+ * not sit on F.v's Yee position are 4-point averages formed as 0.25*(float sum), a double (the
+ * literal 0.25 is a double in C), so every product that involves an average is done in double and
+ * the result is rounded to float once per sweep, exactly like `F += double` in C.  G1/G2 may alias
+ * F (same world on both sides): own-cell values are therefore re-read after every sweep (volatile
+ * accesses, no __restrict__).  One launch per component v, in x, y, z order.                   */
+struct Chi2Params {
+	float *F[3];
+	const float *G1[3], *G2[3];
+	const float *eps[3];          /* C->x/y/z on the full grid                           */
+	const float *fill[3];         /* dense box arrays of the object, x fastest           */
+	float d[3][6];
+	float alt;
+	Box full, upd;                /* fill allocation box; cells to update (iMin..iMax-1) */
+	int ny, pitch; long long plane;
+};
+
+/* average of component U onto the position of component V (update.c:347-352) */
+template<int V, int U>
+__device__ __forceinline__ double chi2_avg(const float *g, size_t i, const long long *e)
+{
+	return 0.25*(double)(((g[i] + g[i - e[V]]) + g[i + e[U]]) + g[i - e[V] + e[U]]);
+}
+
+template<int V, int U1, int U2>
+__device__ __forceinline__ void chi2_term(const Chi2Params &p, size_t i, size_t j, float dq, const long long *e)
+{
+	if (!dq) return;                                                          /* twm(): if (C->M[n].d) */
+	volatile float *F = p.F[V];
+	const float pre = 2*p.alt*dq*p.eps[V][i]*p.fill[V][j];                    /* float, left to right */
+	if (U1 == V && U2 == V) {
+		const float g1 = ((const volatile float*)p.G1[V])[i], g2 = ((const volatile float*)p.G2[V])[i];
+		F[i] = F[i] + pre*(g1*g2);
+	} else {
+		const double g1 = U1 == V ? (double)((const volatile float*)p.G1[V])[i] : chi2_avg<V,U1>(p.G1[U1], i, e);
+		const double g2 = U2 == V ? (double)((const volatile float*)p.G2[V])[i] : chi2_avg<V,U2>(p.G2[U2], i, e);
+		F[i] = (float)((double)F[i] + (double)pre*(g1*g2));
+	}
+}
+
+template<int V>
+__global__ void chi2_couple(const __grid_constant__ Chi2Params p)
+{
+	const int ny = p.ny, pitch = p.pitch;
+	int a, b, c; size_t q;
+	if (!box_cell(p.upd, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const size_t j = ((size_t)(c - p.full.c0)*p.full.nb + (b - p.full.b0))*p.full.na + (a - p.full.a0);
+	const long long e[3] = {1, (long long)pitch, p.plane};
+	constexpr int A = V, B1 = (V+1)%3, B2 = (V+2)%3;       /* x: (x,y,z)  y: (y,z,x)  z: (z,x,y) */
+	(void)A; (void)B1; (void)B2;
+	/* Voigt order of update.c:364-390: xx, yy, zz, then yz+zy, zx+xz, xy+yx */
+	chi2_term<V,0,0>(p, i, j, p.d[V][0], e);
+	chi2_term<V,1,1>(p, i, j, p.d[V][1], e);
+	chi2_term<V,2,2>(p, i, j, p.d[V][2], e);
+	chi2_term<V,1,2>(p, i, j, p.d[V][3], e);
+	chi2_term<V,2,1>(p, i, j, p.d[V][3], e);
+	chi2_term<V,2,0>(p, i, j, p.d[V][4], e);
+	chi2_term<V,0,2>(p, i, j, p.d[V][4], e);
+	chi2_term<V,0,1>(p, i, j, p.d[V][5], e);
+	chi2_term<V,1,0>(p, i, j, p.d[V][5], e);
+}
+
 /* reference update.c:161-179 (updateS).  vals != 0: per-cell products Amplitude*wave(t,Phase)
  * evaluated on the host; else amp[q]*f or amplitude*f with the host-evaluated scalar f.   */
 __global__ void source_add(float *F, Box B, Box full, int ny, int pitch, const float *vals, const float *amp, float amplitude, float f)

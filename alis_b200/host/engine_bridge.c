@@ -387,6 +387,18 @@ void alis_bridge_step_H(alis_bridge *B)
 	pull_time(B);
 }
 
+/* nonLinearSHG / nonLinearTWM (update.c:394-411): object by object, field set by field set.
+ * C->M is indexed with the ADE-object index n exactly as the reference does (update.c:354).   */
+void alis_bridge_chi2(alis_bridge *S, alis_bridge *P1, alis_bridge *P2, float alt)
+{
+	if (S->dirty) alis_bridge_commit(S);
+	if (P1->dirty) alis_bridge_commit(P1);
+	if (P2->dirty) alis_bridge_commit(P2);
+	coeffs *C = S->W->CE;
+	for (int n=0; n<C->N; n++) for (int m=0; m<=S->W->complexField; m++)
+		CHECK(alisb_chi2_couple(S->E, n, m, P1->E, P2->E, &C->M[n].d[0][0], alt));
+}
+
 void alis_bridge_invalidate(alis_bridge *B) { alis_bridge_mark(B, DIRTY_ALL); }
 
 /* dense host block (reference layout, incl. ghost layer) of one field component */

@@ -16,6 +16,7 @@ void          alis_bridge_invalidate(alis_bridge *B);/* setup changed: re-commit
 void          alis_bridge_mark(alis_bridge *B, int dirty_mask);   /* 1 tables, 2 materials, 4 sources, 8 copies */
 void          alis_bridge_step_E(alis_bridge *B);    /* updateE  (update.c:275-299)              */
 void          alis_bridge_step_H(alis_bridge *B);    /* updateH  (update.c:302-341)              */
+void          alis_bridge_chi2(alis_bridge *S, alis_bridge *P1, alis_bridge *P2, float alt);   /* nonLinearSHG/TWM (update.c:394-411) */
 alisb_engine *alis_bridge_engine(alis_bridge *B);
 void          alis_bridge_read_field(alis_bridge *B, int set, int comp, int m, float *host);
 void          alis_bridge_write_field(alis_bridge *B, int set, int comp, int m, const float *host);

@@ -76,20 +76,32 @@ void (copyBoundary)(float ***F, float ***G, float cosk, float sink, int iMin, in
 	}
 }
 
-/* chi(2) three-wave mixing (reference update.c:354-411) is outside the scope of this build
- * (used by no example). */
+/* chi(2) second-harmonic / three-wave mixing (reference update.c:354-411): the signal world's E
+ * receives 2*Alt*d*inv_eps*fill*(E1..*E2..) inside every ADE object box.  All worlds are device
+ * resident; the coupling is one engine call per object and field set (kernel chi2_couple).  The
+ * worlds must share one grid (the reference indexes all three with the same i,j,k).         */
+static void same_grid(world A, world B, const char *who)
+{
+	if (A->iMIN != B->iMIN || A->iMAX != B->iMAX || A->jMIN != B->jMIN || A->jMAX != B->jMAX || A->kMIN != B->kMIN || A->kMAX != B->kMAX
+	    || B->complexField < A->complexField) {
+		printf("%s: the coupled worlds must have the same grid.\n", who);
+		exit(0);
+	}
+}
+
 void nonLinearSHG(world WS, world WP, float Alt)
 {
-	(void)WS; (void)WP; (void)Alt;
-	printf("alis-b200: nonLinearSHG is not supported by this build.\n");
-	exit(0);
+	same_grid(WS, WP, "nonLinearSHG");
+	alis_bridge_chi2(alis_host_bridge(WS), alis_host_bridge(WP), alis_host_bridge(WP), Alt);
+	alis_host_touch(WS);
 }
 
 void nonLinearTWM(world WS, world WP1, world WP2, float Alt)
 {
-	(void)WS; (void)WP1; (void)WP2; (void)Alt;
-	printf("alis-b200: nonLinearTWM is not supported by this build.\n");
-	exit(0);
+	same_grid(WS, WP1, "nonLinearTWM");
+	same_grid(WS, WP2, "nonLinearTWM");
+	alis_bridge_chi2(alis_host_bridge(WS), alis_host_bridge(WP1), alis_host_bridge(WP2), Alt);
+	alis_host_touch(WS);
 }
 
 /* progress line at most once per second; returns n<=N so it can be the loop condition

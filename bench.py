@@ -97,7 +97,7 @@ def reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -155,7 +155,7 @@ def ours(args):
     nz = args.nz_per_gpu * world
     w = synthetic.BoxWorld(args.nx, args.ny, nz, num=NUM)
     eng = w.make_engine(lib, device=local, rank=rank, world=world)
-    runner = sharding.SlabRunner(eng, rank, world, cuda=True)      # engine now runs on torch's current stream
+    runner = sharding.SlabRunner(eng, rank, world, cuda=True, overlap=not os.environ.get("ALISB_NO_OVERLAP"))      # engine now runs on torch's current stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,7 +222,7 @@ def ours(args):
                        "per_gpu_mcells_per_s": value / world},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -298,7 +298,16 @@ def load_traffic():
     return None
 
 
+def emit(line):
+    """the ONE JSON line, on the process's real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # libraries (NCCL's version banner, torchrun) write to fd 1; keep stdout for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         reference_arm(a)

@@ -180,6 +180,15 @@ int  alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH
 int  alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH);
 int  alisb_reset_fields(alisb_engine *e);        /* rebootWorld field part, world.c:334-368   */
 
+/* ---- second-order (chi2) mixing between worlds -------------------------------------- */
+/* coupleTWM (update.c:356-391) for ADE object `obj` (index in add order) and field set m of the
+ * signal engine e:  E(e).v += 2*alt*d[v][q]*inv_eps.v*fill.v*(E(p1)..*E(p2)..), nine ordered sweeps
+ * per component with the reference's double-precision averages.  d is the 3x6 contracted tensor,
+ * row-major (matter.d, alis_c.h:155).  nonLinearSHG(WS,WP,Alt) = couple(WS, WP, WP); nonLinearTWM
+ * (WS,WP1,WP2,Alt) = couple(WS, WP1, WP2) (update.c:394-411).  All three engines must have the same
+ * grid and device; p1/p2 may be e itself.                                                   */
+int  alisb_chi2_couple(alisb_engine *e, int obj, int m, alisb_engine *p1, alisb_engine *p2, const float *d, float alt);
+
 /* ---- data access (parity dumps, slices, get) -------------------------------------- */
 /* ids: meaning depends on arr (see enum).  box inclusive, host block dense z-fastest.      */
 int  alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host);

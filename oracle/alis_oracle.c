@@ -587,6 +587,54 @@ int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, dou
 }
 
 /* ---- halo ------------------------------------------------------------------------------ */
+/* ---- chi2 mixing: reference update.c:344-411 (coupleTWM), sweep by sweep ---------------------- */
+static double chi2_at(alisb_engine *g, int m, int u, int v, int a, int b, int c)
+{
+	/* component u of g's E field seen from the Yee position of component v.  u == v: the value
+	 * itself (float); else the 4-point average 0.25*(f0+f1+f2+f3) of update.c:347-352, where the
+	 * sum is float arithmetic and the product with the double literal 0.25 is double.          */
+	const float *G = g->F[ALISB_SET_E][m][u];
+	int o[3] = {a, b, c};
+	if (u == v) return (double)G[IDX(g, a, b, c)];
+	int p1[3] = {o[0], o[1], o[2]}, p2[3] = {o[0], o[1], o[2]}, p3[3] = {o[0], o[1], o[2]};
+	p1[v] -= 1; p2[u] += 1; p3[v] -= 1; p3[u] += 1;
+	const float sum = ((G[IDX(g,a,b,c)] + G[IDX(g,p1[0],p1[1],p1[2])]) + G[IDX(g,p2[0],p2[1],p2[2])]) + G[IDX(g,p3[0],p3[1],p3[2])];
+	return 0.25 * sum;
+}
+
+static void chi2_sweep(alisb_engine *e, const dispobj *o, int m, alisb_engine *g1, alisb_engine *g2, int v, int u1, int u2, float dq, float alt)
+{
+	if (!dq) return;                                                       /* twm(): if (C->M[n].d) */
+	float *F = e->F[ALISB_SET_E][m][v];
+	const float *Cv = e->eps[v];
+	for (int a=o->bx.lo[0]; a<=o->bx.hi[0]-1; a++)
+	for (int b=o->bx.lo[1]; b<=o->bx.hi[1]-1; b++)
+	for (int c=o->bx.lo[2]; c<=o->bx.hi[2]-1; c++) {
+		const size_t i = IDX(e, a, b, c);
+		const float pre = 2 * alt * dq * Cv[i] * o->fill[v].v[bidx(&o->fill[v], a, b, c)];
+		if (u1 == v && u2 == v) {
+			const float G1 = g1->F[ALISB_SET_E][m][v][IDX(g1,a,b,c)], G2 = g2->F[ALISB_SET_E][m][v][IDX(g2,a,b,c)];
+			F[i] += pre * (G1 * G2);
+		} else {
+			F[i] += pre * (chi2_at(g1, m, u1, v, a, b, c) * chi2_at(g2, m, u2, v, a, b, c));
+		}
+	}
+}
+
+int alisb_chi2_couple(alisb_engine *e, int obj, int m, alisb_engine *p1, alisb_engine *p2, const float *d, float alt)
+{
+	if (!e || !p1 || !p2 || !d || obj < 0 || obj >= e->nobj || m < 0 || m > e->g.complex_field) return fail(ALISB_EINVAL, "chi2: bad argument");
+	if (!e->eps[0]) return fail(ALISB_EINVAL, "chi2: the signal world has no material arrays");
+	for (int q=0; q<3; q++) if (p1->n[q] != e->n[q] || p2->n[q] != e->n[q]) return fail(ALISB_EINVAL, "chi2: grids differ");
+	const dispobj *o = e->obj[obj];
+	/* Voigt pairs in the order of update.c:364-390 */
+	static const int U[9][2] = {{0,0},{1,1},{2,2},{1,2},{2,1},{2,0},{0,2},{0,1},{1,0}};
+	static const int Q[9]    = {0, 1, 2, 3, 3, 4, 4, 5, 5};
+	for (int v=0; v<3; v++) for (int s=0; s<9; s++)
+		chi2_sweep(e, o, m, p1, p2, v, U[s][0], U[s][1], d[v*6 + Q[s]], alt);
+	return ALISB_OK;
+}
+
 int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)
 {
 	if (set<0||set>1||m<0||m>e->g.complex_field||comp<0||comp>1) return fail(ALISB_EINVAL, "bad halo id");

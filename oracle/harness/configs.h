@@ -11,7 +11,11 @@
 #define HARNESS_CONFIGS_H
 #include <string.h>
 
-typedef struct { const char *name; world (*make)(void); int default_steps; int order; } harness_config;
+/* pump1/pump2: optional further worlds on the same grid, stepped in lock step and mixed into the
+ * main (signal) world after every E update: pump2 == 0 -> nonLinearSHG(W, P1, alt), else
+ * nonLinearTWM(W, P1, P2, alt); alias != 0 -> nonLinearTWM(W, W, P1, alt) (signal is its own pump) */
+typedef struct { const char *name; world (*make)(void); int default_steps; int order;
+                 world (*pump1)(void); world (*pump2)(void); float alt; int alias; } harness_config;
 
 /* examples/Dipole_PML.c:6-13 */
 static world cfg_dipole_pml(void)
@@ -157,6 +161,32 @@ static world cfg_aniso_ade(void)
 	return W;
 }
 
+/* chi(2) mixing (update.c:354-411): a nonlinear crystal with a fairly full contracted d tensor and
+ * a Lorentz pole, next to a metal (second ADE object, d = 0), all-PML box.  which: 0 signal world,
+ * 1 pump at 800 nm (Ey dipole), 2 pump at 1000 nm (Ex dipole, other corner). */
+static world chi2_world(int which, int bloch)
+{
+	dom Dom = {{-200, 200}, {-150, 150}, {-180, 180}};
+	res Res = {10, {20}, {1240}};
+	sur SurP = {{PML, PML}, {PML, PML}, {PML, PML}};
+	sur SurB = {{BBC, 1700}, {PBC}, {PML, PML}};
+	world W = createWorld(Dom, Res, bloch ? SurB : SurP, "");
+	matter NL = {{2.25, 2.4, 2.6}, {{5.5, 0.4, 1.1}, {5.7, 0.3, 0.9}, {5.9, 0.2, 0.8}},
+	             {{0.011, 0.023, -0.017, 0.031, 0.0, 0.027}, {0.013, 0.0, 0.029, -0.019, 0.037, 0.021}, {-0.015, 0.033, 0.041, 0.0, 0.025, 0.0}}};
+	object Crystal = {Box, {{-90, 110}, {-80, 60}, {-100, 70}}};
+	object Tip = {Ball, {{60, 160}, {-30, 70}, {-20, 80}}};
+	putObjects(W, NL, Crystal, Au, Tip, Air);
+	if (which == 0) pointDipole(W, Ez, -120, 90, 110, Pulse, 450, 900, 0.2);
+	if (which == 1) pointDipole(W, Ey, 0, -20, -140, Pulse, 800, 1600, 1);
+	if (which == 2) pointDipole(W, Ex, -40, 100, 20, Sine, 1000, 2, 1);
+	return W;
+}
+static world cfg_chi2_signal(void) { return chi2_world(0, 0); }
+static world cfg_chi2_pump1(void)  { return chi2_world(1, 0); }
+static world cfg_chi2_pump2(void)  { return chi2_world(2, 0); }
+static world cfg_chi2b_signal(void) { return chi2_world(0, 1); }
+static world cfg_chi2b_pump1(void)  { return chi2_world(1, 1); }
+
 static const harness_config harness_configs[] = {
 	{"dipole_pml",  cfg_dipole_pml,  60, 0},
 	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
@@ -168,6 +198,9 @@ static const harness_config harness_configs[] = {
 	{"metasurface", cfg_metasurface, 120, 0},
 	{"dipole_band", cfg_dipole_band, 80, 0},
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
+	{"chi2_shg",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, 0, 0.7f, 0},
+	{"chi2_twm",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, cfg_chi2_pump2, -1.3f, 0},
+	{"chi2_alias",  cfg_chi2b_signal, 80, 0, cfg_chi2b_pump1, 0, 0.9f, 1},
 	{0, 0, 0, 0}
 };
 

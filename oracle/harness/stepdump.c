@@ -41,18 +41,32 @@ int main(int argc, char **argv)
 	if (steps <= 0) steps = cfg->default_steps;
 	int order = argc > 4 ? atoi(argv[4]) : cfg->order;
 	world W = cfg->make();
+	world P1 = cfg->pump1 ? cfg->pump1() : 0, P2 = cfg->pump2 ? cfg->pump2() : 0;
+	const float alt = getenv("HARNESS_ALT") ? (float)atof(getenv("HARNESS_ALT")) : cfg->alt;   /* 0 switches the mixing off */
+	world all[3] = {P1, P2, W};                       /* pumps first, the signal world last */
 
 #if defined(HARNESS_MODE_BRIDGE)
-	alis_bridge *B = alis_bridge_create(W);
-	#define STEP_E() alis_bridge_step_E(B)
-	#define STEP_H() alis_bridge_step_H(B)
+	alis_bridge *Bs[3] = {P1 ? alis_bridge_create(P1) : 0, P2 ? alis_bridge_create(P2) : 0, alis_bridge_create(W)};
+	alis_bridge *B = Bs[2];
+	#define STEP_E(q) alis_bridge_step_E(Bs[q])
+	#define STEP_H(q) alis_bridge_step_H(Bs[q])
+	#define MIX()     alis_bridge_chi2(Bs[2], cfg->alias ? Bs[2] : Bs[0], cfg->alias ? Bs[0] : (P2 ? Bs[1] : Bs[0]), alt)
 #else
-	#define STEP_E() updateE(W)
-	#define STEP_H() updateH(W)
+	#define STEP_E(q) updateE(all[q])
+	#define STEP_H(q) updateH(all[q])
+	#define MIX()     do { if (cfg->alias) nonLinearTWM(W, W, P1, alt); else if (P2) nonLinearTWM(W, P1, P2, alt); \
+	                       else nonLinearSHG(W, P1, alt); } while (0)
 #endif
 	for (int s=0; s<steps; s++) {
-		if (order) { STEP_H(); STEP_E(); }
-		else       { STEP_E(); STEP_H(); }
+		if (order) {
+			for (int q=0; q<3; q++) if (all[q]) STEP_H(q);
+			for (int q=0; q<3; q++) if (all[q]) STEP_E(q);
+			if (P1) MIX();
+		} else {
+			for (int q=0; q<3; q++) if (all[q]) STEP_E(q);
+			if (P1) MIX();
+			for (int q=0; q<3; q++) if (all[q]) STEP_H(q);
+		}
 	}
 
 	FILE *f = fopen(argv[3], "wb");
