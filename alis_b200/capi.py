@@ -84,6 +84,7 @@ def _declare(lib):
         "alisb_write_box": (i, [vp, i, i32p, i32p, f32p]),
         "alisb_set_spacing": (i, [vp, i, i, f32p]),
         "alisb_plane_flux": (i, [vp, C.c_void_p, i, C.POINTER(C.c_double)]),
+        "alisb_chi2_couple": (i, [vp, i, i, vp, vp, f32p, f]),
         "alisb_halo_info": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "alisb_halo_pack": (i, [vp, i]),
         "alisb_halo_unpack": (i, [vp, i]),
@@ -289,6 +290,11 @@ class Engine:
         out = np.zeros((arr.shape[0], 2), np.float64)
         self._ck(self.lib.alisb_plane_flux(self.h, arr.ctypes.data_as(C.c_void_p), arr.shape[0], out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def chi2_couple(self, obj, m, pump1, pump2, d, alt):
+        """coupleTWM (update.c:356-391): mixes E(pump1) x E(pump2) into this engine's E inside ADE object obj"""
+        d = np.ascontiguousarray(d, dtype=np.float32).reshape(18)
+        self._ck(self.lib.alisb_chi2_couple(self.h, obj, m, pump1.h, pump2.h, _fp(d), alt))
 
     # --- halo -----------------------------------------------------------------------------
     def halo_info(self, set_, m, comp):

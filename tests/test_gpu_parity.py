@@ -213,3 +213,33 @@ def test_split_pass_equals_whole_pass_on_gpu(oracle_lib, engine_lib):
         assert g.time() == o.time()
         helpers.assert_fields_identical(g, o, f"split pass on GPU, rank {rank}")
         compare_psi(g, o)
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_chi2_coupling_seeded_bit_exact(oracle_lib, engine_lib, alias):
+    """coupleTWM (update.c:356-391) through the C ABI on seeded dense fields: every sweep, the float and
+    the double products, a zero tensor entry (skipped sweep) and the signal-is-its-own-pump case."""
+    shape = (45, 38, 41)
+    rng = np.random.RandomState(7)
+    box = [5, 33, 4, 30, 7, 36]
+    dims = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1)
+    fill = [rng.rand(*dims).astype(np.float32) for _ in range(3)]
+    eps = [(0.2 + rng.rand(shape[0] + (c == 0), shape[1] + (c == 1), shape[2] + (c == 2))).astype(np.float32) for c in range(3)]
+    d = (rng.rand(3, 6).astype(np.float32) - 0.5)
+    d[1, 2] = 0.0
+    zero = {k: [[0.0] * 8] * 3 for k in ("JJ", "JK", "JE", "KJ", "KK", "KE")}
+    out = []
+    for lib in (engine_lib, oracle_lib):
+        w = synthetic.BoxWorld(*shape, num=6)
+        sig, p1, p2 = (w.make_engine(lib) for _ in range(3))
+        for q, e in enumerate((sig, p1, p2)):
+            helpers.seed_fields([e], tuple(n + 2 for n in shape), seed=100 + q, scale=0.5)
+        sig.set_inv_eps(*eps)
+        sig.add_dispersive(box, 0, 0, [0.0, 0.0, 0.0], zero, fill)
+        for _ in range(2):
+            sig.chi2_couple(0, 0, sig if alias else p1, p2, d, 0.37)
+        out.append(sig.read_all_fields())
+        for e in (sig, p1, p2):
+            e.close()
+    assert np.array_equal(out[0], out[1])
+    assert np.abs(out[0]).max() > 0
