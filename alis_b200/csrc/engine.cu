@@ -83,6 +83,7 @@ struct alisb_engine {
 	uint64_t launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_merge;                    /* PML shell boxes gathered into two merged launches  */
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
 	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
@@ -210,6 +211,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		if ((s = getenv("ALISB_STREAM"))) e->tune_stream = atoi(s);
 		e->tune_debug = (s = getenv("ALISB_DEBUG")) ? atoi(s) : 0;
 		e->tune_conc = (s = getenv("ALISB_CONC")) ? atoi(s) : 1;
+		e->tune_merge = (s = getenv("ALISB_MERGE")) ? atoi(s) : 1;
 		e->tune_small = (s = getenv("ALISB_SMALL")) ? atol(s) : 3000000L;   /* crossover measured at ~150^3 (profiles/small_grid_probe.py) */
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -414,29 +416,40 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 
 /* ---- one pass ------------------------------------------------------------------------- */
 template <int S, bool EPS>
-static void launch_volume_te(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, int pm, bool narrow)
+static void launch_volume_te(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block)
 {
-	if (narrow) {                     /* 32-cell wide x strips: 8 lanes along x, 4 rows per warp */
-		if (pm == 1) yee_volume<S,EPS,1,8><<<grid,block,0,st>>>(p);
-		else         yee_volume<S,EPS,5,8><<<grid,block,0,st>>>(p);
+	if (r.narrow) {                   /* 32-cell wide x strips: 8 lanes along x, 4 rows per warp */
+		if (r.pm == 1) yee_volume<S,EPS,1,8><<<grid,block,0,st>>>(p, r);
+		else           yee_volume<S,EPS,5,8><<<grid,block,0,st>>>(p, r);
 		return;
 	}
-	switch (pm) {
-	case 0: yee_volume<S,EPS,0,32><<<grid,block,0,st>>>(p); break;
-	case 1: yee_volume<S,EPS,1,32><<<grid,block,0,st>>>(p); break;
-	case 2: yee_volume<S,EPS,2,32><<<grid,block,0,st>>>(p); break;
-	case 3: yee_volume<S,EPS,3,32><<<grid,block,0,st>>>(p); break;
-	case 4: yee_volume<S,EPS,4,32><<<grid,block,0,st>>>(p); break;
-	case 5: yee_volume<S,EPS,5,32><<<grid,block,0,st>>>(p); break;
-	case 6: yee_volume<S,EPS,6,32><<<grid,block,0,st>>>(p); break;
-	default: yee_volume<S,EPS,7,32><<<grid,block,0,st>>>(p); break;
+	switch (r.pm) {
+	case 0: yee_volume<S,EPS,0,32><<<grid,block,0,st>>>(p, r); break;
+	case 1: yee_volume<S,EPS,1,32><<<grid,block,0,st>>>(p, r); break;
+	case 2: yee_volume<S,EPS,2,32><<<grid,block,0,st>>>(p, r); break;
+	case 3: yee_volume<S,EPS,3,32><<<grid,block,0,st>>>(p, r); break;
+	case 4: yee_volume<S,EPS,4,32><<<grid,block,0,st>>>(p, r); break;
+	case 5: yee_volume<S,EPS,5,32><<<grid,block,0,st>>>(p, r); break;
+	case 6: yee_volume<S,EPS,6,32><<<grid,block,0,st>>>(p, r); break;
+	default: yee_volume<S,EPS,7,32><<<grid,block,0,st>>>(p, r); break;
 	}
 }
 template <int S>
-static void launch_volume_t(cudaStream_t st, const VolParams &p, dim3 grid, dim3 block, bool eps, int pm, bool narrow)
+static void launch_volume_t(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, bool eps)
 {
-	if (eps) launch_volume_te<S,true>(st, p, grid, block, pm, narrow);
-	else     launch_volume_te<S,false>(st, p, grid, block, pm, narrow);
+	if (eps) launch_volume_te<S,true>(st, p, r, grid, block);
+	else     launch_volume_te<S,false>(st, p, r, grid, block);
+}
+template <int S, bool EPS>
+static void launch_multi_te(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls)
+{
+	if (cls == 0) yee_multi<S,EPS,0><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
+	else          yee_multi<S,EPS,1><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
+}
+static void launch_multi(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls, int set, bool eps)
+{
+	if (set == ALISB_SET_E) { if (eps) launch_multi_te<1,true>(st, mp, nctas, cls); else launch_multi_te<1,false>(st, mp, nctas, cls); }
+	else                    launch_multi_te<-1,false>(st, mp, nctas, cls);
 }
 
 /* Region-specialised launches.  Per axis the cells split into lo slab / slab-free middle / hi slab
@@ -511,52 +524,89 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	const bool eps = set == ALISB_SET_E && e->eps[0] && e->eps[1] && e->eps[2];
 	if (e->plan[set].empty()) plan_volume(e, set, e->plan[set]);
 
-	/* Sub-launches touch disjoint cells, so they may run concurrently: the PML-shell launches are
-	 * spread over three side streams (fork/join with events) so that their ramp-up and tail phases
-	 * overlap; the interior launch runs alone first (tune_conc 1) or concurrently too (2). */
+	/* Sub-launches touch disjoint cells, so they may run concurrently.  The slab-free interior is
+	 * one launch of the lean kernel on the engine's stream; the PML shell boxes are gathered into
+	 * two merged launches (faces / edges+corners, yee_multi) on side streams, fork/join with events.
+	 * ALISB_MERGE=0: one launch per box, spread over three side streams.                        */
 	int sub = -1, nlaunched = 0, rr = 0;
 	bool forked = false, used[3] = {false, false, false};
 	const bool conc = e->tune_conc > 0 && e->plan[set].size() > 2;
+	const bool merge = e->tune_merge && e->plan[set].size() > 2 && e->tune_bx == 1 && e->tune_by == 8;
+	MultiParams mp[2];
+	unsigned mcta[2] = {0, 0}; double mcells[2] = {0, 0}, mplanes[2] = {0, 0};
+	if (merge) for (int q=0; q<2; q++) { mp[q].v = p; mp[q].nreg = 0; }
 	if (conc && e->tune_conc == 2) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
+	auto side_stream = [&](bool first_alone) -> cudaStream_t {
+		if (!conc || (first_alone && nlaunched == 0 && e->tune_conc != 2)) return e->stream;
+		if (!forked) { cudaEventRecord(e->ev_fork, e->stream); forked = true; }
+		const int slot = rr++ % 4;                         /* slot 3 = the main stream itself */
+		if (slot == 3) return e->stream;
+		if (!used[slot]) { cudaStreamWaitEvent(e->side[slot], e->ev_fork, 0); used[slot] = true; }
+		return e->side[slot];
+	};
+	auto prof_begin = [&](cudaStream_t st, int subidx, double cells) -> cudaEvent_t {
+		if (!e->profiling) return (cudaEvent_t)0;
+		if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev_pool.push_back(ev); }
+		e->prof.push_back({e->ev_used, set, subidx, cells});
+		cudaEventRecord(e->ev_pool[e->ev_used++], st);
+		return e->ev_pool[e->ev_used++];
+	};
 	for (const SubBox &sb0 : e->plan[set]) {
 		sub++;
 		SubBox sb = sb0;
 		sb.c0 = std::max(sb.c0, e->f_lo); sb.c1 = std::min(sb.c1, e->f_hi);
 		if (sb.c0 > sb.c1) continue;
-		cudaStream_t st = e->stream;
-		if (conc && (nlaunched > 0 || e->tune_conc == 2)) {
-			if (!forked) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
-			const int slot = rr++ % 4;                     /* slot 3 = the main stream itself */
-			if (slot < 3) {
-				st = e->side[slot];
-				if (!used[slot]) { CU(cudaStreamWaitEvent(st, e->ev_fork, 0)); used[slot] = true; }
-			}
-		}
-		nlaunched++;
-		cudaEvent_t e1 = 0;
-		if (e->profiling) {
-			if (e->ev_used + 2 > e->ev_pool.size()) for (int q=0; q<64; q++) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
-			e->prof.push_back({e->ev_used, set, sub, (double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*(sb.c1-sb.c0+1)});
-			CU(cudaEventRecord(e->ev_pool[e->ev_used++], st));
-			e1 = e->ev_pool[e->ev_used++];
-		}
+		VolRegion r;
+		memset(&r, 0, sizeof r);
 		const bool narrow = (sb.pml == 1 || sb.pml == 5) && sb.a1 - sb.a0 + 1 <= 64;     /* x-PML strips */
-		p.a_first = sb.a0; p.a_last = sb.a1; p.nseg = div_up(sb.a1 - sb.a0 + 1, narrow ? 32 : 128);
-		p.b_first = sb.b0; p.b_last = sb.b1; p.c_first = sb.c0; p.c_last = sb.c1;
-		const int bx = narrow ? 1 : e->tune_bx, by = narrow ? 8 : e->tune_by;
-		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(p.nseg, bx), gy = div_up(sb.b1 - sb.b0 + 1, by*(narrow ? 4 : 1));
+		r.pm = sb.pml; r.narrow = narrow ? 1 : 0;
+		r.a_first = sb.a0; r.a_last = sb.a1; r.nseg = div_up(sb.a1 - sb.a0 + 1, narrow ? 32 : 128);
+		r.b_first = sb.b0; r.b_last = sb.b1; r.c_first = sb.c0; r.c_last = sb.c1;
+		const bool merged = merge && sb.pml != 0 && mp[0].nreg < ALISB_MAXREG && mp[1].nreg < ALISB_MAXREG;
+		const int bx = (narrow || merged) ? 1 : e->tune_bx, by = (narrow || merged) ? 8 : e->tune_by;
+		const int nzs = sb.c1 - sb.c0 + 1, gx = div_up(r.nseg, bx), gy = div_up(sb.b1 - sb.b0 + 1, by*(narrow ? 4 : 1));
 		const long tiles = (long)gx*gy;
 		long want = ((long)e->tune_waves*e->resident_ctas + tiles - 1)/tiles;   /* many short z-chunks balance best  */
 		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* (the carry preload is an L2 hit)  */
 		int nchunks = (int)std::max(1L, std::min(want, maxc));
-		if (tiles*nchunks < 2L*e->resident_ctas) nchunks = (int)std::min((long)nzs, (2L*e->resident_ctas + tiles - 1)/tiles);   /* small grids: fill the GPU */
-		p.cchunk = div_up(nzs, nchunks);
-		nchunks = div_up(nzs, p.cchunk);
+		if (!merged && tiles*nchunks < 2L*e->resident_ctas) nchunks = (int)std::min((long)nzs, (2L*e->resident_ctas + tiles - 1)/tiles);   /* small grids: fill the GPU */
+		r.cchunk = div_up(nzs, nchunks);
+		nchunks = div_up(nzs, r.cchunk);
+		r.gx = gx; r.gy = gy; r.gz = nchunks;
+		const double cells = (double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*(sb.c1-sb.c0+1);
+		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] set %d sub %d pm %d cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d (resident %d)%s\n",
+			set, sub, sb.pml, sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, gx, gy, nchunks, r.cchunk, e->resident_ctas, merged ? " merged" : "");
+		if (merged) {                                       /* chunking is decided per class below */
+			const int cls = (sb.pml == 1 || sb.pml == 2 || sb.pml == 4) ? 0 : 1;
+			mp[cls].r[mp[cls].nreg++] = r;
+			mcells[cls] += cells; mplanes[cls] += (double)tiles*nzs;
+			continue;
+		}
+		cudaStream_t st = side_stream(true);
+		nlaunched++;
+		cudaEvent_t e1 = prof_begin(st, sub, cells);
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
-		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] set %d sub %d pm %d cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d (resident %d)\n",
-			set, sub, sb.pml, sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, gx, gy, nchunks, p.cchunk, e->resident_ctas);
-		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, grid, block, eps, sb.pml, narrow);
-		else                    launch_volume_t<-1>(st, p, grid, block, false, sb.pml, narrow);
+		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, r, grid, block, eps);
+		else                    launch_volume_t<-1>(st, p, r, grid, block, false);
+		e->launches++;
+		if (e->profiling) CU(cudaEventRecord(e1, st));
+	}
+	if (merge) for (int cls=0; cls<2; cls++) if (mp[cls].nreg) {
+		/* z-chunk of a merged launch: tune_minchunk planes when that still gives >= 4 CTAs per resident
+		 * slot over the whole class, fewer planes per chunk on mid-size grids (more, shorter marches) */
+		const double slots = 4.0*148*(cls == 0 ? 3 : 2);
+		const int chunk = (int)std::max(1.0, std::min((double)e->tune_minchunk, floor(mplanes[cls]/slots)));
+		for (int q=0; q<mp[cls].nreg; q++) {
+			VolRegion &r = mp[cls].r[q];
+			const int nzs = r.c_last - r.c_first + 1;
+			r.cchunk = std::min(chunk, nzs); r.gz = div_up(nzs, r.cchunk);
+			r.cta0 = mcta[cls];
+			mcta[cls] += (unsigned)r.gx*r.gy*r.gz;
+		}
+		cudaStream_t st = side_stream(true);
+		nlaunched++;
+		cudaEvent_t e1 = prof_begin(st, -2 - cls, mcells[cls]);
+		launch_multi(st, mp[cls], mcta[cls], cls, set, eps);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}

@@ -28,13 +28,22 @@ struct VolParams {
 	int slab[3][2][2];            /* [axis][side]{first,last} in array coordinates      */
 	int xbase[2], xpitch[2];      /* x-slab psi arrays: slot = a - xbase, row pitch      */
 	int nx, ny, nz, pitch;
-	int a_first, a_last;          /* x range updated by this launch (a_first = 1 mod 4); a warp covers 128 cells from a_first */
-	int nseg;                     /* number of 128-cell warp segments covering [a_first, a_last]    */
-	int b_first, b_last;          /* rows updated by this launch                        */
-	int c_first, c_last;          /* planes updated by this launch                      */
-	int cchunk;                   /* planes per z-chunk (grid.z chunks)                  */
 	size_t plane;                 /* (ny+2)*pitch                                        */
 };
+
+/* one box of the region plan and the CTA grid that covers it */
+struct VolRegion {
+	int a_first, a_last;          /* x range updated (a_first = 1 mod 4); a warp covers 4*XL cells from a_first */
+	int nseg;                     /* number of warp segments covering [a_first, a_last]  */
+	int b_first, b_last;          /* rows updated                                        */
+	int c_first, c_last;          /* planes updated                                      */
+	int cchunk;                   /* planes per z-chunk                                  */
+	int pm, narrow;               /* PML bitmask of the box; 1 = XL=8 mapping (x strips) */
+	int gx, gy, gz;               /* CTA grid of the box                                 */
+	unsigned cta0;                /* first linear CTA of the box inside a merged launch  */
+};
+#define ALISB_MAXREG 28
+struct MultiParams { VolParams v; int nreg; VolRegion r[ALISB_MAXREG]; };
 
 static __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4*>(p); }
 static __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -58,25 +67,24 @@ template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, flo
  */
 /* XL = lanes of a warp along x: 32 (a warp is one 128-cell row segment) or 8 (a warp is a 32-cell
  * wide, 4-row patch: used for the narrow x-PML strips so that all lanes have work). */
-template <int S, bool EPS, int PM, int XL>  /* PM: bit 0/1/2 = this launch may touch x / y / z PML slabs */
-__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
-yee_volume(const __grid_constant__ VolParams p)
+template <int S, bool EPS, int PM, int XL>  /* PM: bit 0/1/2 = this box may touch x / y / z PML slabs */
+static __device__ __forceinline__ void yee_body(const VolParams &p, const VolRegion &r, const int bix, const int biy, const int biz)
 {
 	constexpr int RW = 32/XL;                               /* rows per warp */
 	const int lane = threadIdx.x & 31;
 	const int lx = lane % XL;                               /* lane position along x */
-	const int seg = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);     /* (4*XL)-cell segment within the launch */
-	const int a0 = p.a_first + 4*(seg*XL + lx);
-	const int bw = p.b_first + (blockIdx.y*blockDim.y + threadIdx.y)*RW;   /* first row of this warp */
+	const int seg = bix*(blockDim.x >> 5) + (threadIdx.x >> 5);            /* (4*XL)-cell segment within the box */
+	const int a0 = r.a_first + 4*(seg*XL + lx);
+	const int bw = r.b_first + (biy*blockDim.y + threadIdx.y)*RW;          /* first row of this warp */
 	const int b  = bw + lane/XL;
-	if (bw > p.b_last || seg >= p.nseg) return;             /* whole warp leaves */
-	const bool rowok = b <= p.b_last;
-	const bool act = rowok && a0 <= p.a_last;               /* owns at least one cell of this launch */
-	const bool ldg = rowok && a0 <= p.a_last + 1;           /* G quad holds data the lane before needs (a_last+1) */
-	const bool full = rowok && a0 + 3 <= p.a_last;
+	if (bw > r.b_last || seg >= r.nseg) return;             /* whole warp leaves */
+	const bool rowok = b <= r.b_last;
+	const bool act = rowok && a0 <= r.a_last;               /* owns at least one cell of this box */
+	const bool ldg = rowok && a0 <= r.a_last + 1;           /* G quad holds data the lane before needs (a_last+1) */
+	const bool full = rowok && a0 + 3 <= r.a_last;
 
-	const int cf = p.c_first + blockIdx.z*p.cchunk;
-	const int cl = min(cf + p.cchunk - 1, p.c_last);
+	const int cf = r.c_first + biz*r.cchunk;
+	const int cl = min(cf + r.cchunk - 1, r.c_last);
 	if (cf > cl) return;
 	const int nsteps = cl - cf + 1;
 	int c = (S > 0) ? cl : cf;
@@ -249,9 +257,43 @@ yee_volume(const __grid_constant__ VolParams p)
 			st4s<STREAM>(F2 + o, make_float4(Fz[0], Fz[1], Fz[2], Fz[3]));
 		} else if (act) {
 			#pragma unroll
-			for (int e = 0; e < 4; e++) if (a0 + e <= p.a_last) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
+			for (int e = 0; e < 4; e++) if (a0 + e <= r.a_last) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
 		}
 		gxp = gx; gyp = gy;
+	}
+}
+
+/* one box per launch: the slab-free interior (PM=0) and, with ALISB_MERGE=0, every other box */
+template <int S, bool EPS, int PM, int XL>
+__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
+yee_volume(const __grid_constant__ VolParams p, const __grid_constant__ VolRegion r)
+{
+	yee_body<S,EPS,PM,XL>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+/* many boxes per launch: the PML shell of a grid is up to 26 boxes (6 faces, 12 edges, 8 corners),
+ * most of them far too small to fill the GPU on their own.  A CTA looks its box up in the table and
+ * runs the body specialised for that box's PML bitmask.  Two classes so that the big single-axis
+ * faces keep 3 CTAs/SM: CLS 0 = faces (PM 1,2,4), CLS 1 = edges and corners (PM 3,5,6,7).   */
+template <int S, bool EPS, int CLS>
+__global__ void __launch_bounds__(256, CLS == 0 ? 3 : 2)
+yee_multi(const __grid_constant__ MultiParams mp)
+{
+	unsigned id = blockIdx.x;
+	int q = 0;
+	while (q + 1 < mp.nreg && id >= mp.r[q + 1].cta0) q++;
+	const VolRegion &r = mp.r[q];
+	id -= r.cta0;
+	const int bix = (int)(id % (unsigned)r.gx), biy = (int)((id / (unsigned)r.gx) % (unsigned)r.gy), biz = (int)(id / ((unsigned)r.gx*(unsigned)r.gy));
+	if (CLS == 0) {
+		if (r.pm == 1) { if (r.narrow) yee_body<S,EPS,1,8>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,1,32>(mp.v, r, bix, biy, biz); }
+		else if (r.pm == 2) yee_body<S,EPS,2,32>(mp.v, r, bix, biy, biz);
+		else                yee_body<S,EPS,4,32>(mp.v, r, bix, biy, biz);
+	} else {
+		if (r.pm == 5) { if (r.narrow) yee_body<S,EPS,5,8>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,5,32>(mp.v, r, bix, biy, biz); }
+		else if (r.pm == 3) yee_body<S,EPS,3,32>(mp.v, r, bix, biy, biz);
+		else if (r.pm == 6) yee_body<S,EPS,6,32>(mp.v, r, bix, biy, biz);
+		else                yee_body<S,EPS,7,32>(mp.v, r, bix, biy, biz);
 	}
 }
 
