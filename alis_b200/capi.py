@@ -85,6 +85,10 @@ def _declare(lib):
         "alisb_set_spacing": (i, [vp, i, i, f32p]),
         "alisb_plane_flux": (i, [vp, C.c_void_p, i, C.POINTER(C.c_double)]),
         "alisb_chi2_couple": (i, [vp, i, i, vp, vp, f32p, f]),
+        "alisb_set_fusion": (i, [vp, i]),
+        "alisb_flush": (i, [vp, i]),
+        "alisb_begin_pass": (i, [vp, i]),
+        "alisb_fused_launch_count": (u64, [vp]),
         "alisb_halo_info": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "alisb_halo_pack": (i, [vp, i]),
         "alisb_halo_unpack": (i, [vp, i]),
@@ -290,6 +294,19 @@ class Engine:
         out = np.zeros((arr.shape[0], 2), np.float64)
         self._ck(self.lib.alisb_plane_flux(self.h, arr.ctypes.data_as(C.c_void_p), arr.shape[0], out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def set_fusion(self, on):
+        """fused E+H stepping where a step is only the two curls (include/alis_b200.h)"""
+        self._ck(self.lib.alisb_set_fusion(self.h, 1 if on else 0))
+
+    def fused_launch_count(self):
+        return int(self.lib.alisb_fused_launch_count(self.h))
+
+    def flush(self, h_pass_follows=False):
+        self._ck(self.lib.alisb_flush(self.h, 1 if h_pass_follows else 0))
+
+    def begin_pass(self, set_):
+        self._ck(self.lib.alisb_begin_pass(self.h, set_))
 
     def chi2_couple(self, obj, m, pump1, pump2, d, alt):
         """coupleTWM (update.c:356-391): mixes E(pump1) x E(pump2) into this engine's E inside ADE object obj"""

@@ -30,7 +30,7 @@ static int fail(int code, const char *fmt, ...)
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ALISB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-struct SubBox { int a0, a1, b0, b1, c0, c1; int pml; };   /* cell ranges; pml: bit 0/1/2 = may touch x/y/z slabs */
+struct SubBox { int a0, a1, b0, b1, c0, c1; int pml; int fusable; };   /* fusable: the slab-free, fix-up-free box of the fused E+H kernel */   /* cell ranges; pml: bit 0/1/2 = may touch x/y/z slabs */
 struct ProfRec { size_t ev; int set, sub; double cells; };
 struct alisb_engine;
 /* a whole pass (all kernels of updateE or updateH, auxiliary TFSF worlds included) captured once as
@@ -69,7 +69,18 @@ struct alisb_engine {
 	alisb_grid g;
 	int nx, ny, nz, pitch;
 	size_t plane, elems;               /* floats per z-plane / per array (incl. slack)    */
-	float *F[2][2][3];
+	float *F[2][2][3];                 /* current fields [set][m][comp]                    */
+	float *Fb[2][2][3];                /* double-buffered mode: the other buffer (input of a running pass) */
+	bool dbuf;                         /* passes run out of place (Fb -> F) and swap at pass begin */
+	bool pass_open[2];                 /* the running pass of this set has already swapped  */
+	int fuse_req;                      /* fused E+H kernel requested (ALISB_FUSE / alisb_set_fusion) */
+	double tune_fuse_frac;             /* smallest fused share of the grid worth fusing     */
+	long tune_fuse_min;                /* smallest grid (cells) worth fusing                */
+	bool fuse_ok; uint64_t fuse_cfg;   /* feasibility for the current configuration          */
+	int R[6];                          /* the fused box a0,a1,b0,b1,c0,c1                    */
+	std::vector<std::pair<int,int> > fuse_z;   /* its clean z ranges                        */
+	int pendingE;                      /* -1, or the part of an E pass prepared but not yet launched */
+	bool fusing, h_fused;              /* launching the fused variant / H' of the fused box is already in the H output buffer */
 	float *eps[3];
 	float *dtd[2][3], *P[2][3], *P1[2][3], *P2[2][3];
 	float *psi[2][2][3][2][2]; size_t psi_elems[2][3][2];
@@ -80,9 +91,10 @@ struct alisb_engine {
 	std::vector<alisb_copy> copies[2];
 	cudaStream_t stream; bool own_stream;
 	uint64_t step; float t, tE, tH;
-	uint64_t launches;
+	uint64_t launches, fused_launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_fchunk;                   /* planes per z-chunk of the fused kernel              */
 	int tune_merge;                    /* PML shell boxes gathered into two merged launches  */
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
@@ -108,6 +120,13 @@ struct alisb_phaser {
 	float2 *acc[6];
 	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev; bool ev_pending;
 };
+
+/* fused stepping defers the E pass (see alisb_step_part): every entry point that reads the device
+ * state calls SETTLE, every one that changes fields or the configuration calls UNFUSE (the H' already
+ * written for the fused box would be stale) */
+static int launch_pending(alisb_engine *e, bool fused);
+#define SETTLE(e) TRY(launch_pending((e), false))
+#define UNFUSE(e) do { TRY(launch_pending((e), false)); (e)->h_fused = false; } while (0)
 
 extern "C" int alisb_abi_version(void) { return ALISB_ABI_VERSION; }
 extern "C" const char *alisb_last_error(void) { return g_err; }
@@ -162,9 +181,10 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	e->pitch = ((ALISB_XO + g->nx + 2) + 31)/32*32;
 	e->plane = (size_t)(g->ny + 2)*e->pitch;
 	e->elems = e->plane*(g->nz + 2) + 64;
-	memset(e->F, 0, sizeof e->F); memset(e->eps, 0, sizeof e->eps); memset(e->psi, 0, sizeof e->psi);
+	memset(e->F, 0, sizeof e->F); memset(e->Fb, 0, sizeof e->Fb); memset(e->eps, 0, sizeof e->eps);
+	e->dbuf = false; e->pass_open[0] = e->pass_open[1] = false; e->fuse_ok = false; e->fuse_cfg = 0; e->pendingE = -1; e->fusing = false; e->h_fused = false; memset(e->psi, 0, sizeof e->psi);
 	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
-	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
+	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->fused_launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
 	for (int r=0; r<SRC_RING; r++) { e->srcv_h[r] = 0; e->srcv_d[r] = 0; e->srcv_ev[r] = 0; }
 	e->cfg_version = 1; e->cur_src_fused[0] = e->cur_src_fused[1] = false; e->cur_src_slot[0] = e->cur_src_slot[1] = -1;
@@ -212,6 +232,10 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		e->tune_debug = (s = getenv("ALISB_DEBUG")) ? atoi(s) : 0;
 		e->tune_conc = (s = getenv("ALISB_CONC")) ? atoi(s) : 1;
 		e->tune_merge = (s = getenv("ALISB_MERGE")) ? atoi(s) : 1;
+		e->fuse_req = (s = getenv("ALISB_FUSE")) ? atoi(s) : 1;      /* on by default; only grids of >= tune_fuse_min cells with a large clean box actually fuse */
+		e->tune_fchunk = (s = getenv("ALISB_FCHUNK")) ? atoi(s) : 16;
+		e->tune_fuse_frac = (s = getenv("ALISB_FUSE_FRAC")) ? atof(s) : 0.5;
+		e->tune_fuse_min = (s = getenv("ALISB_FUSE_MIN")) ? atol(s) : (1L << 24);
 		e->tune_small = (s = getenv("ALISB_SMALL")) ? atol(s) : 3000000L;   /* crossover measured at ~150^3 (profiles/small_grid_probe.py) */
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -234,6 +258,7 @@ static void free_src(SrcObj *s)
 
 extern "C" int alisb_clear_sources(alisb_engine *e)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
@@ -245,6 +270,7 @@ extern "C" int alisb_clear_sources(alisb_engine *e)
 
 extern "C" int alisb_clear_dispersive(alisb_engine *e)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
@@ -261,9 +287,10 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	if (!e) return;
 	cudaSetDevice(e->g.device);
 	cudaStreamSynchronize(e->stream);
+	e->pendingE = -1; e->h_fused = false;
 	alisb_clear_sources(e);
 	alisb_clear_dispersive(e);
-	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int c=0; c<3; c++) cudaFree(e->F[s][m][c]);
+	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int c=0; c<3; c++) { cudaFree(e->F[s][m][c]); cudaFree(e->Fb[s][m][c]); }
 	for (int c=0; c<3; c++) cudaFree(e->eps[c]);
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { cudaFree(e->dtd[s][ax]); cudaFree(e->P[s][ax]); cudaFree(e->P1[s][ax]); cudaFree(e->P2[s][ax]); }
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psi[s][m][ax][sd][w]);
@@ -281,6 +308,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 
 extern "C" int alisb_set_stream(alisb_engine *e, void *s)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
@@ -301,6 +329,7 @@ static int upload_table(alisb_engine *e, float *dst, const float *src, int n, in
 
 extern "C" int alisb_set_axis_tables(alisb_engine *e, int set, int axis, const float *dtd, const float *P, const float *P1, const float *P2)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	if (set<0 || set>1 || axis<0 || axis>2 || !dtd) return fail(ALISB_EINVAL, "bad tables");
 	DEV(e);
@@ -314,6 +343,7 @@ extern "C" int alisb_set_axis_tables(alisb_engine *e, int set, int axis, const f
 
 extern "C" int alisb_set_inv_eps(alisb_engine *e, const float *cx, const float *cy, const float *cz)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	DEV(e);
 	CU(cudaStreamSynchronize(e->stream));
@@ -347,6 +377,7 @@ static int upload_box(float **dst, const float *zfast, const Box &B)
 
 extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	if (!d || d->nk > ALISB_MAXPOLES || d->nj > d->nk || d->nk < 0) return fail(ALISB_EINVAL, "bad pole counts");
 	DEV(e);
@@ -370,6 +401,7 @@ extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
 
 extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	if (!s || s->set<0 || s->set>1 || s->comp<0 || s->comp>2 || s->m<0 || s->m>e->g.complex_field || !s->waveform) return fail(ALISB_EINVAL, "bad source");
 	DEV(e);
@@ -396,6 +428,7 @@ extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
 
 extern "C" int alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	if (!t || !t->aux) return fail(ALISB_EINVAL, "bad tfsf");
 	TfsfObj *o = new TfsfObj();
@@ -408,6 +441,7 @@ extern "C" int alisb_add_tfsf(alisb_engine *e, const alisb_tfsf *t)
 
 extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops, int n)
 {
+	UNFUSE(e);
 	e->cfg_version++;
 	if (set<0 || set>1 || n<0) return fail(ALISB_EINVAL, "bad copies");
 	e->copies[set].assign(ops, ops + n);
@@ -452,6 +486,97 @@ static void launch_multi(cudaStream_t st, const MultiParams &mp, unsigned nctas,
 	else                    launch_multi_te<-1,false>(st, mp, nctas, cls);
 }
 
+/* ---- fused E+H stepping (temporal blocking) ------------------------------------------------------
+ * Where a step is nothing but the two curls -- no CPML slab, no material array, no ADE object, no
+ * source / TFSF strip / boundary-copy target -- E' and H' of a cell can be formed in one pass over
+ * memory (kernel yee_fused).  fuse_eval finds the largest such box R and its clean z ranges for the
+ * current configuration.  R needs plain cells on its low sides (the kernel recomputes E' on the
+ * halo a-1, b-1, c-1), so it starts one cell above the low slabs; its x range is a whole number of
+ * 32-cell groups.  Everything outside R keeps the two-pass kernels.  Fields are double buffered in
+ * this mode: every pass reads Fb and writes F, the pointers swap when a pass begins.             */
+static void fuse_eval(alisb_engine *e)
+{
+	if (e->fuse_cfg == e->cfg_version) return;
+	e->fuse_cfg = e->cfg_version;
+	const bool was = e->fuse_ok;
+	e->fuse_ok = false; e->fuse_z.clear();
+	auto done = [&]() { if (was != e->fuse_ok) { e->plan[0].clear(); e->plan[1].clear(); } };
+	const long cells = (long)e->nx*e->ny*e->nz;
+	if (!e->fuse_req || cells < e->tune_fuse_min || cells < e->tune_small || e->eps[0] || !e->obj.empty() || e->tune_bx != 1 || e->tune_by != 8) return done();
+	const int n[3] = {e->nx, e->ny, e->nz};
+	int lo[3], hi[3];
+	for (int ax=0; ax<3; ax++) {
+		lo[ax] = 2; hi[ax] = n[ax];                 /* the low halo (cell 1 at least) must be an updated cell */
+		for (int set=0; set<2; set++) {
+			const int f0 = e->g.pml[set][ax][0][0], l0 = e->g.pml[set][ax][0][1], f1 = e->g.pml[set][ax][1][0], l1 = e->g.pml[set][ax][1][1];
+			if (f0 <= l0) lo[ax] = std::max(lo[ax], l0 + (set == ALISB_SET_E ? 2 : 1));   /* E' is also formed on the halo cell below */
+			if (f1 <= l1) hi[ax] = std::min(hi[ax], f1 - 1);
+		}
+	}
+	hi[2] = std::min(hi[2], e->nz - 1);             /* plane nz is the E send plane of a sharded run (alisb_step_part) */
+	/* x in whole 32-cell groups starting at a = 1 mod 32 */
+	int a0 = (lo[0] - 1 + 31)/32*32 + 1;
+	int a1 = a0 - 1 + (hi[0] - a0 + 1)/32*32;
+	if (a1 < a0 || lo[1] > hi[1] || lo[2] > hi[2]) return done();
+	e->R[0] = a0; e->R[1] = a1; e->R[2] = lo[1]; e->R[3] = hi[1]; e->R[4] = lo[2]; e->R[5] = hi[2];
+	/* boundary copies on E change E after the curl: none may land in R or on its low halo (H' of R
+	 * was formed from the plain E').  Copies on H are applied after the H pass, on top of H'.      */
+	for (const alisb_copy &k : e->copies[ALISB_SET_E]) {
+		bool hit = true;
+		for (int ax=0; ax<3; ax++) if (k.box[2*ax+1] < e->R[2*ax] - 1 || k.box[2*ax] > e->R[2*ax+1]) hit = false;
+		if (hit) return done();
+	}
+	/* planes whose H' depends on an E that a fix-up changes after the curl: sources on E, TFSF E strips */
+	std::vector<char> dirty(e->nz + 3, 0);
+	auto mark = [&](int c0, int c1) { for (int c=std::max(c0, 0); c<=std::min(c1 + 1, e->nz + 1); c++) dirty[c] = 1; };
+	for (SrcObj *so : e->src[ALISB_SET_E]) mark(so->d.box[4], so->d.box[5]);
+	for (TfsfObj *t : e->tf) for (const alisb_strip &st : t->sE) mark(st.box[4], st.box[5]);
+	long fused_planes = 0;
+	for (int c=lo[2]; c<=hi[2]; ) {
+		if (dirty[c]) { c++; continue; }
+		int d = c;
+		while (d + 1 <= hi[2] && !dirty[d + 1]) d++;
+		if (d - c + 1 >= 4) { e->fuse_z.push_back(std::make_pair(c, d)); fused_planes += d - c + 1; }
+		c = d + 1;
+	}
+	const double frac = (double)(a1 - a0 + 1)*(hi[1] - lo[1] + 1)*fused_planes/(double)cells;
+	if (frac < e->tune_fuse_frac) { e->fuse_z.clear(); return done(); }   /* not worth doubling the field memory */
+	e->fuse_ok = true;
+	if (e->tune_debug) fprintf(stderr, "[alisb] fused box a %d..%d b %d..%d c %d..%d, %zu clean z range(s), %.1f%% of the grid\n", a0, a1, lo[1], hi[1], lo[2], hi[2], e->fuse_z.size(), 100*frac);
+	done();
+}
+
+/* switch to double-buffered passes (sticky): the second buffer starts as a copy so that ghost cells
+ * and not-yet-updated cells agree */
+static int enable_dbuf(alisb_engine *e)
+{
+	if (e->dbuf) return ALISB_OK;
+	/* twice the field memory: only when it fits with room to spare */
+	size_t free_b = 0, total_b = 0;
+	CU(cudaMemGetInfo(&free_b, &total_b));
+	const size_t need = (size_t)6*(e->g.complex_field + 1)*e->elems*sizeof(float);
+	if (need + (total_b >> 4) > free_b) {
+		if (e->tune_debug) fprintf(stderr, "[alisb] fused stepping off: %.1f GB more field memory needed, %.1f GB free\n", need*1e-9, free_b*1e-9);
+		e->fuse_req = 0; e->fuse_ok = false; e->fuse_z.clear(); e->plan[0].clear(); e->plan[1].clear();
+		return ALISB_OK;
+	}
+	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) for (int c=0; c<3; c++) {
+		TRY(dalloc(&e->Fb[s][m][c], e->elems));
+		CU(cudaMemcpyAsync(e->Fb[s][m][c], e->F[s][m][c], e->elems*sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+	}
+	e->dbuf = true;
+	e->cfg_version++; e->fuse_cfg = e->cfg_version;      /* drops captured graphs; feasibility is unchanged */
+	return ALISB_OK;
+}
+
+/* a pass of `set` begins: in double-buffered mode the buffers swap once per pass */
+static void open_pass(alisb_engine *e, int set)
+{
+	if (!e->dbuf || e->pass_open[set]) return;
+	for (int m=0; m<=e->g.complex_field; m++) for (int c=0; c<3; c++) std::swap(e->F[set][m][c], e->Fb[set][m][c]);
+	e->pass_open[set] = true;
+}
+
 /* Region-specialised launches.  Per axis the cells split into lo slab / slab-free middle / hi slab
  * (x in units of 128-cell tiles: tiles that contain slab cells vs. the rest).  Every region runs
  * the yee_volume instantiation that only carries the PML code (and registers) of the slabs it can
@@ -481,25 +606,49 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 		/* small grids are launch-bound: one launch with every slab the grid has */
 		int pm = 0;
 		for (int ax=0; ax<3; ax++) if (lo[ax] > 1 || hi[ax] < n[ax]) pm |= 1 << ax;
-		L.push_back({1, e->nx, 1, e->ny, 1, e->nz, pm});
+		L.push_back({1, e->nx, 1, e->ny, 1, e->nz, pm, 0});
 		return;
 	}
-	if (xl >= 1)         X.push_back({1, xl, 1});
-	if (xl + 1 <= xh - 1) X.push_back({xl + 1, xh - 1, 0});
-	if (xh <= e->nx)     X.push_back({xh, e->nx, 1});
-	if (lo[1] > 1)       Y.push_back({1, lo[1] - 1, 2});
-	if (lo[1] <= hi[1])  Y.push_back({lo[1], hi[1], 0});
-	if (hi[1] < e->ny)   Y.push_back({hi[1] + 1, e->ny, 2});
-	if (lo[2] > 1)       Z.push_back({1, lo[2] - 1, 4});
-	if (lo[2] <= hi[2])  Z.push_back({lo[2], hi[2], 0});
-	if (hi[2] < e->nz)   Z.push_back({hi[2] + 1, e->nz, 4});
-	const int xany = (xl >= 1 || xh <= e->nx) ? 1 : 0;
-	for (const Range &z : Z) for (const Range &y : Y) {
-		if (y.pm) {      /* thin y-slab rows: one launch over the whole row with the x code included */
-			L.push_back({1, e->nx, y.a, y.b, z.a, z.b, xany | y.pm | z.pm});
+	/* does [a,b] on axis ax hold slab cells of this field set? */
+	auto slabby = [&](int ax, int a, int b) -> bool {
+		for (int sd=0; sd<2; sd++) { const int f = e->g.pml[set][ax][sd][0], l = e->g.pml[set][ax][sd][1]; if (f <= l && a <= l && b >= f) return true; }
+		return false; };
+	if (e->fuse_ok) {
+		/* the centre box is the fused box R (same for both field sets); what lies outside it is cut
+		 * as usual and carries a PML bit wherever it holds slab cells */
+		const int *R = e->R;
+		if (R[0] > 1)       X.push_back({1, R[0] - 1, slabby(0, 1, R[0] - 1) ? 1 : 0});
+		X.push_back({R[0], R[1], 0});
+		if (R[1] < e->nx)   X.push_back({R[1] + 1, e->nx, slabby(0, R[1] + 1, e->nx) ? 1 : 0});
+		if (R[2] > 1)       Y.push_back({1, R[2] - 1, slabby(1, 1, R[2] - 1) ? 2 : 0});
+		Y.push_back({R[2], R[3], 0});
+		if (R[3] < e->ny)   Y.push_back({R[3] + 1, e->ny, slabby(1, R[3] + 1, e->ny) ? 2 : 0});
+		if (R[4] > 1)       Z.push_back({1, R[4] - 1, slabby(2, 1, R[4] - 1) ? 4 : 0});
+		Z.push_back({R[4], R[5], 0});
+		if (R[5] < e->nz)   Z.push_back({R[5] + 1, e->nz, slabby(2, R[5] + 1, e->nz) ? 4 : 0});
+	} else {
+		if (xl >= 1)         X.push_back({1, xl, 1});
+		if (xl + 1 <= xh - 1) X.push_back({xl + 1, xh - 1, 0});
+		if (xh <= e->nx)     X.push_back({xh, e->nx, 1});
+		if (lo[1] > 1)       Y.push_back({1, lo[1] - 1, 2});
+		if (lo[1] <= hi[1])  Y.push_back({lo[1], hi[1], 0});
+		if (hi[1] < e->ny)   Y.push_back({hi[1] + 1, e->ny, 2});
+		if (lo[2] > 1)       Z.push_back({1, lo[2] - 1, 4});
+		if (lo[2] <= hi[2])  Z.push_back({lo[2], hi[2], 0});
+		if (hi[2] < e->nz)   Z.push_back({hi[2] + 1, e->nz, 4});
+	}
+	const int xany = slabby(0, 1, e->nx) ? 1 : 0;
+	for (size_t zi=0; zi<Z.size(); zi++) for (size_t yi=0; yi<Y.size(); yi++) {
+		const Range &z = Z[zi], &y = Y[yi];
+		const bool ymid = e->fuse_ok ? (y.a == e->R[2] && y.b == e->R[3]) : y.pm == 0;
+		if (!ymid && (y.b - y.a + 1) <= 64) {      /* thin y rows: one launch over the whole row with the x code included */
+			L.push_back({1, e->nx, y.a, y.b, z.a, z.b, xany | y.pm | z.pm, 0});
 			continue;
 		}
-		for (const Range &x : X) L.push_back({x.a, x.b, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm});
+		for (const Range &x : X) {
+			const int fus = e->fuse_ok && x.a == e->R[0] && x.b == e->R[1] && y.a == e->R[2] && y.b == e->R[3] && z.a == e->R[4] && z.b == e->R[5];
+			L.push_back({x.a, x.b, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm, fus});
+		}
 	}
 	/* largest region first (it is also the dominant kernel reported by alisb_profile_dominant) */
 	std::stable_sort(L.begin(), L.end(), [](const SubBox &p, const SubBox &q) {
@@ -512,6 +661,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	memset(&p, 0, sizeof p);
 	for (int c=0; c<3; c++) {
 		p.F[c] = e->F[set][m][c]; p.G[c] = e->F[1-set][m][c];
+		p.Fin[c] = e->dbuf ? e->Fb[set][m][c] : e->F[set][m][c];
 		p.C[c] = set == ALISB_SET_E ? e->eps[c] : 0;
 		p.dtd[c] = e->dtd[set][c]; p.P[c] = e->P[set][c]; p.P1[c] = e->P1[set][c]; p.P2[c] = e->P2[set][c];
 		for (int sd=0; sd<2; sd++) {
@@ -551,11 +701,54 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		cudaEventRecord(e->ev_pool[e->ev_used++], st);
 		return e->ev_pool[e->ev_used++];
 	};
+	/* the fused box: in the E pass its clean z ranges run the fused E+H kernel (when the pass is
+	 * issued as the fused variant), in the following H pass they are skipped; its other planes and
+	 * every other box run the two-pass kernel */
+	struct Piece { SubBox sb; int sub; bool fused; };
+	std::vector<Piece> work;
 	for (const SubBox &sb0 : e->plan[set]) {
 		sub++;
-		SubBox sb = sb0;
+		const bool skipz = sb0.fusable && e->fuse_ok && ((set == ALISB_SET_E && e->fusing) || (set == ALISB_SET_H && e->h_fused));
+		if (!skipz) { work.push_back({sb0, sub, false}); continue; }
+		int c = sb0.c0;
+		for (const std::pair<int,int> &z : e->fuse_z) {
+			if (z.first > c) { SubBox d = sb0; d.c0 = c; d.c1 = z.first - 1; work.push_back({d, sub, false}); }
+			if (set == ALISB_SET_E) { SubBox d = sb0; d.c0 = z.first; d.c1 = z.second; work.push_back({d, sub, true}); }
+			c = z.second + 1;
+		}
+		if (c <= sb0.c1) { SubBox d = sb0; d.c0 = c; d.c1 = sb0.c1; work.push_back({d, sub, false}); }
+	}
+	for (const Piece &pc : work) {
+		sub = pc.sub;
+		SubBox sb = pc.sb;
 		sb.c0 = std::max(sb.c0, e->f_lo); sb.c1 = std::min(sb.c1, e->f_hi);
 		if (sb.c0 > sb.c1) continue;
+		if (pc.fused) {
+			FusedParams fp;
+			memset(&fp, 0, sizeof fp);
+			for (int c=0; c<3; c++) {
+				fp.Ei[c] = e->Fb[ALISB_SET_E][m][c]; fp.Eo[c] = e->F[ALISB_SET_E][m][c];
+				fp.Hi[c] = e->F[ALISB_SET_H][m][c];  fp.Ho[c] = e->Fb[ALISB_SET_H][m][c];
+				fp.dtdE[c] = e->dtd[ALISB_SET_E][c]; fp.dtdH[c] = e->dtd[ALISB_SET_H][c];
+			}
+			fp.ny = e->ny; fp.pitch = e->pitch; fp.plane = e->plane;
+			fp.a_first = sb.a0; fp.a_last = sb.a1; fp.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
+			fp.b_first = sb.b0; fp.b_last = sb.b1; fp.c_first = sb.c0; fp.c_last = sb.c1;
+			const int nzs = sb.c1 - sb.c0 + 1, gyf = div_up(sb.b1 - sb.b0 + 1, 8);
+			fp.cchunk = std::min(nzs, std::max(1, e->tune_fchunk));
+			dim3 grid(fp.nseg, gyf, div_up(nzs, fp.cchunk)), block(32, 9, 1);
+			cudaStream_t st = side_stream(true);
+			nlaunched++;
+			/* profiling counts cell-passes: a fused launch does two passes per cell */
+			cudaEvent_t e1 = prof_begin(st, sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
+			if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] fused E+H cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, grid.x, grid.y, grid.z, fp.cchunk);
+			static bool smem_set = false;
+			if (!smem_set) { CU(cudaFuncSetAttribute(yee_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))); smem_set = true; }
+			yee_fused<<<grid, block, sizeof(FusedSmem), st>>>(fp);
+			e->launches++; e->fused_launches++;
+			if (e->profiling) CU(cudaEventRecord(e1, st));
+			continue;
+		}
 		VolRegion r;
 		memset(&r, 0, sizeof r);
 		const bool narrow = (sb.pml == 1 || sb.pml == 5) && sb.a1 - sb.a0 + 1 <= 64;     /* x-PML strips */
@@ -630,15 +823,18 @@ static void fill_ade(alisb_engine *e, DispObj *o, int m, AdeParams &p)
 
 static int ade_pre(alisb_engine *e, int m)
 {
+	/* loss and J subtraction act on the OLD E (update.c:89-108), i.e. on the pass's input buffer */
 	AdeParams p;
 	for (DispObj *o : e->obj) {
 		fill_ade(e, o, m, p);
+		if (e->dbuf) for (int c=0; c<3; c++) p.F[c] = e->Fb[ALISB_SET_E][m][c];
 		const size_t n = bcount(p.upd);
 		if (!n || !p.lossy) continue;
 		ade_loss<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
 	}
 	for (DispObj *o : e->obj) {
 		fill_ade(e, o, m, p);
+		if (e->dbuf) for (int c=0; c<3; c++) p.F[c] = e->Fb[ALISB_SET_E][m][c];
 		const size_t n = bcount(p.upd);
 		if (!n || !p.nk) continue;
 		ade_subtract<<<div_up(n, 256), 256, 0, e->stream>>>(p); e->launches++;
@@ -879,6 +1075,7 @@ static int pass_prepare(alisb_engine *e, int set, int part)
 		if (x->stream != e->stream) { CU(cudaStreamSynchronize(x->stream)); if (x->own_stream) { cudaStreamDestroy(x->stream); x->own_stream = false; } x->stream = e->stream; x->cfg_version++; }
 		TRY(pass_prepare(x, set, ALISB_PART_ALL));
 	}
+	open_pass(e, set);
 	set_filter(e, set, part);
 	TRY(prepare_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
 	return ALISB_OK;
@@ -906,14 +1103,19 @@ static int pass_launch(alisb_engine *e, int set, int part)
 }
 
 /* bookkeeping after the pass has been issued (times: update.c:298,340) */
-static int pass_finish(alisb_engine *e, int set, int part)
+static void pass_time(alisb_engine *e, int set, int part)
+{
+	if (part == ALISB_PART_SEND_PLANE) return;
+	if (set == ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;
+	else e->t = e->tH = e->tE + 0.5 * e->g.dt;
+	e->pass_open[set] = false;
+}
+
+static int pass_finish(alisb_engine *e, int set, int part, bool time_done = false)
 {
 	if (part != ALISB_PART_REST) for (TfsfObj *t : e->tf) TRY(pass_finish(t->d.aux, set, ALISB_PART_ALL));
 	TRY(finish_sources(e, set));
-	if (part != ALISB_PART_SEND_PLANE) {
-		if (set == ALISB_SET_E) e->t = e->tE = ++e->step * e->g.dt;
-		else e->t = e->tH = e->tE + 0.5 * e->g.dt;
-	}
+	if (!time_done) pass_time(e, set, part);
 	return ALISB_OK;
 }
 
@@ -926,15 +1128,76 @@ static uint64_t config_version(alisb_engine *e)
 
 static bool graphable(alisb_engine *e, int set)
 {
-	if (!e->graph_ok || e->profiling) return false;
+	if (!e->graph_ok || e->profiling || e->dbuf || e->fuse_ok) return false;
 	if (!e->src[set].empty() && !e->cur_src_fused[set]) return false;
 	for (TfsfObj *t : e->tf) if (!graphable(t->d.aux, set)) return false;
 	return true;
 }
 
+/* issue a deferred E pass: as the fused variant (the caller is about to run the H pass and nothing
+ * touched the fields in between) or as the plain two-pass variant */
+static int launch_pending(alisb_engine *e, bool fused)
+{
+	if (e->pendingE < 0) return ALISB_OK;
+	const int part = e->pendingE;
+	e->pendingE = -1;
+	e->fusing = fused && e->fuse_ok;
+	const int r = pass_launch(e, ALISB_SET_E, part);
+	const bool did = e->fusing;
+	e->fusing = false;
+	if (r != ALISB_OK) return r;
+	e->h_fused = did;
+	return pass_finish(e, ALISB_SET_E, part, true);
+}
+
+extern "C" uint64_t alisb_fused_launch_count(alisb_engine *e) { return e->fused_launches; }
+
+extern "C" int alisb_set_fusion(alisb_engine *e, int on)
+{
+	UNFUSE(e);
+	e->fuse_req = on ? 1 : 0; e->cfg_version++;
+	return ALISB_OK;
+}
+
+extern "C" int alisb_flush(alisb_engine *e, int h_pass_follows)
+{
+	DEV(e);
+	return launch_pending(e, h_pass_follows != 0);
+}
+
+extern "C" int alisb_begin_pass(alisb_engine *e, int set)
+{
+	if (set < 0 || set > 1) return fail(ALISB_EINVAL, "bad field set");
+	DEV(e);
+	if (set == ALISB_SET_E) UNFUSE(e);
+	fuse_eval(e);
+	if (e->fuse_ok) TRY(enable_dbuf(e));
+	open_pass(e, set);
+	return ALISB_OK;
+}
+
 extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 {
 	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
+	if (e->fuse_req || e->dbuf) {
+		CU(cudaSetDevice(e->g.device));
+		if (set == ALISB_SET_E) {
+			if (e->pendingE >= 0 || (e->h_fused && part != ALISB_PART_REST)) UNFUSE(e);
+			fuse_eval(e);
+			if (e->fuse_ok) TRY(enable_dbuf(e));
+			bool list_sources = true;
+			for (SrcObj *so : e->src[ALISB_SET_E]) if (so->cnt > 16384) list_sources = false;
+			if (e->fuse_ok && part != ALISB_PART_SEND_PLANE && list_sources && (int)e->src[ALISB_SET_E].size() <= ALISB_MAXSRCOPS) {
+				/* host side and bookkeeping now, kernels when the H pass (or anything else) arrives */
+				TRY(pass_prepare(e, set, part));
+				pass_time(e, set, part);
+				e->pendingE = part;
+				return ALISB_OK;
+			}
+		} else {
+			TRY(launch_pending(e, true));
+		}
+	}
 	TRY(pass_prepare(e, set, part));
 	if (graphable(e, set)) {
 		PassGraph &G = e->graph[set][part];
@@ -975,6 +1238,7 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 		return pass_finish(e, set, part);
 	}
 	TRY(pass_launch(e, set, part));
+	if (set == ALISB_SET_H && part != ALISB_PART_SEND_PLANE) e->h_fused = false;      /* the H pass is complete */
 	return pass_finish(e, set, part);
 }
 
@@ -988,15 +1252,17 @@ extern "C" int alisb_run(alisb_engine *e, int steps)
 	return ALISB_OK;
 }
 
-extern "C" int alisb_synchronize(alisb_engine *e) { DEV(e); CU(cudaStreamSynchronize(e->stream)); return ALISB_OK; }
+extern "C" int alisb_synchronize(alisb_engine *e) { DEV(e); SETTLE(e); CU(cudaStreamSynchronize(e->stream)); return ALISB_OK; }
 extern "C" int alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH) { if (n) *n = e->step; if (t) *t = e->t; if (tE) *tE = e->tE; if (tH) *tH = e->tH; return ALISB_OK; }
-extern "C" int alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH) { e->step = n; e->t = t; e->tE = tE; e->tH = tH; return ALISB_OK; }
+extern "C" int alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH) { SETTLE(e); e->step = n; e->t = t; e->tE = tE; e->tH = tH; return ALISB_OK; }
 
 extern "C" int alisb_reset_fields(alisb_engine *e)
 {
 	DEV(e);
+	UNFUSE(e);
 	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) {
 		for (int c=0; c<3; c++) CU(cudaMemsetAsync(e->F[s][m][c], 0, e->elems*sizeof(float), e->stream));
+		if (e->dbuf) for (int c=0; c<3; c++) CU(cudaMemsetAsync(e->Fb[s][m][c], 0, e->elems*sizeof(float), e->stream));
 		for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++)
 			if (e->psi[s][m][ax][sd][w]) CU(cudaMemsetAsync(e->psi[s][m][ax][sd][w], 0, e->psi_elems[s][ax][sd]*sizeof(float), e->stream));
 	}
@@ -1069,7 +1335,7 @@ static long long arr_offset(alisb_engine *e, const ArrRef &r, int a, int b, int 
 	return -1;
 }
 
-static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
+static int rw_box_one(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
 {
 	DEV(e);
 	ArrRef r;
@@ -1100,6 +1366,22 @@ static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t 
 	e->launches++;
 	return ALISB_OK;
 }
+static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
+{
+	DEV(e);
+	if (write) UNFUSE(e); else SETTLE(e);
+	TRY(rw_box_one(e, arr, ids, box, host, write));
+	if (write && arr == ALISB_ARR_FIELD && e->dbuf) {
+		/* both buffers, so that ghost cells and cells no pass rewrites stay in agreement */
+		float **cur = &e->F[ids[0]][ids[2]][ids[1]], **oth = &e->Fb[ids[0]][ids[2]][ids[1]];
+		std::swap(*cur, *oth);
+		const int r = rw_box_one(e, arr, ids, box, host, true);
+		std::swap(*cur, *oth);
+		return r;
+	}
+	return ALISB_OK;
+}
+
 extern "C" int alisb_read_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(e, arr, ids, box, host, false); }
 extern "C" int alisb_write_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(e, arr, ids, box, (float*)host, true); }
 
@@ -1114,6 +1396,7 @@ extern "C" int alisb_chi2_couple(alisb_engine *e, int obj, int m, alisb_engine *
 			return fail(ALISB_EINVAL, "chi2: the coupled worlds must share one grid and one device");
 	if (!e->eps[0]) return fail(ALISB_EINVAL, "chi2: the signal world has no material arrays");
 	DEV(e);
+	UNFUSE(e); SETTLE(p1); SETTLE(p2);
 	const DispObj *o = e->obj[obj];
 	Chi2Params p;
 	memset(&p, 0, sizeof p);
@@ -1160,6 +1443,7 @@ extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes,
 {
 	if (n < 1 || !planes || !out) return fail(ALISB_EINVAL, "bad flux request");
 	DEV(e);
+	SETTLE(e);
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) if (!e->spacing[s][ax]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
 	if (n > e->flux_cap) {
 		cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
@@ -1242,6 +1526,7 @@ extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const
 {
 	alisb_engine *e = p->e;
 	DEV(e);
+	SETTLE(e);
 	if (p->ev_pending) CU(cudaEventSynchronize(p->ev));       /* pinned staging buffers free again */
 	memcpy(p->hexp[0], expE, 2*(size_t)p->nfreq*sizeof(float));
 	memcpy(p->hexp[1], expH, 2*(size_t)p->nfreq*sizeof(float));

@@ -20,6 +20,7 @@
 
 struct VolParams {
 	float       *F[3];            /* field set being updated (E or H), components x,y,z */
+	const float *Fin[3];          /* where the old values are read: == F (in place) or the other buffer (double-buffered mode) */
 	const float *G[3];            /* the other field set                                */
 	const float *C[3];            /* inverse permittivity (E pass, EPS variant)         */
 	const float *dtd[3];          /* dtdx (stored shifted by XO), dtdy, dtdz            */
@@ -92,7 +93,8 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 	const size_t row = (size_t)b*p.pitch + ALISB_XO + a0;    /* offset inside a plane */
 	const ptrdiff_t yn = (ptrdiff_t)S*p.pitch;               /* to row b+S            */
 
-	float *__restrict__ F0 = p.F[0], *__restrict__ F1 = p.F[1], *__restrict__ F2 = p.F[2];
+	float *F0 = p.F[0], *F1 = p.F[1], *F2 = p.F[2];
+	const float *I0 = p.Fin[0], *I1 = p.Fin[1], *I2 = p.Fin[2];
 	const float *__restrict__ G0 = p.G[0], *__restrict__ G1 = p.G[1], *__restrict__ G2 = p.G[2];
 
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -137,7 +139,7 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 		if (ldg) { gx = ld4(G0 + o); gy = ld4s<STREAM>(G1 + o); gz = ld4(G2 + o); }
 		if (act) {
 			gxn = ld4(G0 + o + yn); gzn = ld4(G2 + o + yn);
-			fx = ld4s<STREAM>(F0 + o); fy = ld4s<STREAM>(F1 + o); fz = ld4s<STREAM>(F2 + o);
+			fx = ld4s<STREAM>(I0 + o); fy = ld4s<STREAM>(I1 + o); fz = ld4s<STREAM>(I2 + o);
 			if (EPS) { cx = ld4(p.C[0] + o); cy = ld4(p.C[1] + o); cz = ld4(p.C[2] + o); }
 		}
 		/* x-neighbour element (a0+4 for S=+1, a0-1 for S=-1) from the adjacent lane */
@@ -260,6 +262,202 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 			for (int e = 0; e < 4; e++) if (a0 + e <= r.a_last) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
 		}
 		gxp = gx; gyp = gy;
+	}
+}
+
+/*
+ * Fused E+H step on a slab-free, fix-up-free box (temporal blocking of update.c:275-341 where
+ * nothing but the two curls happens): E' = E + curl H,  H' = H + curl E'  in ONE pass over memory,
+ * 48 B per cell-step instead of 72.  Out of place (reads Ei/Hi, writes Eo/Ho), because a CTA
+ * recomputes E' on a one-cell halo (row b-1, column a-1, plane c-1 of its tile) from old values
+ * that the owning CTA may already have replaced.  Same expressions and order as yee_body<+1> and
+ * yee_body<-1>, so the results are bit-identical to the two-pass path.
+ *
+ * CTA = 32 x 9 threads: warp wy=0 is the halo row b0-1 (computes E', stores nothing), warps 1..8
+ * own rows b0..b0+7; a warp is a 128-cell row segment (float4 per lane).  The CTA marches DOWN in
+ * z: at plane c it forms E'(c) from H(c), H(c+1) [carried], then H'(c+1) from the carried E'(c+1)
+ * and the fresh E'(c).  E'(row b-1) travels through shared memory, E'(a-1) through a shuffle; lane 0
+ * recomputes the single cell a0-1 with scalar loads.
+ */
+struct FusedParams {
+	const float *Ei[3], *Hi[3];
+	float *Eo[3], *Ho[3];
+	const float *dtdE[3], *dtdH[3];   /* x tables shifted by XO                             */
+	int ny, pitch; size_t plane;
+	int a_first, a_last, nseg;        /* a_first = 1 mod 4, (a_last - a_first + 1) % 4 == 0  */
+	int b_first, b_last, c_first, c_last, cchunk;
+};
+
+/* cp.async staging: every global load of the kernel is issued two planes ahead into shared memory
+ * (no registers are held while the data is in flight), three stages deep */
+static __device__ __forceinline__ void cp_async16(void *smem, const void *g)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(g) : "memory");
+}
+static __device__ __forceinline__ void cp_async4(void *smem, const void *g)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(g) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+#define FUSED_STAGES 3
+struct FusedStage {
+	float4 e[3][9][32];            /* E x,y,z: rows b0-1 .. b0+7                          */
+	float4 hy[9][32];
+	float4 hx[10][32], hz[10][32]; /* rows b0-1 .. b0+8 (row b+1 feeds the y differences)  */
+	float  edge[9][8];             /* per warp: lane 0's cell a0-1 {Ey,Ez,Hz,Hy,Hx,Hx(b+1)}, lane 31's cell a0+128 {Hy,Hz} */
+};
+struct FusedSmem {
+	FusedStage st[FUSED_STAGES];
+	float4 sx[2][9][32], sz[2][9][32];   /* E'x, E'z rows of a plane, for the row above     */
+};
+
+__global__ void __launch_bounds__(288, 2)
+yee_fused(const __grid_constant__ FusedParams p)
+{
+	extern __shared__ __align__(16) unsigned char fused_smem_raw[];
+	FusedSmem &sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
+	const int lane = threadIdx.x, wy = threadIdx.y;
+	const int a0 = p.a_first + 4*((int)blockIdx.x*32 + lane);
+	const int b  = p.b_first - 1 + (int)blockIdx.y*8 + wy;
+	const bool rowok = b <= p.b_last;
+	const bool act = rowok && a0 <= p.a_last;              /* forms E' for its quad                  */
+	const bool ldg = rowok && a0 <= p.a_last + 1;          /* its H quad feeds the lane before       */
+	const bool own = act && wy > 0;                        /* stores E', forms and stores H'         */
+	const bool xh  = act && lane == 0;                     /* recomputes the cell a0-1               */
+	const bool xt  = act && lane == 31;                    /* needs H of the cell a0+128             */
+	const bool top = wy == 8 || b == p.b_last;             /* nobody stages row b+1 for this warp    */
+
+	const int cf = p.c_first + (int)blockIdx.z*p.cchunk;
+	const int cl = min(cf + p.cchunk - 1, p.c_last);
+	if (cf > cl) return;                                    /* whole CTA */
+
+	const size_t row = (size_t)b*p.pitch + ALISB_XO + a0;
+	const ptrdiff_t yp = p.pitch;
+	const float *E0 = p.Ei[0], *E1 = p.Ei[1], *E2 = p.Ei[2];
+	const float *H0 = p.Hi[0], *H1 = p.Hi[1], *H2 = p.Hi[2];
+
+	/* all loads of plane c, asynchronously, into stage s */
+	auto stage_plane = [&](int c, int s) {
+		FusedStage &S = sm.st[s];
+		const size_t o = (size_t)c*p.plane + row;
+		if (ldg) { cp_async16(&S.hx[wy][lane], H0 + o); cp_async16(&S.hy[wy][lane], H1 + o); cp_async16(&S.hz[wy][lane], H2 + o); }
+		if (act) {
+			cp_async16(&S.e[0][wy][lane], E0 + o); cp_async16(&S.e[1][wy][lane], E1 + o); cp_async16(&S.e[2][wy][lane], E2 + o);
+			if (top) { cp_async16(&S.hx[wy + 1][lane], H0 + o + yp); cp_async16(&S.hz[wy + 1][lane], H2 + o + yp); }
+		}
+		if (xh) {
+			cp_async4(&S.edge[wy][0], E1 + o - 1); cp_async4(&S.edge[wy][1], E2 + o - 1);
+			cp_async4(&S.edge[wy][2], H2 + o - 1); cp_async4(&S.edge[wy][3], H1 + o - 1);
+			cp_async4(&S.edge[wy][4], H0 + o - 1); cp_async4(&S.edge[wy][5], H0 + o - 1 + yp);
+		}
+		if (xt) { cp_async4(&S.edge[wy][6], H1 + o + 4); cp_async4(&S.edge[wy][7], H2 + o + 4); }
+	};
+
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4 dxe4 = act ? ld4(p.dtdE[0] + ALISB_XO + a0) : zero4;
+	const float4 dxh4 = act ? ld4(p.dtdH[0] + ALISB_XO + a0) : zero4;
+	const float dye = rowok ? __ldg(p.dtdE[1] + b) : 0.f, dyh = rowok ? __ldg(p.dtdH[1] + b) : 0.f;
+	const float dxeh = xh ? __ldg(p.dtdE[0] + ALISB_XO + a0 - 1) : 0.f;    /* E table at the cell a0-1 */
+	const float DxE[4] = {dxe4.x, dxe4.y, dxe4.z, dxe4.w}, DxH[4] = {dxh4.x, dxh4.y, dxh4.z, dxh4.w};
+
+	/* pipeline prologue: planes cl and cl-1 */
+	stage_plane(cl, 0); cp_async_commit();
+	if (cl - 1 >= cf - 1) stage_plane(cl - 1, 1);
+	cp_async_commit();
+
+	/* carried state of plane c+1 */
+	float4 hxp = zero4, hyp = zero4, hzp = zero4;           /* H(c+1)                                  */
+	float4 exp_ = zero4, eyp = zero4, ezp = zero4;          /* E'(c+1)                                 */
+	float eym1 = 0.f, ezm1 = 0.f;                           /* E'y, E'z of the cell a0-1 at plane c+1 (lane 0) */
+	float hxp1 = 0.f;                                       /* Hx of the cell a0-1 at plane c+1 (lane 0)       */
+	if (ldg) {
+		const size_t o = (size_t)(cl + 1)*p.plane + row;
+		hxp = ld4(H0 + o); hyp = ld4(H1 + o);
+		if (xh) hxp1 = H0[o - 1];
+	}
+
+	int c = cl;
+	for (int it = 0; c >= cf - 1; ++it, --c) {
+		const size_t o = (size_t)c*p.plane + row;
+		cp_async_wait<1>();                                 /* this thread's copies of plane c have landed */
+		__syncthreads();                                    /* ... and everybody else's; iteration it-1 is over everywhere */
+		{                                                   /* plane c-2 goes into the stage iteration it-1 used */
+			if (c - 2 >= cf - 1) stage_plane(c - 2, (it + 2) % FUSED_STAGES);
+			cp_async_commit();
+		}
+		const FusedStage &S = sm.st[it % FUSED_STAGES];
+		float4 ex = zero4, ey = zero4, ez = zero4, hx = zero4, hy = zero4, hz = zero4, hxn = zero4, hzn = zero4;
+		if (ldg) { hx = S.hx[wy][lane]; hy = S.hy[wy][lane]; hz = S.hz[wy][lane]; }
+		if (act) {
+			hxn = S.hx[wy + 1][lane]; hzn = S.hz[wy + 1][lane];
+			ex = S.e[0][wy][lane]; ey = S.e[1][wy][lane]; ez = S.e[2][wy][lane];
+		}
+		float hye = __shfl_down_sync(0xffffffffu, hy.x, 1), hze = __shfl_down_sync(0xffffffffu, hz.x, 1);
+		if (xt) { hye = S.edge[wy][6]; hze = S.edge[wy][7]; }
+		/* E'x, E'z of row b-1 at plane c+1, written by the warp below during iteration it-1 */
+		float4 exm = zero4, ezm = zero4;
+		if (wy > 0 && it > 0) { exm = sm.sx[(it - 1) & 1][wy - 1][lane]; ezm = sm.sz[(it - 1) & 1][wy - 1][lane]; }
+		const float dze = __ldg(p.dtdE[2] + c);
+
+		/* ---- E'(c), update.c:110-112 as in yee_body<+1> ---- */
+		float Ex[4] = {ex.x, ex.y, ex.z, ex.w}, Ey[4] = {ey.x, ey.y, ey.z, ey.w}, Ez[4] = {ez.x, ez.y, ez.z, ez.w};
+		{
+			const float Hx[4] = {hx.x, hx.y, hx.z, hx.w}, Hy[4] = {hy.x, hy.y, hy.z, hy.w}, Hz[4] = {hz.x, hz.y, hz.z, hz.w};
+			const float Hxn[4] = {hxn.x, hxn.y, hxn.z, hxn.w}, Hzn[4] = {hzn.x, hzn.y, hzn.z, hzn.w};
+			const float Hxp[4] = {hxp.x, hxp.y, hxp.z, hxp.w}, Hyp[4] = {hyp.x, hyp.y, hyp.z, hyp.w};
+			const float hy5[5] = {hy.x, hy.y, hy.z, hy.w, hye}, hz5[5] = {hz.x, hz.y, hz.z, hz.w, hze};
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				const float ux = dze*(Hy[e] - Hyp[e]) + dye*(Hzn[e] - Hz[e]);
+				const float uy = DxE[e]*(hz5[e] - hz5[e+1]) + dze*(Hxp[e] - Hx[e]);
+				const float uz = dye*(Hx[e] - Hxn[e]) + DxE[e]*(hy5[e+1] - hy5[e]);
+				Ex[e] += ux; Ey[e] += uy; Ez[e] += uz;
+			}
+		}
+		/* the cell a0-1 (lane 0): E'y and E'z only */
+		float eyh = 0.f, ezh = 0.f, hxh = 0.f;
+		if (xh) {
+			const float eyo = S.edge[wy][0], ezo = S.edge[wy][1];
+			const float hzh = S.edge[wy][2], hyh = S.edge[wy][3], hxnh = S.edge[wy][5];
+			hxh = S.edge[wy][4];
+			eyh = eyo + (dxeh*(hzh - hz.x) + dze*(hxp1 - hxh));
+			ezh = ezo + (dye*(hxh - hxnh) + dxeh*(hy.x - hyh));
+		}
+		const float4 nex = make_float4(Ex[0], Ex[1], Ex[2], Ex[3]), ney = make_float4(Ey[0], Ey[1], Ey[2], Ey[3]), nez = make_float4(Ez[0], Ez[1], Ez[2], Ez[3]);
+		if (own && c >= cf) { st4(p.Eo[0] + o, nex); st4(p.Eo[1] + o, ney); st4(p.Eo[2] + o, nez); }
+		sm.sx[it & 1][wy][lane] = nex; sm.sz[it & 1][wy][lane] = nez;     /* read by the row above in iteration it+1 */
+
+		/* ---- H'(c+1), update.c:115-117 as in yee_body<-1> ---- */
+		if (it > 0) {
+			float eya = __shfl_up_sync(0xffffffffu, eyp.w, 1), eza = __shfl_up_sync(0xffffffffu, ezp.w, 1);
+			if (lane == 0) { eya = eym1; eza = ezm1; }
+			if (own) {
+				const size_t op = o + p.plane;
+				const float dzh = __ldg(p.dtdH[2] + c + 1);
+				float Hx[4] = {hxp.x, hxp.y, hxp.z, hxp.w}, Hy[4] = {hyp.x, hyp.y, hyp.z, hyp.w}, Hz[4] = {hzp.x, hzp.y, hzp.z, hzp.w};
+				const float Gx[4] = {exp_.x, exp_.y, exp_.z, exp_.w}, Gy[4] = {eyp.x, eyp.y, eyp.z, eyp.w}, Gz[4] = {ezp.x, ezp.y, ezp.z, ezp.w};
+				const float Gxn[4] = {exm.x, exm.y, exm.z, exm.w}, Gzn[4] = {ezm.x, ezm.y, ezm.z, ezm.w};
+				const float gy5[5] = {eya, eyp.x, eyp.y, eyp.z, eyp.w}, gz5[5] = {eza, ezp.x, ezp.y, ezp.z, ezp.w};
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const float ux = dzh*(Gy[e] - Ey[e]) + dyh*(Gzn[e] - Gz[e]);
+					const float uy = DxH[e]*(gz5[e+1] - gz5[e]) + dzh*(Ex[e] - Gx[e]);
+					const float uz = dyh*(Gx[e] - Gxn[e]) + DxH[e]*(gy5[e] - gy5[e+1]);
+					Hx[e] += ux; Hy[e] += uy; Hz[e] += uz;
+				}
+				st4(p.Ho[0] + op, make_float4(Hx[0], Hx[1], Hx[2], Hx[3]));
+				st4(p.Ho[1] + op, make_float4(Hy[0], Hy[1], Hy[2], Hy[3]));
+				st4(p.Ho[2] + op, make_float4(Hz[0], Hz[1], Hz[2], Hz[3]));
+			}
+		}
+		/* plane c becomes plane c+1 */
+		hxp = hx; hyp = hy; hzp = hz;
+		exp_ = nex; eyp = ney; ezp = nez;
+		eym1 = eyh; ezm1 = ezh; hxp1 = hxh;
 	}
 }
 

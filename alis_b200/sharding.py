@@ -38,20 +38,29 @@ def _as_tensor(ptr, nbytes, cuda):
 class SlabRunner:
     """Steps one z-slab engine and exchanges halos with its neighbours."""
 
-    def __init__(self, engine: capi.Engine, rank, world, cuda, complex_field=0, overlap=True):
+    def __init__(self, engine: capi.Engine, rank, world, cuda, complex_field=0, overlap=True, fuse=False):
         self.e, self.rank, self.world, self.cuda = engine, rank, world, cuda
         self.overlap, self.pending_H = overlap, None
+        self.fuse = fuse
         self.ncf = complex_field + 1
-        self.send, self.recv = {}, {}
-        for s in range(2):
-            for m in range(self.ncf):
-                for comp in range(2):
-                    sp, rp, nb = engine.halo_info(s, m, comp)
-                    self.send[(s, m, comp)] = _as_tensor(sp, nb, cuda)
-                    self.recv[(s, m, comp)] = _as_tensor(rp, nb, cuda)
+        self._tensors = {}
         if cuda:
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        if fuse:
+            engine.set_fusion(True)
         self.exchanged_bytes = 0
+
+    def _planes(self, set_, m, comp):
+        """(send, recv) tensors over the halo planes the engine currently exposes for this field set;
+        with fused stepping the fields are double buffered, so the pointers alternate between passes"""
+        sp, rp, nb = self.e.halo_info(set_, m, comp)
+        out = []
+        for ptr in (sp, rp):
+            t = self._tensors.get(ptr)
+            if t is None:
+                t = self._tensors[ptr] = _as_tensor(ptr, nb, self.cuda)
+            out.append(t)
+        return out
 
     def _post(self, set_):
         """post the send of my plane and the receive of the neighbour's plane for field set `set_`;
@@ -64,11 +73,12 @@ class SlabRunner:
         ops = []
         for m in range(self.ncf):
             for comp in range(2):
+                send, recv = self._planes(set_, m, comp)
                 if 0 <= dst < self.world:
-                    ops.append(dist.P2POp(dist.isend, self.send[(set_, m, comp)], dst))
-                    self.exchanged_bytes += self.send[(set_, m, comp)].numel() * 4
+                    ops.append(dist.P2POp(dist.isend, send, dst))
+                    self.exchanged_bytes += send.numel() * 4
                 if 0 <= src < self.world:
-                    ops.append(dist.P2POp(dist.irecv, self.recv[(set_, m, comp)], src))
+                    ops.append(dist.P2POp(dist.irecv, recv, src))
         works = dist.batch_isend_irecv(ops) if ops else []
         return works, (0 <= src < self.world)
 
@@ -92,12 +102,16 @@ class SlabRunner:
             return
         if not self.overlap:
             self.e.step_E()
+            if self.fuse:
+                self.e.flush(True)                       # the send plane must exist before it travels
             self.exchange(capi.SET_E)
             self.e.step_H()
             self.exchange(capi.SET_H)
             return
         up, down = self.rank + 1 < self.world, self.rank > 0
         # E pass: its top plane needs the H halo posted in the previous H pass
+        if self.fuse:
+            self.e.begin_pass(capi.SET_E)                # buffers swap now: halo_info is about the planes this pass writes
         if self.pending_H is not None:
             self._finish(capi.SET_H, self.pending_H)
             self.pending_H = None
@@ -108,6 +122,9 @@ class SlabRunner:
         else:
             pending_E = self._post(capi.SET_E)           # only receives from below
             self.e.step_E()
+        if self.fuse:
+            self.e.flush(True)                           # the deferred bulk of the E pass, fused with H where possible
+            self.e.begin_pass(capi.SET_H)
         # H pass: its bottom plane needs the E halo that is in flight
         self._finish(capi.SET_E, pending_E)
         if down:

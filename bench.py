@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NX, NY, NZ_PER_GPU, NUM = 2048, 2048, 256, 12
+FUSE_DEFAULT = "1"      # fused E+H stepping (alisb_set_fusion); --fuse 0 times the two-pass path
 METRIC, UNIT = "Mcells/s", "Mcells/s"
 
 
@@ -49,6 +50,8 @@ def parse():
     ap.add_argument("--nz-per-gpu", type=int, default=NZ_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fuse", type=int, default=int(os.environ.get("ALISB_FUSE", FUSE_DEFAULT)),
+                    help="1: fused E+H stepping where a step is only the two curls (48 B per cell-step instead of 72)")
     return ap.parse_args()
 
 
@@ -154,8 +157,9 @@ def ours(args):
     lib = capi.load_engine()
     nz = args.nz_per_gpu * world
     w = synthetic.BoxWorld(args.nx, args.ny, nz, num=NUM)
+    os.environ["ALISB_FUSE"] = str(args.fuse)        # read by the engine at creation (here and in the C driver of the e2e leg)
     eng = w.make_engine(lib, device=local, rank=rank, world=world)
-    runner = sharding.SlabRunner(eng, rank, world, cuda=True, overlap=not os.environ.get("ALISB_NO_OVERLAP"))      # engine now runs on torch's current stream
+    runner = sharding.SlabRunner(eng, rank, world, cuda=True, overlap=not os.environ.get("ALISB_NO_OVERLAP"), fuse=bool(args.fuse))      # engine now runs on torch's current stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -182,6 +186,7 @@ def ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
+    fused_launches = eng.fused_launch_count()
     kinfo = lib_kernel_stats(eng)
     eng.set_profiling(False)
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -207,7 +212,9 @@ def ours(args):
         if kinfo:
             ach = kinfo["bytes_per_launch"] / (kinfo["avg_ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": load_traffic(),
-                    "kernel": "yee_volume (interior, no-PML instantiation)", "avg_launch_ms": kinfo["avg_ms"], "launches_timed": kinfo["n"],
+                    "kernel": ("yee_fused (interior, E and H half steps in one pass; algorithmic bytes are the two-pass 72 B per cell-step of SURVEY 8d, "
+                               "the kernel itself moves 48 B per cell-step, so frac may exceed 1)") if fused_launches else "yee_volume (interior, no-PML instantiation)",
+                    "avg_launch_ms": kinfo["avg_ms"], "launches_timed": kinfo["n"],
                     "bytes_per_launch": kinfo["bytes_per_launch"], "peak_source": peak_src,
                     "whole_step": {"algorithmic_bytes": w.algorithmic_bytes_per_step() / world, "achieved_GBps": w.algorithmic_bytes_per_step() / world / (ms / args.steps * 1e-3) / 1e9}}
         cpu = None
@@ -220,7 +227,7 @@ def ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args.nx, args.ny, nz, world), "l2": "inputs (6 field arrays, >= 26 GB per GPU) are far larger than the 126 MB L2",
                        "per_gpu_mcells_per_s": value / world},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "fused_launches": fused_launches, "clocks": clocks,
         }
         emit(line)
     if world > 1:

@@ -175,6 +175,22 @@ int  alisb_run(alisb_engine *e, int steps);      /* steps x (E then H), no host 
  * neighbour and its H pass if it has a lower one; alis_b200/sharding.py).                      */
 enum { ALISB_PART_ALL = 0, ALISB_PART_SEND_PLANE = 1, ALISB_PART_REST = 2 };
 int  alisb_step_part(alisb_engine *e, int set, int part);
+/* Fused E+H stepping (temporal blocking of update.c:275-341).  Where a step is nothing but the two
+ * curls -- outside CPML slabs, material arrays, ADE boxes, sources, TFSF strips -- both half steps of
+ * a cell are formed in one pass over memory (48 B per cell-step instead of 72), bit-identical to the
+ * two-pass path.  With fusion on (alisb_set_fusion, or ALISB_FUSE=1 in the environment) an E pass is
+ * prepared when alisb_step_E / alisb_step_part(E) is called but issued only when the H pass, or any
+ * other call that looks at the device state, arrives; fields are double buffered (2x field memory).
+ *   alisb_flush(e, 1)       issue the deferred E pass now as the fused variant; the caller promises
+ *                           that the next thing to touch this engine's fields is the H pass
+ *   alisb_flush(e, 0)       issue it as the plain two-pass variant
+ *   alisb_begin_pass(e,set) swap the buffers for the coming pass now, so that alisb_halo_info returns
+ *                           the planes that pass will write (alis_b200/sharding.py posts its receives
+ *                           before the pass is issued)                                            */
+int  alisb_set_fusion(alisb_engine *e, int on);
+int  alisb_flush(alisb_engine *e, int h_pass_follows);
+int  alisb_begin_pass(alisb_engine *e, int set);
+uint64_t alisb_fused_launch_count(alisb_engine *e);   /* launches of the fused kernel so far (tests, bench) */
 int  alisb_synchronize(alisb_engine *e);
 int  alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH);
 int  alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH);

@@ -473,6 +473,11 @@ int alisb_step_H(alisb_engine *e) { return alisb_step_part(e, ALISB_SET_H, ALISB
 
 int alisb_run(alisb_engine *e, int steps) { for (int i=0; i<steps; i++) { alisb_step_E(e); alisb_step_H(e); } return ALISB_OK; }
 int alisb_synchronize(alisb_engine *e) { (void)e; return ALISB_OK; }
+/* the oracle always steps in two plain passes; fusion is an implementation choice of the CUDA engine */
+int alisb_set_fusion(alisb_engine *e, int on) { (void)e; (void)on; return ALISB_OK; }
+int alisb_flush(alisb_engine *e, int h) { (void)e; (void)h; return ALISB_OK; }
+int alisb_begin_pass(alisb_engine *e, int set) { (void)e; (void)set; return ALISB_OK; }
+uint64_t alisb_fused_launch_count(alisb_engine *e) { (void)e; return 0; }
 int alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH) { if (n) *n=e->step; if (t) *t=e->t; if (tE) *tE=e->tE; if (tH) *tH=e->tH; return ALISB_OK; }
 int alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH) { e->step=n; e->t=t; e->tE=tE; e->tH=tH; return ALISB_OK; }
 

@@ -20,7 +20,7 @@ def main():
     lib = capi.load_engine()
     w = synthetic.BoxWorld(*shape)
     e = w.make_engine(lib, device=local, rank=rank, world=world)
-    r = sharding.SlabRunner(e, rank, world, cuda=True)
+    r = sharding.SlabRunner(e, rank, world, cuda=True, fuse=bool(os.environ.get("ALISB_TEST_FUSE")))
     r.run(steps)
     torch.cuda.synchronize()
     mine = e.read_all_fields()[..., 1:-1]

@@ -135,7 +135,7 @@ def test_two_slabs_on_one_gpu_equal_single(engine_lib):
     _slab_check(engine_lib, (70, 50, 62), 45)
 
 
-def _slab_check(engine_lib, shape, steps):
+def _slab_check(engine_lib, shape, steps, fuse=False):
     rt = _cudart()
     rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
     w = synthetic.BoxWorld(*shape)
@@ -162,6 +162,8 @@ def _slab_check(engine_lib, shape, steps):
     for _ in range(steps):
         for e in parts:
             e.step_E()
+            if fuse:
+                e.flush(True)          # issue the deferred E pass as the fused variant (the H pass follows)
         xchg(capi.SET_E, lo, hi)
         for e in parts:
             e.step_H()
@@ -243,3 +245,63 @@ def test_chi2_coupling_seeded_bit_exact(oracle_lib, engine_lib, alias):
             e.close()
     assert np.array_equal(out[0], out[1])
     assert np.abs(out[0]).max() > 0
+
+
+# ---- fused E+H stepping (temporal blocking): must be bit-identical to the two-pass oracle ----------
+@pytest.fixture
+def fusion_env(monkeypatch):
+    """engines created under this fixture fuse whatever they can, however small the grid"""
+    monkeypatch.setenv("ALISB_FUSE", "1")
+    monkeypatch.setenv("ALISB_FUSE_MIN", "1")
+    monkeypatch.setenv("ALISB_SMALL", "1")
+    monkeypatch.setenv("ALISB_FUSE_FRAC", "0.01")
+
+
+@pytest.mark.parametrize("shape,num,steps", [
+    ((160, 72, 64), 12, 30),     # the fused box is three 32-cell groups wide; the dipole's planes are excluded
+    ((300, 61, 47), 6, 20),      # ragged rows (61-13 not a multiple of 8), several x segments
+    ((96, 40, 90), 8, 25),       # long z: several z-chunks per range
+])
+def test_fused_stepping_bit_exact(oracle_lib, engine_lib, fusion_env, monkeypatch, shape, num, steps):
+    monkeypatch.setenv("ALISB_FCHUNK", "7")
+    w, g, o = both(oracle_lib, engine_lib, shape, num=num)
+    helpers.seed_fields([g, o], tuple(n + 2 for n in shape))
+    l0 = g.launch_count()
+    for e in (g, o):
+        e.run(steps)
+    assert g.time() == o.time()
+    assert g.fused_launch_count() >= steps, "the fused kernel did not run"
+    helpers.assert_fields_identical(g, o, f"fused box {shape}")
+    compare_psi(g, o)
+    # interleaved access: reading between the passes forces the plain variant, results must not change
+    for e in (g, o):
+        for _ in range(3):
+            e.step_E()
+            e.read_box(capi.ARR_FIELD, [0, 2, 0], [1, 4, 1, 4, 1, 4])
+            e.step_H()
+        e.step_E()
+        e.step_E()
+        e.step_H()
+        e.run(2)
+    helpers.assert_fields_identical(g, o, f"fused box {shape} after interleaved access")
+
+
+def test_fused_write_between_passes(oracle_lib, engine_lib, fusion_env):
+    """a field write after the (deferred) E pass must reach the H pass of the same step"""
+    shape = (160, 48, 40)
+    w, g, o = both(oracle_lib, engine_lib, shape, num=6)
+    helpers.seed_fields([g, o], tuple(n + 2 for n in shape))
+    rng = np.random.RandomState(3)
+    patch = rng.rand(6, 5, 4).astype(np.float32)
+    for e in (g, o):
+        e.run(3)
+        e.step_E()
+        e.write_box(capi.ARR_FIELD, [0, 1, 0], [60, 65, 20, 24, 18, 21], patch)
+        e.step_H()
+        e.run(4)
+    helpers.assert_fields_identical(g, o, "write between passes")
+
+
+def test_fused_two_slabs_equal_single(engine_lib, fusion_env):
+    _slab_check(engine_lib, (160, 50, 62), 30, fuse=True)
+
