@@ -94,6 +94,7 @@ struct alisb_engine {
 	uint64_t launches, fused_launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_frows;                    /* rows per CTA of the fused kernel (8 or 16)          */
 	int tune_fchunk;                   /* planes per z-chunk of the fused kernel              */
 	int tune_merge;                    /* PML shell boxes gathered into two merged launches  */
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
@@ -234,8 +235,9 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		e->tune_merge = (s = getenv("ALISB_MERGE")) ? atoi(s) : 1;
 		e->fuse_req = (s = getenv("ALISB_FUSE")) ? atoi(s) : 1;      /* on by default; only grids of >= tune_fuse_min cells with a large clean box actually fuse */
 		e->tune_fchunk = (s = getenv("ALISB_FCHUNK")) ? atoi(s) : 32;   /* measured: 32 planes 11.70 ms/step, 16: 11.79, 8: 13.9 (profiles/fuse_r01.sh) */
+		e->tune_frows = (s = getenv("ALISB_FROWS")) ? atoi(s) : 16;   /* measured: 16 rows 11.38 ms/step, 8 rows 11.72 */
 		e->tune_fuse_frac = (s = getenv("ALISB_FUSE_FRAC")) ? atof(s) : 0.5;
-		e->tune_fuse_min = (s = getenv("ALISB_FUSE_MIN")) ? atol(s) : (1L << 24);
+		e->tune_fuse_min = (s = getenv("ALISB_FUSE_MIN")) ? atol(s) : 40000000L;   /* measured: equal at 320^3, +4 % at 384^3, +12 % at 512^3 (profiles/midfuse_r01.sh) */
 		e->tune_small = (s = getenv("ALISB_SMALL")) ? atol(s) : 3000000L;   /* crossover measured at ~150^3 (profiles/small_grid_probe.py) */
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -734,17 +736,23 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			fp.ny = e->ny; fp.pitch = e->pitch; fp.plane = e->plane;
 			fp.a_first = sb.a0; fp.a_last = sb.a1; fp.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
 			fp.b_first = sb.b0; fp.b_last = sb.b1; fp.c_first = sb.c0; fp.c_last = sb.c1;
-			const int nzs = sb.c1 - sb.c0 + 1, gyf = div_up(sb.b1 - sb.b0 + 1, 8);
+			const int frows = e->tune_frows == 16 ? 16 : 8;
+			const int nzs = sb.c1 - sb.c0 + 1, gyf = div_up(sb.b1 - sb.b0 + 1, frows);
 			fp.cchunk = std::min(nzs, std::max(1, e->tune_fchunk));
-			dim3 grid(fp.nseg, gyf, div_up(nzs, fp.cchunk)), block(32, 9, 1);
+			dim3 grid(fp.nseg, gyf, div_up(nzs, fp.cchunk)), block(32, frows + 1, 1);
 			cudaStream_t st = side_stream(true);
 			nlaunched++;
 			/* profiling counts cell-passes: a fused launch does two passes per cell */
 			cudaEvent_t e1 = prof_begin(st, sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
 			if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] fused E+H cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, grid.x, grid.y, grid.z, fp.cchunk);
 			static bool smem_set = false;
-			if (!smem_set) { CU(cudaFuncSetAttribute(yee_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))); smem_set = true; }
-			yee_fused<<<grid, block, sizeof(FusedSmem), st>>>(fp);
+			if (!smem_set) {
+				CU(cudaFuncSetAttribute(yee_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
+				CU(cudaFuncSetAttribute(yee_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
+				smem_set = true;
+			}
+			if (frows == 16) yee_fused<16><<<grid, block, sizeof(FusedSmem<16>), st>>>(fp);
+			else             yee_fused<8><<<grid, block, sizeof(FusedSmem<8>), st>>>(fp);
 			e->launches++; e->fused_launches++;
 			if (e->profiling) CU(cudaEventRecord(e1, st));
 			continue;

@@ -273,8 +273,8 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
  * that the owning CTA may already have replaced.  Same expressions and order as yee_body<+1> and
  * yee_body<-1>, so the results are bit-identical to the two-pass path.
  *
- * CTA = 32 x 9 threads: warp wy=0 is the halo row b0-1 (computes E', stores nothing), warps 1..8
- * own rows b0..b0+7; a warp is a 128-cell row segment (float4 per lane).  The CTA marches DOWN in
+ * CTA = 32 x (ROWS+1) threads: warp wy=0 is the halo row b0-1 (computes E', stores nothing), warps
+ * 1..ROWS own rows b0..b0+ROWS-1; a warp is a 128-cell row segment (float4 per lane).  The CTA marches DOWN in
  * z: at plane c it forms E'(c) from H(c), H(c+1) [carried], then H'(c+1) from the carried E'(c+1)
  * and the fresh E'(c).  E'(row b-1) travels through shared memory, E'(a-1) through a shuffle; lane 0
  * recomputes the single cell a0-1 with scalar loads.
@@ -304,32 +304,33 @@ static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.asyn
 template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 #define FUSED_STAGES 3
-struct FusedStage {
-	float4 e[3][9][32];            /* E x,y,z: rows b0-1 .. b0+7                          */
-	float4 hy[9][32];
-	float4 hx[10][32], hz[10][32]; /* rows b0-1 .. b0+8 (row b+1 feeds the y differences)  */
-	float  edge[9][8];             /* per warp: lane 0's cell a0-1 {Ey,Ez,Hz,Hy,Hx,Hx(b+1)}, lane 31's cell a0+128 {Hy,Hz} */
+template <int ROWS> struct FusedStage {      /* ROWS owned rows + the halo row below them */
+	float4 e[3][ROWS+1][32];       /* E x,y,z: rows b0-1 .. b0+ROWS-1                     */
+	float4 hy[ROWS+1][32];
+	float4 hx[ROWS+2][32], hz[ROWS+2][32];   /* rows b0-1 .. b0+ROWS (row b+1 feeds the y differences) */
+	float  edge[ROWS+1][8];        /* per warp: lane 0's cell a0-1 {Ey,Ez,Hz,Hy,Hx,Hx(b+1)}, lane 31's cell a0+128 {Hy,Hz} */
 };
-struct FusedSmem {
-	FusedStage st[FUSED_STAGES];
-	float4 sx[2][9][32], sz[2][9][32];   /* E'x, E'z rows of a plane, for the row above     */
+template <int ROWS> struct FusedSmem {
+	FusedStage<ROWS> st[FUSED_STAGES];
+	float4 sx[2][ROWS+1][32], sz[2][ROWS+1][32];   /* E'x, E'z rows of a plane, for the row above */
 };
 
-__global__ void __launch_bounds__(288, 2)
+template <int ROWS>
+__global__ void __launch_bounds__(32*(ROWS+1), ROWS == 8 ? 2 : 1)
 yee_fused(const __grid_constant__ FusedParams p)
 {
 	extern __shared__ __align__(16) unsigned char fused_smem_raw[];
-	FusedSmem &sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
+	FusedSmem<ROWS> &sm = *reinterpret_cast<FusedSmem<ROWS>*>(fused_smem_raw);
 	const int lane = threadIdx.x, wy = threadIdx.y;
 	const int a0 = p.a_first + 4*((int)blockIdx.x*32 + lane);
-	const int b  = p.b_first - 1 + (int)blockIdx.y*8 + wy;
+	const int b  = p.b_first - 1 + (int)blockIdx.y*ROWS + wy;
 	const bool rowok = b <= p.b_last;
 	const bool act = rowok && a0 <= p.a_last;              /* forms E' for its quad                  */
 	const bool ldg = rowok && a0 <= p.a_last + 1;          /* its H quad feeds the lane before       */
 	const bool own = act && wy > 0;                        /* stores E', forms and stores H'         */
 	const bool xh  = act && lane == 0;                     /* recomputes the cell a0-1               */
 	const bool xt  = act && lane == 31;                    /* needs H of the cell a0+128             */
-	const bool top = wy == 8 || b == p.b_last;             /* nobody stages row b+1 for this warp    */
+	const bool top = wy == ROWS || b == p.b_last;             /* nobody stages row b+1 for this warp    */
 
 	const int cf = p.c_first + (int)blockIdx.z*p.cchunk;
 	const int cl = min(cf + p.cchunk - 1, p.c_last);
@@ -342,7 +343,7 @@ yee_fused(const __grid_constant__ FusedParams p)
 
 	/* all loads of plane c, asynchronously, into stage s */
 	auto stage_plane = [&](int c, int s) {
-		FusedStage &S = sm.st[s];
+		FusedStage<ROWS> &S = sm.st[s];
 		const size_t o = (size_t)c*p.plane + row;
 		if (ldg) { cp_async16(&S.hx[wy][lane], H0 + o); cp_async16(&S.hy[wy][lane], H1 + o); cp_async16(&S.hz[wy][lane], H2 + o); }
 		if (act) {
@@ -389,7 +390,7 @@ yee_fused(const __grid_constant__ FusedParams p)
 			if (c - 2 >= cf - 1) stage_plane(c - 2, (it + 2) % FUSED_STAGES);
 			cp_async_commit();
 		}
-		const FusedStage &S = sm.st[it % FUSED_STAGES];
+		const FusedStage<ROWS> &S = sm.st[it % FUSED_STAGES];
 		float4 ex = zero4, ey = zero4, ez = zero4, hx = zero4, hy = zero4, hz = zero4, hxn = zero4, hzn = zero4;
 		if (ldg) { hx = S.hx[wy][lane]; hy = S.hy[wy][lane]; hz = S.hz[wy][lane]; }
 		if (act) {

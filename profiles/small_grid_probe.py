@@ -3,7 +3,8 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alis_b200 import capi, synthetic
 lib = capi.load_engine()
-for shape in ((76, 76, 76), (128, 128, 128), (192, 192, 192), (256, 256, 256), (384, 384, 384), (512, 512, 512)):
+sizes = [int(a) for a in sys.argv[1:]] or [76, 128, 192, 256, 384, 512]
+for shape in [(n, n, n) for n in sizes]:
     w = synthetic.BoxWorld(*shape)
     e = w.make_engine(lib)
     e.run(100); e.synchronize()
@@ -12,4 +13,4 @@ for shape in ((76, 76, 76), (128, 128, 128), (192, 192, 192), (256, 256, 256), (
     t_enq = time.perf_counter() - t0
     e.synchronize()
     dt = time.perf_counter() - t0
-    print(shape, "us/step %.1f (host enqueue %.1f)" % (dt/500*1e6, t_enq/500*1e6), "launches/step %.1f" % ((e.launch_count()-l0)/500), "Mcells/s %.0f" % (w.cells()*500/dt*1e-6))
+    print(shape, "us/step %.1f (host enqueue %.1f)" % (dt/500*1e6, t_enq/500*1e6), "launches/step %.1f" % ((e.launch_count()-l0)/500), "Mcells/s %.0f" % (w.cells()*500/dt*1e-6), "fused launches", e.fused_launch_count())
