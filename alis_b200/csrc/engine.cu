@@ -234,7 +234,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		e->tune_conc = (s = getenv("ALISB_CONC")) ? atoi(s) : 1;
 		e->tune_merge = (s = getenv("ALISB_MERGE")) ? atoi(s) : 1;
 		e->fuse_req = (s = getenv("ALISB_FUSE")) ? atoi(s) : 1;      /* on by default; only grids of >= tune_fuse_min cells with a large clean box actually fuse */
-		e->tune_fchunk = (s = getenv("ALISB_FCHUNK")) ? atoi(s) : 32;   /* measured: 32 planes 11.70 ms/step, 16: 11.79, 8: 13.9 (profiles/fuse_r01.sh) */
+		e->tune_fchunk = (s = getenv("ALISB_FCHUNK")) ? atoi(s) : 64;   /* measured (16-row tiles): 57..113 planes 11.27 ms/step, 32: 11.37 (profiles/fuse_r01.sh) */
 		e->tune_frows = (s = getenv("ALISB_FROWS")) ? atoi(s) : 16;   /* measured: 16 rows 11.38 ms/step, 8 rows 11.72 */
 		e->tune_fuse_frac = (s = getenv("ALISB_FUSE_FRAC")) ? atof(s) : 0.5;
 		e->tune_fuse_min = (s = getenv("ALISB_FUSE_MIN")) ? atol(s) : 40000000L;   /* measured: equal at 320^3, +4 % at 384^3, +12 % at 512^3 (profiles/midfuse_r01.sh) */

@@ -211,7 +211,7 @@ def ours(args):
         roof = None
         if kinfo:
             ach = kinfo["bytes_per_launch"] / (kinfo["avg_ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": load_traffic(),
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": load_traffic("yee_fused" if fused_launches else "yee_volume"),
                     "kernel": ("yee_fused (interior, E and H half steps in one pass; algorithmic bytes are the two-pass 72 B per cell-step of SURVEY 8d, "
                                "the kernel itself moves 48 B per cell-step, so frac may exceed 1)") if fused_launches else "yee_volume (interior, no-PML instantiation)",
                     "avg_launch_ms": kinfo["avg_ms"], "launches_timed": kinfo["n"],
@@ -295,11 +295,12 @@ def load_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def load_traffic():
+def load_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
     p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p))[kernel].get("dram_bytes_per_launch")
         except Exception:
             return None
     return None

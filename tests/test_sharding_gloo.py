@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, steps, outdir, overlap):
+def _worker(rank, world, port, shape, steps, outdir, overlap, fuse=False):
     import torch.distributed as dist
     from alis_b200 import sharding
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -27,7 +27,7 @@ def _worker(rank, world, port, shape, steps, outdir, overlap):
     lib = capi.load_oracle()
     w = synthetic.BoxWorld(*shape)
     e = w.make_engine(lib, rank=rank, world=world)
-    r = sharding.SlabRunner(e, rank, world, cuda=False, overlap=overlap)
+    r = sharding.SlabRunner(e, rank, world, cuda=False, overlap=overlap, fuse=fuse)
     r.run(steps)
     c0, c1 = e.shard
     a = e.read_all_fields()                       # local (nz_local+2) planes
@@ -37,15 +37,18 @@ def _worker(rank, world, port, shape, steps, outdir, overlap):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,overlap", [(2, (40, 34, 44), True), (3, (36, 40, 61), True), (2, (40, 34, 44), False)])
-def test_sharded_equals_single(world, shape, overlap, tmp_path, oracle_lib):
+@pytest.mark.parametrize("world,shape,overlap,fuse", [(2, (40, 34, 44), True, False), (3, (36, 40, 61), True, False), (2, (40, 34, 44), False, False),
+                                                     (3, (36, 40, 61), True, True), (2, (40, 34, 44), False, True)])
+def test_sharded_equals_single(world, shape, overlap, fuse, tmp_path, oracle_lib):
+    """fuse=True drives the runner's fused-stepping control flow (begin_pass / deferred E / flush); the
+    oracle engine steps in two plain passes either way, so the result must not change"""
     steps = 40
     w = synthetic.BoxWorld(*shape)
     single = w.make_engine(oracle_lib)
     single.run(steps)
     ref = single.read_all_fields()
     assert np.abs(ref).max() > 0
-    mp.spawn(_worker, args=(world, _free_port(), shape, steps, str(tmp_path), overlap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, steps, str(tmp_path), overlap, fuse), nprocs=world, join=True)
     parts = [np.load(tmp_path / f"r{r}.npy") for r in range(world)]
     got = np.concatenate(parts, axis=-1)
     assert np.array_equal(got, ref[..., 1:-1]), "sharded interior planes differ from the single-domain run"
