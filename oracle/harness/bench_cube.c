@@ -7,6 +7,9 @@
  * prints one line:  cells=<n> steps=<k> seconds=<s> mcells_per_s=<v> threads=<t> probe=<Ez>
  * With probe_every_step = 1 the loop also reads get(W, Ez, ...) after every step, i.e. the way a
  * driver with a point monitor runs (one 4-byte device->host read per step in our library).
+ * With 2 it additionally evaluates sliceMax(W, EE, XY) on the z=0 plane every 4th step, the monitor
+ * cadence of examples/Dipole_PML.c:21-25 without the file output (in our library: a device->host
+ * read of the plane's E components, ~100 MB at 2048^2).
  * Linked against the unmodified reference it is the CPU baseline (`--impl reference` and
  * cpu_baseline.kind "reference" in bench.py).
  */
@@ -34,14 +37,16 @@ int main(int argc, char **argv)
 	world W = createWorld(Dom, Res, Sur, "");
 	if (W->iNUM != n[0] || W->jNUM != n[1] || W->kNUM != n[2]) { printf("grid mismatch %d %d %d\n", W->iNUM, W->jNUM, W->kNUM); return 1; }
 	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 1);
-	for (int s=0; s<warm; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); }
+	slice XY = createSliceXY(W, 0);
+	double smax = 0;
+	for (int s=0; s<warm; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); if (every == 2 && s % 4 == 3) smax += sliceMax(W, EE, XY); }
 	acc = get(W, Ez, 0, 0, 50);                       /* (also drains the device queue before the clock starts) */
 	double t0 = now();
-	for (int s=0; s<steps; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); }
+	for (int s=0; s<steps; s++) { updateE(W); updateH(W); if (every) acc += get(W, Ez, 0, 0, 50); if (every == 2 && s % 4 == 3) smax += sliceMax(W, EE, XY); }
 	acc += get(W, Ez, 0, 0, 50);                      /* device work is complete when this returns */
 	double dt = now() - t0;
 	double cells = (double)n[0]*n[1]*n[2];
-	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g\n", cells, steps, dt, cells*steps/dt*1e-6,
-		omp_get_max_threads(), acc);
+	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g slicemax=%.9g\n", cells, steps, dt, cells*steps/dt*1e-6,
+		omp_get_max_threads(), acc, smax);
 	return 0;
 }
