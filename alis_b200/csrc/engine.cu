@@ -504,7 +504,7 @@ static void fuse_eval(alisb_engine *e)
 	e->fuse_ok = false; e->fuse_z.clear();
 	auto done = [&]() { if (was != e->fuse_ok) { e->plan[0].clear(); e->plan[1].clear(); } };
 	const long cells = (long)e->nx*e->ny*e->nz;
-	if (!e->fuse_req || cells < e->tune_fuse_min || cells < e->tune_small || e->eps[0] || !e->obj.empty() || e->tune_bx != 1 || e->tune_by != 8) return done();
+	if (!e->fuse_req || cells < e->tune_fuse_min || cells < e->tune_small || e->tune_bx != 1 || e->tune_by != 8) return done();
 	const int n[3] = {e->nx, e->ny, e->nz};
 	int lo[3], hi[3];
 	for (int ax=0; ax<3; ax++) {
@@ -732,6 +732,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 				fp.Ei[c] = e->Fb[ALISB_SET_E][m][c]; fp.Eo[c] = e->F[ALISB_SET_E][m][c];
 				fp.Hi[c] = e->F[ALISB_SET_H][m][c];  fp.Ho[c] = e->Fb[ALISB_SET_H][m][c];
 				fp.dtdE[c] = e->dtd[ALISB_SET_E][c]; fp.dtdH[c] = e->dtd[ALISB_SET_H][c];
+				fp.C[c] = eps ? e->eps[c] : 0;
 			}
 			fp.ny = e->ny; fp.pitch = e->pitch; fp.plane = e->plane;
 			fp.a_first = sb.a0; fp.a_last = sb.a1; fp.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
@@ -747,12 +748,14 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] fused E+H cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, grid.x, grid.y, grid.z, fp.cchunk);
 			static bool smem_set = false;
 			if (!smem_set) {
-				CU(cudaFuncSetAttribute(yee_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
-				CU(cudaFuncSetAttribute(yee_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
+				CU(cudaFuncSetAttribute(yee_fused<8,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,false>)));
+				CU(cudaFuncSetAttribute(yee_fused<8,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,true>)));
+				CU(cudaFuncSetAttribute(yee_fused<16,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,false>)));
+				CU(cudaFuncSetAttribute(yee_fused<16,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,true>)));
 				smem_set = true;
 			}
-			if (frows == 16) yee_fused<16><<<grid, block, sizeof(FusedSmem<16>), st>>>(fp);
-			else             yee_fused<8><<<grid, block, sizeof(FusedSmem<8>), st>>>(fp);
+			if (frows == 16) { if (eps) yee_fused<16,true><<<grid, block, sizeof(FusedSmem<16,true>), st>>>(fp); else yee_fused<16,false><<<grid, block, sizeof(FusedSmem<16,false>), st>>>(fp); }
+			else             { if (eps) yee_fused<8,true><<<grid, block, sizeof(FusedSmem<8,true>), st>>>(fp);  else yee_fused<8,false><<<grid, block, sizeof(FusedSmem<8,false>), st>>>(fp); }
 			e->launches++; e->fused_launches++;
 			if (e->profiling) CU(cudaEventRecord(e1, st));
 			continue;

@@ -283,6 +283,7 @@ struct FusedParams {
 	const float *Ei[3], *Hi[3];
 	float *Eo[3], *Ho[3];
 	const float *dtdE[3], *dtdH[3];   /* x tables shifted by XO                             */
+	const float *C[3];                /* inverse permittivity (EPS variant), full-grid arrays */
 	int ny, pitch; size_t plane;
 	int a_first, a_last, nseg;        /* a_first = 1 mod 4, (a_last - a_first + 1) % 4 == 0  */
 	int b_first, b_last, c_first, c_last, cchunk;
@@ -303,24 +304,28 @@ static __device__ __forceinline__ void cp_async4(void *smem, const void *g)
 static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-#define FUSED_STAGES 3
-template <int ROWS> struct FusedStage {      /* ROWS owned rows + the halo row below them */
+/* vacuum: 3 stages (loads two planes ahead); with material arrays the ring also carries the three
+ * inverse-permittivity rows and is 2 stages deep (one plane ahead) so that it still fits */
+template <int ROWS, bool EPS> struct FusedStage {      /* ROWS owned rows + the halo row below them */
 	float4 e[3][ROWS+1][32];       /* E x,y,z: rows b0-1 .. b0+ROWS-1                     */
 	float4 hy[ROWS+1][32];
 	float4 hx[ROWS+2][32], hz[ROWS+2][32];   /* rows b0-1 .. b0+ROWS (row b+1 feeds the y differences) */
-	float  edge[ROWS+1][8];        /* per warp: lane 0's cell a0-1 {Ey,Ez,Hz,Hy,Hx,Hx(b+1)}, lane 31's cell a0+128 {Hy,Hz} */
+	float4 c[EPS ? 3 : 1][EPS ? ROWS+1 : 1][EPS ? 32 : 1];   /* inverse permittivity x,y,z of the same rows */
+	float  edge[ROWS+1][12];       /* per warp: lane 0's cell a0-1 {Ey,Ez,Hz,Hy,Hx,Hx(b+1)}, lane 31's cell a0+128 {Hy,Hz}, lane 0's {Cy,Cz} */
 };
-template <int ROWS> struct FusedSmem {
-	FusedStage<ROWS> st[FUSED_STAGES];
+template <int ROWS, bool EPS> struct FusedSmem {
+	static constexpr int NST = EPS ? 2 : 3;
+	FusedStage<ROWS,EPS> st[NST];
 	float4 sx[2][ROWS+1][32], sz[2][ROWS+1][32];   /* E'x, E'z rows of a plane, for the row above */
 };
 
-template <int ROWS>
+template <int ROWS, bool EPS>
 __global__ void __launch_bounds__(32*(ROWS+1), ROWS == 8 ? 2 : 1)
 yee_fused(const __grid_constant__ FusedParams p)
 {
 	extern __shared__ __align__(16) unsigned char fused_smem_raw[];
-	FusedSmem<ROWS> &sm = *reinterpret_cast<FusedSmem<ROWS>*>(fused_smem_raw);
+	FusedSmem<ROWS,EPS> &sm = *reinterpret_cast<FusedSmem<ROWS,EPS>*>(fused_smem_raw);
+	constexpr int NST = FusedSmem<ROWS,EPS>::NST, AHEAD = NST - 1;     /* planes in flight */
 	const int lane = threadIdx.x, wy = threadIdx.y;
 	const int a0 = p.a_first + 4*((int)blockIdx.x*32 + lane);
 	const int b  = p.b_first - 1 + (int)blockIdx.y*ROWS + wy;
@@ -343,12 +348,13 @@ yee_fused(const __grid_constant__ FusedParams p)
 
 	/* all loads of plane c, asynchronously, into stage s */
 	auto stage_plane = [&](int c, int s) {
-		FusedStage<ROWS> &S = sm.st[s];
+		FusedStage<ROWS,EPS> &S = sm.st[s];
 		const size_t o = (size_t)c*p.plane + row;
 		if (ldg) { cp_async16(&S.hx[wy][lane], H0 + o); cp_async16(&S.hy[wy][lane], H1 + o); cp_async16(&S.hz[wy][lane], H2 + o); }
 		if (act) {
 			cp_async16(&S.e[0][wy][lane], E0 + o); cp_async16(&S.e[1][wy][lane], E1 + o); cp_async16(&S.e[2][wy][lane], E2 + o);
 			if (top) { cp_async16(&S.hx[wy + 1][lane], H0 + o + yp); cp_async16(&S.hz[wy + 1][lane], H2 + o + yp); }
+			if (EPS) { cp_async16(&S.c[0][wy][lane], p.C[0] + o); cp_async16(&S.c[1][wy][lane], p.C[1] + o); cp_async16(&S.c[2][wy][lane], p.C[2] + o); }
 		}
 		if (xh) {
 			cp_async4(&S.edge[wy][0], E1 + o - 1); cp_async4(&S.edge[wy][1], E2 + o - 1);
@@ -356,6 +362,7 @@ yee_fused(const __grid_constant__ FusedParams p)
 			cp_async4(&S.edge[wy][4], H0 + o - 1); cp_async4(&S.edge[wy][5], H0 + o - 1 + yp);
 		}
 		if (xt) { cp_async4(&S.edge[wy][6], H1 + o + 4); cp_async4(&S.edge[wy][7], H2 + o + 4); }
+		if (EPS && xh) { cp_async4(&S.edge[wy][8], p.C[1] + o - 1); cp_async4(&S.edge[wy][9], p.C[2] + o - 1); }
 	};
 
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -365,10 +372,12 @@ yee_fused(const __grid_constant__ FusedParams p)
 	const float dxeh = xh ? __ldg(p.dtdE[0] + ALISB_XO + a0 - 1) : 0.f;    /* E table at the cell a0-1 */
 	const float DxE[4] = {dxe4.x, dxe4.y, dxe4.z, dxe4.w}, DxH[4] = {dxh4.x, dxh4.y, dxh4.z, dxh4.w};
 
-	/* pipeline prologue: planes cl and cl-1 */
-	stage_plane(cl, 0); cp_async_commit();
-	if (cl - 1 >= cf - 1) stage_plane(cl - 1, 1);
-	cp_async_commit();
+	/* pipeline prologue: the first AHEAD planes */
+	#pragma unroll
+	for (int q = 0; q < AHEAD; q++) {
+		if (cl - q >= cf - 1) stage_plane(cl - q, q);
+		cp_async_commit();
+	}
 
 	/* carried state of plane c+1 */
 	float4 hxp = zero4, hyp = zero4, hzp = zero4;           /* H(c+1)                                  */
@@ -380,17 +389,19 @@ yee_fused(const __grid_constant__ FusedParams p)
 		hxp = ld4(H0 + o); hyp = ld4(H1 + o);
 		if (xh) hxp1 = H0[o - 1];
 	}
-
 	int c = cl;
 	for (int it = 0; c >= cf - 1; ++it, --c) {
 		const size_t o = (size_t)c*p.plane + row;
-		cp_async_wait<1>();                                 /* this thread's copies of plane c have landed */
+		cp_async_wait<AHEAD - 1>();                         /* this thread's copies of plane c have landed */
 		__syncthreads();                                    /* ... and everybody else's; iteration it-1 is over everywhere */
-		{                                                   /* plane c-2 goes into the stage iteration it-1 used */
-			if (c - 2 >= cf - 1) stage_plane(c - 2, (it + 2) % FUSED_STAGES);
+		{                                                   /* plane c-AHEAD goes into the stage iteration it-1 used */
+			if (c - AHEAD >= cf - 1) stage_plane(c - AHEAD, (it + AHEAD) % NST);
 			cp_async_commit();
 		}
-		const FusedStage<ROWS> &S = sm.st[it % FUSED_STAGES];
+		const FusedStage<ROWS,EPS> &S = sm.st[it % NST];
+		float4 cx4 = zero4, cy4 = zero4, cz4 = zero4;
+		float cyh = 0.f, czh = 0.f;
+		if (EPS && act) { cx4 = S.c[0][wy][lane]; cy4 = S.c[1][wy][lane]; cz4 = S.c[2][wy][lane]; if (xh) { cyh = S.edge[wy][8]; czh = S.edge[wy][9]; } }
 		float4 ex = zero4, ey = zero4, ez = zero4, hx = zero4, hy = zero4, hz = zero4, hxn = zero4, hzn = zero4;
 		if (ldg) { hx = S.hx[wy][lane]; hy = S.hy[wy][lane]; hz = S.hz[wy][lane]; }
 		if (act) {
@@ -416,7 +427,10 @@ yee_fused(const __grid_constant__ FusedParams p)
 				const float ux = dze*(Hy[e] - Hyp[e]) + dye*(Hzn[e] - Hz[e]);
 				const float uy = DxE[e]*(hz5[e] - hz5[e+1]) + dze*(Hxp[e] - Hx[e]);
 				const float uz = dye*(Hx[e] - Hxn[e]) + DxE[e]*(hy5[e+1] - hy5[e]);
-				Ex[e] += ux; Ey[e] += uy; Ez[e] += uz;
+				if (EPS) {
+					const float Cx[4] = {cx4.x, cx4.y, cx4.z, cx4.w}, Cy[4] = {cy4.x, cy4.y, cy4.z, cy4.w}, Cz[4] = {cz4.x, cz4.y, cz4.z, cz4.w};
+					Ex[e] += ux*Cx[e]; Ey[e] += uy*Cy[e]; Ez[e] += uz*Cz[e];
+				} else { Ex[e] += ux; Ey[e] += uy; Ez[e] += uz; }
 			}
 		}
 		/* the cell a0-1 (lane 0): E'y and E'z only */
@@ -425,8 +439,13 @@ yee_fused(const __grid_constant__ FusedParams p)
 			const float eyo = S.edge[wy][0], ezo = S.edge[wy][1];
 			const float hzh = S.edge[wy][2], hyh = S.edge[wy][3], hxnh = S.edge[wy][5];
 			hxh = S.edge[wy][4];
-			eyh = eyo + (dxeh*(hzh - hz.x) + dze*(hxp1 - hxh));
-			ezh = ezo + (dye*(hxh - hxnh) + dxeh*(hy.x - hyh));
+			if (EPS) {
+				eyh = eyo + (dxeh*(hzh - hz.x) + dze*(hxp1 - hxh))*cyh;
+				ezh = ezo + (dye*(hxh - hxnh) + dxeh*(hy.x - hyh))*czh;
+			} else {
+				eyh = eyo + (dxeh*(hzh - hz.x) + dze*(hxp1 - hxh));
+				ezh = ezo + (dye*(hxh - hxnh) + dxeh*(hy.x - hyh));
+			}
 		}
 		const float4 nex = make_float4(Ex[0], Ex[1], Ex[2], Ex[3]), ney = make_float4(Ey[0], Ey[1], Ey[2], Ey[3]), nez = make_float4(Ez[0], Ez[1], Ez[2], Ez[3]);
 		if (own && c >= cf) { st4(p.Eo[0] + o, nex); st4(p.Eo[1] + o, ney); st4(p.Eo[2] + o, nez); }

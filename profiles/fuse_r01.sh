@@ -1,3 +1,1 @@
-for fc in 32 57 113; do ALISB_FCHUNK=$fc timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --fuse 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('frows 16 fchunk $fc', d['ms_per_step'], d['value'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"; done
-ALISB_CONC=2 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --fuse 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('conc2', d['ms_per_step'], d['value'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"
-ALISB_CONC=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --fuse 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('conc0', d['ms_per_step'], d['value'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused" 2>&1 | tail -8

@@ -257,16 +257,39 @@ def fusion_env(monkeypatch):
     monkeypatch.setenv("ALISB_FUSE_FRAC", "0.01")
 
 
-@pytest.mark.parametrize("shape,num,steps", [
-    ((160, 72, 64), 12, 30),     # the fused box is three 32-cell groups wide; the dipole's planes are excluded
-    ((300, 61, 47), 6, 20),      # ragged rows (61-13 not a multiple of 8), several x segments
-    ((96, 40, 90), 8, 25),       # long z: several z-chunks per range
+def _add_materials(engines, shape, seed=21):
+    """random inverse permittivity everywhere and one dispersive box (1 Drude + 1 critical-point pole,
+    lossy) in the middle of the grid -- the same on every engine"""
+    rng = np.random.RandomState(seed)
+    eps = [(0.3 + 0.7 * rng.rand(shape[0] + (c == 0), shape[1] + (c == 1), shape[2] + (c == 2))).astype(np.float32) for c in range(3)]
+    box = [shape[0] // 3, 2 * shape[0] // 3, shape[1] // 3, 2 * shape[1] // 3, shape[2] // 3, 2 * shape[2] // 3]
+    dims = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1)
+    fill = [rng.rand(*dims).astype(np.float32) for _ in range(3)]
+    coef = {k: [[0.0] * 8 for _ in range(3)] for k in ("JJ", "JK", "JE", "KJ", "KK", "KE")}
+    for c in range(3):
+        coef["JJ"][c][0], coef["JE"][c][0] = 0.93 - 0.01 * c, 0.011 + 0.001 * c
+        coef["JJ"][c][1], coef["JK"][c][1], coef["JE"][c][1] = 0.9, -0.05 - 0.01 * c, 0.007
+        coef["KJ"][c][1], coef["KK"][c][1], coef["KE"][c][1] = 0.04, 0.91, 0.003 + 0.001 * c
+    for e in engines:
+        e.set_inv_eps(*eps)
+        e.add_dispersive(box, 1, 2, [0.012, 0.009, 0.015], coef, fill)
+
+
+@pytest.mark.parametrize("shape,num,steps,materials", [
+    ((160, 72, 64), 12, 30, False),    # the fused box is three 32-cell groups wide; the dipole's planes are excluded
+    ((300, 61, 47), 6, 20, False),     # ragged rows (61-13 not a multiple of the tile), several x segments
+    ((96, 40, 90), 8, 25, False),      # long z: several z-chunks per range
+    ((160, 72, 64), 12, 30, True),     # material arrays and an ADE object inside the fused box
+    ((96, 40, 90), 8, 25, True),
 ])
-def test_fused_stepping_bit_exact(oracle_lib, engine_lib, fusion_env, monkeypatch, shape, num, steps):
+@pytest.mark.parametrize("rows", [8, 16])
+def test_fused_stepping_bit_exact(oracle_lib, engine_lib, fusion_env, monkeypatch, shape, num, steps, materials, rows):
     monkeypatch.setenv("ALISB_FCHUNK", "7")
+    monkeypatch.setenv("ALISB_FROWS", str(rows))
     w, g, o = both(oracle_lib, engine_lib, shape, num=num)
+    if materials:
+        _add_materials([g, o], shape)
     helpers.seed_fields([g, o], tuple(n + 2 for n in shape))
-    l0 = g.launch_count()
     for e in (g, o):
         e.run(steps)
     assert g.time() == o.time()
