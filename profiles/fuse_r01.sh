@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused" 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "forced_fusion" -s 2>&1 | grep -E "fused_launches|passed|failed|Error|differ" | head -40
