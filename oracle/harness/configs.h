@@ -187,6 +187,22 @@ static world cfg_chi2_pump2(void)  { return chi2_world(2, 0); }
 static world cfg_chi2b_signal(void) { return chi2_world(0, 1); }
 static world cfg_chi2b_pump1(void)  { return chi2_world(1, 1); }
 
+/* a Bloch-periodic (complex-field) world wide enough for the fused E+H box of the CUDA engine:
+ * BBC in x (no slab), PBC in y, PML in z, a tilted dielectric bar and a lossy Drude ball */
+static world cfg_bloch_wide(void)
+{
+	dom Dom = {{-1100, 1100}, {-300, 300}, {-400, 400}};
+	res Res = {10, {20}, {1240}};
+	sur Sur = {{BBC, 5100}, {PBC}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Bar = {Box, {{-700, 550}, {-120, 190}, {-90, 110}}};
+	object Ball_ = {Ball, {{200, 560}, {-180, 180}, {40, 400}}};
+	putObjects(W, n(2.1), Bar, Ag, Ball_, Air);
+	pointDipole(W, Ey, -750, 40, -240, Pulse, 500, 900, 1);
+	pointDipole(W, iHz, 780, -80, 260, Sine, 600, 3, 0.5);
+	return W;
+}
+
 static const harness_config harness_configs[] = {
 	{"dipole_pml",  cfg_dipole_pml,  60, 0},
 	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
@@ -198,6 +214,7 @@ static const harness_config harness_configs[] = {
 	{"metasurface", cfg_metasurface, 120, 0},
 	{"dipole_band", cfg_dipole_band, 80, 0},
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
+	{"bloch_wide",  cfg_bloch_wide,  70, 0},
 	{"chi2_shg",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, 0, 0.7f, 0},
 	{"chi2_twm",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, cfg_chi2_pump2, -1.3f, 0},
 	{"chi2_alias",  cfg_chi2b_signal, 80, 0, cfg_chi2b_pump1, 0, 0.9f, 1},

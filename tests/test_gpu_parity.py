@@ -333,7 +333,7 @@ def test_fused_two_slabs_equal_single(engine_lib, fusion_env):
 @pytest.mark.skipif(not helpers.have_ref_bin("stepdump_bridge_cuda"), reason="oracle/_ref harness not built")
 @pytest.mark.parametrize("cfg", helpers.CONFIGS)
 def test_named_configs_with_forced_fusion(cfg, tmp_path, fusion_env):
-    """the 13 reference configurations (TFSF, ADE, material arrays, Bloch-complex fields, SYM/PBC/BBC/HBC
+    """the 14 reference configurations (TFSF, ADE, material arrays, Bloch-complex fields, SYM/PBC/BBC/HBC
     boundaries, chi2 mixing between worlds) with fused stepping forced on wherever a fusable box exists:
     the field state must still hash to the reference golden"""
     out = str(tmp_path / "g.bin")
@@ -346,5 +346,5 @@ def test_named_configs_with_forced_fusion(cfg, tmp_path, fusion_env):
         bad = np.argwhere(a != b)
         raise AssertionError(f"{cfg} (fused): {len(bad)} values differ from the oracle, first {bad[:1].tolist()}, rel L2 {helpers.rel_l2(a, b):.3e}\n{log[-500:]}")
     print(cfg, [l for l in log.splitlines() if l.startswith("fused_launches")])
-    if cfg in ("vacuum_cpml", "nanoblock"):     # the grids wide enough for a fused box (>= one 32-cell group between the x slabs)
+    if cfg in ("vacuum_cpml", "nanoblock", "bloch_wide"):     # the grids wide enough for a fused box (>= one 32-cell group between the x slabs)
         assert "fused_launches=0" not in log, f"{cfg}: the fused kernel did not run"
