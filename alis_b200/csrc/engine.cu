@@ -41,7 +41,6 @@ struct PassGraph { cudaGraphExec_t exec; cudaGraph_t graph; std::vector<SrcNode>
 enum { GMODE_NONE = 0, GMODE_CAPTURE = 1 };
 static thread_local int g_mode = GMODE_NONE;
 static thread_local std::vector<SrcNode> *g_nodes = 0;
-static thread_local int g_nkernels = 0;
 
 struct DispObj {
 	alisb_dispersive d;
@@ -157,16 +156,12 @@ static int dalloc(float **p, size_t n)
 #define TRY(call) do { int r_ = (call); if (r_ != ALISB_OK) return r_; } while (0)
 #define DEV(e) CU(cudaSetDevice((e)->g.device))
 
-/* host dense block, z fastest (reference layout)  <->  dense block, x fastest (device order) */
+/* host dense block, z fastest (reference layout)  ->  dense block, x fastest (device order);
+ * the way back is done on the device (box_gather) */
 static void to_xfast(const float *zf, float *xf, const Box &B)
 {
 	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
 		xf[((size_t)c*B.nb + b)*B.na + a] = zf[((size_t)a*B.nb + b)*B.nc + c];
-}
-static void to_zfast(const float *xf, float *zf, const Box &B)
-{
-	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
-		zf[((size_t)a*B.nb + b)*B.nc + c] = xf[((size_t)c*B.nb + b)*B.na + a];
 }
 
 extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
