@@ -96,6 +96,7 @@ def _declare(lib):
         "alisb_phaser_destroy": (None, [vp]),
         "alisb_phaser_accumulate": (i, [vp, f32p, f32p]),
         "alisb_phaser_read": (i, [vp, i, i, i, f32p]),
+        "alisb_phaser_surface_sums": (i, [vp, i, C.c_void_p, i, f32p, C.c_size_t, C.POINTER(C.c_double)]),
         "alisb_launch_count": (u64, [vp]),
         "alisb_set_profiling": (i, [vp, i]),
         "alisb_last_run_kernel_ms": (i, [vp, C.POINTER(f), C.POINTER(i)]),
@@ -345,6 +346,22 @@ class Phaser:
         out = np.empty(shape + (2,), dtype=np.float32)
         self.e._ck(self.e.lib.alisb_phaser_read(self.h, freq, face, which, _fp(out)))
         return out.view(np.complex64)[..., 0]
+
+    def face_extents(self, face):
+        """(n_lo, n_hi): face extents along its lower / higher in-face axis"""
+        n = [self.box[1] - self.box[0] + 1, self.box[3] - self.box[2] + 1, self.box[5] - self.box[4] + 1]
+        ax = face // 2
+        return n[1 if ax == 0 else 0], n[1 if ax == 2 else 2]
+
+    def surface_sums(self, freq, jobs, weights):
+        """jobs: [(face, which, w_lo, w_hi)] with offsets into `weights` (complex64, 1-D);
+        returns complex128 per job: sum_u sum_v w_lo[u] A[u][v] w_hi[v]  (farfld.c:248-459)"""
+        J = np.ascontiguousarray(np.array(jobs, dtype=np.int64).reshape(-1, 4).astype(np.uint32)).view(np.int32)
+        W = np.ascontiguousarray(np.asarray(weights, dtype=np.complex64)).view(np.float32)
+        out = np.zeros((J.shape[0], 2), np.float64)
+        self.e._ck(self.e.lib.alisb_phaser_surface_sums(self.h, freq, J.ctypes.data_as(C.c_void_p), J.shape[0], _fp(W), W.size // 2,
+                                                        out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[:, 0] + 1j * out[:, 1]
 
     def close(self):
         if self.h:

@@ -119,6 +119,7 @@ struct alisb_phaser {
 	Box face[6]; size_t cells[6];
 	float2 *acc[6];
 	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev; bool ev_pending;
+	SurfJob *d_jobs; float2 *d_w; double *d_sums; size_t jobs_cap, w_cap;   /* far-field surface sums (grown on demand) */
 };
 
 /* fused stepping defers the E pass (see alisb_step_part): every entry point that reads the device
@@ -1499,6 +1500,7 @@ extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int fa
 	DEV(e);
 	alisb_phaser *p = new alisb_phaser();
 	p->e = e; memcpy(p->box, box, sizeof p->box); p->mask = face_mask; p->nfreq = nfreq; p->ev_pending = false;
+	p->d_jobs = 0; p->d_w = 0; p->d_sums = 0; p->jobs_cap = 0; p->w_cap = 0;
 	for (int f=0; f<6; f++) {
 		p->acc[f] = 0; p->cells[f] = 0;
 		if (!(face_mask & (1<<f))) continue;
@@ -1524,6 +1526,7 @@ extern "C" void alisb_phaser_destroy(alisb_phaser *p)
 	cudaStreamSynchronize(p->e->stream);
 	for (int f=0; f<6; f++) cudaFree(p->acc[f]);
 	for (int k=0; k<2; k++) { cudaFree(p->dexp[k]); cudaFreeHost(p->hexp[k]); }
+	cudaFree(p->d_jobs); cudaFree(p->d_w); cudaFree(p->d_sums);
 	cudaEventDestroy(p->ev);
 	delete p;
 }
@@ -1562,6 +1565,52 @@ extern "C" int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which,
 	float2 *o = (float2*)host;
 	for (int a=0; a<B.na; a++) for (int b=0; b<B.nb; b++) for (int c=0; c<B.nc; c++)
 		o[((size_t)a*B.nb + b)*B.nc + c] = h[((size_t)c*B.nb + b)*B.na + a];
+	return ALISB_OK;
+}
+
+/* near-to-far-field surface sums: every job of an angular sweep in one launch (kernel surface_sums) */
+extern "C" int alisb_phaser_surface_sums(alisb_phaser *p, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out)
+{
+	if (!p || freq < 0 || freq >= p->nfreq || njobs < 0 || (njobs && (!jobs || !weights || !out))) return fail(ALISB_EINVAL, "bad surface-sum request");
+	if (!njobs) return ALISB_OK;
+	alisb_engine *e = p->e;
+	DEV(e);
+	SurfParams sp;
+	memset(&sp, 0, sizeof sp);
+	sp.freq = freq;
+	for (int f=0; f<6; f++) {
+		sp.acc[f] = p->acc[f];
+		const Box &B = p->face[f];
+		const int ax = f/2;
+		if (p->acc[f]) { sp.nlo[f] = ax == 0 ? B.nb : B.na; sp.nhi[f] = ax == 2 ? B.nb : B.nc; }
+	}
+	std::vector<SurfJob> hj((size_t)njobs);
+	for (int q=0; q<njobs; q++) {
+		const alisb_surface_job &j = jobs[q];
+		if (j.face < 0 || j.face > 5 || !p->acc[j.face] || j.which < 0 || j.which > 3) return fail(ALISB_EINVAL, "surface sum: face %d is not accumulated", j.face);
+		if ((size_t)j.w_lo + sp.nlo[j.face] > nweights || (size_t)j.w_hi + sp.nhi[j.face] > nweights) return fail(ALISB_EINVAL, "surface sum: weight vector outside the buffer");
+		hj[q].face = j.face; hj[q].which = j.which; hj[q].w_lo = j.w_lo; hj[q].w_hi = j.w_hi;
+	}
+	if ((size_t)njobs > p->jobs_cap) {
+		cudaFree(p->d_jobs); cudaFree(p->d_sums); p->d_jobs = 0; p->d_sums = 0; p->jobs_cap = 0;
+		const size_t cap = std::max((size_t)njobs, (size_t)1024);
+		CU(cudaMalloc((void**)&p->d_jobs, cap*sizeof(SurfJob)));
+		CU(cudaMalloc((void**)&p->d_sums, cap*2*sizeof(double)));
+		p->jobs_cap = cap;
+	}
+	if (nweights > p->w_cap) {
+		cudaFree(p->d_w); p->d_w = 0; p->w_cap = 0;
+		const size_t cap = std::max(nweights, (size_t)4096);
+		CU(cudaMalloc((void**)&p->d_w, cap*sizeof(float2)));
+		p->w_cap = cap;
+	}
+	CU(cudaMemcpyAsync(p->d_jobs, hj.data(), (size_t)njobs*sizeof(SurfJob), cudaMemcpyHostToDevice, e->stream));
+	CU(cudaMemcpyAsync(p->d_w, weights, nweights*sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+	surface_sums<<<(unsigned)njobs, 128, 0, e->stream>>>(sp, p->d_jobs, p->d_w, p->d_sums);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, p->d_sums, (size_t)njobs*2*sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	e->launches++;
 	return ALISB_OK;
 }
 

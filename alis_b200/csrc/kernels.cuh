@@ -892,3 +892,49 @@ __global__ void flux_finish(const double *partial, int nblocks, double *out)
 		out[2*q] = s1; out[2*q + 1] = s2;
 	}
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Near-to-far-field surface sums (reference farfld.c:248-459, the double loops of farFieldX/Y/Z):
+ *     out[job] = sum_v sum_u  Wlo[u] * A[u][v] * Whi[v]
+ * over one phasor face, A = accumulator `which` at frequency `freq`, u the lower-numbered in-face
+ * axis (fastest in the accumulator layout), v the higher one.  The trapezoid end weights and the
+ * staggered ranges of the reference loops are folded into the weight vectors by the host.
+ * One CTA per job; all (theta, phi, polarisation) queries of an angular sweep are jobs of one
+ * launch.  Products are fp32 (A*Whi first, then *Wlo, no FMA), the sum is double and reduced in a
+ * fixed order, so the result is deterministic.
+ * ------------------------------------------------------------------------------------------ */
+struct SurfJob { int face, which; unsigned w_lo, w_hi; };
+struct SurfParams {
+	const float2 *acc[6];             /* per face: [freq][which][cell]                       */
+	int nlo[6], nhi[6];               /* face extents along the lower / higher in-face axis  */
+	int freq;
+};
+
+static __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+	return make_float2(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x);
+}
+
+__global__ void __launch_bounds__(128) surface_sums(const __grid_constant__ SurfParams p, const SurfJob *jobs, const float2 *W, double *out)
+{
+	const SurfJob J = jobs[blockIdx.x];
+	const int nlo = p.nlo[J.face], nhi = p.nhi[J.face];
+	const size_t cells = (size_t)nlo*nhi;
+	const float2 *A = p.acc[J.face] + ((size_t)p.freq*4 + J.which)*cells;
+	const float2 *Wlo = W + J.w_lo, *Whi = W + J.w_hi;
+	double sr = 0, si = 0;
+	for (size_t q = threadIdx.x; q < cells; q += blockDim.x) {
+		const int v = (int)(q / nlo), u = (int)(q - (size_t)v*nlo);
+		const float2 t = cmulf(cmulf(A[q], Whi[v]), Wlo[u]);
+		sr += (double)t.x; si += (double)t.y;
+	}
+	__shared__ double sh[2][4];
+	for (int o = 16; o > 0; o >>= 1) { sr += __shfl_down_sync(0xffffffffu, sr, o); si += __shfl_down_sync(0xffffffffu, si, o); }
+	const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+	if (l == 0) { sh[0][w] = sr; sh[1][w] = si; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		out[2*(size_t)blockIdx.x]     = ((sh[0][0] + sh[0][1]) + sh[0][2]) + sh[0][3];
+		out[2*(size_t)blockIdx.x + 1] = ((sh[1][0] + sh[1][1]) + sh[1][2]) + sh[1][3];
+	}
+}

@@ -8,10 +8,11 @@
  * transfer recursion.  The x,y dependence of the test field is a plane-wave factor, so every face
  * integral is separable: a weighted sum with 1-D weight vectors.
  *
- * The phasor faces are small (N^2 complex values per face), so they are pulled from the device
- * once (alisSyncPhaser) and the angular sweep runs on the host (device-side sweep: SURVEY.md 8
- * row f2).  farFieldProfile evaluates its pixels in parallel over the host cores.
- * Arithmetic follows the reference expression by expression (cited per function).
+ * The face integrals run ON THE DEVICE: the phasor faces stay where
+ * updatePhaser accumulated them, the host prepares the 1-D weight vectors and test fields of every
+ * direction with the reference's expressions and libm (cited per function), and all directions of
+ * a sweep (farFieldProfile, farFieldTheta/Phi, farFieldFlux) go to the GPU as one batched launch
+ * per 4096 queries (alisb_phaser_surface_sums).
  */
 #include <sys/stat.h>
 #include <string.h>
@@ -246,24 +247,55 @@ tfield Spol(phaser P, float theta, float phi)
  *   along z they are the test-field samples times the cell size (node-type uses T[-k], cell-type
  *   T[1-k] for the mirror image).
  * surface sum: outer index runs lo+1..hi with cell-type weights, inner index is a trapezoid over
- * lo..hi with node-type weights. */
+ * lo..hi with node-type weights.
+ *
+ * The double loops themselves run ON THE DEVICE (alisb_phaser_surface_sums, kernel surface_sums):
+ * the phasor faces stay where updatePhaser accumulated them.  Every query (direction x
+ * polarisation) is evaluated twice by the same code: a RECORD pass that builds the weight vectors
+ * and lists the sums it needs (ff_job), and -- after one device call for all queries of a sweep --
+ * a REPLAY pass in which surface_sum() hands back the device results in the same order. */
 typedef struct { float complex *w; int lo, hi; } wvec;
 
-static wvec vec_alloc(int lo, int hi)
+typedef struct { int face, which; int lo_vec, hi_vec; } ff_job;       /* indices into ff_ctx.vec */
+typedef struct { float complex *w; int len; const float complex *key; } ff_vec;
+typedef struct {
+	int replay;
+	/* record */
+	ff_job *job; int njob, capjob;
+	ff_vec *vec; int nvec, capvec;
+	/* replay */
+	const double *result; int next;
+} ff_ctx;
+
+static void ctx_free(ff_ctx *c)
+{
+	for (int q=0; q<c->nvec; q++) free(c->vec[q].w);
+	free(c->vec); free(c->job);
+	memset(c, 0, sizeof *c);
+}
+
+static wvec vec_alloc(ff_ctx *c, int lo, int hi)
 {
 	wvec v = { 0, lo, hi };
-	MALLOC(v.w, lo, 1-lo+hi);
+	if (!c->replay) MALLOC(v.w, lo, 1-lo+hi);
 	return v;
 }
-static void vec_free(wvec v) { free(&v.w[v.lo]); }
+/* a released vector's address may be handed out again by malloc: forget it as a sharing key */
+static void vec_free(ff_ctx *c, wvec v)
+{
+	if (!v.w) return;
+	for (int q=0; q<c->nvec; q++) if (c->vec[q].key == v.w) c->vec[q].key = 0;
+	free(&v.w[v.lo]);
+}
 
-static wvec plane_wave_weights(world W, int axis, int lo, int hi, float kq, int cell_type)
+static wvec plane_wave_weights(ff_ctx *c, world W, int axis, int lo, int hi, float kq, int cell_type)
 {
 	const float *d = cell_type ? (axis==0 ? W->CH->dx : W->CH->dy) : (axis==0 ? W->CE->dx : W->CE->dy);
 	float (*coord)(world, float) = axis==0 ? W->itox : W->jtoy;
 	const int sym = (axis==0 ? W->xMinSur : W->yMinSur) == SYM;
 	const float cosk = axis==0 ? W->coskx : W->cosky;
-	wvec v = vec_alloc(lo, hi);
+	wvec v = vec_alloc(c, lo, hi);
+	if (c->replay) return v;
 	for (int q = cell_type ? lo+1 : lo; q<=hi; q++) {
 		v.w[q] = d[q] * cexpf(I*kq*coord(W, cell_type ? q-0.5 : q));
 		if (sym) { if (cell_type) v.w[q] += conjf(v.w[q]) * cosk; else v.w[q] -= conjf(v.w[q]) * cosk; }
@@ -271,11 +303,12 @@ static wvec plane_wave_weights(world W, int axis, int lo, int hi, float kq, int 
 	return v;
 }
 
-static wvec test_field_weights(world W, int lo, int hi, const float complex *T, int cell_type)
+static wvec test_field_weights(ff_ctx *c, world W, int lo, int hi, const float complex *T, int cell_type)
 {
 	const float *d = cell_type ? W->CH->dz : W->CE->dz;
 	const int sym = W->zMinSur == SYM;
-	wvec v = vec_alloc(lo, hi);
+	wvec v = vec_alloc(c, lo, hi);
+	if (c->replay) return v;
 	for (int k = cell_type ? lo+1 : lo; k<=hi; k++) {
 		v.w[k] = d[k] * T[k];
 		if (sym) { if (cell_type) v.w[k] += d[k] * T[1-k] * W->coskz; else v.w[k] -= d[k] * T[-k] * W->coskz; }
@@ -283,102 +316,113 @@ static wvec test_field_weights(world W, int lo, int hi, const float complex *T, 
 	return v;
 }
 
-static inline float complex cget(float complex ***A, int a, int at, int b, int ib, int c, int ic)
+/* the device sums over the whole face box with these weights: the outer (cell-type) vector gets a
+ * zero at lo, the inner (node-type) vector the trapezoid's halves at both ends */
+static int ctx_vector(ff_ctx *c, wvec v, int outer)
 {
-	int q[3];
-	q[a] = at; q[b] = ib; q[c] = ic;
-	return A[q[0]][q[1]][q[2]];
-}
-
-/* face normal a at index `at`; outer axis o (cell-type weights), inner axis n (node-type weights) */
-static float complex surface_sum(float complex ***A, int a, int at, int o, wvec Wo, int n, wvec Wn)
-{
-	float complex acc = 0;
-	for (int io=Wo.lo+1; io<=Wo.hi; io++) {
-		float complex sum = 0.5 * (cget(A,a,at,o,io,n,Wn.lo) * Wn.w[Wn.lo] + cget(A,a,at,o,io,n,Wn.hi) * Wn.w[Wn.hi]);
-		for (int in=Wn.lo+1; in<Wn.hi; in++) sum += cget(A,a,at,o,io,n,in) * Wn.w[in];
-		acc += Wo.w[io] * sum;
+	for (int q=0; q<c->nvec; q++) if (c->vec[q].key == v.w) return q;
+	if (c->nvec == c->capvec) { c->capvec = c->capvec ? 2*c->capvec : 16; c->vec = realloc(c->vec, sizeof(ff_vec)*c->capvec); }
+	ff_vec *f = &c->vec[c->nvec];
+	f->len = v.hi - v.lo + 1; f->key = v.w;
+	f->w = malloc(sizeof(float complex)*f->len);
+	for (int q=v.lo; q<=v.hi; q++) {
+		if (outer) f->w[q-v.lo] = q == v.lo ? 0 : v.w[q];
+		else f->w[q-v.lo] = ((q==v.lo ? 0.5f : 0) + (q==v.hi ? 0.5f : 0) + (q!=v.lo && q!=v.hi ? 1.0f : 0)) * v.w[q];
 	}
-	return acc;
+	return c->nvec++;
 }
 
-static float complex face_x(phaser P, cfield S, int i, tfield T, float kx, float ky)
+/* face `face` (normal a = face/2); field component `comp` of E (isH 0) or H (isH 1); outer axis o
+ * (cell-type weights), inner axis n (node-type weights) */
+static float complex surface_sum(ff_ctx *c, int face, int isH, int comp, int o, wvec Wo, int n, wvec Wn)
+{
+	if (c->replay) { const double *r = c->result + 2*(size_t)c->next++; return (float)r[0] + I*(float)r[1]; }
+	const int a = face/2;
+	if (c->njob == c->capjob) { c->capjob = c->capjob ? 2*c->capjob : 16; c->job = realloc(c->job, sizeof(ff_job)*c->capjob); }
+	ff_job *j = &c->job[c->njob++];
+	j->face = face; j->which = (comp - a + 3)%3 - 1 + (isH ? 2 : 0);
+	const int vo = ctx_vector(c, Wo, 1), vn = ctx_vector(c, Wn, 0);
+	if (o < n) j->lo_vec = vo, j->hi_vec = vn; else j->lo_vec = vn, j->hi_vec = vo;
+	return 0;
+}
+
+static float complex face_x(ff_ctx *c, phaser P, int face, int i, tfield T, float kx, float ky)
 {
 	world W = P->W;
 	float complex EyHz=0, EzHy=0, HyEz=0, HzEy=0, Sum=0;
 
 	if (T.Hz || T.Ey) {
-		wvec Y = plane_wave_weights(W, 1, P->jMin, P->jMax, ky, 1);
-		if (T.Hz) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Hz, 0); EyHz = surface_sum(S.Ey, 0, i, 1, Y, 2, Z); vec_free(Z); }
-		if (T.Ey) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Ey, 0); HzEy = surface_sum(S.Hz, 0, i, 1, Y, 2, Z); vec_free(Z); }
-		vec_free(Y);
+		wvec Y = plane_wave_weights(c, W, 1, P->jMin, P->jMax, ky, 1);
+		if (T.Hz) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Hz, 0); EyHz = surface_sum(c, face, 0, 1, 1, Y, 2, Z); vec_free(c, Z); }
+		if (T.Ey) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Ey, 0); HzEy = surface_sum(c, face, 1, 2, 1, Y, 2, Z); vec_free(c, Z); }
+		vec_free(c, Y);
 	}
 	if (T.Hy || T.Ez) {
-		wvec Y = plane_wave_weights(W, 1, P->jMin, P->jMax, ky, 0);
-		if (T.Hy) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Hy, 1); EzHy = surface_sum(S.Ez, 0, i, 2, Z, 1, Y); vec_free(Z); }
-		if (T.Ez) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Ez, 1); HyEz = surface_sum(S.Hy, 0, i, 2, Z, 1, Y); vec_free(Z); }
-		vec_free(Y);
+		wvec Y = plane_wave_weights(c, W, 1, P->jMin, P->jMax, ky, 0);
+		if (T.Hy) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Hy, 1); EzHy = surface_sum(c, face, 0, 2, 2, Z, 1, Y); vec_free(c, Z); }
+		if (T.Ez) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Ez, 1); HyEz = surface_sum(c, face, 1, 1, 2, Z, 1, Y); vec_free(c, Z); }
+		vec_free(c, Y);
 	}
 	Sum += (EyHz-HzEy-EzHy+HyEz) * cexpf(I*kx*W->itox(W,i));
 	if (W->xMinSur==SYM) Sum += (EyHz+HzEy-EzHy-HyEz) * cexpf(-I*kx*W->itox(W,i)) * W->coskx;
 	return Sum;
 }
 
-static float complex face_y(phaser P, cfield S, int j, tfield T, float kx, float ky)
+static float complex face_y(ff_ctx *c, phaser P, int face, int j, tfield T, float kx, float ky)
 {
 	world W = P->W;
 	float complex ExHz=0, EzHx=0, HxEz=0, HzEx=0, Sum=0;
 
 	if (T.Hx || T.Ez) {
-		wvec X = plane_wave_weights(W, 0, P->iMin, P->iMax, kx, 0);
-		if (T.Hx) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Hx, 1); EzHx = surface_sum(S.Ez, 1, j, 2, Z, 0, X); vec_free(Z); }
-		if (T.Ez) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Ez, 1); HxEz = surface_sum(S.Hx, 1, j, 2, Z, 0, X); vec_free(Z); }
-		vec_free(X);
+		wvec X = plane_wave_weights(c, W, 0, P->iMin, P->iMax, kx, 0);
+		if (T.Hx) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Hx, 1); EzHx = surface_sum(c, face, 0, 2, 2, Z, 0, X); vec_free(c, Z); }
+		if (T.Ez) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Ez, 1); HxEz = surface_sum(c, face, 1, 0, 2, Z, 0, X); vec_free(c, Z); }
+		vec_free(c, X);
 	}
 	if (T.Hz || T.Ex) {
-		wvec X = plane_wave_weights(W, 0, P->iMin, P->iMax, kx, 1);
-		if (T.Hz) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Hz, 0); ExHz = surface_sum(S.Ex, 1, j, 0, X, 2, Z); vec_free(Z); }
-		if (T.Ex) { wvec Z = test_field_weights(W, P->kMin, P->kMax, T.Ex, 0); HzEx = surface_sum(S.Hz, 1, j, 0, X, 2, Z); vec_free(Z); }
-		vec_free(X);
+		wvec X = plane_wave_weights(c, W, 0, P->iMin, P->iMax, kx, 1);
+		if (T.Hz) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Hz, 0); ExHz = surface_sum(c, face, 0, 0, 0, X, 2, Z); vec_free(c, Z); }
+		if (T.Ex) { wvec Z = test_field_weights(c, W, P->kMin, P->kMax, T.Ex, 0); HzEx = surface_sum(c, face, 1, 2, 0, X, 2, Z); vec_free(c, Z); }
+		vec_free(c, X);
 	}
 	Sum += (EzHx-HxEz-ExHz+HzEx) * cexpf(I*ky*W->jtoy(W,j));
 	if (W->yMinSur==SYM) Sum += (EzHx+HxEz-ExHz-HzEx) * cexpf(-I*ky*W->jtoy(W,j)) * W->cosky;
 	return Sum;
 }
 
-static float complex face_z(phaser P, cfield S, int k, tfield T, float kx, float ky)
+static float complex face_z(ff_ctx *c, phaser P, int face, int k, tfield T, float kx, float ky)
 {
 	world W = P->W;
 	float complex ExHy=0, EyHx=0, HxEy=0, HyEx=0, Sum=0;
 	const int sym = W->zMinSur==SYM;
 
 	if (T.Hy || T.Ex) {
-		wvec X = plane_wave_weights(W, 0, P->iMin, P->iMax, kx, 1), Y = plane_wave_weights(W, 1, P->jMin, P->jMax, ky, 0);
+		wvec X = plane_wave_weights(c, W, 0, P->iMin, P->iMax, kx, 1), Y = plane_wave_weights(c, W, 1, P->jMin, P->jMax, ky, 0);
 		if (T.Hy) {
-			ExHy = surface_sum(S.Ex, 2, k, 0, X, 1, Y);
+			ExHy = surface_sum(c, face, 0, 0, 0, X, 1, Y);
 			Sum += ExHy * 0.5 * (T.Hy[k]+T.Hy[k+1]);
 			if (sym) Sum += ExHy * 0.5 * (T.Hy[1-k]+T.Hy[-k]) * W->coskz;
 		}
 		if (T.Ex) {
-			HyEx = surface_sum(S.Hy, 2, k, 0, X, 1, Y);
+			HyEx = surface_sum(c, face, 1, 1, 0, X, 1, Y);
 			Sum -= HyEx * T.Ex[k];
 			if (sym) Sum += HyEx * T.Ex[-k] * W->coskz;
 		}
-		vec_free(X); vec_free(Y);
+		vec_free(c, X); vec_free(c, Y);
 	}
 	if (T.Hx || T.Ey) {
-		wvec X = plane_wave_weights(W, 0, P->iMin, P->iMax, kx, 0), Y = plane_wave_weights(W, 1, P->jMin, P->jMax, ky, 1);
+		wvec X = plane_wave_weights(c, W, 0, P->iMin, P->iMax, kx, 0), Y = plane_wave_weights(c, W, 1, P->jMin, P->jMax, ky, 1);
 		if (T.Hx) {
-			EyHx = surface_sum(S.Ey, 2, k, 1, Y, 0, X);
+			EyHx = surface_sum(c, face, 0, 1, 1, Y, 0, X);
 			Sum -= EyHx * 0.5 * (T.Hx[k]+T.Hx[k+1]);
 			if (sym) Sum -= EyHx * 0.5 * (T.Hx[1-k]+T.Hx[-k]) * W->coskz;
 		}
 		if (T.Ey) {
-			HxEy = surface_sum(S.Hx, 2, k, 1, Y, 0, X);
+			HxEy = surface_sum(c, face, 1, 0, 1, Y, 0, X);
 			Sum += HxEy * T.Ey[k];
 			if (sym) Sum -= HxEy * T.Ey[-k] * W->coskz;
 		}
-		vec_free(X); vec_free(Y);
+		vec_free(c, X); vec_free(c, Y);
 	}
 	return Sum;
 }
@@ -386,25 +430,24 @@ static float complex face_z(phaser P, cfield S, int k, tfield T, float kx, float
 /* ---- the transform (reference farfld.c:462-514) ------------------------------------------------------------- */
 static void ensure_ready(phaser P)
 {
-	alisSyncPhaser(P);
 	if (!P->dE) build_layer_column(P, P->W);
 }
 
-float complex farField(phaser P, tfield pol(phaser,float,float), float theta, float phi)
+/* one query; called once in record mode and once in replay mode with identical control flow */
+static float complex far_field_eval(ff_ctx *c, phaser P, tfield pol(phaser,float,float), float theta, float phi)
 {
 	float sinth = 0, kx, ky;
 	float complex Sum = 0;
 	world W = P->W;
 
-	ensure_ready(P);
 	if (theta == INF || phi == INF) return 0;
 	while (theta < 0) theta += 360;
 	while (theta >= 360) theta -= 360;
 	while (phi < 0) phi += 360;
 	while (phi >= 360) phi -= 360;
 	/* grazing directions: average the two neighbours */
-	if ( 89 < theta && theta <  91) return 0.5 * (farField(P, pol,  89, phi) + farField(P, pol,  91, phi));
-	if (269 < theta && theta < 271) return 0.5 * (farField(P, pol, 269, phi) + farField(P, pol, 271, phi));
+	if ( 89 < theta && theta <  91) return 0.5 * (far_field_eval(c, P, pol,  89, phi) + far_field_eval(c, P, pol,  91, phi));
+	if (269 < theta && theta < 271) return 0.5 * (far_field_eval(c, P, pol, 269, phi) + far_field_eval(c, P, pol, 271, phi));
 	/* no far field inside an absorbing half space */
 	if (theta < 90 || 270 < theta) {
 		if (cimagf(P->ex[P->kMax])) return 0;
@@ -419,12 +462,12 @@ float complex farField(phaser P, tfield pol(phaser,float,float), float theta, fl
 	kx = - 2 * PI * P->f * sinth * cosf(phi*PI/180);
 	ky = - 2 * PI * P->f * sinth * sinf(phi*PI/180);
 
-	if (W->xMinSur==PML) Sum -= face_x(P, P->xMin, P->iMin, T, kx, ky);
-	if (W->xMaxSur==PML) Sum += face_x(P, P->xMax, P->iMax, T, kx, ky);
-	if (W->yMinSur==PML) Sum -= face_y(P, P->yMin, P->jMin, T, kx, ky);
-	if (W->yMaxSur==PML) Sum += face_y(P, P->yMax, P->jMax, T, kx, ky);
-	if (W->zMinSur==PML) Sum -= face_z(P, P->zMin, P->kMin, T, kx, ky);
-	if (W->zMaxSur==PML) Sum += face_z(P, P->zMax, P->kMax, T, kx, ky);
+	if (W->xMinSur==PML && P->xMin.Ey) Sum -= face_x(c, P, 0, P->iMin, T, kx, ky);
+	if (W->xMaxSur==PML) Sum += face_x(c, P, 1, P->iMax, T, kx, ky);
+	if (W->yMinSur==PML && P->yMin.Ex) Sum -= face_y(c, P, 2, P->jMin, T, kx, ky);
+	if (W->yMaxSur==PML) Sum += face_y(c, P, 3, P->jMax, T, kx, ky);
+	if (W->zMinSur==PML && P->zMin.Ex) Sum -= face_z(c, P, 4, P->kMin, T, kx, ky);
+	if (W->zMaxSur==PML) Sum += face_z(c, P, 5, P->kMax, T, kx, ky);
 
 	float complex *parts[6] = { T.Ex, T.Ey, T.Ez, T.Hx, T.Hy, T.Hz };
 	for (int q=0; q<6; q++) if (parts[q]) free(&parts[q][P->kMIN]);
@@ -443,11 +486,76 @@ float complex farField(phaser P, tfield pol(phaser,float,float), float theta, fl
 	return Sum * T.A * P->A * P->f;
 }
 
+/* n queries (pol[q], theta[q], phi[q]) -> out[q]; the surface sums of a chunk of queries are one
+ * device call */
+#define FF_CHUNK 4096
+typedef tfield (*polfn)(phaser, float, float);
+static void far_field_batch(phaser P, int n, const polfn *pol, const float *theta, const float *phi, float complex *out)
+{
+	ensure_ready(P);
+	int freq = 0;
+	alisb_phaser *dev = alis_phaser_device(P, &freq);
+	if (!dev) { for (int q=0; q<n; q++) out[q] = 0; return; }      /* no absorbing face: nothing was recorded */
+	ff_ctx *ctx = calloc(FF_CHUNK, sizeof *ctx);
+	size_t *job0 = malloc(sizeof(size_t)*(FF_CHUNK+1));
+	for (int base=0; base<n; base+=FF_CHUNK) {
+		const int m = MIN(FF_CHUNK, n-base);
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (int q=0; q<m; q++) far_field_eval(&ctx[q], P, pol[base+q], theta[base+q], phi[base+q]);
+		size_t njobs = 0, nw = 0;
+		for (int q=0; q<m; q++) { job0[q] = njobs; njobs += ctx[q].njob; for (int v=0; v<ctx[q].nvec; v++) nw += ctx[q].vec[v].len; }
+		job0[m] = njobs;
+		alisb_surface_job *jobs = malloc(sizeof *jobs*(njobs+1));
+		float complex *weights = malloc(sizeof *weights*(nw+1));
+		double *sums = malloc(sizeof(double)*2*(njobs+1));
+		size_t w = 0;
+		for (int q=0; q<m; q++) {
+			size_t off[ctx[q].nvec+1];
+			for (int v=0; v<ctx[q].nvec; v++) { off[v] = w; memcpy(weights+w, ctx[q].vec[v].w, sizeof(float complex)*ctx[q].vec[v].len); w += ctx[q].vec[v].len; }
+			for (int j=0; j<ctx[q].njob; j++) {
+				alisb_surface_job *J = &jobs[job0[q]+j];
+				J->face = ctx[q].job[j].face; J->which = ctx[q].job[j].which;
+				J->w_lo = (uint32_t)off[ctx[q].job[j].lo_vec]; J->w_hi = (uint32_t)off[ctx[q].job[j].hi_vec];
+			}
+			ctx_free(&ctx[q]);
+		}
+		if (alisb_phaser_surface_sums(dev, freq, jobs, (int)njobs, (const float*)weights, nw, sums) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (int q=0; q<m; q++) {
+			ff_ctx r = { 0 };
+			r.replay = 1; r.result = sums + 2*job0[q];
+			out[base+q] = far_field_eval(&r, P, pol[base+q], theta[base+q], phi[base+q]);
+		}
+		free(jobs); free(weights); free(sums);
+	}
+	free(ctx); free(job0);
+}
+
+float complex farField(phaser P, tfield pol(phaser,float,float), float theta, float phi)
+{
+	float complex f = 0;
+	polfn p = pol;
+	far_field_batch(P, 1, &p, &theta, &phi, &f);
+	return f;
+}
+
 float farFieldI(phaser P, tfield pol(phaser,float,float), float theta, float phi)
 {
 	if (pol == Unpol) return farFieldI(P, Ppol, theta, phi) + farFieldI(P, Spol, theta, phi);
 	float complex f = farField(P, pol, theta, phi);
 	return conjf(f) * f;
+}
+
+/* P- and S-polarised far field towards n directions */
+static void far_field_pairs(phaser P, int n, const float *theta, const float *phi, float complex *p, float complex *s)
+{
+	polfn *pol = malloc(sizeof(polfn)*2*n);
+	float *th = malloc(sizeof(float)*2*n), *ph = malloc(sizeof(float)*2*n);
+	float complex *f = malloc(sizeof(float complex)*2*n);
+	for (int q=0; q<n; q++) { pol[2*q] = Ppol; pol[2*q+1] = Spol; th[2*q] = th[2*q+1] = theta[q]; ph[2*q] = ph[2*q+1] = phi[q]; }
+	far_field_batch(P, 2*n, pol, th, ph, f);
+	for (int q=0; q<n; q++) { p[q] = f[2*q]; s[q] = f[2*q+1]; }
+	free(pol); free(th); free(ph); free(f);
 }
 
 /* ---- angular maps and cuts (reference farfld.c:525-662) -------------------------------------------------------- */
@@ -475,17 +583,17 @@ void farFieldProfile(world W, phaser P, projmap projMap, int X, int Y, ...)
 	for (int q=0; q<7; q++) map[q] = makeField(S->iMIN, S->iMAX, S->jMIN, S->jMAX, S->kMIN, S->kMAX);
 
 	printf("Performing Near-to-Far-Field Transformation.\n");
-	ensure_ready(P);
+	/* every pixel's direction, both polarisations: one batched sweep on the device */
 	float complex *pp = calloc((size_t)X*Y, sizeof *pp), *ss = calloc((size_t)X*Y, sizeof *ss);
-	float *phis = calloc((size_t)X*Y, sizeof *phis);
-	#pragma omp parallel for collapse(2) schedule(dynamic, 16)
+	float *thetas = calloc((size_t)X*Y, sizeof *thetas), *phis = calloc((size_t)X*Y, sizeof *phis);
 	for (int x=0; x<X; x++) for (int y=0; y<Y; y++) {
 		float angle[2];
 		projMap(x, y, X, Y, angle);
-		pp[(size_t)x*Y+y] = farField(P, Ppol, angle[0], angle[1]);
-		ss[(size_t)x*Y+y] = farField(P, Spol, angle[0], angle[1]);
+		thetas[(size_t)x*Y+y] = angle[0];
 		phis[(size_t)x*Y+y] = angle[1];
 	}
+	far_field_pairs(P, X*Y, thetas, phis, pp, ss);
+	free(thetas);
 	for (int x=0; x<X; x++) for (int y=0; y<Y; y++) {
 		const float complex p = pp[(size_t)x*Y+y], s = ss[(size_t)x*Y+y];
 		const float a1 = phis[(size_t)x*Y+y];
@@ -523,11 +631,12 @@ void farFieldTheta(world W, phaser P, float phi, char *format, ...)
 	va_start(ap, format);
 	vsprintf(filename, format, ap);
 	va_end(ap);
-	for (float theta=0; theta<360; theta+=1) {
-		float complex p = farField(P, Ppol, theta, phi);
-		float complex s = farField(P, Spol, theta, phi);
-		writeRow(W, "%s", filename, theta, sq(cabsf(p))+sq(cabsf(s)), sq(cabsf(p)), sq(cabsf(s)));
-	}
+	float th[360], ph[360];
+	float complex p[360], s[360];
+	int n = 0;
+	for (float theta=0; theta<360 && n<360; theta+=1) th[n] = theta, ph[n] = phi, n++;
+	far_field_pairs(P, n, th, ph, p, s);
+	for (int q=0; q<n; q++) writeRow(W, "%s", filename, th[q], sq(cabsf(p[q]))+sq(cabsf(s[q])), sq(cabsf(p[q])), sq(cabsf(s[q])));
 }
 
 void farFieldPhi(world W, phaser P, float theta, char *format, ...)
@@ -537,11 +646,12 @@ void farFieldPhi(world W, phaser P, float theta, char *format, ...)
 	va_start(ap, format);
 	vsprintf(filename, format, ap);
 	va_end(ap);
-	for (float phi=0; phi<360; phi+=1) {
-		float complex p = farField(P, Ppol, theta, phi);
-		float complex s = farField(P, Spol, theta, phi);
-		writeRow(W, "%s", filename, phi, sq(cabsf(p))+sq(cabsf(s)), sq(cabsf(p)), sq(cabsf(s)));
-	}
+	float th[360], ph[360];
+	float complex p[360], s[360];
+	int n = 0;
+	for (float phi=0; phi<360 && n<360; phi+=1) th[n] = theta, ph[n] = phi, n++;
+	far_field_pairs(P, n, th, ph, p, s);
+	for (int q=0; q<n; q++) writeRow(W, "%s", filename, ph[q], sq(cabsf(p[q]))+sq(cabsf(s[q])), sq(cabsf(p[q])), sq(cabsf(s[q])));
 }
 
 /* power radiated into the cone aMin..aMax (degrees) around (theta, phi), integrated on rings of
@@ -561,15 +671,30 @@ float (farFieldFlux)(phaser P, tfield pol(phaser,float,float), float theta, floa
 		nMin++;
 	}
 	if (nMax) {
+		/* all ring samples first (one batched sweep on the device), then the reference's sum in its order */
+		int count = 0;
+		for (int n=nMin; n<=nMax; n++) count += n<floor(60/delta+0.5) ? n*6 : floor(60/delta+0.5)*6;
+		float *ta = malloc(sizeof(float)*(count+1)), *tb = malloc(sizeof(float)*(count+1));
+		float complex *fp = malloc(sizeof(float complex)*(count+1)), *fs = malloc(sizeof(float complex)*(count+1));
+		int q = 0;
+		for (int n=nMin; n<=nMax; n++) {
+			int N = n<floor(60/delta+0.5) ? n*6 : floor(60/delta+0.5)*6;
+			for (int m=0; m<N; m++, q++) {
+				ta[q] = tilt_theta(theta, delta*n, 360.0*m/N);
+				tb[q] = tilt_phi(theta, delta*n, 360.0*m/N)+phi;
+			}
+		}
+		far_field_pairs(P, count, ta, tb, fp, fs);
+		q = 0;
 		for (int n=nMin; n<=nMax; n++) {
 			int N = n<floor(60/delta+0.5) ? n*6 : floor(60/delta+0.5)*6;
 			float dth = cosf(MAX(aMin,delta*(n-0.5))*PI/180) - cosf(MIN(aMax,delta*(n+0.5))*PI/180);
-			for (int m=0; m<N; m++) {
-				float a = tilt_theta(theta, delta*n, 360.0*m/N);
-				float b = tilt_phi(theta, delta*n, 360.0*m/N)+phi;
+			for (int m=0; m<N; m++, q++) {
+				float a = ta[q];
+				float b = tb[q];
 				float c = tilt_phi(-a, theta, phi-b)+180-360.0*m/N;
-				float complex p = farField(P, Ppol, a, b);
-				float complex s = farField(P, Spol, a, b);
+				float complex p = fp[q];
+				float complex s = fs[q];
 				float pp = sq(cabsf((p * cosf(c*PI/180) - s * sinf(c*PI/180))));
 				float ss = sq(cabsf((s * cosf(c*PI/180) + p * sinf(c*PI/180))));
 				if (pol == Ppol) Sum += dth * (pp * (PI/N + sinf(PI/N)) + ss * (PI/N - sinf(PI/N)));
@@ -577,6 +702,7 @@ float (farFieldFlux)(phaser P, tfield pol(phaser,float,float), float theta, floa
 				if (pol == Unpol) Sum += 2 * PI/N * dth * (pp + ss);
 			}
 		}
+		free(ta); free(tb); free(fp); free(fs);
 	}
 	return Sum;
 }

@@ -31,5 +31,6 @@ unsigned alis_field_arrays(world W, field F);   /* bit (m*2+set)*3+comp for ever
 void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* only the arrays F reads */
 void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
 void alis_view_free(world W);
+alisb_phaser *alis_phaser_device(phaser P, int *freq);   /* device accumulators + frequency index of P */
 
 #endif

@@ -138,6 +138,13 @@ void updatePhaser(world W, phaser P)
 	free(wE); free(wH);
 }
 
+/* device accumulator set and frequency index of one list element (far-field sums, farfld.c) */
+alisb_phaser *alis_phaser_device(phaser P, int *freq)
+{
+	if (freq) *freq = P->b200_index;
+	return (alisb_phaser*)base_of(P)->b200_dev;
+}
+
 /* refresh the host views of the whole frequency list */
 void alisSyncPhaser(phaser P)
 {

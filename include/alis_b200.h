@@ -16,6 +16,7 @@
  *   alisb_set_copies                       copyBoundary call lists  update.c:182-191,284-297,311-339
  *   alisb_step_E / alisb_step_H            updateE / updateH  update.c:275-341
  *   alisb_phaser_*                         createPhasers/updatePhaser  phaser.c:21-110
+ *   alisb_phaser_surface_sums              farFieldX/Y/Z double loops  farfld.c:248-459
  *   alisb_read_box / alisb_write_box       the host float*** views  world.c:58-70
  *
  * Coordinates.  The engine uses ARRAY coordinates: a = i-(iMIN-1), b = j-(jMIN-1),
@@ -245,6 +246,20 @@ int  alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const float *ex
 /* which: 0,1 = E1,E2 ; 2,3 = H1,H2 of that face (phaser.c:57-62 ordering); host gets
  * (re,im) pairs, dense over the face, z fastest.                                           */
 int  alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *host_complex);
+
+/* Near-to-far-field transform, the surface sums (reference farfld.c:248-459, the
+ * double loops of farFieldX/Y/Z).  One job = one separable sum over one accumulator of one face,
+ *     out[job] = sum_v sum_u  w_lo[u] * A[u][v] * w_hi[v],
+ * u running over the face box along its LOWER-numbered in-face axis and v along the higher one
+ * (x face: u=y, v=z; y face: u=x, v=z; z face: u=x, v=y).  weights holds nweights complex floats
+ * (re,im); a job names its two vectors by their offsets (in complex elements).  The host folds the
+ * reference's trapezoid end weights, staggered ranges, cell sizes, plane-wave factors and test-field
+ * samples into the vectors.  All directions and polarisations of an angular sweep are the jobs of
+ * ONE call (one launch, one synchronisation); the phasor faces never leave the device.
+ * out: (re,im) doubles per job.  Products in fp32 (A*w_hi, then *w_lo), sums in double.          */
+typedef struct { int32_t face, which; uint32_t w_lo, w_hi; } alisb_surface_job;
+int  alisb_phaser_surface_sums(alisb_phaser *p, int freq, const alisb_surface_job *jobs, int njobs,
+                               const float *weights, size_t nweights, double *out);
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 uint64_t alisb_launch_count(alisb_engine *e);    /* kernels launched by this engine so far   */

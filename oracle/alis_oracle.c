@@ -725,6 +725,36 @@ int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *hos
 	return ALISB_OK;
 }
 
+/* far-field surface sums (reference farfld.c:248-459 inner loops, weights folded by the host):
+ * fp32 products A*w_hi then *w_lo, double accumulation in the reference's loop nesting (u outer
+ * loop = the face's lower in-face axis is the OUTER loop of the z-fastest block here) */
+int alisb_phaser_surface_sums(alisb_phaser *p, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out)
+{
+	if (!p || freq<0 || freq>=p->nfreq || njobs<0) return fail(ALISB_EINVAL, "bad surface-sum request");
+	#pragma omp parallel for schedule(static)
+	for (int q=0; q<njobs; q++) {
+		const alisb_surface_job *J = &jobs[q];
+		out[2*q] = out[2*q+1] = 0;
+		if (J->face<0 || J->face>5 || J->which<0 || J->which>3 || !(p->mask & (1<<J->face))) continue;
+		const block *B = &p->acc[J->face][J->which];
+		const int ax = J->face/2, lo = ax==0 ? 1 : 0, hi = ax==2 ? 1 : 2;
+		const int nlo = B->n[lo], nhi = B->n[hi];
+		if ((size_t)J->w_lo + nlo > nweights || (size_t)J->w_hi + nhi > nweights) continue;
+		const size_t cells = (size_t)B->n[0]*B->n[1]*B->n[2];
+		const float *A = B->v + 2*cells*freq, *Wlo = weights + 2*(size_t)J->w_lo, *Whi = weights + 2*(size_t)J->w_hi;
+		double sr = 0, si = 0;
+		for (int u=0; u<nlo; u++) for (int v=0; v<nhi; v++) {
+			const size_t c = 2*((size_t)u*nhi + v);          /* z-fastest block: the higher axis is fastest */
+			const float ar = A[c], ai = A[c+1], br = Whi[2*v], bi = Whi[2*v+1];
+			const float tr = ar*br - ai*bi, ti = ar*bi + ai*br;
+			const float cr = Wlo[2*u], ci = Wlo[2*u+1];
+			sr += (double)(tr*cr - ti*ci); si += (double)(tr*ci + ti*cr);
+		}
+		out[2*q] = sr; out[2*q+1] = si;
+	}
+	return ALISB_OK;
+}
+
 uint64_t alisb_launch_count(alisb_engine *e) { return e->launches; }
 int alisb_profile_dominant(alisb_engine *e, float *ms, int *n, double *b) { (void)e; if (ms) *ms=0; if (n) *n=0; if (b) *b=0; return ALISB_OK; }
 int alisb_set_profiling(alisb_engine *e, int on) { (void)e; (void)on; return ALISB_OK; }

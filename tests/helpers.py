@@ -43,6 +43,34 @@ def run_monitors(binary, config, threads=None, steps=0):
     return vals
 
 
+def monitor_mismatches(got, want, device_flux=False):
+    """Value-by-value comparison of two monitors.c outputs.  Everything must be identical to the
+    printed digit (%.9g) except
+      * far-field values (tags ff*): the surface sums run on the device / in the oracle with fp32
+        products and double accumulation, the reference sums in float with an OpenMP reduction --
+        tolerance 1e-5 (the north-star bound for spectra), relative to |f| for re/im pairs;
+      * with device_flux, the Poynting integrals (reduced on the device in double): 5e-6."""
+    assert [g[0] for g in got] == [w[0] for w in want]
+    val = {w[0]: float(w[1]) for w in want}
+    bad = []
+    for g, w in zip(got, want):
+        tag, a, b = g[0], g[1], w[1]
+        if a == b:
+            continue
+        x, y = float(a), float(b)
+        if tag.startswith("ff"):
+            scale = max(abs(x), abs(y))
+            if tag.endswith(("_re", "_im")):
+                stem = tag[:-3]
+                scale = max(scale, (val.get(stem + "_re", 0.0) ** 2 + val.get(stem + "_im", 0.0) ** 2) ** 0.5)
+            if abs(x - y) <= 1e-5 * scale:
+                continue
+        if device_flux and tag.startswith(("poynting", "flux_")) and abs(x - y) <= 5e-6 * max(abs(x), abs(y)):
+            continue
+        bad.append((g, w))
+    return bad
+
+
 def run_mine_stepdump(binary, config, out, steps=0, cwd=None):
     exe = os.path.join(TEST_BIN, binary)
     r = subprocess.run([exe, config, str(steps), out], cwd=cwd, capture_output=True, text=True, timeout=900)

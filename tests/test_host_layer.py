@@ -1,7 +1,8 @@
 """The host C layer (alis_b200/host: our own createWorld / putObjects / planewave / monitors ...)
 validated WITHOUT a GPU: linked against the CPU oracle engine (tests/bin/libalis_oracle.so, test
 infrastructure) it must reproduce the unmodified reference bit for bit -- the complete field
-state of the 10 configurations (sha256 goldens) and every monitor value of monitors.c."""
+state of the 10 configurations (sha256 goldens) and every monitor value of monitors.c (far-field
+values, whose surface sums are engine calls, to 1e-5: helpers.monitor_mismatches)."""
 import pytest
 
 from tests import helpers
@@ -23,6 +24,5 @@ def test_monitor_values_equal_reference(cfg):
     got = helpers.run_monitors("monitors_mine_oracle", cfg)
     want = helpers.golden_monitors()[cfg]
     assert len(want) > 35
-    assert [g[0] for g in got] == [w[0] for w in want]
-    bad = [(g, w) for g, w in zip(got, want) if g[1] != w[1]]
+    bad = helpers.monitor_mismatches(got, want)
     assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
