@@ -50,6 +50,15 @@ class Source(C.Structure):
                 ("n_active", C.c_uint64), ("waveform", WAVEFORM_FN), ("user", C.c_void_p)]
 
 
+class FieldFn(C.Structure):
+    """alisb_field_fn: one of the reference's point-wise field functions (fields.c) + mirror info"""
+    _fields_ = [("fn", C.c_int32), ("set", C.c_int32), ("comp", C.c_int32), ("comp2", C.c_int32), ("m", C.c_int32),
+                ("sym", C.c_int32 * 3), ("cosk", C.c_float * 3), ("org", C.c_int32 * 3)]
+
+
+FN_RAW, FN_NODE, FN_EE, FN_HH, FN_UH, FN_EXH, FN_S, FN_TDIAG, FN_TOFF, FN_DIVE = range(10)
+
+
 class Copy(C.Structure):
     _fields_ = [("set", C.c_int32), ("comp", C.c_int32), ("cosk", C.c_float), ("sink", C.c_float),
                 ("box", C.c_int32 * 6), ("alt", C.c_int32 * 3)]
@@ -84,6 +93,9 @@ def _declare(lib):
         "alisb_write_box": (i, [vp, i, i32p, i32p, f32p]),
         "alisb_set_spacing": (i, [vp, i, i, f32p]),
         "alisb_plane_flux": (i, [vp, C.c_void_p, i, C.POINTER(C.c_double)]),
+        "alisb_eval_box": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
+        "alisb_reduce_absmax": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
+        "alisb_column_sums": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_chi2_couple": (i, [vp, i, i, vp, vp, f32p, f]),
         "alisb_set_fusion": (i, [vp, i]),
         "alisb_flush": (i, [vp, i]),
@@ -294,6 +306,28 @@ class Engine:
         arr = np.ascontiguousarray(np.array(planes, dtype=np.int32).reshape(-1, 6))
         out = np.zeros((arr.shape[0], 2), np.float64)
         self._ck(self.lib.alisb_plane_flux(self.h, arr.ctypes.data_as(C.c_void_p), arr.shape[0], out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def field_fn(self, fn, set_=0, comp=0, comp2=0, m=0, sym=(0, 0, 0), cosk=(1.0, 1.0, 1.0), org=(0, 0, 0)):
+        f = FieldFn()
+        f.fn, f.set, f.comp, f.comp2, f.m = fn, set_, comp, comp2, m
+        f.sym, f.cosk, f.org = (C.c_int32 * 3)(*sym), (C.c_float * 3)(*cosk), (C.c_int32 * 3)(*org)
+        return f
+
+    def eval_box(self, f, ibox):
+        """field function f (field_fn(...)) on the inclusive INDEX box -> (ni, nj, nk) float32"""
+        out = np.empty((ibox[1] - ibox[0] + 1, ibox[3] - ibox[2] + 1, ibox[5] - ibox[4] + 1), np.float32)
+        self._ck(self.lib.alisb_eval_box(self.h, C.byref(f), _ip(ibox), _fp(out)))
+        return out
+
+    def reduce_absmax(self, f, ibox):
+        out = np.zeros(1, np.float32)
+        self._ck(self.lib.alisb_reduce_absmax(self.h, C.byref(f), _ip(ibox), _fp(out)))
+        return out[0]
+
+    def column_sums(self, f, ibox):
+        out = np.empty((ibox[1] - ibox[0] + 1, ibox[3] - ibox[2] + 1), np.float32)
+        self._ck(self.lib.alisb_column_sums(self.h, C.byref(f), _ip(ibox), _fp(out)))
         return out
 
     def set_fusion(self, on):

@@ -1480,6 +1480,87 @@ extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes,
 	return ALISB_OK;
 }
 
+/* ---- device-side field functions (kernels eval_box, reduce_absmax, column_sums) ------------------ */
+static int eval_setup(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], bool columns, EvalParams &p)
+{
+	if (!f || !ibox) return fail(ALISB_EINVAL, "eval: null argument");
+	if (f->fn < ALISB_FN_RAW || f->fn > ALISB_FN_DIVE || f->set < 0 || f->set > 1 || f->comp < 0 || f->comp > 2 || f->comp2 < 0 || f->comp2 > 2 || f->m < 0 || f->m > 1)
+		return fail(ALISB_EINVAL, "eval: bad field function");
+	if ((f->fn == ALISB_FN_EXH || f->fn == ALISB_FN_TOFF) && f->comp == f->comp2) return fail(ALISB_EINVAL, "eval: the two components must differ");
+	if (f->m > e->g.complex_field && f->fn != ALISB_FN_NODE) return fail(ALISB_EINVAL, "eval: no such field set");
+	const int n[3] = { e->nx, e->ny, e->nz };
+	const int reach = f->fn == ALISB_FN_RAW ? 0 : 1;           /* the stencils read index +1 */
+	for (int ax=0; ax<3; ax++) {
+		int lo = ibox[2*ax], hi = ibox[2*ax+1];
+		if (lo > hi) return fail(ALISB_EINVAL, "eval: empty box");
+		if (columns && ax == 2) { if (lo + f->org[2] < 0 || hi + f->org[2] > n[2] + 1) return fail(ALISB_EINVAL, "eval: column range outside the spacing table"); }
+		if (f->sym[ax] && lo < 0) { const int far = std::max(-lo, hi); lo = hi < 0 ? -hi : 0; hi = far; }
+		if (lo + f->org[ax] < 0 || hi + f->org[ax] + reach > n[ax] + 1) return fail(ALISB_EINVAL, "eval: box outside the arrays");
+	}
+	memset(&p, 0, sizeof p);
+	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) for (int c=0; c<3; c++) p.F[s][m][c] = e->F[s][m][c];
+	for (int ax=0; ax<3; ax++) p.dtd[ax] = e->dtd[0][ax];
+	p.dz = e->spacing[0][2];
+	p.f = *f; p.ny = e->ny; p.pitch = e->pitch; p.complex_field = e->g.complex_field; p.dt = e->g.dt;
+	p.i0 = ibox[0]; p.j0 = ibox[2]; p.k0 = ibox[4];
+	p.ni = ibox[1]-ibox[0]+1; p.nj = ibox[3]-ibox[2]+1; p.nk = ibox[5]-ibox[4]+1;
+	if (columns && !p.dz) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
+	return ALISB_OK;
+}
+
+extern "C" int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
+{
+	DEV(e);
+	EvalParams p;
+	TRY(eval_setup(e, f, ibox, false, p));
+	if (!host) return fail(ALISB_EINVAL, "eval: null output");
+	SETTLE(e);
+	const size_t n = (size_t)p.ni*p.nj*p.nk;
+	TRY(need_scratch(e, n));
+	eval_box<<<div_up(n, 256), 256, 0, e->stream>>>(p, e->scratch);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(host, e->scratch, n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	e->launches++;
+	return ALISB_OK;
+}
+
+extern "C" int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out)
+{
+	DEV(e);
+	EvalParams p;
+	TRY(eval_setup(e, f, ibox, false, p));
+	if (!out) return fail(ALISB_EINVAL, "eval: null output");
+	SETTLE(e);
+	const size_t n = (size_t)p.ni*p.nj*p.nk;
+	TRY(need_scratch(e, 1));
+	CU(cudaMemsetAsync(e->scratch, 0, sizeof(float), e->stream));
+	const int blocks = (int)std::min<size_t>(div_up(n, 256), (size_t)e->resident_ctas*4);
+	reduce_absmax<<<blocks, 256, 0, e->stream>>>(p, (unsigned*)e->scratch);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, e->scratch, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	e->launches++;
+	return ALISB_OK;
+}
+
+extern "C" int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
+{
+	DEV(e);
+	EvalParams p;
+	TRY(eval_setup(e, f, ibox, true, p));
+	if (!host) return fail(ALISB_EINVAL, "eval: null output");
+	SETTLE(e);
+	const size_t n = (size_t)p.ni*p.nj;
+	TRY(need_scratch(e, n));
+	column_sums<<<div_up(n, 128), 128, 0, e->stream>>>(p, e->scratch);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(host, e->scratch, n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	e->launches++;
+	return ALISB_OK;
+}
+
 /* ---- halo: planes are contiguous in this layout, hand out pointers into the arrays -------- */
 extern "C" int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)
 {

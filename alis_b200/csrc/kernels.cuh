@@ -938,3 +938,65 @@ __global__ void __launch_bounds__(128) surface_sums(const __grid_constant__ Surf
 		out[2*(size_t)blockIdx.x + 1] = ((sh[1][0] + sh[1][1]) + sh[1][2]) + sh[1][3];
 	}
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Device-side monitors: the reference's point-wise field functions
+ * (fields.c:130-681, the ones that read E/H only) evaluated where the fields live, so that a
+ * slice moves one float per pixel and a world reduction one number (or one float per z column)
+ * instead of up to six field arrays.  The arithmetic is in monitor_eval.h (shared with the CPU
+ * oracle); threads run x fastest for coalesced loads.
+ * ------------------------------------------------------------------------------------------ */
+struct EvalParams {
+	const float *F[2][2][3];          /* [set][m][comp]                                     */
+	const float *dtd[3];              /* CE->dtdx (shifted by XO), dtdy, dtdz                */
+	const float *dz;                  /* CE->dz, array coordinates (column sums)             */
+	alisb_field_fn f;
+	int ny, pitch, complex_field;
+	float dt;
+	int i0, j0, k0, ni, nj, nk;       /* the box, world INDEX coordinates                    */
+};
+#define MON_FN static __device__ __forceinline__
+#define MON_CTX EvalParams
+#define MON_DESC(X) (&(X)->f)
+#define MON_LD(X,set,m,c,a,b,cc) ((X)->F[set][m][c][((size_t)(cc)*((X)->ny+2) + (size_t)(b))*(X)->pitch + ALISB_XO + (a)])
+#define MON_DTD(X,axis,q) ((axis) == 0 ? (X)->dtd[0][ALISB_XO + (q)] : (X)->dtd[axis][q])
+#define MON_DT(X) ((X)->dt)
+#define MON_COMPLEX(X) ((X)->complex_field)
+#include "monitor_eval.h"
+
+/* out: dense block in the HOST order (z fastest), like box_gather */
+__global__ void eval_box(const __grid_constant__ EvalParams p, float *out)
+{
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= (size_t)p.ni*p.nj*p.nk) return;
+	const int ia = (int)(t % p.ni); const size_t r = t / p.ni;
+	const int ib = (int)(r % p.nj), ic = (int)(r / p.nj);
+	out[((size_t)ia*p.nj + ib)*p.nk + ic] = mon_eval(&p, p.i0 + ia, p.j0 + ib, p.k0 + ic);
+}
+
+/* max |F| over the box (worldMax output.c:56-70, sliceMax slices.c:382-394): order independent;
+ * NaNs are skipped exactly like the reference's `if (max < f)`.  *out must be zeroed. */
+__global__ void reduce_absmax(const __grid_constant__ EvalParams p, unsigned *out)
+{
+	const size_t n = (size_t)p.ni*p.nj*p.nk;
+	float m = 0;
+	for (size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x*blockDim.x) {
+		const int ia = (int)(t % p.ni); const size_t r = t / p.ni;
+		const int ib = (int)(r % p.nj), ic = (int)(r / p.nj);
+		const float v = fabsf(mon_eval(&p, p.i0 + ia, p.j0 + ib, p.k0 + ic));
+		if (m < v) m = v;
+	}
+	for (int o = 16; o > 0; o >>= 1) { const float u = __shfl_down_sync(0xffffffffu, m, o); if (m < u) m = u; }
+	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, __float_as_uint(m));     /* non-negative floats order like their bit patterns */
+}
+
+/* one thread per (i,j): the z column sum of worldSum / sliceSum in the reference's order */
+__global__ void column_sums(const __grid_constant__ EvalParams p, float *out)
+{
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= (size_t)p.ni*p.nj) return;
+	const int ia = (int)(t % p.ni), ib = (int)(t / p.ni);
+	float s;
+	MON_COLUMN_SUM(&p, p.dz, p.i0 + ia, p.j0 + ib, p.k0, p.k0 + p.nk - 1, s);
+	out[(size_t)ia*p.nj + ib] = s;
+}

@@ -12,6 +12,7 @@
  * mirror-symmetry parities and the summation order are the reference's, so monitor values agree
  * bit for bit when the fields do.
  */
+#include <string.h>
 #include "alis_c.h"
 #include "host_internal.h"
 
@@ -475,4 +476,123 @@ unsigned alis_field_arrays(world W, field F)
 	if (F == HH || F == UH) return 070;
 	if (F == RI || F == LogRI || F == ContourRI || F == Contour || F == raweEffx || F == raweEffy || F == raweEffz || F == eEff) return 0;
 	return W->complexField ? 07777 : 077;
+}
+
+/* ---- device-side evaluation ---------------------------------------------------------------
+ * The field functions that read E and H only have a twin on the device (alisb_eval_box /
+ * alisb_reduce_absmax / alisb_column_sums, csrc/monitor_eval.h): slices and world reductions of
+ * those move the evaluated values (or one number) instead of the field arrays.  Everything else
+ * (material-dependent quantities, currents, TFSF source/scattered fields, user callbacks) keeps
+ * the host-view path above. */
+static unsigned long device_calls;
+unsigned long alisDeviceMonitorCalls(void) { return device_calls; }
+
+int alis_field_device_fn(world W, field F, alisb_field_fn *d, int *take_log)
+{
+	field *Ec[2][3] = { {Ex, Ey, Ez}, {iEx, iEy, iEz} }, *Hc[2][3] = { {Hx, Hy, Hz}, {iHx, iHy, iHz} };
+	field *rawE[3] = { rawEx, rawEy, rawEz }, *rawH[3] = { rawHx, rawHy, rawHz };
+	field *exh[6] = { ExHy, ExHz, EyHz, EyHx, EzHx, EzHy };
+	static const int exh_ab[6][2] = { {0,1}, {0,2}, {1,2}, {1,0}, {2,0}, {2,1} };
+	field *S[3] = { Sx, Sy, Sz }, *Td[3] = { Txx, Tyy, Tzz };
+	field *To[6] = { Txy, Tyx, Txz, Tzx, Tyz, Tzy };
+	static const int to_ab[6][2] = { {0,1}, {0,1}, {2,0}, {2,0}, {1,2}, {1,2} };
+	memset(d, 0, sizeof *d);
+	*take_log = 0;
+	d->fn = -1;
+	for (int m=0; m<2; m++) for (int c=0; c<3; c++) {
+		if (F == Ec[m][c]) d->fn = ALISB_FN_NODE, d->set = 0, d->comp = c, d->m = m;
+		if (F == Hc[m][c]) d->fn = ALISB_FN_NODE, d->set = 1, d->comp = c, d->m = m;
+	}
+	for (int c=0; c<3; c++) {
+		if (F == rawE[c]) d->fn = ALISB_FN_RAW, d->set = 0, d->comp = c;
+		if (F == rawH[c]) d->fn = ALISB_FN_RAW, d->set = 1, d->comp = c;
+		if (F == S[c])    d->fn = ALISB_FN_S, d->comp = c;
+		if (F == Td[c])   d->fn = ALISB_FN_TDIAG, d->comp = c;
+	}
+	for (int q=0; q<6; q++) {
+		if (F == exh[q]) d->fn = ALISB_FN_EXH, d->comp = exh_ab[q][0], d->comp2 = exh_ab[q][1];
+		if (F == To[q])  d->fn = ALISB_FN_TOFF, d->comp = to_ab[q][0], d->comp2 = to_ab[q][1];
+	}
+	if (F == EE) d->fn = ALISB_FN_EE;
+	if (F == HH) d->fn = ALISB_FN_HH;
+	if (F == UH) d->fn = ALISB_FN_UH;
+	if (F == DivE) d->fn = ALISB_FN_DIVE;
+	if (F == LogEE) d->fn = ALISB_FN_EE, *take_log = 1;
+	if (F == LogHH || F == LogUH) d->fn = ALISB_FN_HH, *take_log = 1;      /* LogUH: sic, as the reference */
+	if (d->fn < 0) return 0;
+	d->sym[0] = W->xMinSur==SYM; d->sym[1] = W->yMinSur==SYM; d->sym[2] = W->zMinSur==SYM;
+	d->cosk[0] = W->coskx; d->cosk[1] = W->cosky; d->cosk[2] = W->coskz;
+	d->org[0] = 1-W->iMIN; d->org[1] = 1-W->jMIN; d->org[2] = 1-W->kMIN;
+	return 1;
+}
+
+/* the index box, mirror images folded back, and the +1 reach of the stencils lie inside the arrays */
+int alis_device_region_ok(world W, const alisb_field_fn *d, const int box[6])
+{
+	const int MIN_[3] = { W->iMIN, W->jMIN, W->kMIN }, MAX_[3] = { W->iMAX, W->jMAX, W->kMAX };
+	const int reach = d->fn == ALISB_FN_RAW ? 0 : 1;
+	for (int a=0; a<3; a++) {
+		int lo = box[2*a], hi = box[2*a+1];
+		if (lo > hi) return 0;
+		if (d->sym[a] && lo < 0) { const int far = MAX(-lo, hi); lo = hi < 0 ? -hi : 0; hi = far; }
+		if (lo < MIN_[a]-1 || hi + reach > MAX_[a]+1) return 0;
+	}
+	return 1;
+}
+
+/* F over the inclusive index box as a dense block (k fastest), evaluated on the device when F has a
+ * device twin, through the host views otherwise.  Caller frees. */
+float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1)
+{
+	const int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
+	if (ni <= 0 || nj <= 0 || nk <= 0) return calloc(1, sizeof(float));
+	float *v = malloc(sizeof(float)*(size_t)ni*nj*nk);
+	if (!v) printf("\nMemory allocation failure\n"), exit(1);
+	alisb_field_fn d;
+	int take_log;
+	const int box[6] = { i0, i1, j0, j1, k0, k1 };
+	if (alis_field_device_fn(W, F, &d, &take_log) && alis_device_region_ok(W, &d, box)) {
+		const int32_t ib[6] = { i0, i1, j0, j1, k0, k1 };
+		alis_bridge_commit(alis_host_bridge(W));                       /* DivE reads the dtd tables */
+		if (alisb_eval_box(alis_bridge_engine(alis_host_bridge(W)), &d, ib, v) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		if (take_log) for (size_t q=0; q<(size_t)ni*nj*nk; q++) v[q] = log10f(v[q]);
+		device_calls++;
+		return v;
+	}
+	int lo[3] = { i0, j0, k0 }, hi[3] = { i1, j1, k1 };
+	const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
+	for (int a=0; a<3; a++) if (sym[a] && lo[a] < 0) { const int far = MAX(-lo[a], hi[a]); lo[a] = hi[a] < 0 ? -hi[a] : 0; hi[a] = far; }
+	alis_view_need_for(W, F, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
+	size_t q = 0;
+	for (int i=i0; i<=i1; i++) for (int j=j0; j<=j1; j++) for (int k=k0; k<=k1; k++) v[q++] = F(W, i, j, k);
+	return v;
+}
+
+/* max |F| over the inclusive index box; on the device when F has a twin there (Log variants are not
+ * monotonic in |.|: host path).  Returns 0 and leaves *out alone when the host path must be used. */
+int alis_device_absmax(world W, field F, const int box[6], float *out)
+{
+	alisb_field_fn d;
+	int take_log;
+	if (!alis_field_device_fn(W, F, &d, &take_log) || take_log || !alis_device_region_ok(W, &d, box)) return 0;
+	const int32_t ib[6] = { box[0], box[1], box[2], box[3], box[4], box[5] };
+	alis_bridge_commit(alis_host_bridge(W));
+	if (alisb_reduce_absmax(alis_bridge_engine(alis_host_bridge(W)), &d, ib, out) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	device_calls++;
+	return 1;
+}
+
+/* z column sums of worldSum / sliceSum for every (i,j) of the box, from the device: cols[(i-i0)*nj +
+ * (j-j0)].  Returns 0 when the host path must be used. */
+int alis_device_column_sums(world W, field F, const int box[6], float *cols)
+{
+	alisb_field_fn d;
+	int take_log;
+	if (!alis_field_device_fn(W, F, &d, &take_log) || take_log || !alis_device_region_ok(W, &d, box)) return 0;
+	if (box[4] < W->kMIN-1 || box[5] > W->kMAX+1) return 0;          /* dz is read at the unfolded index */
+	const int32_t ib[6] = { box[0], box[1], box[2], box[3], box[4], box[5] };
+	alis_bridge_commit(alis_host_bridge(W));
+	if (alisb_column_sums(alis_bridge_engine(alis_host_bridge(W)), &d, ib, cols) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	device_calls++;
+	return 1;
 }

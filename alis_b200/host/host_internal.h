@@ -31,6 +31,12 @@ unsigned alis_field_arrays(world W, field F);   /* bit (m*2+set)*3+comp for ever
 void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* only the arrays F reads */
 void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
 void alis_view_free(world W);
+/* device twins of the field functions (fields.c) */
+int    alis_field_device_fn(world W, field F, alisb_field_fn *d, int *take_log);   /* 1 when F has one   */
+int    alis_device_region_ok(world W, const alisb_field_fn *d, const int box[6]);   /* inclusive INDEX box */
+float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* dense block, k fastest; caller frees */
+int    alis_device_absmax(world W, field F, const int box[6], float *out);          /* 0: use the host path */
+int    alis_device_column_sums(world W, field F, const int box[6], float *cols);    /* 0: use the host path */
 alisb_phaser *alis_phaser_device(phaser P, int *freq);   /* device accumulators + frequency index of P */
 
 #endif

@@ -62,6 +62,8 @@ float get(world W, field F, float x, float y, float z)
 float worldMax(world W, field F)
 {
 	float best = 0, f;
+	const int box[6] = { W->iMin, W->iMax-1, W->jMin, W->jMax-1, W->kMin, W->kMax-1 };
+	if (alis_device_absmax(W, F, box, &best)) return best;              /* reduced on the device: one number comes back */
 	alis_view_need_for(W, F, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
 	for (int i=W->iMin; i<W->iMax; i++) for (int j=W->jMin; j<W->jMax; j++) for (int k=W->kMin; k<W->kMax; k++)
 		if (best < (f=fabsf(F(W, i, j, k)))) best = f;
@@ -87,13 +89,36 @@ static float sheet_sum(world W, field F, int i)
 	return s;
 }
 
+/* the same with the z column sums already formed on the device: cols[(i-iMin)*nj + (j-jMin)] */
+static float sheet_sum_cols(world W, const float *cols, int i)
+{
+	const int nj = W->jMax-W->jMin+1;
+	const float *c = cols + (size_t)(i-W->iMin)*nj - W->jMin;
+	float s = 0;
+	for (int j=W->jMin+1; j<W->jMax; j++) s += W->CE->dy[j] * c[j];
+	s += 0.5 * W->CE->dy[W->jMin] * c[W->jMin];
+	s += 0.5 * W->CE->dy[W->jMax] * c[W->jMax];
+	return s;
+}
+
 float worldSum(world W, field F)
 {
 	float Sum = 0;
+	const int box[6] = { W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax };
+	float *cols = malloc(sizeof(float)*(size_t)(W->iMax-W->iMin+1)*(W->jMax-W->jMin+1));
+	if (cols && alis_device_column_sums(W, F, box, cols)) {              /* one float per z column comes back, not the fields */
+		for (int i=W->iMin+1; i<W->iMax; i++) Sum += W->CE->dx[i] * sheet_sum_cols(W, cols, i);
+		Sum += 0.5 * W->CE->dx[W->iMin] * sheet_sum_cols(W, cols, W->iMin);
+		Sum += 0.5 * W->CE->dx[W->iMax] * sheet_sum_cols(W, cols, W->iMax);
+		free(cols);
+	}
+	else {
+	free(cols);
 	alis_view_need_for(W, F, W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax);
 	for (int i=W->iMin+1; i<W->iMax; i++) Sum += W->CE->dx[i] * sheet_sum(W, F, i);
 	Sum += 0.5 * W->CE->dx[W->iMin] * sheet_sum(W, F, W->iMin);
 	Sum += 0.5 * W->CE->dx[W->iMax] * sheet_sum(W, F, W->iMax);
+	}
 	if (W->xMinSur==SYM) Sum *= 2;
 	if (W->yMinSur==SYM) Sum *= 2;
 	if (W->zMinSur==SYM) Sum *= 2;

@@ -302,12 +302,19 @@ static void expand_name(char *filename, const char *f, const char *s)
 	strcat(strcat(strcat(strcpy(mark, f), "-"), s), rest);
 }
 
+/* F over the slice as a dense block, k fastest (evaluated on the device when F has a twin there) */
+static float *slice_values(world W, field F, slice S)
+{
+	return alis_eval_region(W, F, S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
+}
+
 static float sample(world W, field F, slice S, float ***dst)
 {
-	float max = 0;
-	prefetch(W, F, S);
+	float max = 0, *v = slice_values(W, F, S);
+	size_t q = 0;
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
-		if (max < fabsf(dst[i][j][k] = F(W, i, j, k))) max = fabsf(dst[i][j][k]);
+		if (max < fabsf(dst[i][j][k] = v[q++])) max = fabsf(dst[i][j][k]);
+	free(v);
 	return max;
 }
 
@@ -363,9 +370,13 @@ void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 	if (N) sprintf(string, "%05ld", e->calls / N), strcat(filename, string);
 
 	if (e->calls == 1) e->F = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
-	prefetch(W, F, S);
-	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
-		e->F[i][j][k] += F(W, i, j, k);
+	{
+		float *v = slice_values(W, F, S);
+		size_t q = 0;
+		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
+			e->F[i][j][k] += v[q++];
+		free(v);
+	}
 
 	if (e->calls % N == 0) {
 		float max = 0;
@@ -406,10 +417,14 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 	}
 	float real = cosf(2 * PI * e->calls * W->dt / L);
 	float imag = sinf(2 * PI * e->calls * W->dt / L);
-	prefetch(W, F, S);
-	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++) {
-		e->F[i][j][k] += F(W, i, j, k) * real;
-		e->G[i][j][k] += F(W, i, j, k) * imag;
+	{
+		float *v = slice_values(W, F, S);
+		size_t q = 0;
+		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++, q++) {
+			e->F[i][j][k] += v[q] * real;
+			e->G[i][j][k] += v[q] * imag;
+		}
+		free(v);
 	}
 
 	if (e->calls % N == 0) {
@@ -432,6 +447,8 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 float sliceMax(world W, field F, slice S)
 {
 	float best = 0, f;
+	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
+	if (alis_device_absmax(W, F, box, &best)) return best;
 	prefetch(W, F, S);
 	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
 		if (best < (f=fabsf(F(W, i, j, k)))) best = f;
@@ -456,13 +473,36 @@ static float sheet_sum(world W, field F, slice S, int i)
 	return s;
 }
 
+/* the same with the z column sums already formed on the device: cols[(i-iMin)*nj + (j-jMin)] */
+static float sheet_sum_cols(world W, slice S, const float *cols, int i)
+{
+	const int nj = S->jMax-S->jMin+1;
+	const float *c = cols + (size_t)(i-S->iMin)*nj - S->jMin;
+	float s = 0;
+	for (int j=S->jMin+1; j<S->jMax; j++) s += W->CE->dy[j] * c[j];
+	s += 0.5 * W->CE->dy[S->jMin] * c[S->jMin];
+	s += 0.5 * W->CE->dy[S->jMax] * c[S->jMax];
+	return s;
+}
+
 float sliceSum(world W, field F, slice S)
 {
 	float Sum = 0;
+	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
+	float *cols = malloc(sizeof(float)*(size_t)(S->iMax-S->iMin+1)*(S->jMax-S->jMin+1));
+	if (cols && alis_device_column_sums(W, F, box, cols)) {
+		for (int i=S->iMin+1; i<S->iMax; i++) Sum += W->CE->dx[i] * sheet_sum_cols(W, S, cols, i);
+		Sum += 0.5 * W->CE->dx[S->iMin] * sheet_sum_cols(W, S, cols, S->iMin);
+		Sum += 0.5 * W->CE->dx[S->iMax] * sheet_sum_cols(W, S, cols, S->iMax);
+		free(cols);
+	}
+	else {
+	free(cols);
 	prefetch(W, F, S);
 	for (int i=S->iMin+1; i<S->iMax; i++) Sum += W->CE->dx[i] * sheet_sum(W, F, S, i);
 	Sum += 0.5 * W->CE->dx[S->iMin] * sheet_sum(W, F, S, S->iMin);
 	Sum += 0.5 * W->CE->dx[S->iMax] * sheet_sum(W, F, S, S->iMax);
+	}
 	if (S->iMin==S->iMax) Sum /= W->CE->dx[S->iMin];
 	if (S->jMin==S->jMax) Sum /= W->CE->dy[S->jMin];
 	if (S->kMin==S->kMax) Sum /= W->CE->dz[S->kMin];

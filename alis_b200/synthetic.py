@@ -108,7 +108,8 @@ def pulse_waveform(frequency, deviation, peaktime):
 class BoxWorld:
     """All-PML vacuum box of nx x ny x nz cells (PML included) with an Ez point dipole."""
 
-    def __init__(self, nx, ny, nz, dx=10.0, dt=5.0, num=12, wavelength=400.0, supplement=800.0, amplitude=1.0):
+    def __init__(self, nx, ny, nz, dx=10.0, dt=5.0, num=12, wavelength=400.0, supplement=800.0, amplitude=1.0, complex_field=0):
+        self.complex_field = complex_field             # 1: a second (imaginary) field set, as in Bloch-periodic worlds
         self.ax = [Axis(nx, dx, num), Axis(ny, dx, num), Axis(nz, dx, num)]
         self.n = (nx, ny, nz)
         self.dt, self.num = F(dt), num
@@ -175,7 +176,7 @@ class BoxWorld:
         nzl = c1 - c0 + 1
         off = c0 - 1                                   # local c = global c - off
         g = capi.Grid()
-        g.nx, g.ny, g.nz, g.complex_field, g.dt = nx, ny, nzl, 0, float(self.dt)
+        g.nx, g.ny, g.nz, g.complex_field, g.dt = nx, ny, nzl, self.complex_field, float(self.dt)
         g.kshard_lo, g.nz_global, g.device = c0, nz, device
         pr = self.pml_ranges()
         for s in range(2):

@@ -18,6 +18,8 @@
  *   alisb_phaser_*                         createPhasers/updatePhaser  phaser.c:21-110
  *   alisb_phaser_surface_sums              farFieldX/Y/Z double loops  farfld.c:248-459
  *   alisb_read_box / alisb_write_box       the host float*** views  world.c:58-70
+ *   alisb_eval_box / _reduce_absmax / _column_sums   field functions + slices/world reductions
+ *                                          fields.c:130-681, slices.c:242-427, output.c:56-101
  *
  * Coordinates.  The engine uses ARRAY coordinates: a = i-(iMIN-1), b = j-(jMIN-1),
  * c = k-(kMIN-1), so a runs 0..nx+1 where 1..nx are the updated cells (iMIN..iMAX) and
@@ -223,6 +225,38 @@ int  alisb_set_spacing(alisb_engine *e, int set, int axis, const float *d);
  * n planes (a Poynting box is one call).                                                      */
 typedef struct { int32_t axis, at, b0, b1, c0, c1; } alisb_flux_plane;
 int  alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, double *out);
+
+/* Point-wise field functions evaluated on the device (reference fields.c:130-681, those that read
+ * E and H only), for slices and world reductions (slices.c:242-427, output.c:56-101).            */
+enum {
+	ALISB_FN_RAW   = 0,   /* rawEx..rawHz: set, comp                       fields.c:130-176      */
+	ALISB_FN_NODE  = 1,   /* Ex..Hz, iEx..iHz at the node: set, comp, m     fields.c:179-291      */
+	ALISB_FN_EE    = 2,   /* |E|^2                                         fields.c:453-461      */
+	ALISB_FN_HH    = 3,   /* |H|^2                                         fields.c:476-484      */
+	ALISB_FN_UH    = 4,   /* HH/2                                          fields.c:486          */
+	ALISB_FN_EXH   = 5,   /* E_comp * H_comp2 (ExHy ...)                   fields.c:381-439      */
+	ALISB_FN_S     = 6,   /* Poynting vector component comp                fields.c:483-485      */
+	ALISB_FN_TDIAG = 7,   /* Maxwell stress Txx, Tyy, Tzz: comp            fields.c:564-611      */
+	ALISB_FN_TOFF  = 8,   /* off-diagonal stress, factors comp, comp2      fields.c:613-681      */
+	ALISB_FN_DIVE  = 9    /* div E                                         fields.c:552-562      */
+};
+typedef struct {
+	int32_t fn, set, comp, comp2, m;
+	int32_t sym[3];       /* the axis has a mirror plane at index 0 (W->xMinSur==SYM ...): negative
+	                       * indices fold to their mirror image with the component's parity       */
+	float   cosk[3];      /* W->coskx, W->cosky, W->coskz                                          */
+	int32_t org[3];       /* array coordinate of world index 0: a = i + org[0] (= i-(iMIN-1)) ...  */
+} alisb_field_fn;
+/* ibox: inclusive box in world INDEX coordinates (may be negative on mirror axes).  After folding,
+ * every point and (except for ALISB_FN_RAW) its +1 neighbours must lie inside the arrays.
+ * alisb_eval_box: values into a dense host block, z fastest.  alisb_reduce_absmax: max |F| (NaNs
+ * skipped, like the reference's comparisons).  alisb_column_sums: for every (i,j) the z column sum
+ * of worldSum/sliceSum -- interior points weighted dz[k], then the two ends weighted dz/2, in the
+ * reference's order and promotions (output.c:73-80) -- into host[(i-i0)*nj + (j-j0)]; needs
+ * alisb_set_spacing(e, ALISB_SET_E, ALISB_Z, ...) and a k range inside the arrays.              */
+int  alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
+int  alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out);
+int  alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
 
 /* ---- z-slab halo (multi-GPU) -------------------------------------------- */
 /* Buffers (device memory for the CUDA engine) holding one full z-plane incl. ghosts of

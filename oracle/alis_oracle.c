@@ -591,6 +591,75 @@ int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, dou
 	return ALISB_OK;
 }
 
+/* ---- point-wise field functions, slices and world reductions: reference fields.c:130-681 through
+ * the shared restatement alis_b200/csrc/monitor_eval.h, looped like slices.c:382-394 (max) and
+ * output.c:73-80 (z column sums) ---------------------------------------------------------------- */
+typedef struct { alisb_engine *e; const alisb_field_fn *f; } mon_ctx;
+#define MON_FN static inline
+#define MON_CTX mon_ctx
+#define MON_DESC(X) ((X)->f)
+#define MON_LD(X,set,m,c,a,b,cc) ((X)->e->F[set][m][c][IDX((X)->e, a, b, cc)])
+#define MON_DTD(X,axis,q) ((X)->e->dtd[0][axis][q])
+#define MON_DT(X) ((X)->e->g.dt)
+#define MON_COMPLEX(X) ((X)->e->g.complex_field)
+#include "../alis_b200/csrc/monitor_eval.h"
+
+static int eval_check(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], int columns)
+{
+	if (!f || !ibox) return fail(ALISB_EINVAL, "eval: null argument");
+	if (f->fn < ALISB_FN_RAW || f->fn > ALISB_FN_DIVE || f->set<0 || f->set>1 || f->comp<0 || f->comp>2 || f->comp2<0 || f->comp2>2 || f->m<0 || f->m>1)
+		return fail(ALISB_EINVAL, "eval: bad field function");
+	if ((f->fn == ALISB_FN_EXH || f->fn == ALISB_FN_TOFF) && f->comp == f->comp2) return fail(ALISB_EINVAL, "eval: the two components must differ");
+	if (f->m > e->g.complex_field && f->fn != ALISB_FN_NODE) return fail(ALISB_EINVAL, "eval: no such field set");
+	const int reach = f->fn == ALISB_FN_RAW ? 0 : 1;
+	for (int ax=0; ax<3; ax++) {
+		int lo = ibox[2*ax], hi = ibox[2*ax+1];
+		if (lo > hi) return fail(ALISB_EINVAL, "eval: empty box");
+		if (columns && ax == 2 && (lo + f->org[2] < 0 || hi + f->org[2] > e->n[2] + 1)) return fail(ALISB_EINVAL, "eval: column range outside the spacing table");
+		if (f->sym[ax] && lo < 0) { const int far = -lo > hi ? -lo : hi; lo = hi < 0 ? -hi : 0; hi = far; }
+		if (lo + f->org[ax] < 0 || hi + f->org[ax] + reach > e->n[ax] + 1) return fail(ALISB_EINVAL, "eval: box outside the arrays");
+	}
+	if (columns && !e->spacing[0][2]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
+	return ALISB_OK;
+}
+
+int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
+{
+	int rc = eval_check(e, f, ibox, 0);
+	if (rc) return rc;
+	const mon_ctx X = { e, f };
+	size_t q = 0;
+	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++) host[q++] = mon_eval(&X, i, j, k);
+	return ALISB_OK;
+}
+
+int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out)
+{
+	int rc = eval_check(e, f, ibox, 0);
+	if (rc) return rc;
+	const mon_ctx X = { e, f };
+	float max = 0, v;
+	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++)
+		if (max < (v = fabsf(mon_eval(&X, i, j, k)))) max = v;
+	*out = max;
+	return ALISB_OK;
+}
+
+int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
+{
+	int rc = eval_check(e, f, ibox, 1);
+	if (rc) return rc;
+	const mon_ctx X = { e, f };
+	const float *dz = e->spacing[0][2];
+	size_t q = 0;
+	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) {
+		float s;
+		MON_COLUMN_SUM(&X, dz, i, j, ibox[4], ibox[5], s);
+		host[q++] = s;
+	}
+	return ALISB_OK;
+}
+
 /* ---- halo ------------------------------------------------------------------------------ */
 /* ---- chi2 mixing: reference update.c:344-411 (coupleTWM), sweep by sweep ---------------------- */
 static double chi2_at(alisb_engine *g, int m, int u, int v, int a, int b, int c)
@@ -731,15 +800,19 @@ int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which, float *hos
 int alisb_phaser_surface_sums(alisb_phaser *p, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out)
 {
 	if (!p || freq<0 || freq>=p->nfreq || njobs<0) return fail(ALISB_EINVAL, "bad surface-sum request");
+	for (int q=0; q<njobs; q++) {
+		const alisb_surface_job *J = &jobs[q];
+		if (J->face<0 || J->face>5 || J->which<0 || J->which>3 || !(p->mask & (1<<J->face))) return fail(ALISB_EINVAL, "surface sum: face is not accumulated");
+		const block *B = &p->acc[J->face][J->which];
+		const int ax = J->face/2;
+		if ((size_t)J->w_lo + B->n[ax==0 ? 1 : 0] > nweights || (size_t)J->w_hi + B->n[ax==2 ? 1 : 2] > nweights) return fail(ALISB_EINVAL, "surface sum: weight vector outside the buffer");
+	}
 	#pragma omp parallel for schedule(static)
 	for (int q=0; q<njobs; q++) {
 		const alisb_surface_job *J = &jobs[q];
-		out[2*q] = out[2*q+1] = 0;
-		if (J->face<0 || J->face>5 || J->which<0 || J->which>3 || !(p->mask & (1<<J->face))) continue;
 		const block *B = &p->acc[J->face][J->which];
 		const int ax = J->face/2, lo = ax==0 ? 1 : 0, hi = ax==2 ? 1 : 2;
 		const int nlo = B->n[lo], nhi = B->n[hi];
-		if ((size_t)J->w_lo + nlo > nweights || (size_t)J->w_hi + nhi > nweights) continue;
 		const size_t cells = (size_t)B->n[0]*B->n[1]*B->n[2];
 		const float *A = B->v + 2*cells*freq, *Wlo = weights + 2*(size_t)J->w_lo, *Whi = weights + 2*(size_t)J->w_hi;
 		double sr = 0, si = 0;

@@ -11,6 +11,23 @@
 
 static void emit(const char *tag, double v) { printf("%-28s % .9g\n", tag, v); }
 
+/* a slice "writer" that prints checksums of the sampled slice instead of a file: user-supplied
+ * methods are part of the API (sliceSnap only special-cases png) */
+static void checksum(world W, slice S, float Max, char *F, char *filename, unsigned long int *cmap)
+{
+	double s1 = 0, s2 = 0; long bad = 0;
+	char tag[64];
+	(void)W; (void)filename; (void)cmap;
+	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++) {
+		const float v = S->F[i][j][k];
+		if (isfinite(v)) s1 += v, s2 += (double)v*v; else bad++;
+	}
+	sprintf(tag, "snap_%s_sum", F); emit(tag, s1);
+	sprintf(tag, "snap_%s_sq", F); emit(tag, s2);
+	sprintf(tag, "snap_%s_bad", F); emit(tag, bad);
+	sprintf(tag, "snap_%s_max", F); emit(tag, isfinite(Max) ? Max : -1);
+}
+
 int main(int argc, char **argv)
 {
 	if (argc < 3) { printf("usage: %s <config> <steps> [outdir]\n", argv[0]); return 2; }
@@ -54,6 +71,36 @@ int main(int argc, char **argv)
 	emit("sliceMax_XY_EE", sliceMax(W, EE, XY)); emit("sliceSum_XZ_U", sliceSum(W, U, XZ));
 	emit("poyntingX", poyntingX(W, 100)); emit("poyntingY", poyntingY(W, 50, -100, 100, -80, 120)); emit("poyntingZ", poyntingZ(W, 100, -150, 150));
 	emit("poyntingOut", poyntingOut(W, -120, 120, 20, 120, -100, 140));
+	/* slices and world reductions of the field functions (evaluated on the device by alis-b200) */
+	{
+		struct { const char *name; field *F; } fn[] = {
+			{"rawEx", rawEx}, {"rawEz", rawEz}, {"rawHy", rawHy}, {"Ex", Ex}, {"Ey", Ey}, {"Ez", Ez}, {"Hx", Hx}, {"Hy", Hy}, {"Hz", Hz},
+			{"iEx", iEx}, {"iHz", iHz}, {"EE", EE}, {"HH", HH}, {"UH", UH}, {"ExHy", ExHy}, {"EyHx", EyHx}, {"EzHx", EzHx}, {"ExHz", ExHz},
+			{"Sx", Sx}, {"Sy", Sy}, {"Sz", Sz}, {"Txx", Txx}, {"Tyy", Tyy}, {"Tzz", Tzz}, {"Txy", Txy}, {"Tyz", Tyz}, {"Tzx", Tzx},
+			{"DivE", DivE}, {"U", U}, {"ScEx", ScEx}
+		};
+		slice YZ = createSliceYZ(W, 0);
+		char tag[64];
+		for (unsigned q=0; q<sizeof fn/sizeof fn[0]; q++) {
+			sprintf(tag, "worldMax_%s", fn[q].name); emit(tag, worldMax(W, fn[q].F));
+			sprintf(tag, "worldSum_%s", fn[q].name); emit(tag, worldSum(W, fn[q].F));
+			sprintf(tag, "sliceMax_XZ_%s", fn[q].name); emit(tag, sliceMax(W, fn[q].F, XZ));
+			sprintf(tag, "sliceSum_XY_%s", fn[q].name); emit(tag, sliceSum(W, fn[q].F, XY));
+			sprintf(tag, "sliceSum_YZ_%s", fn[q].name); emit(tag, sliceSum(W, fn[q].F, YZ));
+		}
+		sliceSnap(W, Ez, XY, 0, checksum, "chk-%%");
+		sliceSnap(W, Hx, YZ, 0, checksum, "chk-%%");
+		sliceSnap(W, rawHz, XZ, 0, checksum, "chk-%%");
+		sliceSnap(W, EE, XZ, 0, checksum, "chk-%%");
+		sliceSnap(W, LogEE, XY, 0, checksum, "chk-%%");
+		sliceSnap(W, LogHH, YZ, 0, checksum, "chk-%%");
+		sliceSnap(W, Sz, XY, 0, checksum, "chk-%%");
+		sliceSnap(W, Txy, XZ, 0, checksum, "chk-%%");
+		sliceSnap(W, DivE, YZ, 0, checksum, "chk-%%");
+		sliceSnap(W, iEy, XY, 0, checksum, "chk-%%");
+		sliceSnap(W, U, XY, 0, checksum, "chk-%%");
+		for (int r=0; r<3; r++) { sliceTimeAvg(W, HH, XY, 3, checksum, "avg-%%"); sliceFreqDom(W, Ex, XZ, 3, 500, checksum, "dft-%%"); }
+	}
 	if (is_nano) { emit("flux_in", flux_in); emit("flux_out", flux_out); emit("absorption", absn); }
 	if (P) {
 		phaser Q = is_band ? choosePhaser(P, 500) : P;
@@ -68,6 +115,9 @@ int main(int argc, char **argv)
 		for (int x=0; x<24; x++) for (int y=0; y<12; y++) { float ang[2]; AzimuthalMap(x, y, 24, 12, ang); acc += farFieldI(Q, Unpol, ang[0], ang[1]); }
 		emit("ff_map_sum", acc);
 	}
+#ifdef HARNESS_MODE_MINE
+	fprintf(stderr, "device_monitor_calls %lu\n", alisDeviceMonitorCalls());
+#endif
 	if (argc > 3) {
 		sliceSnap(W, Ez, XY, 0, txt, "/snap-%%");
 		sliceSnap(W, EE, XZ, 0, png(hot,0), "/snap-%%");
