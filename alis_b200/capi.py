@@ -96,6 +96,7 @@ def _declare(lib):
         "alisb_eval_box": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_reduce_absmax": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_column_sums": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
+        "alisb_absorption_columns": (i, [vp, i, i32p, f32p]),
         "alisb_chi2_couple": (i, [vp, i, i, vp, vp, f32p, f]),
         "alisb_set_fusion": (i, [vp, i]),
         "alisb_flush": (i, [vp, i]),
@@ -328,6 +329,12 @@ class Engine:
     def column_sums(self, f, ibox):
         out = np.empty((ibox[1] - ibox[0] + 1, ibox[3] - ibox[2] + 1), np.float32)
         self._ck(self.lib.alisb_column_sums(self.h, C.byref(f), _ip(ibox), _fp(out)))
+        return out
+
+    def absorption_columns(self, obj, box):
+        """(na, nb, 3): the z sums xs, ys, zs of E.J per column of ADE object obj (output.c:375-404)"""
+        out = np.empty((box[1] - box[0] + 1, box[3] - box[2] + 1, 3), np.float32)
+        self._ck(self.lib.alisb_absorption_columns(self.h, obj, _ip(box), _fp(out)))
         return out
 
     def set_fusion(self, on):

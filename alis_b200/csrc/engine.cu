@@ -1561,6 +1561,39 @@ extern "C" int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const
 	return ALISB_OK;
 }
 
+extern "C" int alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], float *host)
+{
+	if (!box || !host) return fail(ALISB_EINVAL, "absorption: null argument");
+	if (obj < 0 || obj >= (int)e->obj.size()) return fail(ALISB_EINVAL, "absorption: no such object");
+	if (!e->eps[0] || !e->eps[1] || !e->eps[2]) return fail(ALISB_ESTATE, "absorption: no material arrays");
+	if (!e->spacing[0][2] || !e->spacing[1][2]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
+	DEV(e);
+	const DispObj *o = e->obj[obj];
+	const Box &B = o->full;
+	if (box[0] > box[1] || box[2] > box[3] || box[4] > box[5] ||
+	    box[0] < std::max(B.a0, 1) || box[1] > std::min(B.a0 + B.na - 1, e->nx) || box[2] < std::max(B.b0, 1) || box[3] > std::min(B.b0 + B.nb - 1, e->ny) ||
+	    box[4] < std::max(B.c0, 1) || box[5] > std::min(B.c0 + B.nc - 1, e->nz)) return fail(ALISB_EINVAL, "absorption: box outside the object");
+	SETTLE(e);
+	EvalParams p;
+	memset(&p, 0, sizeof p);
+	for (int c=0; c<3; c++) {
+		p.F[0][0][c] = e->F[0][0][c]; p.inv[c] = e->eps[c]; p.fill[c] = o->fill[c]; p.loss[c] = o->d.a[c];
+		for (int q=0; q<o->d.nk; q++) p.J[q][c] = o->J[0][q][c];
+	}
+	p.npoles = o->d.nk; p.full = B; p.dz = e->spacing[0][2]; p.dzH = e->spacing[1][2];
+	p.ny = e->ny; p.pitch = e->pitch;
+	p.i0 = box[0]; p.j0 = box[2]; p.k0 = box[4];
+	p.ni = box[1]-box[0]+1; p.nj = box[3]-box[2]+1; p.nk = box[5]-box[4]+1;
+	const size_t n = (size_t)p.ni*p.nj;
+	TRY(need_scratch(e, 3*n));
+	absorption_columns<<<div_up(n, 128), 128, 0, e->stream>>>(p, 1, e->nz, e->scratch);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(host, e->scratch, 3*n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	e->launches++;
+	return ALISB_OK;
+}
+
 /* ---- halo: planes are contiguous in this layout, hand out pointers into the arrays -------- */
 extern "C" int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes)
 {

@@ -954,6 +954,11 @@ struct EvalParams {
 	int ny, pitch, complex_field;
 	float dt;
 	int i0, j0, k0, ni, nj, nk;       /* the box, world INDEX coordinates                    */
+	/* objectAbsorption columns only: */
+	const float *inv[3], *fill[3], *J[ALISB_MAXPOLES][3];
+	const float *dzH;
+	float loss[3]; int npoles;
+	Box full;                         /* the object's dense ADE box                          */
 };
 #define MON_FN static __device__ __forceinline__
 #define MON_CTX EvalParams
@@ -962,6 +967,15 @@ struct EvalParams {
 #define MON_DTD(X,axis,q) ((axis) == 0 ? (X)->dtd[0][ALISB_XO + (q)] : (X)->dtd[axis][q])
 #define MON_DT(X) ((X)->dt)
 #define MON_COMPLEX(X) ((X)->complex_field)
+#define MON_GIDX(X,a,b,cc) (((size_t)(cc)*((X)->ny+2) + (size_t)(b))*(X)->pitch + ALISB_XO + (a))
+#define MON_OIDX(X,a,b,cc) (((size_t)((cc) - (X)->full.c0)*(X)->full.nb + ((b) - (X)->full.b0))*(X)->full.na + ((a) - (X)->full.a0))
+#define MON_INV(X,c,a,b,cc) ((X)->inv[c][MON_GIDX(X,a,b,cc)])
+#define MON_FILL(X,c,a,b,cc) ((X)->fill[c][MON_OIDX(X,a,b,cc)])
+#define MON_J(X,p,c,a,b,cc) ((X)->J[p][c][MON_OIDX(X,a,b,cc)])
+#define MON_NPOLES(X) ((X)->npoles)
+#define MON_LOSS(X,c) ((X)->loss[c])
+#define MON_DZE(X,cc) ((X)->dz[cc])
+#define MON_DZH(X,cc) ((X)->dzH[cc])
 #include "monitor_eval.h"
 
 /* out: dense block in the HOST order (z fastest), like box_gather */
@@ -999,4 +1013,19 @@ __global__ void column_sums(const __grid_constant__ EvalParams p, float *out)
 	float s;
 	MON_COLUMN_SUM(&p, p.dz, p.i0 + ia, p.j0 + ib, p.k0, p.k0 + p.nk - 1, s);
 	out[(size_t)ia*p.nj + ib] = s;
+}
+
+/* objectAbsorption (output.c:365-435): one thread per (a,b) column of the object's box, (xs, ys, zs)
+ * per column; the host applies the reference's edge weights and sums in its order.  Box: array
+ * coordinates (i0,j0 = first column; k0..k0+nk-1 = planes); cmin/cmax: the world's first/last plane. */
+__global__ void absorption_columns(const __grid_constant__ EvalParams p, int cmin, int cmax, float *out)
+{
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= (size_t)p.ni*p.nj) return;
+	const int ia = (int)(t % p.ni), ib = (int)(t / p.ni);
+	const int a = p.i0 + ia, b = p.j0 + ib;
+	float xs, ys, zs;
+	MON_ABSORPTION_COLUMN(&p, a, b, p.k0, p.k0 + p.nk - 1, cmin, cmax, xs, ys, zs);
+	float *o = out + 3*((size_t)ia*p.nj + ib);
+	o[0] = xs; o[1] = ys; o[2] = zs;
 }

@@ -155,4 +155,41 @@ MON_FN float mon_eval(const MON_CTX *X, int i, int j, int k)
 	(result) = Sum_; \
 } while (0)
 
+/* one z column of objectAbsorption (output.c:23-47 rawJ, :375-404 partialAbsorption): the three
+ * sums xs, ys, zs of E.J over the planes c0..c1 of ADE object n at array coordinates (a,b), with
+ * the half-weight corrections at the world's first / last plane.  The includer also defines
+ *   MON_INV(X,c,a,b,cc)  inverse permittivity     MON_FILL(X,c,a,b,cc)  fill factor of the object
+ *   MON_J(X,p,c,a,b,cc)  polarisation current p   MON_NPOLES(X), MON_LOSS(X,c)  NK and ax/ay/az
+ *   MON_DZE(X,cc), MON_DZH(X,cc)  CE->dz, CH->dz at array coordinate cc                          */
+#ifdef MON_INV
+MON_FN float mon_object_current(const MON_CTX *X, int c, int a, int b, int cc)
+{
+	const float loss = MON_LOSS(X, c);
+	float f = 0;
+	if (loss) f += 2 * MON_FILL(X,c,a,b,cc) * MON_LD(X,0,0,c,a,b,cc) / (1 + 1 / loss);
+	for (int p=0; p<MON_NPOLES(X); p++) f += MON_J(X,p,c,a,b,cc);
+	return f / MON_INV(X,c,a,b,cc);
+}
+#define MON_ABSORPTION_COLUMN(X, a, b, c0, c1, cMIN, cMAX, xs, ys, zs) do { \
+	float xs_ = 0, ys_ = 0, zs_ = 0; \
+	for (int c_ = (c0); c_ <= (c1); c_++) { \
+		if (MON_INV(X,0,a,b,c_)) xs_ += MON_DZE(X,c_) * MON_LD(X,0,0,0,a,b,c_) * mon_object_current(X, 0, a, b, c_); \
+		if (MON_INV(X,1,a,b,c_)) ys_ += MON_DZE(X,c_) * MON_LD(X,0,0,1,a,b,c_) * mon_object_current(X, 1, a, b, c_); \
+		if (MON_INV(X,2,a,b,c_)) zs_ += MON_DZH(X,c_) * MON_LD(X,0,0,2,a,b,c_) * mon_object_current(X, 2, a, b, c_); \
+	} \
+	if ((c0) == (cMIN)) { \
+		const int c_ = (cMIN); \
+		if (MON_INV(X,0,a,b,c_)) xs_ -= MON_DZE(X,c_) * MON_LD(X,0,0,0,a,b,c_) * mon_object_current(X, 0, a, b, c_) * 0.5; \
+		if (MON_INV(X,1,a,b,c_)) ys_ -= MON_DZE(X,c_) * MON_LD(X,0,0,1,a,b,c_) * mon_object_current(X, 1, a, b, c_) * 0.5; \
+		if (MON_INV(X,2,a,b,c_)) zs_ -= MON_DZH(X,c_) * MON_LD(X,0,0,2,a,b,c_) * mon_object_current(X, 2, a, b, c_); \
+	} \
+	if ((c1) == (cMAX)) { \
+		const int c_ = (cMAX); \
+		if (MON_INV(X,0,a,b,c_)) xs_ -= MON_DZE(X,c_) * MON_LD(X,0,0,0,a,b,c_) * mon_object_current(X, 0, a, b, c_) * 0.5; \
+		if (MON_INV(X,1,a,b,c_)) ys_ -= MON_DZE(X,c_) * MON_LD(X,0,0,1,a,b,c_) * mon_object_current(X, 1, a, b, c_) * 0.5; \
+	} \
+	(xs) = xs_; (ys) = ys_; (zs) = zs_; \
+} while (0)
+#endif
+
 #endif

@@ -32,6 +32,7 @@ void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0
 void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
 void alis_view_free(world W);
 /* device twins of the field functions (fields.c) */
+int    alis_host_monitors(void);                       /* env ALIS_HOST_MONITORS=1: host-view path only */
 int    alis_field_device_fn(world W, field F, alisb_field_fn *d, int *take_log);   /* 1 when F has one   */
 int    alis_device_region_ok(world W, const alisb_field_fn *d, const int box[6]);   /* inclusive INDEX box */
 float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* dense block, k fastest; caller frees */

@@ -377,10 +377,11 @@ static float object_current(world W, int c, int n, int i, int j, int k)
 	return f / inv[i][j][k];
 }
 
-static float column_absorption(world W, int n, int i, int j, float x, float y, float z)
+/* the three z sums of E.J of one column (reference output.c:375-404, before the x,y weights) */
+static void column_sums_host(world W, int n, int i, int j, float out[3])
 {
 	coeffs *C = W->CE;
-	float Sum = 0, xs = 0, ys = 0, zs = 0;
+	float xs = 0, ys = 0, zs = 0;
 	const int k0 = MAX(W->kMIN, C->kMin[n]), k1 = MIN(W->kMAX, C->kMax[n]);
 
 	for (int k=k0; k<=k1; k++) {
@@ -399,9 +400,23 @@ static float column_absorption(world W, int n, int i, int j, float x, float y, f
 		if (C->x[i][j][k]) xs -= C->dz[k] * W->E->x[i][j][k] * object_current(W, 0, n, i, j, k) * 0.5;
 		if (C->y[i][j][k]) ys -= C->dz[k] * W->E->y[i][j][k] * object_current(W, 1, n, i, j, k) * 0.5;
 	}
-	Sum += x * xs * W->CH->dx[i] * C->dy[j];
-	Sum += y * ys * C->dx[i] * W->CH->dy[j];
-	Sum += z * zs * C->dx[i] * C->dy[j];
+	out[0] = xs; out[1] = ys; out[2] = zs;
+}
+
+/* columns of the object's box: from the device (alisb_absorption_columns: three floats per column
+ * come back instead of the E, J and material arrays), or from the host views */
+typedef struct { world W; int n, i0, j0, nj; float *dev; } abs_cols;
+
+static float column_absorption(const abs_cols *A, int i, int j, float x, float y, float z)
+{
+	world W = A->W;
+	coeffs *C = W->CE;
+	float s[3], Sum = 0;
+	if (A->dev) memcpy(s, A->dev + 3*((size_t)(i-A->i0)*A->nj + (j-A->j0)), sizeof s);
+	else column_sums_host(W, A->n, i, j, s);
+	Sum += x * s[0] * W->CH->dx[i] * C->dy[j];
+	Sum += y * s[1] * C->dx[i] * W->CH->dy[j];
+	Sum += z * s[2] * C->dx[i] * C->dy[j];
 	return Sum;
 }
 
@@ -413,28 +428,43 @@ float objectAbsorption(world W, object O)
 	for (int o=0; !same_object(O, C->O[o]); o++) if (needs_aux(C->M[o])) n++;
 	const int i0 = MAX(W->iMIN, C->iMin[n]), i1 = MIN(W->iMAX, C->iMax[n]);
 	const int j0 = MAX(W->jMIN, C->jMin[n]), j1 = MIN(W->jMAX, C->jMax[n]);
-	alis_view_need(W, i0, i1, j0, j1, MAX(W->kMIN, C->kMin[n]), MIN(W->kMAX, C->kMax[n]));
-	alis_view_need_ade(W);
+	const int k0 = MAX(W->kMIN, C->kMin[n]), k1 = MIN(W->kMAX, C->kMax[n]);
+	abs_cols A = { W, n, i0, j0, j1-j0+1, 0 };
+	if (i0 > i1 || j0 > j1 || k0 > k1) return 0;
+	if (!alis_host_monitors()) {
+		alis_bridge *B = alis_host_bridge(W);
+		alis_bridge_commit(B);
+		const int32_t box[6] = { i0-(W->iMIN-1), i1-(W->iMIN-1), j0-(W->jMIN-1), j1-(W->jMIN-1), k0-(W->kMIN-1), k1-(W->kMIN-1) };
+		A.dev = malloc(sizeof(float)*3*(size_t)(i1-i0+1)*(j1-j0+1));
+		if (!A.dev) printf("\nMemory allocation failure\n"), exit(1);
+		if (alisb_absorption_columns(alis_bridge_engine(B), n, box, A.dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	}
+	else {
+		alis_view_need(W, i0, i1, j0, j1, k0, k1);
+		alis_view_need_ade(W);
+	}
 
 	for (int i=i0; i<=i1; i++) {
-		for (int j=j0; j<=j1; j++) Sum += column_absorption(W, n, i, j, 1, 1, 1);
-		if (j0 == W->jMIN) Sum += column_absorption(W, n, i, W->jMIN,-0.5,-1,-0.5);
-		if (j1 == W->jMAX) Sum += column_absorption(W, n, i, W->jMAX,-0.5, 0,-0.5);
+		for (int j=j0; j<=j1; j++) Sum += column_absorption(&A, i, j, 1, 1, 1);
+		if (j0 == W->jMIN) Sum += column_absorption(&A, i, W->jMIN,-0.5,-1,-0.5);
+		if (j1 == W->jMAX) Sum += column_absorption(&A, i, W->jMAX,-0.5, 0,-0.5);
 	}
 	if (i0 == W->iMIN) {                         /* (separate partial sums: see plane_flux) */
 		float part = 0;
-		for (int j=j0; j<=j1; j++) part += column_absorption(W, n, W->iMIN, j,-1,-0.5,-0.5);
+		for (int j=j0; j<=j1; j++) part += column_absorption(&A, W->iMIN, j,-1,-0.5,-0.5);
 		Sum += part;
-		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMIN, W->jMIN, 0.5, 0.5, 0.25);
-		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMIN, W->jMAX, 0.5, 0.0, 0.25);
+		if (j0 == W->jMIN) Sum += column_absorption(&A, W->iMIN, W->jMIN, 0.5, 0.5, 0.25);
+		if (j1 == W->jMAX) Sum += column_absorption(&A, W->iMIN, W->jMAX, 0.5, 0.0, 0.25);
 	}
 	if (i1 == W->iMAX) {
 		float part = 0;
-		for (int j=j0; j<=j1; j++) part += column_absorption(W, n, W->iMAX, j, 0,-0.5,-0.5);
+		for (int j=j0; j<=j1; j++) part += column_absorption(&A, W->iMAX, j, 0,-0.5,-0.5);
 		Sum += part;
-		if (j0 == W->jMIN) Sum += column_absorption(W, n, W->iMAX, W->jMIN, 0.0, 0.5, 0.25);
-		if (j1 == W->jMAX) Sum += column_absorption(W, n, W->iMAX, W->jMAX, 0.0, 0.0, 0.25);
+		if (j0 == W->jMIN) Sum += column_absorption(&A, W->iMAX, W->jMIN, 0.0, 0.5, 0.25);
+		if (j1 == W->jMAX) Sum += column_absorption(&A, W->iMAX, W->jMAX, 0.0, 0.0, 0.25);
 	}
+
+	free(A.dev);
 
 	if (W->Dom.x.Min==W->Dom.x.Max) Sum /= W->CH->dx[W->iMax]+W->CH->dx[W->iMax-1];
 	if (W->Dom.y.Min==W->Dom.y.Max) Sum /= W->CH->dy[W->jMax]+W->CH->dy[W->jMax-1];

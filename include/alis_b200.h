@@ -257,6 +257,13 @@ typedef struct {
 int  alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
 int  alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out);
 int  alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
+/* objectAbsorption (reference output.c:23-47,365-435): for ADE object `obj` (index in add order) and
+ * every column (a,b) of box[0..3] (ARRAY coordinates, inside the object's box) the three z sums
+ * xs, ys, zs of E.J over the planes box[4]..box[5], including the half-weight corrections at the
+ * world's first / last plane (array coordinate 1 / nz): host[((a-a0)*nb + (b-b0))*3 + {0,1,2}].
+ * Needs alisb_set_inv_eps and the z spacing tables of both field sets.  The host applies the
+ * reference's edge weights in x,y and adds the columns in its order.                          */
+int  alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], float *host);
 
 /* ---- z-slab halo (multi-GPU) -------------------------------------------- */
 /* Buffers (device memory for the CUDA engine) holding one full z-plane incl. ghosts of

@@ -594,7 +594,7 @@ int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, dou
 /* ---- point-wise field functions, slices and world reductions: reference fields.c:130-681 through
  * the shared restatement alis_b200/csrc/monitor_eval.h, looped like slices.c:382-394 (max) and
  * output.c:73-80 (z column sums) ---------------------------------------------------------------- */
-typedef struct { alisb_engine *e; const alisb_field_fn *f; } mon_ctx;
+typedef struct { alisb_engine *e; const alisb_field_fn *f; const dispobj *o; } mon_ctx;
 #define MON_FN static inline
 #define MON_CTX mon_ctx
 #define MON_DESC(X) ((X)->f)
@@ -602,6 +602,13 @@ typedef struct { alisb_engine *e; const alisb_field_fn *f; } mon_ctx;
 #define MON_DTD(X,axis,q) ((X)->e->dtd[0][axis][q])
 #define MON_DT(X) ((X)->e->g.dt)
 #define MON_COMPLEX(X) ((X)->e->g.complex_field)
+#define MON_INV(X,c,a,b,cc) ((X)->e->eps[c][IDX((X)->e, a, b, cc)])
+#define MON_FILL(X,c,a,b,cc) ((X)->o->fill[c].v[bidx(&(X)->o->fill[c], a, b, cc)])
+#define MON_J(X,p,c,a,b,cc) ((X)->o->J[0][p][c].v[bidx(&(X)->o->J[0][p][c], a, b, cc)])
+#define MON_NPOLES(X) ((X)->o->nk)
+#define MON_LOSS(X,c) ((X)->o->a[c])
+#define MON_DZE(X,cc) ((X)->e->spacing[0][2][cc])
+#define MON_DZH(X,cc) ((X)->e->spacing[1][2][cc])
 #include "../alis_b200/csrc/monitor_eval.h"
 
 static int eval_check(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], int columns)
@@ -627,7 +634,7 @@ int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[
 {
 	int rc = eval_check(e, f, ibox, 0);
 	if (rc) return rc;
-	const mon_ctx X = { e, f };
+	const mon_ctx X = { e, f, 0 };
 	size_t q = 0;
 	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++) host[q++] = mon_eval(&X, i, j, k);
 	return ALISB_OK;
@@ -637,7 +644,7 @@ int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t 
 {
 	int rc = eval_check(e, f, ibox, 0);
 	if (rc) return rc;
-	const mon_ctx X = { e, f };
+	const mon_ctx X = { e, f, 0 };
 	float max = 0, v;
 	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++)
 		if (max < (v = fabsf(mon_eval(&X, i, j, k)))) max = v;
@@ -649,13 +656,35 @@ int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ib
 {
 	int rc = eval_check(e, f, ibox, 1);
 	if (rc) return rc;
-	const mon_ctx X = { e, f };
+	const mon_ctx X = { e, f, 0 };
 	const float *dz = e->spacing[0][2];
 	size_t q = 0;
 	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) {
 		float s;
 		MON_COLUMN_SUM(&X, dz, i, j, ibox[4], ibox[5], s);
 		host[q++] = s;
+	}
+	return ALISB_OK;
+}
+
+int alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], float *host)
+{
+	if (!box || !host) return fail(ALISB_EINVAL, "absorption: null argument");
+	if (obj < 0 || obj >= e->nobj) return fail(ALISB_EINVAL, "absorption: no such object");
+	if (!e->eps[0] || !e->eps[1] || !e->eps[2]) return fail(ALISB_ESTATE, "absorption: no material arrays");
+	if (!e->spacing[0][2] || !e->spacing[1][2]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
+	const dispobj *o = e->obj[obj];
+	for (int d=0; d<3; d++) {
+		const int lo = o->bx.lo[d] > 1 ? o->bx.lo[d] : 1, hi = o->bx.hi[d] < e->n[d] ? o->bx.hi[d] : e->n[d];
+		if (box[2*d] > box[2*d+1] || box[2*d] < lo || box[2*d+1] > hi) return fail(ALISB_EINVAL, "absorption: box outside the object");
+	}
+	static const alisb_field_fn none;
+	const mon_ctx X = { e, &none, o };
+	size_t q = 0;
+	for (int a=box[0]; a<=box[1]; a++) for (int b=box[2]; b<=box[3]; b++) {
+		float xs, ys, zs;
+		MON_ABSORPTION_COLUMN(&X, a, b, box[4], box[5], 1, e->n[2], xs, ys, zs);
+		host[q++] = xs; host[q++] = ys; host[q++] = zs;
 	}
 	return ALISB_OK;
 }

@@ -22,10 +22,15 @@ def have_test_bin(name):
     return os.path.exists(os.path.join(TEST_BIN, name))
 
 
-def run_monitors(binary, config, threads=None, steps=0):
-    """runs oracle/harness/monitors.c (reference- or own-library build) -> ordered [(tag, text value)]"""
+def run_monitors(binary, config, threads=None, steps=0, host_monitors=False):
+    """runs oracle/harness/monitors.c (reference- or own-library build) -> ordered [(tag, text value)]
+    host_monitors: ALIS_HOST_MONITORS=1, i.e. every monitor through the host views instead of the
+    device-side evaluation"""
     exe = os.path.join(REF_BIN if binary.endswith("_ref") else TEST_BIN, binary)
     env = dict(os.environ)
+    env.pop("ALIS_HOST_MONITORS", None)
+    if host_monitors:
+        env["ALIS_HOST_MONITORS"] = "1"
     if threads:
         env["OMP_NUM_THREADS"] = str(threads)
     r = subprocess.run([exe, config, str(steps)], env=env, capture_output=True, text=True, timeout=1800)
@@ -137,6 +142,29 @@ def seed_fields(engines, shape, complex_field=0, seed=12345, scale=1e-3):
                 f[1:-1, 1:-1, 1:-1] = ((rng.rand(*[n - 2 for n in shape]) * 2 - 1) * scale).astype(np.float32)
                 for e in engines:
                     e.write_field(s, c, m, f)
+
+
+def add_materials(engines, shape, seed=21, box=None, zero_some=False):
+    """random inverse permittivity everywhere and one dispersive box (1 Drude + 1 critical-point pole,
+    lossy) in the middle of the grid -- the same on every engine"""
+    rng = np.random.RandomState(seed)
+    eps = [(0.3 + 0.7 * rng.rand(shape[0] + (c == 0), shape[1] + (c == 1), shape[2] + (c == 2))).astype(np.float32) for c in range(3)]
+    if zero_some:                                   # cells without material response (objectAbsorption skips them)
+        for a in eps:
+            a[rng.rand(*a.shape) < 0.1] = 0
+    if box is None:
+        box = [shape[0] // 3, 2 * shape[0] // 3, shape[1] // 3, 2 * shape[1] // 3, shape[2] // 3, 2 * shape[2] // 3]
+    dims = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1)
+    fill = [rng.rand(*dims).astype(np.float32) for _ in range(3)]
+    coef = {k: [[0.0] * 8 for _ in range(3)] for k in ("JJ", "JK", "JE", "KJ", "KK", "KE")}
+    for c in range(3):
+        coef["JJ"][c][0], coef["JE"][c][0] = 0.93 - 0.01 * c, 0.011 + 0.001 * c
+        coef["JJ"][c][1], coef["JK"][c][1], coef["JE"][c][1] = 0.9, -0.05 - 0.01 * c, 0.007
+        coef["KJ"][c][1], coef["KK"][c][1], coef["KE"][c][1] = 0.04, 0.91, 0.003 + 0.001 * c
+    for e in engines:
+        e.set_inv_eps(*eps)
+        e.add_dispersive(box, 1, 2, [0.012, 0.009, 0.015], coef, fill)
+    return box
 
 
 def assert_fields_identical(e1, e2, what=""):

@@ -26,3 +26,13 @@ def test_dropin_monitor_values(cfg):
     # printed digit.
     bad = helpers.monitor_mismatches(got, want, device_flux=True)
     assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
+
+
+@pytest.mark.parametrize("cfg", ["nanoblock", "dipole_pml", "phc"])
+def test_device_monitors_equal_host_view_monitors(cfg):
+    """slices / world reductions / absorption evaluated on the GPU (kernels eval_box, reduce_absmax,
+    column_sums, absorption_columns) against the same monitors evaluated through the host views
+    (ALIS_HOST_MONITORS=1): identical to the printed digit"""
+    dev = helpers.run_monitors("monitors_mine_cuda", cfg)
+    host = helpers.run_monitors("monitors_mine_cuda", cfg, host_monitors=True)
+    assert len(dev) > 250 and dev == host

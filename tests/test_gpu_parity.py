@@ -257,22 +257,7 @@ def fusion_env(monkeypatch):
     monkeypatch.setenv("ALISB_FUSE_FRAC", "0.01")
 
 
-def _add_materials(engines, shape, seed=21):
-    """random inverse permittivity everywhere and one dispersive box (1 Drude + 1 critical-point pole,
-    lossy) in the middle of the grid -- the same on every engine"""
-    rng = np.random.RandomState(seed)
-    eps = [(0.3 + 0.7 * rng.rand(shape[0] + (c == 0), shape[1] + (c == 1), shape[2] + (c == 2))).astype(np.float32) for c in range(3)]
-    box = [shape[0] // 3, 2 * shape[0] // 3, shape[1] // 3, 2 * shape[1] // 3, shape[2] // 3, 2 * shape[2] // 3]
-    dims = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1)
-    fill = [rng.rand(*dims).astype(np.float32) for _ in range(3)]
-    coef = {k: [[0.0] * 8 for _ in range(3)] for k in ("JJ", "JK", "JE", "KJ", "KK", "KE")}
-    for c in range(3):
-        coef["JJ"][c][0], coef["JE"][c][0] = 0.93 - 0.01 * c, 0.011 + 0.001 * c
-        coef["JJ"][c][1], coef["JK"][c][1], coef["JE"][c][1] = 0.9, -0.05 - 0.01 * c, 0.007
-        coef["KJ"][c][1], coef["KK"][c][1], coef["KE"][c][1] = 0.04, 0.91, 0.003 + 0.001 * c
-    for e in engines:
-        e.set_inv_eps(*eps)
-        e.add_dispersive(box, 1, 2, [0.012, 0.009, 0.015], coef, fill)
+_add_materials = helpers.add_materials
 
 
 @pytest.mark.parametrize("shape,num,steps,materials", [

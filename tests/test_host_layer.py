@@ -26,3 +26,13 @@ def test_monitor_values_equal_reference(cfg):
     assert len(want) > 35
     bad = helpers.monitor_mismatches(got, want)
     assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
+
+
+@needs_bins
+@pytest.mark.parametrize("cfg", ["nanoblock", "dipole_pml", "phc"])
+def test_device_monitors_equal_host_view_monitors(cfg):
+    """slices / world reductions / absorption evaluated by the engine calls (row f1) against the
+    same monitors evaluated through the host views: identical to the printed digit"""
+    dev = helpers.run_monitors("monitors_mine_oracle", cfg)
+    host = helpers.run_monitors("monitors_mine_oracle", cfg, host_monitors=True)
+    assert len(dev) > 250 and dev == host

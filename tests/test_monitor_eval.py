@@ -145,3 +145,57 @@ def test_cuda_absmax_skips_nans_like_the_reference(oracle_lib, engine_lib):
     box = [1, 39, 1, 35, 1, 31]
     a, b = g.reduce_absmax(g.field_fn(capi.FN_RAW, 0, 2), box), o.reduce_absmax(o.field_fn(capi.FN_RAW, 0, 2), box)
     assert a == b == F32(3.5)
+
+
+def _absorbing_pair(libs, shape, box, steps=4):
+    w = synthetic.BoxWorld(*shape, num=5)
+    engines = [w.make_engine(lib) for lib in libs]
+    helpers.add_materials(engines, shape, box=box)
+    helpers.seed_fields(engines, tuple(n + 2 for n in shape), seed=13)
+    dzE = np.linspace(1.0, 2.0, shape[2] + 2).astype(F32)
+    dzH = np.linspace(2.0, 1.5, shape[2] + 2).astype(F32)
+    for e in engines:
+        e.set_spacing(0, 2, dzE)
+        e.set_spacing(1, 2, dzH)
+        e.run(steps)
+    return engines
+
+
+def test_oracle_absorption_columns_match_numpy(oracle_lib):
+    """objectAbsorption's z columns (output.c:23-47,375-404) against a numpy float32 restatement"""
+    shape, box = (30, 26, 22), [8, 20, 6, 18, 5, 15]
+    (o,) = _absorbing_pair([oracle_lib], shape, box)
+    got = o.absorption_columns(0, box)
+    sl = np.s_[box[0]:box[1] + 1, box[2]:box[3] + 1, box[4]:box[5] + 1]
+    dzE = np.linspace(1.0, 2.0, shape[2] + 2).astype(F32)[box[4]:box[5] + 1]
+    dzH = np.linspace(2.0, 1.5, shape[2] + 2).astype(F32)[box[4]:box[5] + 1]
+    loss = [F32(0.012), F32(0.009), F32(0.015)]
+    for c in range(3):
+        E = o.read_field(0, c)[sl]
+        inv = o.read_box(capi.ARR_INVEPS, [c], box)
+        fill = o.read_box(capi.ARR_ADE_FILL, [0, c], box)
+        cur = (F32(2) * fill * E) / (F32(1) + F32(1) / loss[c])
+        for p in range(2):
+            cur = cur + o.read_box(capi.ARR_ADE_J, [0, 0, p, c], box)
+        cur = cur / inv
+        terms = (dzH if c == 2 else dzE) * E * cur
+        want = np.zeros(terms.shape[:2], F32)
+        for k in range(terms.shape[2]):
+            want = want + terms[:, :, k]
+        assert np.array_equal(got[:, :, c], want), c
+        assert np.abs(want).max() > 0
+
+
+@pytest.mark.gpu
+def test_cuda_absorption_columns_bit_exact(oracle_lib, engine_lib):
+    shape = (45, 33, 28)
+    for box in ([10, 30, 8, 25, 6, 20], [1, 45, 1, 33, 1, 28]):        # interior box; the whole grid (end-plane corrections)
+        g, o = _absorbing_pair([engine_lib, oracle_lib], shape, box)
+        helpers.assert_fields_identical(g, o)
+        a, b = g.absorption_columns(0, box), o.absorption_columns(0, box)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), box
+        assert np.abs(b).max() > 0
+        sub = [box[0] + 2, box[1] - 3, box[2] + 1, box[3] - 1, box[4], box[5]]
+        assert np.array_equal(g.absorption_columns(0, sub), b[2:-3, 1:-1])
+    with pytest.raises(capi.EngineError):
+        g.absorption_columns(1, box)
