@@ -1,0 +1,83 @@
+"""Drop-in check against the reference's OWN example programs (reference examples/*.c, all 16,
+unmodified): each must compile against include/alis.h and link against the host layer -- same
+macros, varargs conventions, struct members and symbols.  A few short ones are also
+run next to their twins built against the unmodified reference and their text outputs compared.
+
+Runs only where /root/reference is mounted (the build container); the GPU box has no reference
+tree, there tests/test_gpu_examples.py runs this repo's own copies of the named configurations."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+REF = os.environ.get("ALIS_REFERENCE", "/root/reference")
+EXAMPLES = sorted(glob.glob(os.path.join(REF, "examples", "*.c")))
+needs_ref = pytest.mark.skipif(not EXAMPLES, reason="reference tree not mounted")
+needs_lib = pytest.mark.skipif(not os.path.exists(os.path.join(helpers.TEST_BIN, "libalis_oracle.so")), reason="tests/bin not built (run __graft_entry__.build())")
+
+
+def build_mine(src, exe):
+    cmd = ["gcc", "-std=c99", "-O2", "-fopenmp", "-w", "-I" + os.path.join(helpers.ROOT, "include"), src,
+           "-L" + helpers.TEST_BIN, "-lalis_oracle", "-Wl,-rpath," + helpers.TEST_BIN, "-lm", "-o", exe]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+def build_ref(src, exe):
+    cmd = ["gcc", "-std=c99", "-O3", "-fopenmp", "-w", "-I" + os.path.join(helpers.ROOT, "oracle", "shim"), "-I" + os.path.join(REF, "src"), src,
+           os.path.join(helpers.ROOT, "oracle", "_ref", "libalis_ref.a"), "-lm", "-o", exe]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+@needs_ref
+@needs_lib
+def test_all_reference_examples_build_against_our_header_and_library(tmp_path):
+    assert len(EXAMPLES) == 16
+    failed = []
+    for src in EXAMPLES:
+        r = build_mine(src, str(tmp_path / "a.out"))
+        if r.returncode != 0:
+            failed.append((os.path.basename(src), r.stderr[-400:]))
+    assert not failed, failed
+
+
+def _txt_outputs(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".txt"):
+                out[os.path.relpath(os.path.join(d, f), root)] = np.atleast_2d(np.loadtxt(os.path.join(d, f)))
+    return out
+
+
+@needs_ref
+@needs_lib
+@pytest.mark.parametrize("name", ["Dipole_PML", "Metasurface_Farfield"])
+def test_unmodified_reference_example_runs_and_matches(name, tmp_path):
+    """the reference's own driver source, once linked with the reference, once with our host layer
+    (CPU oracle engine here; tests/test_gpu_examples.py does the same on the GPU with our copies)"""
+    src = os.path.join(REF, "examples", name + ".c")
+    outs = {}
+    for tag, build in (("ref", build_ref), ("mine", build_mine)):
+        d = tmp_path / tag
+        d.mkdir()
+        exe = str(d / name)
+        r = build(src, exe)
+        assert r.returncode == 0, r.stderr[-1000:]
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = helpers.TEST_BIN + os.pathsep + os.path.join(helpers.ROOT, "oracle")
+        r = subprocess.run([exe], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        outs[tag] = _txt_outputs(str(d))
+    assert sorted(outs["ref"]) == sorted(outs["mine"])
+    for k, a in outs["ref"].items():
+        b = outs["mine"][k]
+        assert a.shape == b.shape, k
+        scale = np.abs(a).max(axis=0, keepdims=True) + 1e-30
+        assert (np.abs(a - b) / scale).max() < 2e-4, k
+    if name == "Dipole_PML":                      # writes PNG frames only: our encoder must have produced them
+        pngs = [f for _, _, fs in os.walk(str(tmp_path / "mine")) for f in fs if f.endswith(".png")]
+        assert len(pngs) > 10
