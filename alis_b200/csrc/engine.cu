@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <limits.h>
 #include <vector>
 #include <algorithm>
 #include "alis_b200.h"
@@ -1591,6 +1592,100 @@ extern "C" int alisb_absorption_columns(alisb_engine *e, int obj, const int32_t 
 	CU(cudaMemcpyAsync(host, e->scratch, 3*n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
 	CU(cudaStreamSynchronize(e->stream));
 	e->launches++;
+	return ALISB_OK;
+}
+
+/* ---- geometry rasterisation (kernels geometry_bounds, geometry_fill) ------------------------------- */
+struct GeoDev {
+	alisb_geometry g; void *p[6]; size_t old_stack; bool stack_set;
+	GeoDev() { memset(&g, 0, sizeof g); memset(p, 0, sizeof p); old_stack = 0; stack_set = false; }
+	~GeoDev() { for (void *q : p) cudaFree(q); if (stack_set) cudaDeviceSetLimit(cudaLimitStackSize, old_stack); }
+};
+
+static int geo_check(const alisb_geometry *g, const int32_t ibox[6])
+{
+	if (!g || !ibox || g->nobjects < 1 || !g->roots || g->nnodes < 1 || !g->nodes || g->subn < 1 || g->subn > 64) return fail(ALISB_EINVAL, "geometry: bad description");
+	for (int a=0; a<3; a++) {
+		if (!g->coord[a] || g->lo[a] > g->hi[a]) return fail(ALISB_EINVAL, "geometry: missing coordinate table");
+		if (ibox[2*a] > ibox[2*a+1] || ibox[2*a] < g->lo[a] || ibox[2*a+1] > g->hi[a]) return fail(ALISB_EINVAL, "geometry: box outside the coordinate tables");
+	}
+	for (int o=0; o<g->nobjects; o++) if (g->roots[o] < 0 || g->roots[o] >= g->nnodes) return fail(ALISB_EINVAL, "geometry: bad root");
+	for (int n=0; n<g->nnodes; n++) {
+		const alisb_shape &s = g->nodes[n];
+		if (s.type < 0 || s.type >= ALISB_SHAPE_COUNT) return fail(ALISB_EINVAL, "geometry: unknown shape type");
+		if (s.type > ALISB_SHAPE_HRODZY) {
+			/* children come after their parent: the tree is acyclic and recursion ends */
+			if (s.nchild < 1 || s.child <= n || s.child + s.nchild > g->nnodes) return fail(ALISB_EINVAL, "geometry: bad child range");
+			const int need = s.type == ALISB_SHAPE_ROTATION ? 6 : (s.type >= ALISB_SHAPE_CLATTICEX ? 2*(int)s.f[0][0] : 0);
+			if (need && (s.aux < 0 || s.aux + need > g->naux || !g->aux)) return fail(ALISB_EINVAL, "geometry: bad constant range");
+		}
+	}
+	return ALISB_OK;
+}
+
+/* device copy of the description; raises the per-thread stack for the recursive interpreter */
+static int geo_upload(int device, const alisb_geometry *g, GeoDev &d)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(ALISB_ECUDA, "geometry: no CUDA device %d (this library has no CPU fallback)", device);
+	CU(cudaSetDevice(device));
+	d.g = *g;
+	const size_t slots = (size_t)g->subn + 3;
+	const void *src[6] = { g->roots, g->nodes, g->aux, g->coord[0], g->coord[1], g->coord[2] };
+	const size_t bytes[6] = { sizeof(int32_t)*g->nobjects, sizeof(alisb_shape)*g->nnodes, sizeof(float)*std::max(g->naux, 1),
+		sizeof(float)*2*slots*(g->hi[0]-g->lo[0]+1), sizeof(float)*2*slots*(g->hi[1]-g->lo[1]+1), sizeof(float)*2*slots*(g->hi[2]-g->lo[2]+1) };
+	for (int q=0; q<6; q++) {
+		CU(cudaMalloc(&d.p[q], bytes[q]));
+		if (src[q] && !(q == 2 && g->naux == 0)) CU(cudaMemcpy(d.p[q], src[q], bytes[q], cudaMemcpyHostToDevice));
+	}
+	d.g.roots = (const int32_t*)d.p[0]; d.g.nodes = (const alisb_shape*)d.p[1]; d.g.aux = (const float*)d.p[2];
+	for (int a=0; a<3; a++) d.g.coord[a] = (const float*)d.p[3+a];
+	CU(cudaDeviceGetLimit(&d.old_stack, cudaLimitStackSize));
+	if (d.old_stack < 8192) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); d.stack_set = true; }
+	return ALISB_OK;
+}
+
+extern "C" int alisb_geometry_bounds(int device, const alisb_geometry *g, const int32_t ibox[6], int32_t *bounds)
+{
+	TRY(geo_check(g, ibox));
+	if (!bounds) return fail(ALISB_EINVAL, "geometry: null output");
+	GeoDev d;
+	TRY(geo_upload(device, g, d));
+	const int ni = ibox[1]-ibox[0]+1, nj = ibox[3]-ibox[2]+1, nk = ibox[5]-ibox[4]+1;
+	std::vector<int32_t> h((size_t)6*g->nobjects);
+	for (int o=0; o<g->nobjects; o++) for (int a=0; a<3; a++) { h[6*o+2*a] = INT32_MAX; h[6*o+2*a+1] = INT32_MIN; }
+	int *db = 0;
+	CU(cudaMalloc((void**)&db, h.size()*sizeof(int32_t)));
+	cudaError_t ce = cudaMemcpy(db, h.data(), h.size()*sizeof(int32_t), cudaMemcpyHostToDevice);
+	if (ce == cudaSuccess) {
+		const size_t n = (size_t)ni*nj*nk;
+		geometry_bounds<<<div_up(n, 128), 128>>>(d.g, ibox[0], ibox[2], ibox[4], ni, nj, nk, db);
+		ce = cudaGetLastError();
+		if (ce == cudaSuccess) ce = cudaMemcpy(h.data(), db, h.size()*sizeof(int32_t), cudaMemcpyDeviceToHost);
+	}
+	cudaFree(db);
+	if (ce != cudaSuccess) return fail(ALISB_ECUDA, "geometry_bounds: %s", cudaGetErrorString(ce));
+	memcpy(bounds, h.data(), h.size()*sizeof(int32_t));
+	return ALISB_OK;
+}
+
+extern "C" int alisb_geometry_fill(int device, const alisb_geometry *g, int object, const int32_t ibox[6], float *fx, float *fy, float *fz)
+{
+	TRY(geo_check(g, ibox));
+	if (object < 0 || object >= g->nobjects || !fx || !fy || !fz) return fail(ALISB_EINVAL, "geometry: bad object or null output");
+	for (int a=0; a<3; a++) if (ibox[2*a] - 1 < g->lo[a] - 1 || ibox[2*a] < g->lo[a]) return fail(ALISB_EINVAL, "geometry: box outside the coordinate tables");
+	GeoDev d;
+	TRY(geo_upload(device, g, d));
+	const int ni = ibox[1]-ibox[0]+1, nj = ibox[3]-ibox[2]+1, nk = ibox[5]-ibox[4]+1;
+	const size_t n = (size_t)ni*nj*nk;
+	float *df = 0;
+	CU(cudaMalloc((void**)&df, 3*n*sizeof(float)));
+	geometry_fill<<<div_up(3*n, 128), 128>>>(d.g, object, ibox[0], ibox[2], ibox[4], ni, nj, nk, df, df + n, df + 2*n);
+	cudaError_t ce = cudaGetLastError();
+	float *dst[3] = { fx, fy, fz };
+	for (int c=0; c<3 && ce == cudaSuccess; c++) ce = cudaMemcpy(dst[c], df + c*n, n*sizeof(float), cudaMemcpyDeviceToHost);
+	cudaFree(df);
+	if (ce != cudaSuccess) return fail(ALISB_ECUDA, "geometry_fill: %s", cudaGetErrorString(ce));
 	return ALISB_OK;
 }
 

@@ -1029,3 +1029,41 @@ __global__ void absorption_columns(const __grid_constant__ EvalParams p, int cmi
 	float *o = out + 3*((size_t)ia*p.nj + ib);
 	o[0] = xs; o[1] = ys; o[2] = zs;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Geometry rasterisation: the shape tree interpreter of geometry_eval.h (shared
+ * with the CPU oracle) over the cells of a box.  Recursive device functions: the engine raises the
+ * per-thread stack limit around these launches.
+ * ------------------------------------------------------------------------------------------ */
+#define GEO_FN static __device__
+#include "geometry_eval.h"
+
+/* object.c:229-262: first object owning the node (i,j,k) -> atomic min/max of its index box */
+__global__ void geometry_bounds(const alisb_geometry g, int i0, int j0, int k0, int ni, int nj, int nk, int *bounds)
+{
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= (size_t)ni*nj*nk) return;
+	const int ia = (int)(t % ni); const size_t r = t / ni;
+	const int i = i0 + ia, j = j0 + (int)(r % nj), k = k0 + (int)(r / nj);
+	const float x = geo_coord(&g, 0, i, 0, 0), y = geo_coord(&g, 1, j, 0, 0), z = geo_coord(&g, 2, k, 0, 0);
+	int o = 0;
+	while (o < g.nobjects && !geo_inside(g.nodes, g.aux, g.roots[o], x, y, z)) o++;
+	if (o == g.nobjects) return;
+	int *b = bounds + 6*o;
+	atomicMin(&b[0], i); atomicMax(&b[1], i); atomicMin(&b[2], j); atomicMax(&b[3], j); atomicMin(&b[4], k); atomicMax(&b[5], k);
+}
+
+/* one thread per (cell, component); out[comp] dense over the box in the HOST order (z fastest) */
+__global__ void geometry_fill(const alisb_geometry g, int object, int i0, int j0, int k0, int ni, int nj, int nk, float *fx, float *fy, float *fz)
+{
+	const size_t n = (size_t)ni*nj*nk;
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= 3*n) return;
+	const int comp = (int)(t / n); const size_t q = t - (size_t)comp*n;
+	const int ia = (int)(q % ni); const size_t r = q / ni;
+	const int ib = (int)(r % nj), ic = (int)(r / nj);
+	const int idx[3] = { i0 + ia, j0 + ib, k0 + ic };
+	const int half[3] = { comp == 0, comp == 1, comp == 2 };
+	float *out = comp == 0 ? fx : comp == 1 ? fy : fz;
+	out[((size_t)ia*nj + ib)*nk + ic] = geo_fill(&g, object, idx, half);
+}

@@ -17,6 +17,8 @@
  *   alisb_step_E / alisb_step_H            updateE / updateH  update.c:275-341
  *   alisb_phaser_*                         createPhasers/updatePhaser  phaser.c:21-110
  *   alisb_phaser_surface_sums              farFieldX/Y/Z double loops  farfld.c:248-459
+ *   alisb_geometry_bounds / _fill          getObjectsBounds, fillFactor + the built-in shapes
+ *                                          object.c:70-121,229-279, shapes.c:17-221
  *   alisb_read_box / alisb_write_box       the host float*** views  world.c:58-70
  *   alisb_eval_box / _reduce_absmax / _column_sums   field functions + slices/world reductions
  *                                          fields.c:130-681, slices.c:242-427, output.c:56-101
@@ -264,6 +266,39 @@ int  alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t i
  * Needs alisb_set_inv_eps and the z spacing tables of both field sets.  The host applies the
  * reference's edge weights in x,y and adds the columns in its order.                          */
 int  alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], float *host);
+
+/* ---- geometry rasterisation on the device (reference shapes.c:17-221,
+ * object.c:70-121,229-279) ---------------------------------------------------------------------
+ * The host flattens the object list into alisb_shape nodes (children of a node are contiguous);
+ * whatever needs libm is evaluated by the host and passed in: aux holds cos/sin constants
+ * (ROTATION: cx,sx,cy,sy,cz,sz at node.aux; CLATTICE*: count (cos,sin) pairs at node.aux), coord[axis]
+ * the coordinates itox/jtoy/ktoz of every sample position, [(idx-lo)*2 + half][slot], subn+3 slots:
+ * 0 = the position itself, 1/2 = minus/plus the outermost sub-sample offset (object.c:104),
+ * 3+q = the q-th regular sub-sample (object.c:116-118); half = 1 means idx - 1/2.              */
+enum {
+	ALISB_SHAPE_BOX = 0, ALISB_SHAPE_BALL, ALISB_SHAPE_DIAMOND, ALISB_SHAPE_BICONEX, ALISB_SHAPE_BICONEY, ALISB_SHAPE_BICONEZ,
+	ALISB_SHAPE_RODX, ALISB_SHAPE_RODY, ALISB_SHAPE_RODZ, ALISB_SHAPE_DRODX, ALISB_SHAPE_DRODY, ALISB_SHAPE_DRODZ,
+	ALISB_SHAPE_HRODXY, ALISB_SHAPE_HRODYZ, ALISB_SHAPE_HRODZX, ALISB_SHAPE_HRODXZ, ALISB_SHAPE_HRODYX, ALISB_SHAPE_HRODZY,
+	ALISB_SHAPE_TRANSLATION, ALISB_SHAPE_ROTATION, ALISB_SHAPE_COMBINATION, ALISB_SHAPE_INTERSECTION, ALISB_SHAPE_DIFFERENCE,
+	ALISB_SHAPE_LATTICE, ALISB_SHAPE_DLATTICE, ALISB_SHAPE_CLATTICEX, ALISB_SHAPE_CLATTICEY, ALISB_SHAPE_CLATTICEZ,
+	ALISB_SHAPE_COUNT
+};
+typedef struct { int32_t type, child, nchild, aux; float f[3][3]; } alisb_shape;
+typedef struct {
+	int32_t nobjects; const int32_t *roots;      /* root node of every object, list order (earlier wins) */
+	int32_t nnodes;   const alisb_shape *nodes;
+	int32_t naux;     const float *aux;
+	int32_t subn;                                /* W->subN, >= 1                                         */
+	int32_t lo[3], hi[3];                        /* index range the coordinate tables cover (inclusive)   */
+	const float *coord[3];
+} alisb_geometry;
+/* getObjectsBounds (object.c:229-262): for every object the index bounding box of the nodes of
+ * ibox (inclusive, world indices) that lie in it and in no earlier object: bounds[o*6 + ...] =
+ * iMin,iMax,jMin,jMax,kMin,kMax; an object that owns no node gets iMin > iMax.                  */
+int  alisb_geometry_bounds(int device, const alisb_geometry *g, const int32_t ibox[6], int32_t *bounds);
+/* fillFactor (object.c:78-121) of object `object` for the three staggered components at every cell
+ * of ibox: fx at (i-1/2,j,k), fy at (i,j-1/2,k), fz at (i,j,k-1/2); dense host blocks, z fastest. */
+int  alisb_geometry_fill(int device, const alisb_geometry *g, int object, const int32_t ibox[6], float *fx, float *fy, float *fz);
 
 /* ---- z-slab halo (multi-GPU) -------------------------------------------- */
 /* Buffers (device memory for the CUDA engine) holding one full z-plane incl. ghosts of
