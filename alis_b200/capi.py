@@ -59,6 +59,22 @@ class FieldFn(C.Structure):
 FN_RAW, FN_NODE, FN_EE, FN_HH, FN_UH, FN_EXH, FN_S, FN_TDIAG, FN_TOFF, FN_DIVE = range(10)
 
 
+class Shape(C.Structure):
+    """alisb_shape: one node of a flattened object tree (reference shapes.c)"""
+    _fields_ = [("type", C.c_int32), ("child", C.c_int32), ("nchild", C.c_int32), ("aux", C.c_int32), ("f", C.c_float * 3 * 3)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("nobjects", C.c_int32), ("roots", i32p), ("nnodes", C.c_int32), ("nodes", C.POINTER(Shape)),
+                ("naux", C.c_int32), ("aux", f32p), ("subn", C.c_int32), ("lo", C.c_int32 * 3), ("hi", C.c_int32 * 3),
+                ("coord", f32p * 3)]
+
+
+SHAPES = ("BOX BALL DIAMOND BICONEX BICONEY BICONEZ RODX RODY RODZ DRODX DRODY DRODZ HRODXY HRODYZ HRODZX HRODXZ HRODYX HRODZY "
+          "TRANSLATION ROTATION COMBINATION INTERSECTION DIFFERENCE LATTICE DLATTICE CLATTICEX CLATTICEY CLATTICEZ").split()
+SHAPE = {name: q for q, name in enumerate(SHAPES)}
+
+
 class Copy(C.Structure):
     _fields_ = [("set", C.c_int32), ("comp", C.c_int32), ("cosk", C.c_float), ("sink", C.c_float),
                 ("box", C.c_int32 * 6), ("alt", C.c_int32 * 3)]
@@ -97,6 +113,8 @@ def _declare(lib):
         "alisb_reduce_absmax": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_column_sums": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_absorption_columns": (i, [vp, i, i32p, f32p]),
+        "alisb_geometry_bounds": (i, [i, C.POINTER(Geometry), i32p, i32p]),
+        "alisb_geometry_fill": (i, [i, C.POINTER(Geometry), i, i32p, f32p, f32p, f32p]),
         "alisb_chi2_couple": (i, [vp, i, i, vp, vp, f32p, f]),
         "alisb_set_fusion": (i, [vp, i]),
         "alisb_flush": (i, [vp, i]),
@@ -408,3 +426,86 @@ class Phaser:
         if self.h:
             self.e.lib.alisb_phaser_destroy(self.h)
             self.h = C.c_void_p()
+
+
+class GeometryDesc:
+    """Flattened object list + coordinate tables for alisb_geometry_bounds / alisb_geometry_fill.
+
+    objects: list of nested tuples (type_name, f(3x3 list), [children]); earlier objects win.
+    coords(axis, position) -> coordinate (the world's itox/jtoy/ktoz) as a python callable."""
+
+    def __init__(self, lib, objects, lo, hi, subn, coords, device=0):
+        self.lib, self.device, self.subn = lib, device, subn
+        nodes, aux, roots = [], [], []
+
+        def add(obj, slot):
+            name, f, kids = obj
+            n = nodes[slot]
+            n.type = SHAPE[name]
+            for a in range(3):
+                for b in range(3):
+                    n.f[a][b] = float(f[a][b])
+            if name == "ROTATION":
+                n.aux = len(aux)
+                for q in range(3):
+                    ang = np.float32(np.float32(f[0][q]) * np.pi / 180.0)
+                    aux.extend([np.cos(ang, dtype=np.float32), np.sin(ang, dtype=np.float32)])
+            if name.startswith("CLATTICE"):
+                n.aux = len(aux)
+                cnt = int(f[0][0])
+                for q in range(cnt):
+                    th = np.float32(2 * np.pi * q / cnt)
+                    aux.extend([np.cos(th, dtype=np.float32), np.sin(th, dtype=np.float32)])
+            if kids:
+                n.child, n.nchild = len(nodes), len(kids)
+                first = len(nodes)
+                nodes.extend(Shape() for _ in kids)
+                for q, k in enumerate(kids):
+                    add(k, first + q)
+
+        for obj in objects:
+            roots.append(len(nodes))
+            nodes.append(Shape())
+            add(obj, roots[-1])
+        self._nodes = (Shape * len(nodes))(*nodes)
+        self._roots = np.array(roots, np.int32)
+        self._aux = np.array(aux if aux else [0.0], np.float32)
+        slots = subn + 3
+        edge = np.float32((subn - 1.0) / (subn * 2.0))
+        self._coord = []
+        for a in range(3):
+            t = np.zeros((hi[a] - lo[a] + 1, 2, slots), np.float32)
+            for q, idx in enumerate(range(lo[a], hi[a] + 1)):
+                for half in range(2):
+                    base = np.float32(idx - 0.5 * half)
+                    t[q, half, 0] = coords(a, base)
+                    t[q, half, 1] = coords(a, np.float32(base - edge))
+                    t[q, half, 2] = coords(a, np.float32(base + edge))
+                    for s_ in range(subn):
+                        d = 1 - subn + 2 * s_
+                        t[q, half, 3 + s_] = coords(a, np.float32(np.float64(base) + 0.5 * d / subn))
+            self._coord.append(np.ascontiguousarray(t))
+        g = Geometry()
+        g.nobjects, g.roots = len(roots), self._roots.ctypes.data_as(i32p)
+        g.nnodes, g.nodes = len(nodes), C.cast(self._nodes, C.POINTER(Shape))
+        g.naux, g.aux = len(aux), _fp(self._aux)
+        g.subn = subn
+        g.lo, g.hi = (C.c_int32 * 3)(*lo), (C.c_int32 * 3)(*hi)
+        for a in range(3):
+            g.coord[a] = _fp(self._coord[a])
+        self.g = g
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(f"{self.lib.alisb_backend().decode()}: {self.lib.alisb_last_error().decode()} (rc={rc})")
+
+    def bounds(self, ibox):
+        out = np.zeros((self.g.nobjects, 6), np.int32)
+        self._ck(self.lib.alisb_geometry_bounds(self.device, C.byref(self.g), _ip(ibox), out.ctypes.data_as(i32p)))
+        return out
+
+    def fill(self, obj, ibox):
+        shape = (ibox[1] - ibox[0] + 1, ibox[3] - ibox[2] + 1, ibox[5] - ibox[4] + 1)
+        f = [np.empty(shape, np.float32) for _ in range(3)]
+        self._ck(self.lib.alisb_geometry_fill(self.device, C.byref(self.g), obj, _ip(ibox), _fp(f[0]), _fp(f[1]), _fp(f[2])))
+        return f

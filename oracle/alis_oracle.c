@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdint.h>
 #include "alis_b200.h"
 
 #define MAXOBJ 64
@@ -685,6 +686,72 @@ int alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], flo
 		float xs, ys, zs;
 		MON_ABSORPTION_COLUMN(&X, a, b, box[4], box[5], 1, e->n[2], xs, ys, zs);
 		host[q++] = xs; host[q++] = ys; host[q++] = zs;
+	}
+	return ALISB_OK;
+}
+
+/* ---- geometry rasterisation: reference shapes.c:17-221 + object.c:70-121,229-262 through the shared
+ * restatement alis_b200/csrc/geometry_eval.h, looped like the reference ------------------------- */
+#define GEO_FN static
+#include "../alis_b200/csrc/geometry_eval.h"
+
+static int geo_check(const alisb_geometry *g, const int32_t ibox[6])
+{
+	if (!g || !ibox || g->nobjects < 1 || !g->roots || g->nnodes < 1 || !g->nodes || g->subn < 1 || g->subn > 64) return fail(ALISB_EINVAL, "geometry: bad description");
+	for (int a=0; a<3; a++) {
+		if (!g->coord[a] || g->lo[a] > g->hi[a]) return fail(ALISB_EINVAL, "geometry: missing coordinate table");
+		if (ibox[2*a] > ibox[2*a+1] || ibox[2*a] < g->lo[a] || ibox[2*a+1] > g->hi[a]) return fail(ALISB_EINVAL, "geometry: box outside the coordinate tables");
+	}
+	for (int o=0; o<g->nobjects; o++) if (g->roots[o] < 0 || g->roots[o] >= g->nnodes) return fail(ALISB_EINVAL, "geometry: bad root");
+	for (int n=0; n<g->nnodes; n++) {
+		const alisb_shape *s = &g->nodes[n];
+		if (s->type < 0 || s->type >= ALISB_SHAPE_COUNT) return fail(ALISB_EINVAL, "geometry: unknown shape type");
+		if (s->type > ALISB_SHAPE_HRODZY) {
+			if (s->nchild < 1 || s->child <= n || s->child + s->nchild > g->nnodes) return fail(ALISB_EINVAL, "geometry: bad child range");
+			const int need = s->type == ALISB_SHAPE_ROTATION ? 6 : (s->type >= ALISB_SHAPE_CLATTICEX ? 2*(int)s->f[0][0] : 0);
+			if (need && (s->aux < 0 || s->aux + need > g->naux || !g->aux)) return fail(ALISB_EINVAL, "geometry: bad constant range");
+		}
+	}
+	return ALISB_OK;
+}
+
+int alisb_geometry_bounds(int device, const alisb_geometry *g, const int32_t ibox[6], int32_t *bounds)
+{
+	(void)device;
+	int rc = geo_check(g, ibox);
+	if (rc) return rc;
+	for (int o=0; o<g->nobjects; o++) for (int a=0; a<3; a++) { bounds[6*o+2*a] = INT32_MAX; bounds[6*o+2*a+1] = INT32_MIN; }
+	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++) {
+		const float x = geo_coord(g, 0, i, 0, 0), y = geo_coord(g, 1, j, 0, 0), z = geo_coord(g, 2, k, 0, 0);
+		int o = 0;
+		while (o < g->nobjects && !geo_inside(g->nodes, g->aux, g->roots[o], x, y, z)) o++;
+		if (o == g->nobjects) continue;
+		int32_t *b = bounds + 6*o;
+		if (i < b[0]) b[0] = i;
+		if (i > b[1]) b[1] = i;
+		if (j < b[2]) b[2] = j;
+		if (j > b[3]) b[3] = j;
+		if (k < b[4]) b[4] = k;
+		if (k > b[5]) b[5] = k;
+	}
+	return ALISB_OK;
+}
+
+int alisb_geometry_fill(int device, const alisb_geometry *g, int object, const int32_t ibox[6], float *fx, float *fy, float *fz)
+{
+	(void)device;
+	int rc = geo_check(g, ibox);
+	if (rc) return rc;
+	if (object < 0 || object >= g->nobjects || !fx || !fy || !fz) return fail(ALISB_EINVAL, "geometry: bad object or null output");
+	const int nj = ibox[3]-ibox[2]+1, nk = ibox[5]-ibox[4]+1;
+	#pragma omp parallel for schedule(guided)
+	for (int i=ibox[0]; i<=ibox[1]; i++) for (int j=ibox[2]; j<=ibox[3]; j++) for (int k=ibox[4]; k<=ibox[5]; k++) {
+		const size_t q = ((size_t)(i-ibox[0])*nj + (j-ibox[2]))*nk + (k-ibox[4]);
+		const int idx[3] = { i, j, k };
+		const int hx[3] = { 1, 0, 0 }, hy[3] = { 0, 1, 0 }, hz[3] = { 0, 0, 1 };
+		fx[q] = geo_fill(g, object, idx, hx);
+		fy[q] = geo_fill(g, object, idx, hy);
+		fz[q] = geo_fill(g, object, idx, hz);
 	}
 	return ALISB_OK;
 }
