@@ -1641,7 +1641,7 @@ static int geo_upload(int device, const alisb_geometry *g, GeoDev &d)
 	d.g.roots = (const int32_t*)d.p[0]; d.g.nodes = (const alisb_shape*)d.p[1]; d.g.aux = (const float*)d.p[2];
 	for (int a=0; a<3; a++) d.g.coord[a] = (const float*)d.p[3+a];
 	CU(cudaDeviceGetLimit(&d.old_stack, cudaLimitStackSize));
-	if (d.old_stack < 8192) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); d.stack_set = true; }
+	if (d.old_stack < 4096) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 4096)); d.stack_set = true; }   /* geo_inside: 144 B per level */
 	return ALISB_OK;
 }
 

@@ -220,15 +220,181 @@ static bounds *object_bounds(world W, object *O, int N)
 	return B;
 }
 
+/* ---- rasterisation on the device ------------------------------------------------------------
+ * Default (ALIS_DEVICE_GEOMETRY=0 keeps everything on the host): the object list is flattened into alisb_shape nodes and the two
+ * O(cells x sub-samples) loops -- object_bounds and fill_factor -- run on the GPU
+ * (alisb_geometry_bounds / alisb_geometry_fill).  Everything that needs libm stays here: the cos/sin
+ * of Rotation / CLattice angles and the coordinates of every sample position (uniform, graded or
+ * user grid functions alike) are tabulated with the same expressions the host path evaluates, so the
+ * fill factors are bit-identical.  Objects with a user-written shape, ImportContour height maps
+ * and subN < 0 keep the host path. */
+typedef struct {
+	alisb_geometry g;
+	alisb_shape *nodes; int nnodes, capnodes;
+	float *aux; int naux, capaux;
+	int32_t *roots;
+	float *coord[3];
+} geo_ctx;
+
+static int geo_type(shape *S)
+{
+	shape *known[ALISB_SHAPE_COUNT] = { Box, Ball, Diamond, BiconeX, BiconeY, BiconeZ, RodX, RodY, RodZ, DRodX, DRodY, DRodZ,
+		HRodXY, HRodYZ, HRodZX, HRodXZ, HRodYX, HRodZY, Translation, Rotation, Combination, Intersection, Difference,
+		Lattice, DLattice, CLatticeX, CLatticeY, CLatticeZ };
+	for (int t=0; t<ALISB_SHAPE_COUNT; t++) if (S == known[t]) return t;
+	return -1;
+}
+
+static int geo_new_nodes(geo_ctx *G, int count)
+{
+	while (G->nnodes + count > G->capnodes) { G->capnodes = G->capnodes ? 2*G->capnodes : 32; G->nodes = realloc(G->nodes, sizeof(alisb_shape)*G->capnodes); }
+	memset(G->nodes + G->nnodes, 0, sizeof(alisb_shape)*count);
+	G->nnodes += count;
+	return G->nnodes - count;
+}
+
+static void geo_push_aux(geo_ctx *G, float v)
+{
+	if (G->naux == G->capaux) { G->capaux = G->capaux ? 2*G->capaux : 32; G->aux = realloc(G->aux, sizeof(float)*G->capaux); }
+	G->aux[G->naux++] = v;
+}
+
+/* object O -> node `slot` (children appended behind); 0 when some shape has no device twin */
+static int geo_flatten(geo_ctx *G, object O, int slot)
+{
+	const int type = geo_type(O.S);
+	if (type < 0) return 0;
+	int count = 0;
+	if (type > ALISB_SHAPE_HRODZY) {
+		if (!O.p) return 0;
+		count = (type == ALISB_SHAPE_COMBINATION || type == ALISB_SHAPE_INTERSECTION || type == ALISB_SHAPE_DIFFERENCE) ? (int)O.f[0][0] : 1;
+		if (count < 1) return 0;
+	}
+	int aux = 0;
+	if (type == ALISB_SHAPE_ROTATION) {                   /* shapes.c:133-140 */
+		aux = G->naux;
+		for (int q=0; q<3; q++) { geo_push_aux(G, cosf(O.f[0][q]*PI/180.)); geo_push_aux(G, sinf(O.f[0][q]*PI/180.)); }
+	}
+	if (type >= ALISB_SHAPE_CLATTICEX) {                  /* shapes.c:191-221 */
+		aux = G->naux;
+		const int copies = O.f[0][0];
+		for (int q=0; q<copies; q++) { float theta = 2 * PI * q / copies; geo_push_aux(G, cosf(theta)); geo_push_aux(G, sinf(theta)); }
+	}
+	const int first = count ? geo_new_nodes(G, count) : 0;
+	alisb_shape *n = &G->nodes[slot];
+	n->type = type; n->child = first; n->nchild = count; n->aux = aux;
+	for (int a=0; a<3; a++) for (int b=0; b<3; b++) n->f[a][b] = O.f[a][b];
+	object *child = O.p;
+	for (int q=0; q<count; q++) if (!geo_flatten(G, child[q], first+q)) return 0;
+	return 1;
+}
+
+static void geo_free(geo_ctx *G)
+{
+	if (!G) return;
+	free(G->nodes); free(G->aux); free(G->roots);
+	for (int a=0; a<3; a++) free(G->coord[a]);
+	free(G);
+}
+
+static unsigned long geo_objects;
+unsigned long alisDeviceGeometryObjects(void) { return geo_objects; }   /* objects rasterised by the engine so far (diagnostics) */
+
+int alis_device_geometry(void)
+{
+	static int mode = -1;
+	if (mode < 0) { const char *s = getenv("ALIS_DEVICE_GEOMETRY"); mode = s ? atoi(s) != 0 : 1; }     /* on unless ALIS_DEVICE_GEOMETRY=0 */
+	return mode;
+}
+
+static geo_ctx *geo_build(world W, object *O, int N)
+{
+	if (!alis_device_geometry() || W->subN < 1 || N < 1) return 0;
+	geo_ctx *G = calloc(1, sizeof *G);
+	G->roots = malloc(sizeof(int32_t)*N);
+	for (int o=0; o<N; o++) {
+		G->roots[o] = geo_new_nodes(G, 1);
+		if (!geo_flatten(G, O[o], G->roots[o])) { geo_free(G); return 0; }
+	}
+	/* sample coordinates, [(idx-lo)*2 + half][slot] (object.c:72, 104-118 evaluate W->itox at exactly these arguments) */
+	const int lo[3] = { W->iMIN, W->jMIN, W->kMIN }, hi[3] = { W->iMAX+1, W->jMAX+1, W->kMAX+1 };
+	float (*map[3])(world, float) = { W->itox, W->jtoy, W->ktoz };
+	const int slots = W->subN + 3;
+	const float edge = (W->subN-1.0) / (W->subN*2.0);
+	for (int a=0; a<3; a++) {
+		G->coord[a] = malloc(sizeof(float)*2*slots*(hi[a]-lo[a]+1));
+		for (int idx=lo[a]; idx<=hi[a]; idx++) for (int half=0; half<2; half++) {
+			float *t = G->coord[a] + ((size_t)(idx-lo[a])*2 + half)*slots;
+			const float base = half ? idx-0.5 : idx;
+			t[0] = map[a](W, base);
+			t[1] = map[a](W, base + -edge);
+			t[2] = map[a](W, base + edge);
+			for (int q=0; q<W->subN; q++) { const int d = 1-W->subN+2*q; t[3+q] = map[a](W, base+0.5*d/W->subN); }
+		}
+		G->g.lo[a] = lo[a]; G->g.hi[a] = hi[a]; G->g.coord[a] = G->coord[a];
+	}
+	G->g.nobjects = N; G->g.roots = G->roots; G->g.nnodes = G->nnodes; G->g.nodes = G->nodes;
+	G->g.naux = G->naux; G->g.aux = G->aux; G->g.subn = W->subN;
+	return G;
+}
+
+/* object_bounds with the node scan on the device */
+static bounds *object_bounds_device(world W, geo_ctx *G, int N)
+{
+	bounds *B;
+	MALLOC(B, 0, N);
+	int32_t *raw = malloc(sizeof(int32_t)*6*N);
+	const int32_t box[6] = { W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX };
+	if (alisb_geometry_bounds(alis_bridge_device(), &G->g, box, raw) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	for (int o=0; o<N; o++) {
+		B[o].iMin = raw[6*o], B[o].iMax = raw[6*o+1], B[o].jMin = raw[6*o+2], B[o].jMax = raw[6*o+3], B[o].kMin = raw[6*o+4], B[o].kMax = raw[6*o+5];
+		if (B[o].iMin > B[o].iMax || B[o].jMin > B[o].jMax || B[o].kMin > B[o].kMax) {
+			printf("\rVolume of object %d/%d is zero!\n", o+1, N);
+			exit(0);
+		}
+		B[o].iMin = MAX(B[o].iMin-1, W->iMIN), B[o].iMax = MIN(B[o].iMax+2, W->iMAX);
+		B[o].jMin = MAX(B[o].jMin-1, W->jMIN), B[o].jMax = MIN(B[o].jMax+2, W->jMAX);
+		B[o].kMin = MAX(B[o].kMin-1, W->kMIN), B[o].kMax = MIN(B[o].kMax+2, W->kMAX);
+	}
+	free(raw);
+	return B;
+}
+
+/* the three fill-factor arrays of object o over its box widened by the boundary layers, from the
+ * device: f[c][((i-i0)*nj + (j-j0))*nk + (k-k0)] */
+typedef struct { float *f[3]; int i0, j0, k0, nj, nk; } geo_fill_t;
+
+static geo_fill_t geo_fill_object(world W, geo_ctx *G, int o, bounds b)
+{
+	geo_fill_t F;
+	const int32_t box[6] = { b.iMin, b.iMax + (b.iMax == W->iMAX), b.jMin, b.jMax + (b.jMax == W->jMAX), b.kMin, b.kMax + (b.kMax == W->kMAX) };
+	const size_t n = (size_t)(box[1]-box[0]+1)*(box[3]-box[2]+1)*(box[5]-box[4]+1);
+	for (int c=0; c<3; c++) if (!(F.f[c] = malloc(sizeof(float)*n))) printf("\nMemory allocation failure\n"), exit(1);
+	F.i0 = box[0]; F.j0 = box[2]; F.k0 = box[4]; F.nj = box[3]-box[2]+1; F.nk = box[5]-box[4]+1;
+	if (alisb_geometry_fill(alis_bridge_device(), &G->g, o, box, F.f[0], F.f[1], F.f[2]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	geo_objects++;
+	return F;
+}
+#define GEO_AT(F,c,i,j,k) ((F).f[c][((size_t)((i)-(F).i0)*(F).nj + ((j)-(F).j0))*(F).nk + ((k)-(F).k0)])
+
 /* fill factors of the three staggered components + the pole coefficients of dispersive object n
  * (= list entry o); tri = 1 for anisotropic matter (reference object.c:290-336) */
-static void set_dispersive(world W, coeffs *C, matter *M, object *O, int n, int o, int tri)
+static void set_dispersive(world W, coeffs *C, matter *M, object *O, int n, int o, int tri, const geo_fill_t *dev)
 {
+	if (dev) {
+		for (int i=C->iMin[n]; i<=C->iMax[n]; i++) for (int j=C->jMin[n]; j<=C->jMax[n]; j++) for (int k=C->kMin[n]; k<=C->kMax[n]; k++) {
+			C->Jx[n][i][j][k] = GEO_AT(*dev, 0, i, j, k);
+			C->Jy[n][i][j][k] = GEO_AT(*dev, 1, i, j, k);
+			C->Jz[n][i][j][k] = GEO_AT(*dev, 2, i, j, k);
+		}
+	}
+	else {
 	#pragma omp parallel for schedule(guided)
 	for (int i=C->iMin[n]; i<=C->iMax[n]; i++) for (int j=C->jMin[n]; j<=C->jMax[n]; j++) for (int k=C->kMin[n]; k<=C->kMax[n]; k++) {
 		C->Jx[n][i][j][k] = fill_factor(W, O, o, i-0.5, j, k);
 		C->Jy[n][i][j][k] = fill_factor(W, O, o, i, j-0.5, k);
 		C->Jz[n][i][j][k] = fill_factor(W, O, o, i, j, k-0.5);
+	}
 	}
 
 	C->ax[n] = PI * W->dt * conductivity(W, M[o], 0) / (M[o].e.x ? M[o].e.x : M[o].e.x);
@@ -273,7 +439,8 @@ void putObjectArray(world W, matter *M, object *O)
 	printf("\rPreparing to put %d objects.\n", N);
 	/* sub-pixel sampling defaults: 1 if anything is dispersive, else 12 per axis */
 	W->subN = W->Res.spec.subN = W->Res.spec.subN ? W->Res.spec.subN : W->CE->N ? 1 : 12;
-	bounds *B = object_bounds(W, O, N);
+	geo_ctx *G = geo_build(W, O, N);                /* non-NULL: rasterise on the device (default; ALIS_DEVICE_GEOMETRY=0 or a user-written shape: host) */
+	bounds *B = G ? object_bounds_device(W, G, N) : object_bounds(W, O, N);
 	coeffs *C = W->CE;
 	alloc_material_tables(W, C, eps_eff(W, M[N], 0), eps_eff(W, M[N], 1), eps_eff(W, M[N], 2));
 	MALLOC(C->O, 0, N+1);
@@ -288,6 +455,8 @@ void putObjectArray(world W, matter *M, object *O)
 		float cy = eps_eff(W, M[o], 1) - eps_eff(W, M[N], 1);
 		float cz = eps_eff(W, M[o], 2) - eps_eff(W, M[N], 2);
 		const bounds b = B[o];
+		geo_fill_t dev;
+		if (G) dev = geo_fill_object(W, G, o, b);
 
 		printf("\rPutting objects: %d left.", o+1);
 		fflush(stdout);
@@ -301,7 +470,7 @@ void putObjectArray(world W, matter *M, object *O)
 			}
 			if (tri) C->NJ[n] /= 3, C->NK[n] /= 3;
 			alloc_dispersive(W, C, n, b);
-			set_dispersive(W, C, M, O, n, o, tri);
+			set_dispersive(W, C, M, O, n, o, tri, G ? &dev : 0);
 
 			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
 				BLEND(C->x[i][j][k], cx, C->Jx[n][i][j][k]);
@@ -314,6 +483,19 @@ void putObjectArray(world W, matter *M, object *O)
 				BLEND(C->y[i][b.jMax+1][k], cy, C->Jy[n][i][b.jMax+1][k]);
 			if (b.kMax == W->kMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++)
 				BLEND(C->z[i][j][b.kMax+1], cz, C->Jz[n][i][j][b.kMax+1]);
+		}
+		else if (G) {
+			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
+				BLEND(C->x[i][j][k], cx, GEO_AT(dev, 0, i, j, k));
+				BLEND(C->y[i][j][k], cy, GEO_AT(dev, 1, i, j, k));
+				BLEND(C->z[i][j][k], cz, GEO_AT(dev, 2, i, j, k));
+			}
+			if (b.iMax == W->iMAX) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->x[b.iMax+1][j][k], cx, GEO_AT(dev, 0, b.iMax+1, j, k));
+			if (b.jMax == W->jMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int k=b.kMin; k<=b.kMax; k++)
+				BLEND(C->y[i][b.jMax+1][k], cy, GEO_AT(dev, 1, i, b.jMax+1, k));
+			if (b.kMax == W->kMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++)
+				BLEND(C->z[i][j][b.kMax+1], cz, GEO_AT(dev, 2, i, j, b.kMax+1));
 		}
 		else {
 			#pragma omp parallel for schedule(guided)
@@ -329,9 +511,11 @@ void putObjectArray(world W, matter *M, object *O)
 			if (b.kMax == W->kMAX) for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++)
 				BLEND(C->z[i][j][b.kMax+1], cz, fill_factor(W, O, o, i, j, b.kMax+0.5));
 		}
+		if (G) for (int c=0; c<3; c++) free(dev.f[c]);
 	}
 
 	free(B);
+	geo_free(G);
 	printf("\rPutting objects: %d done.\n", N);
 	fflush(stdout);
 	alis_host_dirty(W, ALIS_DIRTY_MATERIALS | ALIS_DIRTY_SOURCES);

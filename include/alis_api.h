@@ -342,6 +342,7 @@ void alisSyncFields(world W);                 /* refresh every host view W->E[m]
 void alisSyncPhaser(phaser P);                /* refresh the host views P->xMin.Ey[...] ... of a phaser array          */
 void alisReadField(world W, int set, int comp, int m, float *dense);   /* raw block incl. ghosts, reference layout  */
 void alisWriteField(world W, int set, int comp, int m, const float *dense);
+unsigned long alisDeviceGeometryObjects(void); /* objects rasterised on the device so far (ALIS_DEVICE_GEOMETRY=0: host only) */
 unsigned long alisDeviceMonitorCalls(void);   /* slices / world reductions evaluated on the device so far (diagnostics) */
 const char *alisBackend(void);                /* "cuda-sm_100a"                                                     */
 

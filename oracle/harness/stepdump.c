@@ -91,6 +91,9 @@ int main(int argc, char **argv)
 	fclose(f);
 	printf("\n%s: %d steps, grid %dx%dx%d complex=%d n=%lu t=%g tE=%g tH=%g\n", cfg->name, steps, W->iNUM, W->jNUM, W->kNUM,
 		W->complexField, (unsigned long)W->n, W->t, W->E->t, W->H->t);
+#if defined(HARNESS_MODE_MINE)
+	fprintf(stderr, "device_geometry_objects %lu\n", alisDeviceGeometryObjects());
+#endif
 #if defined(HARNESS_MODE_BRIDGE)
 	printf("fused_launches=%lu\n", (unsigned long)alisb_fused_launch_count(alis_bridge_engine(B)));
 #endif
