@@ -144,8 +144,11 @@ static void alloc_material_tables(world W, coeffs *C, float ex, float ey, float 
 	C->x = makeField(W->iMIN, W->iMAX+1, W->jMIN, W->jMAX, W->kMIN, W->kMAX);
 	C->y = makeField(W->iMIN, W->iMAX, W->jMIN, W->jMAX+1, W->kMIN, W->kMAX);
 	C->z = makeField(W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX+1);
+	#pragma omp parallel for
 	for (int i=W->iMIN; i<=W->iMAX+1; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX; k++) C->x[i][j][k] = 1/ex;
+	#pragma omp parallel for
 	for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX+1; j++) for (int k=W->kMIN; k<=W->kMAX; k++) C->y[i][j][k] = 1/ey;
+	#pragma omp parallel for
 	for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX+1; k++) C->z[i][j][k] = 1/ez;
 }
 
@@ -382,6 +385,7 @@ static geo_fill_t geo_fill_object(world W, geo_ctx *G, int o, bounds b)
 static void set_dispersive(world W, coeffs *C, matter *M, object *O, int n, int o, int tri, const geo_fill_t *dev)
 {
 	if (dev) {
+		#pragma omp parallel for
 		for (int i=C->iMin[n]; i<=C->iMax[n]; i++) for (int j=C->jMin[n]; j<=C->jMax[n]; j++) for (int k=C->kMin[n]; k<=C->kMax[n]; k++) {
 			C->Jx[n][i][j][k] = GEO_AT(*dev, 0, i, j, k);
 			C->Jy[n][i][j][k] = GEO_AT(*dev, 1, i, j, k);
@@ -472,6 +476,7 @@ void putObjectArray(world W, matter *M, object *O)
 			alloc_dispersive(W, C, n, b);
 			set_dispersive(W, C, M, O, n, o, tri, G ? &dev : 0);
 
+			#pragma omp parallel for
 			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
 				BLEND(C->x[i][j][k], cx, C->Jx[n][i][j][k]);
 				BLEND(C->y[i][j][k], cy, C->Jy[n][i][j][k]);
@@ -485,6 +490,7 @@ void putObjectArray(world W, matter *M, object *O)
 				BLEND(C->z[i][j][b.kMax+1], cz, C->Jz[n][i][j][b.kMax+1]);
 		}
 		else if (G) {
+			#pragma omp parallel for
 			for (int i=b.iMin; i<=b.iMax; i++) for (int j=b.jMin; j<=b.jMax; j++) for (int k=b.kMin; k<=b.kMax; k++) {
 				BLEND(C->x[i][j][k], cx, GEO_AT(dev, 0, i, j, k));
 				BLEND(C->y[i][j][k], cy, GEO_AT(dev, 1, i, j, k));
