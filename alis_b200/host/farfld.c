@@ -561,7 +561,7 @@ static void far_field_pairs(phaser P, int n, const float *theta, const float *ph
 /* ---- angular maps and cuts (reference farfld.c:525-662) -------------------------------------------------------- */
 void farFieldProfile(world W, phaser P, projmap projMap, int X, int Y, ...)
 {
-	char *format, fieldname[4], filename[1024], fullname[1024];
+	char *format, fieldname[8] = "", filename[1024], fullname[1024];   /* png() looks at F[4] */
 	va_list ap;
 	va_start(ap, Y);
 	method M = va_arg(ap, method);
