@@ -5,16 +5,100 @@
  * The accumulators live on the GPU (alisb_phaser_*, kernel phaser_face): updatePhaser computes the
  * two phase factors per frequency on the host (same cexpf as the reference) and launches ONE
  * kernel per face for all frequencies.  The host arrays P->zMax.Ex[i][j][k] ... are views that
- * are refreshed lazily (alisSyncPhaser) when a library routine -- or the user -- needs them.
+ * are refreshed lazily: library routines call alisSyncPhaser; user code that indexes the arrays
+ * directly (reference examples/Cross_Polarization_T.c:3-19) is served by page protection -- while
+ * the device holds newer data the arrays are PROT_NONE, the first touch faults, the handler pulls
+ * the accumulators from the device and the access is retried (the scheme of managed memory).
  * Definitions follow reference src/phaser.c (cited per function).
  */
+#define _GNU_SOURCE
 #include <sys/stat.h>
+#include <sys/mman.h>
+#include <signal.h>
+#include <unistd.h>
 #include <string.h>
 #include "alis_c.h"
 #include "host_internal.h"
 
 static alisb_engine *engine_of(world W) { return alis_bridge_engine(alis_host_bridge(W)); }
 static phaser base_of(phaser P) { return P - P->b200_index; }
+
+/* ---- guarded host views -------------------------------------------------------------------------------
+ * Every phasor array's data block is page aligned and page sized, registered with the list it
+ * belongs to.  ALIS_PHASER_GUARD=0 turns the protection off (the arrays are then only valid after
+ * alisSyncPhaser). */
+typedef struct guard { char *lo; size_t bytes; phaser base; struct guard *next; } guard;
+static guard *guards;
+static struct sigaction chained;
+static int handler_installed;
+
+static int guard_enabled(void)
+{
+	static int mode = -1;
+	if (mode < 0) { const char *s = getenv("ALIS_PHASER_GUARD"); mode = s ? atoi(s) != 0 : 1; }
+	return mode;
+}
+
+static void guard_protect(phaser base, int prot)
+{
+	if (!guard_enabled()) return;
+	for (guard *g = guards; g; g = g->next) if (g->base == base) mprotect(g->lo, g->bytes, prot);
+}
+
+static void guard_fault(int sig, siginfo_t *si, void *ctx)
+{
+	const char *addr = (const char*)si->si_addr;
+	for (guard *g = guards; g; g = g->next) if (g->lo <= addr && addr < g->lo + g->bytes) {
+		phaser base = g->base;
+		guard_protect(base, PROT_READ | PROT_WRITE);     /* whatever happens next, the retry must not fault again */
+		alisSyncPhaser(base);
+		return;
+	}
+	/* not ours: hand over to whoever was installed before (or the default action) */
+	if ((chained.sa_flags & SA_SIGINFO) && chained.sa_sigaction) { chained.sa_sigaction(sig, si, ctx); return; }
+	if (!(chained.sa_flags & SA_SIGINFO) && chained.sa_handler != SIG_DFL && chained.sa_handler != SIG_IGN) { chained.sa_handler(sig); return; }
+	signal(sig, SIG_DFL);
+}
+
+/* makeComplexField with a page-aligned, page-sized data block registered for protection */
+static float complex ***make_guarded_field(phaser base, int iMin, int iMax, int jMin, int jMax, int kMin, int kMax)
+{
+	if (!guard_enabled()) return makeComplexField(iMin, iMax, jMin, jMax, kMin, kMax);
+	const long ni = 1-iMin+iMax, nj = 1-jMin+jMax, nk = 1-kMin+kMax;
+	const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+	const size_t bytes = (sizeof(float complex)*(size_t)ni*nj*nk + page - 1)/page*page;
+	float complex ***f, *data = 0;
+	MALLOC(f, iMin, ni);
+	MALLOC(f[iMin], jMin, ni*nj);
+	if (posix_memalign((void**)&data, page, bytes)) printf("Insufficient memory!\n"), exit(1);
+	memset(data, 0, bytes);
+	f[iMin][jMin] = data - kMin;
+	for (int i=iMin; i<=iMax; i++) {
+		f[i] = f[iMin] + nj*(i-iMin);
+		for (int j=jMin; j<=jMax; j++) f[i][j] = f[iMin][jMin] + nk*(nj*(i-iMin)+(j-jMin));
+	}
+	guard *g = malloc(sizeof *g);
+	g->lo = (char*)data; g->bytes = bytes; g->base = base; g->next = guards; guards = g;
+	if (!handler_installed) {
+		struct sigaction sa;
+		memset(&sa, 0, sizeof sa);
+		sa.sa_sigaction = guard_fault;
+		sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+		sigemptyset(&sa.sa_mask);
+		sigaction(SIGSEGV, &sa, &chained);
+		handler_installed = 1;
+	}
+	return f;
+}
+
+static void guard_release(phaser base)
+{
+	guard_protect(base, PROT_READ | PROT_WRITE);
+	for (guard **g = &guards; *g; ) {
+		if ((*g)->base == base) { guard *dead = *g; *g = dead->next; free(dead); }
+		else g = &(*g)->next;
+	}
+}
 
 /* face order used with the engine: 0 xMin, 1 xMax, 2 yMin, 3 yMax, 4 zMin, 5 zMax; the four
  * accumulators of a face are E(c+1), E(c+2), H(c+1), H(c+2) for face normal c */
@@ -91,7 +175,7 @@ phaser (createPhasers)(world W, float LMin, float LMax, float dL, float xMin, fl
 			face_box(p, face, b);
 			mask |= 1<<face;
 			for (int which=0; which<4; which++)
-				*slot_of(face_of(p, face), face/2, which) = makeComplexField(b[0], b[1], b[2], b[3], b[4], b[5]);
+				*slot_of(face_of(p, face), face/2, which) = make_guarded_field(P, b[0], b[1], b[2], b[3], b[4], b[5]);
 		}
 	}
 
@@ -134,7 +218,7 @@ void updatePhaser(world W, phaser P)
 		printf("alis-b200: %s\n", alisb_last_error());
 		exit(1);
 	}
-	B->b200_stale = 1;
+	if (!B->b200_stale) { B->b200_stale = 1; guard_protect(B, PROT_NONE); }      /* the device is ahead of the host views now */
 	free(wE); free(wH);
 }
 
@@ -150,6 +234,7 @@ void alisSyncPhaser(phaser P)
 {
 	phaser B = base_of(P);
 	if (!B->b200_dev || !B->b200_stale) return;
+	guard_protect(B, PROT_READ | PROT_WRITE);
 	for (phaser p = B; p->f; p++) for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
 		float complex ***A = *slot_of(face_of(p, face), face/2, which);
 		if (!A) continue;
@@ -164,6 +249,7 @@ void alisSyncPhaser(phaser P)
 void deletePhaser(phaser P)
 {
 	phaser B = base_of(P);
+	guard_release(B);
 	if (B->b200_dev) alisb_phaser_destroy(B->b200_dev);
 	for (phaser p = B; p->f; p++) {
 		for (int face=0; face<6; face++) for (int which=0; which<4; which++) {

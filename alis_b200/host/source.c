@@ -158,15 +158,54 @@ void (pointDipole)(world W, field F, float x, float y, float z, waveform waveFor
 	refresh_period(W, wavelength);
 }
 
-/* ---- guided-wave sources need a mode profile from an HDF5 file (reference source.c:127-220) ------ */
-static void no_guided_wave(const char *which, const char *file)
+/* ---- guided-wave sources (reference source.c:127-220) ----------------------------------------------
+ * A plane source over the whole cross-section at x, y or z whose per-cell amplitude is a mode
+ * profile read from <file>.h5 (normally written earlier by sliceFreqDom(..., h5, ...) of a mode
+ * calculation: Waveguide_Dispersion.c -> Waveguide_Propagation.c).  The profile's last row/column
+ * is aligned with the world's upper edge, so a profile computed on a mirror-symmetric world (which
+ * stores the mirror image too) fits a world with or without the mirror. */
+static void guided_wave(world W, int axis, char *file, field F, float pos, waveform waveForm, float wavelength, float supplement, float amplitude, float phase)
 {
-	printf("alis-b200: %s(\"%s\"): guided-wave sources need HDF5 input, which is not built into this library.\n", which, file);
-	exit(0);
+	const int b = axis == 0 ? 1 : 0, c = axis == 2 ? 1 : 2;          /* the two transverse axes, in index order */
+	const int minSur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
+	const int Min[3] = { W->iMin, W->jMin, W->kMin }, Max[3] = { W->iMax, W->jMax, W->kMax };
+	float *cosk[3] = { &W->coskx, &W->cosky, &W->coskz };
+	const int at = axis == 0 ? W->xtoi(W, pos) : axis == 1 ? W->ytoj(W, pos) : W->ztok(W, pos);
+
+	if (minSur[b]==SYM) *cosk[b] = along(F, b) ? 1 : -1;
+	if (minSur[c]==SYM) *cosk[c] = along(F, c) ? 1 : -1;
+	if (minSur[axis]==SYM && !at) *cosk[axis] = along(F, axis) ? 1 : -1;
+	if (minSur[axis]==SYM && !*cosk[axis]) *cosk[axis] = along(F, axis) ? -1 : 1;
+	alis_host_dirty(W, ALIS_DIRTY_COPIES);
+
+	if (waveForm) {
+		int d[2];
+		float **f = h5read(d, "%s", file);
+		if (!amplitude) amplitude = 1;
+		source S = new_source(W, F, waveForm, wavelength, supplement, amplitude);
+
+		if (d[0] != 1+Max[b]+(minSur[b]==SYM?Max[b]:-Min[b])) printf("The dimension of guided wave does not match!\n"), exit(0);
+		if (d[1] != 1+Max[c]+(minSur[c]==SYM?Max[c]:-Min[c])) printf("The dimension of guided wave does not match!\n"), exit(0);
+		S->phase = phase * PI / 180;
+		S->iMin = W->iMin, S->iMax = W->iMax;
+		S->jMin = W->jMin, S->jMax = W->jMax;
+		S->kMin = W->kMin, S->kMax = W->kMax;
+		if (axis == 0) S->iMin = S->iMax = at;
+		if (axis == 1) S->jMin = S->jMax = at;
+		if (axis == 2) S->kMin = S->kMax = at;
+		S->Amplitude = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
+		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++) {
+			const int q[3] = { i, j, k };
+			S->Amplitude[i][j][k] = amplitude * f[q[b]-Max[b]+d[0]-1][q[c]-Max[c]+d[1]-1];
+		}
+		free(f[0]); free(f);
+	}
+	refresh_period(W, wavelength);
 }
-void (guidedWaveX)(world W, char *file, field F, float x, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { (void)W; (void)F; (void)x; (void)waveForm; (void)wavelength; (void)supplement; (void)amplitude; (void)phase; no_guided_wave("guidedWaveX", file); }
-void (guidedWaveY)(world W, char *file, field F, float y, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { (void)W; (void)F; (void)y; (void)waveForm; (void)wavelength; (void)supplement; (void)amplitude; (void)phase; no_guided_wave("guidedWaveY", file); }
-void (guidedWaveZ)(world W, char *file, field F, float z, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { (void)W; (void)F; (void)z; (void)waveForm; (void)wavelength; (void)supplement; (void)amplitude; (void)phase; no_guided_wave("guidedWaveZ", file); }
+
+void (guidedWaveX)(world W, char *file, field F, float x, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { guided_wave(W, 0, file, F, x, waveForm, wavelength, supplement, amplitude, phase); }
+void (guidedWaveY)(world W, char *file, field F, float y, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { guided_wave(W, 1, file, F, y, waveForm, wavelength, supplement, amplitude, phase); }
+void (guidedWaveZ)(world W, char *file, field F, float z, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...) { guided_wave(W, 2, file, F, z, waveForm, wavelength, supplement, amplitude, phase); }
 
 /* ---- total-field / scattered-field region (reference source.c:251-334) ---------------------------- */
 

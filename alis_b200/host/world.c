@@ -9,6 +9,7 @@
 #include <string.h>
 #include "alis_c.h"
 #include "host_internal.h"
+#include "h5lite.h"
 
 /* ---- coordinate <-> index maps ------------------------------------------------------------ */
 
@@ -328,17 +329,43 @@ void deleteCloneWorld(world W)
 }
 
 /* HDF5 is not available in this image: the I/O helpers (reference world.c:469-537) report it */
+/* reference world.c:469-517: the first dataset of <name>.h5 as float*, float** or float*** (row
+ * pointers into one block), dimensions into dim[].  libhdf5 is replaced by h5lite.c. */
 void *h5read(int *dim, char *format, ...)
 {
-	(void)dim;
-	printf("alis-b200: h5read(\"%s\"): HDF5 support is not built into this library.\n", format);
-	exit(0);
-	return 0;
+	va_list ap;
+	char name[1024], err[200];
+	unsigned long long dims[3];
+	int N = 0;
+	va_start(ap, format);
+	vsprintf(name, format, ap);
+	va_end(ap);
+	float *data = h5lite_read(strcat(name, ".h5"), &N, dims, err, sizeof err);
+	if (!data) { printf("alis-b200: h5read(\"%s\"): %s\n", name, err); exit(0); }
+	if (dim) for (int n=0; n<N; n++) dim[n] = dims[n];
+	if (N == 1) return data;
+	if (N == 2) {
+		float **f = calloc(dims[0], sizeof(float*));
+		for (unsigned long long i=0; i<dims[0]; i++) f[i] = data + dims[1]*i;
+		return f;
+	}
+	float ***f = calloc(dims[0], sizeof(float**));
+	f[0] = calloc(dims[0]*dims[1], sizeof(float*));
+	for (unsigned long long i=1; i<dims[0]; i++) f[i] = f[0] + dims[1]*i;
+	for (unsigned long long i=0; i<dims[0]; i++) for (unsigned long long j=0; j<dims[1]; j++) f[i][j] = data + dims[2]*(dims[1]*i + j);
+	return f;
 }
 
+/* reference world.c:520-537: dataset "data" of the non-zero dimensions in <name>.h5 */
 void h5write(int *dim, float *p, char *format, ...)
 {
-	(void)dim; (void)p;
-	static int warned;
-	if (!warned++) printf("alis-b200: h5write(\"%s\"): HDF5 support is not built into this library; output skipped.\n", format);
+	va_list ap;
+	char filename[1024];
+	int d = 0;
+	unsigned long long dims[3] = {0};
+	va_start(ap, format);
+	vsprintf(filename, format, ap);
+	va_end(ap);
+	for (int n=0; n<3; n++) if (dim[n]) dims[d++] = dim[n];
+	if (h5lite_write(strcat(filename, ".h5"), d, dims, p)) { printf("alis-b200: h5write: cannot write %s\n", filename); exit(0); }
 }

@@ -1,8 +1,8 @@
 #!/bin/sh
 # Builds the UNMODIFIED reference (hseelab/alis, /root/reference/src/*.c) into
 # oracle/_ref/ with the reference's own flags (reference src/Makefile:2-4:
-# gcc -fopenmp -O3 -std=c99 -fpic), using two stub headers for the libraries that
-# are absent from this image (hdf5.h, png.h).  Test infrastructure only: the
+# gcc -fopenmp -O3 -std=c99 -fpic), using two shim headers for the libraries that
+# are absent from this image (hdf5.h -> this repo's minimal HDF5 reader/writer, png.h -> no-ops).  Test infrastructure only: the
 # products (libalis_ref.so/.a, abench, harness binaries) are used as the parity
 # checker and as the CPU baseline; nothing under alis_b200/ links or loads them.
 # Sources are compiled where they lie; nothing is copied into the repo.
@@ -21,6 +21,10 @@ for f in world object shapes source update output slices fields phaser farfld; d
 		gcc $CFLAGS -c "$REF/src/$f.c" -o "$OUT/obj/$f.o"
 	fi
 done
+# the hdf5.h shim maps the reference's H5* calls onto this repo's minimal HDF5 reader/writer
+gcc -std=c99 -O2 -fpic -w -c "$HERE/../alis_b200/host/h5lite.c" -o "$OUT/obj/h5lite.o"
+# world.o must pick up a changed shim
+if [ "$HERE/shim/hdf5.h" -nt "$OUT/obj/world.o" ]; then gcc $CFLAGS -c "$REF/src/world.c" -o "$OUT/obj/world.o"; fi
 rm -f "$OUT/libalis_ref.a"
 ar rcs "$OUT/libalis_ref.a" "$OUT"/obj/*.o
 gcc -shared -fopenmp -o "$OUT/libalis_ref.so" "$OUT"/obj/*.o -lm

@@ -203,6 +203,53 @@ static world cfg_bloch_wide(void)
 	return W;
 }
 
+/* examples/Waveguide_Propagation.c:6-16: a guided mode launched from a profile file.  The profiles
+ * are synthetic (analytic), written with h5write and read back by guidedWaveY/X/Z (reference
+ * source.c:127-220): covers the HDF5 round trip, the alignment of a profile that includes the
+ * mirror image with a SYM world, and the per-cell amplitude plane source. */
+static void guided_profile(const char *name, int n0, int n1, int o0, int o1, float scale, int odd)
+{
+	int d[3] = { n0, 0, n1 };
+	float *p = calloc((size_t)n0*n1, sizeof(float));
+	for (int a=0; a<n0; a++) for (int b=0; b<n1; b++) {
+		const float u = 10.0f*(a-o0), v = 10.0f*(b-o1);
+		p[(size_t)a*n1+b] = scale * (odd ? u/100 : 1) * expf(-(u*u+v*v)/sq(120.0f));
+	}
+	h5write(d, p, "%s", name);
+	free(p);
+}
+
+static world cfg_guided_y(void)
+{
+	dom Dom = {{300}, {400}, {-200, 300}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{SYM, PML}, {PML, PML}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Waveguide = {Box, {{ -50,  50}, {-INF, INF}, { -50,  50}}};
+	object Substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF, -50}}};
+	putObjects(W, n(4), Waveguide, n(1.5), Substrate, Air);
+	guided_profile("harness_guided_a", 1+2*W->iMax, 1+W->kMax-W->kMin, W->iMax, -W->kMin, 1.0f, 0);
+	guided_profile("harness_guided_b", 1+2*W->iMax, 1+W->kMax-W->kMin, W->iMax, -W->kMin, 0.4f, 1);
+	guidedWaveY(W, "harness_guided_a", Ex, -200, Sine, 625, 10, 1, 0);
+	guidedWaveY(W, "harness_guided_b", Ez, -200, Sine, 625, 10, 0.5, 90);
+	return W;
+}
+
+static world cfg_guided_xz(void)
+{
+	dom Dom = {{-250, 350}, {300}, {350}};
+	res Res = {5, {10}, {1240}};
+	sur Sur = {{PML, PML}, {PML, PML}, {SYM, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Waveguide = {Box, {{-INF, INF}, { -60,  60}, { -40,  40}}};
+	putObjects(W, n(3.2), Waveguide, Air);
+	guided_profile("harness_guided_c", 1+W->jMax-W->jMin, 1+2*W->kMax, -W->jMin, W->kMax, 1.0f, 0);
+	guided_profile("harness_guided_d", 1+W->iMax-W->iMin, 1+W->jMax-W->jMin, -W->iMin, -W->jMin, 0.2f, 0);
+	guidedWaveX(W, "harness_guided_c", Ey, -150, Pulse, 600, 900, 1, 0);
+	guidedWaveZ(W, "harness_guided_d", Hy, 200, Sine, 625, 10, 1, 30);
+	return W;
+}
+
 static const harness_config harness_configs[] = {
 	{"dipole_pml",  cfg_dipole_pml,  60, 0},
 	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
@@ -215,6 +262,8 @@ static const harness_config harness_configs[] = {
 	{"dipole_band", cfg_dipole_band, 80, 0},
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
 	{"bloch_wide",  cfg_bloch_wide,  70, 0},
+	{"guided_y",    cfg_guided_y,    110, 0},
+	{"guided_xz",   cfg_guided_xz,   110, 0},
 	{"chi2_shg",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, 0, 0.7f, 0},
 	{"chi2_twm",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, cfg_chi2_pump2, -1.3f, 0},
 	{"chi2_alias",  cfg_chi2b_signal, 80, 0, cfg_chi2b_pump1, 0, 0.9f, 1},

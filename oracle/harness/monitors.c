@@ -11,6 +11,18 @@
 
 static void emit(const char *tag, double v) { printf("%-28s % .9g\n", tag, v); }
 
+/* user code indexing the phasor arrays directly, as reference examples/Cross_Polarization_T.c:3-19
+ * does: no library call in between that could refresh them */
+static double direct_phasor_sum(phaser Q)
+{
+	double s = 0;
+	for (int i=Q->iMin; i<=Q->iMax; i++) for (int j=Q->jMin; j<=Q->jMax; j++) {
+		const float complex e = Q->zMax.Ex[i][j][Q->kMax], h = Q->zMax.Hy[i][j][Q->kMax];
+		s += crealf(e*conjf(h)) + 0.5*cabsf(Q->zMax.Ey[i][j][Q->kMax]);
+	}
+	return s;
+}
+
 /* a slice "writer" that prints checksums of the sampled slice instead of a file: user-supplied
  * methods are part of the API (sliceSnap only special-cases png) */
 static void checksum(world W, slice S, float Max, char *F, char *filename, unsigned long int *cmap)
@@ -45,7 +57,7 @@ int main(int argc, char **argv)
 	if (is_band) P = createPhasers(W, 400, 800, 50);
 	slice XY = createSliceXY(W, 0), XZ = createSliceXZ(W, 0);
 
-	double flux_in = 0, flux_out = 0, probe = 0, absn = 0;
+	double flux_in = 0, flux_out = 0, probe = 0, absn = 0, direct_mid = 0;
 	object Nanoblock = {Box, {{-200, 200}, {-200, 200}, {-200, 200}}};
 	for (int s=1; s<=steps; s++) {
 		if (cfg->order) updateH(W); else updateE(W);
@@ -53,6 +65,7 @@ int main(int argc, char **argv)
 		if (cfg->order) updateE(W); else updateH(W);
 		if (is_nano) { flux_in += poyntingIn(W,-250, 250,-250, 250,-250, 250); flux_out += poyntingOut(W,-350, 350,-350, 350,-350, 350); absn += objectAbsorption(W, Nanoblock); }
 		if (P && steps - s < 40) updatePhaser(W, P);
+		if (P && steps - s == 25) direct_mid = direct_phasor_sum(is_band ? choosePhaser(P, 500) : P);
 		probe += get(W, is_phc ? Hz : Ez, 20, 10, 30);
 	}
 	emit("t", W->t); emit("n", W->n);
@@ -104,6 +117,7 @@ int main(int argc, char **argv)
 	if (is_nano) { emit("flux_in", flux_in); emit("flux_out", flux_out); emit("absorption", absn); }
 	if (P) {
 		phaser Q = is_band ? choosePhaser(P, 500) : P;
+		emit("phasor_direct_mid", direct_mid); emit("phasor_direct_end", direct_phasor_sum(Q));
 		emit("phaser_f", Q->f); emit("phaser_A", Q->A); emit("phaser_N", Q->N);
 		emit("phaserPoyntingOut", phaserPoyntingOut(Q));
 		float complex a = farField(Q, Ppol, 20, 30), b = farField(Q, Spol, 140, 250);

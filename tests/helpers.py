@@ -11,7 +11,8 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 CONFIGS = ["dipole_pml", "vacuum_cpml", "pec_box", "pbc_slab", "nanoblock", "tfsf_normal",
-           "phc", "metasurface", "dipole_band", "aniso_ade", "bloch_wide", "chi2_shg", "chi2_twm", "chi2_alias"]
+           "phc", "metasurface", "dipole_band", "aniso_ade", "bloch_wide", "chi2_shg", "chi2_twm", "chi2_alias",
+           "guided_y", "guided_xz"]
 
 
 MONITOR_CONFIGS = ["nanoblock", "metasurface", "dipole_band", "phc", "dipole_pml", "aniso_ade"]
