@@ -21,7 +21,7 @@ def test_own_setup_reproduces_reference_fields(cfg, tmp_path):
 @needs_bins
 @pytest.mark.parametrize("cfg", helpers.MONITOR_CONFIGS)
 def test_monitor_values_equal_reference(cfg):
-    got = helpers.run_monitors("monitors_mine_oracle", cfg)
+    got = helpers.run_monitors("monitors_mine_oracle", cfg, direct_phasor=True)
     want = helpers.golden_monitors()[cfg]
     assert len(want) > 35
     bad = helpers.monitor_mismatches(got, want)
@@ -36,3 +36,22 @@ def test_device_monitors_equal_host_view_monitors(cfg):
     dev = helpers.run_monitors("monitors_mine_oracle", cfg)
     host = helpers.run_monitors("monitors_mine_oracle", cfg, host_monitors=True)
     assert len(dev) > 250 and dev == host
+
+
+@needs_bins
+@pytest.mark.parametrize("cfg", ["metasurface", "dipole_band"])
+def test_phasor_arrays_are_coherent_for_direct_user_access(cfg):
+    """user code indexing P->zMax.Ex[i][j][k] itself (reference examples/Cross_Polarization_T.c:3-19):
+    the page-protection guard refreshes the host views on first touch -- same values as with an
+    explicit alisSyncPhaser and as the reference; with the guard off the views are stale (zero)"""
+    want = {w[0]: w[1] for w in helpers.golden_monitors()[cfg]}
+    for direct in (True, False):
+        got = {g[0]: g[1] for g in helpers.run_monitors("monitors_mine_oracle", cfg, direct_phasor=direct)}
+        for tag in ("phasor_direct_mid", "phasor_direct_end"):
+            assert got[tag] == want[tag] and float(want[tag]) != 0, (tag, direct)
+    import os
+    import subprocess
+    env = dict(os.environ, HARNESS_DIRECT_PHASOR="1", ALIS_PHASER_GUARD="0")
+    r = subprocess.run([os.path.join(helpers.TEST_BIN, "monitors_mine_oracle"), cfg, "0"], env=env, capture_output=True, text=True, timeout=900)
+    stale = dict(line.split() for line in r.stdout.splitlines() if line.startswith("phasor_direct"))
+    assert float(stale["phasor_direct_mid"]) == 0 and float(stale["phasor_direct_end"]) == 0
