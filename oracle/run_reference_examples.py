@@ -22,6 +22,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("ALIS_REFERENCE", "/root/reference")
+# command lines of the examples that take arguments; examples that consume another example's output
+# run in that example's directory (Waveguide_Propagation reads the .h5 mode profiles that
+# Waveguide_Dispersion 3.0 wrote)
+ARGS = {"Cross_Polarization_T": ["300", "120", "80", "200"], "Waveguide_Dispersion": ["3.0"]}
+RUN_IN = {"Waveguide_Propagation": "Waveguide_Dispersion"}
 
 
 def build(src, exe, mine):
@@ -38,7 +43,7 @@ def tables(root):
     out = {}
     for d, _, files in os.walk(root):
         for f in files:
-            if f.endswith(".txt") and f != "log.txt":
+            if f.endswith(".txt") and not f.startswith("log"):
                 try:
                     out[os.path.relpath(os.path.join(d, f), root)] = np.atleast_2d(np.loadtxt(os.path.join(d, f)))
                 except Exception:
@@ -52,27 +57,40 @@ def main():
     ap.add_argument("--reuse", action="store_true", help="compare the outputs already under --work (run_<name>_{ref,mine}/)")
     ap.add_argument("--timeout", type=int, default=400)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_reference_examples_cpu.json"))
+    ap.add_argument("--only", default="", help="comma-separated example names: rerun these and merge into --out")
     a = ap.parse_args()
     os.makedirs(a.work, exist_ok=True)
     report = {"host_threads": os.cpu_count(), "engine_of_our_twin": "CPU oracle (tests/bin/libalis_oracle.so)", "examples": {}}
+    only = [x for x in a.only.split(",") if x]
+    if only and os.path.exists(a.out):
+        report = json.load(open(a.out))
     for src in sorted(glob.glob(os.path.join(REF, "examples", "*.c"))):
         name = os.path.basename(src)[:-2]
-        rec = {}
+        if only and name not in only:
+            continue
+        rec = {"args": ARGS.get(name, [])}
         for tag in ("ref", "mine"):
-            d = os.path.join(a.work, f"run_{name}_{tag}")
+            d = os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_{tag}")
             if not a.reuse:
-                subprocess.run(["rm", "-rf", d])
-                os.makedirs(d)
+                if name not in RUN_IN:
+                    subprocess.run(["rm", "-rf", d])
+                os.makedirs(d, exist_ok=True)
                 rec[tag + "_builds"] = build(src, os.path.join(d, name), tag == "mine")
                 env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "tests", "bin") + os.pathsep + os.path.join(ROOT, "oracle"))
                 t0 = time.time()
                 try:
-                    r = subprocess.run(["./" + name], cwd=d, env=env, stdout=open(os.path.join(d, "log.txt"), "w"), stderr=subprocess.STDOUT, timeout=a.timeout)
+                    r = subprocess.run(["./" + name] + ARGS.get(name, []), cwd=d, env=env, stdout=open(os.path.join(d, f"log_{name}.txt"), "w"), stderr=subprocess.STDOUT, timeout=a.timeout)
                     rec[tag + "_rc"] = r.returncode
                 except subprocess.TimeoutExpired:
                     rec[tag + "_rc"] = "timeout"
                 rec[tag + "_seconds"] = round(time.time() - t0, 1)
-        ta, tb = tables(os.path.join(a.work, f"run_{name}_ref")), tables(os.path.join(a.work, f"run_{name}_mine"))
+        ta, tb = tables(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_ref")), tables(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_mine"))
+        h5 = [os.path.relpath(os.path.join(d_, f), os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_ref"))
+              for d_, _, fs in os.walk(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_ref")) for f in fs if f.endswith(".h5")]
+        if h5:
+            same = sum(open(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_ref", f), "rb").read() ==
+                       (open(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_mine", f), "rb").read() if os.path.exists(os.path.join(a.work, f"run_{RUN_IN.get(name, name)}_mine", f)) else b"") for f in h5)
+            rec["h5_files_byte_identical"] = f"{same}/{len(h5)}"
         cmp_ = {}
         for k in sorted(set(ta) | set(tb)):
             if k not in ta or k not in tb:
