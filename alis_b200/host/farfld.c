@@ -15,6 +15,7 @@
  * per 4096 queries (alisb_phaser_surface_sums).
  */
 #include <sys/stat.h>
+#include <sys/time.h>
 #include <string.h>
 #include "alis_c.h"
 #include "host_internal.h"
@@ -258,11 +259,15 @@ typedef struct { float complex *w; int lo, hi; } wvec;
 
 typedef struct { int face, which; int lo_vec, hi_vec; } ff_job;       /* indices into ff_ctx.vec */
 typedef struct { float complex *w; int len; const float complex *key; } ff_vec;
+/* plane-wave weight vectors depend on (axis, staggering, range, k) only: the faces and the two
+ * polarisations of one direction share them */
+typedef struct { int axis, cell_type, lo, hi; float kq; wvec v; } ff_cached;
 typedef struct {
 	int replay;
 	/* record */
 	ff_job *job; int njob, capjob;
 	ff_vec *vec; int nvec, capvec;
+	ff_cached cache[8]; int ncache;
 	/* replay */
 	const double *result; int next;
 } ff_ctx;
@@ -270,6 +275,7 @@ typedef struct {
 static void ctx_free(ff_ctx *c)
 {
 	for (int q=0; q<c->nvec; q++) free(c->vec[q].w);
+	for (int q=0; q<c->ncache; q++) free(&c->cache[q].v.w[c->cache[q].v.lo]);
 	free(c->vec); free(c->job);
 	memset(c, 0, sizeof *c);
 }
@@ -284,6 +290,7 @@ static wvec vec_alloc(ff_ctx *c, int lo, int hi)
 static void vec_free(ff_ctx *c, wvec v)
 {
 	if (!v.w) return;
+	for (int q=0; q<c->ncache; q++) if (c->cache[q].v.w == v.w) return;      /* owned by the cache until ctx_free */
 	for (int q=0; q<c->nvec; q++) if (c->vec[q].key == v.w) c->vec[q].key = 0;
 	free(&v.w[v.lo]);
 }
@@ -294,12 +301,17 @@ static wvec plane_wave_weights(ff_ctx *c, world W, int axis, int lo, int hi, flo
 	float (*coord)(world, float) = axis==0 ? W->itox : W->jtoy;
 	const int sym = (axis==0 ? W->xMinSur : W->yMinSur) == SYM;
 	const float cosk = axis==0 ? W->coskx : W->cosky;
+	if (!c->replay) for (int q=0; q<c->ncache; q++) {
+		const ff_cached *e = &c->cache[q];
+		if (e->axis == axis && e->cell_type == cell_type && e->lo == lo && e->hi == hi && e->kq == kq) return e->v;
+	}
 	wvec v = vec_alloc(c, lo, hi);
 	if (c->replay) return v;
 	for (int q = cell_type ? lo+1 : lo; q<=hi; q++) {
 		v.w[q] = d[q] * cexpf(I*kq*coord(W, cell_type ? q-0.5 : q));
 		if (sym) { if (cell_type) v.w[q] += conjf(v.w[q]) * cosk; else v.w[q] -= conjf(v.w[q]) * cosk; }
 	}
+	if (c->ncache < 8) { ff_cached *e = &c->cache[c->ncache++]; e->axis = axis; e->cell_type = cell_type; e->lo = lo; e->hi = hi; e->kq = kq; e->v = v; }
 	return v;
 }
 
@@ -486,31 +498,41 @@ static float complex far_field_eval(ff_ctx *c, phaser P, tfield pol(phaser,float
 	return Sum * T.A * P->A * P->f;
 }
 
-/* n queries (pol[q], theta[q], phi[q]) -> out[q]; the surface sums of a chunk of queries are one
- * device call */
+/* n directions, each with one or two polarisations (P and S share the plane-wave weights) ->
+ * out[q][k]; the surface sums of a chunk of directions are one device call */
 #define FF_CHUNK 4096
 typedef tfield (*polfn)(phaser, float, float);
-static void far_field_batch(phaser P, int n, const polfn *pol, const float *theta, const float *phi, float complex *out)
+typedef struct { polfn pol[2]; int npol; float theta, phi; } ff_query;
+
+static double wall_seconds(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + 1e-6*tv.tv_usec; }
+
+static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*out)[2])
 {
+	const int timing = getenv("ALIS_FF_TIMING") != 0;       /* prints where a sweep spends its time */
+	double t_rec = 0, t_pack = 0, t_dev = 0, t_rep = 0, t0;
+	size_t tot_jobs = 0, tot_w = 0;
 	ensure_ready(P);
 	int freq = 0;
 	alisb_phaser *dev = alis_phaser_device(P, &freq);
-	if (!dev) { for (int q=0; q<n; q++) out[q] = 0; return; }      /* no absorbing face: nothing was recorded */
+	if (!dev) { for (int q=0; q<n; q++) out[q][0] = out[q][1] = 0; return; }      /* no absorbing face: nothing was recorded */
 	ff_ctx *ctx = calloc(FF_CHUNK, sizeof *ctx);
-	size_t *job0 = malloc(sizeof(size_t)*(FF_CHUNK+1));
+	size_t *job0 = malloc(sizeof(size_t)*(FF_CHUNK+1)), *w0 = malloc(sizeof(size_t)*(FF_CHUNK+1));
 	for (int base=0; base<n; base+=FF_CHUNK) {
 		const int m = MIN(FF_CHUNK, n-base);
+		t0 = wall_seconds();
 		#pragma omp parallel for schedule(dynamic, 16)
-		for (int q=0; q<m; q++) far_field_eval(&ctx[q], P, pol[base+q], theta[base+q], phi[base+q]);
+		for (int q=0; q<m; q++) for (int k=0; k<Q[base+q].npol; k++) far_field_eval(&ctx[q], P, Q[base+q].pol[k], Q[base+q].theta, Q[base+q].phi);
+		t_rec += wall_seconds() - t0; t0 = wall_seconds();
 		size_t njobs = 0, nw = 0;
-		for (int q=0; q<m; q++) { job0[q] = njobs; njobs += ctx[q].njob; for (int v=0; v<ctx[q].nvec; v++) nw += ctx[q].vec[v].len; }
-		job0[m] = njobs;
+		for (int q=0; q<m; q++) { job0[q] = njobs; w0[q] = nw; njobs += ctx[q].njob; for (int v=0; v<ctx[q].nvec; v++) nw += ctx[q].vec[v].len; }
+		job0[m] = njobs; w0[m] = nw;
+		if (nw > 0xFFFFFFFFu) { printf("alis-b200: far-field batch too large\n"); exit(1); }
 		alisb_surface_job *jobs = malloc(sizeof *jobs*(njobs+1));
 		float complex *weights = malloc(sizeof *weights*(nw+1));
 		double *sums = malloc(sizeof(double)*2*(njobs+1));
-		size_t w = 0;
+		#pragma omp parallel for schedule(static)
 		for (int q=0; q<m; q++) {
-			size_t off[ctx[q].nvec+1];
+			size_t off[ctx[q].nvec+1], w = w0[q];
 			for (int v=0; v<ctx[q].nvec; v++) { off[v] = w; memcpy(weights+w, ctx[q].vec[v].w, sizeof(float complex)*ctx[q].vec[v].len); w += ctx[q].vec[v].len; }
 			for (int j=0; j<ctx[q].njob; j++) {
 				alisb_surface_job *J = &jobs[job0[q]+j];
@@ -519,24 +541,31 @@ static void far_field_batch(phaser P, int n, const polfn *pol, const float *thet
 			}
 			ctx_free(&ctx[q]);
 		}
+		t_pack += wall_seconds() - t0; t0 = wall_seconds();
 		if (alisb_phaser_surface_sums(dev, freq, jobs, (int)njobs, (const float*)weights, nw, sums) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		t_dev += wall_seconds() - t0; t0 = wall_seconds();
+		tot_jobs += njobs; tot_w += nw;
 		#pragma omp parallel for schedule(dynamic, 16)
 		for (int q=0; q<m; q++) {
 			ff_ctx r = { 0 };
 			r.replay = 1; r.result = sums + 2*job0[q];
-			out[base+q] = far_field_eval(&r, P, pol[base+q], theta[base+q], phi[base+q]);
+			out[base+q][0] = out[base+q][1] = 0;
+			for (int k=0; k<Q[base+q].npol; k++) out[base+q][k] = far_field_eval(&r, P, Q[base+q].pol[k], Q[base+q].theta, Q[base+q].phi);
 		}
+		t_rep += wall_seconds() - t0;
 		free(jobs); free(weights); free(sums);
 	}
-	free(ctx); free(job0);
+	free(ctx); free(job0); free(w0);
+	if (timing) fprintf(stderr, "[alis far field] %d directions, %zu surface sums, %zu weights: record %.3f s, pack %.3f s, engine %.3f s, replay %.3f s\n",
+	                    n, tot_jobs, tot_w, t_rec, t_pack, t_dev, t_rep);
 }
 
 float complex farField(phaser P, tfield pol(phaser,float,float), float theta, float phi)
 {
-	float complex f = 0;
-	polfn p = pol;
-	far_field_batch(P, 1, &p, &theta, &phi, &f);
-	return f;
+	float complex f[1][2];
+	ff_query q = { { pol, 0 }, 1, theta, phi };
+	far_field_batch(P, 1, &q, f);
+	return f[0][0];
 }
 
 float farFieldI(phaser P, tfield pol(phaser,float,float), float theta, float phi)
@@ -549,13 +578,12 @@ float farFieldI(phaser P, tfield pol(phaser,float,float), float theta, float phi
 /* P- and S-polarised far field towards n directions */
 static void far_field_pairs(phaser P, int n, const float *theta, const float *phi, float complex *p, float complex *s)
 {
-	polfn *pol = malloc(sizeof(polfn)*2*n);
-	float *th = malloc(sizeof(float)*2*n), *ph = malloc(sizeof(float)*2*n);
-	float complex *f = malloc(sizeof(float complex)*2*n);
-	for (int q=0; q<n; q++) { pol[2*q] = Ppol; pol[2*q+1] = Spol; th[2*q] = th[2*q+1] = theta[q]; ph[2*q] = ph[2*q+1] = phi[q]; }
-	far_field_batch(P, 2*n, pol, th, ph, f);
-	for (int q=0; q<n; q++) { p[q] = f[2*q]; s[q] = f[2*q+1]; }
-	free(pol); free(th); free(ph); free(f);
+	ff_query *Q = malloc(sizeof(ff_query)*(n+1));
+	float complex (*f)[2] = malloc(sizeof(float complex)*2*(n+1));
+	for (int q=0; q<n; q++) { Q[q].pol[0] = Ppol; Q[q].pol[1] = Spol; Q[q].npol = 2; Q[q].theta = theta[q]; Q[q].phi = phi[q]; }
+	far_field_batch(P, n, Q, f);
+	for (int q=0; q<n; q++) { p[q] = f[q][0]; s[q] = f[q][1]; }
+	free(Q); free(f);
 }
 
 /* ---- angular maps and cuts (reference farfld.c:525-662) -------------------------------------------------------- */
