@@ -250,6 +250,58 @@ static world cfg_guided_xz(void)
 	return W;
 }
 
+/* every built-in shape type of reference shapes.c:17-221 once (28 objects on a 4 x 3 x 3 raster of
+ * 200 nm cells, sub-pixel sampling 3^3), so that each predicate -- and each branch of the device
+ * shape interpreter -- is pinned against the unmodified reference through the permittivity arrays */
+#define ZOO_BOX(cx,cy,cz,rx,ry,rz) {{(cx)-(rx), (cx)+(rx)}, {(cy)-(ry), (cy)+(ry)}, {(cz)-(rz), (cz)+(rz)}}
+static world cfg_shape_zoo(void)
+{
+	dom Dom = {{-400, 400}, {-300, 300}, {-300, 300}};
+	res Res = {5, {10}, {1240, 3}};
+	sur Sur = {{PML, PML}, {PML, PML}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	static object O[29];
+	static matter M[29];
+	shape *prim[18] = { Box, Ball, Diamond, BiconeX, BiconeY, BiconeZ, RodX, RodY, RodZ, DRodX, DRodY, DRodZ,
+	                    HRodXY, HRodYZ, HRodZX, HRodXZ, HRodYX, HRodZY };
+	int q = 0;
+	#define ZOO_AT(q) const float cx = -300 + 200*((q)%4), cy = -200 + 200*(((q)/4)%3), cz = -200 + 200*((q)/12)
+	for (; q<18; q++) {
+		ZOO_AT(q);
+		O[q] = (object){prim[q], ZOO_BOX(cx, cy, cz, 71, 63, 77)};
+	}
+	/* compound objects: the children live in static arrays (a compound literal dies with its block) */
+	static object kids[10][3];
+	#define ZOO_KID(slot, idx, S_, ...) kids[slot][idx] = (object){S_, __VA_ARGS__}
+	{ ZOO_AT(q); ZOO_KID(0, 0, Ball, ZOO_BOX(cx-13.5, cy+7.25, cz-21, 60, 70, 50));
+	  O[q++] = (object){Translation, {{13.5, -7.25, 21}}, kids[0]}; }
+	{ ZOO_AT(q); ZOO_KID(1, 0, Box, ZOO_BOX(0, 0, 0, 70, 30, 45));
+	  O[q++] = (object){Rotation, {{20, 35, 50}, {cx, cy, cz}}, kids[1]}; }
+	{ ZOO_AT(q); ZOO_KID(2, 0, RodZ, ZOO_BOX(cx-30, cy, cz, 30, 40, 80)); ZOO_KID(2, 1, Box, ZOO_BOX(cx+20, cy+10, cz, 50, 20, 30)); ZOO_KID(2, 2, Ball, ZOO_BOX(cx, cy-40, cz+30, 35, 35, 35));
+	  O[q++] = (object){Combination, {{3}}, kids[2]}; }
+	{ ZOO_AT(q); ZOO_KID(3, 0, Ball, ZOO_BOX(cx, cy, cz, 80, 80, 80)); ZOO_KID(3, 1, DRodZ, ZOO_BOX(cx+10, cy, cz, 60, 90, 50));
+	  O[q++] = (object){Intersection, {{2}}, kids[3]}; }
+	{ ZOO_AT(q); ZOO_KID(4, 0, Box, ZOO_BOX(cx, cy, cz, 80, 80, 40)); ZOO_KID(4, 1, RodZ, ZOO_BOX(cx-30, cy-30, cz, 25, 25, 100)); ZOO_KID(4, 2, Ball, ZOO_BOX(cx+35, cy+35, cz+40, 30, 30, 30));
+	  O[q++] = (object){Difference, {{3}}, kids[4]}; }
+	{ ZOO_AT(q); ZOO_KID(5, 0, Box, ZOO_BOX(cx, cy, cz, 18, 60, 22));
+	  O[q++] = (object){Lattice, {{60, 3}, {0}, {70, 2}}, kids[5]}; }
+	{ ZOO_AT(q); ZOO_KID(6, 0, RodZ, ZOO_BOX(cx, cy, cz, 22, 22, 1000));
+	  ZOO_KID(7, 0, Box, ZOO_BOX(cx, cy, cz, 85, 85, 60)); ZOO_KID(7, 1, DLattice, {{80}, {80*1.7320508f}}, kids[6]);
+	  O[q++] = (object){Intersection, {{2}}, kids[7]}; }
+	{ ZOO_AT(q); ZOO_KID(8, 0, Box, ZOO_BOX(cx, cy+45, cz, 60, 18, 14));
+	  O[q++] = (object){CLatticeX, {{3}, {cy, cz}}, kids[8]}; }
+	{ ZOO_AT(q); ZOO_KID(8, 1, Diamond, ZOO_BOX(cx+45, cy, cz, 30, 60, 25));
+	  O[q++] = (object){CLatticeY, {{4}, {cx, cz}}, &kids[8][1]}; }
+	{ ZOO_AT(q); ZOO_KID(8, 2, Ball, ZOO_BOX(cx+50, cy, cz, 28, 20, 60));
+	  O[q++] = (object){CLatticeZ, {{5}, {cx, cy}}, &kids[8][2]}; }
+	for (int o=0; o<q; o++) M[o] = n(1.3f + 0.1f*(o%9));
+	M[q] = Air;
+	O[q] = (object){0};
+	putObjectArray(W, M, O);
+	pointDipole(W, Ex, 5, -5, 15, Pulse, 500, 700);
+	return W;
+}
+
 static const harness_config harness_configs[] = {
 	{"dipole_pml",  cfg_dipole_pml,  60, 0},
 	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
@@ -262,6 +314,7 @@ static const harness_config harness_configs[] = {
 	{"dipole_band", cfg_dipole_band, 80, 0},
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
 	{"bloch_wide",  cfg_bloch_wide,  70, 0},
+	{"shape_zoo",   cfg_shape_zoo,   90, 0},
 	{"guided_y",    cfg_guided_y,    110, 0},
 	{"guided_xz",   cfg_guided_xz,   110, 0},
 	{"chi2_shg",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, 0, 0.7f, 0},

@@ -18,7 +18,7 @@ from tests import helpers
 F32 = np.float32
 INF = float(np.finfo(np.float32).max)
 needs_bins = pytest.mark.skipif(not helpers.have_test_bin("stepdump_mine_oracle"), reason="tests/bin not built (run __graft_entry__.build())")
-OBJECT_CONFIGS = ["nanoblock", "phc", "metasurface", "aniso_ade", "pbc_slab", "tfsf_normal"]
+OBJECT_CONFIGS = ["nanoblock", "phc", "metasurface", "aniso_ade", "pbc_slab", "tfsf_normal", "shape_zoo", "guided_y"]
 
 
 def uniform(dx):
@@ -144,7 +144,7 @@ def test_cuda_rasteriser_bit_exact(oracle_lib, engine_lib, subn):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["1", "0"])
-@pytest.mark.parametrize("cfg", ["nanoblock", "phc", "aniso_ade"])
+@pytest.mark.parametrize("cfg", ["nanoblock", "phc", "aniso_ade", "shape_zoo"])
 def test_dropin_with_device_and_host_rasteriser(cfg, mode, tmp_path):
     out = str(tmp_path / "m.bin")
     env = dict(os.environ, ALIS_DEVICE_GEOMETRY=mode)
