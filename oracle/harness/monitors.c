@@ -85,6 +85,26 @@ int main(int argc, char **argv)
 	emit("get_DivE", get(W, DivE, 10, 20, 30)); emit("get_RI", get(W, RI, 10, 20, 30)); emit("get_eEff", get(W, eEff, 10, 20, -150));
 	emit("get_Jx", get(W, Jx, 10, 20, 30)); emit("get_JE", get(W, JE, 10, 20, 30)); emit("get_Fz", get(W, Fz, 10, 20, 30));
 	emit("get_ScEx", get(W, ScEx, 10, 20, 30)); emit("get_ScEE", get(W, ScEE, 10, 20, 30)); emit("get_SoEz", get(W, SoEz, 10, 20, 30)); emit("get_SoEE", get(W, SoEE, 10, 20, 30));
+	/* every remaining public field function at two points (one of them a mirror image on SYM worlds);
+	 * non-finite values (log of zero, 0/0 of a dispersive model at W->f = 0) are printed as class codes */
+	{
+		struct { const char *name; field *F; } rest[] = {
+			{"Contour", Contour}, {"ContourRI", ContourRI}, {"EyHz", EyHz}, {"EzHy", EzHy}, {"Fx", Fx}, {"Fy", Fy},
+			{"JxHy", JxHy}, {"JxHz", JxHz}, {"Jy", Jy}, {"JyHx", JyHx}, {"JyHz", JyHz}, {"Jz", Jz}, {"JzHx", JzHx}, {"JzHy", JzHy},
+			{"LogEE", LogEE}, {"LogHH", LogHH}, {"LogJE", LogJE}, {"LogRI", LogRI}, {"LogU", LogU}, {"LogUE", LogUE}, {"LogUH", LogUH},
+			{"ScEy", ScEy}, {"ScEz", ScEz}, {"SoEx", SoEx}, {"SoEy", SoEy}, {"Txz", Txz}, {"Tyx", Tyx}, {"Tzy", Tzy}, {"UE", UE}, {"UH", UH},
+			{"iEy", iEy}, {"iHy", iHy}, {"rawEx", rawEx}, {"rawEy", rawEy}, {"rawEz", rawEz}, {"rawHx", rawHx}, {"rawHy", rawHy}, {"rawHz", rawHz},
+			{"rawJx", rawJx}, {"rawJy", rawJy}, {"rawJz", rawJz}, {"raweEffx", raweEffx}, {"raweEffy", raweEffy}, {"raweEffz", raweEffz},
+			{"ExHy", ExHy}, {"ExHz", ExHz}, {"EyHx", EyHx}, {"EzHx", EzHx}, {"Tyy", Tyy}, {"Tzz", Tzz}, {"Jx", Jx}, {"eEff", eEff}, {"RI", RI}
+		};
+		char tag[64];
+		for (unsigned q=0; q<sizeof rest/sizeof rest[0]; q++) for (int pt=0; pt<2; pt++) {
+			/* second point: mirrored only along axes that have a mirror plane (elsewhere it would lie outside the domain) */
+			const float v = pt ? get(W, rest[q].F, W->xMinSur==SYM ? -30 : 30, W->yMinSur==SYM ? -20 : 20, W->zMinSur==SYM ? -10 : 10) : get(W, rest[q].F, 10, 20, 30);
+			sprintf(tag, "at%d_%s", pt, rest[q].name);
+			emit(tag, isfinite(v) ? v : isnan(v) ? -7777 : v > 0 ? 8888 : -8888);
+		}
+	}
 	emit("worldMax_Ez", worldMax(W, Ez)); emit("worldSum_U", worldSum(W, U));
 	emit("sliceMax_XY_EE", sliceMax(W, EE, XY)); emit("sliceSum_XZ_U", sliceSum(W, U, XZ));
 	emit("poyntingX", poyntingX(W, 100)); emit("poyntingY", poyntingY(W, 50, -100, 100, -80, 120)); emit("poyntingZ", poyntingZ(W, 100, -150, 150));
