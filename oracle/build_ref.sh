@@ -36,6 +36,7 @@ INC="-I$HERE/shim -I$REF/src -I$HERE/harness -I$HERE/../include -I$HOSTDIR"
 gcc -std=c99 -fopenmp -O3 -w -DHARNESS_MODE_REF $INC "$HERE/harness/stepdump.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/stepdump_ref"
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/bench_cube.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/bench_cube_ref"
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/monitors.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/monitors_ref"
+gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/api_misc.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/api_misc_ref"
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/putobjects_bench.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/putobjects_bench_ref"
 # the example drivers (ours, examples/*.c) linked against the reference: the CPU twins used for
 # output and wall-time comparison on the GPU box

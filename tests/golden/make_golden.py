@@ -41,3 +41,16 @@ for cfg in helpers.MONITOR_CONFIGS:
     print(cfg, len(mon[cfg]), "monitor values")
 with open(os.path.join(helpers.GOLDEN, "monitor_values.json"), "w") as f:
     json.dump(mon, f, indent=1)
+
+# the remaining public API (clone / reboot / removeSources / removeObjects / LT / nkFile / phasor fluxes):
+# oracle/harness/api_misc.c linked against the reference
+import subprocess  # noqa: E402
+with tempfile.TemporaryDirectory() as tmp:
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([os.path.join(helpers.REF_BIN, "api_misc_ref")], cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-500:]
+    vals = helpers.parse_tag_values(r.stdout)
+    assert vals and vals[-1][0] == "done"
+    print("api_misc", len(vals), "values")
+with open(os.path.join(helpers.GOLDEN, "api_misc_values.json"), "w") as f:
+    json.dump(vals, f, indent=1)

@@ -52,6 +52,32 @@ def run_monitors(binary, config, threads=None, steps=0, host_monitors=False, dir
     return vals
 
 
+def parse_tag_values(stdout):
+    """'tag value' lines of a harness program -> ordered [[tag, text value]]"""
+    vals = []
+    for line in stdout.splitlines():
+        parts = line.split()
+        if len(parts) == 2 and not line.startswith(("Preparing", "Putting")):
+            try:
+                float(parts[1])
+            except ValueError:
+                continue
+            vals.append([parts[0], parts[1]])
+    return vals
+
+
+def run_api_misc(binary, cwd):
+    r = subprocess.run([os.path.join(TEST_BIN, binary)], cwd=cwd, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return parse_tag_values(r.stdout)
+
+
+def golden_api_misc():
+    with open(os.path.join(GOLDEN, "api_misc_values.json")) as f:
+        return json.load(f)
+
+
 def monitor_mismatches(got, want, device_flux=False):
     """Value-by-value comparison of two monitors.c outputs.  Everything must be identical to the
     printed digit (%.9g) except

@@ -55,3 +55,12 @@ def test_phasor_arrays_are_coherent_for_direct_user_access(cfg):
     r = subprocess.run([os.path.join(helpers.TEST_BIN, "monitors_mine_oracle"), cfg, "0"], env=env, capture_output=True, text=True, timeout=900)
     stale = dict(line.split() for line in r.stdout.splitlines() if line.startswith("phasor_direct"))
     assert float(stale["phasor_direct_mid"]) == 0 and float(stale["phasor_direct_end"]) == 0
+
+
+@needs_bins
+def test_remaining_public_api_equals_reference(tmp_path):
+    """cloneWorld, rebootWorld, removeSources, removeObjects + new objects, LT, nkFile, phaserPoynting*,
+    deleteCloneWorld / deletePhasers / deleteWorld (oracle/harness/api_misc.c): every value as the
+    unmodified reference prints it"""
+    got, want = helpers.run_api_misc("api_misc_mine_oracle", str(tmp_path)), helpers.golden_api_misc()
+    assert len(want) >= 28 and got == want, [(g, w) for g, w in zip(got, want) if g != w][:5]

@@ -163,3 +163,12 @@ def test_phasor_guard_on_gpu(cfg):
     got = helpers.run_monitors("monitors_mine_cuda", cfg, direct_phasor=True)
     want = helpers.golden_monitors()[cfg]
     assert not helpers.monitor_mismatches(got, want, device_flux=True)
+
+
+@pytest.mark.gpu
+def test_remaining_public_api_on_gpu(tmp_path):
+    """cloneWorld, rebootWorld, removeSources, removeObjects + new objects ... (oracle/harness/api_misc.c)
+    with the CUDA engine: every value as the unmodified reference prints it (flux values reduced on
+    the device to 5e-6)"""
+    got, want = helpers.run_api_misc("api_misc_mine_cuda", str(tmp_path)), helpers.golden_api_misc()
+    assert not helpers.monitor_mismatches(got, want, device_flux=True)
