@@ -302,6 +302,117 @@ static world cfg_shape_zoo(void)
 	return W;
 }
 
+/* randomised differential test: a world drawn from the seed in the environment variable FUZZ_SEED --
+ * cell sizes (isotropic or not), time step, domain, flat (2-D) axes, boundary types per axis (PML with
+ * several depths incl. true CPML, mirror, PEC, periodic, Bloch -> complex fields), graded grids, sub-pixel
+ * sampling, up to three objects of dielectric / dispersive / anisotropic matter, one or two point
+ * dipoles of random component, waveform and phase.  Only the public API is used; every draw stays
+ * inside what the reference handles without undefined behaviour. */
+static unsigned fuzz_state;
+static unsigned fuzz_next(void) { fuzz_state = fuzz_state*1664525u + 1013904223u; return fuzz_state >> 8; }
+static int fuzz_int(int lo, int hi) { return lo + (int)(fuzz_next() % (unsigned)(hi-lo+1)); }
+static float fuzz_pick(const float *v, int n) { return v[fuzz_next() % n]; }
+
+static world cfg_fuzz(void)
+{
+	const char *seed = getenv("FUZZ_SEED");
+	fuzz_state = seed ? (unsigned)atoi(seed)*2654435761u + 12345u : 1u;
+	for (int q=0; q<4; q++) fuzz_next();
+	static const float cell[3] = {10, 12.5f, 20};
+	const float dx = fuzz_pick(cell, 3);
+	const int aniso = fuzz_int(0, 3) == 0;
+	const float dy = aniso ? fuzz_pick(cell, 3) : dx, dz = aniso ? fuzz_pick(cell, 3) : dx;
+	const float dmin = MIN(dx, MIN(dy, dz));
+	res Res = {(fuzz_int(0, 1) ? 0.5f : 0.4f)*dmin, {dx, dy, dz}, {1240, (int[]){0, 1, 2, 4}[fuzz_int(0, 3)]}};
+	dom Dom; sur Sur = {{0}};
+	float *dlo[3] = {&Dom.x.Min, &Dom.y.Min, &Dom.z.Min}, *dhi[3] = {&Dom.x.Max, &Dom.y.Max, &Dom.z.Max};
+	float *slo[3] = {&Sur.x.MinSur, &Sur.y.MinSur, &Sur.z.MinSur}, *shi[3] = {&Sur.x.MaxSur, &Sur.y.MaxSur, &Sur.z.MaxSur};
+	const float d[3] = {dx, dy, dz};
+	int sym[3] = {0, 0, 0}, flat[3] = {0, 0, 0}, pml[3] = {0, 0, 0};
+	const int tfsf_mode = fuzz_int(0, 3) == 0;                /* every fourth world is laid out so that a TFSF plane wave fits */
+	const int flat_axis = tfsf_mode ? 5 : fuzz_int(0, 5);     /* 0..2: that axis is flat (2-D world), else 3-D */
+	for (int a=0; a<3; a++) {
+		const float half = d[a]*fuzz_int(6, 11);
+		*dlo[a] = -half - d[a]*fuzz_int(0, 3); *dhi[a] = half;
+		switch (tfsf_mode ? (a < 2 ? fuzz_int(0, 1) : 0) : fuzz_int(0, 5)) {
+		case 0: *slo[a] = PML; *shi[a] = PML; pml[a] = 1; break;
+		case 1: *slo[a] = SYM; *shi[a] = PML; sym[a] = 1; pml[a] = 1; *dlo[a] = half; *dhi[a] = 0; break;
+		case 2: *slo[a] = PBC; *shi[a] = 0; break;
+		case 3: *slo[a] = BBC; *shi[a] = (*dhi[a] - *dlo[a])*(2 + fuzz_int(0, 3)*0.75f); break;
+		case 4: *slo[a] = PEC; *shi[a] = fuzz_int(0, 1) ? PEC : PML; pml[a] = *shi[a] == PML; break;
+		default: *slo[a] = PML; *shi[a] = fuzz_int(0, 1) ? PML : PEC; pml[a] = 1; break;
+		}
+		if (a == flat_axis) { flat[a] = 1; *dlo[a] = *dhi[a] = 0; *slo[a] = PBC; *shi[a] = 0; sym[a] = 0; pml[a] = 0; }
+	}
+	Sur.pml.Num = (int[]){0, 6, 8, 24}[fuzz_int(0, 3)];
+	if (!tfsf_mode && fuzz_int(0, 3) == 0) for (int a=0; a<3; a++) if (pml[a] && !flat[a]) {      /* graded grid outside +-4 cells on one absorbing axis */
+		if (a == 0) Res.nug.x.m = 3, Res.nug.x.Min = 4*d[a];
+		if (a == 1) Res.nug.y.m = 3, Res.nug.y.Min = 4*d[a];
+		if (a == 2) Res.nug.z.m = 2, Res.nug.z.Min = 4*d[a];
+		break;
+	}
+	world W = createWorld(Dom, Res, Sur, "");
+	fprintf(stderr, "fuzz: d=%g,%g,%g dt=%g sur=%g/%g %g/%g %g/%g num=%d flat=%d nug=%d%d%d subN=%d\n", dx, dy, dz, Res.dt,
+		Sur.x.MinSur, Sur.x.MaxSur, Sur.y.MinSur, Sur.y.MaxSur, Sur.z.MinSur, Sur.z.MaxSur, Sur.pml.Num, flat_axis, Res.nug.x.m, Res.nug.y.m, Res.nug.z.m, Res.spec.subN);
+
+	static object O[4];
+	static matter M[4];
+	static object kid[3];
+	const int nobj = fuzz_int(0, 3);
+	matter Lossy = {{2.25}, {{0, 0.35}, {2.1, 0.3, 1.7}}};
+	matter Aniso = {{2.0, 3.0, 4.0}, {{8.0, 0.05}, {7.0, 0.06}, {6.0, 0.07}, {2.5, 0.3, 0.4, 0.2}, {2.7, 0.25, 0.5, 0.1}, {2.9, 0.2, 0.6, 0.3}}};
+	for (int o=0; o<nobj; o++) {
+		const float cx = flat[0] ? 0 : d[0]*fuzz_int(-3, 3), cy = flat[1] ? 0 : d[1]*fuzz_int(-3, 3), cz = flat[2] ? 0 : d[2]*fuzz_int(-3, 3);
+		const float rx = flat[0] ? INF : d[0]*(2 + 0.5f*fuzz_int(0, 6)), ry = flat[1] ? INF : d[1]*(2 + 0.5f*fuzz_int(0, 6)), rz = flat[2] ? INF : d[2]*(2 + 0.5f*fuzz_int(0, 6));
+		shape *S[6] = {Box, Ball, RodZ, Diamond, DRodX, BiconeY};
+		shape *pick = S[fuzz_int(0, 5)];
+		if (flat[0] || flat[1] || flat[2]) pick = Box;          /* infinite extents: only the box predicate is meaningful */
+		object base = {pick, {{cx-rx, cx+rx}, {cy-ry, cy+ry}, {cz-rz, cz+rz}}};
+		if (fuzz_int(0, 4) == 0 && pick != Box) { kid[o] = base; O[o] = (object){Translation, {{d[0], -d[1], 0.5f*d[2]}}, &kid[o]}; }
+		else O[o] = base;
+		switch (fuzz_int(0, 5)) {
+		case 0: M[o] = n(1.5); break;
+		case 1: M[o] = n(3.4); break;
+		case 2: M[o] = Au; break;
+		case 3: M[o] = Ag; break;
+		case 4: M[o] = Lossy; break;
+		default: M[o] = Aniso; break;
+		}
+	}
+	M[nobj] = fuzz_int(0, 2) ? Air : n(1.3);
+	O[nobj] = (object){0};
+	if (nobj) putObjectArray(W, M, O);
+
+	/* sometimes a normal-incidence TFSF plane wave (its auxiliary 1-D world is stepped first every pass):
+	 * only on 3-D real worlds whose x and y sides absorb or mirror and whose z sides absorb */
+	{
+		const int ok_xy = (Sur.x.MinSur==PML || Sur.x.MinSur==SYM) && Sur.x.MaxSur==PML && (Sur.y.MinSur==PML || Sur.y.MinSur==SYM) && Sur.y.MaxSur==PML;
+		const int want = tfsf_mode;
+		if (want && ok_xy && Sur.z.MinSur==PML && Sur.z.MaxSur==PML && flat_axis > 2 && !W->complexField && !Res.nug.x.m && !Res.nug.y.m && !Res.nug.z.m) {
+			dom DTF = {{sym[0] ? W->xMax-3*d[0] : W->xMin+3*d[0], sym[0] ? 0 : W->xMax-3*d[0]},
+			           {sym[1] ? W->yMax-3*d[1] : W->yMin+3*d[1], sym[1] ? 0 : W->yMax-3*d[1]},
+			           {W->zMin+3*d[2], W->zMax-3*d[2]}};
+			const float wl = 40*dmin*(1 + 0.25f*fuzz_int(0, 4));
+			fprintf(stderr, "fuzz: tfsf\n");
+			if (fuzz_int(0, 1)) planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, fuzz_int(0, 1) ? 0 : 180, 0, Pulse, wl, 1.5f*wl);
+			else planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, 0, 90.0f*fuzz_int(0, 1), Sine, wl, 3);
+		}
+	}
+
+	field *Fre[6] = {Ex, Ey, Ez, Hx, Hy, Hz}, *Fim[6] = {iEx, iEy, iEz, iHx, iHy, iHz};
+	waveform *Wf[3] = {Pulse, Sine, Band};
+	for (int s=0, ns=fuzz_int(1, 2); s<ns; s++) {
+		field *F = (W->complexField && fuzz_int(0, 2) == 0) ? Fim[fuzz_int(0, 5)] : Fre[fuzz_int(0, 5)];
+		float p[3];
+		for (int a=0; a<3; a++) p[a] = flat[a] ? 0 : sym[a] ? d[a]*fuzz_int(0, 3) : d[a]*fuzz_int(-3, 3);
+		const int w = fuzz_int(0, 2);
+		const float wl = 40*dmin*(1 + 0.25f*fuzz_int(0, 4));
+		if (w == 1) pointDipole(W, F, p[0], p[1], p[2], Sine, wl, 3 + fuzz_int(0, 3), 1, 30.0f*fuzz_int(0, 5));
+		else pointDipole(W, F, p[0], p[1], p[2], Wf[w], wl, wl*(1.5f + 0.25f*fuzz_int(0, 3)), 1 + fuzz_int(0, 1));
+	}
+	return W;
+}
+
 static const harness_config harness_configs[] = {
 	{"dipole_pml",  cfg_dipole_pml,  60, 0},
 	{"vacuum_cpml", cfg_vacuum_cpml, 60, 0},
@@ -315,6 +426,7 @@ static const harness_config harness_configs[] = {
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
 	{"bloch_wide",  cfg_bloch_wide,  70, 0},
 	{"shape_zoo",   cfg_shape_zoo,   90, 0},
+	{"fuzz",        cfg_fuzz,        40, 0},
 	{"guided_y",    cfg_guided_y,    110, 0},
 	{"guided_xz",   cfg_guided_xz,   110, 0},
 	{"chi2_shg",    cfg_chi2_signal, 80, 0, cfg_chi2_pump1, 0, 0.7f, 0},

@@ -1,0 +1,62 @@
+"""Randomised differential test against the UNMODIFIED reference (oracle/_ref/bin/stepdump_ref):
+worlds drawn from a seed -- cell sizes, time step, flat axes, boundary types per axis (PML depths
+incl. true CPML, mirror, PEC, periodic, Bloch/complex), graded grids, sub-pixel sampling, up to three
+objects of dielectric / dispersive / anisotropic matter, a normal-incidence TFSF plane wave in every
+fourth world, one or two dipoles (oracle/harness/configs.h,
+cfg_fuzz) -- are stepped by the reference and by this repo; the complete field state must be
+identical to the bit.  No goldens: both sides run live, so the reference build must be present
+(it travels to the GPU box with the snapshot).
+
+CPU: own host layer over the oracle engine (both rasterisers) and reference set-up + oracle engine
+through the bridge.  GPU: own host layer + CUDA engine, reference set-up + CUDA engine."""
+import os
+import subprocess
+
+import pytest
+
+from tests import helpers
+
+REF = os.path.join(helpers.REF_BIN, "stepdump_ref")
+needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="reference twin not built (oracle/build_ref.sh needs /root/reference)")
+CPU_SEEDS = list(range(1, 121))
+# 3-D CPML, anisotropic cells, TFSF (with and without objects, Num 24), flat axis + graded grid, Bloch/complex
+# with mirror and PEC sides, three objects, graded 3-D grid
+GPU_SEEDS = [5, 7, 9, 16, 20, 23, 29, 32, 41, 59, 67, 76]
+
+
+def dump(exe, seed, out, cwd, **env):
+    e = dict(os.environ, FUZZ_SEED=str(seed), **env)
+    r = subprocess.run([exe, "fuzz", "0", out], cwd=cwd, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, f"{os.path.basename(exe)} seed {seed}: rc {r.returncode}\n{r.stdout[-800:]}\n{r.stderr[-800:]}"
+    if not os.path.exists(out):
+        # a drawn object that owns no grid node: both libraries print the reference's message and exit(0)
+        assert "is zero!" in r.stdout, r.stdout[-400:]
+        return "volume-of-object-is-zero", "no dump"
+    return helpers.sha256_file(out), r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", CPU_SEEDS)
+def test_random_world_matches_reference_cpu(seed, tmp_path):
+    if not helpers.have_test_bin("stepdump_mine_oracle"):
+        pytest.skip("tests/bin not built")
+    t = str(tmp_path)
+    want, what = dump(REF, seed, os.path.join(t, "r.bin"), t, OMP_NUM_THREADS="2")
+    got, _ = dump(os.path.join(helpers.TEST_BIN, "stepdump_mine_oracle"), seed, os.path.join(t, "m.bin"), t)
+    assert got == want, f"seed {seed}: own host layer (engine rasteriser) differs from the reference [{what}]"
+    got, _ = dump(os.path.join(helpers.TEST_BIN, "stepdump_mine_oracle"), seed, os.path.join(t, "h.bin"), t, ALIS_DEVICE_GEOMETRY="0")
+    assert got == want, f"seed {seed}: own host layer (host rasteriser) differs from the reference [{what}]"
+    got, _ = dump(os.path.join(helpers.REF_BIN, "stepdump_bridge_oracle"), seed, os.path.join(t, "b.bin"), t)
+    assert got == want, f"seed {seed}: reference set-up + oracle engine differs from the reference [{what}]"
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", GPU_SEEDS)
+def test_random_world_matches_reference_gpu(seed, tmp_path):
+    t = str(tmp_path)
+    want, what = dump(REF, seed, os.path.join(t, "r.bin"), t)
+    got, _ = dump(os.path.join(helpers.TEST_BIN, "stepdump_mine_cuda"), seed, os.path.join(t, "m.bin"), t)
+    assert got == want, f"seed {seed}: drop-in library on the GPU differs from the reference [{what}]"
+    got, _ = dump(os.path.join(helpers.REF_BIN, "stepdump_bridge_cuda"), seed, os.path.join(t, "b.bin"), t)
+    assert got == want, f"seed {seed}: reference set-up + CUDA engine differs from the reference [{what}]"
