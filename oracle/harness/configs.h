@@ -329,10 +329,11 @@ static world cfg_fuzz(void)
 	float *slo[3] = {&Sur.x.MinSur, &Sur.y.MinSur, &Sur.z.MinSur}, *shi[3] = {&Sur.x.MaxSur, &Sur.y.MaxSur, &Sur.z.MaxSur};
 	const float d[3] = {dx, dy, dz};
 	int sym[3] = {0, 0, 0}, flat[3] = {0, 0, 0}, pml[3] = {0, 0, 0};
+	const int big = getenv("FUZZ_BIG") != 0;                  /* 3-D worlds of at least +-180 nm: the fixed probe positions of monitors.c fit */
 	const int tfsf_mode = fuzz_int(0, 3) == 0;                /* every fourth world is laid out so that a TFSF plane wave fits */
-	const int flat_axis = tfsf_mode ? 5 : fuzz_int(0, 5);     /* 0..2: that axis is flat (2-D world), else 3-D */
+	const int flat_axis = tfsf_mode || big ? 5 : fuzz_int(0, 5);     /* 0..2: that axis is flat (2-D world), else 3-D */
 	for (int a=0; a<3; a++) {
-		const float half = d[a]*fuzz_int(6, 11);
+		const float half = big ? d[a]*ceilf(180/d[a] + fuzz_int(0, 3)) : d[a]*fuzz_int(6, 11);
 		*dlo[a] = -half - d[a]*fuzz_int(0, 3); *dhi[a] = half;
 		switch (tfsf_mode ? (a < 2 ? fuzz_int(0, 1) : 0) : fuzz_int(0, 5)) {
 		case 0: *slo[a] = PML; *shi[a] = PML; pml[a] = 1; break;

@@ -23,7 +23,7 @@ def have_test_bin(name):
     return os.path.exists(os.path.join(TEST_BIN, name))
 
 
-def run_monitors(binary, config, threads=None, steps=0, host_monitors=False, direct_phasor=False):
+def run_monitors(binary, config, threads=None, steps=0, host_monitors=False, direct_phasor=False, extra_env=None):
     """runs oracle/harness/monitors.c (reference- or own-library build) -> ordered [(tag, text value)]
     host_monitors: ALIS_HOST_MONITORS=1, i.e. every monitor through the host views instead of the
     device-side evaluation"""
@@ -32,6 +32,7 @@ def run_monitors(binary, config, threads=None, steps=0, host_monitors=False, dir
     env.pop("ALIS_HOST_MONITORS", None)
     if host_monitors:
         env["ALIS_HOST_MONITORS"] = "1"
+    env.update(extra_env or {})
     env.pop("HARNESS_DIRECT_PHASOR", None)
     if direct_phasor:                    # the harness indexes the phasor arrays without refreshing them first
         env["HARNESS_DIRECT_PHASOR"] = "1"

@@ -60,3 +60,33 @@ def test_random_world_matches_reference_gpu(seed, tmp_path):
     assert got == want, f"seed {seed}: drop-in library on the GPU differs from the reference [{what}]"
     got, _ = dump(os.path.join(helpers.REF_BIN, "stepdump_bridge_cuda"), seed, os.path.join(t, "b.bin"), t)
     assert got == want, f"seed {seed}: reference set-up + CUDA engine differs from the reference [{what}]"
+
+
+MONITOR_SEEDS_CPU = list(range(1, 25))
+MONITOR_SEEDS_GPU = [2, 9, 14, 23]
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", MONITOR_SEEDS_CPU)
+def test_random_world_monitors_match_reference_cpu(seed):
+    """the monitor harness (about 390 values: every field function, probes, flux boxes, world and slice
+    reductions, slice checksums, time-averaged and frequency-domain slices) on random 3-D worlds large
+    enough for its fixed probe positions (FUZZ_BIG): identical to the printed digit"""
+    if not helpers.have_test_bin("monitors_mine_oracle"):
+        pytest.skip("tests/bin not built")
+    env = {"FUZZ_SEED": str(seed), "FUZZ_BIG": "1"}
+    want = helpers.run_monitors("monitors_ref", "fuzz", threads=1, extra_env=env)
+    got = helpers.run_monitors("monitors_mine_oracle", "fuzz", extra_env=env)
+    assert len(want) > 350
+    assert not helpers.monitor_mismatches(got, want), f"seed {seed}"
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", MONITOR_SEEDS_GPU)
+def test_random_world_monitors_match_reference_gpu(seed):
+    env = {"FUZZ_SEED": str(seed), "FUZZ_BIG": "1"}
+    want = helpers.run_monitors("monitors_ref", "fuzz", threads=1, extra_env=env)
+    got = helpers.run_monitors("monitors_mine_cuda", "fuzz", extra_env=env)
+    assert len(want) > 350
+    assert not helpers.monitor_mismatches(got, want, device_flux=True), f"seed {seed}"
