@@ -60,6 +60,9 @@ int main(int argc, char **argv)
 	phaser P = 0;
 	if (is_meta) P = createPhaser(W, 500,-2000, 2000,-2000, 2000);
 	if (is_band) P = createPhasers(W, 400, 800, 50);
+	/* random worlds: a two-frequency list on whatever absorbing faces the world has */
+	const int is_fuzz = !strcmp(cfg->name, "fuzz");
+	if (is_fuzz && (W->xMaxSur==PML || W->yMaxSur==PML || W->zMaxSur==PML)) P = createPhasers(W, 400, 600, 200);
 	slice XY = createSliceXY(W, 0), XZ = createSliceXZ(W, 0);
 
 	double flux_in = 0, flux_out = 0, probe = 0, absn = 0, direct_mid = 0;
@@ -70,7 +73,7 @@ int main(int argc, char **argv)
 		if (cfg->order) updateE(W); else updateH(W);
 		if (is_nano) { flux_in += poyntingIn(W,-250, 250,-250, 250,-250, 250); flux_out += poyntingOut(W,-350, 350,-350, 350,-350, 350); absn += objectAbsorption(W, Nanoblock); }
 		if (P && steps - s < 40) updatePhaser(W, P);
-		if (P && steps - s == 25) direct_mid = direct_phasor_sum(is_band ? choosePhaser(P, 500) : P);
+		if (P && steps - s == 25 && (!is_fuzz || W->zMaxSur==PML)) direct_mid = direct_phasor_sum(is_band ? choosePhaser(P, 500) : P);
 		probe += get(W, is_phc ? Hz : Ez, 20, 10, 30);
 	}
 	emit("t", W->t); emit("n", W->n);
@@ -142,7 +145,7 @@ int main(int argc, char **argv)
 	if (is_nano) { emit("flux_in", flux_in); emit("flux_out", flux_out); emit("absorption", absn); }
 	if (P) {
 		phaser Q = is_band ? choosePhaser(P, 500) : P;
-		emit("phasor_direct_mid", direct_mid); emit("phasor_direct_end", direct_phasor_sum(Q));
+		if (!is_fuzz || W->zMaxSur==PML) { emit("phasor_direct_mid", direct_mid); emit("phasor_direct_end", direct_phasor_sum(Q)); }
 		emit("phaser_f", Q->f); emit("phaser_A", Q->A); emit("phaser_N", Q->N);
 		emit("phaserPoyntingOut", phaserPoyntingOut(Q));
 		float complex a = farField(Q, Ppol, 20, 30), b = farField(Q, Spol, 140, 250);
