@@ -69,14 +69,16 @@ MONITOR_SEEDS_GPU = [2, 9, 14, 23]
 @needs_ref
 @pytest.mark.parametrize("seed", MONITOR_SEEDS_CPU)
 def test_random_world_monitors_match_reference_cpu(seed):
-    """the monitor harness (about 390 values: every field function, probes, flux boxes, world and slice
-    reductions, slice checksums, time-averaged and frequency-domain slices) on random 3-D worlds large
-    enough for its fixed probe positions (FUZZ_BIG): identical to the printed digit"""
+    """the monitor harness (about 400 values: every field function, probes, flux boxes, world and slice
+    reductions, slice checksums, time-averaged and frequency-domain slices, a phaser list on the
+    world's absorbing faces with phasor flux, far field and direct array access) on random 3-D worlds
+    large enough for its fixed probe positions (FUZZ_BIG): identical to the printed digit, far field
+    within 1e-5"""
     if not helpers.have_test_bin("monitors_mine_oracle"):
         pytest.skip("tests/bin not built")
     env = {"FUZZ_SEED": str(seed), "FUZZ_BIG": "1"}
     want = helpers.run_monitors("monitors_ref", "fuzz", threads=1, extra_env=env)
-    got = helpers.run_monitors("monitors_mine_oracle", "fuzz", extra_env=env)
+    got = helpers.run_monitors("monitors_mine_oracle", "fuzz", extra_env=env, direct_phasor=True)
     assert len(want) > 350
     assert not helpers.monitor_mismatches(got, want), f"seed {seed}"
 
