@@ -19,9 +19,10 @@ from tests import helpers
 REF = os.path.join(helpers.REF_BIN, "stepdump_ref")
 needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="reference twin not built (oracle/build_ref.sh needs /root/reference)")
 CPU_SEEDS = list(range(1, 121))
-# 3-D CPML, anisotropic cells, TFSF (with and without objects, Num 24), flat axis + graded grid, Bloch/complex
+# (kept late in the alphabet: new GPU coverage runs after the established suite)
+# 3-D CPML, anisotropic cells, a flat x axis, TFSF (with and without objects, Num 24), flat axis + graded grid, Bloch/complex
 # with mirror and PEC sides, three objects, graded 3-D grid
-GPU_SEEDS = [5, 7, 9, 16, 20, 23, 29, 32, 41, 59, 67, 76]
+GPU_SEEDS = [5, 7, 8, 9, 16, 20, 23, 29, 32, 41, 59, 67, 76]
 
 
 def dump(exe, seed, out, cwd, **env):
