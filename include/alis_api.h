@@ -17,7 +17,16 @@
  *  - The trailing-default macros (putObjects, pointDipole, sliceSnap, ...) behave as in the
  *    reference: they append sentinel / zero arguments to a variadic function.
  *  - vfield.x/y/z are HOST VIEWS of device arrays: they are valid after alisSyncFields(W) (the
- *    library's own monitors sync the region they need on demand).
+ *    library's own monitors evaluate on the device or sync the region they need on demand).
+ *  - The phasor arrays P->zMax.Ex[i][j][k] ... may be indexed directly, as in the reference: they
+ *    are page-protected while the device holds newer data and refreshed on first touch
+ *    (ALIS_PHASER_GUARD=0 turns that off; then call alisSyncPhaser(P) first).
+ *  - h5read / h5write / the h5 slice writer / guidedWaveX,Y,Z work without libhdf5 (one contiguous
+ *    float dataset per file, classic HDF5 layout).
+ *  - Where the reference's behaviour is undefined this library is defined: get() of a point outside
+ *    the domain on a non-mirror axis is 0; a clone made by cloneWorld starts with an empty source
+ *    list (the reference shares the list, whose nodes keep writing into the original's arrays);
+ *    deleteCloneWorld and deletePhasers free everything exactly once.
  */
 #ifndef ALIS_API_H
 #define ALIS_API_H
@@ -339,7 +348,7 @@ void removeSources(world W);
 
 /* ---- alis-b200 extensions (not in the reference) ------------------------------------------------------------ */
 void alisSyncFields(world W);                 /* refresh every host view W->E[m].x/y/z, W->H[m].x/y/z (full D2H)      */
-void alisSyncPhaser(phaser P);                /* refresh the host views P->xMin.Ey[...] ... of a phaser array          */
+void alisSyncPhaser(phaser P);                /* refresh the host views P->xMin.Ey[...] ... of a phaser array now        */
 void alisReadField(world W, int set, int comp, int m, float *dense);   /* raw block incl. ghosts, reference layout  */
 void alisWriteField(world W, int set, int comp, int m, const float *dense);
 unsigned long alisDeviceGeometryObjects(void); /* objects rasterised on the device so far (ALIS_DEVICE_GEOMETRY=0: host only) */
