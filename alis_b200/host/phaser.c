@@ -60,25 +60,18 @@ static void guard_fault(int sig, siginfo_t *si, void *ctx)
 	signal(sig, SIG_DFL);
 }
 
-/* makeComplexField with a page-aligned, page-sized data block registered for protection */
-static float complex ***make_guarded_field(phaser base, int iMin, int iMax, int jMin, int jMax, int kMin, int kMax)
+/* one page-aligned, page-sized block for all host views of a list, registered for protection as a
+ * single range (one mprotect per transition, however many frequencies the list has) */
+static char *guard_arena(phaser base, size_t bytes)
 {
-	if (!guard_enabled()) return makeComplexField(iMin, iMax, jMin, jMax, kMin, kMax);
-	const long ni = 1-iMin+iMax, nj = 1-jMin+jMax, nk = 1-kMin+kMax;
+	if (!guard_enabled() || !bytes) return 0;
 	const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-	const size_t bytes = (sizeof(float complex)*(size_t)ni*nj*nk + page - 1)/page*page;
-	float complex ***f, *data = 0;
-	MALLOC(f, iMin, ni);
-	MALLOC(f[iMin], jMin, ni*nj);
+	char *data = 0;
+	bytes = (bytes + page - 1)/page*page;
 	if (posix_memalign((void**)&data, page, bytes)) printf("Insufficient memory!\n"), exit(1);
 	memset(data, 0, bytes);
-	f[iMin][jMin] = data - kMin;
-	for (int i=iMin; i<=iMax; i++) {
-		f[i] = f[iMin] + nj*(i-iMin);
-		for (int j=jMin; j<=jMax; j++) f[i][j] = f[iMin][jMin] + nk*(nj*(i-iMin)+(j-jMin));
-	}
 	guard *g = malloc(sizeof *g);
-	g->lo = (char*)data; g->bytes = bytes; g->base = base; g->next = guards; guards = g;
+	g->lo = data; g->bytes = bytes; g->base = base; g->next = guards; guards = g;
 	if (!handler_installed) {
 		struct sigaction sa;
 		memset(&sa, 0, sizeof sa);
@@ -88,8 +81,25 @@ static float complex ***make_guarded_field(phaser base, int iMin, int iMax, int 
 		sigaction(SIGSEGV, &sa, &chained);
 		handler_installed = 1;
 	}
+	return data;
+}
+
+/* makeComplexField over a given data block (or its own when data == 0) */
+static float complex ***field_over(float complex *data, int iMin, int iMax, int jMin, int jMax, int kMin, int kMax)
+{
+	if (!data) return makeComplexField(iMin, iMax, jMin, jMax, kMin, kMax);
+	const long ni = 1-iMin+iMax, nj = 1-jMin+jMax, nk = 1-kMin+kMax;
+	float complex ***f;
+	MALLOC(f, iMin, ni);
+	MALLOC(f[iMin], jMin, ni*nj);
+	f[iMin][jMin] = data - kMin;
+	for (int i=iMin; i<=iMax; i++) {
+		f[i] = f[iMin] + nj*(i-iMin);
+		for (int j=jMin; j<=jMax; j++) f[i][j] = f[iMin][jMin] + nk*(nj*(i-iMin)+(j-jMin));
+	}
 	return f;
 }
+#define VIEW_BYTES(b) ((sizeof(float complex)*(size_t)((b)[1]-(b)[0]+1)*((b)[3]-(b)[2]+1)*((b)[5]-(b)[4]+1) + 63)/64*64)
 
 static void guard_release(phaser base)
 {
@@ -170,12 +180,22 @@ phaser (createPhasers)(world W, float LMin, float LMax, float dL, float xMin, fl
 		                    W->yMinSur==PML && p->jMin != p->jMax, W->yMaxSur==PML,
 		                    W->zMinSur==PML && p->kMin != p->kMax, W->zMaxSur==PML };
 		mask = 0;
-		for (int face=0; face<6; face++) if (on[face]) {
+		for (int face=0; face<6; face++) if (on[face]) mask |= 1<<face;
+	}
+
+	/* host views of the accumulators, all in one guarded arena */
+	if (mask) {
+		size_t per = 0;
+		for (int face=0; face<6; face++) if (mask & (1<<face)) { int b[6]; face_box(P, face, b); per += 4*VIEW_BYTES(b); }
+		char *cur = guard_arena(P, per*count);
+		P->b200_arena = cur;
+		for (int n=0; n<count; n++) for (int face=0; face<6; face++) if (mask & (1<<face)) {
 			int b[6];
-			face_box(p, face, b);
-			mask |= 1<<face;
-			for (int which=0; which<4; which++)
-				*slot_of(face_of(p, face), face/2, which) = make_guarded_field(P, b[0], b[1], b[2], b[3], b[4], b[5]);
+			face_box(&P[n], face, b);
+			for (int which=0; which<4; which++) {
+				*slot_of(face_of(&P[n], face), face/2, which) = field_over((float complex*)cur, b[0], b[1], b[2], b[3], b[4], b[5]);
+				if (cur) cur += VIEW_BYTES(b);
+			}
 		}
 	}
 
@@ -258,7 +278,8 @@ void deletePhaser(phaser P)
 				int b[6];
 				face_box(p, face, b);
 				float complex ***A = *slot;
-				removeField(A, b[0], b[2], b[4]);
+				if (B->b200_arena) { free(&A[b[0]][b[2]]); free(&A[b[0]]); }     /* the data block belongs to the arena */
+				else removeField(A, b[0], b[2], b[4]);
 				*slot = 0;
 			}
 		}
@@ -267,6 +288,7 @@ void deletePhaser(phaser P)
 		if (p->ex) free(&p->ex[p->kMIN]);
 		if (p->ez) free(&p->ez[p->kMIN]);
 	}
+	free(B->b200_arena);
 	free(B);
 }
 

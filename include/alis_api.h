@@ -205,6 +205,7 @@ struct phaser {
 	/* --- alis-b200 --- */
 	void *b200_dev;                                      /* shared device accumulator set (element 0 owns it) */
 	int b200_index, b200_count, b200_stale;
+	void *b200_arena;                                    /* element 0: page-aligned block holding every host view of the list */
 };
 
 /* ---- world ----------------------------------------------------------------------------------- */
