@@ -1753,6 +1753,12 @@ extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const
 	for (int f=0; f<6; f++) if (p->acc[f]) {
 		const int ax = f/2, c1 = (ax+1)%3, c2 = (ax+2)%3;
 		const size_t hstep = ax == 0 ? 1 : ax == 1 ? (size_t)e->pitch : e->plane;
+		const char *pe = getenv("ALISB_PHASER_PAR");           /* opt-in: one thread per (cell, frequency); read per call so that tests can switch it */
+		const int par = pe ? atoi(pe) : 0;
+		if (par && p->nfreq > 1)
+			phaser_face_par<<<div_up(p->cells[f]*(size_t)p->nfreq, 128), 128, 0, e->stream>>>(p->acc[f], e->F[0][0][c1], e->F[0][0][c2], e->F[1][0][c1], e->F[1][0][c2],
+				p->face[f], e->ny, e->pitch, hstep, p->nfreq, p->dexp[0], p->dexp[1]);
+		else
 		phaser_face<<<div_up(p->cells[f], 128), 128, 0, e->stream>>>(p->acc[f], e->F[0][0][c1], e->F[0][0][c2], e->F[1][0][c1], e->F[1][0][c2],
 			p->face[f], e->ny, e->pitch, hstep, p->nfreq, p->dexp[0], p->dexp[1]);
 		e->launches++;

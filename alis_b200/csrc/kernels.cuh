@@ -828,6 +828,32 @@ __global__ void phaser_face(float2 *acc, const float *E1, const float *E2, const
 	}
 }
 
+/* the same accumulation with one thread per (face cell, frequency): identical arithmetic per
+ * accumulator, nfreq times the parallelism for multi-frequency lists (a face of a few hundred cells
+ * with 81 frequencies otherwise runs as a handful of CTAs looping serially).  Opt-in (ALISB_PHASER_PAR=1)
+ * until it has been validated and timed on the GPU. */
+__global__ void phaser_face_par(float2 *acc, const float *E1, const float *E2, const float *H1, const float *H2,
+                                Box B, int ny, int pitch, size_t hstep, int nfreq, const float2 *expE, const float2 *expH)
+{
+	const size_t cells = (size_t)B.na*B.nb*B.nc;
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= cells*(size_t)nfreq) return;
+	const int f = (int)(t / cells);
+	int a, b, c; size_t q;
+	if (!box_cell(B, t - (size_t)f*cells, a, b, c, q)) return;
+	const size_t i = GIDX(a, b, c);
+	const float e1 = E1[i], e2 = E2[i];
+	const float h1 = H1[i] + H1[i + hstep], h2 = H2[i] + H2[i + hstep];
+	const float2 wE = expE[f], wH = expH[f];
+	float2 *A = acc + (size_t)f*4*cells + q;
+	float2 v = A[0];       v.x += wE.x*e1; v.y += wE.y*e1; A[0] = v;
+	v = A[cells];          v.x += wE.x*e2; v.y += wE.y*e2; A[cells] = v;
+	v = A[2*cells];
+	v.x = (float)((double)v.x + (double)(wH.x*h1)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h1)*0.5); A[2*cells] = v;
+	v = A[3*cells];
+	v.x = (float)((double)v.x + (double)(wH.x*h2)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h2)*0.5); A[3*cells] = v;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Poynting flux through rectangles (reference output.c:233-332).  blockIdx.y = plane.  Every
  * thread accumulates its cells in double, the block reduces with shuffles in a fixed order and

@@ -93,3 +93,34 @@ def test_random_world_monitors_match_reference_gpu(seed):
     got = helpers.run_monitors("monitors_mine_cuda", "fuzz", extra_env=env)
     assert len(want) > 350
     assert not helpers.monitor_mismatches(got, want, device_flux=True), f"seed {seed}"
+
+
+@pytest.mark.gpu
+def test_parallel_phaser_kernel_bit_exact(monkeypatch):
+    """ALISB_PHASER_PAR=1 (one thread per face cell and frequency; opt-in until timed): accumulators
+    identical to the oracle's, i.e. to the default kernel's"""
+    import numpy as np
+    from alis_b200 import capi, synthetic
+    monkeypatch.setenv("ALISB_PHASER_PAR", "1")
+    eng, ora = capi.load_engine(), capi.load_oracle()
+    w = synthetic.BoxWorld(48, 44, 40, num=6)
+    g, o = w.make_engine(eng), w.make_engine(ora)
+    helpers.seed_fields([g, o], (50, 46, 42), seed=7)
+    freqs = np.linspace(1 / 800.0, 1 / 400.0, 9).astype(np.float32)
+    box = [8, 41, 8, 37, 8, 33]
+    pg, po = capi.Phaser(g, box, 0x3F, len(freqs)), capi.Phaser(o, box, 0x3F, len(freqs))
+    for _ in range(8):
+        for e in (g, o):
+            e.step_E()
+            e.step_H()
+        _, _, tE, tH = g.time()
+        wE = np.exp(2j * np.pi * freqs.astype(np.float64) * tE).astype(np.complex64)
+        wH = np.exp(2j * np.pi * freqs.astype(np.float64) * tH).astype(np.complex64)
+        pg.accumulate(wE, wH)
+        po.accumulate(wE, wH)
+    for f in range(len(freqs)):
+        for face in range(6):
+            for which in range(4):
+                a, b = pg.read(f, face, which), po.read(f, face, which)
+                assert np.array_equal(a.view(np.float32), b.view(np.float32)), (f, face, which)
+                assert np.abs(a).max() > 0
