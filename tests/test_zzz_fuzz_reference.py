@@ -124,3 +124,24 @@ def test_parallel_phaser_kernel_bit_exact(monkeypatch):
                 a, b = pg.read(f, face, which), po.read(f, face, which)
                 assert np.array_equal(a.view(np.float32), b.view(np.float32)), (f, face, which)
                 assert np.abs(a).max() > 0
+
+
+# ---- the GPU paths that have never run on a GPU yet come last ----------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["metasurface", "dipole_band"])
+def test_phasor_guard_on_gpu(cfg):
+    """direct user access to the phasor arrays with the accumulators on the GPU: the SIGSEGV handler
+    pulls them from the device (kept at the end of the suite: it is the one path that calls CUDA from
+    a signal handler)"""
+    got = helpers.run_monitors("monitors_mine_cuda", cfg, direct_phasor=True)
+    want = helpers.golden_monitors()[cfg]
+    assert not helpers.monitor_mismatches(got, want, device_flux=True)
+
+
+@pytest.mark.gpu
+def test_remaining_public_api_on_gpu(tmp_path):
+    """cloneWorld, rebootWorld, removeSources, removeObjects + new objects ... (oracle/harness/api_misc.c)
+    with the CUDA engine: every value as the unmodified reference prints it (flux values reduced on
+    the device to 5e-6)"""
+    got, want = helpers.run_api_misc("api_misc_mine_cuda", str(tmp_path)), helpers.golden_api_misc()
+    assert not helpers.monitor_mismatches(got, want, device_flux=True)
