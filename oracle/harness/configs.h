@@ -395,8 +395,10 @@ static world cfg_fuzz(void)
 			           {W->zMin+3*d[2], W->zMax-3*d[2]}};
 			const float wl = 40*dmin*(1 + 0.25f*fuzz_int(0, 4));
 			fprintf(stderr, "fuzz: tfsf\n");
-			if (fuzz_int(0, 1)) planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, fuzz_int(0, 1) ? 0 : 180, 0, Pulse, wl, 1.5f*wl);
-			else planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, 0, 90.0f*fuzz_int(0, 1), Sine, wl, 3);
+			const int kind = fuzz_int(0, 2);
+			if (kind == 0) planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, fuzz_int(0, 1) ? 0 : 180, 0, Pulse, wl, 1.5f*wl);
+			else if (kind == 1) planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, 0, 90.0f*fuzz_int(0, 1), Sine, wl, 3);
+			else planewave(W, DTF, fuzz_int(0, 1) ? Ppol : Spol, (float[]){25, 40, 55}[fuzz_int(0, 2)], 0, Sine, wl, 4);   /* oblique: Bloch-complex auxiliary world */
 		}
 	}
 
