@@ -333,10 +333,10 @@ static wvec test_field_weights(ff_ctx *c, world W, int lo, int hi, const float c
 static int ctx_vector(ff_ctx *c, wvec v, int outer)
 {
 	for (int q=0; q<c->nvec; q++) if (c->vec[q].key == v.w) return q;
-	if (c->nvec == c->capvec) { c->capvec = c->capvec ? 2*c->capvec : 16; c->vec = realloc(c->vec, sizeof(ff_vec)*c->capvec); }
+	if (c->nvec == c->capvec) { c->capvec = c->capvec ? 2*c->capvec : 16; c->vec = xrealloc(c->vec, sizeof(ff_vec)*c->capvec); }
 	ff_vec *f = &c->vec[c->nvec];
 	f->len = v.hi - v.lo + 1; f->key = v.w;
-	f->w = malloc(sizeof(float complex)*f->len);
+	f->w = xmalloc(sizeof(float complex)*f->len);
 	for (int q=v.lo; q<=v.hi; q++) {
 		if (outer) f->w[q-v.lo] = q == v.lo ? 0 : v.w[q];
 		else f->w[q-v.lo] = ((q==v.lo ? 0.5f : 0) + (q==v.hi ? 0.5f : 0) + (q!=v.lo && q!=v.hi ? 1.0f : 0)) * v.w[q];
@@ -350,7 +350,7 @@ static float complex surface_sum(ff_ctx *c, int face, int isH, int comp, int o, 
 {
 	if (c->replay) { const double *r = c->result + 2*(size_t)c->next++; return (float)r[0] + I*(float)r[1]; }
 	const int a = face/2;
-	if (c->njob == c->capjob) { c->capjob = c->capjob ? 2*c->capjob : 16; c->job = realloc(c->job, sizeof(ff_job)*c->capjob); }
+	if (c->njob == c->capjob) { c->capjob = c->capjob ? 2*c->capjob : 16; c->job = xrealloc(c->job, sizeof(ff_job)*c->capjob); }
 	ff_job *j = &c->job[c->njob++];
 	j->face = face; j->which = (comp - a + 3)%3 - 1 + (isH ? 2 : 0);
 	const int vo = ctx_vector(c, Wo, 1), vn = ctx_vector(c, Wn, 0);
@@ -515,8 +515,8 @@ static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*
 	int freq = 0;
 	alisb_phaser *dev = alis_phaser_device(P, &freq);
 	if (!dev) { for (int q=0; q<n; q++) out[q][0] = out[q][1] = 0; return; }      /* no absorbing face: nothing was recorded */
-	ff_ctx *ctx = calloc(FF_CHUNK, sizeof *ctx);
-	size_t *job0 = malloc(sizeof(size_t)*(FF_CHUNK+1)), *w0 = malloc(sizeof(size_t)*(FF_CHUNK+1));
+	ff_ctx *ctx = xcalloc(FF_CHUNK, sizeof *ctx);
+	size_t *job0 = xmalloc(sizeof(size_t)*(FF_CHUNK+1)), *w0 = xmalloc(sizeof(size_t)*(FF_CHUNK+1));
 	for (int base=0; base<n; base+=FF_CHUNK) {
 		const int m = MIN(FF_CHUNK, n-base);
 		t0 = wall_seconds();
@@ -527,9 +527,9 @@ static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*
 		for (int q=0; q<m; q++) { job0[q] = njobs; w0[q] = nw; njobs += ctx[q].njob; for (int v=0; v<ctx[q].nvec; v++) nw += ctx[q].vec[v].len; }
 		job0[m] = njobs; w0[m] = nw;
 		if (nw > 0xFFFFFFFFu) { printf("alis-b200: far-field batch too large\n"); exit(1); }
-		alisb_surface_job *jobs = malloc(sizeof *jobs*(njobs+1));
-		float complex *weights = malloc(sizeof *weights*(nw+1));
-		double *sums = malloc(sizeof(double)*2*(njobs+1));
+		alisb_surface_job *jobs = xmalloc(sizeof *jobs*(njobs+1));
+		float complex *weights = xmalloc(sizeof *weights*(nw+1));
+		double *sums = xmalloc(sizeof(double)*2*(njobs+1));
 		#pragma omp parallel for schedule(static)
 		for (int q=0; q<m; q++) {
 			size_t off[ctx[q].nvec+1], w = w0[q];
@@ -578,8 +578,8 @@ float farFieldI(phaser P, tfield pol(phaser,float,float), float theta, float phi
 /* P- and S-polarised far field towards n directions */
 static void far_field_pairs(phaser P, int n, const float *theta, const float *phi, float complex *p, float complex *s)
 {
-	ff_query *Q = malloc(sizeof(ff_query)*(n+1));
-	float complex (*f)[2] = malloc(sizeof(float complex)*2*(n+1));
+	ff_query *Q = xmalloc(sizeof(ff_query)*(n+1));
+	float complex (*f)[2] = xmalloc(sizeof(float complex)*2*(n+1));
 	for (int q=0; q<n; q++) { Q[q].pol[0] = Ppol; Q[q].pol[1] = Spol; Q[q].npol = 2; Q[q].theta = theta[q]; Q[q].phi = phi[q]; }
 	far_field_batch(P, n, Q, f);
 	for (int q=0; q<n; q++) { p[q] = f[q][0]; s[q] = f[q][1]; }
@@ -612,8 +612,8 @@ void farFieldProfile(world W, phaser P, projmap projMap, int X, int Y, ...)
 
 	printf("Performing Near-to-Far-Field Transformation.\n");
 	/* every pixel's direction, both polarisations: one batched sweep on the device */
-	float complex *pp = calloc((size_t)X*Y, sizeof *pp), *ss = calloc((size_t)X*Y, sizeof *ss);
-	float *thetas = calloc((size_t)X*Y, sizeof *thetas), *phis = calloc((size_t)X*Y, sizeof *phis);
+	float complex *pp = xcalloc((size_t)X*Y, sizeof *pp), *ss = xcalloc((size_t)X*Y, sizeof *ss);
+	float *thetas = xcalloc((size_t)X*Y, sizeof *thetas), *phis = xcalloc((size_t)X*Y, sizeof *phis);
 	for (int x=0; x<X; x++) for (int y=0; y<Y; y++) {
 		float angle[2];
 		projMap(x, y, X, Y, angle);
@@ -702,8 +702,8 @@ float (farFieldFlux)(phaser P, tfield pol(phaser,float,float), float theta, floa
 		/* all ring samples first (one batched sweep on the device), then the reference's sum in its order */
 		int count = 0;
 		for (int n=nMin; n<=nMax; n++) count += n<floor(60/delta+0.5) ? n*6 : floor(60/delta+0.5)*6;
-		float *ta = malloc(sizeof(float)*(count+1)), *tb = malloc(sizeof(float)*(count+1));
-		float complex *fp = malloc(sizeof(float complex)*(count+1)), *fs = malloc(sizeof(float complex)*(count+1));
+		float *ta = xmalloc(sizeof(float)*(count+1)), *tb = xmalloc(sizeof(float)*(count+1));
+		float complex *fp = xmalloc(sizeof(float complex)*(count+1)), *fs = xmalloc(sizeof(float complex)*(count+1));
 		int q = 0;
 		for (int n=nMin; n<=nMax; n++) {
 			int N = n<floor(60/delta+0.5) ? n*6 : floor(60/delta+0.5)*6;

@@ -555,9 +555,8 @@ int alis_device_region_ok(world W, const alisb_field_fn *d, const int box[6])
 float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1)
 {
 	const int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
-	if (ni <= 0 || nj <= 0 || nk <= 0) return calloc(1, sizeof(float));
-	float *v = malloc(sizeof(float)*(size_t)ni*nj*nk);
-	if (!v) printf("\nMemory allocation failure\n"), exit(1);
+	if (ni <= 0 || nj <= 0 || nk <= 0) return xcalloc(1, sizeof(float));
+	float *v = xmalloc(sizeof(float)*(size_t)ni*nj*nk);
 	alisb_field_fn d;
 	int take_log;
 	const int box[6] = { i0, i1, j0, j1, k0, k1 };

@@ -9,8 +9,20 @@
 #ifndef ALIS_HOST_INTERNAL_H
 #define ALIS_HOST_INTERNAL_H
 
+#include <stdio.h>
+#include <stdlib.h>
 #include "alis_b200.h"
 #include "engine_bridge.h"
+
+/* allocation failure ends the program like the reference's MALLOC (alis_c.h:34) */
+static inline void *alis_checked(void *p, size_t bytes)
+{
+	if (!p && bytes) { printf("Insufficient memory!\n"); exit(1); }
+	return p;
+}
+#define xmalloc(bytes)        alis_checked(malloc(bytes), (bytes))
+#define xcalloc(n, size)      alis_checked(calloc((n), (size)), (size_t)(n)*(size))
+#define xrealloc(p, bytes)    alis_checked(realloc((p), (bytes)), (bytes))
 
 enum { ALIS_DIRTY_TABLES = 1, ALIS_DIRTY_MATERIALS = 2, ALIS_DIRTY_SOURCES = 4, ALIS_DIRTY_COPIES = 8, ALIS_DIRTY_ALL = 15 };
 

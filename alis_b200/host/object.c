@@ -250,7 +250,7 @@ static int geo_type(shape *S)
 
 static int geo_new_nodes(geo_ctx *G, int count)
 {
-	while (G->nnodes + count > G->capnodes) { G->capnodes = G->capnodes ? 2*G->capnodes : 32; G->nodes = realloc(G->nodes, sizeof(alisb_shape)*G->capnodes); }
+	while (G->nnodes + count > G->capnodes) { G->capnodes = G->capnodes ? 2*G->capnodes : 32; G->nodes = xrealloc(G->nodes, sizeof(alisb_shape)*G->capnodes); }
 	memset(G->nodes + G->nnodes, 0, sizeof(alisb_shape)*count);
 	G->nnodes += count;
 	return G->nnodes - count;
@@ -258,7 +258,7 @@ static int geo_new_nodes(geo_ctx *G, int count)
 
 static void geo_push_aux(geo_ctx *G, float v)
 {
-	if (G->naux == G->capaux) { G->capaux = G->capaux ? 2*G->capaux : 32; G->aux = realloc(G->aux, sizeof(float)*G->capaux); }
+	if (G->naux == G->capaux) { G->capaux = G->capaux ? 2*G->capaux : 32; G->aux = xrealloc(G->aux, sizeof(float)*G->capaux); }
 	G->aux[G->naux++] = v;
 }
 
@@ -313,8 +313,8 @@ int alis_device_geometry(void)
 static geo_ctx *geo_build(world W, object *O, int N)
 {
 	if (!alis_device_geometry() || W->subN < 1 || N < 1) return 0;
-	geo_ctx *G = calloc(1, sizeof *G);
-	G->roots = malloc(sizeof(int32_t)*N);
+	geo_ctx *G = xcalloc(1, sizeof *G);
+	G->roots = xmalloc(sizeof(int32_t)*N);
 	for (int o=0; o<N; o++) {
 		G->roots[o] = geo_new_nodes(G, 1);
 		if (!geo_flatten(G, O[o], G->roots[o])) { geo_free(G); return 0; }
@@ -325,7 +325,7 @@ static geo_ctx *geo_build(world W, object *O, int N)
 	const int slots = W->subN + 3;
 	const float edge = (W->subN-1.0) / (W->subN*2.0);
 	for (int a=0; a<3; a++) {
-		G->coord[a] = malloc(sizeof(float)*2*slots*(hi[a]-lo[a]+1));
+		G->coord[a] = xmalloc(sizeof(float)*2*slots*(hi[a]-lo[a]+1));
 		for (int idx=lo[a]; idx<=hi[a]; idx++) for (int half=0; half<2; half++) {
 			float *t = G->coord[a] + ((size_t)(idx-lo[a])*2 + half)*slots;
 			const float base = half ? idx-0.5 : idx;
@@ -346,7 +346,7 @@ static bounds *object_bounds_device(world W, geo_ctx *G, int N)
 {
 	bounds *B;
 	MALLOC(B, 0, N);
-	int32_t *raw = malloc(sizeof(int32_t)*6*N);
+	int32_t *raw = xmalloc(sizeof(int32_t)*6*N);
 	const int32_t box[6] = { W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX };
 	if (alisb_geometry_bounds(alis_bridge_device(), &G->g, box, raw) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 	for (int o=0; o<N; o++) {
@@ -372,7 +372,7 @@ static geo_fill_t geo_fill_object(world W, geo_ctx *G, int o, bounds b)
 	geo_fill_t F;
 	const int32_t box[6] = { b.iMin, b.iMax + (b.iMax == W->iMAX), b.jMin, b.jMax + (b.jMax == W->jMAX), b.kMin, b.kMax + (b.kMax == W->kMAX) };
 	const size_t n = (size_t)(box[1]-box[0]+1)*(box[3]-box[2]+1)*(box[5]-box[4]+1);
-	for (int c=0; c<3; c++) if (!(F.f[c] = malloc(sizeof(float)*n))) printf("\nMemory allocation failure\n"), exit(1);
+	for (int c=0; c<3; c++) F.f[c] = xmalloc(sizeof(float)*n);
 	F.i0 = box[0]; F.j0 = box[2]; F.k0 = box[4]; F.nj = box[3]-box[2]+1; F.nk = box[5]-box[4]+1;
 	if (alisb_geometry_fill(alis_bridge_device(), &G->g, o, box, F.f[0], F.f[1], F.f[2]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 	geo_objects++;

@@ -105,7 +105,7 @@ float worldSum(world W, field F)
 {
 	float Sum = 0;
 	const int box[6] = { W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax };
-	float *cols = malloc(sizeof(float)*(size_t)(W->iMax-W->iMin+1)*(W->jMax-W->jMin+1));
+	float *cols = xmalloc(sizeof(float)*(size_t)(W->iMax-W->iMin+1)*(W->jMax-W->jMin+1));
 	if (cols && alis_device_column_sums(W, F, box, cols)) {              /* one float per z column comes back, not the fields */
 		for (int i=W->iMin+1; i<W->iMax; i++) Sum += W->CE->dx[i] * sheet_sum_cols(W, cols, i);
 		Sum += 0.5 * W->CE->dx[W->iMin] * sheet_sum_cols(W, cols, W->iMin);
@@ -435,8 +435,7 @@ float objectAbsorption(world W, object O)
 		alis_bridge *B = alis_host_bridge(W);
 		alis_bridge_commit(B);
 		const int32_t box[6] = { i0-(W->iMIN-1), i1-(W->iMIN-1), j0-(W->jMIN-1), j1-(W->jMIN-1), k0-(W->kMIN-1), k1-(W->kMIN-1) };
-		A.dev = malloc(sizeof(float)*3*(size_t)(i1-i0+1)*(j1-j0+1));
-		if (!A.dev) printf("\nMemory allocation failure\n"), exit(1);
+		A.dev = xmalloc(sizeof(float)*3*(size_t)(i1-i0+1)*(j1-j0+1));
 		if (alisb_absorption_columns(alis_bridge_engine(B), n, box, A.dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 	}
 	else {

@@ -70,7 +70,7 @@ static char *guard_arena(phaser base, size_t bytes)
 	bytes = (bytes + page - 1)/page*page;
 	if (posix_memalign((void**)&data, page, bytes)) printf("Insufficient memory!\n"), exit(1);
 	memset(data, 0, bytes);
-	guard *g = malloc(sizeof *g);
+	guard *g = xmalloc(sizeof *g);
 	g->lo = data; g->bytes = bytes; g->base = base; g->next = guards; guards = g;
 	if (!handler_installed) {
 		struct sigaction sa;
@@ -229,7 +229,7 @@ void updatePhaser(world W, phaser P)
 	phaser B = base_of(P);
 	if (!B->b200_dev) return;
 	const int count = B->b200_count;
-	float complex *wE = calloc(count, sizeof *wE), *wH = calloc(count, sizeof *wH);
+	float complex *wE = xcalloc(count, sizeof *wE), *wH = xcalloc(count, sizeof *wH);
 	for (phaser p = P; p->f; p++) {
 		wE[p->b200_index] = cexpf(2 * PI * I * p->f * W->E->t);
 		wH[p->b200_index] = cexpf(2 * PI * I * p->f * W->H->t);

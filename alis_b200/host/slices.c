@@ -489,7 +489,7 @@ float sliceSum(world W, field F, slice S)
 {
 	float Sum = 0;
 	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
-	float *cols = malloc(sizeof(float)*(size_t)(S->iMax-S->iMin+1)*(S->jMax-S->jMin+1));
+	float *cols = xmalloc(sizeof(float)*(size_t)(S->iMax-S->iMin+1)*(S->jMax-S->jMin+1));
 	if (cols && alis_device_column_sums(W, F, box, cols)) {
 		for (int i=S->iMin+1; i<S->iMax; i++) Sum += W->CE->dx[i] * sheet_sum_cols(W, S, cols, i);
 		Sum += 0.5 * W->CE->dx[S->iMin] * sheet_sum_cols(W, S, cols, S->iMin);

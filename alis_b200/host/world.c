@@ -345,12 +345,12 @@ void *h5read(int *dim, char *format, ...)
 	if (dim) for (int n=0; n<N; n++) dim[n] = dims[n];
 	if (N == 1) return data;
 	if (N == 2) {
-		float **f = calloc(dims[0], sizeof(float*));
+		float **f = xcalloc(dims[0], sizeof(float*));
 		for (unsigned long long i=0; i<dims[0]; i++) f[i] = data + dims[1]*i;
 		return f;
 	}
-	float ***f = calloc(dims[0], sizeof(float**));
-	f[0] = calloc(dims[0]*dims[1], sizeof(float*));
+	float ***f = xcalloc(dims[0], sizeof(float**));
+	f[0] = xcalloc(dims[0]*dims[1], sizeof(float*));
 	for (unsigned long long i=1; i<dims[0]; i++) f[i] = f[0] + dims[1]*i;
 	for (unsigned long long i=0; i<dims[0]; i++) for (unsigned long long j=0; j<dims[1]; j++) f[i][j] = data + dims[2]*(dims[1]*i + j);
 	return f;
