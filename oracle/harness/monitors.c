@@ -153,6 +153,7 @@ int main(int argc, char **argv)
 		emit("ff_S_140_250_re", crealf(b)); emit("ff_S_140_250_im", cimagf(b));
 		emit("ffI_unpol_0_0", farFieldI(Q, Unpol, 0, 0)); emit("ffI_P_55_0", farFieldI(Q, Ppol, 55, 0)); emit("ffI_S_89.5_10", farFieldI(Q, Spol, 89.5, 10));
 		emit("ffFlux_30", farFieldFlux(Q, Unpol, 0, 0, 30, 0, 5));
+		emit("ffFlux_P_tilted", farFieldFlux(Q, Ppol, 10, 20, 25, 0, 5)); emit("ffFlux_S_ring", farFieldFlux(Q, Spol, 170, 45, 10, 30, 5));
 		double acc = 0;
 		for (int x=0; x<24; x++) for (int y=0; y<12; y++) { float ang[2]; AzimuthalMap(x, y, 24, 12, ang); acc += farFieldI(Q, Unpol, ang[0], ang[1]); }
 		emit("ff_map_sum", acc);
