@@ -11,6 +11,16 @@
  * from /root/reference (oracle/_ref, see oracle/build_ref.sh and tests/test_oracle_vs_ref.py)
  * and against the golden vectors under tests/golden/ that were generated from it.
  *
+ * The monitor calls (field functions, slice / world reductions, absorption columns: reference
+ * fields.c, slices.c, output.c) and the geometry calls (shape predicates and fill factors:
+ * shapes.c, object.c) evaluate the restatements in alis_b200/csrc/monitor_eval.h and
+ * geometry_eval.h -- the same source the CUDA kernels compile -- looped here in the reference's
+ * order.  They are pinned the same way: through the host layer against the reference's monitor
+ * values (tests/golden/monitor_values.json), its field hashes (shape_zoo and every configuration
+ * with objects), and live against the reference on random worlds (tests/test_zzz_fuzz_reference.py).
+ * The far-field surface sums (farfld.c:248-459) are restated below and additionally checked
+ * against numpy (tests/test_farfield_sums.py).
+ *
  * Layout here is the reference's: [a][b][c] with c (z) fastest, one ghost layer
  * (world.c:58-70,170-172).  Arithmetic is fp32 with the reference's expression order;
  * compile with -std=c99 -ffp-contract=off so no FMA is formed (the reference build,
