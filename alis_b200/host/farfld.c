@@ -268,6 +268,8 @@ typedef struct {
 	ff_job *job; int njob, capjob;
 	ff_vec *vec; int nvec, capvec;
 	ff_cached cache[8]; int ncache;
+	/* test fields: built in the record pass, consumed (and released) by the replay pass */
+	tfield *T; int nT, capT, iT;
 	/* replay */
 	const double *result; int next;
 } ff_ctx;
@@ -277,7 +279,9 @@ static void ctx_free(ff_ctx *c)
 	for (int q=0; q<c->nvec; q++) free(c->vec[q].w);
 	for (int q=0; q<c->ncache; q++) free(&c->cache[q].v.w[c->cache[q].v.lo]);
 	free(c->vec); free(c->job);
+	tfield *T = c->T; const int nT = c->nT;          /* handed over to the replay pass */
 	memset(c, 0, sizeof *c);
+	c->T = T; c->nT = nT;
 }
 
 static wvec vec_alloc(ff_ctx *c, int lo, int hi)
@@ -470,7 +474,15 @@ static float complex far_field_eval(ff_ctx *c, phaser P, tfield pol(phaser,float
 		else sinth = sinf(theta*PI/180) * sqrtf(crealf(P->ex[P->kMIN]));
 	}
 
-	tfield T = pol(P, theta, phi);
+	tfield T;
+	if (c->replay && c->iT < c->nT) T = c->T[c->iT++];             /* the record pass's test field */
+	else {
+		T = pol(P, theta, phi);
+		if (!c->replay) {
+			if (c->nT == c->capT) { c->capT = c->capT ? 2*c->capT : 4; c->T = xrealloc(c->T, sizeof(tfield)*c->capT); }
+			c->T[c->nT++] = T;
+		}
+	}
 	kx = - 2 * PI * P->f * sinth * cosf(phi*PI/180);
 	ky = - 2 * PI * P->f * sinth * sinf(phi*PI/180);
 
@@ -481,8 +493,10 @@ static float complex far_field_eval(ff_ctx *c, phaser P, tfield pol(phaser,float
 	if (W->zMinSur==PML && P->zMin.Ex) Sum -= face_z(c, P, 4, P->kMin, T, kx, ky);
 	if (W->zMaxSur==PML) Sum += face_z(c, P, 5, P->kMax, T, kx, ky);
 
-	float complex *parts[6] = { T.Ex, T.Ey, T.Ez, T.Hx, T.Hy, T.Hz };
-	for (int q=0; q<6; q++) if (parts[q]) free(&parts[q][P->kMIN]);
+	if (c->replay) {                                               /* in the record pass the context keeps T for the replay */
+		float complex *parts[6] = { T.Ex, T.Ey, T.Ez, T.Hx, T.Hy, T.Hz };
+		for (int q=0; q<6; q++) if (parts[q]) free(&parts[q][P->kMIN]);
+	}
 
 	/* array factor of xNUM x yNUM periodic replicas */
 	if (P->xNUM) {
@@ -549,8 +563,11 @@ static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*
 		for (int q=0; q<m; q++) {
 			ff_ctx r = { 0 };
 			r.replay = 1; r.result = sums + 2*job0[q];
+			r.T = ctx[q].T; r.nT = ctx[q].nT;
 			out[base+q][0] = out[base+q][1] = 0;
 			for (int k=0; k<Q[base+q].npol; k++) out[base+q][k] = far_field_eval(&r, P, Q[base+q].pol[k], Q[base+q].theta, Q[base+q].phi);
+			free(ctx[q].T);
+			ctx[q].T = 0; ctx[q].nT = 0;
 		}
 		t_rep += wall_seconds() - t0;
 		free(jobs); free(weights); free(sums);
