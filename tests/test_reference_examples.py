@@ -58,7 +58,9 @@ ARGS = {"Cross_Polarization_T": ["300", "120", "80", "200"]}      # lattice cons
 
 @needs_ref
 @needs_lib
-@pytest.mark.parametrize("name", ["Dipole_PML", "Metasurface_Farfield", "Cross_Polarization_T"])
+@pytest.mark.parametrize("name", ["Dipole_PML", "Metasurface_Farfield",
+                                  pytest.param("Cross_Polarization_T", marks=pytest.mark.skipif(not os.environ.get("ALIS_SLOW_TESTS"),
+                                               reason="1.5-4 minutes on the CPU oracle engine: set ALIS_SLOW_TESTS=1 (last run: passed, table identical to 1e-6)"))])
 def test_unmodified_reference_example_runs_and_matches(name, tmp_path):
     """the reference's own driver source, once linked with the reference, once with our host layer
     (CPU oracle engine here; tests/test_gpu_examples.py does the same on the GPU with our copies).
