@@ -348,7 +348,11 @@ static bounds *object_bounds_device(world W, geo_ctx *G, int N)
 	MALLOC(B, 0, N);
 	int32_t *raw = xmalloc(sizeof(int32_t)*6*N);
 	const int32_t box[6] = { W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX };
-	if (alisb_geometry_bounds(alis_bridge_device(), &G->g, box, raw) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (alisb_geometry_bounds(alis_bridge_device(), &G->g, box, raw) != ALISB_OK) {
+		printf("alis-b200: device rasteriser unavailable (%s), rasterising on the host\n", alisb_last_error());
+		free(raw); free(B);
+		return 0;
+	}
 	for (int o=0; o<N; o++) {
 		B[o].iMin = raw[6*o], B[o].iMax = raw[6*o+1], B[o].jMin = raw[6*o+2], B[o].jMax = raw[6*o+3], B[o].kMin = raw[6*o+4], B[o].kMax = raw[6*o+5];
 		if (B[o].iMin > B[o].iMax || B[o].jMin > B[o].jMax || B[o].kMin > B[o].kMax) {
@@ -374,7 +378,11 @@ static geo_fill_t geo_fill_object(world W, geo_ctx *G, int o, bounds b)
 	const size_t n = (size_t)(box[1]-box[0]+1)*(box[3]-box[2]+1)*(box[5]-box[4]+1);
 	for (int c=0; c<3; c++) F.f[c] = xmalloc(sizeof(float)*n);
 	F.i0 = box[0]; F.j0 = box[2]; F.k0 = box[4]; F.nj = box[3]-box[2]+1; F.nk = box[5]-box[4]+1;
-	if (alisb_geometry_fill(alis_bridge_device(), &G->g, o, box, F.f[0], F.f[1], F.f[2]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (alisb_geometry_fill(alis_bridge_device(), &G->g, o, box, F.f[0], F.f[1], F.f[2]) != ALISB_OK) {
+		printf("alis-b200: device rasteriser unavailable (%s), rasterising on the host\n", alisb_last_error());
+		for (int c=0; c<3; c++) { free(F.f[c]); F.f[c] = 0; }
+		return F;                                   /* f[0] == 0: the caller switches to the host rasteriser */
+	}
 	geo_objects++;
 	return F;
 }
@@ -444,7 +452,8 @@ void putObjectArray(world W, matter *M, object *O)
 	/* sub-pixel sampling defaults: 1 if anything is dispersive, else 12 per axis */
 	W->subN = W->Res.spec.subN = W->Res.spec.subN ? W->Res.spec.subN : W->CE->N ? 1 : 12;
 	geo_ctx *G = geo_build(W, O, N);                /* non-NULL: rasterise on the device (default; ALIS_DEVICE_GEOMETRY=0 or a user-written shape: host) */
-	bounds *B = G ? object_bounds_device(W, G, N) : object_bounds(W, O, N);
+	bounds *B = G ? object_bounds_device(W, G, N) : 0;
+	if (!B) { geo_free(G); G = 0; B = object_bounds(W, O, N); }
 	coeffs *C = W->CE;
 	alloc_material_tables(W, C, eps_eff(W, M[N], 0), eps_eff(W, M[N], 1), eps_eff(W, M[N], 2));
 	MALLOC(C->O, 0, N+1);
@@ -460,7 +469,7 @@ void putObjectArray(world W, matter *M, object *O)
 		float cz = eps_eff(W, M[o], 2) - eps_eff(W, M[N], 2);
 		const bounds b = B[o];
 		geo_fill_t dev;
-		if (G) dev = geo_fill_object(W, G, o, b);
+		if (G) { dev = geo_fill_object(W, G, o, b); if (!dev.f[0]) { geo_free(G); G = 0; } }
 
 		printf("\rPutting objects: %d left.", o+1);
 		fflush(stdout);
