@@ -279,6 +279,14 @@ tfsf (createTFSF)(world W, dom DOM, sur SUR)
 
 /* ---- plane sources (reference source.c:337-411) --------------------------------------------------- */
 
+/* a source covering the whole plane z = k, absorbing layers included */
+static void whole_plane(source S, world W, int k)
+{
+	S->iMin = W->iMIN; S->iMax = W->iMAX;
+	S->jMin = W->jMIN; S->jMax = W->jMAX;
+	S->kMin = S->kMax = k;
+}
+
 /* one plane source z = k of component F; on a complex (Bloch) world every cell gets its own phase
  * phase + kx x + ky y so the plane radiates obliquely */
 static void plane_source(world W, field F, int k, float kx, float ky, waveform waveForm, float wavelength, float supplement, float resolution, float amplitude, float phase)
@@ -286,7 +294,7 @@ static void plane_source(world W, field F, int k, float kx, float ky, waveform w
 	source S = new_source(W, F, waveForm, wavelength, supplement, resolution);
 	S->amplitude = amplitude;
 	S->phase = phase;
-	S->iMin = W->iMIN, S->iMax = W->iMAX, S->jMin = W->jMIN, S->jMax = W->jMAX, S->kMin = k, S->kMax = k;
+	whole_plane(S, W, k);
 
 	if (W->complexField) {
 		float di = (F==Ex||F==Hy||F==iEx||F==iHy) ? 0.5 : 0;
@@ -377,48 +385,72 @@ void (planewave)(world W, dom Dom, tfield pol(phaser,float,float), float theta, 
 	W->N = S->W->N;
 }
 
-/* ---- Gaussian beam (reference source.c:435-496) ---------------------------------------------------- */
+/* ---- Gaussian beam (reference source.c:435-496) ----------------------------------------------------
+ * A plane source over a whole z plane whose per-cell amplitude and phase are those of a paraxial
+ * Gaussian beam focused at height z: waist w0 from the FWHM spot size, local width w, wavefront
+ * radius R and Gouy phase at the distance of the source plane from the focus.  The expressions are
+ * the reference's (operand order included): the profile is bit-identical. */
+typedef struct { float k, w0, w, R, gouy; } beam_optics;
+
+static beam_optics beam_optics_at(float wavelength, float index, float spotsize, float distance)
+{
+	beam_optics b;
+	b.k = 2 * PI * index / wavelength;
+	b.w0 = wavelength * (spotsize ? spotsize : 1) / (index * sqrtf(-2.0 * logf(0.5)));
+	const float rayleigh = PI * index * sq(b.w0) / wavelength;
+	b.w = b.w0 * sqrtf(1 + sq(distance/rayleigh));
+	b.R = distance * (1 + sq(rayleigh/distance));
+	b.gouy = atanf(distance/rayleigh);
+	return b;
+}
+
+/* the source plane of a wave travelling along theta: the lower face for downward, the upper one for
+ * upward propagation */
+static int launch_plane(world W, float theta)
+{
+	if (90<theta && theta<270) return W->kMin;
+	if (theta<90 || 270<theta) return W->kMax;
+	return 0;
+}
+
 static void beam(world W, field F, float x, float y, float z, float theta, waveform waveForm, float wavelength, float supplement, float spotsize, float amplitude, float phase)
 {
 	while (theta < 0) theta += 360;
 	while (theta >= 360) theta -= 360;
 
+	/* mirror parities of a beam polarised along F */
 	if (W->xMinSur==SYM) W->coskx = (F==Ex || F==iEx) ? 1 : -1;
 	if (W->yMinSur==SYM) W->cosky = (F==Ey || F==iEy) ? 1 : -1;
 	alis_host_dirty(W, ALIS_DIRTY_COPIES);
 
 	if (waveForm) {
-		int k = (90<theta && theta<270) ? W->kMin : (theta<90 || 270<theta) ? W->kMax : 0;
-		float n  = W->CE->z ? 1/sqrtf(W->CE->z[W->xtoi(W,MIN(x,W->xMax))][W->ytoj(W,MIN(y,W->yMax))][k]) : 1;
+		const int k = launch_plane(W, theta);
+		float index = 1;                            /* refractive index where the beam axis crosses the source plane */
+		if (W->CE->z) index = 1/sqrtf(W->CE->z[W->xtoi(W,MIN(x,W->xMax))][W->ytoj(W,MIN(y,W->yMax))][k]);
 		source S = new_source(W, F, waveForm, wavelength, supplement, amplitude);
-		S->iMin = W->iMIN, S->iMax = W->iMAX, S->jMin = W->jMIN, S->jMax = W->jMAX, S->kMin = k, S->kMax = k;
+		whole_plane(S, W, k);
 		if (!amplitude) amplitude = 1;
-		amplitude /= sqrtf(n*n*n);
+		amplitude /= sqrtf(index*index*index);
 
-		if (spotsize) {
-			/* paraxial Gaussian beam focused at z: waist w0 from the FWHM spot size, Rayleigh range
-			 * z0, local width wz, wavefront radius Rz and Gouy phase nz at the source plane */
-			float kz = 2 * PI * n / wavelength;
-			float zz = fabsf(z - W->ktoz(W,k));
-			float w0 = wavelength * (spotsize ? spotsize : 1) / (n * sqrtf(-2.0 * logf(0.5)));
-			float z0 = PI * n * sq(w0) / wavelength;
-			float wz = w0 * sqrtf(1 + sq(zz/z0));
-			float Rz = zz * (1 + sq(z0/zz));
-			float nz = atanf(zz/z0);
-
-			S->Amplitude = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
-			S->Phase = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
-			for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) {
-				float r2 = 0;
-				if (x < INF) r2 += sq(x - W->itox(W,F==Ex?i-0.5:i));
-				if (y < INF) r2 += sq(y - W->jtoy(W,F==Ey?j-0.5:j));
-				S->Amplitude[i][j][k] = amplitude * w0/wz * expf(-r2/sq(wz));
-				S->Phase[i][j][k] = phase * PI / 180 - kz * (0.5 * r2 / Rz) + nz;
-			}
-		}
-		else {
+		if (!spotsize) {                            /* plane wave */
 			S->amplitude = amplitude;
 			S->phase = phase * PI / 180;
+		}
+		else {
+			const beam_optics B = beam_optics_at(wavelength, index, spotsize, fabsf(z - W->ktoz(W,k)));
+			const int focus_x = x < INF, focus_y = y < INF;      /* an infinite coordinate = no focusing along that axis */
+			S->Amplitude = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
+			S->Phase = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
+			for (int i=S->iMin; i<=S->iMax; i++) {
+				const float ux = focus_x ? sq(x - W->itox(W,F==Ex?i-0.5:i)) : 0;
+				for (int j=S->jMin; j<=S->jMax; j++) {
+					float r2 = 0;
+					if (focus_x) r2 += ux;
+					if (focus_y) r2 += sq(y - W->jtoy(W,F==Ey?j-0.5:j));
+					S->Amplitude[i][j][k] = amplitude * B.w0/B.w * expf(-r2/sq(B.w));
+					S->Phase[i][j][k] = phase * PI / 180 - B.k * (0.5 * r2 / B.R) + B.gouy;
+				}
+			}
 		}
 	}
 	refresh_period(W, wavelength);

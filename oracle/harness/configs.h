@@ -302,6 +302,31 @@ static world cfg_shape_zoo(void)
 	return W;
 }
 
+/* examples/Focused_Beam.c:6-11 (whole-domain beam: a plane source with per-cell amplitude and phase), and
+ * a beam injected through a TFSF box in a dielectric half space, focused in x and y, going down */
+static world cfg_focused_beam(void)
+{
+	dom Dom = {{1200}, {1200}, {1200}};
+	res Res = {20, {40}, {1240}};
+	sur Sur = {{SYM, PML}, {SYM, PML}, {PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	focusedBeam(W, Dom, Ex, 0, INF, 0, 0, Sine, 500, 3, 2);
+	return W;
+}
+
+static world cfg_focused_tfsf(void)
+{
+	dom Dom = {{-500, 500}, {-400, 400}, {-500, 500}};
+	dom DTF = {{-300, 300}, {-250, 250}, {-300, 300}};
+	res Res = {10, {20}, {1240}};
+	sur Sur = {{PML, PML}, {PML, PML}, {PML, PML}};
+	world W = createWorld(Dom, Res, Sur, "");
+	object Substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF, -100}}};
+	putObjects(W, n(1.5), Substrate, Air);
+	focusedBeam(W, DTF, Ey, 40, -60, 50, 180, Pulse, 600, 900, 1.5, 1, 30);
+	return W;
+}
+
 /* randomised differential test: a world drawn from the seed in the environment variable FUZZ_SEED --
  * cell sizes (isotropic or not), time step, domain, flat (2-D) axes, boundary types per axis (PML with
  * several depths incl. true CPML, mirror, PEC, periodic, Bloch -> complex fields), graded grids, sub-pixel
@@ -429,6 +454,8 @@ static const harness_config harness_configs[] = {
 	{"aniso_ade",   cfg_aniso_ade,   100, 1},
 	{"bloch_wide",  cfg_bloch_wide,  70, 0},
 	{"shape_zoo",   cfg_shape_zoo,   90, 0},
+	{"focused_beam", cfg_focused_beam, 100, 0},
+	{"focused_tfsf", cfg_focused_tfsf, 110, 0},
 	{"fuzz",        cfg_fuzz,        40, 0},
 	{"guided_y",    cfg_guided_y,    110, 0},
 	{"guided_xz",   cfg_guided_xz,   110, 0},

@@ -12,7 +12,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 CONFIGS = ["dipole_pml", "vacuum_cpml", "pec_box", "pbc_slab", "nanoblock", "tfsf_normal",
            "phc", "metasurface", "dipole_band", "aniso_ade", "bloch_wide", "chi2_shg", "chi2_twm", "chi2_alias",
-           "guided_y", "guided_xz", "shape_zoo"]
+           "guided_y", "guided_xz", "shape_zoo", "focused_beam", "focused_tfsf"]
 
 
 MONITOR_CONFIGS = ["nanoblock", "metasurface", "dipole_band", "phc", "dipole_pml", "aniso_ade"]
