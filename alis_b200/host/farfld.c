@@ -24,28 +24,28 @@
  * the pixel is outside the map (reference farfld.c:14-41) --------------------------------------------- */
 void CylindericalMap(int x, int y, int X, int Y, float angle[2])
 {
-	angle[0] = 180.0 - 180.0 * y / Y;
-	angle[1] = 360.0 * x / X;
+	angle[0] = 180.0 - 180.0 * y / Y;               /* polar angle: rows from the north pole down */
+	angle[1] = 360.0 * x / X;                       /* azimuth: columns */
 }
 
-void NorthernAzimuthalMap(int x, int y, int X, int Y, float angle[2])
+/* azimuthal equidistant chart of one hemisphere: radius from the image centre = polar distance from
+ * that hemisphere's pole, 90 degrees at the rim; pixels outside the disc get theta = INF */
+static void hemisphere_chart(int x, int y, int X, int Y, int southern, float angle[2])
 {
-	angle[0] = 180 * sqrtf(sq(x/(X-1.0)-0.5) + sq(y/(Y-1.0)-0.5));
+	const float radius = 180 * sqrtf(sq(x/(X-1.0)-0.5) + sq(y/(Y-1.0)-0.5));
 	angle[1] = 180 * atan2f(y/(Y-1.0)-0.5, x/(X-1.0)-0.5) / PI;
-	if (angle[0] > 90) angle[0] = INF;
+	if (southern) { angle[0] = 180 - radius; if (angle[0] < 90) angle[0] = INF; }
+	else          { angle[0] = radius;       if (angle[0] > 90) angle[0] = INF; }
 }
 
-void SouthernAzimuthalMap(int x, int y, int X, int Y, float angle[2])
-{
-	angle[0] = 180 - 180 * sqrtf(sq(x/(X-1.0)-0.5) + sq(y/(Y-1.0)-0.5));
-	angle[1] = 180 * atan2f(y/(Y-1.0)-0.5, x/(X-1.0)-0.5) / PI;
-	if (angle[0] < 90) angle[0] = INF;
-}
+void NorthernAzimuthalMap(int x, int y, int X, int Y, float angle[2]) { hemisphere_chart(x, y, X, Y, 0, angle); }
+void SouthernAzimuthalMap(int x, int y, int X, int Y, float angle[2]) { hemisphere_chart(x, y, X, Y, 1, angle); }
 
 void AzimuthalMap(int x, int y, int X, int Y, float angle[2])      /* two hemispheres side by side */
 {
-	if (x < (X+1)/2) NorthernAzimuthalMap(x, y, (X+1)/2, Y, angle);
-	if (x > X/2) SouthernAzimuthalMap(x-X/2, y, (X+1)/2, Y, angle);
+	const int half = (X+1)/2;
+	if (x < half) hemisphere_chart(x, y, half, Y, 0, angle);
+	if (x > X/2) hemisphere_chart(x-X/2, y, half, Y, 1, angle);
 }
 
 /* direction (a,b) given relative to an axis tilted by theta, back in the global frame */
