@@ -118,49 +118,74 @@ struct object {
 	void *p;
 };
 
-/* ---- field storage ------------------------------------------------------------------------- */
+/* ---- field storage -------------------------------------------------------------------------
+ * Member names (and their order) are the reference's: drivers and the engine bridge address
+ * them by name. */
 typedef struct {
-	float ***x, ***y, ***z;                              /* host views [iMIN-1..iMAX+1][..][..] */
-	float ***yMinPx, ***zMinPx, ***xMinPy, ***zMinPy, ***xMinPz, ***yMinPz;   /* psi: device only */
-	float ***yMaxPx, ***zMaxPx, ***xMaxPy, ***zMaxPy, ***xMaxPz, ***yMaxPz;
-	float *****Jx, *****Jy, *****Jz, *****Kx, *****Ky, *****Kz;               /* ADE host views [n][p] */
-	float t;
+	float ***x;                                          /* host views of the three components,         */
+	float ***y;                                          /*   [iMIN-1..iMAX+1][jMIN-1..jMAX+1][kMIN-1..kMAX+1] */
+	float ***z;
+	float ***yMinPx, ***zMinPx;                          /* CPML psi arrays (device only, never allocated */
+	float ***xMinPy, ***zMinPy;                          /*   on the host): <slab axis><side>P<component> */
+	float ***xMinPz, ***yMinPz;
+	float ***yMaxPx, ***zMaxPx;
+	float ***xMaxPy, ***zMaxPy;
+	float ***xMaxPz, ***yMaxPz;
+	float *****Jx, *****Jy, *****Jz;                     /* ADE polarisation currents, host views [n][p]  */
+	float *****Kx, *****Ky, *****Kz;                     /* second ADE variable of critical-point poles   */
+	float t;                                             /* time of this field set                        */
 } vfield;
 
 typedef struct {
-	float *dx, *dy, *dz, *dtdx, *dtdy, *dtdz;
-	float *xP, *yP, *zP, *xPy, *xPz, *yPz, *yPx, *zPx, *zPy;
-	float ***x, ***y, ***z;                              /* inverse permittivity (E only)      */
-	float ****Jx, ****Jy, ****Jz;                        /* fill factors of dispersive objects */
-	float *ax, *ay, *az;
-	float **JJx, **JJy, **JJz, **JKx, **JKy, **JKz, **JEx, **JEy, **JEz;
-	float **KJx, **KJy, **KJz, **KKx, **KKy, **KKz, **KEx, **KEy, **KEz;
-	int N, *NJ, *NK, *iMin, *iMax, *jMin, *jMax, *kMin, *kMax;
-	object *O;
-	matter *M;
+	float *dx, *dy, *dz;                                 /* cell sizes seen by this field set             */
+	float *dtdx, *dtdy, *dtdz;                           /* dt / (kappa * cell size)                      */
+	float *xP, *yP, *zP;                                 /* CPML tables: psi decay ...                    */
+	float *xPy, *xPz, *yPz, *yPx, *zPx, *zPy;            /*   ... and psi drive per (axis, component)     */
+	float ***x, ***y, ***z;                              /* inverse permittivity (E only)                 */
+	float ****Jx, ****Jy, ****Jz;                        /* fill factors of dispersive objects [n]        */
+	float *ax, *ay, *az;                                 /* conductivity loss factor per object           */
+	float **JJx, **JJy, **JJz;                           /* pole coefficients [n][p]: J <- JJ J + JK K + JE E */
+	float **JKx, **JKy, **JKz;
+	float **JEx, **JEy, **JEz;
+	float **KJx, **KJy, **KJz;                           /*                           K <- KJ J + KK K + KE E */
+	float **KKx, **KKy, **KKz;
+	float **KEx, **KEy, **KEz;
+	int N;                                               /* number of dispersive objects                  */
+	int *NJ, *NK;                                        /* Drude poles / all poles per object            */
+	int *iMin, *iMax, *jMin, *jMax, *kMin, *kMax;        /* bounding box per object                       */
+	object *O;                                           /* the object list as given to putObjects ...    */
+	matter *M;                                           /* ... and its matter list (last = background)   */
 } coeffs;
 
 struct world {
-	dom Dom;
+	dom Dom;                                             /* the arguments of createWorld, normalised      */
 	res Res;
 	sur Sur;
-	float t, dt, dx, dy, dz, eV, f;
-	float xMin, xMax, yMin, yMax, zMin, zMax;
-	float xMIN, xMAX, yMIN, yMAX, zMIN, zMAX;
-	float coskx, sinkx, cosky, sinky, coskz, sinkz, coskyp, coskym, sinkyp, sinkym;
-	float xSize, ySize, zSize, xyArea, xzArea, yzArea;
-	int iMin, iMax, iNum, jMin, jMax, jNum, kMin, kMax, kNum;
-	int iMIN, iMAX, iNUM, jMIN, jMAX, jNUM, kMIN, kMAX, kNUM;
-	int xMinSur, xMaxSur, yMinSur, yMaxSur, zMinSur, zMaxSur;
-	int subN, complexField, sourceType;
-	unsigned long int n, N, T;
-	int (*xtoi)(world, float), (*ytoj)(world, float), (*ztok)(world, float);
-	float (*itox)(world, float), (*jtoy)(world, float), (*ktoz)(world, float);
-	char ID[128];
-	vfield *E, *H;
+	float t, dt;                                         /* time after the last H update; time step       */
+	float dx, dy, dz;                                    /* nominal cell sizes                            */
+	float eV, f;                                         /* energy unit of the material tables; source frequency */
+	float xMin, xMax, yMin, yMax, zMin, zMax;            /* interior domain ...                           */
+	float xMIN, xMAX, yMIN, yMAX, zMIN, zMAX;            /* ... and domain including the absorbing layers */
+	float coskx, sinkx, cosky, sinky, coskz, sinkz;      /* Bloch phase per period / mirror parity (+-1)  */
+	float coskyp, coskym, sinkyp, sinkym;                /* hexagonal Bloch boundary: the two skew phases */
+	float xSize, ySize, zSize;
+	float xyArea, xzArea, yzArea;
+	int iMin, iMax, iNum, jMin, jMax, jNum, kMin, kMax, kNum;   /* interior index ranges                  */
+	int iMIN, iMAX, iNUM, jMIN, jMAX, jNUM, kMIN, kMAX, kNUM;   /* index ranges incl. absorbing layers    */
+	int xMinSur, xMaxSur, yMinSur, yMaxSur, zMinSur, zMaxSur;   /* resolved surface codes                 */
+	int subN;                                            /* sub-pixel samples per axis                    */
+	int complexField;                                    /* 1: a second (imaginary) field set exists      */
+	int sourceType;
+	unsigned long int n;                                 /* completed steps                               */
+	unsigned long int N;                                 /* length of the finite sources, in steps        */
+	unsigned long int T;                                 /* source period, in steps                       */
+	int (*xtoi)(world, float), (*ytoj)(world, float), (*ztok)(world, float);     /* coordinate -> index   */
+	float (*itox)(world, float), (*jtoy)(world, float), (*ktoz)(world, float);   /* (fractional) index -> coordinate */
+	char ID[128];                                        /* output prefix                                 */
+	vfield *E, *H;                                       /* field sets [1 + complexField]                 */
 	coeffs *CE, *CH;
-	source SE, SH;
-	tfsf S;
+	source SE, SH;                                       /* soft source lists                             */
+	tfsf S;                                              /* TFSF list                                     */
 	/* --- alis-b200 --- */
 	void *b200_bridge;                                   /* alis_bridge*: engine + descriptors */
 	void *b200_view;                                     /* host-view bookkeeping              */
