@@ -5,28 +5,37 @@
  * Output: <ID>/Power.txt, Far-field.txt, Far-field-theta.txt, Near-field.txt. */
 #include <alis.h>
 
+/* Ex on the z axis at height z, scaled so that a unit-power dipole gives 1 in the far zone */
+static float scaled_probe(world sim, float z)
+{
+	return get(sim, Ex, 0, 0, z) * z * sqrtf(8*PI/3);
+}
+
 int main(int argc, char **argv)
 {
-	dom Dom = {{500}, {500}, {500}};
-	res Res = {10, {20}, {1240}, {{2, 100}, {2, 100}, {2, 100}}};
-	sur Sur = {{SYM, PML}, {SYM, PML}, {SYM, PML}};
-	world W = createWorld(Dom, Res, Sur, "%s.out", argv[0]);
+	dom octant = {{500}, {500}, {500}};
+	res grid = {10, {20}, {1240}, {{2, 100}, {2, 100}, {2, 100}}};   /* cells double outside +-100 nm */
+	sur walls = {{SYM, PML}, {SYM, PML}, {SYM, PML}};
+	world sim = createWorld(octant, grid, walls, "%s.out", argv[0]);
 
-	pointDipole(W, Ex, 0, 0, 0, Band, 400, 800);
-	phaser P = createPhasers(W, 400, 800, 5);
+	pointDipole(sim, Ex, 0, 0, 0, Band, 400, 800);
+	phaser list = createPhasers(sim, 400, 800, 5);
+	const long steps = list->N;                                   /* one beat period of the frequency comb */
 
-	for (int n=1; timer(n, P->N); n++) {
-		updateE(W);
-		updateH(W);
-		updatePhaser(W, P);
-		writeSpectrum(W, P->N, 400, 800, "/Near-field", get(W,Ex,0,0,250)*250*sqrtf(8*PI/3), get(W,Ex,0,0,500)*500*sqrtf(8*PI/3));
+	for (long step = 1; timer(step, steps); step++) {
+		updateE(sim);
+		updateH(sim);
+		updatePhaser(sim, list);
+		const float at_250 = scaled_probe(sim, 250), at_500 = scaled_probe(sim, 500);
+		writeSpectrum(sim, steps, 400, 800, "/Near-field", at_250, at_500);
 	}
-	writePoyntingSpectrum(W, "/Power", P);
-	writeFarFieldSpectrum(W, Unpol, 0, 0, "/Far-field", P);
-	farFieldTheta(W, choosePhaser(P,500), 0, "/Far-field-theta");
+	writePoyntingSpectrum(sim, "/Power", list);
+	writeFarFieldSpectrum(sim, Unpol, 0, 0, "/Far-field", list);
 
-	printf("Total radiated power: %f\n", phaserPoyntingOut(choosePhaser(P,500)));
-	printf("Intensity to (0,0) / (3/(8*PI)): %f\n", farFieldI(choosePhaser(P,500),Unpol,0,0) * 8*PI/3);
-	printf("Radiated power to hemisphere * 2: %f\n", farFieldFlux(choosePhaser(P,500),Unpol,0,0,90) * 2);
+	phaser green = choosePhaser(list, 500);
+	farFieldTheta(sim, green, 0, "/Far-field-theta");
+	printf("Total radiated power: %f\n", phaserPoyntingOut(green));
+	printf("Intensity to (0,0) / (3/(8*PI)): %f\n", farFieldI(green, Unpol, 0, 0) * 8*PI/3);
+	printf("Radiated power to hemisphere * 2: %f\n", farFieldFlux(green, Unpol, 0, 0, 90) * 2);
 	return 0;
 }

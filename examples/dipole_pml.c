@@ -1,27 +1,35 @@
 /* Point dipole radiating in vacuum inside a CPML box (one octant, mirror symmetry on the three
  * coordinate planes).  Same physics as the reference's examples/Dipole_PML.c; written against the
  * public API in include/alis.h and buildable against either library (see examples/README.md).
- * Output: <ID>/Ez-*.png snapshots (real PNGs with this library) and <ID>/probe.txt. */
+ * Output: PNG frames of two cuts under <ID>/ and <ID>/probe.txt (t, Ez and Hy at x = 300, Ez at z = 500). */
 #include <alis.h>
+
+static const float HALF_SIZE = 1000;      /* nm, each axis (the mirror planes double it) */
+static const float CELL = 20, TIME_STEP = 10;
+static const float RUN_TIME = 3000;
 
 int main(int argc, char **argv)
 {
-	dom Dom = {{1000}, {1000}, {1000}};
-	res Res = {10, {20}, {1240}};
-	sur Sur = {{SYM, PML}, {SYM, PML}, {SYM, PML}, {24}};
-	world W = createWorld(Dom, Res, Sur, "%s.out", argv[0]);
+	dom box = {{HALF_SIZE}, {HALF_SIZE}, {HALF_SIZE}};
+	res grid = {TIME_STEP, {CELL}, {1240}};
+	sur walls = {{SYM, PML}, {SYM, PML}, {SYM, PML}, {24}};          /* 24 cells: true CPML */
+	world sim = createWorld(box, grid, walls, "%s.out", argv[0]);
 
-	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 10000000);
+	pointDipole(sim, Ez, 0, 0, 0, Pulse, 400, 800, 10000000);
 
-	slice XY = createSlice(W, W->xMIN, W->xMAX, W->yMIN, W->yMAX, 0, 0);
-	slice XZ = createSlice(W, W->xMIN, W->xMAX, 0, 0, W->zMIN, W->zMAX);
+	slice horizontal = createSlice(sim, sim->xMIN, sim->xMAX, sim->yMIN, sim->yMAX, 0, 0);
+	slice vertical   = createSlice(sim, sim->xMIN, sim->xMAX, 0, 0, sim->zMIN, sim->zMAX);
 
-	for (int n=1, N=3000/W->dt; timer(n, N); n++) {
-		updateE(W);
-		updateH(W);
-		sliceSnap(W, Ez, XY, 10, png(dkbr,1), "/%%/");
-		sliceSnap(W, Ez, XZ, 10, png(dkbr,1), "/%%/");
-		writeRow(W, "/probe", W->t, get(W, Ez, 300, 0, 0), get(W, Hy, 300, 0, 0), get(W, Ez, 0, 0, 500));
+	const int steps = RUN_TIME/sim->dt;
+	int step = 1;
+	while (timer(step, steps)) {
+		updateE(sim);
+		updateH(sim);
+		sliceSnap(sim, Ez, horizontal, 10, png(dkbr,1), "/%%/");
+		sliceSnap(sim, Ez, vertical, 10, png(dkbr,1), "/%%/");
+		const float e_near = get(sim, Ez, 300, 0, 0), h_near = get(sim, Hy, 300, 0, 0), e_axis = get(sim, Ez, 0, 0, 500);
+		writeRow(sim, "/probe", sim->t, e_near, h_near, e_axis);
+		step++;
 	}
 	return 0;
 }

@@ -5,26 +5,31 @@
  * Output: <ID>/Far-field-theta.txt and <ID>/Log-*.png far-field maps. */
 #include <alis.h>
 
+static const float PERIOD = 500;          /* nm, unit cell in x and y */
+
 int main(int argc, char **argv)
 {
-	dom DTF = {{500}, {500}, {300}};
-	dom DSF = {{500}, {500}, {500}};
-	res Res = {10, {20}, {1240}};
-	sur Sur = {{BBC}, {SYM}, {PML}};
-	world W = createWorld(DSF, Res, Sur, "%s.out", argv[0]);
+	dom unit_cell = {{PERIOD}, {PERIOD}, {500}};
+	dom illuminated = {{PERIOD}, {PERIOD}, {300}};                 /* total-field region of the plane wave */
+	res grid = {10, {20}, {1240}};
+	sur walls = {{BBC}, {SYM}, {PML}};
+	world sim = createWorld(unit_cell, grid, walls, "%s.out", argv[0]);
 
-	object Nanoblock = {Lattice, {{500}, {500}}, objects {{Box, {{0, 200}, {-100, 100}, {-100, 100}}}}};
-	object Substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF,-100}}};
-	putObjects(W, n(4), Nanoblock, n(1.5), Substrate, Air);
-	planewave(W, DTF, Ppol, 55, 0, Sine, 530, 5);
+	object pillar = {Box, {{0, 200}, {-100, 100}, {-100, 100}}};
+	object pillars = {Lattice, {{PERIOD}, {PERIOD}}, &pillar};
+	object substrate = {Box, {{-INF, INF}, {-INF, INF}, {-INF,-100}}};
+	putObjects(sim, n(4), pillars, n(1.5), substrate, Air);
+	planewave(sim, illuminated, Ppol, 55, 0, Sine, 530, 5);
 
-	phaser P = createPhaser(W, 500,-2000, 2000,-2000, 2000);
-	for (int n=1, N=10*W->T; timer(n, N); n++) {
-		updateE(W);
-		updateH(W);
-		if (N-n < W->T) updatePhaser(W, P);
+	/* the monitor box is four periods wide: the far field is that of 4 x 4 replicas */
+	phaser dft = createPhaser(sim, 500, -2000, 2000, -2000, 2000);
+	const long periods = 10, period = sim->T;
+	for (long step = 1; timer(step, periods*period); step++) {
+		updateE(sim);
+		updateH(sim);
+		if (periods*period - step < period) updatePhaser(sim, dft);   /* the last period only */
 	}
-	farFieldTheta(W, P, 0, "/Far-field-theta");
-	farFieldProfile(W, P, AzimuthalMap, 360, 180, png(jet,0), "/Log-");
+	farFieldTheta(sim, dft, 0, "/Far-field-theta");
+	farFieldProfile(sim, dft, AzimuthalMap, 360, 180, png(jet,0), "/Log-");
 	return 0;
 }
