@@ -229,6 +229,50 @@ static void copy_background_stack(world W, tfsf S, matter *M, object *O)
 /* The auxiliary world carries the incident field.  Axes marked NIL in SUR are collapsed to a
  * two-cell periodic (or Bloch / symmetric) strip -- the engine reads it with clamped indices
  * where the reference aliases row pointers (source.c:223-248, 298-317). */
+/* one axis of the main world's grid, so that the per-axis rules below are written once */
+typedef struct {
+	int min_sur;
+	float outer_lo;                               /* xMIN: coordinate of the outermost cell      */
+	int iMin, iMax, iMIN, iMAX;                   /* interior and outer index range              */
+	int (*to_index)(world, float);
+	float (*to_coord)(world, float);
+} grid_axis;
+
+static grid_axis grid_axis_of(world W, int a)
+{
+	const grid_axis x = { W->xMinSur, W->xMIN, W->iMin, W->iMax, W->iMIN, W->iMAX, W->xtoi, W->itox };
+	const grid_axis y = { W->yMinSur, W->yMIN, W->jMin, W->jMax, W->jMIN, W->jMAX, W->ytoj, W->jtoy };
+	const grid_axis z = { W->zMinSur, W->zMIN, W->kMin, W->kMax, W->kMIN, W->kMAX, W->ztok, W->ktoz };
+	return a == 0 ? x : a == 1 ? y : z;
+}
+
+/* transverse axis the caller left open (NIL): the auxiliary world is one cell wide there and closes
+ * on itself the way the main world does (mirror, Bloch or plain periodic) */
+static void collapse_transverse(world W, int a, float *lo, float *hi, float *min_sur)
+{
+	const grid_axis A = grid_axis_of(W, a);
+	const int mirror = A.min_sur == SYM;
+	*lo = mirror ? 0 : A.outer_lo;
+	*hi = mirror ? 0 : A.to_coord(W, 1 + A.to_index(W, A.outer_lo));
+	*min_sur = mirror ? SYM : (A.min_sur == BBC) ? BBC : PBC;
+}
+
+/* requested TFSF extent along one axis -> index range lo..hi of the box (snapped to the grid, pushed
+ * to the outer boundary where it reaches into the PML) and tangential range LO..HI of the strips */
+static void snap_box_axis(world W, int a, int mirrored, float want_lo, float want_hi, int *lo, int *hi, int *LO, int *HI)
+{
+	const grid_axis A = grid_axis_of(W, a);
+	if ((!want_hi && want_lo > 0) || mirrored) {          /* a single positive number = symmetric extent */
+		want_hi = want_hi ? want_hi : want_lo;
+		want_lo = -want_hi;
+	}
+	const int whole = want_lo == want_hi;                 /* degenerate request: the whole interior */
+	*lo = A.min_sur == SYM ? 0 : whole ? A.iMin : A.iMin > A.to_index(W, want_lo) ? A.iMIN : A.to_index(W, want_lo);
+	*hi = whole ? A.iMax : A.iMax < A.to_index(W, want_hi) ? A.iMAX : A.to_index(W, want_hi);
+	*LO = (*lo == A.iMIN) ? *lo : *lo + 1;
+	*HI = (*hi == A.iMAX) ? *hi + 1 : *hi;
+}
+
 tfsf (createTFSF)(world W, dom DOM, sur SUR)
 {
 	tfsf S;
@@ -237,40 +281,23 @@ tfsf (createTFSF)(world W, dom DOM, sur SUR)
 	while (*tail) tail = &(*tail)->S;
 	*tail = S;
 
-	dom Dom = W->Dom;
-	sur Sur = SUR;
-	if (SUR.x.MinSur==NIL) {
-		Dom.x.Min = (W->xMinSur==SYM) ? 0 : W->xMIN;
-		Dom.x.Max = (W->xMinSur==SYM) ? 0 : W->itox(W, 1+W->xtoi(W, W->xMIN));
-		Sur.x.MinSur = (W->xMinSur==SYM) ? SYM : (W->xMinSur==BBC) ? BBC : PBC;
-	}
-	if (SUR.y.MinSur==NIL) {
-		Dom.y.Min = (W->yMinSur==SYM) ? 0 : W->yMIN;
-		Dom.y.Max = (W->yMinSur==SYM) ? 0 : W->jtoy(W, 1+W->ytoj(W, W->yMIN));
-		Sur.y.MinSur = (W->yMinSur==SYM) ? SYM : (W->yMinSur==BBC) ? BBC : PBC;
-	}
+	/* the auxiliary world that carries the incident field: the main world's domain, collapsed along
+	 * the open transverse axes and padded by one cell beyond both z faces */
+	dom aux_dom = W->Dom;
+	sur aux_sur = SUR;
+	if (SUR.x.MinSur==NIL) collapse_transverse(W, 0, &aux_dom.x.Min, &aux_dom.x.Max, &aux_sur.x.MinSur);
+	if (SUR.y.MinSur==NIL) collapse_transverse(W, 1, &aux_dom.y.Min, &aux_dom.y.Max, &aux_sur.y.MinSur);
 	if (SUR.z.MinSur==NIL) {
-		Dom.z.Min = W->ktoz(W, W->ztok(W, W->zMin)-1);
-		Dom.z.Max = W->ktoz(W, W->ztok(W, W->zMax)+1);
-		Sur.z.MinSur = Sur.z.MaxSur = PML;
+		aux_dom.z.Min = W->ktoz(W, W->ztok(W, W->zMin)-1);
+		aux_dom.z.Max = W->ktoz(W, W->ztok(W, W->zMax)+1);
+		aux_sur.z.MinSur = aux_sur.z.MaxSur = PML;
 	}
-	S->W = createWorld(Dom, W->Res, Sur, "");
+	S->W = createWorld(aux_dom, W->Res, aux_sur, "");
 	strcpy(S->W->ID, W->ID);
 
-	/* TFSF box: requested domain snapped to the grid, pushed to the outer boundary where it
-	 * reaches the PML; iMIN..iMAX is the tangential range of the correction strips */
-	if (!DOM.x.Max && DOM.x.Min>0 || SUR.x.MinSur==SYM) DOM.x.Min = -(DOM.x.Max = DOM.x.Max ? DOM.x.Max : DOM.x.Min);
-	if (!DOM.y.Max && DOM.y.Min>0 || SUR.y.MinSur==SYM) DOM.y.Min = -(DOM.y.Max = DOM.y.Max ? DOM.y.Max : DOM.y.Min);
-	if (!DOM.z.Max && DOM.z.Min>0 || SUR.z.MinSur==SYM) DOM.z.Min = -(DOM.z.Max = DOM.z.Max ? DOM.z.Max : DOM.z.Min);
-	S->iMin = W->xMinSur==SYM ? 0 : DOM.x.Min == DOM.x.Max ? W->iMin : W->iMin > W->xtoi(W, DOM.x.Min) ? W->iMIN : W->xtoi(W, DOM.x.Min);
-	S->jMin = W->yMinSur==SYM ? 0 : DOM.y.Min == DOM.y.Max ? W->jMin : W->jMin > W->ytoj(W, DOM.y.Min) ? W->jMIN : W->ytoj(W, DOM.y.Min);
-	S->kMin = W->zMinSur==SYM ? 0 : DOM.z.Min == DOM.z.Max ? W->kMin : W->kMin > W->ztok(W, DOM.z.Min) ? W->kMIN : W->ztok(W, DOM.z.Min);
-	S->iMax = DOM.x.Min == DOM.x.Max ? W->iMax : W->iMax < W->xtoi(W, DOM.x.Max) ? W->iMAX : W->xtoi(W, DOM.x.Max);
-	S->jMax = DOM.y.Min == DOM.y.Max ? W->jMax : W->jMax < W->ytoj(W, DOM.y.Max) ? W->jMAX : W->ytoj(W, DOM.y.Max);
-	S->kMax = DOM.z.Min == DOM.z.Max ? W->kMax : W->kMax < W->ztok(W, DOM.z.Max) ? W->kMAX : W->ztok(W, DOM.z.Max);
-	S->iMIN = (S->iMin == W->iMIN) ? S->iMin : S->iMin + 1, S->iMAX = (S->iMax == W->iMAX) ? S->iMax + 1 : S->iMax;
-	S->jMIN = (S->jMin == W->jMIN) ? S->jMin : S->jMin + 1, S->jMAX = (S->jMax == W->jMAX) ? S->jMax + 1 : S->jMax;
-	S->kMIN = (S->kMin == W->kMIN) ? S->kMin : S->kMin + 1, S->kMAX = (S->kMax == W->kMAX) ? S->kMax + 1 : S->kMax;
+	snap_box_axis(W, 0, SUR.x.MinSur==SYM, DOM.x.Min, DOM.x.Max, &S->iMin, &S->iMax, &S->iMIN, &S->iMAX);
+	snap_box_axis(W, 1, SUR.y.MinSur==SYM, DOM.y.Min, DOM.y.Max, &S->jMin, &S->jMax, &S->jMIN, &S->jMAX);
+	snap_box_axis(W, 2, SUR.z.MinSur==SYM, DOM.z.Min, DOM.z.Max, &S->kMin, &S->kMax, &S->kMIN, &S->kMAX);
 
 	if (W->CE->M && W->CE->O) copy_background_stack(W, S, W->CE->M, W->CE->O);
 	alis_host_dirty(W, ALIS_DIRTY_SOURCES | ALIS_DIRTY_COPIES);
