@@ -61,38 +61,47 @@ static void prefetch(world W, field F, slice S)
 }
 
 /* ---- resampling a graded grid onto the uniform raster (reference slices.c:25-64) --------------------- */
+static float *cell_at(float ***F, const int at[3]) { return &F[at[0]][at[1]][at[2]]; }
+
+/* one pass of the resampling: along axis `a` every grid interval [c, c+1] is spread linearly over the
+ * raster points n*d it covers; axes before `a` are already on the raster, the ones after still on the grid.
+ * Intervals go in ascending order: a raster point on the seam between two intervals takes the upper one's value */
+static void resample_along(world W, slice S, int a, float ***from, float ***to)
+{
+	const int grid_lo[3] = {S->iMin, S->jMin, S->kMin}, grid_hi[3] = {S->iMax, S->jMax, S->kMax};
+	const int rast_lo[3] = {S->iMIN, S->jMIN, S->kMIN}, rast_hi[3] = {S->iMAX, S->jMAX, S->kMAX};
+	const float d = a == 0 ? W->dx : a == 1 ? W->dy : W->dz;
+	const int u = (a+1)%3, v = (a+2)%3;
+	const int u0 = u < a ? rast_lo[u] : grid_lo[u], u1 = u < a ? rast_hi[u] : grid_hi[u];
+	const int v0 = v < a ? rast_lo[v] : grid_lo[v], v1 = v < a ? rast_hi[v] : grid_hi[v];
+
+	for (int c = grid_lo[a]; c < grid_hi[a]; c++) {
+		const float p0 = a == 0 ? W->itox(W, c) : a == 1 ? W->jtoy(W, c) : W->ktoz(W, c);
+		const float p1 = a == 0 ? W->itox(W, c+1) : a == 1 ? W->jtoy(W, c+1) : W->ktoz(W, c+1);
+		const int n0 = p0/d + (c>0 ? 1 : 0), n1 = p1/d - (c<0 ? 1 : 0);
+		for (int n = n0; n <= n1; n++) {
+			const float w_lower = p1 - n*d, w_upper = n*d - p0;
+			int lower[3], upper[3], out[3];
+			lower[a] = c, upper[a] = c+1, out[a] = n;
+			for (int p = u0; p <= u1; p++) for (int q = v0; q <= v1; q++) {
+				lower[u] = upper[u] = out[u] = p;
+				lower[v] = upper[v] = out[v] = q;
+				*cell_at(to, out) = (*cell_at(from, lower) * w_lower + *cell_at(from, upper) * w_upper) / (p1 - p0);
+			}
+		}
+	}
+}
+
 static float ***to_uniform_raster(world W, slice S, float ***F)
 {
-	float ***T, ***G = makeField(S->iMIN, S->iMAX, S->jMIN, S->jMAX, S->kMIN, S->kMAX);
+	const int stretched[3] = { S->iMin != S->iMIN || S->iMax != S->iMAX, S->jMin != S->jMIN || S->jMax != S->jMAX, S->kMin != S->kMIN || S->kMax != S->kMAX };
+	float ***spare = makeField(S->iMIN, S->iMAX, S->jMIN, S->jMAX, S->kMIN, S->kMAX);
 
-	if (S->iMin != S->iMIN || S->iMax != S->iMAX) {
-		T = F, F = G, G = T;
-		for (int i=S->iMin; i<S->iMax; i++) {
-			float x0 = W->itox(W, i), x1 = W->itox(W, i+1);
-			int n0 = x0/W->dx+(i>0?1:0), n1 = x1/W->dx-(i<0?1:0);
-			for (int j=S->jMin; j<=S->jMax; j++) for (int n = n0; n <= n1; n++) for (int k=S->kMin; k<=S->kMax; k++)
-				F[n][j][k] = (G[i][j][k] * (x1 - n*W->dx) + G[i+1][j][k] * (n*W->dx - x0)) / (x1 - x0);
-		}
+	for (int a = 0; a < 3; a++) if (stretched[a]) {          /* ping-pong between the slice's buffer and the spare */
+		resample_along(W, S, a, F, spare);
+		float ***done = spare; spare = F; F = done;
 	}
-	if (S->jMin != S->jMIN || S->jMax != S->jMAX) {
-		T = F, F = G, G = T;
-		for (int j=S->jMin; j<S->jMax; j++) {
-			float y0 = W->jtoy(W, j), y1 = W->jtoy(W, j+1);
-			int n0 = y0/W->dy+(j>0?1:0), n1 = y1/W->dy-(j<0?1:0);
-			for (int i=S->iMIN; i<=S->iMAX; i++) for (int n = n0; n <= n1; n++) for (int k=S->kMin; k<=S->kMax; k++)
-				F[i][n][k] = (G[i][j][k] * (y1 - n*W->dy) + G[i][j+1][k] * (n*W->dy - y0)) / (y1 - y0);
-		}
-	}
-	if (S->kMin != S->kMIN || S->kMax != S->kMAX) {
-		T = F, F = G, G = T;
-		for (int k=S->kMin; k<S->kMax; k++) {
-			float z0 = W->ktoz(W, k), z1 = W->ktoz(W, k+1);
-			int n0 = z0/W->dz+(k>0?1:0), n1 = z1/W->dz-(k<0?1:0);
-			for (int i=S->iMIN; i<=S->iMAX; i++) for (int j=S->jMIN; j<=S->jMAX; j++) for (int n = n0; n <= n1; n++)
-				F[i][j][n] = (G[i][j][k] * (z1 - n*W->dz) + G[i][j][k+1] * (n*W->dz - z0)) / (z1 - z0);
-		}
-	}
-	removeField(G, S->iMIN, S->jMIN, S->kMIN);
+	removeField(spare, S->iMIN, S->jMIN, S->kMIN);
 	return F;
 }
 

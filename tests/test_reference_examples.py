@@ -90,3 +90,27 @@ def test_unmodified_reference_example_runs_and_matches(name, tmp_path):
     if name == "Dipole_PML":                      # writes PNG frames only: our encoder must have produced them
         pngs = [f for _, _, fs in os.walk(str(tmp_path / "mine")) for f in fs if f.endswith(".png")]
         assert len(pngs) > 10
+
+
+@needs_ref
+@needs_lib
+def test_graded_grid_slices_are_resampled_like_the_reference(tmp_path):
+    """oracle/harness/graded_slices.c: 1-D / 2-D text slices and a 3-D HDF5 slice of a world graded along
+    x, y and z (reference slices.c:3-36 resampling onto the uniform raster): files identical byte for byte"""
+    src = os.path.join(helpers.ROOT, "oracle", "harness", "graded_slices.c")
+    files = {}
+    for tag, build in (("ref", build_ref), ("mine", build_mine)):
+        d = tmp_path / tag
+        d.mkdir()
+        r = build(src, str(d / "gs"))
+        assert r.returncode == 0, r.stderr[-1000:]
+        env = dict(os.environ, LD_LIBRARY_PATH=helpers.TEST_BIN + os.pathsep + os.path.join(helpers.ROOT, "oracle"))
+        r = subprocess.run([str(d / "gs")], cwd=str(d), env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+        out = d / "graded_slices.out"
+        files[tag] = {f: (out / f).read_bytes() for f in sorted(os.listdir(out))}
+    assert len(files["ref"]) == 10 and sorted(files["ref"]) == sorted(files["mine"])
+    xy = np.loadtxt(str(tmp_path / "ref" / "graded_slices.out" / "xy-Ex-120.txt"))
+    assert xy.shape == (35, 31) and np.abs(xy).max() > 0          # the raster, not the 600/40 x 500/30 grid
+    for f, ref in files["ref"].items():
+        assert files["mine"][f] == ref, f
