@@ -179,46 +179,66 @@ static void alloc_dispersive(world W, coeffs *C, int n, bounds B)
 
 /* bounding boxes of every object (the cells whose NODE lies in the object and in no earlier one),
  * widened by one cell below and two above, clipped to the grid (reference object.c:229-279) */
+static bounds nothing_yet(world W)       /* inverted box: any cell shrinks it to itself */
+{
+	return (bounds){ W->iMAX, W->iMIN, W->jMAX, W->jMIN, W->kMAX, W->kMIN };
+}
+
+static void cover(bounds *b, bounds c)   /* smallest box holding both */
+{
+	b->iMin = MIN(b->iMin, c.iMin), b->iMax = MAX(b->iMax, c.iMax);
+	b->jMin = MIN(b->jMin, c.jMin), b->jMax = MAX(b->jMax, c.jMax);
+	b->kMin = MIN(b->kMin, c.kMin), b->kMax = MAX(b->kMax, c.kMax);
+}
+
+static int owner_of_point(const object *O, float x, float y, float z)     /* first object holding the point; the list ends with S == 0 */
+{
+	int o = 0;
+	while (O[o].S && !O[o].S(O[o], x, y, z)) o++;
+	return o;
+}
+
 static bounds *object_bounds(world W, object *O, int N)
 {
 	bounds *B;
 	MALLOC(B, 0, N);
-	for (int o=0; o<N; o++) {
-		B[o].iMin = W->iMAX, B[o].iMax = W->iMIN;
-		B[o].jMin = W->jMAX, B[o].jMax = W->jMIN;
-		B[o].kMin = W->kMAX, B[o].kMax = W->kMIN;
-	}
+	for (int o=0; o<N; o++) B[o] = nothing_yet(W);
+
+	/* node coordinates once per axis instead of once per cell */
+	float *x, *y, *z;
+	MALLOC(x, W->iMIN, W->iMAX - W->iMIN + 1);
+	MALLOC(y, W->jMIN, W->jMAX - W->jMIN + 1);
+	MALLOC(z, W->kMIN, W->kMAX - W->kMIN + 1);
+	for (int i=W->iMIN; i<=W->iMAX; i++) x[i] = W->itox(W, i);
+	for (int j=W->jMIN; j<=W->jMAX; j++) y[j] = W->jtoy(W, j);
+	for (int k=W->kMIN; k<=W->kMAX; k++) z[k] = W->ktoz(W, k);
+
 	#pragma omp parallel
 	{
-		bounds *b;
-		MALLOC(b, 0, N);
-		memcpy(b, B, sizeof(bounds)*N);
+		bounds *mine;                       /* per-thread boxes, merged at the end (min/max: order-free) */
+		MALLOC(mine, 0, N);
+		for (int o=0; o<N; o++) mine[o] = nothing_yet(W);
 		#pragma omp for
 		for (int i=W->iMIN; i<=W->iMAX; i++) for (int j=W->jMIN; j<=W->jMAX; j++) for (int k=W->kMIN; k<=W->kMAX; k++) {
-			int o = 0;
-			while (O[o].S && !(O[o].S(O[o], W->itox(W, i), W->jtoy(W, j), W->ktoz(W, k)))) o++;
-			if (o < N) {
-				b[o].iMin = MIN(i, b[o].iMin), b[o].iMax = MAX(i, b[o].iMax);
-				b[o].jMin = MIN(j, b[o].jMin), b[o].jMax = MAX(j, b[o].jMax);
-				b[o].kMin = MIN(k, b[o].kMin), b[o].kMax = MAX(k, b[o].kMax);
-			}
+			const int o = owner_of_point(O, x[i], y[j], z[k]);
+			if (o < N) cover(&mine[o], (bounds){ i, i, j, j, k, k });
 		}
 		#pragma omp critical
-		for (int o=0; o<N; o++) {
-			B[o].iMin = MIN(b[o].iMin, B[o].iMin), B[o].iMax = MAX(b[o].iMax, B[o].iMax);
-			B[o].jMin = MIN(b[o].jMin, B[o].jMin), B[o].jMax = MAX(b[o].jMax, B[o].jMax);
-			B[o].kMin = MIN(b[o].kMin, B[o].kMin), B[o].kMax = MAX(b[o].kMax, B[o].kMax);
-		}
-		free(b);
+		for (int o=0; o<N; o++) cover(&B[o], mine[o]);
+		free(mine);
 	}
+	free(x + W->iMIN), free(y + W->jMIN), free(z + W->kMIN);
+
+	const bounds grid = { W->iMIN, W->iMAX, W->jMIN, W->jMAX, W->kMIN, W->kMAX };
 	for (int o=0; o<N; o++) {
 		if (B[o].iMin > B[o].iMax || B[o].jMin > B[o].jMax || B[o].kMin > B[o].kMax) {
 			printf("\rVolume of object %d/%d is zero!\n", o+1, N);
 			exit(0);
 		}
-		B[o].iMin = MAX(B[o].iMin-1, W->iMIN), B[o].iMax = MIN(B[o].iMax+2, W->iMAX);
-		B[o].jMin = MAX(B[o].jMin-1, W->jMIN), B[o].jMax = MIN(B[o].jMax+2, W->jMAX);
-		B[o].kMin = MAX(B[o].kMin-1, W->kMIN), B[o].kMax = MIN(B[o].kMax+2, W->kMAX);
+		/* one cell below, two above (the fill factors look at the neighbours), inside the grid */
+		B[o] = (bounds){ MAX(B[o].iMin-1, grid.iMin), MIN(B[o].iMax+2, grid.iMax),
+		                 MAX(B[o].jMin-1, grid.jMin), MIN(B[o].jMax+2, grid.jMax),
+		                 MAX(B[o].kMin-1, grid.kMin), MIN(B[o].kMax+2, grid.kMax) };
 	}
 	return B;
 }
