@@ -136,23 +136,29 @@ static coeffs *make_set_coeffs(world W, sur S, int offset)
 	MALLOC(C, 0, 1);
 	S.pml.Num = S.pml.Num ? S.pml.Num : 12;
 
-	MALLOC(C->dx, W->xMinSur!=SYM ? W->iMIN : -W->iMAX, W->xMinSur!=SYM ? W->iNUM : 2*W->iNUM-1);
-	MALLOC(C->dy, W->yMinSur!=SYM ? W->jMIN : -W->jMAX, W->yMinSur!=SYM ? W->jNUM : 2*W->jNUM-1);
-	MALLOC(C->dz, W->zMinSur!=SYM ? W->kMIN : -W->kMAX, W->zMinSur!=SYM ? W->kNUM : 2*W->kNUM-1);
-	MALLOC(C->dtdx, W->iMIN, W->iNUM);
-	MALLOC(C->dtdy, W->jMIN, W->jNUM);
-	MALLOC(C->dtdz, W->kMIN, W->kNUM);
-
-	for (int i=W->iMIN; i<=W->iMAX; i++) C->dtdx[i] = W->dt/(C->dx[i]=(W->itox(W, i-0.5*(offset-1))-W->itox(W, i-0.5*(offset+1))));
-	for (int j=W->jMIN; j<=W->jMAX; j++) C->dtdy[j] = W->dt/(C->dy[j]=(W->jtoy(W, j-0.5*(offset-1))-W->jtoy(W, j-0.5*(offset+1))));
-	for (int k=W->kMIN; k<=W->kMAX; k++) C->dtdz[k] = W->dt/(C->dz[k]=(W->ktoz(W, k-0.5*(offset-1))-W->ktoz(W, k-0.5*(offset+1))));
-	if (W->xMinSur==SYM) for (int i=1; i<=W->iMAX; i++) C->dx[-i] = C->dx[i];
-	if (W->yMinSur==SYM) for (int j=1; j<=W->jMAX; j++) C->dy[-j] = C->dy[j];
-	if (W->zMinSur==SYM) for (int k=1; k<=W->kMAX; k++) C->dz[-k] = C->dz[k];
-
-	pml_tables(S, offset, &C->xP, &C->xPy, &C->xPz, C->dtdx, W->dt, W->xMinSur, W->xMaxSur, W->iMin, W->iMax, W->iMIN, W->iNUM);
-	pml_tables(S, offset, &C->yP, &C->yPz, &C->yPx, C->dtdy, W->dt, W->yMinSur, W->yMaxSur, W->jMin, W->jMax, W->jMIN, W->jNUM);
-	pml_tables(S, offset, &C->zP, &C->zPx, &C->zPy, C->dtdz, W->dt, W->zMinSur, W->zMaxSur, W->kMin, W->kMax, W->kMIN, W->kNUM);
+	/* per axis: spacing table (mirrored below 0 on a symmetric axis), dt/ds table, then the PML tables,
+	 * which divide dt/ds by kappa in place */
+	struct {
+		float **d, **dtd, **P0, **P1, **P2;
+		int mirror, min_sur, max_sur, Min, Max, MIN, MAX, NUM;
+		float (*to_coord)(world, float);
+	} ax[3] = {
+		{ &C->dx, &C->dtdx, &C->xP, &C->xPy, &C->xPz, W->xMinSur==SYM, W->xMinSur, W->xMaxSur, W->iMin, W->iMax, W->iMIN, W->iMAX, W->iNUM, W->itox },
+		{ &C->dy, &C->dtdy, &C->yP, &C->yPz, &C->yPx, W->yMinSur==SYM, W->yMinSur, W->yMaxSur, W->jMin, W->jMax, W->jMIN, W->jMAX, W->jNUM, W->jtoy },
+		{ &C->dz, &C->dtdz, &C->zP, &C->zPx, &C->zPy, W->zMinSur==SYM, W->zMinSur, W->zMaxSur, W->kMin, W->kMax, W->kMIN, W->kMAX, W->kNUM, W->ktoz },
+	};
+	for (int a=0; a<3; a++) {
+		float *d, *dtd;
+		MALLOC(d, ax[a].mirror ? -ax[a].MAX : ax[a].MIN, ax[a].mirror ? 2*ax[a].NUM-1 : ax[a].NUM);
+		MALLOC(dtd, ax[a].MIN, ax[a].NUM);
+		for (int q=ax[a].MIN; q<=ax[a].MAX; q++) {
+			d[q] = ax[a].to_coord(W, q-0.5*(offset-1)) - ax[a].to_coord(W, q-0.5*(offset+1));
+			dtd[q] = W->dt/d[q];
+		}
+		if (ax[a].mirror) for (int q=1; q<=ax[a].MAX; q++) d[-q] = d[q];
+		*ax[a].d = d, *ax[a].dtd = dtd;
+		pml_tables(S, offset, ax[a].P0, ax[a].P1, ax[a].P2, dtd, W->dt, ax[a].min_sur, ax[a].max_sur, ax[a].Min, ax[a].Max, ax[a].MIN, ax[a].NUM);
+	}
 	C->N = 0;
 	return C;
 }
@@ -165,6 +171,35 @@ static vfield *make_field_set(world W)
 	vfield *F;
 	MALLOC(F, 0, 1+W->complexField);
 	return F;
+}
+
+/* where one axis' index ranges and extents live in the world, and what the caller asked for */
+typedef struct {
+	int *Min, *Max, *Num, *MIN, *MAX, *NUM;          /* interior range; range with the PML shells      */
+	float *lo, *hi, *size, *LO, *HI;                 /* interior extent; extent with the shells        */
+	int min_sur, max_sur;
+	float want_lo, want_hi;
+	int (*to_index)(world, float);
+	float (*to_coord)(world, float);
+} axis_slots;
+
+/* index ranges and coordinate extents of one axis.  An axis with no extent given (0, 0) collapses to
+ * a 3-cell strip (2 with a mirror); a mirrored axis starts at index 0 and its extent is +-max */
+static void lay_out_axis(world W, axis_slots A, int shell)
+{
+	const int given = A.want_lo || A.want_hi, mirror = A.min_sur==SYM;
+	*A.Min = mirror ? 0 : given ? A.to_index(W, A.want_lo) : -1;
+	*A.Max = given ? A.to_index(W, A.want_hi) : 1;
+	*A.Num = 1 - *A.Min + *A.Max;
+	*A.MIN = *A.Min - (A.min_sur==PML ? shell : 0);
+	*A.MAX = *A.Max + (A.max_sur==PML ? shell : 0);
+	*A.NUM = 1 - *A.MIN + *A.MAX;
+
+	*A.hi = A.to_coord(W, *A.Max);
+	*A.lo = mirror ? -*A.hi : A.to_coord(W, *A.Min);
+	*A.size = *A.hi - *A.lo;
+	*A.HI = A.to_coord(W, *A.MAX);
+	*A.LO = mirror ? -*A.HI : A.to_coord(W, *A.MIN);
 }
 
 /* ---- index ranges, boundary types, Bloch phases (reference world.c:192-258) ---------------------- */
@@ -201,28 +236,13 @@ static world new_world(res R, dom D, sur S)
 	W->yMaxSur = S.y.MinSur!=BBC && S.y.MaxSur ? S.y.MaxSur : S.y.MinSur ? S.y.MinSur : S.x.MinSur;
 	W->zMaxSur = S.z.MinSur!=BBC && S.z.MaxSur ? S.z.MaxSur : S.z.MinSur ? S.z.MinSur : S.x.MinSur;
 
-	/* interior index range; an axis with Min==Max==0 collapses to a 3-cell (2 with SYM) strip */
-	W->iMin = W->xMinSur==SYM ? 0 : D.x.Min || D.x.Max ? W->xtoi(W, D.x.Min) : -1;
-	W->jMin = W->yMinSur==SYM ? 0 : D.y.Min || D.y.Max ? W->ytoj(W, D.y.Min) : -1;
-	W->kMin = W->zMinSur==SYM ? 0 : D.z.Min || D.z.Max ? W->ztok(W, D.z.Min) : -1;
-	W->iMax = D.x.Min || D.x.Max ? W->xtoi(W, D.x.Max) : 1, W->iNum = 1-W->iMin+W->iMax;
-	W->jMax = D.y.Min || D.y.Max ? W->ytoj(W, D.y.Max) : 1, W->jNum = 1-W->jMin+W->jMax;
-	W->kMax = D.z.Min || D.z.Max ? W->ztok(W, D.z.Max) : 1, W->kNum = 1-W->kMin+W->kMax;
-
-	/* range including the PML shells (Num+1 cells per PML face) */
-	W->iMIN = W->iMin-(W->xMinSur==PML ? S.pml.Num+1 : 0);
-	W->jMIN = W->jMin-(W->yMinSur==PML ? S.pml.Num+1 : 0);
-	W->kMIN = W->kMin-(W->zMinSur==PML ? S.pml.Num+1 : 0);
-	W->iMAX = W->iMax+(W->xMaxSur==PML ? S.pml.Num+1 : 0), W->iNUM = 1-W->iMIN+W->iMAX;
-	W->jMAX = W->jMax+(W->yMaxSur==PML ? S.pml.Num+1 : 0), W->jNUM = 1-W->jMIN+W->jMAX;
-	W->kMAX = W->kMax+(W->zMaxSur==PML ? S.pml.Num+1 : 0), W->kNUM = 1-W->kMIN+W->kMAX;
-
-	W->xMax = W->itox(W, W->iMax), W->xMin = W->xMinSur==SYM ? -W->xMax : W->itox(W, W->iMin), W->xSize = W->xMax - W->xMin;
-	W->yMax = W->jtoy(W, W->jMax), W->yMin = W->yMinSur==SYM ? -W->yMax : W->jtoy(W, W->jMin), W->ySize = W->yMax - W->yMin;
-	W->zMax = W->ktoz(W, W->kMax), W->zMin = W->zMinSur==SYM ? -W->zMax : W->ktoz(W, W->kMin), W->zSize = W->zMax - W->zMin;
-	W->xMAX = W->itox(W, W->iMAX), W->xMIN = W->xMinSur==SYM ? -W->xMAX : W->itox(W, W->iMIN);
-	W->yMAX = W->jtoy(W, W->jMAX), W->yMIN = W->yMinSur==SYM ? -W->yMAX : W->jtoy(W, W->jMIN);
-	W->zMAX = W->ktoz(W, W->kMAX), W->zMIN = W->zMinSur==SYM ? -W->zMAX : W->ktoz(W, W->kMIN);
+	const int shell = S.pml.Num+1;            /* cells per PML face */
+	const axis_slots ax[3] = {
+		{ &W->iMin, &W->iMax, &W->iNum, &W->iMIN, &W->iMAX, &W->iNUM, &W->xMin, &W->xMax, &W->xSize, &W->xMIN, &W->xMAX, W->xMinSur, W->xMaxSur, D.x.Min, D.x.Max, W->xtoi, W->itox },
+		{ &W->jMin, &W->jMax, &W->jNum, &W->jMIN, &W->jMAX, &W->jNUM, &W->yMin, &W->yMax, &W->ySize, &W->yMIN, &W->yMAX, W->yMinSur, W->yMaxSur, D.y.Min, D.y.Max, W->ytoj, W->jtoy },
+		{ &W->kMin, &W->kMax, &W->kNum, &W->kMIN, &W->kMAX, &W->kNUM, &W->zMin, &W->zMax, &W->zSize, &W->zMIN, &W->zMAX, W->zMinSur, W->zMaxSur, D.z.Min, D.z.Max, W->ztok, W->ktoz },
+	};
+	for (int a=0; a<3; a++) lay_out_axis(W, ax[a], shell);
 
 	/* phase factors of the boundary copies: Bloch axes rotate by 2 pi L / period; symmetric
 	 * axes start at 0 and get their parity (+-1) from the first source; the rest copy with 1 */
