@@ -29,6 +29,7 @@ int main(void)
 			sliceSnap(W, EE, YZ, 0, txt, "/yz-EE-%d", n);
 			sliceSnap(W, Ez, Line, 0, txt, "/line-Ez-%d", n);
 			sliceSnap(W, LogEE, Vol, 0, h5, "/vol-LogEE-%d", n);
+			sliceSnap(W, RI, XZ, txt, "/xz-RI-%d", n);          /* structure functions take no frame count */
 		}
 	}
 	return 0;

@@ -109,7 +109,7 @@ def test_graded_grid_slices_are_resampled_like_the_reference(tmp_path):
         assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
         out = d / "graded_slices.out"
         files[tag] = {f: (out / f).read_bytes() for f in sorted(os.listdir(out))}
-    assert len(files["ref"]) == 10 and sorted(files["ref"]) == sorted(files["mine"])
+    assert len(files["ref"]) == 12 and sorted(files["ref"]) == sorted(files["mine"])
     xy = np.loadtxt(str(tmp_path / "ref" / "graded_slices.out" / "xy-Ex-120.txt"))
     assert xy.shape == (35, 31) and np.abs(xy).max() > 0          # the raster, not the 600/40 x 500/30 grid
     for f, ref in files["ref"].items():
