@@ -26,7 +26,7 @@ if [ -f "$ROOT/oracle/liboracle_alis.so" ]; then
 	$CC -shared -fopenmp -o "$ROOT/tests/bin/libalis_oracle.so" $OBJS -L"$ROOT/oracle" -loracle_alis -Wl,-rpath,'$ORIGIN/../../oracle' -lm
 fi
 HARNESS=$ROOT/oracle/harness
-for h in stepdump bench_cube monitors putobjects_bench api_misc; do
+for h in stepdump bench_cube monitors putobjects_bench api_misc graded_slices; do
 	[ -f "$HARNESS/$h.c" ] || continue
 	if [ -f "$HERE/libalis.so" ]; then
 		$CC -std=c99 -O2 -fopenmp -w -DHARNESS_MODE_MINE -I"$ROOT/include" -I"$HARNESS" "$HARNESS/$h.c" -L"$HERE" -lalis -Wl,-rpath,'$ORIGIN/../../alis_b200' -lm -o "$ROOT/tests/bin/${h}_mine_cuda"

@@ -38,6 +38,7 @@ gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/bench_cube.c" "$OUT/libalis_ref
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/monitors.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/monitors_ref"
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/api_misc.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/api_misc_ref"
 gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/putobjects_bench.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/putobjects_bench_ref"
+gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/graded_slices.c" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/graded_slices_ref"
 # the example drivers (ours, examples/*.c) linked against the reference: the CPU twins used for
 # output and wall-time comparison on the GPU box
 for ex in "$HERE"/../examples/*.c; do

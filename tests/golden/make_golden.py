@@ -54,3 +54,10 @@ with tempfile.TemporaryDirectory() as tmp:
     print("api_misc", len(vals), "values")
 with open(os.path.join(helpers.GOLDEN, "api_misc_values.json"), "w") as f:
     json.dump(vals, f, indent=1)
+
+# slices of a graded grid resampled onto the uniform raster (oracle/harness/graded_slices.c): sha256 per file
+with tempfile.TemporaryDirectory() as tmp:
+    files = helpers.run_graded_slices("graded_slices_ref", tmp)
+    print("graded_slices", len(files), "files")
+with open(os.path.join(helpers.GOLDEN, "graded_slices.json"), "w") as f:
+    json.dump(files, f, indent=1)

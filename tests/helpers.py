@@ -74,6 +74,21 @@ def run_api_misc(binary, cwd):
     return parse_tag_values(r.stdout)
 
 
+def run_graded_slices(binary, cwd):
+    """oracle/harness/graded_slices.c: {file name: sha256} of the slice files it writes under cwd"""
+    exe = os.path.join(REF_BIN if binary.endswith("_ref") else TEST_BIN, binary)
+    r = subprocess.run([exe], cwd=cwd, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    out = os.path.join(cwd, "graded_slices.out")
+    return {f: sha256_file(os.path.join(out, f)) for f in sorted(os.listdir(out))}
+
+
+def golden_graded_slices():
+    with open(os.path.join(GOLDEN, "graded_slices.json")) as f:
+        return json.load(f)
+
+
 def golden_api_misc():
     with open(os.path.join(GOLDEN, "api_misc_values.json")) as f:
         return json.load(f)

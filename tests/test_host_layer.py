@@ -64,3 +64,12 @@ def test_remaining_public_api_equals_reference(tmp_path):
     unmodified reference prints it"""
     got, want = helpers.run_api_misc("api_misc_mine_oracle", str(tmp_path)), helpers.golden_api_misc()
     assert len(want) >= 28 and got == want, [(g, w) for g, w in zip(got, want) if g != w][:5]
+
+
+def test_graded_grid_slices_match_reference_golden(tmp_path):
+    """oracle/harness/graded_slices.c with the host layer on the oracle engine: every slice file (1-D, 2-D
+    text incl. the refractive-index map, 3-D HDF5) of a world graded along x, y, z has the sha256 of the
+    file the unmodified reference wrote (tests/golden/graded_slices.json, made by make_golden.py)"""
+    want = helpers.golden_graded_slices()
+    assert len(want) == 12
+    assert helpers.run_graded_slices("graded_slices_mine_oracle", str(tmp_path)) == want

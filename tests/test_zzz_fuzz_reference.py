@@ -145,3 +145,10 @@ def test_remaining_public_api_on_gpu(tmp_path):
     the device to 5e-6)"""
     got, want = helpers.run_api_misc("api_misc_mine_cuda", str(tmp_path)), helpers.golden_api_misc()
     assert not helpers.monitor_mismatches(got, want, device_flux=True)
+
+
+@pytest.mark.gpu
+def test_graded_grid_slices_on_gpu(tmp_path):
+    """slices of a world graded along x, y, z, fields from the CUDA engine, resampled onto the uniform
+    raster by the host layer: files identical (sha256) to the unmodified reference's"""
+    assert helpers.run_graded_slices("graded_slices_mine_cuda", str(tmp_path)) == helpers.golden_graded_slices()
