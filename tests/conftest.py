@@ -23,3 +23,18 @@ def engine_lib():
     """The CUDA engine -- fails (does not skip) when the extension is missing."""
     from alis_b200 import capi
     return capi.load_engine()
+
+
+# Golden configurations added after this round's last GPU call: their GPU tests have only run on the CPU
+# engines so far.  The round-end run uses `-x`, so they go to the end of the session -- a surprise there
+# must not hide the established suite.  (Remove a name once a GPU log under profiles/ shows it green.)
+NOT_YET_ON_GPU = ("guided_y", "guided_xz", "shape_zoo", "focused_beam", "focused_tfsf")
+
+
+def pytest_collection_modifyitems(config, items):
+    def late(item):
+        if item.get_closest_marker("gpu") is None or "[" not in item.nodeid:
+            return False
+        params = item.nodeid[item.nodeid.index("[") + 1:-1].split("-")
+        return any(p in NOT_YET_ON_GPU for p in params)
+    items[:] = [i for i in items if not late(i)] + [i for i in items if late(i)]
