@@ -119,7 +119,7 @@ struct alisb_phaser {
 	int box[6]; int mask, nfreq;
 	Box face[6]; size_t cells[6];
 	float2 *acc[6];
-	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev; bool ev_pending;
+	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev[8]; bool ev_pending[8]; int ring, slot;   /* pinned staging: `ring` slots of nfreq factors per set */
 	SurfJob *d_jobs; float2 *d_w; double *d_sums; size_t jobs_cap, w_cap;   /* far-field surface sums (grown on demand) */
 };
 
@@ -1708,7 +1708,14 @@ extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int fa
 	if (nfreq < 1 || !out) return fail(ALISB_EINVAL, "nfreq");
 	DEV(e);
 	alisb_phaser *p = new alisb_phaser();
-	p->e = e; memcpy(p->box, box, sizeof p->box); p->mask = face_mask; p->nfreq = nfreq; p->ev_pending = false;
+	p->e = e; memcpy(p->box, box, sizeof p->box); p->mask = face_mask; p->nfreq = nfreq;
+	/* staging slots for the per-step phase factors.  1 (default): every call waits for the previous call's copy,
+	 * i.e. for the previous step -- host and device alternate.  ALISB_PHASER_RING=2..8 (opt-in until measured on
+	 * a GPU): the host runs up to that many steps ahead */
+	const char *re = getenv("ALISB_PHASER_RING");
+	p->ring = re ? atoi(re) : 1; if (p->ring < 1) p->ring = 1; if (p->ring > 8) p->ring = 8;
+	p->slot = 0;
+	for (int r=0; r<8; r++) p->ev_pending[r] = false;
 	p->d_jobs = 0; p->d_w = 0; p->d_sums = 0; p->jobs_cap = 0; p->w_cap = 0;
 	for (int f=0; f<6; f++) {
 		p->acc[f] = 0; p->cells[f] = 0;
@@ -1721,9 +1728,9 @@ extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int fa
 	}
 	for (int k=0; k<2; k++) {
 		float *d = 0; TRY(dalloc(&d, 2*(size_t)nfreq)); p->dexp[k] = (float2*)d;
-		CU(cudaMallocHost((void**)&p->hexp[k], 2*(size_t)nfreq*sizeof(float)));
+		CU(cudaMallocHost((void**)&p->hexp[k], 2*(size_t)nfreq*sizeof(float)*p->ring));
 	}
-	CU(cudaEventCreateWithFlags(&p->ev, cudaEventDisableTiming));
+	for (int r=0; r<p->ring; r++) CU(cudaEventCreateWithFlags(&p->ev[r], cudaEventDisableTiming));
 	*out = p;
 	return ALISB_OK;
 }
@@ -1736,7 +1743,7 @@ extern "C" void alisb_phaser_destroy(alisb_phaser *p)
 	for (int f=0; f<6; f++) cudaFree(p->acc[f]);
 	for (int k=0; k<2; k++) { cudaFree(p->dexp[k]); cudaFreeHost(p->hexp[k]); }
 	cudaFree(p->d_jobs); cudaFree(p->d_w); cudaFree(p->d_sums);
-	cudaEventDestroy(p->ev);
+	for (int r=0; r<p->ring; r++) cudaEventDestroy(p->ev[r]);
 	delete p;
 }
 
@@ -1745,11 +1752,14 @@ extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const
 	alisb_engine *e = p->e;
 	DEV(e);
 	SETTLE(e);
-	if (p->ev_pending) CU(cudaEventSynchronize(p->ev));       /* pinned staging buffers free again */
-	memcpy(p->hexp[0], expE, 2*(size_t)p->nfreq*sizeof(float));
-	memcpy(p->hexp[1], expH, 2*(size_t)p->nfreq*sizeof(float));
-	for (int k=0; k<2; k++) CU(cudaMemcpyAsync(p->dexp[k], p->hexp[k], 2*(size_t)p->nfreq*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-	CU(cudaEventRecord(p->ev, e->stream)); p->ev_pending = true;
+	const int slot = p->slot;
+	p->slot = (slot+1) % p->ring;
+	if (p->ev_pending[slot]) CU(cudaEventSynchronize(p->ev[slot]));       /* this slot's last copy has left the pinned buffer */
+	float2 *stage[2] = { p->hexp[0] + (size_t)slot*p->nfreq, p->hexp[1] + (size_t)slot*p->nfreq };
+	memcpy(stage[0], expE, 2*(size_t)p->nfreq*sizeof(float));
+	memcpy(stage[1], expH, 2*(size_t)p->nfreq*sizeof(float));
+	for (int k=0; k<2; k++) CU(cudaMemcpyAsync(p->dexp[k], stage[k], 2*(size_t)p->nfreq*sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	CU(cudaEventRecord(p->ev[slot], e->stream)); p->ev_pending[slot] = true;
 	for (int f=0; f<6; f++) if (p->acc[f]) {
 		const int ax = f/2, c1 = (ax+1)%3, c2 = (ax+2)%3;
 		const size_t hstep = ax == 0 ? 1 : ax == 1 ? (size_t)e->pitch : e->plane;

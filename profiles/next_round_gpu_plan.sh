@@ -18,9 +18,15 @@ time)       # host-call timings of the monitor / far-field / geometry entry poin
 	python profiles/monitors_probe.py 512 > gpurun_out/monitors_probe_512.json 2>&1
 	bash profiles/geometry_r01.sh
 	python -m pytest tests/test_gpu_examples.py -m gpu -q -s 2>&1 | grep -E "EXAMPLE_TIMING|passed|failed" > gpurun_out/examples.log
-	# Dipole_Band's 6400-step loop: default phaser kernel against one thread per (cell, frequency)
-	mkdir -p /tmp/db0 /tmp/db1; export LD_LIBRARY_PATH=$PWD/alis_b200:$LD_LIBRARY_PATH
-	for par in 0 1; do ( cd /tmp/db$par; cp $OLDPWD/tests/bin/dipole_band_cuda .; s=$(date +%s.%N); ALISB_PHASER_PAR=$par ALIS_FF_TIMING=1 ./dipole_band_cuda > log.txt 2>&1; echo "dipole_band ALISB_PHASER_PAR=$par $(python -c "import time; print(round(time.time()-$s,2))") s" ) >> gpurun_out/examples.log; done
+	# Dipole_Band's 6400-step loop: default phasor path against one thread per (cell, frequency) and/or a ring of
+	# 8 pinned staging slots (default: each updatePhaser waits for the previous step's copy, host and device alternate)
+	export LD_LIBRARY_PATH=$PWD/alis_b200:$LD_LIBRARY_PATH; BIN=$PWD/tests/bin/dipole_band_cuda; LOG=$PWD/gpurun_out/examples.log
+	for par in 0 1; do for ring in 1 8; do
+		d=/tmp/db_${par}_${ring}; mkdir -p $d
+		( cd $d; cp $BIN .; s=$(date +%s.%N); ALISB_PHASER_PAR=$par ALISB_PHASER_RING=$ring ALIS_FF_TIMING=1 ./dipole_band_cuda > log.txt 2>&1
+		  echo "dipole_band ALISB_PHASER_PAR=$par ALISB_PHASER_RING=$ring $(python -c "import time; print(round(time.time()-$s,2))") s" >> $LOG )
+	done; done
+	for f in /tmp/db_1_8/dipole_band_cuda.out/*.txt; do cmp -s $f /tmp/db_0_1/dipole_band_cuda.out/$(basename $f) || echo "DIFFERS $(basename $f)" >> $LOG; done
 	tail -5 gpurun_out/monitors_probe_512.json gpurun_out/examples.log ;;
 ncu)        # one full capture per new kernel (first launch each), DRAM bytes and durations
 	ncu --set full --clock-control none --import-source on --launch-count 1 \

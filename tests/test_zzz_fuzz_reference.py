@@ -96,12 +96,17 @@ def test_random_world_monitors_match_reference_gpu(seed):
 
 
 @pytest.mark.gpu
-def test_parallel_phaser_kernel_bit_exact(monkeypatch):
-    """ALISB_PHASER_PAR=1 (one thread per face cell and frequency; opt-in until timed): accumulators
-    identical to the oracle's, i.e. to the default kernel's"""
+@pytest.mark.parametrize("knobs", [{"ALISB_PHASER_PAR": "1"}, {"ALISB_PHASER_RING": "4"}, {"ALISB_PHASER_PAR": "1", "ALISB_PHASER_RING": "8"}],
+                         ids=["par", "ring4", "par-ring8"])
+def test_parallel_phaser_kernel_bit_exact(monkeypatch, knobs):
+    """the opt-in phasor knobs (until timed on a GPU): ALISB_PHASER_PAR=1, one thread per face cell and
+    frequency; ALISB_PHASER_RING=n, n pinned staging slots for the phase factors so that the host runs
+    ahead of the device (8 accumulations wrap a ring of 4 twice).  Accumulators identical to the
+    oracle's, i.e. to the default path's"""
     import numpy as np
     from alis_b200 import capi, synthetic
-    monkeypatch.setenv("ALISB_PHASER_PAR", "1")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
     eng, ora = capi.load_engine(), capi.load_oracle()
     w = synthetic.BoxWorld(48, 44, 40, num=6)
     g, o = w.make_engine(eng), w.make_engine(ora)
