@@ -45,4 +45,19 @@ for ex in "$ROOT"/examples/*.c; do
 		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/${b}_oracle"
 	fi
 done
+# the reference's OWN example drivers (reference examples/*.c, all 16, unmodified), compiled where they lie
+# against include/alis.h and linked with the drop-in library: tests/bin/refex_<Name>_cuda run on the GPU box
+# next to oracle/_ref/bin/refex_<Name>_ref (tests/test_gpu_refex.py).  Only where the reference tree is mounted;
+# the binaries travel to the GPU box, no source is copied.
+REF=${ALIS_REFERENCE:-/root/reference}
+for ex in "$REF"/examples/*.c; do
+	[ -f "$ex" ] || continue
+	b=$(basename "$ex" .c)
+	if [ -f "$HERE/libalis.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$HERE" -lalis -Wl,-rpath,'$ORIGIN/../../alis_b200' -lm -o "$ROOT/tests/bin/refex_${b}_cuda"
+	fi
+	if [ -f "$ROOT/tests/bin/libalis_oracle.so" ]; then
+		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/refex_${b}_oracle"
+	fi
+done
 echo "build_host: ok"

@@ -86,6 +86,8 @@ struct alisb_engine {
 	float *psi[2][2][3][2][2]; size_t psi_elems[2][3][2];
 	int xbase[2][2], xpitch[2][2];     /* [set][side]                                     */
 	std::vector<DispObj*> obj;
+	AdeTable *d_ade[2]; uint64_t ade_cfg;   /* device copies of the in-kernel object table per complex set; built for ade_cfg */
+	int tune_ade;                       /* dispersive objects handled inside the volume kernels (ALISB_ADE_FUSE, default 1) */
 	std::vector<SrcObj*> src[2];
 	std::vector<TfsfObj*> tf;
 	std::vector<alisb_copy> copies[2];
@@ -93,6 +95,7 @@ struct alisb_engine {
 	uint64_t step; float t, tE, tH;
 	uint64_t launches, fused_launches;
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
+	int sm_count, multi_resident[2];   /* SMs; resident CTAs of the two merged PML-shell launch classes */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
 	int tune_frows;                    /* rows per CTA of the fused kernel (8 or 16)          */
 	int tune_fchunk;                   /* planes per z-chunk of the fused kernel              */
@@ -119,7 +122,6 @@ struct alisb_phaser {
 	int box[6]; int mask, nfreq;
 	Box face[6]; size_t cells[6];
 	float2 *acc[6];
-	float2 *dexp[2]; float2 *hexp[2]; cudaEvent_t ev[8]; bool ev_pending[8]; int ring, slot;   /* pinned staging: `ring` slots of nfreq factors per set */
 	SurfJob *d_jobs; float2 *d_w; double *d_sums; size_t jobs_cap, w_cap;   /* far-field surface sums (grown on demand) */
 };
 
@@ -127,8 +129,9 @@ struct alisb_phaser {
  * state calls SETTLE, every one that changes fields or the configuration calls UNFUSE (the H' already
  * written for the fused box would be stale) */
 static int launch_pending(alisb_engine *e, bool fused);
-#define SETTLE(e) TRY(launch_pending((e), false))
-#define UNFUSE(e) do { TRY(launch_pending((e), false)); (e)->h_fused = false; } while (0)
+static bool ade_in_kernel(const alisb_engine *e);
+#define SETTLE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); } while (0)
+#define UNFUSE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); (e)->h_fused = false; } while (0)
 
 extern "C" int alisb_abi_version(void) { return ALISB_ABI_VERSION; }
 extern "C" const char *alisb_last_error(void) { return g_err; }
@@ -189,6 +192,8 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	for (int a=0; a<2; a++) for (int b=0; b<3; b++) { e->graph[a][b].exec = 0; e->graph[a][b].graph = 0; e->graph[a][b].version = 0; e->graph[a][b].nkernels = 0; }
 	{ const char *gs = getenv("ALISB_GRAPH"); e->graph_ok = gs ? atoi(gs) != 0 : true; }
 	e->srcv_cap = 0; e->srcv_slot = 0;
+	e->d_ade[0] = e->d_ade[1] = 0; e->ade_cfg = 0;
+	{ const char *as = getenv("ALISB_ADE_FUSE"); e->tune_ade = as ? atoi(as) : 1; }
 	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
@@ -221,7 +226,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		}
 	}
 	int nb = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7,32>, 256, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7,32,false>, 256, 0));
 	{
 		const char *s;
 		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 100000; e->tune_minchunk = 8;   /* measured: profiles/sweep2_r01, sweep3_r01 */
@@ -243,6 +248,19 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	}
 	cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, g->device));
 	e->resident_ctas = std::max(1, nb)*prop.multiProcessorCount;
+	e->sm_count = prop.multiProcessorCount;
+	/* the > 48 KB dynamic shared memory opt-in is a per-device function attribute: set it for THIS engine's
+	 * device (cheap; engines on several devices in one process each do it) */
+	CU(cudaFuncSetAttribute(yee_fused<8,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,false>)));
+	CU(cudaFuncSetAttribute(yee_fused<8,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,true>)));
+	CU(cudaFuncSetAttribute(yee_fused<16,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,false>)));
+	CU(cudaFuncSetAttribute(yee_fused<16,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,true>)));
+	for (int cls=0; cls<2; cls++) {
+		int per_sm = 0;
+		if (cls == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yee_multi<1,false,0,false>, 256, 0));
+		else          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yee_multi<1,false,1,false>, 256, 0));
+		e->multi_resident[cls] = std::max(1, per_sm)*prop.multiProcessorCount;
+	}
 	*out = e;
 	return ALISB_OK;
 }
@@ -297,7 +315,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
-	cudaFree(e->scratch);
+	cudaFree(e->scratch); cudaFree(e->d_ade[0]); cudaFree(e->d_ade[1]);
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
 	for (int r=0; r<SRC_RING; r++) { if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]); cudaFree(e->srcv_d[r]); if (e->srcv_ev[r]) cudaEventDestroy(e->srcv_ev[r]); }
 	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
@@ -387,12 +405,18 @@ extern "C" int alisb_add_dispersive(alisb_engine *e, const alisb_dispersive *d)
 	int32_t u[6] = {std::max(d->box[0],1), std::min(d->box[1],e->nx), std::max(d->box[2],1), std::min(d->box[3],e->ny), std::max(d->box[4],1), std::min(d->box[5],e->nz)};
 	o->upd = mkbox(u);
 	o->cnt = bcount(o->full);
-	for (int c=0; c<3; c++) {
-		TRY(upload_box(&o->fill[c], d->fill[c], o->full));
-		for (int m=0; m<=e->g.complex_field; m++) for (int p=0; p<d->nk; p++) {
-			TRY(dalloc(&o->J[m][p][c], o->cnt));
-			if (p >= d->nj) TRY(dalloc(&o->K[m][p][c], o->cnt));
+	int rc = ALISB_OK;
+	for (int c=0; c<3 && rc == ALISB_OK; c++) {
+		rc = upload_box(&o->fill[c], d->fill[c], o->full);
+		for (int m=0; m<=e->g.complex_field && rc == ALISB_OK; m++) for (int p=0; p<d->nk && rc == ALISB_OK; p++) {
+			rc = dalloc(&o->J[m][p][c], o->cnt);
+			if (rc == ALISB_OK && p >= d->nj) rc = dalloc(&o->K[m][p][c], o->cnt);
 		}
+	}
+	if (rc != ALISB_OK) {                                    /* release the partially built object */
+		for (int c=0; c<3; c++) { cudaFree(o->fill[c]); for (int m=0; m<2; m++) for (int p=0; p<ALISB_MAXPOLES; p++) { cudaFree(o->J[m][p][c]); cudaFree(o->K[m][p][c]); } }
+		delete o;
+		return rc;
 	}
 	e->obj.push_back(o);
 	return ALISB_OK;
@@ -407,19 +431,24 @@ extern "C" int alisb_add_source(alisb_engine *e, const alisb_source *s)
 	SrcObj *o = new SrcObj();
 	o->d = *s; o->B = mkbox(s->box); o->cnt = bcount(o->B); o->dAmp = 0; o->slot = 0;
 	for (int r=0; r<SRC_RING; r++) { o->hvals[r] = 0; o->dvals[r] = 0; o->ev[r] = 0; }
-	if (s->Amplitude) {
-		o->hAmp.resize(o->cnt); to_xfast(s->Amplitude, o->hAmp.data(), o->B);
-		TRY(dalloc(&o->dAmp, o->cnt));
-		CU(cudaMemcpy(o->dAmp, o->hAmp.data(), o->cnt*sizeof(float), cudaMemcpyHostToDevice));
-	}
-	if (s->Phase) {
-		o->hPha.resize(o->cnt); to_xfast(s->Phase, o->hPha.data(), o->B);
-		for (int r=0; r<SRC_RING; r++) {
-			CU(cudaMallocHost((void**)&o->hvals[r], o->cnt*sizeof(float)));
-			TRY(dalloc(&o->dvals[r], o->cnt));
-			CU(cudaEventCreateWithFlags(&o->ev[r], cudaEventDisableTiming));
+	auto build = [&]() -> int {
+		if (s->Amplitude) {
+			o->hAmp.resize(o->cnt); to_xfast(s->Amplitude, o->hAmp.data(), o->B);
+			TRY(dalloc(&o->dAmp, o->cnt));
+			CU(cudaMemcpy(o->dAmp, o->hAmp.data(), o->cnt*sizeof(float), cudaMemcpyHostToDevice));
 		}
-	}
+		if (s->Phase) {
+			o->hPha.resize(o->cnt); to_xfast(s->Phase, o->hPha.data(), o->B);
+			for (int r=0; r<SRC_RING; r++) {
+				CU(cudaMallocHost((void**)&o->hvals[r], o->cnt*sizeof(float)));
+				TRY(dalloc(&o->dvals[r], o->cnt));
+				CU(cudaEventCreateWithFlags(&o->ev[r], cudaEventDisableTiming));
+			}
+		}
+		return ALISB_OK;
+	};
+	const int rc = build();
+	if (rc != ALISB_OK) { free_src(o); return rc; }         /* release the partially built source */
 	o->d.Amplitude = 0; o->d.Phase = 0;
 	e->src[s->set].push_back(o);
 	return ALISB_OK;
@@ -448,41 +477,43 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 }
 
 /* ---- one pass ------------------------------------------------------------------------- */
-template <int S, bool EPS>
+template <int S, bool EPS, bool ADE>
 static void launch_volume_te(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block)
 {
 	if (r.narrow) {                   /* 32-cell wide x strips: 8 lanes along x, 4 rows per warp */
-		if (r.pm == 1) yee_volume<S,EPS,1,8><<<grid,block,0,st>>>(p, r);
-		else           yee_volume<S,EPS,5,8><<<grid,block,0,st>>>(p, r);
+		if (r.pm == 1) yee_volume<S,EPS,1,8,ADE><<<grid,block,0,st>>>(p, r);
+		else           yee_volume<S,EPS,5,8,ADE><<<grid,block,0,st>>>(p, r);
 		return;
 	}
 	switch (r.pm) {
-	case 0: yee_volume<S,EPS,0,32><<<grid,block,0,st>>>(p, r); break;
-	case 1: yee_volume<S,EPS,1,32><<<grid,block,0,st>>>(p, r); break;
-	case 2: yee_volume<S,EPS,2,32><<<grid,block,0,st>>>(p, r); break;
-	case 3: yee_volume<S,EPS,3,32><<<grid,block,0,st>>>(p, r); break;
-	case 4: yee_volume<S,EPS,4,32><<<grid,block,0,st>>>(p, r); break;
-	case 5: yee_volume<S,EPS,5,32><<<grid,block,0,st>>>(p, r); break;
-	case 6: yee_volume<S,EPS,6,32><<<grid,block,0,st>>>(p, r); break;
-	default: yee_volume<S,EPS,7,32><<<grid,block,0,st>>>(p, r); break;
+	case 0: yee_volume<S,EPS,0,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 1: yee_volume<S,EPS,1,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 2: yee_volume<S,EPS,2,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 3: yee_volume<S,EPS,3,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 4: yee_volume<S,EPS,4,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 5: yee_volume<S,EPS,5,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 6: yee_volume<S,EPS,6,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	default: yee_volume<S,EPS,7,32,ADE><<<grid,block,0,st>>>(p, r); break;
 	}
 }
+/* dispersive objects sit in material worlds: the ADE variants exist with the inverse-permittivity arrays only */
 template <int S>
-static void launch_volume_t(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, bool eps)
+static void launch_volume_t(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, bool eps, bool ade)
 {
-	if (eps) launch_volume_te<S,true>(st, p, r, grid, block);
-	else     launch_volume_te<S,false>(st, p, r, grid, block);
+	if (ade)      launch_volume_te<S,(S > 0),true>(st, p, r, grid, block);
+	else if (eps) launch_volume_te<S,(S > 0),false>(st, p, r, grid, block);
+	else          launch_volume_te<S,false,false>(st, p, r, grid, block);
 }
-template <int S, bool EPS>
+template <int S, bool EPS, bool ADE>
 static void launch_multi_te(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls)
 {
-	if (cls == 0) yee_multi<S,EPS,0><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
-	else          yee_multi<S,EPS,1><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
+	if (cls == 0) yee_multi<S,EPS,0,ADE><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
+	else          yee_multi<S,EPS,1,ADE><<<nctas, dim3(32, 8, 1), 0, st>>>(mp);
 }
-static void launch_multi(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls, int set, bool eps)
+static void launch_multi(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls, int set, bool eps, bool ade)
 {
-	if (set == ALISB_SET_E) { if (eps) launch_multi_te<1,true>(st, mp, nctas, cls); else launch_multi_te<1,false>(st, mp, nctas, cls); }
-	else                    launch_multi_te<-1,false>(st, mp, nctas, cls);
+	if (set == ALISB_SET_E) { if (ade) launch_multi_te<1,true,true>(st, mp, nctas, cls); else if (eps) launch_multi_te<1,true,false>(st, mp, nctas, cls); else launch_multi_te<1,false,false>(st, mp, nctas, cls); }
+	else                    { if (ade) launch_multi_te<-1,false,true>(st, mp, nctas, cls); else launch_multi_te<-1,false,false>(st, mp, nctas, cls); }
 }
 
 /* ---- fused E+H stepping (temporal blocking) ------------------------------------------------------
@@ -530,6 +561,9 @@ static void fuse_eval(alisb_engine *e)
 	auto mark = [&](int c0, int c1) { for (int c=std::max(c0, 0); c<=std::min(c1 + 1, e->nz + 1); c++) dirty[c] = 1; };
 	for (SrcObj *so : e->src[ALISB_SET_E]) mark(so->d.box[4], so->d.box[5]);
 	for (TfsfObj *t : e->tf) for (const alisb_strip &st : t->sE) mark(st.box[4], st.box[5]);
+	/* dispersive objects handled inside the two-pass kernels: their planes (and the plane above, whose H'
+	 * the fused kernel would form from an E' recomputed without the currents) stay two-pass */
+	if (ade_in_kernel(e)) for (DispObj *o : e->obj) mark(o->upd.c0, o->upd.c0 + o->upd.nc - 1);
 	long fused_planes = 0;
 	for (int c=lo[2]; c<=hi[2]; ) {
 		if (dirty[c]) { c++; continue; }
@@ -654,10 +688,47 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 		return (double)(p.a1-p.a0+1)*(p.b1-p.b0+1)*(p.c1-p.c0+1) > (double)(q.a1-q.a0+1)*(q.b1-q.b0+1)*(q.c1-q.c0+1); });
 }
 
+/* dispersive objects are handled inside the volume kernels (ADE variants of yee_volume / yee_multi) when
+ * the world has its material arrays and at most ALISB_MAXADE objects; otherwise the three box kernels
+ * ade_loss / ade_subtract / ade_currents run around the volume launches */
+static bool ade_in_kernel(const alisb_engine *e)
+{
+	return e->tune_ade && !e->obj.empty() && e->obj.size() <= ALISB_MAXADE && e->eps[0] && e->eps[1] && e->eps[2];
+}
+
+static int ade_table(alisb_engine *e)
+{
+	if (e->ade_cfg == e->cfg_version && e->d_ade[0]) return ALISB_OK;
+	for (int m=0; m<=e->g.complex_field; m++) {
+		AdeTable T;
+		memset(&T, 0, sizeof T);
+		T.n = (int)e->obj.size();
+		for (int n=0; n<T.n; n++) {
+			const DispObj *o = e->obj[n];
+			AdeObj &d = T.o[n];
+			for (int c=0; c<3; c++) {
+				d.fill[c] = o->fill[c]; d.a[c] = o->d.a[c];
+				for (int q=0; q<ALISB_MAXPOLES; q++) { d.J[q][c] = o->J[m][q][c]; d.K[q][c] = o->K[m][q][c]; }
+			}
+			memcpy(d.JJ, o->d.JJ, sizeof d.JJ); memcpy(d.JK, o->d.JK, sizeof d.JK); memcpy(d.JE, o->d.JE, sizeof d.JE);
+			memcpy(d.KJ, o->d.KJ, sizeof d.KJ); memcpy(d.KK, o->d.KK, sizeof d.KK); memcpy(d.KE, o->d.KE, sizeof d.KE);
+			d.nj = o->d.nj; d.nk = o->d.nk; d.lossy = (o->d.a[0] || o->d.a[1] || o->d.a[2]) ? 1 : 0;
+			d.full = o->full; d.upd = o->upd;
+		}
+		if (!e->d_ade[m]) CU(cudaMalloc((void**)&e->d_ade[m], sizeof(AdeTable)));
+		CU(cudaStreamSynchronize(e->stream));            /* configuration changes are rare; no pass may still read the old table */
+		CU(cudaMemcpy(e->d_ade[m], &T, sizeof T, cudaMemcpyHostToDevice));
+	}
+	e->ade_cfg = e->cfg_version;
+	return ALISB_OK;
+}
+
 static int launch_volume(alisb_engine *e, int set, int m)
 {
 	VolParams p;
 	memset(&p, 0, sizeof p);
+	const bool ade = ade_in_kernel(e);
+	if (ade) p.ade = e->d_ade[m];
 	for (int c=0; c<3; c++) {
 		p.F[c] = e->F[set][m][c]; p.G[c] = e->F[1-set][m][c];
 		p.Fin[c] = e->dbuf ? e->Fb[set][m][c] : e->F[set][m][c];
@@ -787,15 +858,15 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		nlaunched++;
 		cudaEvent_t e1 = prof_begin(st, sub, cells);
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
-		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, r, grid, block, eps);
-		else                    launch_volume_t<-1>(st, p, r, grid, block, false);
+		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, r, grid, block, eps, ade);
+		else                    launch_volume_t<-1>(st, p, r, grid, block, false, ade);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
 	if (merge) for (int cls=0; cls<2; cls++) if (mp[cls].nreg) {
 		/* z-chunk of a merged launch: tune_minchunk planes when that still gives >= 4 CTAs per resident
 		 * slot over the whole class, fewer planes per chunk on mid-size grids (more, shorter marches) */
-		const double slots = 4.0*148*(cls == 0 ? 3 : 2);
+		const double slots = 4.0*e->multi_resident[cls];
 		const int chunk = (int)std::max(1.0, std::min((double)e->tune_minchunk, floor(mplanes[cls]/slots)));
 		for (int q=0; q<mp[cls].nreg; q++) {
 			VolRegion &r = mp[cls].r[q];
@@ -807,7 +878,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		cudaStream_t st = side_stream(true);
 		nlaunched++;
 		cudaEvent_t e1 = prof_begin(st, -2 - cls, mcells[cls]);
-		launch_multi(st, mp[cls], mcta[cls], cls, set, eps);
+		launch_multi(st, mp[cls], mcta[cls], cls, set, eps, ade);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
@@ -891,9 +962,11 @@ static int prepare_sources(alisb_engine *e, int set, float t)
 	if (nvals) {
 		if (nvals > e->srcv_cap) {
 			CU(cudaStreamSynchronize(e->stream));
+			e->srcv_cap = 0;                                 /* until every slot has been re-allocated */
 			for (int r=0; r<SRC_RING; r++) {
 				if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]);
 				cudaFree(e->srcv_d[r]);
+				e->srcv_h[r] = 0; e->srcv_d[r] = 0;
 				CU(cudaMallocHost((void**)&e->srcv_h[r], nvals*sizeof(float)));
 				TRY(dalloc(&e->srcv_d[r], nvals));
 				if (!e->srcv_ev[r]) CU(cudaEventCreateWithFlags(&e->srcv_ev[r], cudaEventDisableTiming));
@@ -1085,6 +1158,7 @@ static int pass_prepare(alisb_engine *e, int set, int part)
 	}
 	open_pass(e, set);
 	set_filter(e, set, part);
+	if (ade_in_kernel(e)) TRY(ade_table(e));
 	TRY(prepare_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
 	return ALISB_OK;
 }
@@ -1095,11 +1169,11 @@ static int pass_launch(alisb_engine *e, int set, int part)
 	set_filter(e, set, part);
 	for (int m=0; m<=e->g.complex_field; m++) {
 		if (set == ALISB_SET_E) {
-			if (!e->obj.empty()) TRY(ade_pre(e, m));
+			if (!e->obj.empty() && !ade_in_kernel(e)) TRY(ade_pre(e, m));
 			TRY(launch_volume(e, ALISB_SET_E, m));
 		} else {
 			TRY(launch_volume(e, ALISB_SET_H, m));
-			if (!e->obj.empty()) TRY(ade_post(e, m));
+			if (!e->obj.empty() && !ade_in_kernel(e)) TRY(ade_post(e, m));
 		}
 	}
 	TRY(apply_tfsf(e, set, part != ALISB_PART_REST));
@@ -1454,12 +1528,16 @@ extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes,
 	SETTLE(e);
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) if (!e->spacing[s][ax]) return fail(ALISB_ESTATE, "alisb_set_spacing has not been called");
 	if (n > e->flux_cap) {
+		/* the old buffers go first and the capacity only grows once every new one exists: a failed
+		 * allocation leaves an engine with capacity 0 and null pointers, never dangling ones */
 		cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
-		e->flux_cap = std::max(16, n);
-		CU(cudaMalloc((void**)&e->d_planes, sizeof(FluxPlane)*e->flux_cap));
-		CU(cudaMalloc((void**)&e->d_partial, sizeof(double)*2*FLUX_BLOCKS*e->flux_cap));
-		CU(cudaMalloc((void**)&e->d_flux, sizeof(double)*2*e->flux_cap));
-		CU(cudaMallocHost((void**)&e->h_flux, sizeof(double)*2*e->flux_cap + sizeof(FluxPlane)*e->flux_cap));
+		e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
+		const int cap = std::max(16, n);
+		CU(cudaMalloc((void**)&e->d_planes, sizeof(FluxPlane)*cap));
+		CU(cudaMalloc((void**)&e->d_partial, sizeof(double)*2*FLUX_BLOCKS*cap));
+		CU(cudaMalloc((void**)&e->d_flux, sizeof(double)*2*cap));
+		CU(cudaMallocHost((void**)&e->h_flux, sizeof(double)*2*cap + sizeof(FluxPlane)*cap));
+		e->flux_cap = cap;
 	}
 	FluxPlane *hp = (FluxPlane*)(e->h_flux + 2*e->flux_cap);
 	const int N[3] = {e->nx, e->ny, e->nz};
@@ -1709,13 +1787,6 @@ extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int fa
 	DEV(e);
 	alisb_phaser *p = new alisb_phaser();
 	p->e = e; memcpy(p->box, box, sizeof p->box); p->mask = face_mask; p->nfreq = nfreq;
-	/* staging slots for the per-step phase factors.  1 (default): every call waits for the previous call's copy,
-	 * i.e. for the previous step -- host and device alternate.  ALISB_PHASER_RING=2..8 (opt-in until measured on
-	 * a GPU): the host runs up to that many steps ahead */
-	const char *re = getenv("ALISB_PHASER_RING");
-	p->ring = re ? atoi(re) : 1; if (p->ring < 1) p->ring = 1; if (p->ring > 8) p->ring = 8;
-	p->slot = 0;
-	for (int r=0; r<8; r++) p->ev_pending[r] = false;
 	p->d_jobs = 0; p->d_w = 0; p->d_sums = 0; p->jobs_cap = 0; p->w_cap = 0;
 	for (int f=0; f<6; f++) {
 		p->acc[f] = 0; p->cells[f] = 0;
@@ -1726,11 +1797,6 @@ extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int fa
 		p->face[f] = mkbox(fb); p->cells[f] = bcount(p->face[f]);
 		float *a = 0; TRY(dalloc(&a, p->cells[f]*8*(size_t)nfreq)); p->acc[f] = (float2*)a;
 	}
-	for (int k=0; k<2; k++) {
-		float *d = 0; TRY(dalloc(&d, 2*(size_t)nfreq)); p->dexp[k] = (float2*)d;
-		CU(cudaMallocHost((void**)&p->hexp[k], 2*(size_t)nfreq*sizeof(float)*p->ring));
-	}
-	for (int r=0; r<p->ring; r++) CU(cudaEventCreateWithFlags(&p->ev[r], cudaEventDisableTiming));
 	*out = p;
 	return ALISB_OK;
 }
@@ -1741,36 +1807,39 @@ extern "C" void alisb_phaser_destroy(alisb_phaser *p)
 	cudaSetDevice(p->e->g.device);
 	cudaStreamSynchronize(p->e->stream);
 	for (int f=0; f<6; f++) cudaFree(p->acc[f]);
-	for (int k=0; k<2; k++) { cudaFree(p->dexp[k]); cudaFreeHost(p->hexp[k]); }
 	cudaFree(p->d_jobs); cudaFree(p->d_w); cudaFree(p->d_sums);
-	for (int r=0; r<p->ring; r++) cudaEventDestroy(p->ev[r]);
 	delete p;
 }
 
+/* one updatePhaser call (reference phaser.c:94-110): every face and every frequency in one launch
+ * (kernel phaser_accumulate), phase factors as kernel arguments.  Lists longer than
+ * ALISB_PHASER_MAXF frequencies take one launch per ALISB_PHASER_MAXF. */
 extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const float *expH)
 {
 	alisb_engine *e = p->e;
 	DEV(e);
 	SETTLE(e);
-	const int slot = p->slot;
-	p->slot = (slot+1) % p->ring;
-	if (p->ev_pending[slot]) CU(cudaEventSynchronize(p->ev[slot]));       /* this slot's last copy has left the pinned buffer */
-	float2 *stage[2] = { p->hexp[0] + (size_t)slot*p->nfreq, p->hexp[1] + (size_t)slot*p->nfreq };
-	memcpy(stage[0], expE, 2*(size_t)p->nfreq*sizeof(float));
-	memcpy(stage[1], expH, 2*(size_t)p->nfreq*sizeof(float));
-	for (int k=0; k<2; k++) CU(cudaMemcpyAsync(p->dexp[k], stage[k], 2*(size_t)p->nfreq*sizeof(float), cudaMemcpyHostToDevice, e->stream));
-	CU(cudaEventRecord(p->ev[slot], e->stream)); p->ev_pending[slot] = true;
-	for (int f=0; f<6; f++) if (p->acc[f]) {
-		const int ax = f/2, c1 = (ax+1)%3, c2 = (ax+2)%3;
-		const size_t hstep = ax == 0 ? 1 : ax == 1 ? (size_t)e->pitch : e->plane;
-		const char *pe = getenv("ALISB_PHASER_PAR");           /* opt-in: one thread per (cell, frequency); read per call so that tests can switch it */
-		const int par = pe ? atoi(pe) : 0;
-		if (par && p->nfreq > 1)
-			phaser_face_par<<<div_up(p->cells[f]*(size_t)p->nfreq, 128), 128, 0, e->stream>>>(p->acc[f], e->F[0][0][c1], e->F[0][0][c2], e->F[1][0][c1], e->F[1][0][c2],
-				p->face[f], e->ny, e->pitch, hstep, p->nfreq, p->dexp[0], p->dexp[1]);
-		else
-		phaser_face<<<div_up(p->cells[f], 128), 128, 0, e->stream>>>(p->acc[f], e->F[0][0][c1], e->F[0][0][c2], e->F[1][0][c1], e->F[1][0][c2],
-			p->face[f], e->ny, e->pitch, hstep, p->nfreq, p->dexp[0], p->dexp[1]);
+	PhaserParams pp;
+	memset(&pp, 0, sizeof pp);
+	pp.ny = e->ny; pp.pitch = e->pitch; pp.nfreq = p->nfreq;
+	int nfaces = 0;
+	for (int f=0; f<6; f++) if (p->acc[f] && p->cells[f]) {
+		const int ax = f/2, c1 = (ax+1)%3, c2 = (ax+2)%3, k = nfaces++;
+		pp.acc[k] = p->acc[f]; pp.B[k] = p->face[f];
+		pp.E1[k] = e->F[0][0][c1]; pp.E2[k] = e->F[0][0][c2]; pp.H1[k] = e->F[1][0][c1]; pp.H2[k] = e->F[1][0][c2];
+		pp.hstep[k] = ax == 0 ? 1 : ax == 1 ? (unsigned long long)e->pitch : (unsigned long long)e->plane;
+	}
+	pp.nfaces = nfaces;
+	if (!nfaces) return ALISB_OK;
+	for (int f0=0; f0<p->nfreq; f0+=ALISB_PHASER_MAXF) {
+		const int nf = std::min(ALISB_PHASER_MAXF, p->nfreq - f0);
+		pp.f0 = f0; pp.nf = nf;
+		memcpy(pp.wE, expE + 2*(size_t)f0, 2*(size_t)nf*sizeof(float));
+		memcpy(pp.wH, expH + 2*(size_t)f0, 2*(size_t)nf*sizeof(float));
+		unsigned long long tot = 0;
+		for (int k=0; k<nfaces; k++) { pp.start[k] = tot; tot += (unsigned long long)bcount(pp.B[k])*nf; }
+		pp.start[nfaces] = tot;
+		phaser_accumulate<<<div_up(tot, 256), 256, 0, e->stream>>>(pp);
 		e->launches++;
 	}
 	CU(cudaGetLastError());

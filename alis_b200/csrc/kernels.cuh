@@ -18,7 +18,27 @@
 
 #define ALISB_XO 31               /* array coordinate a sits at row offset XO + a */
 
+struct Box { int a0, b0, c0, na, nb, nc; };
+
+/* Dispersive objects handled INSIDE the volume kernels (template flag ADE): the E pass applies the
+ * conductivity loss and subtracts the polarisation currents from the E it has just loaded, before
+ * the curl (reference update.c:89-108); the H pass advances J/K from the final E it reads anyway
+ * (updateJ, update.c:128-158).  The table lives in device memory (one per complex field set). */
+#define ALISB_MAXADE 8
+struct AdeObj {
+	const float *fill[3];         /* dense box arrays, x fastest */
+	float *J[ALISB_MAXPOLES][3], *K[ALISB_MAXPOLES][3];
+	float a[3];
+	float JJ[3][ALISB_MAXPOLES], JK[3][ALISB_MAXPOLES], JE[3][ALISB_MAXPOLES];
+	float KJ[3][ALISB_MAXPOLES], KK[3][ALISB_MAXPOLES], KE[3][ALISB_MAXPOLES];
+	int nj, nk, lossy;
+	Box full;                     /* allocation box of fill/J/K                         */
+	Box upd;                      /* full clipped to the updated cells 1..n              */
+};
+struct AdeTable { int n, pad; AdeObj o[ALISB_MAXADE]; };
+
 struct VolParams {
+	const AdeTable *ade;          /* ADE variants only */
 	float       *F[3];            /* field set being updated (E or H), components x,y,z */
 	const float *Fin[3];          /* where the old values are read: == F (in place) or the other buffer (double-buffered mode) */
 	const float *G[3];            /* the other field set                                */
@@ -68,7 +88,7 @@ template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, flo
  */
 /* XL = lanes of a warp along x: 32 (a warp is one 128-cell row segment) or 8 (a warp is a 32-cell
  * wide, 4-row patch: used for the narrow x-PML strips so that all lanes have work). */
-template <int S, bool EPS, int PM, int XL>  /* PM: bit 0/1/2 = this box may touch x / y / z PML slabs */
+template <int S, bool EPS, int PM, int XL, bool ADE>  /* PM: bit 0/1/2 = this box may touch x / y / z PML slabs */
 static __device__ __forceinline__ void yee_body(const VolParams &p, const VolRegion &r, const int bix, const int biy, const int biz)
 {
 	constexpr int RW = 32/XL;                               /* rows per warp */
@@ -168,6 +188,40 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 		const float Dx[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
 		const float Cx[4] = {cx.x, cx.y, cx.z, cx.w}, Cy[4] = {cy.x, cy.y, cy.z, cy.w}, Cz[4] = {cz.x, cz.y, cz.z, cz.w};
 
+		if (ADE && S > 0 && act) {
+			/* update.c:89-108 on the old E in registers: every lossy object's factor, then every object's
+			 * currents, objects and poles in list order (cells are independent, so this is the reference's
+			 * sequence of whole-box sweeps seen from one cell) */
+			const AdeTable &T = *p.ade;
+			for (int n = 0; n < T.n; n++) {
+				const AdeObj &ob = T.o[n];
+				if (!ob.lossy || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
+				const size_t jr = ((size_t)(c - ob.full.c0)*ob.full.nb + (b - ob.full.b0))*ob.full.na;
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int a = a0 + e;
+					if (a < ob.upd.a0 || a >= ob.upd.a0 + ob.upd.na || a > r.a_last) continue;
+					const size_t j = jr + (a - ob.full.a0);
+					const float f0 = ob.fill[0][j], f1 = ob.fill[1][j], f2 = ob.fill[2][j];
+					Fx[e] = Fx[e] * ((1 - ob.a[0]*f0) / (1 + ob.a[0]*f0));       /* update.c:94-96 */
+					Fy[e] = Fy[e] * ((1 - ob.a[1]*f1) / (1 + ob.a[1]*f1));
+					Fz[e] = Fz[e] * ((1 - ob.a[2]*f2) / (1 + ob.a[2]*f2));
+				}
+			}
+			for (int n = 0; n < T.n; n++) {
+				const AdeObj &ob = T.o[n];
+				if (!ob.nk || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
+				const size_t jr = ((size_t)(c - ob.full.c0)*ob.full.nb + (b - ob.full.b0))*ob.full.na;
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int a = a0 + e;
+					if (a < ob.upd.a0 || a >= ob.upd.a0 + ob.upd.na || a > r.a_last) continue;
+					const size_t j = jr + (a - ob.full.a0);
+					for (int s = 0; s < ob.nk; s++) { Fx[e] -= ob.J[s][0][j]; Fy[e] -= ob.J[s][1][j]; Fz[e] -= ob.J[s][2][j]; }   /* update.c:104-106 */
+				}
+			}
+		}
+
 		/* update.c:110-112 / :115-117 */
 		#pragma unroll
 		for (int e = 0; e < 4; e++) {
@@ -260,6 +314,37 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 		} else if (act) {
 			#pragma unroll
 			for (int e = 0; e < 4; e++) if (a0 + e <= r.a_last) { F0[o + e] = Fx[e]; F1[o + e] = Fy[e]; F2[o + e] = Fz[e]; }
+		}
+		if (ADE && S < 0 && act) {
+			/* updateJ (update.c:128-158) from the final E of this thread's own cells, which the H pass has
+			 * in registers as G: Drude poles, then critical-point / Lorentz pairs (K uses the new J) */
+			const AdeTable &T = *p.ade;
+			for (int n = 0; n < T.n; n++) {
+				const AdeObj &ob = T.o[n];
+				if (!ob.nk || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
+				const size_t jr = ((size_t)(c - ob.full.c0)*ob.full.nb + (b - ob.full.b0))*ob.full.na;
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int a = a0 + e;
+					if (a < ob.upd.a0 || a >= ob.upd.a0 + ob.upd.na || a > r.a_last) continue;
+					const size_t j = jr + (a - ob.full.a0);
+					const float Ev[3] = {Gx[e], Gy[e], Gz[e]};
+					#pragma unroll
+					for (int k = 0; k < 3; k++) {
+						const float Fv = Ev[k], f = ob.fill[k][j];
+						for (int s = 0; s < ob.nk; s++) {
+							if (s < ob.nj) {
+								ob.J[s][k][j] = ob.JJ[k][s]*ob.J[s][k][j] + ob.JE[k][s]*f*Fv;                       /* update.c:135 */
+							} else {
+								const float Kold = ob.K[s][k][j];
+								const float Jn = ob.JJ[k][s]*ob.J[s][k][j] + ob.JK[k][s]*Kold + ob.JE[k][s]*f*Fv;   /* update.c:140 */
+								ob.J[s][k][j] = Jn;
+								ob.K[s][k][j] = ob.KJ[k][s]*Jn + ob.KK[k][s]*Kold + ob.KE[k][s]*f*Fv;               /* update.c:142 */
+							}
+						}
+					}
+				}
+			}
 		}
 		gxp = gx; gyp = gy;
 	}
@@ -482,18 +567,18 @@ yee_fused(const __grid_constant__ FusedParams p)
 }
 
 /* one box per launch: the slab-free interior (PM=0) and, with ALISB_MERGE=0, every other box */
-template <int S, bool EPS, int PM, int XL>
+template <int S, bool EPS, int PM, int XL, bool ADE>
 __global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
 yee_volume(const __grid_constant__ VolParams p, const __grid_constant__ VolRegion r)
 {
-	yee_body<S,EPS,PM,XL>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
+	yee_body<S,EPS,PM,XL,ADE>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 /* many boxes per launch: the PML shell of a grid is up to 26 boxes (6 faces, 12 edges, 8 corners),
  * most of them far too small to fill the GPU on their own.  A CTA looks its box up in the table and
  * runs the body specialised for that box's PML bitmask.  Two classes so that the big single-axis
  * faces keep 3 CTAs/SM: CLS 0 = faces (PM 1,2,4), CLS 1 = edges and corners (PM 3,5,6,7).   */
-template <int S, bool EPS, int CLS>
+template <int S, bool EPS, int CLS, bool ADE>
 __global__ void __launch_bounds__(256, CLS == 0 ? 3 : 2)
 yee_multi(const __grid_constant__ MultiParams mp)
 {
@@ -504,14 +589,14 @@ yee_multi(const __grid_constant__ MultiParams mp)
 	id -= r.cta0;
 	const int bix = (int)(id % (unsigned)r.gx), biy = (int)((id / (unsigned)r.gx) % (unsigned)r.gy), biz = (int)(id / ((unsigned)r.gx*(unsigned)r.gy));
 	if (CLS == 0) {
-		if (r.pm == 1) { if (r.narrow) yee_body<S,EPS,1,8>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,1,32>(mp.v, r, bix, biy, biz); }
-		else if (r.pm == 2) yee_body<S,EPS,2,32>(mp.v, r, bix, biy, biz);
-		else                yee_body<S,EPS,4,32>(mp.v, r, bix, biy, biz);
+		if (r.pm == 1) { if (r.narrow) yee_body<S,EPS,1,8,ADE>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,1,32,ADE>(mp.v, r, bix, biy, biz); }
+		else if (r.pm == 2) yee_body<S,EPS,2,32,ADE>(mp.v, r, bix, biy, biz);
+		else                yee_body<S,EPS,4,32,ADE>(mp.v, r, bix, biy, biz);
 	} else {
-		if (r.pm == 5) { if (r.narrow) yee_body<S,EPS,5,8>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,5,32>(mp.v, r, bix, biy, biz); }
-		else if (r.pm == 3) yee_body<S,EPS,3,32>(mp.v, r, bix, biy, biz);
-		else if (r.pm == 6) yee_body<S,EPS,6,32>(mp.v, r, bix, biy, biz);
-		else                yee_body<S,EPS,7,32>(mp.v, r, bix, biy, biz);
+		if (r.pm == 5) { if (r.narrow) yee_body<S,EPS,5,8,ADE>(mp.v, r, bix, biy, biz); else yee_body<S,EPS,5,32,ADE>(mp.v, r, bix, biy, biz); }
+		else if (r.pm == 3) yee_body<S,EPS,3,32,ADE>(mp.v, r, bix, biy, biz);
+		else if (r.pm == 6) yee_body<S,EPS,6,32,ADE>(mp.v, r, bix, biy, biz);
+		else                yee_body<S,EPS,7,32,ADE>(mp.v, r, bix, biy, biz);
 	}
 }
 
@@ -519,8 +604,6 @@ yee_multi(const __grid_constant__ MultiParams mp)
  * Box kernels (regions, planes, strips).  A box is [lo,hi] inclusive in array coordinates,
  * threads run x fastest.
  * ------------------------------------------------------------------------------------------ */
-struct Box { int a0, b0, c0, na, nb, nc; };
-
 static __device__ __forceinline__ bool box_cell(const Box &B, size_t t, int &a, int &b, int &c, size_t &q)
 {
 	const size_t n = (size_t)B.na*B.nb*B.nc;
@@ -804,53 +887,50 @@ __global__ void box_scatter(float *A, const float *buf, Box B, long long sC, lon
 	A[c*sC + b*sB + a + off] = buf[((size_t)(a - B.a0)*B.nb + (b - B.b0))*B.nc + (c - B.c0)];
 }
 
-/* reference phaser.c:83-91: running DFT on one face for all frequencies.
- * acc layout: [freq][which 0..3][cell] float2, cells x fastest over the face box.
- * The H terms reproduce the reference's promotion to double (0.5 is a double constant). */
-__global__ void phaser_face(float2 *acc, const float *E1, const float *E2, const float *H1, const float *H2,
-                            Box B, int ny, int pitch, size_t hstep, int nfreq, const float2 *expE, const float2 *expH)
-{
-	int a, b, c; size_t q;
-	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
-	const size_t cells = (size_t)B.na*B.nb*B.nc;
-	const size_t i = GIDX(a, b, c);
-	const float e1 = E1[i], e2 = E2[i];
-	const float h1 = H1[i] + H1[i + hstep], h2 = H2[i] + H2[i + hstep];
-	for (int f = 0; f < nfreq; f++) {
-		const float2 wE = expE[f], wH = expH[f];
-		float2 *A = acc + (size_t)f*4*cells + q;
-		float2 v = A[0];       v.x += wE.x*e1; v.y += wE.y*e1; A[0] = v;
-		v = A[cells];          v.x += wE.x*e2; v.y += wE.y*e2; A[cells] = v;
-		v = A[2*cells];
-		v.x = (float)((double)v.x + (double)(wH.x*h1)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h1)*0.5); A[2*cells] = v;
-		v = A[3*cells];
-		v.x = (float)((double)v.x + (double)(wH.x*h2)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h2)*0.5); A[3*cells] = v;
-	}
-}
+/* reference phaser.c:83-110 (updatePhaser): the running DFT of one call -- every face of the monitor
+ * box, every frequency of the list -- in ONE launch, one thread per (face cell, frequency).  The
+ * phase factors exp(i w t_E), exp(i w t_H) are evaluated on the host with the caller's cexpf and
+ * travel as kernel arguments (no staging copy, nothing to wait for).
+ * acc layout per face: [freq][which 0..3][cell] float2, cells x fastest over the face box; the four
+ * accumulators are E(c+1), E(c+2), H(c+1), H(c+2) for face normal c.  H is the average of the face
+ * plane and the next one; the H terms reproduce the reference's promotion to double (0.5 is a
+ * double constant).  Each accumulator is owned by exactly one thread: results do not depend on the
+ * launch shape and are bit-identical to the reference's loops. */
+#define ALISB_PHASER_MAXF 96      /* frequencies per launch (longer lists take several launches) */
+struct PhaserParams {
+	float2 *acc[6];
+	const float *E1[6], *E2[6], *H1[6], *H2[6];
+	Box B[6];
+	unsigned long long hstep[6];      /* to the next plane along the face normal             */
+	unsigned long long start[7];      /* first thread of each face: prefix sums of cells*nf   */
+	int nfaces, nfreq, f0, nf;        /* this launch covers frequencies f0 .. f0+nf-1 of nfreq */
+	int ny, pitch;
+	float2 wE[ALISB_PHASER_MAXF], wH[ALISB_PHASER_MAXF];
+};
 
-/* the same accumulation with one thread per (face cell, frequency): identical arithmetic per
- * accumulator, nfreq times the parallelism for multi-frequency lists (a face of a few hundred cells
- * with 81 frequencies otherwise runs as a handful of CTAs looping serially).  Opt-in (ALISB_PHASER_PAR=1)
- * until it has been validated and timed on the GPU. */
-__global__ void phaser_face_par(float2 *acc, const float *E1, const float *E2, const float *H1, const float *H2,
-                                Box B, int ny, int pitch, size_t hstep, int nfreq, const float2 *expE, const float2 *expH)
+__global__ void __launch_bounds__(256) phaser_accumulate(const __grid_constant__ PhaserParams p)
 {
+	const int ny = p.ny, pitch = p.pitch;
+	unsigned long long t = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= p.start[p.nfaces]) return;
+	int k = 0;
+	while (k + 1 < p.nfaces && t >= p.start[k + 1]) k++;
+	t -= p.start[k];
+	const Box &B = p.B[k];
 	const size_t cells = (size_t)B.na*B.nb*B.nc;
-	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
-	if (t >= cells*(size_t)nfreq) return;
-	const int f = (int)(t / cells);
+	const int fl = (int)(t / cells);                 /* frequency within this launch */
 	int a, b, c; size_t q;
-	if (!box_cell(B, t - (size_t)f*cells, a, b, c, q)) return;
+	if (!box_cell(B, (size_t)(t - (unsigned long long)fl*cells), a, b, c, q)) return;
 	const size_t i = GIDX(a, b, c);
-	const float e1 = E1[i], e2 = E2[i];
-	const float h1 = H1[i] + H1[i + hstep], h2 = H2[i] + H2[i + hstep];
-	const float2 wE = expE[f], wH = expH[f];
-	float2 *A = acc + (size_t)f*4*cells + q;
-	float2 v = A[0];       v.x += wE.x*e1; v.y += wE.y*e1; A[0] = v;
-	v = A[cells];          v.x += wE.x*e2; v.y += wE.y*e2; A[cells] = v;
-	v = A[2*cells];
+	const float e1 = p.E1[k][i], e2 = p.E2[k][i];
+	const float h1 = p.H1[k][i] + p.H1[k][i + p.hstep[k]], h2 = p.H2[k][i] + p.H2[k][i + p.hstep[k]];
+	const float2 wE = p.wE[fl], wH = p.wH[fl];
+	float2 *A = p.acc[k] + (size_t)(p.f0 + fl)*4*cells + q;
+	float2 v = A[0];       v.x += wE.x*e1; v.y += wE.y*e1; A[0] = v;                 /* phaser.c:87 */
+	v = A[cells];          v.x += wE.x*e2; v.y += wE.y*e2; A[cells] = v;             /* phaser.c:88 */
+	v = A[2*cells];                                                                /* phaser.c:89 */
 	v.x = (float)((double)v.x + (double)(wH.x*h1)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h1)*0.5); A[2*cells] = v;
-	v = A[3*cells];
+	v = A[3*cells];                                                                /* phaser.c:90 */
 	v.x = (float)((double)v.x + (double)(wH.x*h2)*0.5); v.y = (float)((double)v.y + (double)(wH.y*h2)*0.5); A[3*cells] = v;
 }
 

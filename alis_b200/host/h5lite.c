@@ -145,9 +145,14 @@ static uint64_t le(const unsigned char *p, int bytes) { uint64_t v = 0; for (int
 
 typedef struct { int rank; unsigned long long dims[3]; int elem, is_float, big_endian; int layout; uint64_t addr, size; unsigned char *compact; } dinfo;
 
+/* every field of a message is read only after its extent has been checked against the message size the
+ * file declares (files come from users) */
+#define NEED_BYTES(n) do { if ((uint64_t)(n) > size) { snprintf(r->err, sizeof r->err, "truncated header message (type 0x%04x)", type); free(m); return -1; } } while (0)
 static int parse_messages(rd *r, uint64_t addr, uint64_t bytes, int *left, dinfo *D, int depth)
 {
+	if (bytes > (1u << 26)) { snprintf(r->err, sizeof r->err, "implausible object header size"); return -1; }
 	unsigned char *m = malloc(bytes ? bytes : 1);
+	if (!m) { snprintf(r->err, sizeof r->err, "out of memory"); return -1; }
 	if (rd_at(r, addr, m, bytes)) { free(m); return -1; }
 	uint64_t pos = 0;
 	while (*left > 0 && pos + 8 <= bytes) {
@@ -156,23 +161,37 @@ static int parse_messages(rd *r, uint64_t addr, uint64_t bytes, int *left, dinfo
 		if (pos + 8 + size > bytes) break;
 		(*left)--;
 		if (type == 0x0001) {                                   /* dataspace v1 / v2 */
+			NEED_BYTES(2);
 			const int ver = d[0]; D->rank = d[1];
-			const unsigned char *dim = d + (ver == 1 ? 8 : 4);
+			const size_t lead = ver == 1 ? 8 : 4;
+			const unsigned char *dim = d + lead;
 			if (D->rank < 1 || D->rank > 3) { snprintf(r->err, sizeof r->err, "dataset rank %d (1..3 supported)", D->rank); free(m); return -1; }
+			NEED_BYTES(lead + (size_t)D->rank*r->sl);
 			for (int q=0; q<D->rank; q++) D->dims[q] = le(dim + q*r->sl, r->sl);
 		}
 		else if (type == 0x0003) {                              /* datatype */
+			NEED_BYTES(8);
 			const int cls = d[0] & 15;
 			D->is_float = cls == 1; D->big_endian = d[1] & 1; D->elem = (int)le(d+4, 4);
 		}
 		else if (type == 0x0008) {                              /* data layout */
+			NEED_BYTES(2);
 			if (d[0] != 3) { snprintf(r->err, sizeof r->err, "data layout message version %d (3 supported)", d[0]); free(m); return -1; }
 			D->layout = d[1];
-			if (d[1] == 1) { D->addr = le(d+2, r->so); D->size = le(d+2+r->so, r->sl); }
-			else if (d[1] == 0) { D->size = le(d+2, 2); D->compact = malloc(D->size ? D->size : 1); memcpy(D->compact, d+4, D->size); }
+			if (d[1] == 1) { NEED_BYTES(2 + r->so + r->sl); D->addr = le(d+2, r->so); D->size = le(d+2+r->so, r->sl); }
+			else if (d[1] == 0) {
+				NEED_BYTES(4);
+				D->size = le(d+2, 2);
+				NEED_BYTES(4 + D->size);                            /* the data must lie inside the message */
+				free(D->compact);                                   /* a second layout message replaces the first */
+				D->compact = malloc(D->size ? D->size : 1);
+				if (!D->compact) { snprintf(r->err, sizeof r->err, "out of memory"); free(m); return -1; }
+				memcpy(D->compact, d+4, D->size);
+			}
 		}
 		else if (type == 0x000B) { snprintf(r->err, sizeof r->err, "filtered (compressed) datasets are not supported"); free(m); return -1; }
 		else if (type == 0x0010 && depth < 8) {                 /* continuation block */
+			NEED_BYTES(r->so + r->sl);
 			if (parse_messages(r, le(d, r->so), le(d+r->so, r->sl), left, D, depth+1)) { free(m); return -1; }
 		}
 		pos += 8 + size;
@@ -234,15 +253,20 @@ void *h5lite_read(const char *path, int *rank_out, unsigned long long dims_out[3
 	if (D.layout != 0 && D.layout != 1) FAIL("chunked datasets are not supported");
 	{
 		size_t count = 1;
-		for (int q=0; q<D.rank; q++) count *= D.dims[q];
+		for (int q=0; q<D.rank; q++) {                                /* overflow-safe product, bounded by what a float*** of the library can hold */
+			if (D.dims[q] && count > ((size_t)1 << 40)/D.dims[q]) FAIL("dataset too large");
+			count *= D.dims[q];
+		}
 		unsigned char *raw = D.compact;
 		if (D.layout == 1) {
 			raw = malloc(count*D.elem ? count*D.elem : 1);
+			if (!raw) FAIL("out of memory (%zu elements)", count);
 			if (D.addr == UNDEF) memset(raw, 0, count*D.elem);     /* never written: fill value */
 			else if (rd_at(&r, D.addr, raw, count*D.elem)) { free(raw); goto done; }
 		}
-		else if (D.size < count*D.elem) FAIL("compact dataset shorter than its dataspace");
+		else if (!raw || D.size < count*D.elem) FAIL("compact dataset shorter than its dataspace");
 		out = malloc(sizeof(float)*(count ? count : 1));
+		if (!out) { if (D.layout == 1) free(raw); FAIL("out of memory (%zu elements)", count); }
 		for (size_t q=0; q<count; q++) {
 			unsigned char t[8];
 			for (int b=0; b<D.elem; b++) t[b] = raw[q*D.elem + (D.big_endian ? D.elem-1-b : b)];

@@ -16,6 +16,7 @@
 #include <sys/mman.h>
 #include <signal.h>
 #include <unistd.h>
+#include <pthread.h>
 #include <string.h>
 #include "alis_c.h"
 #include "host_internal.h"
@@ -24,13 +25,24 @@ static alisb_engine *engine_of(world W) { return alis_bridge_engine(alis_host_br
 static phaser base_of(phaser P) { return P - P->b200_index; }
 
 /* ---- guarded host views -------------------------------------------------------------------------------
- * Every phasor array's data block is page aligned and page sized, registered with the list it
- * belongs to.  ALIS_PHASER_GUARD=0 turns the protection off (the arrays are then only valid after
- * alisSyncPhaser). */
-typedef struct guard { char *lo; size_t bytes; phaser base; struct guard *next; } guard;
+ * All host views of a phaser list live in ONE shared-memory block that is mapped twice:
+ *   lo     the user mapping, the one P->zMax.Ex[i][j][k] points into.  PROT_NONE while the device holds
+ *          newer data, readable/writable otherwise.
+ *   alias  a second mapping of the same pages, always writable, never handed out.
+ * A refresh (alisSyncPhaser, called by library routines or by the fault handler) fills the pages through
+ * `alias` under guard_lock and unprotects `lo` only AFTER the data is complete and b200_stale is cleared:
+ * a second thread that touches the arrays meanwhile (reference examples/Cross_Polarization_T.c:3-19 reads
+ * them inside `#pragma omp parallel for`) still faults, blocks on the lock in its own handler, finds the
+ * list fresh and retries -- no thread can ever see a half-filled or stale page.
+ * The handler calls the CUDA runtime (a device-to-host copy), which is not async-signal-safe in general;
+ * it is entered only synchronously, by a load/store of user code on these pages, never from inside the
+ * runtime or libc.  ALIS_PHASER_GUARD=0 turns the protection off: the arrays are then plain memory and
+ * valid only after an explicit alisSyncPhaser(P) (the conservative path; include/alis_api.h). */
+typedef struct guard { char *lo, *alias; size_t bytes; phaser base; struct guard *next; } guard;
 static guard *guards;
 static struct sigaction chained;
 static int handler_installed;
+static pthread_mutex_t guard_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static int guard_enabled(void)
 {
@@ -39,19 +51,23 @@ static int guard_enabled(void)
 	return mode;
 }
 
+static guard *guard_of(phaser base)
+{
+	for (guard *g = guards; g; g = g->next) if (g->base == base) return g;
+	return 0;
+}
+
 static void guard_protect(phaser base, int prot)
 {
-	if (!guard_enabled()) return;
-	for (guard *g = guards; g; g = g->next) if (g->base == base) mprotect(g->lo, g->bytes, prot);
+	guard *g = guard_of(base);
+	if (g) mprotect(g->lo, g->bytes, prot);
 }
 
 static void guard_fault(int sig, siginfo_t *si, void *ctx)
 {
 	const char *addr = (const char*)si->si_addr;
 	for (guard *g = guards; g; g = g->next) if (g->lo <= addr && addr < g->lo + g->bytes) {
-		phaser base = g->base;
-		guard_protect(base, PROT_READ | PROT_WRITE);     /* whatever happens next, the retry must not fault again */
-		alisSyncPhaser(base);
+		alisSyncPhaser(g->base);        /* takes guard_lock; returns with the pages complete and accessible */
 		return;
 	}
 	/* not ours: hand over to whoever was installed before (or the default action) */
@@ -60,18 +76,31 @@ static void guard_fault(int sig, siginfo_t *si, void *ctx)
 	signal(sig, SIG_DFL);
 }
 
-/* one page-aligned, page-sized block for all host views of a list, registered for protection as a
- * single range (one mprotect per transition, however many frequencies the list has) */
+/* the doubly mapped block for all host views of a list, registered for protection as a single range
+ * (one mprotect per transition, however many frequencies the list has); 0 when the guard is off or
+ * the kernel refuses the shared mapping (the views are then ordinary memory) */
 static char *guard_arena(phaser base, size_t bytes)
 {
 	if (!guard_enabled() || !bytes) return 0;
 	const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-	char *data = 0;
 	bytes = (bytes + page - 1)/page*page;
-	if (posix_memalign((void**)&data, page, bytes)) printf("Insufficient memory!\n"), exit(1);
-	memset(data, 0, bytes);
+	const int fd = memfd_create("alis-phasor-views", MFD_CLOEXEC);
+	if (fd < 0) return 0;
+	char *lo = MAP_FAILED, *alias = MAP_FAILED;
+	if (ftruncate(fd, (off_t)bytes) == 0) {
+		lo = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+		alias = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	}
+	close(fd);
+	if (lo == MAP_FAILED || alias == MAP_FAILED) {
+		if (lo != MAP_FAILED) munmap(lo, bytes);
+		if (alias != MAP_FAILED) munmap(alias, bytes);
+		return 0;
+	}
 	guard *g = xmalloc(sizeof *g);
-	g->lo = data; g->bytes = bytes; g->base = base; g->next = guards; guards = g;
+	g->lo = lo; g->alias = alias; g->bytes = bytes; g->base = base;
+	pthread_mutex_lock(&guard_lock);
+	g->next = guards; guards = g;
 	if (!handler_installed) {
 		struct sigaction sa;
 		memset(&sa, 0, sizeof sa);
@@ -81,7 +110,8 @@ static char *guard_arena(phaser base, size_t bytes)
 		sigaction(SIGSEGV, &sa, &chained);
 		handler_installed = 1;
 	}
-	return data;
+	pthread_mutex_unlock(&guard_lock);
+	return lo;
 }
 
 /* makeComplexField over a given data block (or its own when data == 0) */
@@ -103,11 +133,12 @@ static float complex ***field_over(float complex *data, int iMin, int iMax, int 
 
 static void guard_release(phaser base)
 {
-	guard_protect(base, PROT_READ | PROT_WRITE);
+	pthread_mutex_lock(&guard_lock);
 	for (guard **g = &guards; *g; ) {
-		if ((*g)->base == base) { guard *dead = *g; *g = dead->next; free(dead); }
+		if ((*g)->base == base) { guard *dead = *g; *g = dead->next; munmap(dead->lo, dead->bytes); munmap(dead->alias, dead->bytes); free(dead); }
 		else g = &(*g)->next;
 	}
+	pthread_mutex_unlock(&guard_lock);
 }
 
 /* face order used with the engine: 0 xMin, 1 xMax, 2 yMin, 3 yMax, 4 zMin, 5 zMax; the four
@@ -238,7 +269,12 @@ void updatePhaser(world W, phaser P)
 		printf("alis-b200: %s\n", alisb_last_error());
 		exit(1);
 	}
-	if (!B->b200_stale) { B->b200_stale = 1; guard_protect(B, PROT_NONE); }      /* the device is ahead of the host views now */
+	if (!B->b200_stale) {                        /* the device is ahead of the host views now */
+		pthread_mutex_lock(&guard_lock);
+		B->b200_stale = 1;
+		guard_protect(B, PROT_NONE);
+		pthread_mutex_unlock(&guard_lock);
+	}
 	free(wE); free(wH);
 }
 
@@ -253,16 +289,26 @@ alisb_phaser *alis_phaser_device(phaser P, int *freq)
 void alisSyncPhaser(phaser P)
 {
 	phaser B = base_of(P);
-	if (!B->b200_dev || !B->b200_stale) return;
-	guard_protect(B, PROT_READ | PROT_WRITE);
-	for (phaser p = B; p->f; p++) for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
-		float complex ***A = *slot_of(face_of(p, face), face/2, which);
-		if (!A) continue;
-		int b[6];
-		face_box(p, face, b);
-		if (alisb_phaser_read(B->b200_dev, p->b200_index, face, which, (float*)&A[b[0]][b[2]][b[4]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (!B->b200_dev) return;
+	pthread_mutex_lock(&guard_lock);
+	if (B->b200_stale) {
+		/* fill through the always-writable alias mapping; the user mapping opens only when all is there */
+		const guard *g = guard_of(B);
+		const ptrdiff_t shift = g ? g->alias - g->lo : 0;
+		for (phaser p = B; p->f; p++) for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
+			float complex ***A = *slot_of(face_of(p, face), face/2, which);
+			if (!A) continue;
+			int b[6];
+			face_box(p, face, b);
+			/* the row-pointer tables are ordinary memory; only the data block is guarded */
+			float *dst = (float*)((char*)(A[b[0]][b[2]] + b[4]) + shift);
+			if (alisb_phaser_read(B->b200_dev, p->b200_index, face, which, dst) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		}
+		__sync_synchronize();
+		B->b200_stale = 0;
+		guard_protect(B, PROT_READ | PROT_WRITE);
 	}
-	B->b200_stale = 0;
+	pthread_mutex_unlock(&guard_lock);
 }
 
 /* reference phaser.c:122-139 */
@@ -288,8 +334,7 @@ void deletePhaser(phaser P)
 		if (p->ex) free(&p->ex[p->kMIN]);
 		if (p->ez) free(&p->ez[p->kMIN]);
 	}
-	free(B->b200_arena);
-	free(B);
+	free(B);                                     /* the arena's two mappings went with guard_release */
 }
 
 /* ---- flux of the phasors through the monitor box (reference phaser.c:142-245) ---------------------

@@ -14,13 +14,17 @@ grid.  Metric: Mcells/s (cells incl. PML x steps / second), whole job.
   e2e       the same steps driven the way a user's time loop drives them: per step the source
             sample is produced on the host and a probe value (get(W,Ez,...)) is read back
             device->host, host wall clock around the loop
-  roofline  the dominant kernel (yee_volume interior instantiation): algorithmic bytes
-            (36 B per cell per half-step pass) / CUDA-event duration of that launch
+  roofline  the dominant kernel (the interior launch): algorithmic bytes (36 B per cell per
+            half-step pass = 72 B per cell-step) / CUDA-event duration of that launch
+            -> `frac`; beside it `frac_of_moved_bytes` on the bytes the kernel must move (a fused
+            E+H launch: 48 B per cell-step) and `traffic` (ncu dram bytes, reported only while the
+            kernel sources are the captured ones)
   cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample
 
 `--impl reference` times the reference CPU implementation (oracle/_ref/bin/bench_cube_ref, the
-reference library built from its own sources; falls back to the oracle port) on a bounded
-z-sub-slab of the same workload.
+reference library built from its own sources; falls back to the oracle port) on ONE GPU's shard
+of the same workload (2048 x 2048 x 256 with all six CPML sides, when the host RAM allows).
+`--scaling strong` runs the named 2048^3 cube split over N GPUs (N = 1: 2048 x 2048 x 1024).
 """
 import argparse
 import json
@@ -50,6 +54,10 @@ def parse():
     ap.add_argument("--nz-per-gpu", type=int, default=NZ_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver runs): --nz-per-gpu planes per GPU; strong: the named 2048^3 cube split over the GPUs "
+                         "(--nz-total planes in all; the 1-GPU reference point is 2048x2048x1024, SURVEY 8d: the cube does not fit one GPU)")
+    ap.add_argument("--nz-total", type=int, default=2048)
     ap.add_argument("--fuse", type=int, default=int(os.environ.get("ALISB_FUSE", FUSE_DEFAULT)),
                     help="1: fused E+H stepping where a step is only the two curls (48 B per cell-step instead of 72)")
     return ap.parse_args()
@@ -57,6 +65,40 @@ def parse():
 
 def workload_name(nx, ny, nz, n):
     return f"synthetic vacuum+CPML(Num={NUM}) box {nx}x{ny}x{nz} cells, point dipole Ez/Pulse, z-slab sharded over {n} GPU(s), {nz // n} planes per GPU"
+
+
+def total_planes(args, world):
+    """planes of the whole job: weak = nz_per_gpu per GPU; strong = the fixed cube (1 GPU: half of it, it does not fit)"""
+    if args.scaling == "weak":
+        return args.nz_per_gpu * world
+    return args.nz_total if world > 1 else min(args.nz_total, 1024)
+
+
+def config_of(args, world):
+    """identical in both arms (the driver compares them)"""
+    nz = total_planes(args, world)
+    return {"workload": workload_name(args.nx, args.ny, nz, world),
+            "l2": "inputs (6 field arrays, >= 26 GB per GPU) are far larger than the 126 MB L2"}
+
+
+def pml_share(nx, ny, nz):
+    """fraction of the box's cells that lie in a CPML slab (Num + 1 cells on each of the six sides)"""
+    d = NUM + 1
+    inner = max(nx - 2*d, 0) * max(ny - 2*d, 0) * max(nz - 2*d, 0)
+    return 1.0 - inner / float(nx * ny * nz)
+
+
+def host_sample_planes(nx, ny, want):
+    """z extent of the CPU sample: the GPU arm's per-GPU box when the host has the memory for the reference's
+    arrays (6 fields + CPML slabs, ~25 B per cell), else the largest power of two that fits"""
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail = 32 << 30
+    nz = want
+    while nz > 32 and nx * ny * nz * 26 * 1.15 > 0.8 * avail:
+        nz //= 2
+    return nz
 
 
 # ------------------------------------------------------------------------------------------
@@ -87,15 +129,16 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nz_total = args.nz_per_gpu * args.gpus
-    sample_nz = 64                                   # bounded z-sub-slab of the workload
+    per_gpu = total_planes(args, args.gpus) // args.gpus
+    sample_nz = host_sample_planes(args.nx, args.ny, per_gpu)      # one GPU's shard of the workload when the host RAM allows
     r = run_reference_cube(args.nx, args.ny, sample_nz, args.steps, args.warmup)
-    sample = f"{args.nx}x{args.ny}x{sample_nz} z-sub-slab of the workload, {args.steps} steps, all host threads"
+    sample = (f"{args.nx}x{args.ny}x{sample_nz} box (one GPU's shard of the workload with all six CPML sides, "
+              f"{100 * pml_share(args.nx, args.ny, sample_nz):.1f}% of its cells in CPML slabs), {args.steps} steps, all host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.nx, args.ny, nz_total, args.gpus), "timed_sample": sample},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(args, args.gpus), "timed_sample": sample,
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,7 +198,7 @@ def ours(args):
 
     torch.cuda.set_stream(torch.cuda.Stream())       # a real (non-default) stream shared by the engine, NCCL ordering and the timing events
     lib = capi.load_engine()
-    nz = args.nz_per_gpu * world
+    nz = total_planes(args, world)
     w = synthetic.BoxWorld(args.nx, args.ny, nz, num=NUM)
     os.environ["ALISB_FUSE"] = str(args.fuse)        # read by the engine at creation (here and in the C driver of the e2e leg)
     eng = w.make_engine(lib, device=local, rank=rank, world=world)
@@ -211,7 +254,13 @@ def ours(args):
         roof = None
         if kinfo:
             ach = kinfo["bytes_per_launch"] / (kinfo["avg_ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": load_traffic("yee_fused" if fused_launches else "yee_volume"),
+            # what the kernel must move: a fused E+H launch reads and writes every field once (48 B per cell-step,
+            # 2/3 of the two-pass 72 B the algorithmic figure is quoted on)
+            moved = kinfo["bytes_per_launch"] * (2.0 / 3.0 if fused_launches else 1.0)
+            traffic, traffic_note = load_traffic("yee_fused" if fused_launches else "yee_volume")
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks, "traffic": traffic, "traffic_source": traffic_note,
+                    "moved_bytes_per_launch": moved, "achieved_moved_GBps": moved / (kinfo["avg_ms"] * 1e-3) / 1e9,
+                    "frac_of_moved_bytes": moved / (kinfo["avg_ms"] * 1e-3) / 1e9 / peaks,
                     "kernel": ("yee_fused (interior, E and H half steps in one pass; algorithmic bytes are the two-pass 72 B per cell-step of SURVEY 8d, "
                                "the kernel itself moves 48 B per cell-step, so frac may exceed 1)") if fused_launches else "yee_volume (interior, no-PML instantiation)",
                     "avg_launch_ms": kinfo["avg_ms"], "launches_timed": kinfo["n"],
@@ -219,14 +268,15 @@ def ours(args):
                     "whole_step": {"algorithmic_bytes": w.algorithmic_bytes_per_step() / world, "achieved_GBps": w.algorithmic_bytes_per_step() / world / (ms / args.steps * 1e-3) / 1e9}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference_cube(256, 256, 256, 100, 3)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": "256^3 all-PML vacuum cube, 100 steps, all host threads"}
+            snz = host_sample_planes(args.nx, args.ny, nz)
+            r = run_reference_cube(args.nx, args.ny, snz, 8, 1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                   "sample": f"{args.nx}x{args.ny}x{snz} box of the same workload ({100 * pml_share(args.nx, args.ny, snz):.1f}% of its cells in CPML slabs), 8 steps after 1 warm-up, all host threads"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.nx, args.ny, nz, world), "l2": "inputs (6 field arrays, >= 26 GB per GPU) are far larger than the 126 MB L2",
-                       "per_gpu_mcells_per_s": value / world},
+            "config": config_of(args, world), "per_gpu_mcells_per_s": value / world,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "fused_launches": fused_launches, "clocks": clocks,
         }
         emit(line)
@@ -252,14 +302,14 @@ def e2e_through_c_api(args, world, rank, local, w, eng, runner, barrier):
         eng.close()                                  # give the 27 GB back before the C driver allocates its own world
         torch.cuda.empty_cache()
         env = dict(os.environ, ALIS_DEVICE=str(local))
-        out = subprocess.run([exe, str(args.nx), str(args.ny), str(args.nz_per_gpu), str(args.steps), str(args.warmup), "1"],
+        out = subprocess.run([exe, str(args.nx), str(args.ny), str(total_planes(args, world) // world), str(args.steps), str(args.warmup), "1"],
                              env=env, capture_output=True, text=True, timeout=3000).stdout
         m = re.search(r"seconds=([0-9.]+) mcells_per_s=([0-9.]+)", out)
         if m:
             res = {"value": float(m.group(2)), "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4,
                    "path": "C driver on the public API: tests/bin/bench_cube_mine_cuda (oracle/harness/bench_cube.c + alis_b200/libalis.so)", "note": note}
             # the same loop with a plane monitor at the cadence of examples/Dipole_PML.c: sliceMax(W, EE, XY) every 4th step
-            out2 = subprocess.run([exe, str(args.nx), str(args.ny), str(args.nz_per_gpu), str(args.steps), str(args.warmup), "2"],
+            out2 = subprocess.run([exe, str(args.nx), str(args.ny), str(total_planes(args, world) // world), str(args.steps), str(args.warmup), "2"],
                                   env=env, capture_output=True, text=True, timeout=3000).stdout
             m2 = re.search(r"seconds=([0-9.]+) mcells_per_s=([0-9.]+)", out2)
             if m2:
@@ -303,15 +353,30 @@ def load_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def kernels_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("kernels.cuh", "engine.cu"):
+        h.update(open(os.path.join(ROOT, "alis_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture of this bench command, profiles/).  ncu cannot run inside a timed bench, so the
+    figure is a recorded one: it is reported only while the kernel sources are the ones it was captured from
+    (sha of alis_b200/csrc), otherwise null -- never a stale constant."""
     p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))[kernel].get("dram_bytes_per_launch")
+            rec = json.load(open(p))
+            k = rec[kernel]
+            if rec.get("csrc_sha16") != kernels_sha():
+                return None, f"capture {k.get('source', p)} predates the current kernel sources: not reported"
+            return k.get("dram_bytes_per_launch"), f"{k.get('source', p)} (same kernel sources, sha {rec.get('csrc_sha16')})"
         except Exception:
-            return None
-    return None
+            return None, "no capture"
+    return None, "no capture"
 
 
 def emit(line):

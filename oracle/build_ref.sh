@@ -25,6 +25,8 @@ done
 gcc -std=c99 -O2 -fpic -w -c "$HERE/../alis_b200/host/h5lite.c" -o "$OUT/obj/h5lite.o"
 # world.o must pick up a changed shim
 if [ "$HERE/shim/hdf5.h" -nt "$OUT/obj/world.o" ]; then gcc $CFLAGS -c "$REF/src/world.c" -o "$OUT/obj/world.o"; fi
+# ... and slices.o a changed png.h shim (a minimal real PNG writer, so that slice images can be compared)
+if [ "$HERE/shim/png.h" -nt "$OUT/obj/slices.o" ]; then gcc $CFLAGS -c "$REF/src/slices.c" -o "$OUT/obj/slices.o"; fi
 rm -f "$OUT/libalis_ref.a"
 ar rcs "$OUT/libalis_ref.a" "$OUT"/obj/*.o
 gcc -shared -fopenmp -o "$OUT/libalis_ref.so" "$OUT"/obj/*.o -lm
@@ -44,6 +46,12 @@ gcc -std=c99 -fopenmp -O3 -w $INC "$HERE/harness/graded_slices.c" "$OUT/libalis_
 for ex in "$HERE"/../examples/*.c; do
 	[ -f "$ex" ] || continue
 	gcc -std=c99 -fopenmp -O3 -w $INC "$ex" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/$(basename "$ex" .c)_ref"
+done
+# the reference's OWN example drivers, unmodified, compiled where they lie (nothing is copied): the CPU twins
+# of tests/bin/refex_*_cuda (tests/test_gpu_refex.py)
+for ex in "$REF"/examples/*.c; do
+	[ -f "$ex" ] || continue
+	gcc -std=c99 -fopenmp -O3 -w -I"$HERE/shim" -I"$REF/src" "$ex" "$OUT/libalis_ref.a" -lm -o "$OUT/bin/refex_$(basename "$ex" .c)_ref"
 done
 # (2) reference setup + CPU oracle engine through the bridge
 if [ -f "$HERE/liboracle_alis.so" ]; then

@@ -7,25 +7,46 @@
  *   monitors <config> <steps> [outdir]
  */
 #include <alis.h>
+#include <omp.h>
 #include "configs.h"
 
 static void emit(const char *tag, double v) { printf("%-28s % .9g\n", tag, v); }
 
 /* user code indexing the phasor arrays directly, as reference examples/Cross_Polarization_T.c:3-19
  * does: no library call in between that could refresh them */
-static double direct_phasor_sum(phaser Q)
+static double direct_phasor_sum_serial(phaser Q)
 {
 	double s = 0;
-#ifdef HARNESS_MODE_MINE
-	/* HARNESS_DIRECT_PHASOR=1: rely on the page-protection guard of the phasor views (the reference's
-	 * semantics); otherwise refresh them explicitly first.  Same values either way. */
-	if (!getenv("HARNESS_DIRECT_PHASOR")) alisSyncPhaser(Q);
-#endif
 	for (int i=Q->iMin; i<=Q->iMax; i++) for (int j=Q->jMin; j<=Q->jMax; j++) {
 		const float complex e = Q->zMax.Ex[i][j][Q->kMax], h = Q->zMax.Hy[i][j][Q->kMax];
 		s += crealf(e*conjf(h)) + 0.5*cabsf(Q->zMax.Ey[i][j][Q->kMax]);
 	}
 	return s;
+}
+
+static double direct_phasor_sum(phaser Q)
+{
+#ifdef HARNESS_MODE_MINE
+	/* HARNESS_DIRECT_PHASOR=1: rely on the page-protection guard of the phasor views (the reference's
+	 * semantics); otherwise refresh them explicitly first.  Same values either way.
+	 * HARNESS_DIRECT_PHASOR=omp: every thread of an OpenMP team walks the arrays at once, as
+	 * Cross_Polarization_T.c does -- all of them must see the complete, fresh data */
+	const char *mode = getenv("HARNESS_DIRECT_PHASOR");
+	if (!mode) alisSyncPhaser(Q);
+	if (mode && !strcmp(mode, "omp")) {
+		double part[64];
+		int nt = 0;
+		#pragma omp parallel num_threads(8)
+		{
+			#pragma omp single
+			nt = omp_get_num_threads();
+			part[omp_get_thread_num()] = direct_phasor_sum_serial(Q);
+		}
+		for (int t=1; t<nt; t++) if (part[t] != part[0]) return NAN;
+		return part[0];
+	}
+#endif
+	return direct_phasor_sum_serial(Q);
 }
 
 /* a slice "writer" that prints checksums of the sampled slice instead of a file: user-supplied

@@ -35,7 +35,7 @@ def run_monitors(binary, config, threads=None, steps=0, host_monitors=False, dir
     env.update(extra_env or {})
     env.pop("HARNESS_DIRECT_PHASOR", None)
     if direct_phasor:                    # the harness indexes the phasor arrays without refreshing them first
-        env["HARNESS_DIRECT_PHASOR"] = "1"
+        env["HARNESS_DIRECT_PHASOR"] = "omp" if direct_phasor == "omp" else "1"
     if threads:
         env["OMP_NUM_THREADS"] = str(threads)
     r = subprocess.run([exe, config, str(steps)], env=env, capture_output=True, text=True, timeout=1800)
@@ -225,3 +225,61 @@ def assert_fields_identical(e1, e2, what=""):
         raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ; first at [m,set,comp,a,b,c]={bad[0].tolist()} "
                              f"{a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}; rel L2 = {rel_l2(a, b):.3e}")
     assert np.abs(a).max() > 0, f"{what}: fields are all zero - the test is vacuous"
+
+
+def read_png(path):
+    """decodes an 8-bit RGB, non-interlaced PNG (what both png writers here produce; all five scanline
+    filters are handled) -> uint8 array (height, width, 3)"""
+    import struct
+    import zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n", path
+    pos, idat, w = 8, b"", None
+    while pos < len(data):
+        n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(tag + body) == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0], "bad chunk crc"
+        if tag == b"IHDR":
+            w, h, depth, colour, _, _, interlace = struct.unpack(">IIBBBBB", body)
+            assert depth == 8 and colour == 2 and interlace == 0, "only 8-bit RGB, non-interlaced"
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3*w)
+    out = np.zeros((h, 3*w), np.uint8)
+    for y in range(h):
+        f, line = raw[y, 0], raw[y, 1:].astype(np.int32)
+        up = out[y - 1].astype(np.int32) if y else np.zeros(3*w, np.int32)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + up) & 255
+        else:
+            cur = np.zeros(3*w, np.int32)
+            for x in range(3*w):
+                a = cur[x - 3] if x >= 3 else 0
+                c = up[x - 3] if x >= 3 else 0
+                b = up[x]
+                if f == 1:
+                    pred = a
+                elif f == 3:
+                    pred = (a + b)//2
+                else:
+                    p = a + b - c
+                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+                    pred = a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+                cur[x] = (line[x] + pred) & 255
+        out[y] = cur
+    return out.reshape(h, w, 3)
+
+
+def write_png(path, img):
+    import struct
+    import zlib
+    h, w, _ = img.shape
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body))
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))

@@ -170,3 +170,31 @@ def test_reader_refuses_what_it_cannot_read(lib, tmp_path):
         read(lib, str(tmp_path / "junk.h5"))
     with pytest.raises(RuntimeError, match="cannot open"):
         read(lib, str(tmp_path / "missing.h5"))
+
+
+def test_reader_bounds_hostile_sizes(lib, tmp_path):
+    """sizes read from the file are checked against the message that carries them: a compact layout whose
+    declared data size runs past its message, and a dataspace whose dimension product overflows, are
+    refused with a message instead of being copied / allocated"""
+    a = np.ones((3, 3), np.float32)
+    path = str(tmp_path / "a.h5")
+    write(lib, path, a)
+    raw = bytearray(open(path, "rb").read())
+    info = parse(bytes(raw))
+    lay = raw.find(bytes([3, 1]) + struct.pack("<Q", info["addr"]))
+    # (1) turn the contiguous layout message into a compact one that claims 60000 bytes of data inside an 18-byte message
+    b = bytearray(raw)
+    b[lay + 1] = 0
+    b[lay + 2:lay + 4] = struct.pack("<H", 60000)
+    open(str(tmp_path / "compact.h5"), "wb").write(b)
+    with pytest.raises(RuntimeError, match="truncated header message"):
+        read(lib, str(tmp_path / "compact.h5"))
+    # (2) absurd dimensions
+    b = bytearray(raw)
+    ds = b.find(bytes([1, 2, 0, 0, 0, 0, 0, 0]) + struct.pack("<Q", 3))
+    assert ds > 0
+    b[ds + 8:ds + 16] = struct.pack("<Q", 1 << 62)
+    b[ds + 16:ds + 24] = struct.pack("<Q", 1 << 62)
+    open(str(tmp_path / "huge.h5"), "wb").write(b)
+    with pytest.raises(RuntimeError, match="too large"):
+        read(lib, str(tmp_path / "huge.h5"))

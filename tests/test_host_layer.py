@@ -45,7 +45,7 @@ def test_phasor_arrays_are_coherent_for_direct_user_access(cfg):
     the page-protection guard refreshes the host views on first touch -- same values as with an
     explicit alisSyncPhaser and as the reference; with the guard off the views are stale (zero)"""
     want = {w[0]: w[1] for w in helpers.golden_monitors()[cfg]}
-    for direct in (True, False):
+    for direct in (True, "omp", False):        # "omp": eight threads touch the protected arrays at the same time
         got = {g[0]: g[1] for g in helpers.run_monitors("monitors_mine_oracle", cfg, direct_phasor=direct)}
         for tag in ("phasor_direct_mid", "phasor_direct_end"):
             assert got[tag] == want[tag] and float(want[tag]) != 0, (tag, direct)

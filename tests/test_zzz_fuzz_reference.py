@@ -96,22 +96,18 @@ def test_random_world_monitors_match_reference_gpu(seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("knobs", [{"ALISB_PHASER_PAR": "1"}, {"ALISB_PHASER_RING": "4"}, {"ALISB_PHASER_PAR": "1", "ALISB_PHASER_RING": "8"}],
-                         ids=["par", "ring4", "par-ring8"])
-def test_parallel_phaser_kernel_bit_exact(monkeypatch, knobs):
-    """the opt-in phasor knobs (until timed on a GPU): ALISB_PHASER_PAR=1, one thread per face cell and
-    frequency; ALISB_PHASER_RING=n, n pinned staging slots for the phase factors so that the host runs
-    ahead of the device (8 accumulations wrap a ring of 4 twice).  Accumulators identical to the
-    oracle's, i.e. to the default path's"""
+@pytest.mark.parametrize("nfreq", [9, 96, 131], ids=["9freq", "96freq", "131freq-two-launches"])
+def test_parallel_phaser_kernel_bit_exact(nfreq):
+    """kernel phaser_accumulate: every face and frequency of one updatePhaser in one launch, one thread per
+    (face cell, frequency), phase factors as kernel arguments; lists longer than 96 frequencies take one
+    launch per 96.  Accumulators identical to the oracle's loops (reference phaser.c:83-110)"""
     import numpy as np
     from alis_b200 import capi, synthetic
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
     eng, ora = capi.load_engine(), capi.load_oracle()
     w = synthetic.BoxWorld(48, 44, 40, num=6)
     g, o = w.make_engine(eng), w.make_engine(ora)
     helpers.seed_fields([g, o], (50, 46, 42), seed=7)
-    freqs = np.linspace(1 / 800.0, 1 / 400.0, 9).astype(np.float32)
+    freqs = np.linspace(1 / 800.0, 1 / 400.0, nfreq).astype(np.float32)
     box = [8, 41, 8, 37, 8, 33]
     pg, po = capi.Phaser(g, box, 0x3F, len(freqs)), capi.Phaser(o, box, 0x3F, len(freqs))
     for _ in range(8):
@@ -123,7 +119,7 @@ def test_parallel_phaser_kernel_bit_exact(monkeypatch, knobs):
         wH = np.exp(2j * np.pi * freqs.astype(np.float64) * tH).astype(np.complex64)
         pg.accumulate(wE, wH)
         po.accumulate(wE, wH)
-    for f in range(len(freqs)):
+    for f in sorted({0, 1, nfreq//2, 95 % nfreq, 96 % nfreq, nfreq - 1}):
         for face in range(6):
             for which in range(4):
                 a, b = pg.read(f, face, which), po.read(f, face, which)
@@ -138,9 +134,10 @@ def test_phasor_guard_on_gpu(cfg):
     """direct user access to the phasor arrays with the accumulators on the GPU: the SIGSEGV handler
     pulls them from the device (kept at the end of the suite: it is the one path that calls CUDA from
     a signal handler)"""
-    got = helpers.run_monitors("monitors_mine_cuda", cfg, direct_phasor=True)
     want = helpers.golden_monitors()[cfg]
-    assert not helpers.monitor_mismatches(got, want, device_flux=True)
+    for mode in (True, "omp"):         # "omp": eight threads fault on the protected arrays at once
+        got = helpers.run_monitors("monitors_mine_cuda", cfg, direct_phasor=mode)
+        assert not helpers.monitor_mismatches(got, want, device_flux=True), mode
 
 
 @pytest.mark.gpu
