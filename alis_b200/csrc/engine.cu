@@ -20,8 +20,12 @@
 #include <limits.h>
 #include <vector>
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>      /* header-only NVTX 3: ranges cost a few ns when no tool is attached */
 #include "alis_b200.h"
 #include "kernels.cuh"
+
+/* NVTX range per pass / monitor call: visible in nsys / ncu --nvtx timelines */
+struct NvtxRange { NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, ...)
@@ -1261,6 +1265,8 @@ extern "C" int alisb_begin_pass(alisb_engine *e, int set)
 extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 {
 	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
+	static const char *const names[2][3] = { { "alisb:updateE", "alisb:updateE:send-plane", "alisb:updateE:rest" }, { "alisb:updateH", "alisb:updateH:send-plane", "alisb:updateH:rest" } };
+	NvtxRange range(names[set][part]);
 	if (e->fuse_req || e->dbuf) {
 		CU(cudaSetDevice(e->g.device));
 		if (set == ALISB_SET_E) {
@@ -1523,6 +1529,7 @@ extern "C" int alisb_set_spacing(alisb_engine *e, int set, int axis, const float
 #define FLUX_BLOCKS 64
 extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes, int n, double *out)
 {
+	NvtxRange range("alisb:plane_flux");
 	if (n < 1 || !planes || !out) return fail(ALISB_EINVAL, "bad flux request");
 	DEV(e);
 	SETTLE(e);
@@ -1589,6 +1596,7 @@ static int eval_setup(alisb_engine *e, const alisb_field_fn *f, const int32_t ib
 
 extern "C" int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
 {
+	NvtxRange range("alisb:eval_box");
 	DEV(e);
 	EvalParams p;
 	TRY(eval_setup(e, f, ibox, false, p));
@@ -1606,6 +1614,7 @@ extern "C" int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const in
 
 extern "C" int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out)
 {
+	NvtxRange range("alisb:reduce_absmax");
 	DEV(e);
 	EvalParams p;
 	TRY(eval_setup(e, f, ibox, false, p));
@@ -1625,6 +1634,7 @@ extern "C" int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, con
 
 extern "C" int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host)
 {
+	NvtxRange range("alisb:column_sums");
 	DEV(e);
 	EvalParams p;
 	TRY(eval_setup(e, f, ibox, true, p));
@@ -1642,6 +1652,7 @@ extern "C" int alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const
 
 extern "C" int alisb_absorption_columns(alisb_engine *e, int obj, const int32_t box[6], float *host)
 {
+	NvtxRange range("alisb:absorption_columns");
 	if (!box || !host) return fail(ALISB_EINVAL, "absorption: null argument");
 	if (obj < 0 || obj >= (int)e->obj.size()) return fail(ALISB_EINVAL, "absorption: no such object");
 	if (!e->eps[0] || !e->eps[1] || !e->eps[2]) return fail(ALISB_ESTATE, "absorption: no material arrays");
@@ -1817,6 +1828,7 @@ extern "C" void alisb_phaser_destroy(alisb_phaser *p)
 extern "C" int alisb_phaser_accumulate(alisb_phaser *p, const float *expE, const float *expH)
 {
 	alisb_engine *e = p->e;
+	NvtxRange range("alisb:updatePhaser");
 	DEV(e);
 	SETTLE(e);
 	PhaserParams pp;
@@ -1865,6 +1877,7 @@ extern "C" int alisb_phaser_read(alisb_phaser *p, int freq, int face, int which,
 /* near-to-far-field surface sums: every job of an angular sweep in one launch (kernel surface_sums) */
 extern "C" int alisb_phaser_surface_sums(alisb_phaser *p, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out)
 {
+	NvtxRange range("alisb:phaser_surface_sums");
 	if (!p || freq < 0 || freq >= p->nfreq || njobs < 0 || (njobs && (!jobs || !weights || !out))) return fail(ALISB_EINVAL, "bad surface-sum request");
 	if (!njobs) return ALISB_OK;
 	alisb_engine *e = p->e;

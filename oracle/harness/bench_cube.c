@@ -2,7 +2,7 @@
  * bench_cube.c -- times updateE+updateH of an all-PML vacuum box through the PUBLIC API
  * (createWorld + pointDipole + the run loop), i.e. the synthetic configuration of SURVEY 8d.
  *
- *   bench_cube <nx> <ny> <nz> <steps> <warmup> [probe_every_step]
+ *   bench_cube <nx> <ny> <nz> <steps> <warmup> [probe_every_step [au]]
  *
  * prints one line:  cells=<n> steps=<k> seconds=<s> mcells_per_s=<v> threads=<t> probe=<Ez>
  * With probe_every_step = 1 the loop also reads get(W, Ez, ...) after every step, i.e. the way a
@@ -10,6 +10,9 @@
  * With 2 it additionally evaluates sliceMax(W, EE, XY) on the z=0 plane every 4th step, the monitor
  * cadence of examples/Dipole_PML.c:21-25 without the file output (in our library: a device->host
  * read of the plane's E components, ~100 MB at 2048^2).
+ * With a 7th argument "au" a gold block (alis_m.h Au: one Drude pole + two critical-point pairs) covering
+ * the central half of every axis, i.e. 1/8 of the interior, is placed first (putObjects): the dispersive
+ * variant of the benchmark (SURVEY 8d additive terms); the line then also reports ade_cells.
  * Linked against the unmodified reference it is the CPU baseline (`--impl reference` and
  * cpu_baseline.kind "reference" in bench.py).
  */
@@ -36,6 +39,13 @@ int main(int argc, char **argv)
 	sur Sur = {{PML, PML}, {PML, PML}, {PML, PML}};
 	world W = createWorld(Dom, Res, Sur, "");
 	if (W->iNUM != n[0] || W->jNUM != n[1] || W->kNUM != n[2]) { printf("grid mismatch %d %d %d\n", W->iNUM, W->jNUM, W->kNUM); return 1; }
+	double ade_cells = 0;
+	if (argc > 7 && !strcmp(argv[7], "au")) {
+		object Block = {Box, {{lo[0]/2, hi[0]/2}, {lo[1]/2, hi[1]/2}, {lo[2]/2, hi[2]/2}}};
+		putObjects(W, Au, Block, Air);
+		for (int q=0; q<W->CE->N; q++)
+			ade_cells += (double)(W->CE->iMax[q]-W->CE->iMin[q]+1)*(W->CE->jMax[q]-W->CE->jMin[q]+1)*(W->CE->kMax[q]-W->CE->kMin[q]+1);
+	}
 	pointDipole(W, Ez, 0, 0, 0, Pulse, 400, 800, 1);
 	slice XY = createSliceXY(W, 0);
 	double smax = 0;
@@ -46,7 +56,7 @@ int main(int argc, char **argv)
 	acc += get(W, Ez, 0, 0, 50);                      /* device work is complete when this returns */
 	double dt = now() - t0;
 	double cells = (double)n[0]*n[1]*n[2];
-	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g slicemax=%.9g\n", cells, steps, dt, cells*steps/dt*1e-6,
-		omp_get_max_threads(), acc, smax);
+	printf("cells=%.0f steps=%d seconds=%.6f mcells_per_s=%.3f threads=%d probe=%.9g slicemax=%.9g ade_cells=%.0f\n", cells, steps, dt, cells*steps/dt*1e-6,
+		omp_get_max_threads(), acc, smax, ade_cells);
 	return 0;
 }
