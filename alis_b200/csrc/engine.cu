@@ -101,6 +101,9 @@ struct alisb_engine {
 	int resident_ctas;                 /* volume kernel CTAs resident on the whole GPU    */
 	int sm_count, multi_resident[2];   /* SMs; resident CTAs of the two merged PML-shell launch classes */
 	std::vector<SubBox> plan[2];       /* region-specialised volume launches per field set */
+	int tune_wave;                     /* fused stepping in place (kernel yee_wave, no second set of field arrays); ALISB_WAVE */
+	unsigned long long *d_wave_ticket, *d_wave_progress; int *d_wave_error; size_t wave_tiles_cap;
+	unsigned long long wave_ticket_base, wave_epoch;
 	int tune_frows;                    /* rows per CTA of the fused kernel (8 or 16)          */
 	int tune_fchunk;                   /* planes per z-chunk of the fused kernel              */
 	int tune_merge;                    /* PML shell boxes gathered into two merged launches  */
@@ -197,6 +200,8 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	{ const char *gs = getenv("ALISB_GRAPH"); e->graph_ok = gs ? atoi(gs) != 0 : true; }
 	e->srcv_cap = 0; e->srcv_slot = 0;
 	e->d_ade[0] = e->d_ade[1] = 0; e->ade_cfg = 0;
+	e->d_wave_ticket = 0; e->d_wave_progress = 0; e->d_wave_error = 0; e->wave_tiles_cap = 0; e->wave_ticket_base = 0; e->wave_epoch = 0;
+	{ const char *ws = getenv("ALISB_WAVE"); e->tune_wave = ws ? atoi(ws) : 0; }
 	{ const char *as = getenv("ALISB_ADE_FUSE"); e->tune_ade = as ? atoi(as) : 1; }
 	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
@@ -259,6 +264,11 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	CU(cudaFuncSetAttribute(yee_fused<8,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,true>)));
 	CU(cudaFuncSetAttribute(yee_fused<16,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,false>)));
 	CU(cudaFuncSetAttribute(yee_fused<16,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,true>)));
+	CU(cudaFuncSetAttribute(yee_wave<16,false,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<16,false,3>)));
+	CU(cudaFuncSetAttribute(yee_wave<12,false,4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<12,false,4>)));
+	CU(cudaFuncSetAttribute(yee_wave<8,false,4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<8,false,4>)));
+	CU(cudaFuncSetAttribute(yee_wave<16,true,2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<16,true,2>)));
+	CU(cudaFuncSetAttribute(yee_wave<8,true,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<8,true,3>)));
 	for (int cls=0; cls<2; cls++) {
 		int per_sm = 0;
 		if (cls == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yee_multi<1,false,0,false>, 256, 0));
@@ -320,6 +330,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
 	cudaFree(e->scratch); cudaFree(e->d_ade[0]); cudaFree(e->d_ade[1]);
+	cudaFree(e->d_wave_ticket); cudaFree(e->d_wave_progress); cudaFree(e->d_wave_error);
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
 	for (int r=0; r<SRC_RING; r++) { if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]); cudaFree(e->srcv_d[r]); if (e->srcv_ev[r]) cudaEventDestroy(e->srcv_ev[r]); }
 	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
@@ -792,11 +803,13 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		}
 		if (c <= sb0.c1) { SubBox d = sb0; d.c0 = c; d.c1 = sb0.c1; work.push_back({d, sub, false}); }
 	}
+	std::vector<Piece> wave_later;          /* in-place fused pieces: launched after every two-pass piece of this E pass has finished */
 	for (const Piece &pc : work) {
 		sub = pc.sub;
 		SubBox sb = pc.sb;
 		sb.c0 = std::max(sb.c0, e->f_lo); sb.c1 = std::min(sb.c1, e->f_hi);
 		if (sb.c0 > sb.c1) continue;
+		if (pc.fused && e->tune_wave) { Piece q = pc; q.sb = sb; wave_later.push_back(q); continue; }
 		if (pc.fused) {
 			FusedParams fp;
 			memset(&fp, 0, sizeof fp);
@@ -887,6 +900,48 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
 	for (int q=0; q<3; q++) if (used[q]) { CU(cudaEventRecord(e->ev_join[q], e->side[q])); CU(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0)); }
+	/* the in-place wavefront kernel: on the engine's stream, i.e. after all of the above (it reads the E' the
+	 * two-pass E kernels formed on the box's low faces and the old H they left next to it) */
+	for (const Piece &pc : wave_later) {
+		const SubBox &sb = pc.sb;
+		WaveParams wp;
+		memset(&wp, 0, sizeof wp);
+		for (int c=0; c<3; c++) {
+			wp.E[c] = e->F[ALISB_SET_E][m][c]; wp.H[c] = e->F[ALISB_SET_H][m][c];
+			wp.dtdE[c] = e->dtd[ALISB_SET_E][c]; wp.dtdH[c] = e->dtd[ALISB_SET_H][c];
+			wp.C[c] = eps ? e->eps[c] : 0;
+		}
+		wp.ny = e->ny; wp.pitch = e->pitch; wp.plane = e->plane;
+		wp.a_first = sb.a0; wp.a_last = sb.a1; wp.b_first = sb.b0; wp.b_last = sb.b1; wp.c_first = sb.c0; wp.c_last = sb.c1;
+		const int nzs = sb.c1 - sb.c0 + 1;
+		int frows = eps ? (e->tune_frows == 8 ? 8 : 16) : (e->tune_frows == 8 ? 8 : e->tune_frows == 12 ? 12 : 16);
+		wp.cchunk = std::min(nzs, std::max(2, e->tune_fchunk));
+		wp.ntx = div_up(sb.a1 - sb.a0 + 1, 128); wp.nty = div_up(sb.b1 - sb.b0 + 1, frows); wp.ntz = div_up(nzs, wp.cchunk);
+		const size_t ntiles = (size_t)wp.ntx*wp.nty*wp.ntz;
+		if (!e->d_wave_ticket) {
+			CU(cudaMalloc((void**)&e->d_wave_ticket, sizeof(unsigned long long))); CU(cudaMemset(e->d_wave_ticket, 0, sizeof(unsigned long long)));
+			CU(cudaMalloc((void**)&e->d_wave_error, sizeof(int))); CU(cudaMemset(e->d_wave_error, 0, sizeof(int)));
+		}
+		if (ntiles > e->wave_tiles_cap) {
+			CU(cudaStreamSynchronize(e->stream));
+			cudaFree(e->d_wave_progress); e->d_wave_progress = 0; e->wave_tiles_cap = 0;
+			CU(cudaMalloc((void**)&e->d_wave_progress, ntiles*sizeof(unsigned long long)));
+			CU(cudaMemset(e->d_wave_progress, 0, ntiles*sizeof(unsigned long long)));
+			e->wave_tiles_cap = ntiles;
+		}
+		wp.ticket = e->d_wave_ticket; wp.ticket_base = e->wave_ticket_base; wp.progress = e->d_wave_progress;
+		wp.epoch = (++e->wave_epoch) << 20; wp.error = e->d_wave_error;
+		e->wave_ticket_base += ntiles;
+		cudaEvent_t e1 = prof_begin(e->stream, pc.sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
+		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] in-place fused E+H cells %d..%d rows %d..%d planes %d..%d tiles %dx%dx%d of 128x%d cells, %d planes per chunk\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, wp.ntx, wp.nty, wp.ntz, frows, wp.cchunk);
+		const dim3 grid((unsigned)ntiles), block(32, frows + 2, 1);
+		if (eps) { if (frows == 16) yee_wave<16,true,2><<<grid, block, sizeof(WaveSmem<16,true,2>), e->stream>>>(wp); else yee_wave<8,true,3><<<grid, block, sizeof(WaveSmem<8,true,3>), e->stream>>>(wp); }
+		else if (frows == 16) yee_wave<16,false,3><<<grid, block, sizeof(WaveSmem<16,false,3>), e->stream>>>(wp);
+		else if (frows == 12) yee_wave<12,false,4><<<grid, block, sizeof(WaveSmem<12,false,4>), e->stream>>>(wp);
+		else                  yee_wave<8,false,4><<<grid, block, sizeof(WaveSmem<8,false,4>), e->stream>>>(wp);
+		e->launches++; e->fused_launches++;
+		if (e->profiling) CU(cudaEventRecord(e1, e->stream));
+	}
 	CU(cudaGetLastError());
 	return ALISB_OK;
 }
@@ -1257,7 +1312,7 @@ extern "C" int alisb_begin_pass(alisb_engine *e, int set)
 	DEV(e);
 	if (set == ALISB_SET_E) UNFUSE(e);
 	fuse_eval(e);
-	if (e->fuse_ok) TRY(enable_dbuf(e));
+	if (e->fuse_ok && !e->tune_wave) TRY(enable_dbuf(e));
 	open_pass(e, set);
 	return ALISB_OK;
 }
@@ -1272,7 +1327,7 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 		if (set == ALISB_SET_E) {
 			if (e->pendingE >= 0 || (e->h_fused && part != ALISB_PART_REST)) UNFUSE(e);
 			fuse_eval(e);
-			if (e->fuse_ok) TRY(enable_dbuf(e));
+			if (e->fuse_ok && !e->tune_wave) TRY(enable_dbuf(e));
 			bool list_sources = true;
 			for (SrcObj *so : e->src[ALISB_SET_E]) if (so->cnt > 16384) list_sources = false;
 			if (e->fuse_ok && part != ALISB_PART_SEND_PLANE && list_sources && (int)e->src[ALISB_SET_E].size() <= ALISB_MAXSRCOPS) {
@@ -1340,7 +1395,17 @@ extern "C" int alisb_run(alisb_engine *e, int steps)
 	return ALISB_OK;
 }
 
-extern "C" int alisb_synchronize(alisb_engine *e) { DEV(e); SETTLE(e); CU(cudaStreamSynchronize(e->stream)); return ALISB_OK; }
+extern "C" int alisb_synchronize(alisb_engine *e)
+{
+	DEV(e); SETTLE(e);
+	CU(cudaStreamSynchronize(e->stream));
+	if (e->d_wave_error) {
+		int bad = 0;
+		CU(cudaMemcpy(&bad, e->d_wave_error, sizeof bad, cudaMemcpyDeviceToHost));
+		if (bad) return fail(ALISB_ECUDA, "yee_wave: a tile dependency never arrived (fields are invalid)");
+	}
+	return ALISB_OK;
+}
 extern "C" int alisb_get_time(alisb_engine *e, uint64_t *n, float *t, float *tE, float *tH) { if (n) *n = e->step; if (t) *t = e->t; if (tE) *tE = e->tE; if (tH) *tH = e->tH; return ALISB_OK; }
 extern "C" int alisb_set_time(alisb_engine *e, uint64_t n, float t, float tE, float tH) { SETTLE(e); e->step = n; e->t = t; e->tE = tE; e->tH = tH; return ALISB_OK; }
 

@@ -475,8 +475,13 @@ yee_fused(const __grid_constant__ FusedParams p)
 		if (xh) hxp1 = H0[o - 1];
 	}
 	int c = cl;
+	/* the z coefficients are fetched one iteration ahead: a dependent global load at its point of use was the
+	 * largest single stall of this kernel (ncu source page, profiles/r02_ncu_fused_v2_notes.md) */
+	float dze_next = __ldg(p.dtdE[2] + cl), dzh_next = __ldg(p.dtdH[2] + cl + 1);
 	for (int it = 0; c >= cf - 1; ++it, --c) {
 		const size_t o = (size_t)c*p.plane + row;
+		const float dze = dze_next, dzh = dzh_next;
+		if (c > cf - 1) { dze_next = __ldg(p.dtdE[2] + c - 1); dzh_next = __ldg(p.dtdH[2] + c); }
 		cp_async_wait<AHEAD - 1>();                         /* this thread's copies of plane c have landed */
 		__syncthreads();                                    /* ... and everybody else's; iteration it-1 is over everywhere */
 		{                                                   /* plane c-AHEAD goes into the stage iteration it-1 used */
@@ -498,7 +503,6 @@ yee_fused(const __grid_constant__ FusedParams p)
 		/* E'x, E'z of row b-1 at plane c+1, written by the warp below during iteration it-1 */
 		float4 exm = zero4, ezm = zero4;
 		if (wy > 0 && it > 0) { exm = sm.sx[(it - 1) & 1][wy - 1][lane]; ezm = sm.sz[(it - 1) & 1][wy - 1][lane]; }
-		const float dze = __ldg(p.dtdE[2] + c);
 
 		/* ---- E'(c), update.c:110-112 as in yee_body<+1> ---- */
 		float Ex[4] = {ex.x, ex.y, ex.z, ex.w}, Ey[4] = {ey.x, ey.y, ey.z, ey.w}, Ez[4] = {ez.x, ez.y, ez.z, ez.w};
@@ -542,7 +546,6 @@ yee_fused(const __grid_constant__ FusedParams p)
 			if (lane == 0) { eya = eym1; eza = ezm1; }
 			if (own) {
 				const size_t op = o + p.plane;
-				const float dzh = __ldg(p.dtdH[2] + c + 1);
 				float Hx[4] = {hxp.x, hxp.y, hxp.z, hxp.w}, Hy[4] = {hyp.x, hyp.y, hyp.z, hyp.w}, Hz[4] = {hzp.x, hzp.y, hzp.z, hzp.w};
 				const float Gx[4] = {exp_.x, exp_.y, exp_.z, exp_.w}, Gy[4] = {eyp.x, eyp.y, eyp.z, eyp.w}, Gz[4] = {ezp.x, ezp.y, ezp.z, ezp.w};
 				const float Gxn[4] = {exm.x, exm.y, exm.z, exm.w}, Gzn[4] = {ezm.x, ezm.y, ezm.z, ezm.w};
@@ -564,6 +567,291 @@ yee_fused(const __grid_constant__ FusedParams p)
 		exp_ = nex; eyp = ney; ezp = nez;
 		eym1 = eyh; ezm1 = ezh; hxp1 = hxh;
 	}
+}
+
+/*
+ * yee_wave: the fused E+H step IN PLACE (no second set of field arrays), as a dependency wavefront.
+ *
+ * E'(X) reads the OLD H of X and of its +x, +y, +z neighbours; H'(X) reads the NEW E of X and of its
+ * -x, -y, -z neighbours (update.c:110-117).  So a cell depends only on cells that precede it in every
+ * axis: tiles can update their cells in place as long as a tile forms H' of a plane after its -x and -y
+ * neighbour tiles have stored E' of that plane (true dependency; it also guarantees that the neighbour
+ * has read the old H it needs from this tile, so nothing is overwritten too early).  Nothing is
+ * recomputed and nothing is double buffered: every field value is read once and written once per step.
+ *
+ *   - tile = 128 x ROWS cells of an x-y patch, marching DOWN through one z-chunk (planes cl..cf);
+ *   - tiles take their number from a global ticket (z-chunk, then y, then x): every tile a tile waits
+ *     for has a smaller ticket, i.e. is already running or finished -- no deadlock, whatever the
+ *     hardware's block scheduling order;
+ *   - per tile one 64-bit progress word `epoch<<20 | planes stored`, published (fence, then store) by a
+ *     helper warp; a second helper warp polls the -x / -y tiles' words one plane ahead of need and
+ *     fetches their boundary E' (row b0-1: E'x, E'z; column a0-1: E'y, E'z) from L2 into shared memory;
+ *   - the z-chunk below must have stored its top plane before this tile starts (its E' is this tile's
+ *     plane cf-1, and it has then read this tile's old H(cf)); chunks of one column run concurrently;
+ *   - cells outside the fused box are updated by the two-pass kernels: their E pass runs BEFORE this
+ *     kernel (it needs the old H next to the box and provides E' on the box's low faces), their H
+ *     pass after it.
+ * The polls are bounded: a dependency that never arrives sets *error instead of hanging the GPU.
+ * Arithmetic, expression order and operands are those of yee_body<+1> / yee_body<-1>: bit-identical.
+ */
+struct WaveParams {
+	float *E[3], *H[3];
+	const float *dtdE[3], *dtdH[3];   /* x tables shifted by XO                             */
+	const float *C[3];                /* inverse permittivity (EPS variant)                  */
+	int ny, pitch; size_t plane;
+	int a_first, a_last;              /* a_first = 1 mod 4, (a_last - a_first + 1) % 4 == 0  */
+	int b_first, b_last, c_first, c_last, cchunk;
+	int ntx, nty, ntz;
+	unsigned long long *ticket;       /* global counter; this launch owns [ticket_base, ticket_base + ntx*nty*ntz) */
+	unsigned long long ticket_base;
+	unsigned long long *progress;     /* one word per tile                                   */
+	unsigned long long epoch;         /* launch number << 20                                 */
+	int *error;
+};
+
+#define ALISB_WAVE_NH 4              /* boundary-E' slots: the fetch warp runs up to two planes ahead of the workers */
+template <int ROWS, bool EPS, int NST> struct WaveSmem {
+	struct Stage {
+		float4 e[3][ROWS][32];
+		float4 hy[ROWS][32];
+		float4 hx[ROWS+1][32], hz[ROWS+1][32];   /* rows b0 .. b0+ROWS (row b+1 feeds the y differences) */
+		float4 c[EPS ? 3 : 1][EPS ? ROWS : 1][EPS ? 32 : 1];
+		float  edge[ROWS][2];                    /* Hy, Hz of the cell a0+128 (read by the last lane of a row) */
+	} st[NST];
+	float4 sx[2][ROWS][32], sz[2][ROWS][32];     /* E'x, E'z rows of a plane, for the row above   */
+	float4 hrow[ALISB_WAVE_NH][2][32];           /* [slot][E'x, E'z] of row b0-1 (from the -y tile) */
+	float  hcol[ALISB_WAVE_NH][2][ROWS];         /* [slot][E'y, E'z] of column a0-1 (from the -x tile) */
+	unsigned long long ticket;
+	int iter_done;                               /* workers -> helpers: iterations < iter_done are complete */
+	int halo_ready;                              /* fetch warp -> workers: boundary E' of plane indices < halo_ready are in shared memory */
+};
+
+static __device__ __forceinline__ bool wave_wait(const unsigned long long *word, unsigned long long need, int *error)
+{
+	const volatile unsigned long long *w = word;
+	unsigned spins = 0;
+	while (*w < need) {
+		__nanosleep(32);
+		if (*(volatile int*)error) return false;                /* somebody already gave up: do not wait again */
+		if (++spins > (1u << 22)) { atomicExch(error, 1); return false; }    /* seconds: give up rather than hang */
+	}
+	__threadfence();                                       /* acquire: the tile's stores are visible to what follows */
+	return true;
+}
+static __device__ __forceinline__ void smem_wait_ge(const int *word, int need)
+{
+	const volatile int *w = word;
+	while (*w < need) { }
+	__threadfence_block();
+}
+static __device__ __forceinline__ void smem_publish(int *word, int value)
+{
+	__threadfence_block();
+	*(volatile int*)word = value;
+}
+static __device__ __forceinline__ void worker_barrier(int nthreads)
+{
+	asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory");
+}
+
+/* The two helper warps never take part in the workers' per-plane barrier: they talk to them through the
+ * two shared-memory counters above, so a poll of a neighbour tile's progress word or a memory fence
+ * is never on the workers' critical path. */
+template <int ROWS, bool EPS, int NST>
+__global__ void __launch_bounds__(32*(ROWS+2), 1)
+yee_wave(const __grid_constant__ WaveParams p)
+{
+	constexpr int AHEAD = NST - 1, NH = ALISB_WAVE_NH;
+	extern __shared__ __align__(16) unsigned char wave_smem_raw[];
+	WaveSmem<ROWS,EPS,NST> &sm = *reinterpret_cast<WaveSmem<ROWS,EPS,NST>*>(wave_smem_raw);
+	typedef typename WaveSmem<ROWS,EPS,NST>::Stage Stage;
+	const int lane = threadIdx.x, wy = threadIdx.y;
+	const bool worker = wy < ROWS, fetcher = wy == ROWS;
+
+	if (lane == 0 && wy == 0) { sm.ticket = atomicAdd(p.ticket, 1ull) - p.ticket_base; sm.iter_done = 0; sm.halo_ready = 0; }
+	__syncthreads();
+	const unsigned tile = (unsigned)sm.ticket;
+	const int tx = (int)(tile % (unsigned)p.ntx), ty = (int)((tile / (unsigned)p.ntx) % (unsigned)p.nty), tz = (int)(tile / ((unsigned)p.ntx*(unsigned)p.nty));
+	const unsigned long long *prog_x = tx > 0 ? p.progress + tile - 1 : 0;
+	const unsigned long long *prog_y = ty > 0 ? p.progress + tile - p.ntx : 0;
+	const unsigned long long *prog_z = tz > 0 ? p.progress + tile - (unsigned)p.ntx*(unsigned)p.nty : 0;
+
+	const int a0 = p.a_first + 4*(tx*32 + lane);
+	const int b0 = p.b_first + ty*ROWS;
+	const int cf = p.c_first + tz*p.cchunk;
+	const int cl = min(cf + p.cchunk - 1, p.c_last);
+	const int nplanes = cl - cf + 1;
+	float *E0 = p.E[0], *E1 = p.E[1], *E2 = p.E[2];
+	float *H0 = p.H[0], *H1 = p.H[1], *H2 = p.H[2];
+
+	/* the z-chunk below has stored its top plane (= this tile's plane cf-1) and read the old H(cf) */
+	if (fetcher && lane == 0 && prog_z) wave_wait(prog_z, p.epoch + 1, p.error);
+	__syncthreads();
+
+	if (!worker) {
+		if (fetcher) {
+			/* boundary E' of plane index k (plane cl-k) from the -y tile (row b0-1) and the -x tile (column a0-1),
+			 * used by the workers in iteration k+1; the neighbours must have stored k+1 planes */
+			for (int k = 0; k < nplanes; k++) {
+				if (lane == 0) {
+					smem_wait_ge(&sm.iter_done, k - NH + 2);         /* the slot's previous content has been consumed */
+					if (prog_x) wave_wait(prog_x, p.epoch + k + 1, p.error);
+					if (prog_y) wave_wait(prog_y, p.epoch + k + 1, p.error);
+				}
+				__syncwarp();
+				const int c = cl - k, slot = k & (NH - 1);
+				const size_t o = (size_t)c*p.plane + (size_t)(b0 - 1)*p.pitch + ALISB_XO + a0;
+				if (a0 <= p.a_last) { cp_async16(&sm.hrow[slot][0][lane], E0 + o); cp_async16(&sm.hrow[slot][1][lane], E2 + o); }
+				if (lane < ROWS && b0 + lane <= p.b_last) {
+					const size_t q = (size_t)c*p.plane + (size_t)(b0 + lane)*p.pitch + ALISB_XO + (p.a_first + 128*tx) - 1;
+					cp_async4(&sm.hcol[slot][0][lane], E1 + q); cp_async4(&sm.hcol[slot][1][lane], E2 + q);
+				}
+				cp_async_commit();
+				cp_async_wait<1>();                                  /* plane index k-1 has landed (this lane's part) */
+				__syncwarp();
+				if (lane == 0 && k > 0) smem_publish(&sm.halo_ready, k);
+			}
+			cp_async_wait<0>();
+			__syncwarp();
+			if (lane == 0) smem_publish(&sm.halo_ready, nplanes);
+		} else if (lane == 0) {
+			/* every worker stored E' of plane indices < it before the barrier that opened iteration it */
+			for (int it = 1; it <= nplanes; it++) {
+				smem_wait_ge(&sm.iter_done, it);
+				__threadfence();
+				*(volatile unsigned long long*)(p.progress + tile) = p.epoch + (unsigned long long)it;
+			}
+		}
+		return;
+	}
+
+	const int b  = b0 + wy;
+	const bool rowok = b <= p.b_last;
+	const bool act = rowok && a0 <= p.a_last;              /* owns a quad                              */
+	const bool ldg = rowok && a0 <= p.a_last + 1;          /* its H quad feeds the lane before         */
+	const bool xt  = act && lane == 31;                    /* needs H of the cell a0+128               */
+	const bool top = wy == ROWS - 1 || b == p.b_last;      /* nobody stages row b+1 for this warp      */
+	const size_t row = (size_t)b*p.pitch + ALISB_XO + a0;
+	const ptrdiff_t yp = p.pitch;
+
+	/* all loads of plane c into stage s; plane cf-1 only supplies the final E'x, E'y of the chunk below */
+	auto stage_plane = [&](int c, int s) {
+		Stage &S = sm.st[s];
+		const size_t o = (size_t)c*p.plane + row;
+		if (c < cf) { if (act) { cp_async16(&S.e[0][wy][lane], E0 + o); cp_async16(&S.e[1][wy][lane], E1 + o); } return; }
+		if (ldg) { cp_async16(&S.hx[wy][lane], H0 + o); cp_async16(&S.hy[wy][lane], H1 + o); cp_async16(&S.hz[wy][lane], H2 + o); }
+		if (act) {
+			cp_async16(&S.e[0][wy][lane], E0 + o); cp_async16(&S.e[1][wy][lane], E1 + o); cp_async16(&S.e[2][wy][lane], E2 + o);
+			if (top) { cp_async16(&S.hx[wy + 1][lane], H0 + o + yp); cp_async16(&S.hz[wy + 1][lane], H2 + o + yp); }
+			if (EPS) { cp_async16(&S.c[0][wy][lane], p.C[0] + o); cp_async16(&S.c[1][wy][lane], p.C[1] + o); cp_async16(&S.c[2][wy][lane], p.C[2] + o); }
+		}
+		if (xt) { cp_async4(&S.edge[wy][0], H1 + o + 4); cp_async4(&S.edge[wy][1], H2 + o + 4); }
+	};
+
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4 dxe4 = act ? ld4(p.dtdE[0] + ALISB_XO + a0) : zero4;
+	const float4 dxh4 = act ? ld4(p.dtdH[0] + ALISB_XO + a0) : zero4;
+	const float dye = rowok ? __ldg(p.dtdE[1] + b) : 0.f, dyh = rowok ? __ldg(p.dtdH[1] + b) : 0.f;
+	const float DxE[4] = {dxe4.x, dxe4.y, dxe4.z, dxe4.w}, DxH[4] = {dxh4.x, dxh4.y, dxh4.z, dxh4.w};
+
+	/* pipeline prologue: the first AHEAD planes */
+	#pragma unroll
+	for (int q = 0; q < AHEAD; q++) {
+		if (cl - q >= cf - 1) stage_plane(cl - q, q);
+		cp_async_commit();
+	}
+
+	/* carried state of plane c+1 */
+	float4 hxp = zero4, hyp = zero4, hzp = zero4;           /* old H(c+1)                              */
+	float4 exp_ = zero4, eyp = zero4, ezp = zero4;          /* E'(c+1)                                 */
+	if (ldg) {
+		const size_t o = (size_t)(cl + 1)*p.plane + row;
+		hxp = ld4(H0 + o); hyp = ld4(H1 + o);
+	}
+	float dze_next = __ldg(p.dtdE[2] + cl), dzh_next = __ldg(p.dtdH[2] + cl + 1);   /* z coefficients one iteration ahead */
+	int c = cl;
+	for (int it = 0; it <= nplanes; ++it, --c) {
+		const size_t o = (size_t)c*p.plane + row;
+		const float dze = dze_next, dzh = dzh_next;
+		if (it < nplanes) { dze_next = __ldg(p.dtdE[2] + c - 1); dzh_next = __ldg(p.dtdH[2] + c); }
+		cp_async_wait<AHEAD - 1>();                         /* this thread's copies of plane c have landed */
+		worker_barrier(32*ROWS);                            /* ... and every worker's; iteration it-1 is over in all of them */
+		if (wy == 0 && lane == 0) smem_publish(&sm.iter_done, it);
+		{                                                   /* plane c-AHEAD goes into the stage iteration it-1 used */
+			if (c - AHEAD >= cf - 1) stage_plane(c - AHEAD, (it + AHEAD) % NST);
+			cp_async_commit();
+		}
+		const Stage &S = sm.st[it % NST];
+		float4 ex = zero4, ey = zero4, ez = zero4, hx = zero4, hy = zero4, hz = zero4;
+		if (act) { ex = S.e[0][wy][lane]; ey = S.e[1][wy][lane]; }
+		float Ex[4] = {ex.x, ex.y, ex.z, ex.w}, Ey[4] = {ey.x, ey.y, ey.z, ey.w}, Ez[4] = {0.f, 0.f, 0.f, 0.f};
+		float4 nex = ex, ney = ey, nez = zero4;
+		/* E'x, E'z of row b-1 at plane c+1 from the warp below (its iteration it-1) */
+		float4 exm = zero4, ezm = zero4;
+		if (it > 0 && wy > 0) { exm = sm.sx[(it - 1) & 1][wy - 1][lane]; ezm = sm.sz[(it - 1) & 1][wy - 1][lane]; }
+		if (it < nplanes) {
+			/* ---- E'(c), update.c:110-112 as in yee_body<+1> ---- */
+			float4 hxn = zero4, hzn = zero4, cx4 = zero4, cy4 = zero4, cz4 = zero4;
+			if (ldg) { hx = S.hx[wy][lane]; hy = S.hy[wy][lane]; hz = S.hz[wy][lane]; }
+			if (act) {
+				hxn = S.hx[wy + 1][lane]; hzn = S.hz[wy + 1][lane];
+				ez = S.e[2][wy][lane];
+				if (EPS) { cx4 = S.c[0][wy][lane]; cy4 = S.c[1][wy][lane]; cz4 = S.c[2][wy][lane]; }
+			}
+			Ez[0] = ez.x; Ez[1] = ez.y; Ez[2] = ez.z; Ez[3] = ez.w;
+			float hye = __shfl_down_sync(0xffffffffu, hy.x, 1), hze = __shfl_down_sync(0xffffffffu, hz.x, 1);
+			if (xt) { hye = S.edge[wy][0]; hze = S.edge[wy][1]; }
+			const float Hx[4] = {hx.x, hx.y, hx.z, hx.w}, Hy[4] = {hy.x, hy.y, hy.z, hy.w}, Hz[4] = {hz.x, hz.y, hz.z, hz.w};
+			const float Hxn[4] = {hxn.x, hxn.y, hxn.z, hxn.w}, Hzn[4] = {hzn.x, hzn.y, hzn.z, hzn.w};
+			const float Hxp[4] = {hxp.x, hxp.y, hxp.z, hxp.w}, Hyp[4] = {hyp.x, hyp.y, hyp.z, hyp.w};
+			const float hy5[5] = {hy.x, hy.y, hy.z, hy.w, hye}, hz5[5] = {hz.x, hz.y, hz.z, hz.w, hze};
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				const float ux = dze*(Hy[e] - Hyp[e]) + dye*(Hzn[e] - Hz[e]);
+				const float uy = DxE[e]*(hz5[e] - hz5[e+1]) + dze*(Hxp[e] - Hx[e]);
+				const float uz = dye*(Hx[e] - Hxn[e]) + DxE[e]*(hy5[e+1] - hy5[e]);
+				if (EPS) {
+					const float Cx[4] = {cx4.x, cx4.y, cx4.z, cx4.w}, Cy[4] = {cy4.x, cy4.y, cy4.z, cy4.w}, Cz[4] = {cz4.x, cz4.y, cz4.z, cz4.w};
+					Ex[e] += ux*Cx[e]; Ey[e] += uy*Cy[e]; Ez[e] += uz*Cz[e];
+				} else { Ex[e] += ux; Ey[e] += uy; Ez[e] += uz; }
+			}
+			nex = make_float4(Ex[0], Ex[1], Ex[2], Ex[3]); ney = make_float4(Ey[0], Ey[1], Ey[2], Ey[3]); nez = make_float4(Ez[0], Ez[1], Ez[2], Ez[3]);
+			if (act) { st4(E0 + o, nex); st4(E1 + o, ney); st4(E2 + o, nez); }
+			sm.sx[it & 1][wy][lane] = nex; sm.sz[it & 1][wy][lane] = nez;     /* read by the row above in iteration it+1 */
+		}
+
+		/* ---- H'(c+1), update.c:115-117 as in yee_body<-1> ---- */
+		if (it > 0) {
+			/* boundary E' of plane c+1 (plane index it-1) from the neighbour tiles */
+			if (lane == 0) smem_wait_ge(&sm.halo_ready, it);
+			__syncwarp();
+			const int slot = (it - 1) & (NH - 1);
+			if (wy == 0) { exm = sm.hrow[slot][0][lane]; ezm = sm.hrow[slot][1][lane]; }
+			float eya = __shfl_up_sync(0xffffffffu, eyp.w, 1), eza = __shfl_up_sync(0xffffffffu, ezp.w, 1);
+			if (lane == 0) { eya = sm.hcol[slot][0][wy]; eza = sm.hcol[slot][1][wy]; }
+			if (act) {
+				const size_t op = o + p.plane;
+				float Hx[4] = {hxp.x, hxp.y, hxp.z, hxp.w}, Hy[4] = {hyp.x, hyp.y, hyp.z, hyp.w}, Hz[4] = {hzp.x, hzp.y, hzp.z, hzp.w};
+				const float Gx[4] = {exp_.x, exp_.y, exp_.z, exp_.w}, Gy[4] = {eyp.x, eyp.y, eyp.z, eyp.w}, Gz[4] = {ezp.x, ezp.y, ezp.z, ezp.w};
+				const float Gxn[4] = {exm.x, exm.y, exm.z, exm.w}, Gzn[4] = {ezm.x, ezm.y, ezm.z, ezm.w};
+				const float gy5[5] = {eya, eyp.x, eyp.y, eyp.z, eyp.w}, gz5[5] = {eza, ezp.x, ezp.y, ezp.z, ezp.w};
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const float ux = dzh*(Gy[e] - Ey[e]) + dyh*(Gzn[e] - Gz[e]);
+					const float uy = DxH[e]*(gz5[e+1] - gz5[e]) + dzh*(Ex[e] - Gx[e]);
+					const float uz = dyh*(Gx[e] - Gxn[e]) + DxH[e]*(gy5[e] - gy5[e+1]);
+					Hx[e] += ux; Hy[e] += uy; Hz[e] += uz;
+				}
+				st4(H0 + op, make_float4(Hx[0], Hx[1], Hx[2], Hx[3]));
+				st4(H1 + op, make_float4(Hy[0], Hy[1], Hy[2], Hy[3]));
+				st4(H2 + op, make_float4(Hz[0], Hz[1], Hz[2], Hz[3]));
+			}
+		}
+		/* plane c becomes plane c+1 */
+		hxp = hx; hyp = hy; hzp = hz;
+		exp_ = nex; eyp = ney; ezp = nez;
+	}
+	/* the last iteration is complete too: releases the helpers' final waits (nothing reads iter_done beyond nplanes) */
 }
 
 /* one box per launch: the slab-free interior (PM=0) and, with ALISB_MERGE=0, every other box */

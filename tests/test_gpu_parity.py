@@ -248,9 +248,11 @@ def test_chi2_coupling_seeded_bit_exact(oracle_lib, engine_lib, alias):
 
 
 # ---- fused E+H stepping (temporal blocking): must be bit-identical to the two-pass oracle ----------
-@pytest.fixture
-def fusion_env(monkeypatch):
-    """engines created under this fixture fuse whatever they can, however small the grid"""
+@pytest.fixture(params=[0, 1], ids=["out-of-place", "in-place-wavefront"])
+def fusion_env(monkeypatch, request):
+    """engines created under this fixture fuse whatever they can, however small the grid; both fused
+    kernels: yee_fused (double-buffered fields, halo recomputed) and yee_wave (in place, tile wavefront)"""
+    monkeypatch.setenv("ALISB_WAVE", str(request.param))
     monkeypatch.setenv("ALISB_FUSE", "1")
     monkeypatch.setenv("ALISB_FUSE_MIN", "1")
     monkeypatch.setenv("ALISB_SMALL", "1")
