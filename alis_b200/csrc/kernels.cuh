@@ -626,28 +626,35 @@ template <int ROWS, bool EPS, int NST> struct WaveSmem {
 	int halo_ready;                              /* fetch warp -> workers: boundary E' of plane indices < halo_ready are in shared memory */
 };
 
-static __device__ __forceinline__ bool wave_wait(const unsigned long long *word, unsigned long long need, int *error)
+/* progress words: release store by the publishing tile's helper, acquire load by the polling one (the stores
+ * of the publishing tile's workers reach the helper through the shared-memory counter below, released and
+ * acquired at CTA scope: causality order is cumulative).  Returns the value seen (>= need), or 0 after giving up. */
+static __device__ __forceinline__ unsigned long long wave_wait(const unsigned long long *word, unsigned long long need, int *error)
 {
-	const volatile unsigned long long *w = word;
 	unsigned spins = 0;
-	while (*w < need) {
-		__nanosleep(32);
-		if (*(volatile int*)error) return false;                /* somebody already gave up: do not wait again */
-		if (++spins > (1u << 22)) { atomicExch(error, 1); return false; }    /* seconds: give up rather than hang */
+	for (;;) {
+		unsigned long long v;
+		asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+		if (v >= need) return v;
+		__nanosleep(20);
+		if ((++spins & 1023u) == 0 && *(volatile int*)error) return 0;       /* somebody already gave up: do not wait again */
+		if (spins > (1u << 22)) { atomicExch(error, 1); return 0; }          /* seconds: give up rather than hang */
 	}
-	__threadfence();                                       /* acquire: the tile's stores are visible to what follows */
-	return true;
+}
+static __device__ __forceinline__ void wave_publish(unsigned long long *word, unsigned long long v)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(word), "l"(v) : "memory");
 }
 static __device__ __forceinline__ void smem_wait_ge(const int *word, int need)
 {
-	const volatile int *w = word;
-	while (*w < need) { }
-	__threadfence_block();
+	const unsigned a = (unsigned)__cvta_generic_to_shared(word);
+	int v;
+	do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); } while (v < need);
 }
 static __device__ __forceinline__ void smem_publish(int *word, int value)
 {
-	__threadfence_block();
-	*(volatile int*)word = value;
+	const unsigned a = (unsigned)__cvta_generic_to_shared(word);
+	asm volatile("st.release.cta.shared.s32 [%0], %1;" :: "r"(a), "r"(value) : "memory");
 }
 static __device__ __forceinline__ void worker_barrier(int nthreads)
 {
@@ -685,18 +692,21 @@ yee_wave(const __grid_constant__ WaveParams p)
 	float *H0 = p.H[0], *H1 = p.H[1], *H2 = p.H[2];
 
 	/* the z-chunk below has stored its top plane (= this tile's plane cf-1) and read the old H(cf) */
-	if (fetcher && lane == 0 && prog_z) wave_wait(prog_z, p.epoch + 1, p.error);
+	if (fetcher && lane == 0 && prog_z) (void)wave_wait(prog_z, p.epoch + 1, p.error);
 	__syncthreads();
 
 	if (!worker) {
 		if (fetcher) {
 			/* boundary E' of plane index k (plane cl-k) from the -y tile (row b0-1) and the -x tile (column a0-1),
 			 * used by the workers in iteration k+1; the neighbours must have stored k+1 planes */
+			/* a poll returns how far the neighbour has come: usually several planes ahead, so most planes need no poll */
+			unsigned long long known_x = 0, known_y = 0;
 			for (int k = 0; k < nplanes; k++) {
 				if (lane == 0) {
 					smem_wait_ge(&sm.iter_done, k - NH + 2);         /* the slot's previous content has been consumed */
-					if (prog_x) wave_wait(prog_x, p.epoch + k + 1, p.error);
-					if (prog_y) wave_wait(prog_y, p.epoch + k + 1, p.error);
+					const unsigned long long need = p.epoch + (unsigned long long)k + 1;
+					if (prog_x && known_x < need) known_x = wave_wait(prog_x, need, p.error);
+					if (prog_y && known_y < need) known_y = wave_wait(prog_y, need, p.error);
 				}
 				__syncwarp();
 				const int c = cl - k, slot = k & (NH - 1);
@@ -707,19 +717,15 @@ yee_wave(const __grid_constant__ WaveParams p)
 					cp_async4(&sm.hcol[slot][0][lane], E1 + q); cp_async4(&sm.hcol[slot][1][lane], E2 + q);
 				}
 				cp_async_commit();
-				cp_async_wait<1>();                                  /* plane index k-1 has landed (this lane's part) */
+				cp_async_wait<0>();                                  /* an L2 round trip; the fetch warp runs up to two planes ahead of the workers */
 				__syncwarp();
-				if (lane == 0 && k > 0) smem_publish(&sm.halo_ready, k);
+				if (lane == 0) smem_publish(&sm.halo_ready, k + 1);
 			}
-			cp_async_wait<0>();
-			__syncwarp();
-			if (lane == 0) smem_publish(&sm.halo_ready, nplanes);
 		} else if (lane == 0) {
 			/* every worker stored E' of plane indices < it before the barrier that opened iteration it */
 			for (int it = 1; it <= nplanes; it++) {
 				smem_wait_ge(&sm.iter_done, it);
-				__threadfence();
-				*(volatile unsigned long long*)(p.progress + tile) = p.epoch + (unsigned long long)it;
+				wave_publish(p.progress + tile, p.epoch + (unsigned long long)it);
 			}
 		}
 		return;

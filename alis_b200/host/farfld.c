@@ -587,6 +587,7 @@ float complex farField(phaser P, tfield pol(phaser,float,float), float theta, fl
 
 float farFieldI(phaser P, tfield pol(phaser,float,float), float theta, float phi)
 {
+	ALIS_PROF("farFieldI");
 	if (pol == Unpol) return farFieldI(P, Ppol, theta, phi) + farFieldI(P, Spol, theta, phi);
 	float complex f = farField(P, pol, theta, phi);
 	return conjf(f) * f;
@@ -606,6 +607,7 @@ static void far_field_pairs(phaser P, int n, const float *theta, const float *ph
 /* ---- angular maps and cuts (reference farfld.c:525-662) -------------------------------------------------------- */
 void farFieldProfile(world W, phaser P, projmap projMap, int X, int Y, ...)
 {
+	ALIS_PROF("farFieldProfile");
 	char *format, fieldname[8] = "", filename[1024], fullname[1024];   /* png() looks at F[4] */
 	va_list ap;
 	va_start(ap, Y);
@@ -671,6 +673,7 @@ void farFieldProfile(world W, phaser P, projmap projMap, int X, int Y, ...)
 
 void farFieldTheta(world W, phaser P, float phi, char *format, ...)
 {
+	ALIS_PROF("farFieldTheta");
 	char filename[1024];
 	va_list ap;
 	va_start(ap, format);
@@ -686,6 +689,7 @@ void farFieldTheta(world W, phaser P, float phi, char *format, ...)
 
 void farFieldPhi(world W, phaser P, float theta, char *format, ...)
 {
+	ALIS_PROF("farFieldPhi");
 	char filename[1024];
 	va_list ap;
 	va_start(ap, format);
@@ -703,6 +707,7 @@ void farFieldPhi(world W, phaser P, float theta, char *format, ...)
  * width delta with 6 n samples on ring n (capped at 60 degrees) */
 float (farFieldFlux)(phaser P, tfield pol(phaser,float,float), float theta, float phi, float aMin, float aMax, float delta, ...)
 {
+	ALIS_PROF("farFieldFlux");
 	if (!delta) delta=1;
 	if (!aMax) aMax=aMin, aMin=0;
 

@@ -52,4 +52,14 @@ int    alis_device_absmax(world W, field F, const int box[6], float *out);      
 int    alis_device_column_sums(world W, field F, const int box[6], float *cols);    /* 0: use the host path */
 alisb_phaser *alis_phaser_device(phaser P, int *freq);   /* device accumulators + frequency index of P */
 
+
+/* ALIS_PROFILE=1: inclusive wall time and call count of the public entry points, printed at exit (stderr).
+ * Off (one predictable branch per call) otherwise. */
+int    alis_prof_enabled(void);
+double alis_prof_now(void);
+void   alis_prof_add(const char *name, double seconds);
+typedef struct { const char *name; double t0; } alis_prof_scope;
+static inline void alis_prof_end(alis_prof_scope *s) { if (s->name) alis_prof_add(s->name, alis_prof_now() - s->t0); }
+#define ALIS_PROF(label) alis_prof_scope alis_prof_scope_ __attribute__((cleanup(alis_prof_end))) = { alis_prof_enabled() ? (label) : 0, alis_prof_enabled() ? alis_prof_now() : 0 }
+
 #endif

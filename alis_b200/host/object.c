@@ -561,6 +561,7 @@ void putObjectArray(world W, matter *M, object *O)
  * (reference object.c:408-429) */
 void (putObjects)(world W, ...)
 {
+	ALIS_PROF("putObjects");
 	int N = 0;
 	va_list ap;
 	matter *M;

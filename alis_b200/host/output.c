@@ -55,12 +55,14 @@ static entry *lookup(world W, char *name, entry **list)
 /* ---- probes ------------------------------------------------------------------------------------------ */
 float get(world W, field F, float x, float y, float z)
 {
+	ALIS_PROF("get");
 	return F(W, W->xtoi(W, x), W->ytoj(W, y), W->ztok(W, z));
 }
 
 /* reference output.c:56-74 */
 float worldMax(world W, field F)
 {
+	ALIS_PROF("worldMax");
 	float best = 0, f;
 	const int box[6] = { W->iMin, W->iMax-1, W->jMin, W->jMax-1, W->kMin, W->kMax-1 };
 	if (alis_device_absmax(W, F, box, &best)) return best;              /* reduced on the device: one number comes back */
@@ -103,6 +105,7 @@ static float sheet_sum_cols(world W, const float *cols, int i)
 
 float worldSum(world W, field F)
 {
+	ALIS_PROF("worldSum");
 	float Sum = 0;
 	const int box[6] = { W->iMin, W->iMax, W->jMin, W->jMax, W->kMin, W->kMax };
 	float *cols = xmalloc(sizeof(float)*(size_t)(W->iMax-W->iMin+1)*(W->jMax-W->jMin+1));
@@ -179,6 +182,7 @@ void (writeRow)(world W, char *format, ...)
  * (reference output.c:177-230). */
 void (writeSpectrum)(world W, int N, float LMin, float LMax, char *format, ...)
 {
+	ALIS_PROF("writeSpectrum");
 	static entry *spectra;
 	char filename[1024];
 	double d;
@@ -324,6 +328,7 @@ float (poyntingZ)(world W, float z, float xMin, float xMax, float yMin, float yM
  * (reference output.c:335-362).  All faces go to the device in one request. */
 float poyntingOut(world W, float xMin, float xMax, float yMin, float yMax, float zMin, float zMax)
 {
+	ALIS_PROF("poyntingOut");
 	const float lo[3] = { xMin, yMin, zMin }, hi[3] = { xMax, yMax, zMax };
 	const float wlo[3] = { W->xMin, W->yMin, W->zMin }, whi[3] = { W->xMax, W->yMax, W->zMax };
 	const int sur[3] = { W->xMinSur, W->yMinSur, W->zMinSur };
@@ -422,6 +427,7 @@ static float column_absorption(const abs_cols *A, int i, int j, float x, float y
 
 float objectAbsorption(world W, object O)
 {
+	ALIS_PROF("objectAbsorption");
 	coeffs *C = W->CE;
 	float Sum = 0;
 	int n = 0;

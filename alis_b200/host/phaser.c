@@ -257,6 +257,7 @@ phaser choosePhaser(phaser P, float wavelength)
 /* reference phaser.c:94-110: one accumulation of every frequency from P to the end of its list */
 void updatePhaser(world W, phaser P)
 {
+	ALIS_PROF("updatePhaser");
 	phaser B = base_of(P);
 	if (!B->b200_dev) return;
 	const int count = B->b200_count;

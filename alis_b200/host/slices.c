@@ -258,6 +258,7 @@ static void write_png_rgb(FILE *f, int width, int height, const unsigned char *r
  * field plots.  cmap[0] = number of colour stops, negative for maps symmetric about zero. */
 void (png)(world W, slice S, float Max, char *F, char *filename, unsigned long int* cmap)
 {
+	ALIS_PROF("png writer");
 	int d = 0, dim[3] = {1,1,1};
 	FILE *File = fopen(strcat(filename, ".png"), "wb");
 	if (!File) { printf("alis-b200: cannot open %s\n", filename); exit(0); }
@@ -331,6 +332,7 @@ static float sample(world W, field F, slice S, float ***dst)
  * frame, max < 0 auto-scale lagging by -max periods (reference slices.c:242-279) */
 void (sliceSnap)(world W, field F, slice S, char *f, char *s, ...)
 {
+	ALIS_PROF("sliceSnap");
 	static sentry *list;
 	char *format, string[1024], filename[1024];
 	va_list ap;
@@ -363,6 +365,7 @@ void (sliceSnap)(world W, field F, slice S, char *f, char *s, ...)
 /* average over N calls (reference slices.c:282-323) */
 void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 {
+	ALIS_PROF("sliceTimeAvg");
 	static sentry *list;
 	char *format, string[1024], filename[1024];
 	va_list ap;
@@ -401,6 +404,7 @@ void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 /* running DFT at wavelength L over N calls, written as 12 phase frames (reference slices.c:326-379) */
 void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L, ...)
 {
+	ALIS_PROF("sliceFreqDom");
 	field *linear[30] = {Ex, Ey, Ez, Hx, Hy, Hz, iEx, iEy, iEz, iHx, iHy, iHz, rawEx, rawEy, rawEz, rawHx, rawHy, rawHz,
 	                     Jx, Jy, Jz, rawJx, rawJy, rawJz, ScEx, ScEy, ScEz, SoEx, SoEy, SoEz};
 	int known = 0;
@@ -455,6 +459,7 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 /* ---- reductions over a slice (reference slices.c:382-427) ------------------------------------------------------ */
 float sliceMax(world W, field F, slice S)
 {
+	ALIS_PROF("sliceMax");
 	float best = 0, f;
 	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
 	if (alis_device_absmax(W, F, box, &best)) return best;
@@ -496,6 +501,7 @@ static float sheet_sum_cols(world W, slice S, const float *cols, int i)
 
 float sliceSum(world W, field F, slice S)
 {
+	ALIS_PROF("sliceSum");
 	float Sum = 0;
 	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
 	float *cols = xmalloc(sizeof(float)*(size_t)(S->iMax-S->iMin+1)*(S->jMax-S->jMin+1));

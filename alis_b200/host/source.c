@@ -118,6 +118,7 @@ static void refresh_period(world W, float wavelength)
 /* ---- point dipole (reference source.c:78-124) ---------------------------------------------------- */
 void (pointDipole)(world W, field F, float x, float y, float z, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...)
 {
+	ALIS_PROF("pointDipole");
 	int i = W->xtoi(W, x), j = W->ytoj(W, y), k = W->ztok(W, z);
 	set_mirror_parity(W, F, i, j, k);
 
@@ -275,6 +276,7 @@ static void snap_box_axis(world W, int a, int mirrored, float want_lo, float wan
 
 tfsf (createTFSF)(world W, dom DOM, sur SUR)
 {
+	ALIS_PROF("createTFSF");
 	tfsf S;
 	MALLOC(S, 0, 1);
 	tfsf *tail = &W->S;
@@ -393,6 +395,7 @@ static void plane_sources(world W, tfield pol(phaser,float,float), float theta, 
 /* reference source.c:414-432 */
 void (planewave)(world W, dom Dom, tfield pol(phaser,float,float), float theta, float phi, waveform waveForm, float wavelength, float supplement, float amplitude, float phase, ...)
 {
+	ALIS_PROF("planewave");
 	while (theta < 0) theta += 360;
 	while (theta >= 360) theta -= 360;
 	while (phi < 0) phi += 360;

@@ -28,7 +28,7 @@ void alis_host_attach(world W) { W->b200_bridge = 0; W->b200_view = 0; }
 
 alis_bridge *alis_host_bridge(world W)
 {
-	if (!W->b200_bridge) W->b200_bridge = alis_bridge_create(W);
+	if (!W->b200_bridge) { ALIS_PROF("engine create (CUDA init)"); W->b200_bridge = alis_bridge_create(W); }
 	return (alis_bridge*)W->b200_bridge;
 }
 
@@ -49,14 +49,45 @@ void alis_host_reset_fields(world W)
 	alis_host_touch(W);
 }
 
+/* ---- ALIS_PROFILE=1 ------------------------------------------------------------------------------------- */
+#include <sys/time.h>
+static struct { const char *name; double s; long n; } prof_tab[64];
+static int prof_n, prof_mode = -1;
+static double prof_start;
+double alis_prof_now(void) { struct timeval t; gettimeofday(&t, 0); return t.tv_sec + 1e-6*t.tv_usec; }
+static void prof_report(void)
+{
+	fprintf(stderr, "[alis-b200 profile] %-28s %10s %10s\n", "entry point (inclusive)", "calls", "seconds");
+	for (int q=0; q<prof_n; q++) fprintf(stderr, "[alis-b200 profile] %-28s %10ld %10.4f\n", prof_tab[q].name, prof_tab[q].n, prof_tab[q].s);
+	fprintf(stderr, "[alis-b200 profile] %-28s %10s %10.4f\n", "since first profiled call", "", alis_prof_now() - prof_start);
+}
+int alis_prof_enabled(void)
+{
+	if (prof_mode < 0) {
+		const char *e = getenv("ALIS_PROFILE");
+		prof_mode = e && atoi(e) ? 1 : 0;
+		if (prof_mode) { prof_start = alis_prof_now(); atexit(prof_report); }
+	}
+	return prof_mode;
+}
+void alis_prof_add(const char *name, double seconds)
+{
+	int q = 0;
+	while (q < prof_n && prof_tab[q].name != name && strcmp(prof_tab[q].name, name)) q++;
+	if (q == prof_n) { if (prof_n == 64) return; prof_tab[prof_n++].name = name; }
+	prof_tab[q].s += seconds; prof_tab[q].n++;
+}
+
 void updateE(world W)
 {
+	ALIS_PROF("updateE");
 	alis_bridge_step_E(alis_host_bridge(W));
 	alis_host_touch(W);
 }
 
 void updateH(world W)
 {
+	ALIS_PROF("updateH");
 	alis_bridge_step_H(alis_host_bridge(W));
 	alis_host_touch(W);
 }

@@ -269,6 +269,7 @@ static world new_world(res R, dom D, sur S)
 /* reference world.c:261-280 */
 world createWorld(dom D, res R, sur S, char *format, ...)
 {
+	ALIS_PROF("createWorld");
 	va_list ap;
 	world W = new_world(R, D, S);
 
