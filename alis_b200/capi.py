@@ -110,6 +110,11 @@ def _declare(lib):
         "alisb_set_spacing": (i, [vp, i, i, f32p]),
         "alisb_plane_flux": (i, [vp, C.c_void_p, i, C.POINTER(C.c_double)]),
         "alisb_eval_box": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
+        "alisb_accum_create": (i, [vp, C.POINTER(FieldFn), i32p, i, C.POINTER(vp)]),
+        "alisb_accum_add": (i, [vp, f, f]),
+        "alisb_accum_read": (i, [vp, f32p, f32p]),
+        "alisb_accum_clear": (i, [vp]),
+        "alisb_accum_destroy": (None, [vp]),
         "alisb_reduce_absmax": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_column_sums": (i, [vp, C.POINTER(FieldFn), i32p, f32p]),
         "alisb_absorption_columns": (i, [vp, i, i32p, f32p]),
@@ -339,6 +344,10 @@ class Engine:
         self._ck(self.lib.alisb_eval_box(self.h, C.byref(f), _ip(ibox), _fp(out)))
         return out
 
+    def accum(self, f, ibox, with_imag=True):
+        """running sums of field function f over the INDEX box kept by the engine (sliceTimeAvg / sliceFreqDom)"""
+        return Accum(self, f, ibox, with_imag)
+
     def reduce_absmax(self, f, ibox):
         out = np.zeros(1, np.float32)
         self._ck(self.lib.alisb_reduce_absmax(self.h, C.byref(f), _ip(ibox), _fp(out)))
@@ -384,6 +393,30 @@ class Engine:
 
     def halo_unpack(self, set_):
         self._ck(self.lib.alisb_halo_unpack(self.h, set_))
+
+
+class Accum:
+    def __init__(self, eng, f, ibox, with_imag):
+        self.eng, self.shape, self.with_imag = eng, (ibox[1] - ibox[0] + 1, ibox[3] - ibox[2] + 1, ibox[5] - ibox[4] + 1), with_imag
+        self.h = C.c_void_p()
+        eng._ck(eng.lib.alisb_accum_create(eng.h, C.byref(f), _ip(ibox), int(with_imag), C.byref(self.h)))
+
+    def add(self, wr, wi=0.0):
+        self.eng._ck(self.eng.lib.alisb_accum_add(self.h, wr, wi))
+
+    def read(self):
+        re = np.empty(self.shape, np.float32)
+        im = np.empty(self.shape, np.float32) if self.with_imag else None
+        self.eng._ck(self.eng.lib.alisb_accum_read(self.h, _fp(re), _fp(im) if self.with_imag else None))
+        return re, im
+
+    def clear(self):
+        self.eng._ck(self.eng.lib.alisb_accum_clear(self.h))
+
+    def close(self):
+        if self.h:
+            self.eng.lib.alisb_accum_destroy(self.h)
+            self.h = None
 
 
 class Phaser:

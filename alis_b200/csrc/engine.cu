@@ -20,6 +20,7 @@
 #include <limits.h>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include <nvtx3/nvToolsExt.h>      /* header-only NVTX 3: ranges cost a few ns when no tool is attached */
 #include "alis_b200.h"
 #include "kernels.cuh"
@@ -179,11 +180,23 @@ static void to_xfast(const float *zf, float *xf, const Box &B)
 extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 {
 	if (!g || !out || g->nx < 1 || g->ny < 1 || g->nz < 1) return fail(ALISB_EINVAL, "bad grid");
+	/* ALISB_DEBUG=2: where the start-up time goes */
+	const bool trace = getenv("ALISB_DEBUG") && atoi(getenv("ALISB_DEBUG")) >= 2;
+	auto t_last = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!trace) return;
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[alisb] create: %-34s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
 	int ndev = 0;
 	cudaError_t ce = cudaGetDeviceCount(&ndev);
 	if (ce != cudaSuccess || ndev < 1) return fail(ALISB_ECUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(ce));
 	if (g->device < 0 || g->device >= ndev) return fail(ALISB_EINVAL, "device %d out of range (%d devices)", g->device, ndev);
+	lap("cudaGetDeviceCount (driver init)");
 	CU(cudaSetDevice(g->device));
+	CU(cudaFree(0));
+	lap("cudaSetDevice + context");
 	alisb_engine *e = new alisb_engine();
 	e->g = *g; e->nx = g->nx; e->ny = g->ny; e->nz = g->nz;
 	e->pitch = ((ALISB_XO + g->nx + 2) + 31)/32*32;
@@ -234,8 +247,10 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 			}
 		}
 	}
+	lap("stream + field/psi/table allocation");
 	int nb = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yee_volume<1,false,7,32,false>, 256, 0));
+	lap("first kernel query (module load)");
 	{
 		const char *s;
 		e->tune_bx = 1; e->tune_by = 8; e->tune_stream = 0; e->tune_waves = 100000; e->tune_minchunk = 8;   /* measured: profiles/sweep2_r01, sweep3_r01 */
@@ -275,6 +290,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		else          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yee_multi<1,false,1,false>, 256, 0));
 		e->multi_resident[cls] = std::max(1, per_sm)*prop.multiProcessorCount;
 	}
+	lap("side streams, attributes, occupancy");
 	*out = e;
 	return ALISB_OK;
 }
@@ -768,7 +784,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	const bool conc = e->tune_conc > 0 && e->plan[set].size() > 2;
 	const bool merge = e->tune_merge && e->plan[set].size() > 2 && e->tune_bx == 1 && e->tune_by == 8;
 	MultiParams mp[2];
-	unsigned mcta[2] = {0, 0}; double mcells[2] = {0, 0}, mplanes[2] = {0, 0};
+	unsigned mcta[2] = {0, 0}; double mcells[2] = {0, 0}, mplanes[2] = {0, 0}; bool made[2] = {false, false};
 	if (merge) for (int q=0; q<2; q++) { mp[q].v = p; mp[q].nreg = 0; }
 	if (conc && e->tune_conc == 2) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
 	auto side_stream = [&](bool first_alone) -> cudaStream_t {
@@ -789,19 +805,56 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	/* the fused box: in the E pass its clean z ranges run the fused E+H kernel (when the pass is
 	 * issued as the fused variant), in the following H pass they are skipped; its other planes and
 	 * every other box run the two-pass kernel */
-	struct Piece { SubBox sb; int sub; bool fused; };
+	struct Piece { SubBox sb; int sub; bool fused; bool ade; };
 	std::vector<Piece> work;
 	for (const SubBox &sb0 : e->plan[set]) {
 		sub++;
 		const bool skipz = sb0.fusable && e->fuse_ok && ((set == ALISB_SET_E && e->fusing) || (set == ALISB_SET_H && e->h_fused));
-		if (!skipz) { work.push_back({sb0, sub, false}); continue; }
+		if (!skipz) { work.push_back({sb0, sub, false, ade}); continue; }
 		int c = sb0.c0;
 		for (const std::pair<int,int> &z : e->fuse_z) {
-			if (z.first > c) { SubBox d = sb0; d.c0 = c; d.c1 = z.first - 1; work.push_back({d, sub, false}); }
-			if (set == ALISB_SET_E) { SubBox d = sb0; d.c0 = z.first; d.c1 = z.second; work.push_back({d, sub, true}); }
+			if (z.first > c) { SubBox d = sb0; d.c0 = c; d.c1 = z.first - 1; work.push_back({d, sub, false, ade}); }
+			if (set == ALISB_SET_E) { SubBox d = sb0; d.c0 = z.first; d.c1 = z.second; work.push_back({d, sub, true, false}); }
 			c = z.second + 1;
 		}
-		if (c <= sb0.c1) { SubBox d = sb0; d.c0 = c; d.c1 = sb0.c1; work.push_back({d, sub, false}); }
+		if (c <= sb0.c1) { SubBox d = sb0; d.c0 = c; d.c1 = sb0.c1; work.push_back({d, sub, false, ade}); }
+	}
+	if (ade) {
+		/* The ADE variants carry the object code (and its registers: fewer resident CTAs).  Only the part of a
+		 * box that can hold object cells runs them: a box is cut around the bounding box of the objects it
+		 * meets (x cuts on 32-cell groups), everything else runs the plain variant.  Launch-bound grids keep
+		 * their single launch. */
+		const bool split = (long)e->nx*e->ny*e->nz >= e->tune_small;
+		std::vector<Piece> cut;
+		for (const Piece &pc : work) {
+			if (pc.fused) { cut.push_back(pc); continue; }
+			const SubBox &b = pc.sb;
+			int u[6] = { INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN };
+			for (const DispObj *o : e->obj) {
+				const int lo[3] = { std::max(b.a0, o->upd.a0), std::max(b.b0, o->upd.b0), std::max(b.c0, o->upd.c0) };
+				const int hi[3] = { std::min(b.a1, o->upd.a0 + o->upd.na - 1), std::min(b.b1, o->upd.b0 + o->upd.nb - 1), std::min(b.c1, o->upd.c0 + o->upd.nc - 1) };
+				if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) continue;
+				for (int q=0; q<3; q++) { u[2*q] = std::min(u[2*q], lo[q]); u[2*q+1] = std::max(u[2*q+1], hi[q]); }
+			}
+			Piece q = pc;
+			if (u[0] > u[1]) { q.ade = false; cut.push_back(q); continue; }
+			if (!split) { cut.push_back(q); continue; }
+			u[0] = std::max(b.a0, (u[0] - 1)/32*32 + 1); u[1] = std::min(b.a1, (u[1] - 1)/32*32 + 32);
+			auto piece = [&](int a0, int a1, int b0, int b1, int c0, int c1, bool with_ade) {
+				if (a0 > a1 || b0 > b1 || c0 > c1) return;
+				Piece r = pc; r.ade = with_ade;
+				r.sb.a0 = a0; r.sb.a1 = a1; r.sb.b0 = b0; r.sb.b1 = b1; r.sb.c0 = c0; r.sb.c1 = c1;
+				cut.push_back(r);
+			};
+			piece(u[0], u[1], u[2], u[3], u[4], u[5], true);
+			piece(b.a0, b.a1, b.b0, b.b1, b.c0, u[4] - 1, false);
+			piece(b.a0, b.a1, b.b0, b.b1, u[5] + 1, b.c1, false);
+			piece(b.a0, b.a1, b.b0, u[2] - 1, u[4], u[5], false);
+			piece(b.a0, b.a1, u[3] + 1, b.b1, u[4], u[5], false);
+			piece(b.a0, u[0] - 1, u[2], u[3], u[4], u[5], false);
+			piece(u[1] + 1, b.a1, u[2], u[3], u[4], u[5], false);
+		}
+		work.swap(cut);
 	}
 	std::vector<Piece> wave_later;          /* in-place fused pieces: launched after every two-pass piece of this E pass has finished */
 	for (const Piece &pc : work) {
@@ -869,14 +922,15 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			const int cls = (sb.pml == 1 || sb.pml == 2 || sb.pml == 4) ? 0 : 1;
 			mp[cls].r[mp[cls].nreg++] = r;
 			mcells[cls] += cells; mplanes[cls] += (double)tiles*nzs;
+			if (pc.ade) made[cls] = true;
 			continue;
 		}
 		cudaStream_t st = side_stream(true);
 		nlaunched++;
 		cudaEvent_t e1 = prof_begin(st, sub, cells);
 		dim3 grid(gx, gy, nchunks), block(32*bx, by, 1);
-		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, r, grid, block, eps, ade);
-		else                    launch_volume_t<-1>(st, p, r, grid, block, false, ade);
+		if (set == ALISB_SET_E) launch_volume_t<1>(st, p, r, grid, block, eps, pc.ade);
+		else                    launch_volume_t<-1>(st, p, r, grid, block, false, pc.ade);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
@@ -895,7 +949,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		cudaStream_t st = side_stream(true);
 		nlaunched++;
 		cudaEvent_t e1 = prof_begin(st, -2 - cls, mcells[cls]);
-		launch_multi(st, mp[cls], mcta[cls], cls, set, eps, ade);
+		launch_multi(st, mp[cls], mcta[cls], cls, set, eps, made[cls]);
 		e->launches++;
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
@@ -1675,6 +1729,69 @@ extern "C" int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const in
 	CU(cudaStreamSynchronize(e->stream));
 	e->launches++;
 	return ALISB_OK;
+}
+
+struct alisb_accum { alisb_engine *e; alisb_field_fn f; int32_t ibox[6]; size_t n; float *re, *im; };
+
+extern "C" int alisb_accum_create(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], int with_imag, alisb_accum **out)
+{
+	if (!e || !out) return fail(ALISB_EINVAL, "accum: null argument");
+	DEV(e);
+	EvalParams p;
+	TRY(eval_setup(e, f, ibox, false, p));
+	alisb_accum *a = new alisb_accum();
+	a->e = e; a->f = *f; memcpy(a->ibox, ibox, sizeof a->ibox); a->n = (size_t)p.ni*p.nj*p.nk; a->re = a->im = 0;
+	int rc = dalloc(&a->re, a->n);
+	if (rc == ALISB_OK && with_imag) rc = dalloc(&a->im, a->n);
+	if (rc != ALISB_OK) { cudaFree(a->re); cudaFree(a->im); delete a; return rc; }
+	*out = a;
+	return ALISB_OK;
+}
+
+extern "C" int alisb_accum_add(alisb_accum *a, float wr, float wi)
+{
+	if (!a) return fail(ALISB_EINVAL, "accum: null argument");
+	NvtxRange range("alisb:accum_add");
+	alisb_engine *e = a->e;
+	DEV(e);
+	EvalParams p;
+	TRY(eval_setup(e, &a->f, a->ibox, false, p));          /* the field pointers may have changed (double-buffered passes) */
+	SETTLE(e);
+	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) for (int c=0; c<3; c++) p.F[s][m][c] = e->F[s][m][c];
+	eval_accumulate<<<div_up(a->n, 256), 256, 0, e->stream>>>(p, a->re, a->im, wr, wi);
+	CU(cudaGetLastError());
+	e->launches++;
+	return ALISB_OK;
+}
+
+extern "C" int alisb_accum_read(alisb_accum *a, float *re, float *im)
+{
+	if (!a || !re || (im && !a->im)) return fail(ALISB_EINVAL, "accum: bad read");
+	alisb_engine *e = a->e;
+	DEV(e);
+	CU(cudaMemcpyAsync(re, a->re, a->n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	if (im) CU(cudaMemcpyAsync(im, a->im, a->n*sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	CU(cudaStreamSynchronize(e->stream));
+	return ALISB_OK;
+}
+
+extern "C" int alisb_accum_clear(alisb_accum *a)
+{
+	if (!a) return fail(ALISB_EINVAL, "accum: null argument");
+	alisb_engine *e = a->e;
+	DEV(e);
+	CU(cudaMemsetAsync(a->re, 0, a->n*sizeof(float), e->stream));
+	if (a->im) CU(cudaMemsetAsync(a->im, 0, a->n*sizeof(float), e->stream));
+	return ALISB_OK;
+}
+
+extern "C" void alisb_accum_destroy(alisb_accum *a)
+{
+	if (!a) return;
+	cudaSetDevice(a->e->g.device);
+	cudaStreamSynchronize(a->e->stream);
+	cudaFree(a->re); cudaFree(a->im);
+	delete a;
 }
 
 extern "C" int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out)

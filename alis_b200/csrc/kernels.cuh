@@ -699,33 +699,54 @@ yee_wave(const __grid_constant__ WaveParams p)
 		if (fetcher) {
 			/* boundary E' of plane index k (plane cl-k) from the -y tile (row b0-1) and the -x tile (column a0-1),
 			 * used by the workers in iteration k+1; the neighbours must have stored k+1 planes */
-			/* a poll returns how far the neighbour has come: usually several planes ahead, so most planes need no poll */
+			/* Every round fetches as many planes as are allowed right now -- the workers have freed the slots
+			 * (at most NH-1 planes ahead of the iteration they are in) and both neighbours have stored them
+			 * (a poll returns how far a neighbour has come: usually several planes, so most rounds need no
+			 * poll) -- then waits once for the copies and publishes them together. */
 			unsigned long long known_x = 0, known_y = 0;
-			for (int k = 0; k < nplanes; k++) {
+			int k = 0;
+			while (k < nplanes) {
+				int kend = k;
 				if (lane == 0) {
-					smem_wait_ge(&sm.iter_done, k - NH + 2);         /* the slot's previous content has been consumed */
+					const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.iter_done);
+					int itw;
+					do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); } while (itw < k - NH + 2);
 					const unsigned long long need = p.epoch + (unsigned long long)k + 1;
 					if (prog_x && known_x < need) known_x = wave_wait(prog_x, need, p.error);
 					if (prog_y && known_y < need) known_y = wave_wait(prog_y, need, p.error);
+					kend = min(nplanes - 1, itw + NH - 2);
+					if (prog_x) kend = min(kend, known_x >= need ? (int)(known_x - p.epoch) - 1 : k);
+					if (prog_y) kend = min(kend, known_y >= need ? (int)(known_y - p.epoch) - 1 : k);
+					kend = max(kend, k);
 				}
-				__syncwarp();
-				const int c = cl - k, slot = k & (NH - 1);
-				const size_t o = (size_t)c*p.plane + (size_t)(b0 - 1)*p.pitch + ALISB_XO + a0;
-				if (a0 <= p.a_last) { cp_async16(&sm.hrow[slot][0][lane], E0 + o); cp_async16(&sm.hrow[slot][1][lane], E2 + o); }
-				if (lane < ROWS && b0 + lane <= p.b_last) {
-					const size_t q = (size_t)c*p.plane + (size_t)(b0 + lane)*p.pitch + ALISB_XO + (p.a_first + 128*tx) - 1;
-					cp_async4(&sm.hcol[slot][0][lane], E1 + q); cp_async4(&sm.hcol[slot][1][lane], E2 + q);
+				kend = __shfl_sync(0xffffffffu, kend, 0);
+				for (int j = k; j <= kend; j++) {
+					const int c = cl - j, slot = j & (NH - 1);
+					const size_t o = (size_t)c*p.plane + (size_t)(b0 - 1)*p.pitch + ALISB_XO + a0;
+					if (a0 <= p.a_last) { cp_async16(&sm.hrow[slot][0][lane], E0 + o); cp_async16(&sm.hrow[slot][1][lane], E2 + o); }
+					if (lane < ROWS && b0 + lane <= p.b_last) {
+						const size_t q = (size_t)c*p.plane + (size_t)(b0 + lane)*p.pitch + ALISB_XO + (p.a_first + 128*tx) - 1;
+						cp_async4(&sm.hcol[slot][0][lane], E1 + q); cp_async4(&sm.hcol[slot][1][lane], E2 + q);
+					}
 				}
 				cp_async_commit();
-				cp_async_wait<0>();                                  /* an L2 round trip; the fetch warp runs up to two planes ahead of the workers */
+				cp_async_wait<0>();                                  /* one L2 round trip per round */
 				__syncwarp();
-				if (lane == 0) smem_publish(&sm.halo_ready, k + 1);
+				if (lane == 0) smem_publish(&sm.halo_ready, kend + 1);
+				k = kend + 1;
 			}
 		} else if (lane == 0) {
-			/* every worker stored E' of plane indices < it before the barrier that opened iteration it */
-			for (int it = 1; it <= nplanes; it++) {
-				smem_wait_ge(&sm.iter_done, it);
-				wave_publish(p.progress + tile, p.epoch + (unsigned long long)it);
+			/* every worker stored E' of plane indices < it before the barrier that opened iteration it.  A release
+			 * costs a memory barrier (it waits for the SM's stores in flight): publish whatever has been reached
+			 * since the last one instead of one word per plane -- the successors then see progress in batches but
+			 * never faster planes than barriers */
+			int done = 0;
+			const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.iter_done);
+			while (done < nplanes) {
+				int itw;
+				do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); } while (itw <= done);
+				wave_publish(p.progress + tile, p.epoch + (unsigned long long)itw);
+				done = itw;
 			}
 		}
 		return;
@@ -775,6 +796,7 @@ yee_wave(const __grid_constant__ WaveParams p)
 		hxp = ld4(H0 + o); hyp = ld4(H1 + o);
 	}
 	float dze_next = __ldg(p.dtdE[2] + cl), dzh_next = __ldg(p.dtdH[2] + cl + 1);   /* z coefficients one iteration ahead */
+	int halo_known = 0;                                     /* boundary planes known to be in shared memory (uniform in the warp) */
 	int c = cl;
 	for (int it = 0; it <= nplanes; ++it, --c) {
 		const size_t o = (size_t)c*p.plane + row;
@@ -829,8 +851,13 @@ yee_wave(const __grid_constant__ WaveParams p)
 		/* ---- H'(c+1), update.c:115-117 as in yee_body<-1> ---- */
 		if (it > 0) {
 			/* boundary E' of plane c+1 (plane index it-1) from the neighbour tiles */
-			if (lane == 0) smem_wait_ge(&sm.halo_ready, it);
-			__syncwarp();
+			if (halo_known < it) {
+				if (lane == 0) {
+					const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.halo_ready);
+					do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(halo_known) : "r"(sa) : "memory"); } while (halo_known < it);
+				}
+				halo_known = __shfl_sync(0xffffffffu, halo_known, 0);
+			}
 			const int slot = (it - 1) & (NH - 1);
 			if (wy == 0) { exm = sm.hrow[slot][0][lane]; ezm = sm.hrow[slot][1][lane]; }
 			float eya = __shfl_up_sync(0xffffffffu, eyp.w, 1), eza = __shfl_up_sync(0xffffffffu, ezp.w, 1);
@@ -862,7 +889,7 @@ yee_wave(const __grid_constant__ WaveParams p)
 
 /* one box per launch: the slab-free interior (PM=0) and, with ALISB_MERGE=0, every other box */
 template <int S, bool EPS, int PM, int XL, bool ADE>
-__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : 1)   /* single-axis slab variants: keep 3 CTAs/SM */
+__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : (ADE && PM == 0) ? 2 : 1)   /* single-axis slab variants: keep 3 CTAs/SM; interior with objects: 2 */
 yee_volume(const __grid_constant__ VolParams p, const __grid_constant__ VolRegion r)
 {
 	yee_body<S,EPS,PM,XL,ADE>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
@@ -1386,6 +1413,20 @@ __global__ void eval_box(const __grid_constant__ EvalParams p, float *out)
 	const int ia = (int)(t % p.ni); const size_t r = t / p.ni;
 	const int ib = (int)(r % p.nj), ic = (int)(r / p.nj);
 	out[((size_t)ia*p.nj + ib)*p.nk + ic] = mon_eval(&p, p.i0 + ia, p.j0 + ib, p.k0 + ic);
+}
+
+/* running sums over a box (sliceTimeAvg / sliceFreqDom accumulations, slices.c:282-379): re += F*wr, im += F*wi,
+ * accumulators dense in the HOST order like eval_box's output; one thread owns one point */
+__global__ void eval_accumulate(const __grid_constant__ EvalParams p, float *re, float *im, float wr, float wi)
+{
+	const size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= (size_t)p.ni*p.nj*p.nk) return;
+	const int ia = (int)(t % p.ni); const size_t r = t / p.ni;
+	const int ib = (int)(r % p.nj), ic = (int)(r / p.nj);
+	const float v = mon_eval(&p, p.i0 + ia, p.j0 + ib, p.k0 + ic);
+	const size_t q = ((size_t)ia*p.nj + ib)*p.nk + ic;
+	re[q] += v * wr;
+	if (im) im[q] += v * wi;
 }
 
 /* max |F| over the box (worldMax output.c:56-70, sliceMax slices.c:382-394): order independent;

@@ -330,9 +330,21 @@ int alis_device_geometry(void)
 	return mode;
 }
 
+/* grids below this many cells are rasterised on the host: the device path costs a CUDA start-up plus a stack
+ * resize before the first step (measured on the B200: putObjects of the 1e5..6e5-cell named examples 1.0-3.6 s
+ * on the device against 0.1-0.3 s on 16 host threads, profiles/r02_named_profiles_v4.txt; at 22.7 M cells the
+ * device wins 1.5 s to 3.7 s).  ALIS_DEVICE_GEOMETRY_MIN overrides. */
+static long geo_min_cells(void)
+{
+	static long n = -1;
+	if (n < 0) { const char *s = getenv("ALIS_DEVICE_GEOMETRY_MIN"); n = s ? atol(s) : 4000000L; }
+	return n;
+}
+
 static geo_ctx *geo_build(world W, object *O, int N)
 {
 	if (!alis_device_geometry() || W->subN < 1 || N < 1) return 0;
+	if ((long)W->iNUM*W->jNUM*W->kNUM < geo_min_cells()) return 0;
 	geo_ctx *G = xcalloc(1, sizeof *G);
 	G->roots = xmalloc(sizeof(int32_t)*N);
 	for (int o=0; o<N; o++) {

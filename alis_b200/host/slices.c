@@ -22,6 +22,8 @@ typedef struct sentry {
 	method M;
 	char *name;
 	float max, Max, ***F, ***G;
+	alisb_accum *dev;             /* the running sums live on the device (F has a device twin): F, G are filled when a frame is due */
+	int dev_tried;
 	long calls;
 	struct sentry *next;
 } sentry;
@@ -328,6 +330,41 @@ static float sample(world W, field F, slice S, float ***dst)
 	return max;
 }
 
+/* Running sums of sliceTimeAvg / sliceFreqDom on the device: one asynchronous kernel per call instead of a
+ * synchronous evaluation + device-to-host copy of the slice every step; the sums come back when a frame
+ * is written.  Same float operations per point in the same order: bit-identical to the host loops. */
+static alisb_accum *accum_open(world W, field F, slice S, int with_imag)
+{
+	alisb_field_fn d;
+	int take_log;
+	const int box[6] = { S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax };
+	if (alis_host_monitors() || !alis_field_device_fn(W, F, &d, &take_log) || take_log || !alis_device_region_ok(W, &d, box)) return 0;
+	const int32_t ib[6] = { box[0], box[1], box[2], box[3], box[4], box[5] };
+	alisb_accum *a = 0;
+	alis_bridge_commit(alis_host_bridge(W));
+	if (alisb_accum_create(alis_bridge_engine(alis_host_bridge(W)), &d, ib, with_imag, &a) != ALISB_OK) return 0;
+	return a;
+}
+
+static void accum_add(world W, alisb_accum *a, float wr, float wi)
+{
+	alis_bridge_commit(alis_host_bridge(W));
+	if (alisb_accum_add(a, wr, wi) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+}
+
+static void accum_fetch(slice S, alisb_accum *a, float ***F, float ***G)
+{
+	const size_t n = (size_t)(S->iMax-S->iMin+1)*(S->jMax-S->jMin+1)*(S->kMax-S->kMin+1);
+	float *re = xmalloc(sizeof(float)*n), *im = G ? xmalloc(sizeof(float)*n) : 0;
+	if (alisb_accum_read(a, re, im) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	size_t q = 0;
+	for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++, q++) {
+		F[i][j][k] = re[q];
+		if (G) G[i][j][k] = im[q];
+	}
+	free(re); free(im);
+}
+
 /* sliceSnap(W, F, S, N, writer[, cmap, max], "name"...): N frames per period W->T; max = 0 auto per
  * frame, max < 0 auto-scale lagging by -max periods (reference slices.c:242-279) */
 void (sliceSnap)(world W, field F, slice S, char *f, char *s, ...)
@@ -382,7 +419,9 @@ void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 	if (N) sprintf(string, "%05ld", e->calls / N), strcat(filename, string);
 
 	if (e->calls == 1) e->F = makeField(S->iMin, S->iMax, S->jMin, S->jMax, S->kMin, S->kMax);
-	{
+	if (!e->dev_tried) { e->dev_tried = 1; e->dev = accum_open(W, F, S, 0); }
+	if (e->dev) accum_add(W, e->dev, 1, 0);              /* F*1 is F: the same sum */
+	else {
 		float *v = slice_values(W, F, S);
 		size_t q = 0;
 		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
@@ -391,6 +430,7 @@ void (sliceTimeAvg)(world W, field F, slice S, char *f, char *s, ...)
 	}
 
 	if (e->calls % N == 0) {
+		if (e->dev) { accum_fetch(S, e->dev, e->F, 0); alisb_accum_clear(e->dev); }
 		float max = 0;
 		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)
 			if (max < fabsf(S->F[i][j][k] = e->F[i][j][k] / N)) max = fabsf(S->F[i][j][k]);
@@ -430,7 +470,9 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 	}
 	float real = cosf(2 * PI * e->calls * W->dt / L);
 	float imag = sinf(2 * PI * e->calls * W->dt / L);
-	{
+	if (!e->dev_tried) { e->dev_tried = 1; e->dev = accum_open(W, F, S, 1); }
+	if (e->dev) accum_add(W, e->dev, real, imag);
+	else {
 		float *v = slice_values(W, F, S);
 		size_t q = 0;
 		for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++, q++) {
@@ -441,6 +483,7 @@ void (sliceFreqDom)(world W, field F, slice S, char *f, char *s, int N, float L,
 	}
 
 	if (e->calls % N == 0) {
+		if (e->dev) accum_fetch(S, e->dev, e->F, e->G);
 		if (Max <= 0) {
 			float max = 0;
 			for (int i=S->iMin; i<=S->iMax; i++) for (int j=S->jMin; j<=S->jMax; j++) for (int k=S->kMin; k<=S->kMax; k++)

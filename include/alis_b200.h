@@ -257,6 +257,17 @@ typedef struct {
  * reference's order and promotions (output.c:73-80) -- into host[(i-i0)*nj + (j-j0)]; needs
  * alisb_set_spacing(e, ALISB_SET_E, ALISB_Z, ...) and a k range inside the arrays.              */
 int  alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
+/* Running sums of a field function over a box, kept where the fields live (reference slices.c:282-379:
+ * the per-pixel accumulations of sliceTimeAvg `Q->F += F` and sliceFreqDom `Q->F += F*real, Q->G += F*imag`,
+ * called every step).  alisb_accum_add queues  re += F*wr  [, im += F*wi]  for every point of the box and
+ * returns without waiting for the device; alisb_accum_read brings the sums back (dense blocks, z fastest).
+ * Float accumulation per point in call order: bit-identical to the reference's loops. */
+typedef struct alisb_accum alisb_accum;
+int  alisb_accum_create(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], int with_imag, alisb_accum **out);
+int  alisb_accum_add(alisb_accum *a, float wr, float wi);
+int  alisb_accum_read(alisb_accum *a, float *re, float *im);
+int  alisb_accum_clear(alisb_accum *a);
+void alisb_accum_destroy(alisb_accum *a);
 int  alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out);
 int  alisb_column_sums(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *host);
 /* objectAbsorption (reference output.c:23-47,365-435): for ADE object `obj` (index in add order) and

@@ -651,6 +651,50 @@ int alisb_eval_box(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[
 	return ALISB_OK;
 }
 
+/* reference slices.c:282-379: the per-point running sums of sliceTimeAvg / sliceFreqDom */
+struct alisb_accum { alisb_engine *e; alisb_field_fn f; int32_t ibox[6]; size_t n; float *re, *im; };
+
+int alisb_accum_create(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], int with_imag, alisb_accum **out)
+{
+	int rc = eval_check(e, f, ibox, 0);
+	if (rc) return rc;
+	alisb_accum *a = calloc(1, sizeof *a);
+	a->e = e; a->f = *f; memcpy(a->ibox, ibox, sizeof a->ibox);
+	a->n = (size_t)(ibox[1]-ibox[0]+1)*(ibox[3]-ibox[2]+1)*(ibox[5]-ibox[4]+1);
+	a->re = calloc(a->n, sizeof(float));
+	a->im = with_imag ? calloc(a->n, sizeof(float)) : 0;
+	*out = a;
+	return ALISB_OK;
+}
+
+int alisb_accum_add(alisb_accum *a, float wr, float wi)
+{
+	const mon_ctx X = { a->e, &a->f, 0 };
+	size_t q = 0;
+	for (int i=a->ibox[0]; i<=a->ibox[1]; i++) for (int j=a->ibox[2]; j<=a->ibox[3]; j++) for (int k=a->ibox[4]; k<=a->ibox[5]; k++, q++) {
+		const float v = mon_eval(&X, i, j, k);
+		a->re[q] += v * wr;                              /* slices.c:352 */
+		if (a->im) a->im[q] += v * wi;                   /* slices.c:353 */
+	}
+	return ALISB_OK;
+}
+
+int alisb_accum_read(alisb_accum *a, float *re, float *im)
+{
+	memcpy(re, a->re, a->n*sizeof(float));
+	if (im && a->im) memcpy(im, a->im, a->n*sizeof(float));
+	return ALISB_OK;
+}
+
+int alisb_accum_clear(alisb_accum *a)
+{
+	memset(a->re, 0, a->n*sizeof(float));
+	if (a->im) memset(a->im, 0, a->n*sizeof(float));
+	return ALISB_OK;
+}
+
+void alisb_accum_destroy(alisb_accum *a) { if (a) { free(a->re); free(a->im); free(a); } }
+
 int alisb_reduce_absmax(alisb_engine *e, const alisb_field_fn *f, const int32_t ibox[6], float *out)
 {
 	int rc = eval_check(e, f, ibox, 0);

@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the product rasterises grids below 4 M cells on the host (alis_b200/host/object.c:geo_min_cells); the tests'
+# grids are all smaller, and they are here to exercise the device rasteriser: no threshold in the test processes
+# (tests/test_refex.py removes the variable again: it times the product as shipped)
+os.environ.setdefault("ALIS_DEVICE_GEOMETRY_MIN", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

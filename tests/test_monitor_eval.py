@@ -199,3 +199,47 @@ def test_cuda_absorption_columns_bit_exact(oracle_lib, engine_lib):
         assert np.array_equal(g.absorption_columns(0, sub), b[2:-3, 1:-1])
     with pytest.raises(capi.EngineError):
         g.absorption_columns(1, box)
+
+
+def _accumulate(e, steps, with_imag):
+    fn = e.field_fn(capi.FN_NODE, 1, 2)                       # Hz, the field of PhC_Band_Diagram's sliceFreqDom
+    box = [2, 30, 3, 28, 10, 10]
+    acc = e.accum(fn, box, with_imag)
+    want_re = np.zeros((29, 26, 1), F32)
+    want_im = np.zeros((29, 26, 1), F32)
+    for n in range(1, steps + 1):
+        e.step_E()
+        e.step_H()
+        wr, wi = F32(np.cos(F32(0.37) * n)), F32(np.sin(F32(0.37) * n))
+        acc.add(float(wr), float(wi))
+        v = e.eval_box(fn, box)
+        want_re += v * wr                                     # float32, one rounding per product and per sum: slices.c:352-353
+        want_im += v * wi
+    return acc, want_re, want_im
+
+
+def test_oracle_running_sums_match_numpy(oracle_lib):
+    """alisb_accum_*: the per-point sums of sliceFreqDom / sliceTimeAvg (reference slices.c:282-379)"""
+    e = make(oracle_lib)
+    acc, want_re, want_im = _accumulate(e, 6, True)
+    re, im = acc.read()
+    assert np.array_equal(re, want_re) and np.array_equal(im, want_im) and np.abs(re).max() > 0
+    acc.clear()
+    re, im = acc.read()
+    assert not re.any() and not im.any()
+    acc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_imag", [True, False])
+def test_cuda_running_sums_bit_exact(oracle_lib, engine_lib, with_imag):
+    """kernel eval_accumulate (asynchronous, one launch per call) against the oracle's loops"""
+    g, o = make(engine_lib), make(oracle_lib)
+    ag, _, _ = _accumulate(g, 8, with_imag)
+    ao, want_re, want_im = _accumulate(o, 8, with_imag)
+    for (a, b) in zip(ag.read(), ao.read()):
+        if a is not None:
+            assert np.array_equal(a, b)
+    assert np.array_equal(ag.read()[0], want_re)
+    ag.close()
+    ao.close()

@@ -55,6 +55,7 @@ def _run(name, tag, cwd, timeout):
     local = os.path.join(cwd, name)                 # argv[0] names the output directory
     shutil.copy(exe, local)
     env = dict(os.environ)
+    env.pop("ALIS_DEVICE_GEOMETRY_MIN", None)        # the library's own defaults: these runs are also the timed ones
     env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(helpers.ROOT, "alis_b200"), helpers.TEST_BIN, os.path.join(helpers.ROOT, "oracle"), env.get("LD_LIBRARY_PATH", "")])
     t0 = time.time()
     r = subprocess.run(["./" + name] + REFEX[name][0], cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
