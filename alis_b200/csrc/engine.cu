@@ -724,7 +724,14 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
  * ade_loss / ade_subtract / ade_currents run around the volume launches */
 static bool ade_in_kernel(const alisb_engine *e)
 {
-	return e->tune_ade && !e->obj.empty() && e->obj.size() <= ALISB_MAXADE && e->eps[0] && e->eps[1] && e->eps[2];
+	if (!(e->tune_ade && !e->obj.empty() && e->obj.size() <= ALISB_MAXADE && e->eps[0] && e->eps[1] && e->eps[2])) return false;
+	/* grids large enough for fused E+H stepping keep the three box kernels: they act on the passes' input and
+	 * output, so the fused kernel also covers the objects' planes (measured at 512^3 with a gold block on 1/8 of
+	 * the interior: 46.1 Gcells/s against 40.5 with the objects' planes two-pass, profiles/r02_ade_bench_v5.txt);
+	 * ALISB_ADE_FUSE=2 forces the in-kernel variant */
+	const long cells = (long)e->nx*e->ny*e->nz;
+	if (e->tune_ade < 2 && e->fuse_req && cells >= e->tune_fuse_min && cells >= e->tune_small) return false;
+	return true;
 }
 
 static int ade_table(alisb_engine *e)
@@ -985,6 +992,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		}
 		wp.ticket = e->d_wave_ticket; wp.ticket_base = e->wave_ticket_base; wp.progress = e->d_wave_progress;
 		wp.epoch = (++e->wave_epoch) << 20; wp.error = e->d_wave_error;
+		{ const char *ls = getenv("ALISB_WAVE_LAG"); wp.lag = ls ? std::max(0, atoi(ls)) : 4; }
 		e->wave_ticket_base += ntiles;
 		cudaEvent_t e1 = prof_begin(e->stream, pc.sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
 		if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] in-place fused E+H cells %d..%d rows %d..%d planes %d..%d tiles %dx%dx%d of 128x%d cells, %d planes per chunk\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, wp.ntx, wp.nty, wp.ntz, frows, wp.cchunk);

@@ -607,9 +607,10 @@ struct WaveParams {
 	unsigned long long *progress;     /* one word per tile                                   */
 	unsigned long long epoch;         /* launch number << 20                                 */
 	int *error;
+	int lag;                          /* planes a tile stays behind its -x / -y neighbours (slack against their jitter) */
 };
 
-#define ALISB_WAVE_NH 4              /* boundary-E' slots: the fetch warp runs up to two planes ahead of the workers */
+#define ALISB_WAVE_NH 8              /* boundary-E' slots: the fetch warp runs up to six planes ahead of the workers */
 template <int ROWS, bool EPS, int NST> struct WaveSmem {
 	struct Stage {
 		float4 e[3][ROWS][32];
@@ -710,14 +711,16 @@ yee_wave(const __grid_constant__ WaveParams p)
 				if (lane == 0) {
 					const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.iter_done);
 					int itw;
-					do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); } while (itw < k - NH + 2);
-					const unsigned long long need = p.epoch + (unsigned long long)k + 1;
+					for (;;) { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); if (itw >= k - NH + 2) break; __nanosleep(100); }
+					/* stay `lag` planes behind the neighbours (they may be at most nplanes ahead): a neighbour's
+					 * hiccup then eats slack instead of stalling this tile and everything downstream of it */
+					const unsigned long long need = p.epoch + (unsigned long long)min(k + 1 + p.lag, nplanes);
 					if (prog_x && known_x < need) known_x = wave_wait(prog_x, need, p.error);
 					if (prog_y && known_y < need) known_y = wave_wait(prog_y, need, p.error);
 					kend = min(nplanes - 1, itw + NH - 2);
 					if (prog_x) kend = min(kend, known_x >= need ? (int)(known_x - p.epoch) - 1 : k);
 					if (prog_y) kend = min(kend, known_y >= need ? (int)(known_y - p.epoch) - 1 : k);
-					kend = max(kend, k);
+					kend = max(kend, k);                             /* plane k itself is covered by `need` (lag >= 0) */
 				}
 				kend = __shfl_sync(0xffffffffu, kend, 0);
 				for (int j = k; j <= kend; j++) {
@@ -744,7 +747,7 @@ yee_wave(const __grid_constant__ WaveParams p)
 			const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.iter_done);
 			while (done < nplanes) {
 				int itw;
-				do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); } while (itw <= done);
+				for (;;) { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(itw) : "r"(sa) : "memory"); if (itw > done) break; __nanosleep(100); }
 				wave_publish(p.progress + tile, p.epoch + (unsigned long long)itw);
 				done = itw;
 			}

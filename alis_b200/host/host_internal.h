@@ -33,6 +33,8 @@ void alis_host_invalidate(world W);             /* setup changed -> re-commit be
 void alis_host_dirty(world W, int mask);
 void alis_host_reset_fields(world W);           /* rebootWorld                                   */
 void alis_host_touch(world W);                  /* device state advanced: host views are stale   */
+unsigned long alis_view_version(world W);       /* number of such advances                       */
+void alis_flux_cache_drop(world W);             /* output.c: forget the flux results kept for W  */
 
 /* host views: make W->E[m].{x,y,z}, W->H[m].{x,y,z} valid on [i0-1..i1+1]x[j0-1..j1+1]x[k0-1..k1+1]
  * (clipped to the allocation), for every field set m, including TFSF aux worlds */

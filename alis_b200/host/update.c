@@ -34,6 +34,7 @@ alis_bridge *alis_host_bridge(world W)
 
 void alis_host_detach(world W)
 {
+	alis_flux_cache_drop(W);
 	alis_view_free(W);
 	if (W->b200_bridge) alis_bridge_destroy((alis_bridge*)W->b200_bridge);
 	W->b200_bridge = 0;

@@ -26,6 +26,8 @@ static view_state *state(world W)
 	return (view_state*)W->b200_view;
 }
 
+unsigned long alis_view_version(world W) { return state(W)->version; }
+
 void alis_host_touch(world W)
 {
 	state(W)->version++;
