@@ -25,6 +25,12 @@
 #include "alis_b200.h"
 #include "kernels.cuh"
 
+/* the fused kernel needs more than the default 48 KB of dynamic shared memory (a per-device function attribute) */
+template <int ROWS, bool EPS, bool PMZ> static cudaError_t fused_optin_one()
+{
+	return cudaFuncSetAttribute(yee_fused<ROWS,EPS,PMZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<ROWS,EPS>));
+}
+
 /* NVTX range per pass / monitor call: visible in nsys / ncu --nvtx timelines */
 struct NvtxRange { NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
@@ -89,6 +95,8 @@ struct alisb_engine {
 	float *eps[3];
 	float *dtd[2][3], *P[2][3], *P1[2][3], *P2[2][3];
 	float *psi[2][2][3][2][2]; size_t psi_elems[2][3][2];
+	float *psib[2][2][2][2];           /* double-buffered mode: the other buffer of the z-slab psi arrays [set][m][side][which] (they swap with the fields) */
+	int tune_pmz;                      /* z CPML slabs inside the fused box (ALISB_FUSE_PMZ, default 0) */
 	int xbase[2][2], xpitch[2][2];     /* [set][side]                                     */
 	std::vector<DispObj*> obj;
 	AdeTable *d_ade[2]; uint64_t ade_cfg;   /* device copies of the in-kernel object table per complex set; built for ade_cfg */
@@ -203,7 +211,7 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	e->plane = (size_t)(g->ny + 2)*e->pitch;
 	e->elems = e->plane*(g->nz + 2) + 64;
 	memset(e->F, 0, sizeof e->F); memset(e->Fb, 0, sizeof e->Fb); memset(e->eps, 0, sizeof e->eps);
-	e->dbuf = false; e->pass_open[0] = e->pass_open[1] = false; e->fuse_ok = false; e->fuse_cfg = 0; e->pendingE = -1; e->fusing = false; e->h_fused = false; memset(e->psi, 0, sizeof e->psi);
+	e->dbuf = false; e->pass_open[0] = e->pass_open[1] = false; e->fuse_ok = false; e->fuse_cfg = 0; e->pendingE = -1; e->fusing = false; e->h_fused = false; memset(e->psi, 0, sizeof e->psi); memset(e->psib, 0, sizeof e->psib);
 	memset(e->dtd, 0, sizeof e->dtd); memset(e->P, 0, sizeof e->P); memset(e->P1, 0, sizeof e->P1); memset(e->P2, 0, sizeof e->P2);
 	e->step = 0; e->t = e->tE = e->tH = 0; e->launches = 0; e->fused_launches = 0; e->profiling = false; e->ev_used = 0; e->last_ms = 0; e->last_launches = 0;
 	e->scratch = 0; e->scratch_elems = 0;
@@ -216,6 +224,10 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	e->d_wave_ticket = 0; e->d_wave_progress = 0; e->d_wave_error = 0; e->wave_tiles_cap = 0; e->wave_ticket_base = 0; e->wave_epoch = 0;
 	{ const char *ws = getenv("ALISB_WAVE"); e->tune_wave = ws ? atoi(ws) : 0; }
 	{ const char *as = getenv("ALISB_ADE_FUSE"); e->tune_ade = as ? atoi(as) : 1; }
+	/* z CPML slabs inside the fused box: opt-in.  Measured on the 2048x2048x256 bench (profiles/r02_pmz_ab_v9.txt): the slab
+	 * planes leave launches that run at 6.7 TB/s (yee_multi faces, 104 B per cell) for one that runs at 5.9 TB/s (80 B per
+	 * cell) and whose psi loads are not staged through the ring: 11.37 ms per step against 10.59 without */
+	{ const char *as = getenv("ALISB_FUSE_PMZ"); e->tune_pmz = as ? atoi(as) : 0; }
 	memset(e->spacing, 0, sizeof e->spacing); e->d_planes = 0; e->d_partial = 0; e->d_flux = 0; e->h_flux = 0; e->flux_cap = 0;
 	e->f_lo = 0; e->f_hi = g->nz + 1;
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true;
@@ -275,10 +287,9 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 	e->sm_count = prop.multiProcessorCount;
 	/* the > 48 KB dynamic shared memory opt-in is a per-device function attribute: set it for THIS engine's
 	 * device (cheap; engines on several devices in one process each do it) */
-	CU(cudaFuncSetAttribute(yee_fused<8,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,false>)));
-	CU(cudaFuncSetAttribute(yee_fused<8,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,true>)));
-	CU(cudaFuncSetAttribute(yee_fused<16,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,false>)));
-	CU(cudaFuncSetAttribute(yee_fused<16,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,true>)));
+	CU((fused_optin_one<8,false,false>())); CU((fused_optin_one<8,true,false>())); CU((fused_optin_one<16,false,false>())); CU((fused_optin_one<16,true,false>()));
+	CU((fused_optin_one<8,false,true>()));  CU((fused_optin_one<8,true,true>()));  CU((fused_optin_one<16,false,true>()));  CU((fused_optin_one<16,true,true>()));
+	CU((fused_optin_one<15,false,false>())); CU((fused_optin_one<15,true,false>())); CU((fused_optin_one<15,false,true>())); CU((fused_optin_one<15,true,true>()));
 	CU(cudaFuncSetAttribute(yee_wave<16,false,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<16,false,3>)));
 	CU(cudaFuncSetAttribute(yee_wave<12,false,4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<12,false,4>)));
 	CU(cudaFuncSetAttribute(yee_wave<8,false,4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WaveSmem<8,false,4>)));
@@ -341,6 +352,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int c=0; c<3; c++) cudaFree(e->eps[c]);
 	for (int s=0; s<2; s++) for (int ax=0; ax<3; ax++) { cudaFree(e->dtd[s][ax]); cudaFree(e->P[s][ax]); cudaFree(e->P1[s][ax]); cudaFree(e->P2[s][ax]); }
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psi[s][m][ax][sd][w]);
+	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) cudaFree(e->psib[s][m][sd][w]);
 	for (int a=0; a<2; a++) for (int b=0; b<3; b++) { if (e->graph[a][b].exec) cudaGraphExecDestroy(e->graph[a][b].exec); if (e->graph[a][b].graph) cudaGraphDestroy(e->graph[a][b].graph); }
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
@@ -574,6 +586,7 @@ static void fuse_eval(alisb_engine *e)
 			if (f1 <= l1) hi[ax] = std::min(hi[ax], f1 - 1);
 		}
 	}
+	if (e->tune_pmz && !e->tune_wave) { lo[2] = 2; hi[2] = n[2]; }   /* yee_fused<..,PMZ> carries the z slabs (the halo plane 1 is an updated cell) */
 	hi[2] = std::min(hi[2], e->nz - 1);             /* plane nz is the E send plane of a sharded run (alisb_step_part) */
 	/* x in whole 32-cell groups starting at a = 1 mod 32 */
 	int a0 = (lo[0] - 1 + 31)/32*32 + 1;
@@ -628,6 +641,13 @@ static int enable_dbuf(alisb_engine *e)
 		TRY(dalloc(&e->Fb[s][m][c], e->elems));
 		CU(cudaMemcpyAsync(e->Fb[s][m][c], e->F[s][m][c], e->elems*sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
 	}
+	/* the z-slab psi arrays follow the same protocol (every kernel of a pass reads the old buffer and writes the
+	 * current one): the fused kernel recomputes E' on halo cells whose psi the owning CTA may already have replaced */
+	for (int s=0; s<2; s++) for (int m=0; m<=e->g.complex_field; m++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) {
+		if (!e->psi[s][m][2][sd][w] || !e->psi_elems[s][2][sd]) continue;
+		TRY(dalloc(&e->psib[s][m][sd][w], e->psi_elems[s][2][sd]));
+		CU(cudaMemcpyAsync(e->psib[s][m][sd][w], e->psi[s][m][2][sd][w], e->psi_elems[s][2][sd]*sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+	}
 	e->dbuf = true;
 	e->cfg_version++; e->fuse_cfg = e->cfg_version;      /* drops captured graphs; feasibility is unchanged */
 	return ALISB_OK;
@@ -638,6 +658,7 @@ static void open_pass(alisb_engine *e, int set)
 {
 	if (!e->dbuf || e->pass_open[set]) return;
 	for (int m=0; m<=e->g.complex_field; m++) for (int c=0; c<3; c++) std::swap(e->F[set][m][c], e->Fb[set][m][c]);
+	for (int m=0; m<=e->g.complex_field; m++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) if (e->psib[set][m][sd][w]) std::swap(e->psi[set][m][2][sd][w], e->psib[set][m][sd][w]);
 	e->pass_open[set] = true;
 }
 
@@ -688,7 +709,22 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 		Y.push_back({R[2], R[3], 0});
 		if (R[3] < e->ny)   Y.push_back({R[3] + 1, e->ny, slabby(1, R[3] + 1, e->ny) ? 2 : 0});
 		if (R[4] > 1)       Z.push_back({1, R[4] - 1, slabby(2, 1, R[4] - 1) ? 4 : 0});
-		Z.push_back({R[4], R[5], 0});
+		{
+			/* the fused box may reach into the z slabs (yee_fused<..,PMZ>): its z range is cut where the slabs of
+			 * either field set end / begin, so that what runs two-pass beside it (x and y strips, planes a fix-up
+			 * touches) carries the z code only on slab planes */
+			int zl = R[4] - 1, zh = R[5] + 1;
+			for (int st=0; st<2; st++) {
+				if (e->g.pml[st][2][0][0] <= e->g.pml[st][2][0][1]) zl = std::max(zl, std::min(R[5], e->g.pml[st][2][0][1]));
+				if (e->g.pml[st][2][1][0] <= e->g.pml[st][2][1][1]) zh = std::min(zh, std::max(R[4], e->g.pml[st][2][1][0]));
+			}
+			if (zl >= zh) { zl = R[4] - 1; zh = R[5] + 1; Z.push_back({R[4], R[5], slabby(2, R[4], R[5]) ? 4 : 0}); }
+			else {
+				if (zl >= R[4]) Z.push_back({R[4], zl, slabby(2, R[4], zl) ? 4 : 0});
+				if (zl + 1 <= zh - 1) Z.push_back({zl + 1, zh - 1, slabby(2, zl + 1, zh - 1) ? 4 : 0});
+				if (zh <= R[5]) Z.push_back({zh, R[5], slabby(2, zh, R[5]) ? 4 : 0});
+			}
+		}
 		if (R[5] < e->nz)   Z.push_back({R[5] + 1, e->nz, slabby(2, R[5] + 1, e->nz) ? 4 : 0});
 	} else {
 		if (xl >= 1)         X.push_back({1, xl, 1});
@@ -710,7 +746,7 @@ static void plan_volume(alisb_engine *e, int set, std::vector<SubBox> &L)
 			continue;
 		}
 		for (const Range &x : X) {
-			const int fus = e->fuse_ok && x.a == e->R[0] && x.b == e->R[1] && y.a == e->R[2] && y.b == e->R[3] && z.a == e->R[4] && z.b == e->R[5];
+			const int fus = e->fuse_ok && x.a == e->R[0] && x.b == e->R[1] && y.a == e->R[2] && y.b == e->R[3] && z.a >= e->R[4] && z.b <= e->R[5];
 			L.push_back({x.a, x.b, y.a, y.b, z.a, z.b, x.pm | y.pm | z.pm, fus});
 		}
 	}
@@ -761,6 +797,18 @@ static int ade_table(alisb_engine *e)
 	return ALISB_OK;
 }
 
+template <int ROWS, bool EPS> static void launch_fused_t(cudaStream_t st, const FusedParams &fp, dim3 grid, dim3 block, bool pmz)
+{
+	if (pmz) yee_fused<ROWS,EPS,true><<<grid, block, sizeof(FusedSmem<ROWS,EPS>), st>>>(fp);
+	else     yee_fused<ROWS,EPS,false><<<grid, block, sizeof(FusedSmem<ROWS,EPS>), st>>>(fp);
+}
+static void launch_fused(cudaStream_t st, const FusedParams &fp, dim3 grid, dim3 block, int frows, bool eps, bool pmz)
+{
+	if (frows == 16) { if (eps) launch_fused_t<16,true>(st, fp, grid, block, pmz); else launch_fused_t<16,false>(st, fp, grid, block, pmz); }
+	else if (frows == 15) { if (eps) launch_fused_t<15,true>(st, fp, grid, block, pmz); else launch_fused_t<15,false>(st, fp, grid, block, pmz); }
+	else             { if (eps) launch_fused_t<8,true>(st, fp, grid, block, pmz);  else launch_fused_t<8,false>(st, fp, grid, block, pmz); }
+}
+
 static int launch_volume(alisb_engine *e, int set, int m)
 {
 	VolParams p;
@@ -778,6 +826,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		}
 	}
 	for (int sd=0; sd<2; sd++) { p.xbase[sd] = e->xbase[set][sd]; p.xpitch[sd] = e->xpitch[set][sd]; }
+	for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++) p.psiz_in[sd][w] = (e->dbuf && e->psib[set][m][sd][w]) ? e->psib[set][m][sd][w] : e->psi[set][m][2][sd][w];
 	p.nx = e->nx; p.ny = e->ny; p.nz = e->nz; p.pitch = e->pitch; p.plane = e->plane;
 	const bool eps = set == ALISB_SET_E && e->eps[0] && e->eps[1] && e->eps[2];
 	if (e->plan[set].empty()) plan_volume(e, set, e->plan[set]);
@@ -819,12 +868,33 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		const bool skipz = sb0.fusable && e->fuse_ok && ((set == ALISB_SET_E && e->fusing) || (set == ALISB_SET_H && e->h_fused));
 		if (!skipz) { work.push_back({sb0, sub, false, ade}); continue; }
 		int c = sb0.c0;
-		for (const std::pair<int,int> &z : e->fuse_z) {
+		for (const std::pair<int,int> &z0 : e->fuse_z) {
+			const std::pair<int,int> z(std::max(z0.first, sb0.c0), std::min(z0.second, sb0.c1));   /* the part of the clean range inside this piece of the box */
+			if (z.first > z.second) continue;
 			if (z.first > c) { SubBox d = sb0; d.c0 = c; d.c1 = z.first - 1; work.push_back({d, sub, false, ade}); }
 			if (set == ALISB_SET_E) { SubBox d = sb0; d.c0 = z.first; d.c1 = z.second; work.push_back({d, sub, true, false}); }
 			c = z.second + 1;
 		}
 		if (c <= sb0.c1) { SubBox d = sb0; d.c0 = c; d.c1 = sb0.c1; work.push_back({d, sub, false, ade}); }
+	}
+	{
+		/* fused pieces of the box that touch in z (it is planned in up to three z ranges: low slabs, slab-free,
+		 * high slabs) become one launch: one march, no halo plane recomputed at the seams */
+		std::vector<Piece> merged;
+		std::vector<Piece> fz;
+		for (const Piece &pc : work) { if (pc.fused) fz.push_back(pc); else merged.push_back(pc); }
+		std::sort(fz.begin(), fz.end(), [](const Piece &p, const Piece &q) { return p.sb.c0 < q.sb.c0; });
+		for (size_t q=0; q<fz.size(); q++) {
+			Piece cur = fz[q];
+			int big = cur.sb.c1 - cur.sb.c0;
+			while (q + 1 < fz.size() && fz[q + 1].sb.c0 == cur.sb.c1 + 1) {
+				q++;
+				if (fz[q].sb.c1 - fz[q].sb.c0 > big) { big = fz[q].sb.c1 - fz[q].sb.c0; cur.sub = fz[q].sub; }   /* profiled under the largest part */
+				cur.sb.c1 = fz[q].sb.c1; cur.sb.pml |= fz[q].sb.pml;
+			}
+			merged.insert(merged.begin(), cur);       /* the big launches first */
+		}
+		work.swap(merged);
 	}
 	if (ade) {
 		/* The ADE variants carry the object code (and its registers: fewer resident CTAs).  Only the part of a
@@ -880,9 +950,25 @@ static int launch_volume(alisb_engine *e, int set, int m)
 				fp.C[c] = eps ? e->eps[c] : 0;
 			}
 			fp.ny = e->ny; fp.pitch = e->pitch; fp.plane = e->plane;
+			/* z CPML slabs inside the box: the E set's psi arrays were swapped when this pass opened (read the other
+			 * buffer, write the current one); the H set's swap when the H pass opens (read the current one, write
+			 * the other: like H' itself) */
+			bool pmz = false;
+			for (int sd=0; sd<2; sd++) {
+				fp.zslabE[sd][0] = e->g.pml[ALISB_SET_E][2][sd][0]; fp.zslabE[sd][1] = e->g.pml[ALISB_SET_E][2][sd][1];
+				fp.zslabH[sd][0] = e->g.pml[ALISB_SET_H][2][sd][0]; fp.zslabH[sd][1] = e->g.pml[ALISB_SET_H][2][sd][1];
+				if (fp.zslabE[sd][0] <= fp.zslabE[sd][1] && fp.zslabE[sd][0] <= sb.c1 && fp.zslabE[sd][1] >= sb.c0 - 1) pmz = true;
+				if (fp.zslabH[sd][0] <= fp.zslabH[sd][1] && fp.zslabH[sd][0] <= sb.c1 && fp.zslabH[sd][1] >= sb.c0) pmz = true;
+				for (int w=0; w<2; w++) {
+					fp.psiEi[sd][w] = e->psib[ALISB_SET_E][m][sd][w]; fp.psiEo[sd][w] = e->psi[ALISB_SET_E][m][2][sd][w];
+					fp.psiHi[sd][w] = e->psi[ALISB_SET_H][m][2][sd][w]; fp.psiHo[sd][w] = e->psib[ALISB_SET_H][m][sd][w];
+				}
+			}
+			fp.PzE[0] = e->P[ALISB_SET_E][2]; fp.PzE[1] = e->P1[ALISB_SET_E][2]; fp.PzE[2] = e->P2[ALISB_SET_E][2];
+			fp.PzH[0] = e->P[ALISB_SET_H][2]; fp.PzH[1] = e->P1[ALISB_SET_H][2]; fp.PzH[2] = e->P2[ALISB_SET_H][2];
 			fp.a_first = sb.a0; fp.a_last = sb.a1; fp.nseg = div_up(sb.a1 - sb.a0 + 1, 128);
 			fp.b_first = sb.b0; fp.b_last = sb.b1; fp.c_first = sb.c0; fp.c_last = sb.c1;
-			const int frows = e->tune_frows == 16 ? 16 : 8;
+			const int frows = e->tune_frows == 16 ? 16 : e->tune_frows == 15 ? 15 : 8;
 			const int nzs = sb.c1 - sb.c0 + 1, gyf = div_up(sb.b1 - sb.b0 + 1, frows);
 			fp.cchunk = std::min(nzs, std::max(1, e->tune_fchunk));
 			dim3 grid(fp.nseg, gyf, div_up(nzs, fp.cchunk)), block(32, frows + 1, 1);
@@ -891,16 +977,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			/* profiling counts cell-passes: a fused launch does two passes per cell */
 			cudaEvent_t e1 = prof_begin(st, sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
 			if (e->tune_debug && e->launches < 64) fprintf(stderr, "[alisb] fused E+H cells %d..%d rows %d..%d planes %d..%d grid %dx%dx%d chunk %d\n", sb.a0, sb.a1, sb.b0, sb.b1, sb.c0, sb.c1, grid.x, grid.y, grid.z, fp.cchunk);
-			static bool smem_set = false;
-			if (!smem_set) {
-				CU(cudaFuncSetAttribute(yee_fused<8,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,false>)));
-				CU(cudaFuncSetAttribute(yee_fused<8,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8,true>)));
-				CU(cudaFuncSetAttribute(yee_fused<16,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,false>)));
-				CU(cudaFuncSetAttribute(yee_fused<16,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16,true>)));
-				smem_set = true;
-			}
-			if (frows == 16) { if (eps) yee_fused<16,true><<<grid, block, sizeof(FusedSmem<16,true>), st>>>(fp); else yee_fused<16,false><<<grid, block, sizeof(FusedSmem<16,false>), st>>>(fp); }
-			else             { if (eps) yee_fused<8,true><<<grid, block, sizeof(FusedSmem<8,true>), st>>>(fp);  else yee_fused<8,false><<<grid, block, sizeof(FusedSmem<8,false>), st>>>(fp); }
+			launch_fused(st, fp, grid, block, frows, eps, pmz);
 			e->launches++; e->fused_launches++;
 			if (e->profiling) CU(cudaEventRecord(e1, st));
 			continue;
@@ -1247,14 +1324,31 @@ static int apply_copies(alisb_engine *e, int set)
 		CU(cudaGetLastError());
 		return ALISB_OK;
 	}
+	/* large planes: one launch per copy.  A copy reads and writes one component (and its imaginary twin), so the
+	 * ordered list falls into up to three independent chains, one per component: they run side by side (the
+	 * launches are latency-bound: a 2048 x 256 x-plane is 0.5 M scattered 4-byte accesses) */
+	float *chain_of[3] = {0, 0, 0};
+	int nchain = 0;
+	const bool conc = e->tune_conc > 0;
+	bool forked = false, used[3] = {false, false, false};
 	for (const alisb_copy &k : e->copies[set]) {
 		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
 		const size_t n = bcount(B);
 		if (!n) continue;
 		float *F = e->F[k.set][0][k.comp], *G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
-		copy_plane<<<div_up(n, 256), 256, 0, e->stream>>>(F, G, k.cosk, k.sink, B, e->ny, e->pitch, k.alt[0], k.alt[1], k.alt[2]);
+		int q = 0;
+		while (q < nchain && chain_of[q] != F) q++;
+		if (q == nchain && nchain < 3) chain_of[nchain++] = F;
+		cudaStream_t st = e->stream;
+		if (conc && q > 0 && q < 3) {                     /* chain 0 stays on the engine's stream */
+			if (!forked) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
+			if (!used[q]) { CU(cudaStreamWaitEvent(e->side[q], e->ev_fork, 0)); used[q] = true; }
+			st = e->side[q];
+		}
+		copy_plane<<<div_up(n, 256), 256, 0, st>>>(F, G, k.cosk, k.sink, B, e->ny, e->pitch, k.alt[0], k.alt[1], k.alt[2]);
 		e->launches++;
 	}
+	for (int q=1; q<3; q++) if (used[q]) { CU(cudaEventRecord(e->ev_join[q], e->side[q])); CU(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0)); }
 	CU(cudaGetLastError());
 	return ALISB_OK;
 }
@@ -1480,6 +1574,8 @@ extern "C" int alisb_reset_fields(alisb_engine *e)
 		if (e->dbuf) for (int c=0; c<3; c++) CU(cudaMemsetAsync(e->Fb[s][m][c], 0, e->elems*sizeof(float), e->stream));
 		for (int ax=0; ax<3; ax++) for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++)
 			if (e->psi[s][m][ax][sd][w]) CU(cudaMemsetAsync(e->psi[s][m][ax][sd][w], 0, e->psi_elems[s][ax][sd]*sizeof(float), e->stream));
+		for (int sd=0; sd<2; sd++) for (int w=0; w<2; w++)
+			if (e->psib[s][m][sd][w]) CU(cudaMemsetAsync(e->psib[s][m][sd][w], 0, e->psi_elems[s][2][sd]*sizeof(float), e->stream));
 	}
 	for (DispObj *o : e->obj) for (int m=0; m<=e->g.complex_field; m++) for (int p=0; p<o->d.nk; p++) for (int c=0; c<3; c++) {
 		CU(cudaMemsetAsync(o->J[m][p][c], 0, o->cnt*sizeof(float), e->stream));
@@ -1584,11 +1680,21 @@ static int rw_box_one(alisb_engine *e, int arr, const int32_t ids[6], const int3
 static int rw_box(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
 {
 	DEV(e);
+	/* in-place fused stepping cannot take back the H' it has already formed: after alisb_flush(e, 1) the H pass must
+	 * follow before anything is written (the public API never opens this window: updateH issues both at once) */
+	if (write && e->h_fused && e->tune_wave > 0) return fail(ALISB_ESTATE, "in-place fused stepping: no writes between alisb_flush(e, 1) and the H pass");
 	if (write) UNFUSE(e); else SETTLE(e);
 	TRY(rw_box_one(e, arr, ids, box, host, write));
 	if (write && arr == ALISB_ARR_FIELD && e->dbuf) {
 		/* both buffers, so that ghost cells and cells no pass rewrites stay in agreement */
 		float **cur = &e->F[ids[0]][ids[2]][ids[1]], **oth = &e->Fb[ids[0]][ids[2]][ids[1]];
+		std::swap(*cur, *oth);
+		const int r = rw_box_one(e, arr, ids, box, host, true);
+		std::swap(*cur, *oth);
+		return r;
+	}
+	if (write && arr == ALISB_ARR_PSI && ids[2] == 2 && e->dbuf && e->psib[ids[0]][ids[1]][ids[3]][ids[4]]) {
+		float **cur = &e->psi[ids[0]][ids[1]][2][ids[3]][ids[4]], **oth = &e->psib[ids[0]][ids[1]][ids[3]][ids[4]];
 		std::swap(*cur, *oth);
 		const int r = rw_box_one(e, arr, ids, box, host, true);
 		std::swap(*cur, *oth);

@@ -46,6 +46,7 @@ struct VolParams {
 	const float *dtd[3];          /* dtdx (stored shifted by XO), dtdy, dtdz            */
 	const float *P[3], *P1[3], *P2[3];   /* CPML tables per axis (x ones shifted by XO) */
 	float       *psi[3][2][2];    /* [axis][side][which]                                */
+	const float *psiz_in[2][2];   /* z slabs: where the old values are read ([side][which]): == psi[2] (in place) or the other buffer (double-buffered mode) */
 	int slab[3][2][2];            /* [axis][side]{first,last} in array coordinates      */
 	int xbase[2], xpitch[2];      /* x-slab psi arrays: slot = a - xbase, row pitch      */
 	int nx, ny, nz, pitch;
@@ -277,7 +278,7 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 					const float zP = __ldg(p.P[2] + c), zP1 = __ldg(p.P1[2] + c), zP2 = __ldg(p.P2[2] + c);
 					const size_t po = ((size_t)(c - p.slab[2][zs][0])*(p.ny + 2) + b)*p.pitch + ALISB_XO + a0;
 					float *q0p = p.psi[2][zs][0] + po, *q1p = p.psi[2][zs][1] + po;
-					float4 q0 = ld4(q0p), q1 = ld4(q1p);
+					float4 q0 = ld4(p.psiz_in[zs][0] + po), q1 = ld4(p.psiz_in[zs][1] + po);
 					float v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
 					#pragma unroll
 					for (int e = 0; e < 4; e++) {
@@ -372,6 +373,11 @@ struct FusedParams {
 	int ny, pitch; size_t plane;
 	int a_first, a_last, nseg;        /* a_first = 1 mod 4, (a_last - a_first + 1) % 4 == 0  */
 	int b_first, b_last, c_first, c_last, cchunk;
+	/* PMZ variant: planes of the box may lie in z CPML slabs (update.c:74-84 inside the fused sweep) */
+	const float *PzE[3], *PzH[3];     /* z tables P, P1, P2 of the E and of the H set         */
+	const float *psiEi[2][2], *psiHi[2][2];   /* [side][which] z-slab psi arrays: old values ...  */
+	float *psiEo[2][2], *psiHo[2][2];         /* ... and where the new ones go (the other buffer) */
+	int zslabE[2][2], zslabH[2][2];   /* [side]{first,last} plane of the slab (first > last: none) */
 };
 
 /* cp.async staging: every global load of the kernel is issued two planes ahead into shared memory
@@ -404,7 +410,7 @@ template <int ROWS, bool EPS> struct FusedSmem {
 	float4 sx[2][ROWS+1][32], sz[2][ROWS+1][32];   /* E'x, E'z rows of a plane, for the row above */
 };
 
-template <int ROWS, bool EPS>
+template <int ROWS, bool EPS, bool PMZ>
 __global__ void __launch_bounds__(32*(ROWS+1), ROWS == 8 ? 2 : 1)
 yee_fused(const __grid_constant__ FusedParams p)
 {
@@ -482,6 +488,25 @@ yee_fused(const __grid_constant__ FusedParams p)
 		const size_t o = (size_t)c*p.plane + row;
 		const float dze = dze_next, dzh = dzh_next;
 		if (c > cf - 1) { dze_next = __ldg(p.dtdE[2] + c - 1); dzh_next = __ldg(p.dtdH[2] + c); }
+		/* z CPML slabs (PMZ): the psi values of plane c (E set) and of plane c+1 (H set) are requested before the
+		 * barrier and used after the curls; only slab planes pay for them */
+		int zsE = -1, zsH = -1;
+		float4 qe0 = zero4, qe1 = zero4, qh0 = zero4, qh1 = zero4;
+		float qeh = 0.f;
+		size_t pe = 0, ph = 0;
+		if (PMZ) {
+			if (c >= p.zslabE[0][0] && c <= p.zslabE[0][1]) zsE = 0; else if (c >= p.zslabE[1][0] && c <= p.zslabE[1][1]) zsE = 1;
+			if (it > 0) { if (c + 1 >= p.zslabH[0][0] && c + 1 <= p.zslabH[0][1]) zsH = 0; else if (c + 1 >= p.zslabH[1][0] && c + 1 <= p.zslabH[1][1]) zsH = 1; }
+			if (zsE >= 0 && act) {
+				pe = (size_t)(c - p.zslabE[zsE][0])*p.plane + row;
+				qe0 = ld4(p.psiEi[zsE][0] + pe); qe1 = ld4(p.psiEi[zsE][1] + pe);
+				if (xh) qeh = p.psiEi[zsE][1][pe - 1];
+			}
+			if (zsH >= 0 && own) {
+				ph = (size_t)(c + 1 - p.zslabH[zsH][0])*p.plane + row;
+				qh0 = ld4(p.psiHi[zsH][0] + ph); qh1 = ld4(p.psiHi[zsH][1] + ph);
+			}
+		}
 		cp_async_wait<AHEAD - 1>();                         /* this thread's copies of plane c have landed */
 		__syncthreads();                                    /* ... and everybody else's; iteration it-1 is over everywhere */
 		{                                                   /* plane c-AHEAD goes into the stage iteration it-1 used */
@@ -521,6 +546,25 @@ yee_fused(const __grid_constant__ FusedParams p)
 					Ex[e] += ux*Cx[e]; Ey[e] += uy*Cy[e]; Ez[e] += uz*Cz[e];
 				} else { Ex[e] += ux; Ey[e] += uy; Ez[e] += uz; }
 			}
+			if (PMZ && zsE >= 0 && act) {
+				/* update.c:77-78 (psi) and :79-80 (their contribution) as in yee_body<+1>, PM & 4; also on the halo
+				 * row and the halo plane, whose new psi is formed but not stored */
+				const float zP = __ldg(p.PzE[0] + c), zP1 = __ldg(p.PzE[1] + c), zP2 = __ldg(p.PzE[2] + c);
+				float v0[4] = {qe0.x, qe0.y, qe0.z, qe0.w}, v1[4] = {qe1.x, qe1.y, qe1.z, qe1.w};
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					v0[e] = zP*v0[e] + zP1*(Hy[e] - Hyp[e]);
+					v1[e] = zP*v1[e] + zP2*(Hx[e] - Hxp[e]);
+					if (EPS) {
+						const float Cx[4] = {cx4.x, cx4.y, cx4.z, cx4.w}, Cy[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
+						Ex[e] += v0[e]*Cx[e]; Ey[e] += v1[e]*Cy[e];
+					} else { Ex[e] += v0[e]; Ey[e] += v1[e]; }
+				}
+				if (own && c >= cf) {
+					st4(p.psiEo[zsE][0] + pe, make_float4(v0[0], v0[1], v0[2], v0[3]));
+					st4(p.psiEo[zsE][1] + pe, make_float4(v1[0], v1[1], v1[2], v1[3]));
+				}
+			}
 		}
 		/* the cell a0-1 (lane 0): E'y and E'z only */
 		float eyh = 0.f, ezh = 0.f, hxh = 0.f;
@@ -534,6 +578,11 @@ yee_fused(const __grid_constant__ FusedParams p)
 			} else {
 				eyh = eyo + (dxeh*(hzh - hz.x) + dze*(hxp1 - hxh));
 				ezh = ezo + (dye*(hxh - hxnh) + dxeh*(hy.x - hyh));
+			}
+			if (PMZ && zsE >= 0) {
+				const float zP = __ldg(p.PzE[0] + c), zP2 = __ldg(p.PzE[2] + c);
+				const float v1h = zP*qeh + zP2*(hxh - hxp1);
+				if (EPS) eyh += v1h*cyh; else eyh += v1h;
 			}
 		}
 		const float4 nex = make_float4(Ex[0], Ex[1], Ex[2], Ex[3]), ney = make_float4(Ey[0], Ey[1], Ey[2], Ey[3]), nez = make_float4(Ez[0], Ez[1], Ez[2], Ez[3]);
@@ -556,6 +605,19 @@ yee_fused(const __grid_constant__ FusedParams p)
 					const float uy = DxH[e]*(gz5[e+1] - gz5[e]) + dzh*(Ex[e] - Gx[e]);
 					const float uz = dyh*(Gx[e] - Gxn[e]) + DxH[e]*(gy5[e] - gy5[e+1]);
 					Hx[e] += ux; Hy[e] += uy; Hz[e] += uz;
+				}
+				if (PMZ && zsH >= 0) {
+					/* update.c:77-80 as in yee_body<-1>: plane c+1 of the H set, differences against E'(c) */
+					const float zP = __ldg(p.PzH[0] + c + 1), zP1 = __ldg(p.PzH[1] + c + 1), zP2 = __ldg(p.PzH[2] + c + 1);
+					float v0[4] = {qh0.x, qh0.y, qh0.z, qh0.w}, v1[4] = {qh1.x, qh1.y, qh1.z, qh1.w};
+					#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						v0[e] = zP*v0[e] + zP1*(Gy[e] - Ey[e]);
+						v1[e] = zP*v1[e] + zP2*(Gx[e] - Ex[e]);
+						Hx[e] += v0[e]; Hy[e] += v1[e];
+					}
+					st4(p.psiHo[zsH][0] + ph, make_float4(v0[0], v0[1], v0[2], v0[3]));
+					st4(p.psiHo[zsH][1] + ph, make_float4(v1[0], v1[1], v1[2], v1[3]));
 				}
 				st4(p.Ho[0] + op, make_float4(Hx[0], Hx[1], Hx[2], Hx[3]));
 				st4(p.Ho[1] + op, make_float4(Hy[0], Hy[1], Hy[2], Hy[3]));

@@ -248,11 +248,13 @@ def test_chi2_coupling_seeded_bit_exact(oracle_lib, engine_lib, alias):
 
 
 # ---- fused E+H stepping (temporal blocking): must be bit-identical to the two-pass oracle ----------
-@pytest.fixture(params=[0, 1], ids=["out-of-place", "in-place-wavefront"])
+@pytest.fixture(params=[(0, 0), (0, 1), (1, 0)], ids=["out-of-place", "out-of-place-zslabs", "in-place-wavefront"])
 def fusion_env(monkeypatch, request):
     """engines created under this fixture fuse whatever they can, however small the grid; both fused
-    kernels: yee_fused (double-buffered fields, halo recomputed) and yee_wave (in place, tile wavefront)"""
-    monkeypatch.setenv("ALISB_WAVE", str(request.param))
+    kernels: yee_fused (double-buffered fields, halo recomputed; also its opt-in variant that carries the z CPML
+    slabs inside the fused box) and yee_wave (in place, tile wavefront)"""
+    monkeypatch.setenv("ALISB_WAVE", str(request.param[0]))
+    monkeypatch.setenv("ALISB_FUSE_PMZ", str(request.param[1]))
     monkeypatch.setenv("ALISB_FUSE", "1")
     monkeypatch.setenv("ALISB_FUSE_MIN", "1")
     monkeypatch.setenv("ALISB_SMALL", "1")
@@ -268,6 +270,7 @@ _add_materials = helpers.add_materials
     ((96, 40, 90), 8, 25, False),      # long z: several z-chunks per range
     ((160, 72, 64), 12, 30, True),     # material arrays and an ADE object inside the fused box
     ((96, 40, 90), 8, 25, True),
+    ((96, 64, 76), 24, 30, False),     # true CPML (Num=24: kappa, alpha): more than half of the fused planes lie in z slabs
 ])
 @pytest.mark.parametrize("rows", [8, 16])
 def test_fused_stepping_bit_exact(oracle_lib, engine_lib, fusion_env, monkeypatch, shape, num, steps, materials, rows):
@@ -294,6 +297,36 @@ def test_fused_stepping_bit_exact(oracle_lib, engine_lib, fusion_env, monkeypatc
         e.step_H()
         e.run(2)
     helpers.assert_fields_identical(g, o, f"fused box {shape} after interleaved access")
+    compare_psi(g, o)
+
+
+def test_fused_flush_then_access(oracle_lib, engine_lib, fusion_env):
+    """alisb_flush(e, 1) issues the fused kernel (E' and, speculatively, H' and the H set's z-slab psi of the fused box);
+    a field write before the H pass must make the H pass recompute all of it from the changed E"""
+    shape = (160, 56, 44)
+    in_place = os.environ.get("ALISB_WAVE") == "1"
+    w, g, o = both(oracle_lib, engine_lib, shape, num=8)
+    helpers.seed_fields([g, o], tuple(n + 2 for n in shape))
+    rng = np.random.RandomState(5)
+    patch = rng.rand(6, 5, 4).astype(np.float32) * 1e-3
+    for e in (g, o):
+        e.run(3)
+        e.step_E()
+        e.flush(True)
+        if in_place and e is g:
+            with pytest.raises(capi.EngineError):      # in-place stepping has already formed H': writes are refused here
+                e.write_box(capi.ARR_FIELD, [0, 0, 0], [60, 65, 20, 24, 3, 6], patch)
+        elif not in_place:
+            e.write_box(capi.ARR_FIELD, [0, 0, 0], [60, 65, 20, 24, 3, 6], patch)      # inside the low z slab
+        e.step_H()
+        e.run(2)
+        e.step_E()
+        e.flush(True)
+        e.read_box(capi.ARR_FIELD, [1, 2, 0], [1, 4, 1, 4, 1, 4])
+        e.step_H()
+        e.run(3)
+    helpers.assert_fields_identical(g, o, "flush, then access, then H pass")
+    compare_psi(g, o)
 
 
 def test_fused_write_between_passes(oracle_lib, engine_lib, fusion_env):
