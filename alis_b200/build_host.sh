@@ -13,7 +13,7 @@ CC=${ALIS_HOST_CC:-gcc}
 OBJ=$HERE/host/obj
 mkdir -p "$OBJ" "$ROOT/tests/bin"
 CFLAGS="-std=c99 -O3 -fopenmp -fPIC -w -I$ROOT/include -I$HERE/host"
-SRCS="world object shapes source update view fields output slices phaser farfld engine_bridge h5lite"
+SRCS="world object shapes source update view fields output slices phaser farfld engine_bridge shard h5lite"
 OBJS=""
 for f in $SRCS; do
 	$CC $CFLAGS -c "$HERE/host/$f.c" -o "$OBJ/$f.o"

@@ -128,6 +128,7 @@ def _declare(lib):
         "alisb_halo_info": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "alisb_halo_pack": (i, [vp, i]),
         "alisb_halo_unpack": (i, [vp, i]),
+        "alisb_halo_exchange": (i, [vp, vp, i]),
         "alisb_phaser_create": (i, [vp, i32p, i, i, C.POINTER(vp)]),
         "alisb_phaser_destroy": (None, [vp]),
         "alisb_phaser_accumulate": (i, [vp, f32p, f32p]),

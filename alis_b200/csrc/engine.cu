@@ -119,6 +119,7 @@ struct alisb_engine {
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
 	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
+	cudaEvent_t ev_halo;               /* alisb_halo_exchange: orders the peer copy between the two engines' streams */
 	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
 	int f_lo, f_hi;                    /* plane filter of the current (partial) pass: ops act on c in [f_lo,f_hi] */
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
@@ -357,6 +358,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
+	if (e->ev_halo) cudaEventDestroy(e->ev_halo);
 	cudaFree(e->scratch); cudaFree(e->d_ade[0]); cudaFree(e->d_ade[1]);
 	cudaFree(e->d_wave_ticket); cudaFree(e->d_wave_progress); cudaFree(e->d_wave_error);
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
@@ -2086,6 +2088,46 @@ extern "C" int alisb_halo_info(alisb_engine *e, int set, int m, int comp, void *
 }
 extern "C" int alisb_halo_pack(alisb_engine *e, int set) { (void)e; (void)set; return ALISB_OK; }
 extern "C" int alisb_halo_unpack(alisb_engine *e, int set) { (void)e; (void)set; return ALISB_OK; }
+
+/* both slabs in one process (host/shard.c): the plane crosses the cut as a peer copy on the owner's stream */
+extern "C" int alisb_halo_exchange(alisb_engine *lower, alisb_engine *upper, int set)
+{
+	if (!lower || !upper || set < 0 || set > 1) return fail(ALISB_EINVAL, "halo exchange: bad argument");
+	if (lower->nx != upper->nx || lower->ny != upper->ny || lower->plane != upper->plane || lower->g.complex_field != upper->g.complex_field)
+		return fail(ALISB_EINVAL, "halo exchange: slabs differ in x, y or field sets");
+	alisb_engine *src = set == ALISB_SET_E ? lower : upper, *dst = set == ALISB_SET_E ? upper : lower;
+	if (src->g.device != dst->g.device) {
+		/* direct peer access (NVLink / NVSwitch) once per ordered pair; without it the copy is staged by the driver */
+		static unsigned long long tried[64];
+		const int a = src->g.device & 63, b = dst->g.device & 63;
+		if (!(tried[a] >> b & 1ull)) {
+			tried[a] |= 1ull << b; tried[b] |= 1ull << a;
+			int ok = 0;
+			if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok) { cudaSetDevice(a); cudaDeviceEnablePeerAccess(b, 0); }
+			ok = 0;
+			if (cudaDeviceCanAccessPeer(&ok, b, a) == cudaSuccess && ok) { cudaSetDevice(b); cudaDeviceEnablePeerAccess(a, 0); }
+			cudaGetLastError();                             /* "already enabled" is fine */
+		}
+	}
+	/* the plane must exist (a deferred E pass is issued now, as the plain variant) and the receiver must be done with
+	 * the old ghost plane */
+	{ alisb_engine *e = src; DEV(e); SETTLE(e); }
+	{ alisb_engine *e = dst; DEV(e); SETTLE(e); if (!e->ev_halo) CU(cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming)); CU(cudaEventRecord(e->ev_halo, e->stream)); }
+	{
+		alisb_engine *e = src; DEV(e);
+		if (!e->ev_halo) CU(cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming));
+		CU(cudaStreamWaitEvent(e->stream, dst->ev_halo, 0));
+		for (int m=0; m<=e->g.complex_field; m++) for (int comp=0; comp<2; comp++) {
+			void *sp = 0, *rp = 0; size_t nb = 0;
+			TRY(alisb_halo_info(src, set, m, comp, &sp, 0, &nb));
+			TRY(alisb_halo_info(dst, set, m, comp, 0, &rp, 0));
+			CU(cudaMemcpyPeerAsync(rp, dst->g.device, sp, src->g.device, nb, e->stream));
+		}
+		CU(cudaEventRecord(e->ev_halo, e->stream));
+	}
+	{ alisb_engine *e = dst; DEV(e); CU(cudaStreamWaitEvent(e->stream, src->ev_halo, 0)); }
+	return ALISB_OK;
+}
 
 /* ---- phasers -------------------------------------------------------------------------------- */
 extern "C" int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int face_mask, int nfreq, alisb_phaser **out)

@@ -18,12 +18,15 @@
 #include "alis_c.h"
 #include "alis_b200.h"
 #include "engine_bridge.h"
+#include "shard.h"
 
 typedef struct wave_ctx { world W; source S; } wave_ctx;
 
 struct alis_bridge {
 	world W;
-	alisb_engine *E;
+	alis_shards *S;                 /* one engine, or one per device: z slabs of W (ALIS_DEVICES), or replicas of an auxiliary world */
+	alisb_engine *E;                /* the first (with one device: the only) engine */
+	int devices[16];
 	struct alis_bridge *aux[8]; int naux;
 	wave_ctx *ctx; int nctx, cap_ctx;
 	int dirty;                      /* DIRTY_* bits: what must be re-uploaded before the next step */
@@ -35,6 +38,11 @@ enum { DIRTY_TABLES = 1, DIRTY_MATERIALS = 2, DIRTY_SOURCES = 4, DIRTY_COPIES = 
 #ifdef ALIS_B200_HOST
 alis_bridge *alis_host_bridge(world W);        /* host layer: every world owns its bridge */
 #endif
+
+/* how the next bridge is created: a world of its own is cut into z slabs over the devices ALIS_DEVICES names;
+ * the auxiliary world of a TFSF source gets one full copy per engine of its main world (push_tfsf) */
+static int create_mode = ALIS_SHARDS_SPLIT, create_n = 0;
+static const int *create_dev = 0;
 
 static float wave_trampoline(void *user, float t, float phase)
 {
@@ -77,14 +85,14 @@ static void push_tables(alis_bridge *B, int set, coeffs *C)
 		float *b = P[ax] ? table(P[ax], MIN[ax], NUM[ax]) : 0;
 		float *c = P[ax] ? table(P1[ax], MIN[ax], NUM[ax]) : 0;
 		float *d = P[ax] ? table(P2[ax], MIN[ax], NUM[ax]) : 0;
-		CHECK(alisb_set_axis_tables(B->E, set, ax, a, b, c, d));
+		CHECK(alis_shards_set_axis_tables(B->S, set, ax, a, b, c, d));
 		free(a); free(b); free(c); free(d);
 	}
 	/* cell sizes, for the device-side flux integrals (reference output.c:233-332) */
 	const float *ds[3] = {C->dx, C->dy, C->dz};
 	for (int ax=0; ax<3; ax++) {
 		float *a = table(ds[ax], MIN[ax], NUM[ax]);
-		CHECK(alisb_set_spacing(B->E, set, ax, a));
+		CHECK(alis_shards_set_spacing(B->S, set, ax, a));
 		free(a);
 	}
 }
@@ -142,7 +150,7 @@ static void push_copies(alis_bridge *B)
 		add_copy(L,&n,W, E,Y, W->coskyp,-W->sinkyp, 1,i1+1,  j1+1,j1+1, k0,k1, i0,1-W->jNUM,0);
 	}
 	else add_copy(L,&n,W, E,Y, W->cosky,-W->sinky, i0,i1, j1+1,j1+1, k0,k1, 0,-jAlt,0);
-	CHECK(alisb_set_copies(B->E, E, L, n));
+	CHECK(alis_shards_set_copies(B->S, E, L, n));
 
 	n = 0;
 	const float cxm = W->xMaxSur==PEC ? 1 : W->coskx, cym = W->yMaxSur==PEC ? 1 : W->cosky, czm = W->zMaxSur==PEC ? 1 : W->coskz;
@@ -171,18 +179,18 @@ static void push_copies(alis_bridge *B)
 		add_copy(L,&n,W, H,Z, W->cosky, W->sinky, i0,i1+1, j0,j0, k0,k1+1, 0,jAlt,0);
 		add_copy(L,&n,W, H,X, W->cosky, W->sinky, i0,i1+1, j0,j0, k0,k1+1, 0,jAlt,0);
 	}
-	CHECK(alisb_set_copies(B->E, H, L, n));
+	CHECK(alis_shards_set_copies(B->S, H, L, n));
 }
 
 static void push_materials(alis_bridge *B)
 {
 	world W = B->W;
 	coeffs *C = W->CE;
-	CHECK(alisb_clear_dispersive(B->E));
+	CHECK(alis_shards_clear_dispersive(B->S));
 	if (C->x && C->y && C->z)
-		CHECK(alisb_set_inv_eps(B->E, &C->x[W->iMIN][W->jMIN][W->kMIN], &C->y[W->iMIN][W->jMIN][W->kMIN], &C->z[W->iMIN][W->jMIN][W->kMIN]));
+		CHECK(alis_shards_set_inv_eps(B->S, &C->x[W->iMIN][W->jMIN][W->kMIN], &C->y[W->iMIN][W->jMIN][W->kMIN], &C->z[W->iMIN][W->jMIN][W->kMIN]));
 	else
-		CHECK(alisb_set_inv_eps(B->E, 0, 0, 0));
+		CHECK(alis_shards_set_inv_eps(B->S, 0, 0, 0));
 	for (int o=0; o<C->N; o++) {
 		alisb_dispersive d;
 		memset(&d, 0, sizeof d);
@@ -198,7 +206,7 @@ static void push_materials(alis_bridge *B)
 		d.fill[0] = &C->Jx[o][C->iMin[o]][C->jMin[o]][C->kMin[o]];
 		d.fill[1] = &C->Jy[o][C->iMin[o]][C->jMin[o]][C->kMin[o]];
 		d.fill[2] = &C->Jz[o][C->iMin[o]][C->jMin[o]][C->kMin[o]];
-		CHECK(alisb_add_dispersive(B->E, &d));
+		CHECK(alis_shards_add_dispersive(B->S, &d));
 	}
 }
 
@@ -220,7 +228,7 @@ static void push_source_list(alis_bridge *B, source S, int set)
 		wave_ctx *c = &B->ctx[B->nctx++];
 		c->W = W; c->S = S;
 		d.waveform = wave_trampoline; d.user = c;
-		CHECK(alisb_add_source(B->E, &d));
+		CHECK(alis_shards_add_source(B->S, &d));
 	}
 }
 
@@ -281,6 +289,10 @@ static void push_tfsf(alis_bridge *B, tfsf S)
 		add_strip(LH,&nH,W, X,Y, +hz[S->kMax+1], 0, S->iMin,S->iMax, S->jMIN,S->jMAX, S->kMax+1,S->kMax+1, 0,0,-1);
 	}
 
+	/* the auxiliary world: one engine per engine of this world (every z slab steps its own copy) */
+	const int outer_mode = create_mode, outer_n = create_n;
+	const int *outer_dev = create_dev;
+	create_mode = ALIS_SHARDS_REPLICA; create_n = alis_shards_count(B->S); create_dev = B->devices;
 #ifdef ALIS_B200_HOST
 	alis_bridge *AB = alis_host_bridge(A);      /* owned by the auxiliary world itself */
 	B->owns_aux = 0;
@@ -288,13 +300,18 @@ static void push_tfsf(alis_bridge *B, tfsf S)
 	alis_bridge *AB = alis_bridge_create(A);
 	B->owns_aux = 1;
 #endif
+	create_mode = outer_mode; create_n = outer_n; create_dev = outer_dev;
+	if (alis_shards_count(AB->S) != alis_shards_count(B->S) || (alis_shards_count(B->S) > 1 && alis_shards_mode(AB->S) != ALIS_SHARDS_REPLICA)) {
+		printf("alis-b200 engine: the auxiliary world of a TFSF source was stepped on its own before the main world was first used; with ALIS_DEVICES naming several devices that is not supported\n");
+		exit(1);
+	}
 	alis_bridge_commit(AB);
 	if (B->naux >= 8) { printf("alis-b200 engine: too many TFSF regions\n"); exit(1); }
 	B->aux[B->naux++] = AB;
 
 	alisb_tfsf t;
 	memset(&t, 0, sizeof t);
-	t.aux = AB->E;
+	t.aux = AB->E;                              /* the shard layer substitutes the copy that lives with each slab */
 	t.offset[0] = W->iMIN - A->iMIN; t.offset[1] = W->jMIN - A->jMIN; t.offset[2] = W->kMIN - A->kMIN;
 	/* pointer aliasing of source.c:223-248,298-317: rows past the collapsed aux extent alias row
 	 * MAX+Alt, Alt = 1 for the components staggered along that axis.                        */
@@ -305,7 +322,7 @@ static void push_tfsf(alis_bridge *B, tfsf S)
 	}
 	t.strips_E = LE; t.n_strips_E = nE;
 	t.strips_H = LH; t.n_strips_H = nH;
-	CHECK(alisb_add_tfsf(B->E, &t));
+	CHECK(alis_shards_add_tfsf(B->S, &t, AB->S));
 }
 
 alis_bridge *alis_bridge_create(world W)
@@ -314,8 +331,19 @@ alis_bridge *alis_bridge_create(world W)
 	alisb_grid g;
 	B->W = W;
 	fill_grid(W, &g);
-	g.device = alis_bridge_device();
-	CHECK(alisb_create(&g, &B->E));
+	int n = 0, mode = create_mode;
+	if (create_n > 0) { n = create_n; memcpy(B->devices, create_dev, sizeof(int)*n); }       /* an auxiliary world follows its main world */
+	else {
+		n = alis_shards_env_devices(B->devices, 16);
+		if (n == 1 && !getenv("ALIS_DEVICES")) B->devices[0] = alis_bridge_device();
+		if (n > 1 && (W->zMinSur == PBC || W->zMinSur == BBC)) {
+			printf("alis-b200: the world is periodic along z: not cut into z slabs, it runs on device %d alone\n", B->devices[0]);
+			n = 1;
+		}
+	}
+	g.device = B->devices[0];
+	CHECK(alis_shards_create(&g, B->devices, n, mode, &B->S));
+	B->E = alis_shards_engine(B->S, 0);
 	B->cap_ctx = 512;
 	B->ctx = calloc(B->cap_ctx, sizeof(wave_ctx));
 	B->dirty = DIRTY_ALL;
@@ -332,12 +360,15 @@ void alis_bridge_destroy(alis_bridge *B)
 {
 	if (!B) return;
 	drop_aux(B);
-	alisb_destroy(B->E);
+	alis_shards_destroy(B->S);
 	free(B->ctx);
 	free(B);
 }
 
 alisb_engine *alis_bridge_engine(alis_bridge *B) { return B->E; }
+int alis_bridge_engines(alis_bridge *B) { return alis_shards_count(B->S); }
+int alis_bridge_read_box(alis_bridge *B, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return alis_shards_read_box(B->S, arr, ids, box, host); }
+int alis_bridge_reset_fields(alis_bridge *B) { return alis_shards_reset_fields(B->S); }
 
 /* (re)upload whatever changed since the last commit; the field state is never touched */
 void alis_bridge_commit(alis_bridge *B)
@@ -351,14 +382,14 @@ void alis_bridge_commit(alis_bridge *B)
 	if (B->dirty & DIRTY_MATERIALS) push_materials(B);
 	if (B->dirty & (DIRTY_COPIES|DIRTY_SOURCES)) push_copies(B);
 	if (B->dirty & DIRTY_SOURCES) {
-		CHECK(alisb_clear_sources(B->E));
+		CHECK(alis_shards_clear_sources(B->S));
 		drop_aux(B);
 		B->nctx = 0;
 		for (tfsf S = W->S; S; S = S->S) push_tfsf(B, S);
 		push_source_list(B, W->SE, ALISB_SET_E);
 		push_source_list(B, W->SH, ALISB_SET_H);
 	}
-	CHECK(alisb_set_time(B->E, W->n, W->t, W->E->t, W->H->t));
+	CHECK(alis_shards_set_time(B->S, W->n, W->t, W->E->t, W->H->t));
 	B->dirty = 0;
 }
 
@@ -368,7 +399,7 @@ static void pull_time(alis_bridge *B)
 {
 	world W = B->W;
 	uint64_t step; float t, tE, tH;
-	CHECK(alisb_get_time(B->E, &step, &t, &tE, &tH));
+	CHECK(alis_shards_get_time(B->S, &step, &t, &tE, &tH));
 	W->n = step; W->t = t; W->E->t = tE; W->H->t = tH;
 	for (int q=0; q<B->naux; q++) pull_time(B->aux[q]);
 }
@@ -376,14 +407,14 @@ static void pull_time(alis_bridge *B)
 void alis_bridge_step_E(alis_bridge *B)
 {
 	if (B->dirty) alis_bridge_commit(B);
-	CHECK(alisb_step_E(B->E));
+	CHECK(alis_shards_step_E(B->S));
 	pull_time(B);
 }
 
 void alis_bridge_step_H(alis_bridge *B)
 {
 	if (B->dirty) alis_bridge_commit(B);
-	CHECK(alisb_step_H(B->E));
+	CHECK(alis_shards_step_H(B->S));
 	pull_time(B);
 }
 
@@ -394,6 +425,7 @@ void alis_bridge_chi2(alis_bridge *S, alis_bridge *P1, alis_bridge *P2, float al
 	if (S->dirty) alis_bridge_commit(S);
 	if (P1->dirty) alis_bridge_commit(P1);
 	if (P2->dirty) alis_bridge_commit(P2);
+	if (alis_shards_count(S->S) > 1 || alis_shards_count(P1->S) > 1 || alis_shards_count(P2->S) > 1) { printf("alis-b200: nonLinearSHG/TWM are not available on a world cut into z slabs (ALIS_DEVICES)\n"); exit(1); }
 	coeffs *C = S->W->CE;
 	for (int n=0; n<C->N; n++) for (int m=0; m<=S->W->complexField; m++)
 		CHECK(alisb_chi2_couple(S->E, n, m, P1->E, P2->E, &C->M[n].d[0][0], alt));
@@ -407,7 +439,7 @@ void alis_bridge_read_field(alis_bridge *B, int set, int comp, int m, float *hos
 	world W = B->W;
 	int32_t ids[6] = {set, comp, m, 0, 0, 0};
 	int32_t box[6] = {0, W->iNUM+1, 0, W->jNUM+1, 0, W->kNUM+1};
-	CHECK(alisb_read_box(B->E, ALISB_ARR_FIELD, ids, box, host));
+	CHECK(alis_shards_read_box(B->S, ALISB_ARR_FIELD, ids, box, host));
 }
 
 void alis_bridge_write_field(alis_bridge *B, int set, int comp, int m, const float *host)
@@ -415,5 +447,5 @@ void alis_bridge_write_field(alis_bridge *B, int set, int comp, int m, const flo
 	world W = B->W;
 	int32_t ids[6] = {set, comp, m, 0, 0, 0};
 	int32_t box[6] = {0, W->iNUM+1, 0, W->jNUM+1, 0, W->kNUM+1};
-	CHECK(alisb_write_box(B->E, ALISB_ARR_FIELD, ids, box, host));
+	CHECK(alis_shards_write_box(B->S, ALISB_ARR_FIELD, ids, box, host));
 }

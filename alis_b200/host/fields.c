@@ -492,7 +492,14 @@ unsigned long alisDeviceMonitorCalls(void) { return device_calls; }
 int alis_host_monitors(void)
 {
 	static int mode = -1;
-	if (mode < 0) { const char *s = getenv("ALIS_HOST_MONITORS"); mode = s && atoi(s) != 0; }
+	if (mode < 0) {
+		const char *s = getenv("ALIS_HOST_MONITORS");
+		mode = s && atoi(s) != 0;
+		/* several devices (ALIS_DEVICES, shard.c): a monitor's region may span z slabs; it is gathered through
+		 * the host views, which read every slab's part (alis_bridge_read_box) */
+		const char *d = getenv("ALIS_DEVICES");
+		if (d && strchr(d, ',')) mode = 1;
+	}
 	return mode;
 }
 

@@ -302,10 +302,40 @@ void alis_flux_cache_drop(world W)
 	}
 }
 
+/* the same two sums from the host views: a world cut into z slabs over several devices (ALIS_DEVICES), where a
+ * plane may cross the cuts.  Terms and weights of kernel flux_partial (reference output.c:233-332), added in double. */
+static void plane_sums_host(world W, const plane_req *r, int n, double *sums)
+{
+	for (int q=0; q<n; q++) {
+		const int a = r[q].a, b = (a+1)%3, c = (a+2)%3;
+		int lo[3], hi[3];
+		lo[a] = r[q].at; hi[a] = r[q].at + 1; lo[b] = r[q].bMin; hi[b] = r[q].bMax; lo[c] = r[q].cMin; hi[c] = r[q].cMax;
+		alis_view_need(W, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+		float ***E[3] = { W->E->x, W->E->y, W->E->z }, ***H[3] = { W->H->x, W->H->y, W->H->z };
+		const float *dE[3] = { W->CE->dx, W->CE->dy, W->CE->dz }, *dH[3] = { W->CH->dx, W->CH->dy, W->CH->dz };
+		double s1 = 0, s2 = 0;
+		for (int ib=r[q].bMin; ib<=r[q].bMax; ib++) for (int ic=r[q].cMin; ic<=r[q].cMax; ic++) {
+			int x[3], y[3];
+			x[a] = r[q].at; x[b] = ib; x[c] = ic;
+			y[a] = r[q].at + 1; y[b] = ib; y[c] = ic;
+			if (ib > r[q].bMin) {
+				const float wc = (ic == r[q].cMin || ic == r[q].cMax) ? 0.5f : 1.0f;
+				s1 += (double)dH[b][ib] * ((double)wc * (double)dE[c][ic] * (double)E[b][x[0]][x[1]][x[2]] * (double)(H[c][x[0]][x[1]][x[2]] + H[c][y[0]][y[1]][y[2]]));
+			}
+			if (ic > r[q].cMin) {
+				const float wb = (ib == r[q].bMin || ib == r[q].bMax) ? 0.5f : 1.0f;
+				s2 -= (double)dH[c][ic] * ((double)wb * (double)dE[b][ib] * (double)E[c][x[0]][x[1]][x[2]] * (double)(H[b][x[0]][x[1]][x[2]] + H[b][y[0]][y[1]][y[2]]));
+			}
+		}
+		sums[2*q] = s1; sums[2*q+1] = s2;
+	}
+}
+
 static void plane_sums(world W, const plane_req *r, int n, double *sums)
 {
 	alis_bridge *B = alis_host_bridge(W);
 	alis_bridge_commit(B);
+	if (alis_bridge_engines(B) > 1) { plane_sums_host(W, r, n, sums); return; }
 	alisb_flux_plane P[6];
 	const int org[3] = { W->iMIN-1, W->jMIN-1, W->kMIN-1 };
 	for (int q=0; q<n; q++) {

@@ -234,6 +234,10 @@ phaser (createPhasers)(world W, float LMin, float LMax, float dL, float xMin, fl
 	if (mask) {
 		int32_t box[6] = { P->iMin-(W->iMIN-1), P->iMax-(W->iMIN-1), P->jMin-(W->jMIN-1), P->jMax-(W->jMIN-1), P->kMin-(W->kMIN-1), P->kMax-(W->kMIN-1) };
 		alisb_phaser *dev = 0;
+		if (alis_bridge_engines(alis_host_bridge(W)) > 1) {
+			printf("alis-b200: phasers (running DFT, far field) are not available on a world cut into z slabs; run with one device (unset ALIS_DEVICES)\n");
+			exit(1);
+		}
 		if (alisb_phaser_create(engine_of(W), box, mask, count, &dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		P->b200_dev = dev;
 	}

@@ -46,7 +46,7 @@ void alis_host_invalidate(world W) { alis_host_dirty(W, ALIS_DIRTY_ALL); }
 void alis_host_reset_fields(world W)
 {
 	if (!W->b200_bridge) return;                /* never stepped: device state is still zero */
-	if (alisb_reset_fields(alis_bridge_engine(W->b200_bridge)) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (alis_bridge_reset_fields(W->b200_bridge) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 	alis_host_touch(W);
 }
 

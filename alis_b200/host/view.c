@@ -44,18 +44,18 @@ static float ***view_array(world W, int set, int comp, int m)
 
 static void pull_box(world W, int set, int comp, int m, const int b[6])
 {
-	alisb_engine *E = alis_bridge_engine(alis_host_bridge(W));
+	alis_bridge *E = alis_host_bridge(W);      /* all z slabs of the world (one engine unless ALIS_DEVICES names several) */
 	const int nj = b[3]-b[2]+1, nk = b[5]-b[4]+1;
 	int32_t box[6] = { b[0]-(W->iMIN-1), b[1]-(W->iMIN-1), b[2]-(W->jMIN-1), b[3]-(W->jMIN-1), b[4]-(W->kMIN-1), b[5]-(W->kMIN-1) };
 	int32_t ids[6] = { set, comp, m, 0, 0, 0 };
 	float ***A = view_array(W, set, comp, m);
 	const int whole_rows = b[4] == W->kMIN-1 && b[5] == W->kMAX+1, whole_sheets = whole_rows && b[2] == W->jMIN-1 && b[3] == W->jMAX+1;
 	if (whole_sheets) {                        /* contiguous in the host view: read straight into it */
-		if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, &A[b[0]][b[2]][b[4]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		if (alis_bridge_read_box(E, ALISB_ARR_FIELD, ids, box, &A[b[0]][b[2]][b[4]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		return;
 	}
 	float *tmp = malloc(sizeof(float)*(size_t)(b[1]-b[0]+1)*nj*nk);
-	if (alisb_read_box(E, ALISB_ARR_FIELD, ids, box, tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (alis_bridge_read_box(E, ALISB_ARR_FIELD, ids, box, tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 	size_t q = 0;
 	for (int i=b[0]; i<=b[1]; i++) for (int j=b[2]; j<=b[3]; j++) { memcpy(&A[i][j][b[4]], tmp+q, sizeof(float)*nk); q += nk; }
 	free(tmp);
@@ -111,13 +111,13 @@ void alis_view_need_ade(world W)
 	coeffs *C = W->CE;
 	if (!C->N) return;
 	if (v->have_ade && v->ade_synced == v->version) return;
-	alisb_engine *E = alis_bridge_engine(alis_host_bridge(W));
+	alis_bridge *E = alis_host_bridge(W);
 	for (int m=0; m<=W->complexField; m++) {
 		float *****J[3] = { W->E[m].Jx, W->E[m].Jy, W->E[m].Jz };
 		for (int n=0; n<C->N; n++) for (int p=0; p<C->NK[n]; p++) for (int c=0; c<3; c++) {
 			int32_t ids[6] = { m, n, p, c, 0, 0 };
 			int32_t box[6] = { C->iMin[n]-(W->iMIN-1), C->iMax[n]-(W->iMIN-1), C->jMin[n]-(W->jMIN-1), C->jMax[n]-(W->jMIN-1), C->kMin[n]-(W->kMIN-1), C->kMax[n]-(W->kMIN-1) };
-			if (alisb_read_box(E, ALISB_ARR_ADE_J, ids, box, &J[c][n][p][C->iMin[n]][C->jMin[n]][C->kMin[n]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+			if (alis_bridge_read_box(E, ALISB_ARR_ADE_J, ids, box, &J[c][n][p][C->iMin[n]][C->jMin[n]][C->kMin[n]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		}
 	}
 	v->have_ade = 1; v->ade_synced = v->version;

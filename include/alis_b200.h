@@ -322,6 +322,13 @@ int  alisb_geometry_fill(int device, const alisb_geometry *g, int object, const 
 int  alisb_halo_info(alisb_engine *e, int set, int m, int comp, void **send_ptr, void **recv_ptr, size_t *bytes);
 int  alisb_halo_pack(alisb_engine *e, int set);      /* owned planes -> send buffers (on stream) */
 int  alisb_halo_unpack(alisb_engine *e, int set);    /* recv buffers -> ghost planes (on stream) */
+/* Both engines in ONE process (alis_b200/host/shard.c: a world cut into z slabs behind the public C API): the
+ * plane of field set `set` that crosses the cut between `lower` (the slab below) and `upper` moves from the
+ * engine that owns it into the other's ghost plane -- set E: E.x, E.y of lower's plane nz -> upper's plane 0;
+ * set H: H.x, H.y of upper's plane 1 -> lower's plane nz+1; every complex field set.  CUDA engine: a peer copy
+ * (cudaMemcpyPeerAsync, NVLink between the GPUs of one box) ordered after the owner's stream, and the receiver's
+ * stream waits for it; nothing blocks the host.  The engines must agree in nx, ny and complex_field.      */
+int  alisb_halo_exchange(alisb_engine *lower, alisb_engine *upper, int set);
 
 /* ---- running DFT (phasers) ---------------------------------------------------------- */
 /* box = interior-clipped monitor box; face_mask bit (axis*2+side) set => that face is

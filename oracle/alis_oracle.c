@@ -880,6 +880,17 @@ static void halo_copy(alisb_engine *e, int set, int pack)
 }
 int alisb_halo_pack(alisb_engine *e, int set) { halo_copy(e, set, 1); return ALISB_OK; }
 int alisb_halo_unpack(alisb_engine *e, int set) { halo_copy(e, set, 0); return ALISB_OK; }
+int alisb_halo_exchange(alisb_engine *lower, alisb_engine *upper, int set)
+{
+	if (!lower || !upper || set < 0 || set > 1) return fail(ALISB_EINVAL, "halo exchange: bad argument");
+	if (lower->n[0] != upper->n[0] || lower->n[1] != upper->n[1] || lower->g.complex_field != upper->g.complex_field) return fail(ALISB_EINVAL, "halo exchange: slabs differ in x, y or field sets");
+	alisb_engine *src = set == ALISB_SET_E ? lower : upper, *dst = set == ALISB_SET_E ? upper : lower;
+	const size_t bytes = (size_t)(src->n[0]+2)*(src->n[1]+2)*sizeof(float);
+	halo_copy(src, set, 1);
+	for (int m=0; m<=src->g.complex_field; m++) for (int k=0; k<2; k++) memcpy(dst->halo_recv[set][m][k], src->halo_send[set][m][k], bytes);
+	halo_copy(dst, set, 0);
+	return ALISB_OK;
+}
 
 /* ---- phasers: reference phaser.c:83-110 ------------------------------------------------ */
 int alisb_phaser_create(alisb_engine *e, const int32_t box[6], int face_mask, int nfreq, alisb_phaser **out)

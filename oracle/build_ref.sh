@@ -55,13 +55,13 @@ for ex in "$REF"/examples/*.c; do
 done
 # (2) reference setup + CPU oracle engine through the bridge
 if [ -f "$HERE/liboracle_alis.so" ]; then
-	gcc -std=c99 -fopenmp -O3 -w -DHARNESS_MODE_BRIDGE $INC "$HERE/harness/stepdump.c" "$HOSTDIR/engine_bridge.c" \
+	gcc -std=c99 -fopenmp -O3 -w -DHARNESS_MODE_BRIDGE $INC "$HERE/harness/stepdump.c" "$HOSTDIR/engine_bridge.c" "$HOSTDIR/shard.c" \
 		"$OUT/libalis_ref.a" -L"$HERE" -loracle_alis -Wl,-rpath,'$ORIGIN/../..' -lm -o "$OUT/bin/stepdump_bridge_oracle"
 fi
 # (3) reference setup + CUDA engine through the bridge (runs on the GPU box only)
 ENGINE_DIR=$HERE/../alis_b200
 if [ -f "$ENGINE_DIR/libalis_b200_engine.so" ]; then
-	gcc -std=c99 -fopenmp -O3 -w -DHARNESS_MODE_BRIDGE $INC "$HERE/harness/stepdump.c" "$HOSTDIR/engine_bridge.c" \
+	gcc -std=c99 -fopenmp -O3 -w -DHARNESS_MODE_BRIDGE $INC "$HERE/harness/stepdump.c" "$HOSTDIR/engine_bridge.c" "$HOSTDIR/shard.c" \
 		"$OUT/libalis_ref.a" -L"$ENGINE_DIR" -lalis_b200_engine -Wl,-rpath,'$ORIGIN/../../../alis_b200' -lm -o "$OUT/bin/stepdump_bridge_cuda"
 fi
 echo "build_ref: ok -> $OUT"
