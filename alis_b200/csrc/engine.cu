@@ -119,7 +119,15 @@ struct alisb_engine {
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
 	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
-	cudaEvent_t ev_halo;               /* alisb_halo_exchange: orders the peer copy between the two engines' streams */
+	/* alisb_halo_exchange (both z neighbours in one process): the peer copy runs on the owner's `comm` stream;
+	 * who has to wait for it is told lazily -- the receiver before the pass that reads the ghost plane (or any
+	 * read of the device state), the owner before it rewrites the plane */
+	cudaStream_t comm;
+	cudaEvent_t ev_plane, ev_war;      /* owner: the plane is complete / receiver: the old ghost plane is no longer read */
+	cudaEvent_t ev_out[2];             /* [set] owner: the copy of my plane has finished (recorded on comm)                  */
+	cudaEvent_t ev_in[2];              /* [set] receiver: the OWNER's ev_out of the copy into my ghost plane (a handle, not owned: events
+	                                    * can only be recorded on a stream of their own device, but waited for from any) */
+	bool wait_in[2], wait_out[2];
 	int tune_bx, tune_by, tune_stream, tune_waves, tune_minchunk;   /* launch tunables (env ALISB_*)  */
 	int f_lo, f_hi;                    /* plane filter of the current (partial) pass: ops act on c in [f_lo,f_hi] */
 	bool profiling; std::vector<cudaEvent_t> ev_pool; size_t ev_used; float last_ms; int last_launches;
@@ -147,8 +155,19 @@ struct alisb_phaser {
  * written for the fused box would be stale) */
 static int launch_pending(alisb_engine *e, bool fused);
 static bool ade_in_kernel(const alisb_engine *e);
-#define SETTLE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); } while (0)
-#define UNFUSE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); (e)->h_fused = false; } while (0)
+/* halo planes in flight (alisb_halo_exchange): a pass of `set` reads the ghost plane of the OTHER field set and rewrites
+ * the plane of its own set that was sent; anything else that looks at the device state waits for both */
+static int halo_fence(alisb_engine *e, int set, int part = ALISB_PART_ALL)
+{
+	for (int q=0; q<2; q++) {
+		if (e->wait_in[q] && (set < 0 || q == 1 - set)) { CU(cudaStreamWaitEvent(e->stream, e->ev_in[q], 0)); e->wait_in[q] = false; }
+		/* the rest of a split pass does not touch the plane that has just been sent: it must not wait for the copy */
+		if (e->wait_out[q] && (set < 0 || (q == set && part != ALISB_PART_REST))) { CU(cudaStreamWaitEvent(e->stream, e->ev_out[q], 0)); e->wait_out[q] = false; }
+	}
+	return ALISB_OK;
+}
+#define SETTLE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); TRY(halo_fence((e), -1)); } while (0)
+#define UNFUSE(e) do { if (!(e)) return fail(ALISB_EINVAL, "null engine"); TRY(launch_pending((e), false)); TRY(halo_fence((e), -1)); (e)->h_fused = false; } while (0)
 
 extern "C" int alisb_abi_version(void) { return ALISB_ABI_VERSION; }
 extern "C" const char *alisb_last_error(void) { return g_err; }
@@ -346,7 +365,9 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	if (!e) return;
 	cudaSetDevice(e->g.device);
 	cudaStreamSynchronize(e->stream);
+	if (e->comm) cudaStreamSynchronize(e->comm);
 	e->pendingE = -1; e->h_fused = false;
+	e->wait_in[0] = e->wait_in[1] = e->wait_out[0] = e->wait_out[1] = false;     /* a neighbour's events may be gone already */
 	alisb_clear_sources(e);
 	alisb_clear_dispersive(e);
 	for (int s=0; s<2; s++) for (int m=0; m<2; m++) for (int c=0; c<3; c++) { cudaFree(e->F[s][m][c]); cudaFree(e->Fb[s][m][c]); }
@@ -358,7 +379,10 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
-	if (e->ev_halo) cudaEventDestroy(e->ev_halo);
+	if (e->comm) cudaStreamDestroy(e->comm);
+	if (e->ev_plane) cudaEventDestroy(e->ev_plane);
+	if (e->ev_war) cudaEventDestroy(e->ev_war);
+	for (int q=0; q<2; q++) if (e->ev_out[q]) cudaEventDestroy(e->ev_out[q]);
 	cudaFree(e->scratch); cudaFree(e->d_ade[0]); cudaFree(e->d_ade[1]);
 	cudaFree(e->d_wave_ticket); cudaFree(e->d_wave_progress); cudaFree(e->d_wave_error);
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
@@ -1440,6 +1464,7 @@ static int launch_pending(alisb_engine *e, bool fused)
 	if (e->pendingE < 0) return ALISB_OK;
 	const int part = e->pendingE;
 	e->pendingE = -1;
+	TRY(halo_fence(e, ALISB_SET_E, part));                 /* the fused kernel also forms H', but of no plane that travels and from no ghost plane */
 	e->fusing = fused && e->fuse_ok;
 	const int r = pass_launch(e, ALISB_SET_E, part);
 	const bool did = e->fusing;
@@ -1500,6 +1525,7 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 		}
 	}
 	TRY(pass_prepare(e, set, part));
+	TRY(halo_fence(e, set, part));
 	if (graphable(e, set)) {
 		PassGraph &G = e->graph[set][part];
 		const uint64_t ver = config_version(e);
@@ -2109,23 +2135,39 @@ extern "C" int alisb_halo_exchange(alisb_engine *lower, alisb_engine *upper, int
 			cudaGetLastError();                             /* "already enabled" is fine */
 		}
 	}
-	/* the plane must exist (a deferred E pass is issued now, as the plain variant) and the receiver must be done with
-	 * the old ghost plane */
-	{ alisb_engine *e = src; DEV(e); SETTLE(e); }
-	{ alisb_engine *e = dst; DEV(e); SETTLE(e); if (!e->ev_halo) CU(cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming)); CU(cudaEventRecord(e->ev_halo, e->stream)); }
+	/* the plane must exist: a deferred E pass is issued now, as the plain variant (a caller that wants the fused
+	 * variant sends the plane first: alisb_step_part(SEND_PLANE), this call, then the rest of the pass) */
+	{ alisb_engine *e = src; DEV(e); TRY(launch_pending(e, false)); }
+	{ alisb_engine *e = dst; DEV(e); TRY(launch_pending(e, false)); }
+	for (alisb_engine *e : {src, dst}) {
+		DEV(e);
+		if (!e->comm) {
+			CU(cudaStreamCreateWithFlags(&e->comm, cudaStreamNonBlocking));
+			CU(cudaEventCreateWithFlags(&e->ev_plane, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_war, cudaEventDisableTiming));
+			for (int q=0; q<2; q++) CU(cudaEventCreateWithFlags(&e->ev_out[q], cudaEventDisableTiming));
+		}
+	}
+	{
+		alisb_engine *e = dst; DEV(e);
+		/* an earlier copy into the same ghost plane that nobody has waited for yet is still ordered before this one */
+		if (e->wait_in[set]) { CU(cudaStreamWaitEvent(e->stream, e->ev_in[set], 0)); e->wait_in[set] = false; }
+		CU(cudaEventRecord(e->ev_war, e->stream));           /* what the receiver has enqueued so far may still read the old ghost plane */
+	}
 	{
 		alisb_engine *e = src; DEV(e);
-		if (!e->ev_halo) CU(cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming));
-		CU(cudaStreamWaitEvent(e->stream, dst->ev_halo, 0));
+		CU(cudaEventRecord(e->ev_plane, e->stream));
+		CU(cudaStreamWaitEvent(e->comm, e->ev_plane, 0));
+		CU(cudaStreamWaitEvent(e->comm, dst->ev_war, 0));
 		for (int m=0; m<=e->g.complex_field; m++) for (int comp=0; comp<2; comp++) {
 			void *sp = 0, *rp = 0; size_t nb = 0;
 			TRY(alisb_halo_info(src, set, m, comp, &sp, 0, &nb));
 			TRY(alisb_halo_info(dst, set, m, comp, 0, &rp, 0));
-			CU(cudaMemcpyPeerAsync(rp, dst->g.device, sp, src->g.device, nb, e->stream));
+			CU(cudaMemcpyPeerAsync(rp, dst->g.device, sp, src->g.device, nb, e->comm));
 		}
-		CU(cudaEventRecord(e->ev_halo, e->stream));
+		CU(cudaEventRecord(e->ev_out[set], e->comm));
+		e->wait_out[set] = true;
+		dst->ev_in[set] = e->ev_out[set]; dst->wait_in[set] = true;
 	}
-	{ alisb_engine *e = dst; DEV(e); CU(cudaStreamWaitEvent(e->stream, src->ev_halo, 0)); }
 	return ALISB_OK;
 }
 

@@ -367,6 +367,7 @@ void alis_bridge_destroy(alis_bridge *B)
 
 alisb_engine *alis_bridge_engine(alis_bridge *B) { return B->E; }
 int alis_bridge_engines(alis_bridge *B) { return alis_shards_count(B->S); }
+alis_shards *alis_bridge_shards(alis_bridge *B) { return B->S; }
 int alis_bridge_read_box(alis_bridge *B, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return alis_shards_read_box(B->S, arr, ids, box, host); }
 int alis_bridge_reset_fields(alis_bridge *B) { return alis_shards_reset_fields(B->S); }
 

@@ -6,6 +6,7 @@
 #define ALIS_ENGINE_BRIDGE_H
 
 #include "alis_b200.h"
+#include "shard.h"
 
 typedef struct alis_bridge alis_bridge;
 
@@ -18,6 +19,7 @@ void          alis_bridge_step_E(alis_bridge *B);    /* updateE  (update.c:275-2
 void          alis_bridge_step_H(alis_bridge *B);    /* updateH  (update.c:302-341)              */
 void          alis_bridge_chi2(alis_bridge *S, alis_bridge *P1, alis_bridge *P2, float alt);   /* nonLinearSHG/TWM (update.c:394-411) */
 alisb_engine *alis_bridge_engine(alis_bridge *B);     /* the first engine (the only one unless ALIS_DEVICES names several) */
+alis_shards  *alis_bridge_shards(alis_bridge *B);     /* all of them: what the world is stepped on (shard.h) */
 int           alis_bridge_engines(alis_bridge *B);    /* > 1: the world is cut into z slabs, one engine per device (shard.c) */
 int           alis_bridge_read_box(alis_bridge *B, int arr, const int32_t ids[6], const int32_t box[6], float *host);   /* alisb_read_box over all slabs */
 int           alis_bridge_reset_fields(alis_bridge *B);

@@ -527,7 +527,7 @@ static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*
 	size_t tot_jobs = 0, tot_w = 0;
 	ensure_ready(P);
 	int freq = 0;
-	alisb_phaser *dev = alis_phaser_device(P, &freq);
+	alis_phasers *dev = alis_phaser_device(P, &freq);
 	if (!dev) { for (int q=0; q<n; q++) out[q][0] = out[q][1] = 0; return; }      /* no absorbing face: nothing was recorded */
 	ff_ctx *ctx = xcalloc(FF_CHUNK, sizeof *ctx);
 	size_t *job0 = xmalloc(sizeof(size_t)*(FF_CHUNK+1)), *w0 = xmalloc(sizeof(size_t)*(FF_CHUNK+1));
@@ -556,7 +556,7 @@ static void far_field_batch(phaser P, int n, const ff_query *Q, float complex (*
 			ctx_free(&ctx[q]);
 		}
 		t_pack += wall_seconds() - t0; t0 = wall_seconds();
-		if (alisb_phaser_surface_sums(dev, freq, jobs, (int)njobs, (const float*)weights, nw, sums) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		if (alis_phasers_surface_sums(dev, freq, jobs, (int)njobs, (const float*)weights, nw, sums) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		t_dev += wall_seconds() - t0; t0 = wall_seconds();
 		tot_jobs += njobs; tot_w += nw;
 		#pragma omp parallel for schedule(dynamic, 16)

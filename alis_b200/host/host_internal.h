@@ -52,7 +52,7 @@ int    alis_device_region_ok(world W, const alisb_field_fn *d, const int box[6])
 float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* dense block, k fastest; caller frees */
 int    alis_device_absmax(world W, field F, const int box[6], float *out);          /* 0: use the host path */
 int    alis_device_column_sums(world W, field F, const int box[6], float *cols);    /* 0: use the host path */
-alisb_phaser *alis_phaser_device(phaser P, int *freq);   /* device accumulators + frequency index of P */
+alis_phasers *alis_phaser_device(phaser P, int *freq);   /* device accumulators (of every z slab) + frequency index of P */
 
 
 /* ALIS_PROFILE=1: inclusive wall time and call count of the public entry points, printed at exit (stderr).

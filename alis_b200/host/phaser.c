@@ -233,12 +233,8 @@ phaser (createPhasers)(world W, float LMin, float LMax, float dL, float xMin, fl
 	/* one device accumulator set for the whole frequency list */
 	if (mask) {
 		int32_t box[6] = { P->iMin-(W->iMIN-1), P->iMax-(W->iMIN-1), P->jMin-(W->jMIN-1), P->jMax-(W->jMIN-1), P->kMin-(W->kMIN-1), P->kMax-(W->kMIN-1) };
-		alisb_phaser *dev = 0;
-		if (alis_bridge_engines(alis_host_bridge(W)) > 1) {
-			printf("alis-b200: phasers (running DFT, far field) are not available on a world cut into z slabs; run with one device (unset ALIS_DEVICES)\n");
-			exit(1);
-		}
-		if (alisb_phaser_create(engine_of(W), box, mask, count, &dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+		alis_phasers *dev = 0;
+		if (alis_phasers_create(alis_bridge_shards(alis_host_bridge(W)), box, mask, count, &dev) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		P->b200_dev = dev;
 	}
 	return P;
@@ -270,7 +266,7 @@ void updatePhaser(world W, phaser P)
 		wE[p->b200_index] = cexpf(2 * PI * I * p->f * W->E->t);
 		wH[p->b200_index] = cexpf(2 * PI * I * p->f * W->H->t);
 	}
-	if (alisb_phaser_accumulate(B->b200_dev, (const float*)wE, (const float*)wH) != ALISB_OK) {
+	if (alis_phasers_accumulate(B->b200_dev, (const float*)wE, (const float*)wH) != ALISB_OK) {
 		printf("alis-b200: %s\n", alisb_last_error());
 		exit(1);
 	}
@@ -284,10 +280,10 @@ void updatePhaser(world W, phaser P)
 }
 
 /* device accumulator set and frequency index of one list element (far-field sums, farfld.c) */
-alisb_phaser *alis_phaser_device(phaser P, int *freq)
+alis_phasers *alis_phaser_device(phaser P, int *freq)
 {
 	if (freq) *freq = P->b200_index;
-	return (alisb_phaser*)base_of(P)->b200_dev;
+	return (alis_phasers*)base_of(P)->b200_dev;
 }
 
 /* refresh the host views of the whole frequency list */
@@ -307,7 +303,7 @@ void alisSyncPhaser(phaser P)
 			face_box(p, face, b);
 			/* the row-pointer tables are ordinary memory; only the data block is guarded */
 			float *dst = (float*)((char*)(A[b[0]][b[2]] + b[4]) + shift);
-			if (alisb_phaser_read(B->b200_dev, p->b200_index, face, which, dst) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+			if (alis_phasers_read(B->b200_dev, p->b200_index, face, which, dst) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
 		}
 		__sync_synchronize();
 		B->b200_stale = 0;
@@ -321,7 +317,7 @@ void deletePhaser(phaser P)
 {
 	phaser B = base_of(P);
 	guard_release(B);
-	if (B->b200_dev) alisb_phaser_destroy(B->b200_dev);
+	if (B->b200_dev) alis_phasers_destroy(B->b200_dev);
 	for (phaser p = B; p->f; p++) {
 		for (int face=0; face<6; face++) for (int which=0; which<4; which++) {
 			float complex ****slot = slot_of(face_of(p, face), face/2, which);

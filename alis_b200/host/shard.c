@@ -93,7 +93,6 @@ int alis_shards_create(const alisb_grid *g, const int *devices, int n, int mode,
 		}
 		int rc = alisb_create(&q, &S->E[s]);
 		if (rc != ALISB_OK) { for (int t=0; t<s; t++) alisb_destroy(S->E[t]); free(S); return rc; }
-		if (split(S)) alisb_set_fusion(S->E[s], 0);     /* the E pass must exist when its top plane travels (alis_shards_step_E) */
 	}
 	*out = S;
 	return ALISB_OK;
@@ -102,6 +101,7 @@ int alis_shards_create(const alisb_grid *g, const int *devices, int n, int mode,
 void alis_shards_destroy(alis_shards *S)
 {
 	if (!S) return;
+	for (int s=0; s<S->n; s++) alisb_synchronize(S->E[s]);      /* no plane may still be on its way into a slab that is being freed */
 	for (int s=0; s<S->n; s++) alisb_destroy(S->E[s]);
 	free(S);
 }
@@ -278,18 +278,47 @@ static int exchange(alis_shards *S, int set)
 	return ALISB_OK;
 }
 
-/* every slab's pass is enqueued on its own device (the calls return at once: the slabs run side by side), then the
- * interface planes travel: E.x, E.y of a slab's top plane up, H.x, H.y of its bottom plane down */
+/* Every slab's pass is enqueued on its own device (the calls return at once: the slabs run side by side).  A slab with
+ * a neighbour above computes the plane that neighbour needs first (alisb_step_part SEND_PLANE), the plane starts its
+ * journey (alisb_halo_exchange: a peer copy on the owner's communication stream; the receiver waits for it only when the
+ * pass that reads the ghost plane begins), then the rest of the pass follows -- E.x, E.y of a slab's top plane go up,
+ * H.x, H.y of its bottom plane go down (update.c:110-111,115-116).  With fused E+H stepping the bulk of the E pass is
+ * issued together with the H pass (alisb_flush(e, 1) in alis_shards_step_H): the buffers swap first (alisb_begin_pass),
+ * so that the planes travel between the buffers the passes are about to write. */
 int alis_shards_step_E(alis_shards *S)
 {
-	for (int s=0; s<S->n; s++) TRYS(alisb_step_E(S->E[s]));
-	return exchange(S, ALISB_SET_E);
+	if (!split(S)) {
+		for (int s=0; s<S->n; s++) TRYS(alisb_step_E(S->E[s]));
+		return ALISB_OK;
+	}
+	for (int s=0; s<S->n; s++) TRYS(alisb_begin_pass(S->E[s], ALISB_SET_E));
+	for (int s=0; s<S->n; s++) {
+		if (s + 1 < S->n) {
+			TRYS(alisb_step_part(S->E[s], ALISB_SET_E, ALISB_PART_SEND_PLANE));
+			TRYS(alisb_halo_exchange(S->E[s], S->E[s+1], ALISB_SET_E));
+			TRYS(alisb_step_part(S->E[s], ALISB_SET_E, ALISB_PART_REST));
+		} else TRYS(alisb_step_E(S->E[s]));
+	}
+	return ALISB_OK;
 }
 
 int alis_shards_step_H(alis_shards *S)
 {
-	for (int s=0; s<S->n; s++) TRYS(alisb_step_H(S->E[s]));
-	return exchange(S, ALISB_SET_H);
+	if (!split(S)) {
+		for (int s=0; s<S->n; s++) TRYS(alisb_step_H(S->E[s]));
+		return ALISB_OK;
+	}
+	for (int s=0; s<S->n; s++) { TRYS(alisb_flush(S->E[s], 1)); TRYS(alisb_begin_pass(S->E[s], ALISB_SET_H)); }
+	/* from the top slab down: a slab's bottom plane is on its way before the slab below enqueues its own pass (the copy
+	 * only has to wait for what that slab had enqueued before: its previous E pass, the last reader of the ghost plane) */
+	for (int s=S->n-1; s>=0; s--) {
+		if (s > 0) {
+			TRYS(alisb_step_part(S->E[s], ALISB_SET_H, ALISB_PART_SEND_PLANE));
+			TRYS(alisb_halo_exchange(S->E[s-1], S->E[s], ALISB_SET_H));
+			TRYS(alisb_step_part(S->E[s], ALISB_SET_H, ALISB_PART_REST));
+		} else TRYS(alisb_step_H(S->E[s]));
+	}
+	return ALISB_OK;
 }
 
 int alis_shards_reset_fields(alis_shards *S)
@@ -352,3 +381,106 @@ static int rw_box(alis_shards *S, int arr, const int32_t ids[6], const int32_t b
 
 int alis_shards_read_box(alis_shards *S, int arr, const int32_t ids[6], const int32_t box[6], float *host) { return rw_box(S, arr, ids, box, host, 0); }
 int alis_shards_write_box(alis_shards *S, int arr, const int32_t ids[6], const int32_t box[6], const float *host) { return rw_box(S, arr, ids, box, (float*)host, 1); }
+
+/* ---- running DFT on a cut world (reference phaser.c:83-110; far-field sums farfld.c:248-459) -------------------------
+ * Every slab accumulates the part of the monitor box's faces that lies in its planes: the x and y faces are cut along z,
+ * a z face belongs to the slab that owns its plane -- the H average over the planes k and k+1 (phaser.c:89-90) then reads
+ * either an own plane or the ghost plane the H exchange fills.  Face arrays are stitched when they are read; a far-field
+ * surface sum is the sum of the slabs' partial sums over their z ranges (weights along z start at the slab's offset). */
+struct alis_phasers {
+	alis_shards *S;
+	int n;
+	alisb_phaser *p[MAXSH];
+	int32_t box[6];
+	int mask;
+	int k0[MAXSH], k1[MAXSH];          /* global planes of the monitor box held by slab s (k0 > k1: none) */
+	int smask[MAXSH];
+};
+
+int alis_phasers_create(alis_shards *S, const int32_t box[6], int face_mask, int nfreq, alis_phasers **out)
+{
+	alis_phasers *P = calloc(1, sizeof *P);
+	if (!P) return ALISB_ENOMEM;
+	P->S = S; P->mask = face_mask; memcpy(P->box, box, sizeof P->box);
+	P->n = split(S) ? S->n : 1;                   /* replicas are identical: the first one records */
+	for (int s=0; s<P->n; s++) {
+		int32_t b[6];
+		memcpy(b, box, sizeof b);
+		P->k0[s] = box[4]; P->k1[s] = box[5]; P->smask[s] = face_mask;
+		if (split(S)) {
+			P->k0[s] = box[4] > S->c0[s] ? box[4] : S->c0[s];
+			P->k1[s] = box[5] < S->c1[s] ? box[5] : S->c1[s];
+			if (P->k0[s] > P->k1[s]) { P->smask[s] = 0; continue; }
+			b[4] = P->k0[s] - off_of(S, s); b[5] = P->k1[s] - off_of(S, s);
+			if (P->k0[s] != box[4]) P->smask[s] &= ~(1 << 4);
+			if (P->k1[s] != box[5]) P->smask[s] &= ~(1 << 5);
+		}
+		if (!P->smask[s]) continue;
+		int rc = alisb_phaser_create(S->E[s], b, P->smask[s], nfreq, &P->p[s]);
+		if (rc != ALISB_OK) { for (int t=0; t<s; t++) if (P->p[t]) alisb_phaser_destroy(P->p[t]); free(P); return rc; }
+	}
+	*out = P;
+	return ALISB_OK;
+}
+
+void alis_phasers_destroy(alis_phasers *P)
+{
+	if (!P) return;
+	for (int s=0; s<P->n; s++) if (P->p[s]) alisb_phaser_destroy(P->p[s]);
+	free(P);
+}
+
+int alis_phasers_accumulate(alis_phasers *P, const float *expE, const float *expH)
+{
+	for (int s=0; s<P->n; s++) if (P->p[s]) TRYS(alisb_phaser_accumulate(P->p[s], expE, expH));
+	return ALISB_OK;
+}
+
+int alis_phasers_read(alis_phasers *P, int freq, int face, int which, float *host_complex)
+{
+	if (P->n == 1) return P->p[0] ? alisb_phaser_read(P->p[0], freq, face, which, host_complex) : ALISB_EINVAL;
+	const int ax = face/2;
+	if (ax == 2) {                                /* the slab that owns the plane */
+		for (int s=0; s<P->n; s++) if (P->p[s] && (P->smask[s] >> face & 1)) return alisb_phaser_read(P->p[s], freq, face, which, host_complex);
+		return ALISB_EINVAL;
+	}
+	/* dense over the face, z fastest: rows of nc complex values, one per cell along the other in-face axis */
+	const size_t rows = ax == 0 ? (size_t)(P->box[3] - P->box[2] + 1) : (size_t)(P->box[1] - P->box[0] + 1), nc = P->box[5] - P->box[4] + 1;
+	for (int s=0; s<P->n; s++) {
+		if (!P->p[s] || !(P->smask[s] >> face & 1)) continue;
+		const size_t nk = P->k1[s] - P->k0[s] + 1, k0 = P->k0[s] - P->box[4];
+		float *tmp = malloc(sizeof(float)*2*rows*nk);
+		if (!tmp) return ALISB_ENOMEM;
+		int rc = alisb_phaser_read(P->p[s], freq, face, which, tmp);
+		if (rc == ALISB_OK) for (size_t r=0; r<rows; r++) memcpy(host_complex + 2*(r*nc + k0), tmp + 2*r*nk, sizeof(float)*2*nk);
+		free(tmp);
+		TRYS(rc);
+	}
+	return ALISB_OK;
+}
+
+int alis_phasers_surface_sums(alis_phasers *P, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out)
+{
+	if (P->n == 1) return P->p[0] ? alisb_phaser_surface_sums(P->p[0], freq, jobs, njobs, weights, nweights, out) : ALISB_EINVAL;
+	alisb_surface_job *mine = malloc(sizeof *mine*(njobs + 1));
+	int *where = malloc(sizeof(int)*(njobs + 1));
+	double *part = malloc(sizeof(double)*2*(njobs + 1));
+	if (!mine || !where || !part) { free(mine); free(where); free(part); return ALISB_ENOMEM; }
+	for (int j=0; j<2*njobs; j++) out[j] = 0;
+	int rc = ALISB_OK;
+	for (int s=0; s<P->n && rc == ALISB_OK; s++) {
+		if (!P->p[s]) continue;
+		int m = 0;
+		for (int j=0; j<njobs; j++) {
+			if (!(P->smask[s] >> jobs[j].face & 1)) continue;
+			mine[m] = jobs[j];
+			if (jobs[j].face < 4) mine[m].w_hi += (uint32_t)(P->k0[s] - P->box[4]);      /* v runs along z on the x and y faces */
+			where[m++] = j;
+		}
+		if (!m) continue;
+		rc = alisb_phaser_surface_sums(P->p[s], freq, mine, m, weights, nweights, part);
+		if (rc == ALISB_OK) for (int q=0; q<m; q++) { out[2*where[q]] += part[2*q]; out[2*where[q]+1] += part[2*q+1]; }
+	}
+	free(mine); free(where); free(part);
+	return rc;
+}

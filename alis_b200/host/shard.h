@@ -48,6 +48,14 @@ int  alis_shards_reset_fields(alis_shards *S);
 int  alis_shards_read_box(alis_shards *S, int arr, const int32_t ids[6], const int32_t box[6], float *host);
 int  alis_shards_write_box(alis_shards *S, int arr, const int32_t ids[6], const int32_t box[6], const float *host);
 
+/* running DFT (alisb_phaser_*) of a monitor box that may span several slabs */
+typedef struct alis_phasers alis_phasers;
+int  alis_phasers_create(alis_shards *S, const int32_t box[6], int face_mask, int nfreq, alis_phasers **out);
+void alis_phasers_destroy(alis_phasers *P);
+int  alis_phasers_accumulate(alis_phasers *P, const float *expE, const float *expH);
+int  alis_phasers_read(alis_phasers *P, int freq, int face, int which, float *host_complex);
+int  alis_phasers_surface_sums(alis_phasers *P, int freq, const alisb_surface_job *jobs, int njobs, const float *weights, size_t nweights, double *out);
+
 /* devices named by the environment: ALIS_DEVICES="0,1,2" (several slabs) or ALIS_DEVICE=k (one engine, default 0);
  * returns the count (<= cap) */
 int  alis_shards_env_devices(int *devices, int cap);

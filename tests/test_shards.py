@@ -75,6 +75,20 @@ def test_reference_driver_on_two_slabs(tmp_path, monkeypatch):
     assert n["png"] > 10
 
 
+@pytest.mark.skipif(not _bin("monitors_mine_oracle"), reason="host layer not built")
+@pytest.mark.parametrize("cfg", ["metasurface", "nanoblock", "dipole_band"])
+def test_monitors_on_three_slabs_equal_reference(cfg):
+    """every monitor of oracle/harness/monitors.c (~400 values: field functions, probes, flux boxes, absorption, world and
+    slice reductions, time-averaged and frequency-domain slices, phasor flux, far field, direct phasor access) on a world cut
+    into three slabs against the UNMODIFIED reference: regions are gathered from all slabs, phasor faces are cut along z and
+    stitched, far-field surface sums are added over the slabs.  The flux integrals are summed on the host in double for cut
+    worlds (tolerance 5e-6, as for the device reduction); everything else must agree to the printed digit."""
+    got = helpers.run_monitors("monitors_mine_oracle", cfg, direct_phasor=True, extra_env={"ALIS_DEVICES": "0,0,0"})
+    want = helpers.golden_monitors()[cfg]
+    bad = helpers.monitor_mismatches(got, want, device_flux=True)
+    assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
+
+
 # ---- CUDA engine ---------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("devices", ["0,0", "0,0,0"])
@@ -105,6 +119,25 @@ def test_one_slab_per_gpu(cfg, tmp_path, monkeypatch):
 @pytest.mark.parametrize("name", ["Nanoblock_Scattering", "PhC_Band_Diagram"])
 def test_reference_driver_on_two_slabs_on_the_gpu(name, tmp_path, monkeypatch):
     """the reference's own drivers with their full monitor sets (flux boxes, slices, probes) on a world cut in two"""
+    if not os.path.exists(test_refex._exe(name, "ref")):
+        pytest.skip("reference twin not built")
+    monkeypatch.setenv("ALIS_DEVICES", "0,0")
+    test_refex._twin(name, "cuda", tmp_path, 1500)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", helpers.MONITOR_CONFIGS)
+def test_monitors_on_two_slabs_on_the_gpu(cfg):
+    got = helpers.run_monitors("monitors_mine_cuda", cfg, direct_phasor=True, extra_env={"ALIS_DEVICES": "0,0"})
+    want = helpers.golden_monitors()[cfg]
+    bad = helpers.monitor_mismatches(got, want, device_flux=True)
+    assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Metasurface_Farfield", "Dipole_Band"])
+def test_phasor_drivers_on_two_slabs_on_the_gpu(name, tmp_path, monkeypatch):
+    """running DFT on cut faces + far-field maps: the reference's own drivers that use phasers"""
     if not os.path.exists(test_refex._exe(name, "ref")):
         pytest.skip("reference twin not built")
     monkeypatch.setenv("ALIS_DEVICES", "0,0")
