@@ -19,3 +19,12 @@ PY
 BARGS="--scaling strong" run r02_bench_strong_n${N} A=1
 if [ $N -gt 1 ]; then BARGS="--scaling strong" run r02_bench_strong_n${N}_nooverlap ALISB_NO_OVERLAP=1; fi
 if [ $N -le 2 ]; then BARGS="--scaling strong" run r02_bench_strong_n${N}_inplace ALISB_WAVE=1; fi
+# the same cube through the public C API in ONE process (ALIS_DEVICES: host/shard.c), updateE / updateH / get() per step
+if [ $N -ge 4 ]; then
+	B=tests/bin/bench_cube_mine_cuda
+	DEV=$(seq -s, 0 $((N-1)))
+	for nz in $((256*N)); do
+		echo "ALIS_DEVICES=$DEV nz=$nz $(ALIS_DEVICES=$DEV timeout 900 $B 2048 2048 $nz 10 3 1 | tail -1)" >> $O/r02_capi_shards_n${N}.txt
+	done
+	cat $O/r02_capi_shards_n${N}.txt
+fi
