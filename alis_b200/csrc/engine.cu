@@ -119,6 +119,9 @@ struct alisb_engine {
 	long tune_small;                   /* grids below this many cells use the single-launch plan */
 	int tune_debug, tune_conc;         /* tune_conc: 0 serial sub-launches, 1 PML shell launches concurrent after the interior, 2 all concurrent */
 	cudaStream_t side[3]; cudaEvent_t ev_fork, ev_join[3];
+	cudaStream_t hi; cudaEvent_t ev_hi;    /* the fused launches: a stream of the highest priority, so that the block scheduler hands SMs to the
+	                                        * PML shell launches (which run beside them) only when the fused kernel has no CTA left to issue */
+	int tune_prio;                         /* ALISB_FUSE_PRIO (1) */
 	/* alisb_halo_exchange (both z neighbours in one process): the peer copy runs on the owner's `comm` stream;
 	 * who has to wait for it is told lazily -- the receiver before the pass that reads the ghost plane (or any
 	 * read of the device state), the owner before it rewrites the plane */
@@ -299,6 +302,9 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		e->tune_small = (s = getenv("ALISB_SMALL")) ? atol(s) : 3000000L;   /* crossover measured at ~150^3 (profiles/small_grid_probe.py) */
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+		e->tune_prio = (s = getenv("ALISB_FUSE_PRIO")) ? atoi(s) : 1;
+		{ int least = 0, greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&least, &greatest)); CU(cudaStreamCreateWithPriority(&e->hi, cudaStreamNonBlocking, greatest)); }
+		CU(cudaEventCreateWithFlags(&e->ev_hi, cudaEventDisableTiming));
 		if ((s = getenv("ALISB_WAVES"))) e->tune_waves = std::max(1, atoi(s));
 		if ((s = getenv("ALISB_MINCHUNK"))) e->tune_minchunk = std::max(1, atoi(s));
 	}
@@ -379,6 +385,8 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	for (int q=0; q<3; q++) { cudaStreamDestroy(e->side[q]); cudaEventDestroy(e->ev_join[q]); }
 	cudaEventDestroy(e->ev_fork);
+	if (e->hi) cudaStreamDestroy(e->hi);
+	if (e->ev_hi) cudaEventDestroy(e->ev_hi);
 	if (e->comm) cudaStreamDestroy(e->comm);
 	if (e->ev_plane) cudaEventDestroy(e->ev_plane);
 	if (e->ev_war) cudaEventDestroy(e->ev_war);
@@ -862,7 +870,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 	 * two merged launches (faces / edges+corners, yee_multi) on side streams, fork/join with events.
 	 * ALISB_MERGE=0: one launch per box, spread over three side streams.                        */
 	int sub = -1, nlaunched = 0, rr = 0;
-	bool forked = false, used[3] = {false, false, false};
+	bool forked = false, used[3] = {false, false, false}, hi_used = false;
 	const bool conc = e->tune_conc > 0 && e->plan[set].size() > 2;
 	const bool merge = e->tune_merge && e->plan[set].size() > 2 && e->tune_bx == 1 && e->tune_by == 8;
 	MultiParams mp[2];
@@ -998,7 +1006,13 @@ static int launch_volume(alisb_engine *e, int set, int m)
 			const int nzs = sb.c1 - sb.c0 + 1, gyf = div_up(sb.b1 - sb.b0 + 1, frows);
 			fp.cchunk = std::min(nzs, std::max(1, e->tune_fchunk));
 			dim3 grid(fp.nseg, gyf, div_up(nzs, fp.cchunk)), block(32, frows + 1, 1);
-			cudaStream_t st = side_stream(true);
+			cudaStream_t st;
+			if (conc && e->tune_prio) {
+				/* all fused pieces one after the other on the high-priority stream, forked from the engine's stream */
+				if (!forked) { CU(cudaEventRecord(e->ev_fork, e->stream)); forked = true; }
+				if (!hi_used) { CU(cudaStreamWaitEvent(e->hi, e->ev_fork, 0)); hi_used = true; }
+				st = e->hi;
+			} else st = side_stream(true);
 			nlaunched++;
 			/* profiling counts cell-passes: a fused launch does two passes per cell */
 			cudaEvent_t e1 = prof_begin(st, sub, 2.0*(double)(sb.a1-sb.a0+1)*(sb.b1-sb.b0+1)*nzs);
@@ -1064,6 +1078,7 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		if (e->profiling) CU(cudaEventRecord(e1, st));
 	}
 	for (int q=0; q<3; q++) if (used[q]) { CU(cudaEventRecord(e->ev_join[q], e->side[q])); CU(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0)); }
+	if (hi_used) { CU(cudaEventRecord(e->ev_hi, e->hi)); CU(cudaStreamWaitEvent(e->stream, e->ev_hi, 0)); }
 	/* the in-place wavefront kernel: on the engine's stream, i.e. after all of the above (it reads the E' the
 	 * two-pass E kernels formed on the box's low faces and the old H they left next to it) */
 	for (const Piece &pc : wave_later) {

@@ -91,8 +91,7 @@ def test_monitors_on_three_slabs_equal_reference(cfg):
 
 # ---- CUDA engine ---------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("devices", ["0,0", "0,0,0"])
-@pytest.mark.parametrize("cfg", SHARDABLE)
+@pytest.mark.parametrize("cfg,devices", [(c, "0,0") for c in SHARDABLE] + [(c, "0,0,0") for c in QUICK])
 def test_z_slabs_on_one_gpu(cfg, devices, tmp_path, monkeypatch):
     """several slabs on ONE GPU: the whole decomposition and the peer copies, on the single-GPU test box"""
     _check(os.path.join(helpers.TEST_BIN, "stepdump_mine_cuda"), cfg, devices, tmp_path, monkeypatch)
@@ -116,9 +115,10 @@ def test_one_slab_per_gpu(cfg, tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["Nanoblock_Scattering", "PhC_Band_Diagram"])
+@pytest.mark.parametrize("name", ["Nanoblock_Scattering", "Metasurface_Farfield"])
 def test_reference_driver_on_two_slabs_on_the_gpu(name, tmp_path, monkeypatch):
-    """the reference's own drivers with their full monitor sets (flux boxes, slices, probes) on a world cut in two"""
+    """the reference's own drivers with their full monitor sets (flux boxes, slices; running DFT on cut faces and the
+    far-field map) on a world cut in two"""
     if not os.path.exists(test_refex._exe(name, "ref")):
         pytest.skip("reference twin not built")
     monkeypatch.setenv("ALIS_DEVICES", "0,0")
@@ -132,13 +132,3 @@ def test_monitors_on_two_slabs_on_the_gpu(cfg):
     want = helpers.golden_monitors()[cfg]
     bad = helpers.monitor_mismatches(got, want, device_flux=True)
     assert not bad, f"{cfg}: {len(bad)} monitor values differ from the reference: {bad[:5]}"
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["Metasurface_Farfield", "Dipole_Band"])
-def test_phasor_drivers_on_two_slabs_on_the_gpu(name, tmp_path, monkeypatch):
-    """running DFT on cut faces + far-field maps: the reference's own drivers that use phasers"""
-    if not os.path.exists(test_refex._exe(name, "ref")):
-        pytest.skip("reference twin not built")
-    monkeypatch.setenv("ALIS_DEVICES", "0,0")
-    test_refex._twin(name, "cuda", tmp_path, 1500)
