@@ -63,6 +63,30 @@ def test_random_world_matches_reference_gpu(seed, tmp_path):
     assert got == want, f"seed {seed}: reference set-up + CUDA engine differs from the reference [{what}]"
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", list(range(1, 41)))
+def test_random_world_cut_into_z_slabs_cpu(seed, tmp_path):
+    """the same worlds cut into three z slabs behind the public API (ALIS_DEVICES, host/shard.c): flat and thin z axes get
+    fewer slabs, worlds periodic along z run uncut -- the field state is the reference's either way (160 seeds x {2, 3}
+    slabs were identical when this was written)"""
+    if not helpers.have_test_bin("stepdump_mine_oracle"):
+        pytest.skip("tests/bin not built")
+    t = str(tmp_path)
+    want, what = dump(REF, seed, os.path.join(t, "r.bin"), t, OMP_NUM_THREADS="2")
+    got, _ = dump(os.path.join(helpers.TEST_BIN, "stepdump_mine_oracle"), seed, os.path.join(t, "m.bin"), t, ALIS_DEVICES="0,0,0")
+    assert got == want, f"seed {seed}: world cut into three slabs differs from the reference [{what}]"
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [5, 8, 16, 23, 41, 59, 67, 76])
+def test_random_world_cut_into_z_slabs_gpu(seed, tmp_path):
+    t = str(tmp_path)
+    want, what = dump(REF, seed, os.path.join(t, "r.bin"), t)
+    got, _ = dump(os.path.join(helpers.TEST_BIN, "stepdump_mine_cuda"), seed, os.path.join(t, "m.bin"), t, ALIS_DEVICES="0,0")
+    assert got == want, f"seed {seed}: world cut into two slabs on the GPU differs from the reference [{what}]"
+
+
 MONITOR_SEEDS_CPU = list(range(1, 25))
 MONITOR_SEEDS_GPU = [2, 9, 14, 23]
 
