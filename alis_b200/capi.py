@@ -395,6 +395,10 @@ class Engine:
     def halo_unpack(self, set_):
         self._ck(self.lib.alisb_halo_unpack(self.h, set_))
 
+    def halo_exchange_with_upper(self, upper, set_):
+        """both slabs in this process: my top E plane -> upper's ghost plane (set E) / upper's bottom H plane -> my ghost plane (set H)"""
+        self._ck(self.lib.alisb_halo_exchange(self.h, upper.h, set_))
+
 
 class Accum:
     def __init__(self, eng, f, ibox, with_imag):
