@@ -122,6 +122,7 @@ struct alisb_engine {
 	cudaStream_t hi; cudaEvent_t ev_hi;    /* the fused launches: a stream of the highest priority, so that the block scheduler hands SMs to the
 	                                        * PML shell launches (which run beside them) only when the fused kernel has no CTA left to issue */
 	int tune_prio;                         /* ALISB_FUSE_PRIO (1) */
+	double trace_s[2][5]; long trace_n[2][5];   /* ALISB_DEBUG: host seconds per field set in {prepare, graph capture, node patching, graph launch, direct launches} */
 	/* alisb_halo_exchange (both z neighbours in one process): the peer copy runs on the owner's `comm` stream;
 	 * who has to wait for it is told lazily -- the receiver before the pass that reads the ghost plane (or any
 	 * read of the device state), the owner before it rewrites the plane */
@@ -366,12 +367,14 @@ extern "C" int alisb_clear_dispersive(alisb_engine *e)
 	return ALISB_OK;
 }
 
+static void trace_print(const alisb_engine *e);
 extern "C" void alisb_destroy(alisb_engine *e)
 {
 	if (!e) return;
 	cudaSetDevice(e->g.device);
 	cudaStreamSynchronize(e->stream);
 	if (e->comm) cudaStreamSynchronize(e->comm);
+	if (e->tune_debug) trace_print(e);
 	e->pendingE = -1; e->h_fused = false;
 	e->wait_in[0] = e->wait_in[1] = e->wait_out[0] = e->wait_out[1] = false;     /* a neighbour's events may be gone already */
 	alisb_clear_sources(e);
@@ -1285,6 +1288,45 @@ static int finish_sources(alisb_engine *e, int set)
 
 static int pass_launch(alisb_engine *e, int set, int part);
 
+/* Orders the ops of a list kernel into chains (kernels.cuh, CopyList): stable partition by target array, then, inside
+ * every chain, a barrier after op q-1 whenever op q conflicts with an op since the chain's last barrier.  Returns the
+ * largest op (cells) so that the caller can choose between one CTA and one cluster per chain. */
+template <typename Op, typename List, typename Conflict>
+static size_t build_chains(List &L, Op *ops, Conflict conflict)
+{
+	Op tmp[sizeof(L.op)/sizeof(L.op[0])];
+	float *key[ALISB_MAXCHAINS];
+	int nkey = 0, chain_of[sizeof(L.op)/sizeof(L.op[0])];
+	for (int q=0; q<L.n; q++) {
+		int c = 0;
+		while (c < nkey && key[c] != ops[q].F) c++;
+		if (c == nkey) { if (nkey < ALISB_MAXCHAINS) key[nkey++] = ops[q].F; else c = nkey - 1; }   /* more arrays than chains: the last chain takes the rest, in order */
+		chain_of[q] = c;
+	}
+	int n = 0;
+	size_t biggest = 0;
+	for (int c=0; c<nkey; c++) {
+		L.first[c] = n;
+		int level_start = n;
+		for (int q=0; q<L.n; q++) if (chain_of[q] == c) {
+			tmp[n] = ops[q]; tmp[n].sync_after = 0;
+			bool hit = false;
+			for (int r=level_start; r<n && !hit; r++) hit = conflict(tmp[r], tmp[n]);
+			if (hit) { tmp[n-1].sync_after = 1; level_start = n; }
+			biggest = std::max(biggest, (size_t)tmp[n].B.na*tmp[n].B.nb*tmp[n].B.nc);
+			n++;
+		}
+	}
+	L.first[nkey] = n; L.nchain = nkey;
+	for (int c=nkey+1; c<=ALISB_MAXCHAINS; c++) L.first[c] = n;
+	memcpy(ops, tmp, sizeof(Op)*n);
+	return biggest;
+}
+static bool boxes_meet(const Box &A, const Box &B)
+{
+	return A.a0 < B.a0 + B.na && B.a0 < A.a0 + A.na && A.b0 < B.b0 + B.nb && B.b0 < A.b0 + A.nb && A.c0 < B.c0 + B.nc && B.c0 < A.c0 + A.nc;
+}
+
 static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 {
 	for (TfsfObj *t : e->tf) {
@@ -1307,7 +1349,14 @@ static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 				o.clampa = t->d.clamp[1-set][s.aux_comp][0]; o.clampb = t->d.clamp[1-set][s.aux_comp][1];
 			}
 			if (ok) {
-				if (SL.n) { strip_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(SL); e->launches++; }
+				if (SL.n) {
+					/* strips that add to the same array keep their order where their boxes meet (float addition is not associative);
+					 * the chains of the three components (and of the complex sets) run side by side */
+					const size_t biggest = build_chains(SL, SL.op, [](const StripOp &p, const StripOp &q) { return p.F == q.F && boxes_meet(p.B, q.B); });
+					if (biggest <= 1024) strip_list1<<<SL.nchain, 1024, 0, e->stream>>>(SL);        /* one cell per thread: a CTA per chain is enough */
+					else                 strip_list<<<SL.nchain*ALISB_LIST_CTAS, 1024, 0, e->stream>>>(SL);
+					e->launches++;
+				}
 				continue;
 			}
 		}
@@ -1347,21 +1396,16 @@ static int apply_copies(alisb_engine *e, int set)
 		}
 	}
 	if (small && total <= 400000) {
-		/* a barrier is needed between op q and the ops since the last barrier only if they conflict:
-		 * same array and (target x target, target x source or source x target boxes intersect) */
-		auto hits = [](const Box &A, const Box &B) {
-			return A.a0 < B.a0 + B.na && B.a0 < A.a0 + A.na && A.b0 < B.b0 + B.nb && B.b0 < A.b0 + A.nb && A.c0 < B.c0 + B.nc && B.c0 < A.c0 + A.nc; };
+		/* a barrier is needed between op q and the ops of its chain since the last barrier only if they conflict:
+		 * (target x target, target x source or source x target boxes intersect) */
 		auto shifted = [](const CopyOp &o) { Box S = o.B; S.a0 += o.alt0; S.b0 += o.alt1; S.c0 += o.alt2; return S; };
-		int level_start = 0;
-		for (int q=1; q<L.n; q++) {
-			bool conflict = false;
-			for (int r=level_start; r<q && !conflict; r++) {
-				if (L.op[r].F != L.op[q].F) continue;
-				conflict = hits(L.op[r].B, L.op[q].B) || hits(L.op[r].B, shifted(L.op[q])) || hits(shifted(L.op[r]), L.op[q].B);
-			}
-			if (conflict) { L.op[q-1].sync_after = 1; level_start = q; }
+		const size_t biggest = build_chains(L, L.op, [&](const CopyOp &p, const CopyOp &q) {
+			return p.F == q.F && (boxes_meet(p.B, q.B) || boxes_meet(p.B, shifted(q)) || boxes_meet(shifted(p), q.B)); });
+		if (L.n) {
+			if (biggest <= 1024) copy_list1<<<L.nchain, 1024, 0, e->stream>>>(L);        /* one cell per thread: a CTA per chain is enough */
+			else                 copy_list<<<L.nchain*ALISB_LIST_CTAS, 1024, 0, e->stream>>>(L);
+			e->launches++;
 		}
-		if (L.n) { copy_list<<<ALISB_LIST_CTAS, 1024, 0, e->stream>>>(L); e->launches++; }
 		CU(cudaGetLastError());
 		return ALISB_OK;
 	}
@@ -1423,15 +1467,25 @@ static int pass_prepare(alisb_engine *e, int set, int part)
 static int pass_launch(alisb_engine *e, int set, int part)
 {
 	set_filter(e, set, part);
-	for (int m=0; m<=e->g.complex_field; m++) {
+	/* launch-bound grids with complex fields: the real and the imaginary set are independent within a pass and their
+	 * (single) volume launches are latency bound -- they run side by side, the imaginary set on a side stream */
+	const bool pair = e->g.complex_field && e->tune_conc > 0 && (long)e->nx*e->ny*e->nz < e->tune_small;
+	cudaStream_t const main_stream = e->stream;
+	if (pair) { CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->side[0], e->ev_fork, 0)); }
+	int rc = ALISB_OK;
+	for (int m=0; m<=e->g.complex_field && rc == ALISB_OK; m++) {
+		if (pair && m == 1) e->stream = e->side[0];
 		if (set == ALISB_SET_E) {
-			if (!e->obj.empty() && !ade_in_kernel(e)) TRY(ade_pre(e, m));
-			TRY(launch_volume(e, ALISB_SET_E, m));
+			if (!e->obj.empty() && !ade_in_kernel(e)) rc = ade_pre(e, m);
+			if (rc == ALISB_OK) rc = launch_volume(e, ALISB_SET_E, m);
 		} else {
-			TRY(launch_volume(e, ALISB_SET_H, m));
-			if (!e->obj.empty() && !ade_in_kernel(e)) TRY(ade_post(e, m));
+			rc = launch_volume(e, ALISB_SET_H, m);
+			if (rc == ALISB_OK && !e->obj.empty() && !ade_in_kernel(e)) rc = ade_post(e, m);
 		}
+		e->stream = main_stream;
 	}
+	if (pair) { CU(cudaEventRecord(e->ev_join[0], e->side[0])); CU(cudaStreamWaitEvent(main_stream, e->ev_join[0], 0)); }
+	TRY(rc);
 	TRY(apply_tfsf(e, set, part != ALISB_PART_REST));
 	set_filter(e, set, part);
 	TRY(launch_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
@@ -1515,6 +1569,13 @@ extern "C" int alisb_begin_pass(alisb_engine *e, int set)
 	return ALISB_OK;
 }
 
+static void trace_print(const alisb_engine *e)
+{
+	static const char *const what[5] = { "prepare (host)", "graph capture", "source-node patching", "graph launch", "direct launches" };
+	for (int st=0; st<2; st++) for (int q=0; q<5; q++) if (e->trace_n[st][q])
+		fprintf(stderr, "[alisb] %dx%dx%d pass %c %-22s %8ld calls %10.4f s (%.1f us each)\n", e->nx, e->ny, e->nz, st ? 'H' : 'E', what[q], e->trace_n[st][q], e->trace_s[st][q], 1e6*e->trace_s[st][q]/e->trace_n[st][q]);
+}
+
 extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 {
 	if (set < 0 || set > 1 || part < 0 || part > 2) return fail(ALISB_EINVAL, "bad step part");
@@ -1539,13 +1600,19 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 			TRY(launch_pending(e, true));
 		}
 	}
+	const bool trace = e->tune_debug != 0;
+	auto tick = [&]() { return trace ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point(); };
+	auto tock = [&](int what, std::chrono::steady_clock::time_point t0) { if (trace) { e->trace_s[set][what] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); e->trace_n[set][what]++; } };
+	auto t0 = tick();
 	TRY(pass_prepare(e, set, part));
+	tock(0, t0);
 	TRY(halo_fence(e, set, part));
 	if (graphable(e, set)) {
 		PassGraph &G = e->graph[set][part];
 		const uint64_t ver = config_version(e);
 		if (!G.exec || G.version != ver) {
 			/* capture the pass once */
+			t0 = tick();
 			if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = 0; }
 			if (G.graph) { cudaGraphDestroy(G.graph); G.graph = 0; }
 			G.nodes.clear();
@@ -1566,7 +1633,9 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 			G.version = ver;
 			G.nkernels = (int)(e->launches - l0);
 			e->launches = l0;
+			tock(1, t0);
 		} else {
+			t0 = tick();
 			for (const SrcNode &sn : G.nodes) {
 				cudaKernelNodeParams kp;
 				memset(&kp, 0, sizeof kp);
@@ -1574,12 +1643,18 @@ extern "C" int alisb_step_part(alisb_engine *e, int set, int part)
 				kp.func = (void*)source_list; kp.gridDim = dim3(ALISB_LIST_CTAS); kp.blockDim = dim3(1024); kp.kernelParams = args;
 				CU(cudaGraphExecKernelNodeSetParams(G.exec, sn.node, &kp));
 			}
+			tock(2, t0);
 		}
+		t0 = tick();
 		CU(cudaGraphLaunch(G.exec, e->stream));
+		tock(3, t0);
+		if (trace && e->tune_debug >= 2 && set == ALISB_SET_H && e->trace_n[set][3] % 2000 == 0) trace_print(e);
 		e->launches += G.nkernels;
 		return pass_finish(e, set, part);
 	}
+	t0 = tick();
 	TRY(pass_launch(e, set, part));
+	tock(4, t0);
 	if (set == ALISB_SET_H && part != ALISB_PART_SEND_PLANE) e->h_fused = false;      /* the H pass is complete */
 	return pass_finish(e, set, part);
 }

@@ -324,23 +324,41 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 				const AdeObj &ob = T.o[n];
 				if (!ob.nk || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
 				const size_t jr = ((size_t)(c - ob.full.c0)*ob.full.nb + (b - ob.full.b0))*ob.full.na;
+				bool in[4];
 				#pragma unroll
-				for (int e = 0; e < 4; e++) {
-					const int a = a0 + e;
-					if (a < ob.upd.a0 || a >= ob.upd.a0 + ob.upd.na || a > r.a_last) continue;
-					const size_t j = jr + (a - ob.full.a0);
-					const float Ev[3] = {Gx[e], Gy[e], Gz[e]};
+				for (int e = 0; e < 4; e++) { const int a = a0 + e; in[e] = !(a < ob.upd.a0 || a >= ob.upd.a0 + ob.upd.na || a > r.a_last); }
+				if (!(in[0] || in[1] || in[2] || in[3])) continue;
+				const size_t j0 = jr + (a0 - ob.full.a0);        /* cell e of the quad sits at j0 + e (only dereferenced where in[e]) */
+				/* per component: every load of the quad's currents first (they are independent; issued one behind the other
+				 * they were a chain of dependent global round trips: the stores between them may alias), then the arithmetic
+				 * of update.c:135-142 pole by pole, then the stores */
+				#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					float Jv[ALISB_MAXPOLES][4], Kv[ALISB_MAXPOLES][4], fv[4];
 					#pragma unroll
-					for (int k = 0; k < 3; k++) {
-						const float Fv = Ev[k], f = ob.fill[k][j];
-						for (int s = 0; s < ob.nk; s++) {
+					for (int e = 0; e < 4; e++) fv[e] = in[e] ? ob.fill[k][j0 + e] : 0.f;
+					#pragma unroll
+					for (int s = 0; s < ALISB_MAXPOLES; s++) {
+						#pragma unroll
+						for (int e = 0; e < 4; e++) {
+							Jv[s][e] = (s < ob.nk && in[e]) ? ob.J[s][k][j0 + e] : 0.f;
+							Kv[s][e] = (s < ob.nk && s >= ob.nj && in[e]) ? ob.K[s][k][j0 + e] : 0.f;
+						}
+					}
+					#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						if (!in[e]) continue;
+						const float Fv = k == 0 ? Gx[e] : k == 1 ? Gy[e] : Gz[e], f = fv[e];
+						#pragma unroll
+						for (int s = 0; s < ALISB_MAXPOLES; s++) {
+							if (s >= ob.nk) continue;
 							if (s < ob.nj) {
-								ob.J[s][k][j] = ob.JJ[k][s]*ob.J[s][k][j] + ob.JE[k][s]*f*Fv;                       /* update.c:135 */
+								ob.J[s][k][j0 + e] = ob.JJ[k][s]*Jv[s][e] + ob.JE[k][s]*f*Fv;                              /* update.c:135 */
 							} else {
-								const float Kold = ob.K[s][k][j];
-								const float Jn = ob.JJ[k][s]*ob.J[s][k][j] + ob.JK[k][s]*Kold + ob.JE[k][s]*f*Fv;   /* update.c:140 */
-								ob.J[s][k][j] = Jn;
-								ob.K[s][k][j] = ob.KJ[k][s]*Jn + ob.KK[k][s]*Kold + ob.KE[k][s]*f*Fv;               /* update.c:142 */
+								const float Kold = Kv[s][e];
+								const float Jn = ob.JJ[k][s]*Jv[s][e] + ob.JK[k][s]*Kold + ob.JE[k][s]*f*Fv;            /* update.c:140 */
+								ob.J[s][k][j0 + e] = Jn;
+								ob.K[s][k][j0 + e] = ob.KJ[k][s]*Jn + ob.KK[k][s]*Kold + ob.KE[k][s]*f*Fv;               /* update.c:142 */
 							}
 						}
 					}
@@ -1180,33 +1198,58 @@ __global__ void copy_plane(float *F, float *G, float cosk, float sink, Box B, in
 #define ALISB_MAXCOPIES 24
 #define ALISB_LIST_CTAS 8          /* one thread-block cluster walks a list; cluster.sync() separates dependent ops */
 struct CopyOp { float *F, *G; float cosk, sink; Box B; int alt0, alt1, alt2; int sync_after; };
-struct CopyList { CopyOp op[ALISB_MAXCOPIES]; int n, ny, pitch; };
+/* Ops are grouped into CHAINS by the array they act on (a copy reads and writes one component, a strip or a source adds
+ * to one): chains are independent and run side by side -- chain q is walked by CTAs q*CL .. q*CL+CL-1 (CL = 1: one CTA,
+ * __syncthreads between dependent ops; CL = 8: one thread-block cluster, barrier.cluster) -- and inside a chain the ops keep
+ * their list order with a barrier wherever an op touches what an earlier one of the same level wrote or read. */
+#define ALISB_MAXCHAINS 6
+struct CopyList { CopyOp op[ALISB_MAXCOPIES]; int n, ny, pitch; int nchain, first[ALISB_MAXCHAINS + 1]; };
 
 static __device__ __forceinline__ void list_sync()
 {
 	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+template <int CL> static __device__ __forceinline__ void chain_sync()
+{
+	if (CL == 1) __syncthreads(); else list_sync();
+}
 
-__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L)
+template <int CL> static __device__ __forceinline__ void copy_chain(const CopyList &L)
 {
 	const int ny = L.ny, pitch = L.pitch;
-	const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nth = (size_t)gridDim.x*blockDim.x;
-	for (int k = 0; k < L.n; k++) {
+	const int chain = blockIdx.x / CL;
+	const size_t tid = (size_t)(blockIdx.x % CL)*blockDim.x + threadIdx.x, nth = (size_t)CL*blockDim.x;
+	for (int k = L.first[chain]; k < L.first[chain + 1]; k++) {
 		const CopyOp &o = L.op[k];
 		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
-		for (size_t t = tid; t < cells; t += nth) {
-			int a, b, c; size_t q;
-			box_cell(o.B, t, a, b, c, q);
-			const size_t i = GIDX(a, b, c), j = GIDX(a + o.alt0, b + o.alt1, c + o.alt2);
-			if (o.G) {
-				const float f = o.F[j], g = o.G[j];
-				o.F[i] = o.cosk*f + o.sink*g;
-				o.G[i] = o.cosk*g - o.sink*f;
-			} else o.F[i] = o.cosk*o.F[j];
+		/* four cells per thread and round: all loads first (a copy's source cells are never targets of the same copy),
+		 * so a thread with several cells pays one memory round trip, not one per cell */
+		for (size_t t0 = tid; t0 < cells; t0 += 4*nth) {
+			size_t i[4]; float f[4], g[4]; bool ok[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const size_t t = t0 + (size_t)u*nth;
+				ok[u] = t < cells; i[u] = 0; f[u] = 0.f; g[u] = 0.f;
+				if (!ok[u]) continue;
+				int a, b, c; size_t q;
+				box_cell(o.B, t, a, b, c, q);
+				i[u] = GIDX(a, b, c);
+				const size_t j = GIDX(a + o.alt0, b + o.alt1, c + o.alt2);
+				f[u] = o.F[j];
+				if (o.G) g[u] = o.G[j];
+			}
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (!ok[u]) continue;
+				if (o.G) { o.F[i[u]] = o.cosk*f[u] + o.sink*g[u]; o.G[i[u]] = o.cosk*g[u] - o.sink*f[u]; }
+				else o.F[i[u]] = o.cosk*f[u];
+			}
 		}
-		if (o.sync_after) list_sync();          /* the next op reads or overwrites what this level wrote */
+		if (o.sync_after) chain_sync<CL>();     /* the next op of the chain reads or overwrites what this level wrote */
 	}
 }
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L) { copy_chain<ALISB_LIST_CTAS>(L); }
+__global__ void __launch_bounds__(1024) copy_list1(const __grid_constant__ CopyList L) { copy_chain<1>(L); }
 
 /* All soft sources of a pass (reference updateS list, update.c:161-179) and all TFSF strips of a
  * pass (update.c:205-272) in one single-CTA launch each, in list order (overlapping boxes add in
@@ -1234,14 +1277,15 @@ __global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) 
 }
 
 #define ALISB_MAXSTRIPOPS 48
-struct StripOp { float *F; const float *G, *C; float coef; Box B; int alt0, alt1, alt2, clampa, clampb; };
-struct StripList { StripOp op[ALISB_MAXSTRIPOPS]; int n, ny, pitch, any, apitch; };
+struct StripOp { float *F; const float *G, *C; float coef; Box B; int alt0, alt1, alt2, clampa, clampb; int sync_after; };
+struct StripList { StripOp op[ALISB_MAXSTRIPOPS]; int n, ny, pitch, any, apitch; int nchain, first[ALISB_MAXCHAINS + 1]; };
 
-__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L)
+template <int CL> static __device__ __forceinline__ void strip_chain(const StripList &L)
 {
 	const int ny = L.ny, pitch = L.pitch;
-	const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nth = (size_t)gridDim.x*blockDim.x;
-	for (int k = 0; k < L.n; k++) {
+	const int chain = blockIdx.x / CL;
+	const size_t tid = (size_t)(blockIdx.x % CL)*blockDim.x + threadIdx.x, nth = (size_t)CL*blockDim.x;
+	for (int k = L.first[chain]; k < L.first[chain + 1]; k++) {
 		const StripOp &o = L.op[k];
 		const size_t cells = (size_t)o.B.na*o.B.nb*o.B.nc;
 		for (size_t t = tid; t < cells; t += nth) {
@@ -1253,9 +1297,11 @@ __global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) 
 			if (o.C) o.F[i] += o.coef*g*o.C[i];
 			else     o.F[i] += o.coef*g;
 		}
-		if (k + 1 < L.n) list_sync();
+		if (o.sync_after) chain_sync<CL>();     /* the next strip of the chain adds to cells this level added to (update.c:205-272: in list order) */
 	}
 }
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L) { strip_chain<ALISB_LIST_CTAS>(L); }
+__global__ void __launch_bounds__(1024) strip_list1(const __grid_constant__ StripList L) { strip_chain<1>(L); }
 
 /* gather / scatter a box between any engine array (element (a,b,c) at c*sC + b*sB + a + off) and a
  * dense buffer in the HOST order (z fastest, reference makeField layout): the transposition is
@@ -1377,12 +1423,19 @@ __global__ void flux_partial(const __grid_constant__ FluxParams p, const FluxPla
 
 __global__ void flux_finish(const double *partial, int nblocks, double *out)
 {
+	/* the partials are fetched by all threads at once (one round trip instead of a chain of dependent loads), then added
+	 * by one thread in index order, so the result does not depend on the launch shape */
+	__shared__ double sh[2][256];
 	const int q = blockIdx.x;
-	if (threadIdx.x == 0) {
-		double s1 = 0, s2 = 0;
-		for (int k = 0; k < nblocks; k++) { s1 += partial[2*((size_t)q*nblocks + k)]; s2 += partial[2*((size_t)q*nblocks + k) + 1]; }
-		out[2*q] = s1; out[2*q + 1] = s2;
+	double s1 = 0, s2 = 0;
+	for (int k0 = 0; k0 < nblocks; k0 += 128) {
+		const int n = min(128, nblocks - k0);
+		for (int k = threadIdx.x; k < n; k += blockDim.x) { sh[0][k] = partial[2*((size_t)q*nblocks + k0 + k)]; sh[1][k] = partial[2*((size_t)q*nblocks + k0 + k) + 1]; }
+		__syncthreads();
+		if (threadIdx.x == 0) for (int k = 0; k < n; k++) { s1 += sh[0][k]; s2 += sh[1][k]; }
+		__syncthreads();
 	}
+	if (threadIdx.x == 0) { out[2*q] = s1; out[2*q + 1] = s2; }
 }
 
 /* ------------------------------------------------------------------------------------------
