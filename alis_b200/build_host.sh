@@ -60,4 +60,6 @@ for ex in "$REF"/examples/*.c; do
 		$CC -std=c99 -O2 -fopenmp -w -I"$ROOT/include" "$ex" -L"$ROOT/tests/bin" -lalis_oracle -Wl,-rpath,'$ORIGIN' -lm -o "$ROOT/tests/bin/refex_${b}_oracle"
 	fi
 done
+# CPU check of the symbolic walk behind kernel copy_resolved (tests/test_copy_resolve.py)
+${CXX:-g++} -O1 -std=c++17 -ffp-contract=off -o "$ROOT/tests/bin/rc_check" "$ROOT/tests/native/rc_check.cpp"
 echo "build_host: ok"

@@ -24,6 +24,7 @@
 #include <nvtx3/nvToolsExt.h>      /* header-only NVTX 3: ranges cost a few ns when no tool is attached */
 #include "alis_b200.h"
 #include "kernels.cuh"
+#include "copy_resolve.h"
 
 /* the fused kernel needs more than the default 48 KB of dynamic shared memory (a per-device function attribute) */
 template <int ROWS, bool EPS, bool PMZ> static cudaError_t fused_optin_one()
@@ -75,6 +76,9 @@ struct TfsfObj {
 	alisb_tfsf d;
 	std::vector<alisb_strip> sE, sH;
 };
+
+/* a resolved copy list (kernels.cuh, copy_resolved): built once per distinct list, found again by comparing the list */
+struct CopyPlan { CopyList key; ResolvedCopy P; int4 *d_ent; float2 *d_tmp; };
 
 struct alisb_engine {
 	alisb_grid g;
@@ -144,6 +148,13 @@ struct alisb_engine {
 	bool graph_ok;                     /* CUDA-graph replay of whole passes allowed (ALISB_GRAPH, no per-source fallback path) */
 	PassGraph graph[2][3];             /* [set][part] */
 	FluxPlane *d_planes; double *d_partial, *d_flux, *h_flux; int flux_cap;
+	std::vector<CopyPlan*> cplan;      /* resolved copy lists (ALISB_RESOLVE, default 1) */
+	int tune_resolve;
+	int tune_onewave, vol_occ[2][2][2][2][8];   /* launch-bound grids: volume launches sized to one wave of resident CTAs (ALISB_ONEWAVE, default 0: measured slower); resident CTAs per SM per variant */
+	int tune_aux_aside;                /* TFSF auxiliary worlds step on a side stream beside the volume launch (ALISB_AUX_ASIDE, default 1) */
+	/* mailbox: small results are stored by the kernel into mapped pinned host memory and announced by a sequence number
+	 * (ALISB_MAILBOX, default 1) instead of travelling by cudaMemcpy + stream synchronisation */
+	int tune_mail; unsigned char *mail_h, *mail_d; unsigned mail_seq; unsigned *d_mail_counters; double *d_mail_partial;
 };
 
 struct alisb_phaser {
@@ -304,6 +315,10 @@ extern "C" int alisb_create(const alisb_grid *g, alisb_engine **out)
 		for (int q=0; q<3; q++) { CU(cudaStreamCreateWithFlags(&e->side[q], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&e->ev_join[q], cudaEventDisableTiming)); }
 		CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 		e->tune_prio = (s = getenv("ALISB_FUSE_PRIO")) ? atoi(s) : 1;
+		e->tune_resolve = (s = getenv("ALISB_RESOLVE")) ? atoi(s) : 1;
+		e->tune_mail = (s = getenv("ALISB_MAILBOX")) ? atoi(s) : 1;
+		e->tune_aux_aside = (s = getenv("ALISB_AUX_ASIDE")) ? atoi(s) : 1;
+		e->tune_onewave = (s = getenv("ALISB_ONEWAVE")) ? atoi(s) : 0;   /* measured slower: Nanoblock loop 0.94 s against 0.83, PhC 3.32 against 3.20 (profiles/r02_small_ab_v19.txt) */
 		{ int least = 0, greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&least, &greatest)); CU(cudaStreamCreateWithPriority(&e->hi, cudaStreamNonBlocking, greatest)); }
 		CU(cudaEventCreateWithFlags(&e->ev_hi, cudaEventDisableTiming));
 		if ((s = getenv("ALISB_WAVES"))) e->tune_waves = std::max(1, atoi(s));
@@ -399,6 +414,9 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int q=0; q<2; q++) for (int ax=0; ax<3; ax++) cudaFree(e->spacing[q][ax]);
 	for (int r=0; r<SRC_RING; r++) { if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]); cudaFree(e->srcv_d[r]); if (e->srcv_ev[r]) cudaEventDestroy(e->srcv_ev[r]); }
 	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
+	for (CopyPlan *cp : e->cplan) { cudaFree(cp->d_ent); cudaFree(cp->d_tmp); delete cp; }
+	if (e->mail_h) cudaFreeHost(e->mail_h);
+	cudaFree(e->d_mail_counters); cudaFree(e->d_mail_partial);
 	if (e->own_stream) cudaStreamDestroy(e->stream);
 	delete e;
 }
@@ -557,32 +575,35 @@ extern "C" int alisb_set_copies(alisb_engine *e, int set, const alisb_copy *ops,
 }
 
 /* ---- one pass ------------------------------------------------------------------------- */
+/* occ != 0: no launch, *occ = resident CTAs per SM of the variant that would be launched */
+#define VOL_GO(PMV, LANES) do { if (occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, yee_volume<S,EPS,PMV,LANES,ADE>, 256, 0); \
+                                else yee_volume<S,EPS,PMV,LANES,ADE><<<grid,block,0,st>>>(p, r); } while (0)
 template <int S, bool EPS, bool ADE>
-static void launch_volume_te(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block)
+static void launch_volume_te(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, int *occ)
 {
 	if (r.narrow) {                   /* 32-cell wide x strips: 8 lanes along x, 4 rows per warp */
-		if (r.pm == 1) yee_volume<S,EPS,1,8,ADE><<<grid,block,0,st>>>(p, r);
-		else           yee_volume<S,EPS,5,8,ADE><<<grid,block,0,st>>>(p, r);
+		if (r.pm == 1) VOL_GO(1, 8);
+		else           VOL_GO(5, 8);
 		return;
 	}
 	switch (r.pm) {
-	case 0: yee_volume<S,EPS,0,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 1: yee_volume<S,EPS,1,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 2: yee_volume<S,EPS,2,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 3: yee_volume<S,EPS,3,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 4: yee_volume<S,EPS,4,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 5: yee_volume<S,EPS,5,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	case 6: yee_volume<S,EPS,6,32,ADE><<<grid,block,0,st>>>(p, r); break;
-	default: yee_volume<S,EPS,7,32,ADE><<<grid,block,0,st>>>(p, r); break;
+	case 0: VOL_GO(0, 32); break;
+	case 1: VOL_GO(1, 32); break;
+	case 2: VOL_GO(2, 32); break;
+	case 3: VOL_GO(3, 32); break;
+	case 4: VOL_GO(4, 32); break;
+	case 5: VOL_GO(5, 32); break;
+	case 6: VOL_GO(6, 32); break;
+	default: VOL_GO(7, 32); break;
 	}
 }
 /* dispersive objects sit in material worlds: the ADE variants exist with the inverse-permittivity arrays only */
 template <int S>
-static void launch_volume_t(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, bool eps, bool ade)
+static void launch_volume_t(cudaStream_t st, const VolParams &p, const VolRegion &r, dim3 grid, dim3 block, bool eps, bool ade, int *occ = 0)
 {
-	if (ade)      launch_volume_te<S,(S > 0),true>(st, p, r, grid, block);
-	else if (eps) launch_volume_te<S,(S > 0),false>(st, p, r, grid, block);
-	else          launch_volume_te<S,false,false>(st, p, r, grid, block);
+	if (ade)      launch_volume_te<S,(S > 0),true>(st, p, r, grid, block, occ);
+	else if (eps) launch_volume_te<S,(S > 0),false>(st, p, r, grid, block, occ);
+	else          launch_volume_te<S,false,false>(st, p, r, grid, block, occ);
 }
 template <int S, bool EPS, bool ADE>
 static void launch_multi_te(cudaStream_t st, const MultiParams &mp, unsigned nctas, int cls)
@@ -1039,6 +1060,20 @@ static int launch_volume(alisb_engine *e, int set, int m)
 		long maxc = std::max(1, nzs/e->tune_minchunk);                          /* (the carry preload is an L2 hit)  */
 		int nchunks = (int)std::max(1L, std::min(want, maxc));
 		if (!merged && tiles*nchunks < 2L*e->resident_ctas) nchunks = (int)std::min((long)nzs, (2L*e->resident_ctas + tiles - 1)/tiles);   /* small grids: fill the GPU */
+		if (!merged && e->tune_onewave && (long)e->nx*e->ny*e->nz < e->tune_small) {
+			/* launch-bound grids: the launch is over when its slowest CTA is, so all CTAs should be resident at once -- as
+			 * many z-chunks as the variant has resident slots (shared with the twin launch of the other complex set),
+			 * not a few more (448 CTAs on 444 slots ran as two waves) */
+			int &occ = e->vol_occ[set][eps ? 1 : 0][pc.ade ? 1 : 0][narrow ? 1 : 0][sb.pml & 7];
+			if (!occ) {
+				VolRegion probe = r;
+				if (set == ALISB_SET_E) launch_volume_t<1>(0, p, probe, dim3(1), dim3(1), eps, pc.ade, &occ);
+				else                    launch_volume_t<-1>(0, p, probe, dim3(1), dim3(1), false, pc.ade, &occ);
+				if (occ < 1) occ = 1;
+			}
+			const long slots = (long)occ*e->sm_count/(e->g.complex_field && e->tune_conc > 0 ? 2 : 1);
+			if (tiles*nchunks > slots && tiles <= slots) nchunks = (int)std::max(1L, slots/tiles);
+		}
 		r.cchunk = div_up(nzs, nchunks);
 		nchunks = div_up(nzs, r.cchunk);
 		r.gx = gx; r.gy = gy; r.gz = nchunks;
@@ -1375,27 +1410,97 @@ static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 	return ALISB_OK;
 }
 
-static int apply_copies(alisb_engine *e, int set)
+/* the copies of a pass (clipped to the planes of the current part) as a list for the list kernels; false: the planes
+ * are large, one launch per copy */
+static bool small_copy_list(alisb_engine *e, int set, CopyList &L)
 {
-	/* small planes: the whole ordered list in one single-CTA launch */
-	CopyList L;
+	memset(&L, 0, sizeof L);             /* the list is also the key of its resolved plan: no indeterminate padding */
 	L.n = 0; L.ny = e->ny; L.pitch = e->pitch;
-	bool small = e->copies[set].size() <= ALISB_MAXCOPIES;
+	if (e->copies[set].size() > ALISB_MAXCOPIES) return false;
 	size_t total = 0;
 	for (const alisb_copy &k : e->copies[set]) {
 		Box B = clipc(mkbox(k.box), e->f_lo, e->f_hi);
 		const size_t n = bcount(B);
 		if (!n) continue;
-		if (n > 32768) { small = false; break; }
+		if (n > 32768) return false;
 		total += n;
-		if (small) {
-			CopyOp &o = L.op[L.n++];
-			o.F = e->F[k.set][0][k.comp]; o.G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
-			o.cosk = k.cosk; o.sink = k.sink; o.B = B; o.alt0 = k.alt[0]; o.alt1 = k.alt[1]; o.alt2 = k.alt[2];
-			o.sync_after = 0;
+		CopyOp &o = L.op[L.n++];
+		o.F = e->F[k.set][0][k.comp]; o.G = e->g.complex_field ? e->F[k.set][1][k.comp] : 0;
+		o.cosk = k.cosk; o.sink = k.sink; o.B = B; o.alt0 = k.alt[0]; o.alt1 = k.alt[1]; o.alt2 = k.alt[2];
+		o.sync_after = 0;
+	}
+	return total <= 400000;
+}
+
+/* The list resolved by copy_resolve.h into the tables of copy_resolved.  Returns 0 when the list does not fit them (the
+ * list kernels take it then). */
+static CopyPlan *build_copy_plan(alisb_engine *e, const CopyList &L)
+{
+	if ((e->nz + 2)*e->plane >= ((size_t)1 << 31)) return 0;
+	RcOp ops[ALISB_MAXCOPIES];
+	for (int q=0; q<L.n; q++) {
+		const CopyOp &o = L.op[q];
+		ops[q].F = o.F; ops[q].G = o.G; ops[q].a0 = o.B.a0; ops[q].b0 = o.B.b0; ops[q].c0 = o.B.c0; ops[q].na = o.B.na; ops[q].nb = o.B.nb; ops[q].nc = o.B.nc;
+		ops[q].alt0 = o.alt0; ops[q].alt1 = o.alt1; ops[q].alt2 = o.alt2;
+	}
+	RcPlan R;
+	if (!rc_resolve(ops, L.n, L.ny, L.pitch, ALISB_XO, ALISB_RC_ARRAYS, ALISB_RC_CHAINS, ALISB_RC_DEPTH, R)) return 0;
+	std::vector<int4> ent(R.ent.size());
+	for (size_t q=0; q<R.ent.size(); q++) ent[q] = make_int4(R.ent[q].tgt, R.ent[q].src, (R.ent[q].arr << 8) | R.ent[q].chain, 0);
+	CopyPlan *cp = new CopyPlan();
+	memset(&cp->P, 0, sizeof cp->P);
+	cp->key = L; cp->d_ent = 0; cp->d_tmp = 0;
+	for (size_t arr=0; arr<R.F.size(); arr++) { cp->P.F[arr] = (float*)R.F[arr]; cp->P.G[arr] = (float*)R.G[arr]; }
+	for (size_t ch=0; ch<R.chains.size(); ch++) {
+		cp->P.depth[ch] = (int)R.chains[ch].size();
+		for (size_t d=0; d<R.chains[ch].size(); d++) { cp->P.cosk[ch][d] = L.op[R.chains[ch][d]].cosk; cp->P.sink[ch][d] = L.op[R.chains[ch][d]].sink; }
+	}
+	cp->P.n = (int)ent.size(); cp->P.nbound = (int)R.nbound;
+	if (cp->P.n) {
+		if (cudaMalloc((void**)&cp->d_ent, sizeof(int4)*ent.size()) != cudaSuccess || cudaMalloc((void**)&cp->d_tmp, sizeof(float2)*ent.size()) != cudaSuccess
+		    || cudaMemcpy(cp->d_ent, ent.data(), sizeof(int4)*ent.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+			cudaGetLastError(); cudaFree(cp->d_ent); cudaFree(cp->d_tmp); delete cp; return 0;
 		}
 	}
-	if (small && total <= 400000) {
+	cp->P.ent = cp->d_ent; cp->P.tmp = cp->d_tmp;
+	return cp;
+}
+
+/* the resolved plan of a list: looked up by the list itself; built on first sight unless the stream is being captured
+ * (pass_prepare has then built it already) */
+static CopyPlan *copy_plan(alisb_engine *e, const CopyList &L, bool may_build)
+{
+	if (!e->tune_resolve || e->dbuf || L.n < 2) return 0;          /* double-buffered passes alternate their arrays: the list kernels take those */
+	for (CopyPlan *cp : e->cplan) if (!memcmp(&cp->key, &L, sizeof L)) return cp->P.n >= 0 ? cp : 0;
+	if (!may_build) return 0;
+	if (e->cplan.size() >= 16) {                                   /* the configuration keeps changing: start over (captured passes hold plan pointers) */
+		cudaStreamSynchronize(e->stream);
+		for (CopyPlan *cp : e->cplan) { cudaFree(cp->d_ent); cudaFree(cp->d_tmp); delete cp; }
+		e->cplan.clear(); e->cfg_version++;
+	}
+	CopyPlan *cp = build_copy_plan(e, L);
+	if (!cp) { cp = new CopyPlan(); cp->key = L; cp->d_ent = 0; cp->d_tmp = 0; memset(&cp->P, 0, sizeof cp->P); cp->P.n = -1; }   /* remembered as "does not resolve" */
+	e->cplan.push_back(cp);
+	return cp->P.n >= 0 ? cp : 0;
+}
+
+static int apply_copies(alisb_engine *e, int set)
+{
+	/* small planes: the whole ordered list in one launch */
+	CopyList L;
+	const bool small = small_copy_list(e, set, L);
+	if (small) {
+		if (CopyPlan *cp = copy_plan(e, L, g_mode != GMODE_CAPTURE)) {
+			if (cp->P.n) {
+				/* one cluster for the bound entries (if any) and one per 16 K free entries (two per thread) */
+				const int nfree = cp->P.n - cp->P.nbound;
+				const int clusters = (cp->P.nbound ? 1 : 0) + std::min(16, div_up(nfree, 2*1024*ALISB_LIST_CTAS));
+				copy_resolved<<<ALISB_LIST_CTAS*clusters, 1024, 0, e->stream>>>(cp->P);
+				e->launches++;
+			}
+			CU(cudaGetLastError());
+			return ALISB_OK;
+		}
 		/* a barrier is needed between op q and the ops of its chain since the last barrier only if they conflict:
 		 * (target x target, target x source or source x target boxes intersect) */
 		auto shifted = [](const CopyOp &o) { Box S = o.B; S.a0 += o.alt0; S.b0 += o.alt1; S.c0 += o.alt2; return S; };
@@ -1460,6 +1565,7 @@ static int pass_prepare(alisb_engine *e, int set, int part)
 	set_filter(e, set, part);
 	if (ade_in_kernel(e)) TRY(ade_table(e));
 	TRY(prepare_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
+	if (e->tune_resolve && !e->dbuf) { CopyList L; if (small_copy_list(e, set, L)) copy_plan(e, L, true); }   /* the pass may be captured: plans are built here */
 	return ALISB_OK;
 }
 
@@ -1471,6 +1577,24 @@ static int pass_launch(alisb_engine *e, int set, int part)
 	 * (single) volume launches are latency bound -- they run side by side, the imaginary set on a side stream */
 	const bool pair = e->g.complex_field && e->tune_conc > 0 && (long)e->nx*e->ny*e->nz < e->tune_small;
 	cudaStream_t const main_stream = e->stream;
+	/* launch-bound grids with TFSF regions: the auxiliary worlds' passes (volume, source, copies: a chain of latency-bound
+	 * launches) run on a side stream beside this world's whole pass.  Nothing here waits for them: the strips of an E pass
+	 * read the auxiliary world's H, which its E pass (update.c:207 before update.c:209-234) does not touch, and vice versa
+	 * (update.c:242-269); the pass as a whole ends when both have finished */
+	const bool aux_aside = part != ALISB_PART_REST && !e->tf.empty() && e->tune_conc > 0 && e->tune_aux_aside && (long)e->nx*e->ny*e->nz < e->tune_small;
+	if (aux_aside) {
+		CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->side[1], e->ev_fork, 0));
+		int rca = ALISB_OK;
+		for (TfsfObj *t : e->tf) {
+			alisb_engine *x = t->d.aux;
+			cudaStream_t const xs = x->stream;
+			x->stream = e->side[1];
+			if (rca == ALISB_OK) rca = pass_launch(x, set, ALISB_PART_ALL);
+			x->stream = xs;
+		}
+		CU(cudaEventRecord(e->ev_join[1], e->side[1]));
+		TRY(rca);
+	}
 	if (pair) { CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->side[0], e->ev_fork, 0)); }
 	int rc = ALISB_OK;
 	for (int m=0; m<=e->g.complex_field && rc == ALISB_OK; m++) {
@@ -1486,10 +1610,11 @@ static int pass_launch(alisb_engine *e, int set, int part)
 	}
 	if (pair) { CU(cudaEventRecord(e->ev_join[0], e->side[0])); CU(cudaStreamWaitEvent(main_stream, e->ev_join[0], 0)); }
 	TRY(rc);
-	TRY(apply_tfsf(e, set, part != ALISB_PART_REST));
+	TRY(apply_tfsf(e, set, part != ALISB_PART_REST && !aux_aside));
 	set_filter(e, set, part);
 	TRY(launch_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
 	TRY(apply_copies(e, set));
+	if (aux_aside) CU(cudaStreamWaitEvent(main_stream, e->ev_join[1], 0));
 	e->f_lo = 0; e->f_hi = e->nz + 1;
 	return ALISB_OK;
 }
@@ -1764,6 +1889,42 @@ static long long arr_offset(alisb_engine *e, const ArrRef &r, int a, int b, int 
 	return -1;
 }
 
+/* ---- mailbox (see box_gather_mail / flux_mail in kernels.cuh) ------------------------------------------ */
+#define MAIL_BYTES 4096                 /* payload; the sequence word follows it */
+static int mail_open(alisb_engine *e)
+{
+	if (e->mail_h) return ALISB_OK;
+	unsigned char *h = 0, *d = 0;
+	CU(cudaHostAlloc((void**)&h, MAIL_BYTES + 64, cudaHostAllocMapped));
+	memset(h, 0, MAIL_BYTES + 64);
+	if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return fail(ALISB_ECUDA, "mailbox: no device pointer for mapped host memory"); }
+	unsigned *cnt = 0; double *part = 0;
+	if (cudaMalloc((void**)&cnt, sizeof(unsigned)*(1 + ALISB_FLUX_MAIL_PLANES)) != cudaSuccess || cudaMalloc((void**)&part, sizeof(double)*2*128*ALISB_FLUX_MAIL_PLANES) != cudaSuccess
+	    || cudaMemset(cnt, 0, sizeof(unsigned)*(1 + ALISB_FLUX_MAIL_PLANES)) != cudaSuccess) {
+		cudaGetLastError(); cudaFree(cnt); cudaFree(part); cudaFreeHost(h); return fail(ALISB_ECUDA, "mailbox: allocation failed");
+	}
+	e->mail_h = h; e->mail_d = d; e->d_mail_counters = cnt; e->d_mail_partial = part; e->mail_seq = 0;
+	return ALISB_OK;
+}
+/* waits for the kernel that was launched with sequence number `seq`; polls the stream now and then so that a launch
+ * that died does not hang the host */
+static int mail_wait(alisb_engine *e, unsigned seq)
+{
+	volatile unsigned *flag = (volatile unsigned*)(e->mail_h + MAIL_BYTES);
+	for (unsigned long spins = 1; *flag != seq; spins++) {
+		if ((spins & 0xffff) == 0) {
+			const cudaError_t st = cudaStreamQuery(e->stream);
+			if (st == cudaSuccess) { if (*flag == seq) break; return fail(ALISB_ECUDA, "mailbox: the stream drained without the result arriving"); }
+			if (st != cudaErrorNotReady) return fail(ALISB_ECUDA, "mailbox: %s", cudaGetErrorString(st));
+		}
+#if defined(__x86_64__) || defined(__i386__)
+		__builtin_ia32_pause();
+#endif
+	}
+	__sync_synchronize();
+	return ALISB_OK;
+}
+
 static int rw_box_one(alisb_engine *e, int arr, const int32_t ids[6], const int32_t box[6], float *host, bool write)
 {
 	DEV(e);
@@ -1781,6 +1942,16 @@ static int rw_box_one(alisb_engine *e, int arr, const int32_t ids[6], const int3
 	case 2:  sB = e->pitch; sC = (long long)r.dense.nb*e->pitch; off = ALISB_XO - (long long)r.dense.b0*sB; break;
 	case 3:  sB = e->pitch; sC = (long long)(e->ny+2)*e->pitch; off = ALISB_XO - (long long)r.dense.c0*sC; break;
 	default: sB = r.dense.na; sC = (long long)r.dense.nb*r.dense.na; off = -((long long)r.dense.c0*sC + (long long)r.dense.b0*sB + r.dense.a0); break;
+	}
+	if (!write && e->tune_mail && n*sizeof(float) <= MAIL_BYTES) {
+		TRY(mail_open(e));
+		const unsigned seq = ++e->mail_seq;
+		box_gather_mail<<<1, 256, 0, e->stream>>>(r.p, (float*)e->mail_d, B, sC, sB, off, (volatile unsigned*)(e->mail_d + MAIL_BYTES), seq);
+		CU(cudaGetLastError());
+		e->launches++;
+		TRY(mail_wait(e, seq));
+		memcpy(host, e->mail_h, n*sizeof(float));
+		return ALISB_OK;
 	}
 	TRY(need_scratch(e, n));
 	if (write) {
@@ -1907,6 +2078,20 @@ extern "C" int alisb_plane_flux(alisb_engine *e, const alisb_flux_plane *planes,
 	FluxParams p;
 	for (int c=0; c<3; c++) { p.E[c] = e->F[0][0][c]; p.H[c] = e->F[1][0][c]; p.dE[c] = e->spacing[0][c]; p.dH[c] = e->spacing[1][c]; }
 	p.ny = e->ny; p.pitch = e->pitch;
+	if (e->tune_mail && n <= ALISB_FLUX_MAIL_PLANES && sizeof(double)*2*n <= MAIL_BYTES) {
+		/* one launch, planes as kernel arguments, sums into the mailbox (same partial sums added in the same order) */
+		TRY(mail_open(e));
+		FluxPlaneList PL;
+		memset(&PL, 0, sizeof PL);
+		memcpy(PL.P, hp, sizeof(FluxPlane)*n);
+		const unsigned seq = ++e->mail_seq;
+		flux_mail<<<dim3(FLUX_BLOCKS, n), 256, 0, e->stream>>>(p, PL, e->d_mail_partial, e->d_mail_counters, (double*)e->mail_d, (volatile unsigned*)(e->mail_d + MAIL_BYTES), seq);
+		CU(cudaGetLastError());
+		e->launches++;
+		TRY(mail_wait(e, seq));
+		memcpy(out, e->mail_h, sizeof(double)*2*n);
+		return ALISB_OK;
+	}
 	CU(cudaMemcpyAsync(e->d_planes, hp, sizeof(FluxPlane)*n, cudaMemcpyHostToDevice, e->stream));
 	flux_partial<<<dim3(FLUX_BLOCKS, n), 256, 0, e->stream>>>(p, e->d_planes, e->d_partial);
 	flux_finish<<<n, 32, 0, e->stream>>>(e->d_partial, FLUX_BLOCKS, e->d_flux);

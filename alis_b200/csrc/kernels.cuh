@@ -92,6 +92,19 @@ template <bool STREAM> static __device__ __forceinline__ void st4s(float *p, flo
 template <int S, bool EPS, int PM, int XL, bool ADE>  /* PM: bit 0/1/2 = this box may touch x / y / z PML slabs */
 static __device__ __forceinline__ void yee_body(const VolParams &p, const VolRegion &r, const int bix, const int biy, const int biz)
 {
+	/* the object table is read by every thread in every plane: the CTA keeps its own copy in shared memory (one cooperative
+	 * fetch instead of chains of dependent global loads, and loads the compiler may keep across the field stores) */
+	const AdeTable *adeT = 0;
+	if (ADE) {
+		__shared__ __align__(16) unsigned long long ade_words[sizeof(AdeTable)/8];
+		const int tid = threadIdx.y*blockDim.x + threadIdx.x, nth = blockDim.x*blockDim.y;
+		const int nobj = min(max(p.ade->n, 0), ALISB_MAXADE);
+		const int words = (int)((offsetof(AdeTable, o) + (size_t)nobj*sizeof(AdeObj))/8);
+		const unsigned long long *src = reinterpret_cast<const unsigned long long*>(p.ade);
+		for (int q = tid; q < words; q += nth) ade_words[q] = src[q];
+		__syncthreads();
+		adeT = reinterpret_cast<const AdeTable*>(ade_words);
+	}
 	constexpr int RW = 32/XL;                               /* rows per warp */
 	const int lane = threadIdx.x & 31;
 	const int lx = lane % XL;                               /* lane position along x */
@@ -193,7 +206,7 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 			/* update.c:89-108 on the old E in registers: every lossy object's factor, then every object's
 			 * currents, objects and poles in list order (cells are independent, so this is the reference's
 			 * sequence of whole-box sweeps seen from one cell) */
-			const AdeTable &T = *p.ade;
+			const AdeTable &T = *adeT;
 			for (int n = 0; n < T.n; n++) {
 				const AdeObj &ob = T.o[n];
 				if (!ob.lossy || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
@@ -319,7 +332,7 @@ static __device__ __forceinline__ void yee_body(const VolParams &p, const VolReg
 		if (ADE && S < 0 && act) {
 			/* updateJ (update.c:128-158) from the final E of this thread's own cells, which the H pass has
 			 * in registers as G: Drude poles, then critical-point / Lorentz pairs (K uses the new J) */
-			const AdeTable &T = *p.ade;
+			const AdeTable &T = *adeT;
 			for (int n = 0; n < T.n; n++) {
 				const AdeObj &ob = T.o[n];
 				if (!ob.nk || c < ob.upd.c0 || c >= ob.upd.c0 + ob.upd.nc || b < ob.upd.b0 || b >= ob.upd.b0 + ob.upd.nb) continue;
@@ -972,7 +985,7 @@ yee_wave(const __grid_constant__ WaveParams p)
 
 /* one box per launch: the slab-free interior (PM=0) and, with ALISB_MERGE=0, every other box */
 template <int S, bool EPS, int PM, int XL, bool ADE>
-__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : (ADE && PM == 0) ? 2 : 1)   /* single-axis slab variants: keep 3 CTAs/SM; interior with objects: 2 */
+__global__ void __launch_bounds__(256, (PM == 1 || PM == 2 || PM == 4) ? 3 : ADE ? 2 : 1)   /* single-axis slab variants: keep 3 CTAs/SM; interior with objects: 2 */
 yee_volume(const __grid_constant__ VolParams p, const __grid_constant__ VolRegion r)
 {
 	yee_body<S,EPS,PM,XL,ADE>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
@@ -1251,6 +1264,77 @@ template <int CL> static __device__ __forceinline__ void copy_chain(const CopyLi
 __global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) copy_list(const __grid_constant__ CopyList L) { copy_chain<ALISB_LIST_CTAS>(L); }
 __global__ void __launch_bounds__(1024) copy_list1(const __grid_constant__ CopyList L) { copy_chain<1>(L); }
 
+/* The ordered copy list RESOLVED on the host (engine.cu, build_copy_plan): walking the list symbolically gives, for every
+ * cell some copy writes, the cell whose value from BEFORE the list it ends up with and the sequence of Bloch rotations
+ * (cosk, sink) that value passes through on its way (a ghost corner of a periodic world goes through up to three copies).
+ * The kernel applies those rotations one after the other in registers -- the same multiplications and additions in the
+ * same order as the chain of copies (update.c:182-191), so the result is bit-identical -- and the whole list needs ONE
+ * barrier (every load before any store: a source cell may itself be rewritten) instead of one per dependent level. */
+#define ALISB_RC_ARRAYS 8
+#define ALISB_RC_CHAINS 48
+#define ALISB_RC_DEPTH 4
+#define ALISB_RC_PER_THREAD 8
+struct ResolvedCopy {
+	float *F[ALISB_RC_ARRAYS], *G[ALISB_RC_ARRAYS];
+	float cosk[ALISB_RC_CHAINS][ALISB_RC_DEPTH], sink[ALISB_RC_CHAINS][ALISB_RC_DEPTH];
+	int depth[ALISB_RC_CHAINS];
+	const int4 *ent;        /* x: target index, y: source index, z: array << 8 | chain; the bound entries first */
+	float2 *tmp;            /* one slot per bound entry, used when a thread owns more than ALISB_RC_PER_THREAD of them */
+	int n, nbound;          /* entries [0,nbound) read or write a cell that the list both reads and writes: every load before any
+	                         * store (one cluster, one barrier); entries [nbound,n) touch nothing another entry touches */
+};
+static __device__ __forceinline__ float2 rc_value(const ResolvedCopy &P, const int4 en)
+{
+	const int arr = en.z >> 8, ch = en.z & 255;
+	float f = P.F[arr][en.y], g = P.G[arr] ? P.G[arr][en.y] : 0.f;
+	const int depth = P.depth[ch];
+	for (int d = 0; d < depth; d++) {
+		const float c = P.cosk[ch][d], s = P.sink[ch][d];
+		if (P.G[arr]) { const float nf = c*f + s*g, ng = c*g - s*f; f = nf; g = ng; }
+		else f = c*f;
+	}
+	return make_float2(f, g);
+}
+static __device__ __forceinline__ void rc_store(const ResolvedCopy &P, const int4 en, const float2 v)
+{
+	const int arr = en.z >> 8;
+	P.F[arr][en.x] = v.x; if (P.G[arr]) P.G[arr][en.x] = v.y;
+}
+/* grid: [one cluster for the bound entries, if any] + clusters that share the free entries (two per thread and round, both
+ * loads in flight together) */
+__global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) copy_resolved(const __grid_constant__ ResolvedCopy P)
+{
+	const int lead = P.nbound ? ALISB_LIST_CTAS : 0;
+	if ((int)blockIdx.x >= lead) {
+		const int tid = (blockIdx.x - lead)*blockDim.x + threadIdx.x, nth = (gridDim.x - lead)*blockDim.x;
+		for (int t0 = P.nbound + tid; t0 < P.n; t0 += 2*nth) {
+			const int t1 = t0 + nth;
+			const int4 e0 = P.ent[t0]; int4 e1 = e0;
+			if (t1 < P.n) e1 = P.ent[t1];
+			const float2 v0 = rc_value(P, e0); float2 v1 = v0;
+			if (t1 < P.n) v1 = rc_value(P, e1);
+			rc_store(P, e0, v0);
+			if (t1 < P.n) rc_store(P, e1, v1);
+		}
+		return;
+	}
+	const int tid = blockIdx.x*blockDim.x + threadIdx.x, nth = ALISB_LIST_CTAS*blockDim.x;
+	if (P.nbound <= nth*ALISB_RC_PER_THREAD) {
+		int4 en[ALISB_RC_PER_THREAD]; float2 v[ALISB_RC_PER_THREAD];
+		#pragma unroll
+		for (int u = 0; u < ALISB_RC_PER_THREAD; u++) { const int t = tid + u*nth; if (t < P.nbound) en[u] = P.ent[t]; }
+		#pragma unroll
+		for (int u = 0; u < ALISB_RC_PER_THREAD; u++) { const int t = tid + u*nth; if (t < P.nbound) v[u] = rc_value(P, en[u]); }
+		list_sync();
+		#pragma unroll
+		for (int u = 0; u < ALISB_RC_PER_THREAD; u++) { const int t = tid + u*nth; if (t < P.nbound) rc_store(P, en[u], v[u]); }
+		return;
+	}
+	for (int t = tid; t < P.nbound; t += nth) P.tmp[t] = rc_value(P, P.ent[t]);
+	list_sync();
+	for (int t = tid; t < P.nbound; t += nth) rc_store(P, P.ent[t], P.tmp[t]);
+}
+
 /* All soft sources of a pass (reference updateS list, update.c:161-179) and all TFSF strips of a
  * pass (update.c:205-272) in one single-CTA launch each, in list order (overlapping boxes add in
  * the reference's order). */
@@ -1317,6 +1401,22 @@ __global__ void box_scatter(float *A, const float *buf, Box B, long long sC, lon
 	int a, b, c; size_t q;
 	if (!box_cell(B, (size_t)blockIdx.x*blockDim.x + threadIdx.x, a, b, c, q)) return;
 	A[c*sC + b*sB + a + off] = buf[((size_t)(a - B.a0)*B.nb + (b - B.b0))*B.nc + (c - B.c0)];
+}
+
+/* Small results go straight into mapped, pinned host memory ("mailbox"): the kernel stores the values, fences at system
+ * scope and then publishes a sequence number; the host spins on that word instead of paying for a device-to-host copy
+ * and a stream synchronisation (the launch-bound examples read one probe value or a few flux sums per step). */
+__global__ void __launch_bounds__(256) box_gather_mail(const float *A, float *host_buf, Box B, long long sC, long long sB, long long off, volatile unsigned *flag, unsigned seq)
+{
+	const size_t n = (size_t)B.na*B.nb*B.nc;
+	for (size_t t = threadIdx.x; t < n; t += blockDim.x) {
+		int a, b, c; size_t q;
+		box_cell(B, t, a, b, c, q);
+		host_buf[((size_t)(a - B.a0)*B.nb + (b - B.b0))*B.nc + (c - B.c0)] = A[c*sC + b*sB + a + off];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) { *flag = seq; __threadfence_system(); }
 }
 
 /* reference phaser.c:83-110 (updatePhaser): the running DFT of one call -- every face of the monitor
@@ -1436,6 +1536,66 @@ __global__ void flux_finish(const double *partial, int nblocks, double *out)
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) { out[2*q] = s1; out[2*q + 1] = s2; }
+}
+
+/* flux_partial + flux_finish in one launch, planes as kernel arguments, sums into the mailbox: the block that finishes a
+ * plane last adds the plane's partials in index order (so the result equals flux_finish's, whatever the order in which the
+ * blocks ran), and the last plane to finish publishes the sequence number */
+#define ALISB_FLUX_MAIL_PLANES 32
+struct FluxPlaneList { FluxPlane P[ALISB_FLUX_MAIL_PLANES]; };
+__global__ void __launch_bounds__(256) flux_mail(const __grid_constant__ FluxParams p, const __grid_constant__ FluxPlaneList planes, double *partial, unsigned *counters,
+                                                   double *host_out, volatile unsigned *flag, unsigned seq)
+{
+	const FluxPlane &P = planes.P[blockIdx.y];
+	const int a = P.axis, b = (a+1)%3, c = (a+2)%3;
+	const int ny = p.ny, pitch = p.pitch;
+	const int nb = P.b1 - P.b0 + 1, nc = P.c1 - P.c0 + 1;
+	const size_t step = a == 0 ? 1 : a == 1 ? (size_t)pitch : (size_t)(ny+2)*pitch;
+	double s1 = 0, s2 = 0;
+	for (size_t t = (size_t)blockIdx.x*blockDim.x + threadIdx.x; t < (size_t)nb*nc; t += (size_t)gridDim.x*blockDim.x) {
+		int ib, ic;
+		if (b == 0) { ib = P.b0 + (int)(t % nb); ic = P.c0 + (int)(t / nb); }
+		else        { ic = P.c0 + (int)(t % nc); ib = P.b0 + (int)(t / nc); }
+		const size_t i = flux_idx(a, P.at, ib, ic, ny, pitch);
+		if (ib > P.b0) {
+			const float wc = (ic == P.c0 || ic == P.c1) ? 0.5f : 1.0f;
+			s1 += (double)p.dH[b][ib] * ((double)wc * (double)p.dE[c][ic] * (double)p.E[b][i] * (double)(p.H[c][i] + p.H[c][i + step]));
+		}
+		if (ic > P.c0) {
+			const float wb = (ib == P.b0 || ib == P.b1) ? 0.5f : 1.0f;
+			s2 -= (double)p.dH[c][ic] * ((double)wb * (double)p.dE[b][ib] * (double)p.E[c][i] * (double)(p.H[b][i] + p.H[b][i + step]));
+		}
+	}
+	__shared__ double sh[2][128];
+	__shared__ bool last;
+	for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+	const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+	if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; }
+	__syncthreads();
+	if (w == 0) {
+		s1 = l < (blockDim.x >> 5) ? sh[0][l] : 0; s2 = l < (blockDim.x >> 5) ? sh[1][l] : 0;
+		for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+		if (l == 0) {
+			partial[2*((size_t)blockIdx.y*gridDim.x + blockIdx.x)] = s1; partial[2*((size_t)blockIdx.y*gridDim.x + blockIdx.x) + 1] = s2;
+			__threadfence();
+			last = atomicAdd(&counters[1 + blockIdx.y], 1u) == gridDim.x - 1;
+		}
+	}
+	__syncthreads();
+	if (!last) return;
+	__threadfence();
+	for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {          /* gridDim.x <= 128 */
+		sh[0][k] = __ldcg(&partial[2*((size_t)blockIdx.y*gridDim.x + k)]); sh[1][k] = __ldcg(&partial[2*((size_t)blockIdx.y*gridDim.x + k) + 1]);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		s1 = 0; s2 = 0;
+		for (int k = 0; k < (int)gridDim.x; k++) { s1 += sh[0][k]; s2 += sh[1][k]; }
+		host_out[2*blockIdx.y] = s1; host_out[2*blockIdx.y + 1] = s2;
+		counters[1 + blockIdx.y] = 0;
+		__threadfence_system();
+		if (atomicAdd(&counters[0], 1u) == gridDim.y - 1) { counters[0] = 0; __threadfence_system(); *flag = seq; __threadfence_system(); }
+	}
 }
 
 /* ------------------------------------------------------------------------------------------
