@@ -25,6 +25,7 @@
 #include "alis_b200.h"
 #include "kernels.cuh"
 #include "copy_resolve.h"
+#include "strip_resolve.h"
 
 /* the fused kernel needs more than the default 48 KB of dynamic shared memory (a per-device function attribute) */
 template <int ROWS, bool EPS, bool PMZ> static cudaError_t fused_optin_one()
@@ -79,6 +80,8 @@ struct TfsfObj {
 
 /* a resolved copy list (kernels.cuh, copy_resolved): built once per distinct list, found again by comparing the list */
 struct CopyPlan { CopyList key; ResolvedCopy P; int4 *d_ent; float2 *d_tmp; };
+/* a strip list regrouped per cell (kernels.cuh, strip_resolved), found again the same way */
+struct StripPlan { StripList key; ResolvedStrips P; RsCellDev *d_cells; RsTermDev *d_terms; };
 
 struct alisb_engine {
 	alisb_grid g;
@@ -149,6 +152,7 @@ struct alisb_engine {
 	PassGraph graph[2][3];             /* [set][part] */
 	FluxPlane *d_planes; double *d_partial, *d_flux, *h_flux; int flux_cap;
 	std::vector<CopyPlan*> cplan;      /* resolved copy lists (ALISB_RESOLVE, default 1) */
+	std::vector<StripPlan*> splan;     /* regrouped strip lists (same switch) */
 	int tune_resolve;
 	int tune_onewave, vol_occ[2][2][2][2][8];   /* launch-bound grids: volume launches sized to one wave of resident CTAs (ALISB_ONEWAVE, default 0: measured slower); resident CTAs per SM per variant */
 	int tune_aux_aside;                /* TFSF auxiliary worlds step on a side stream beside the volume launch (ALISB_AUX_ASIDE, default 1) */
@@ -415,6 +419,7 @@ extern "C" void alisb_destroy(alisb_engine *e)
 	for (int r=0; r<SRC_RING; r++) { if (e->srcv_h[r]) cudaFreeHost(e->srcv_h[r]); cudaFree(e->srcv_d[r]); if (e->srcv_ev[r]) cudaEventDestroy(e->srcv_ev[r]); }
 	cudaFree(e->d_planes); cudaFree(e->d_partial); cudaFree(e->d_flux); if (e->h_flux) cudaFreeHost(e->h_flux);
 	for (CopyPlan *cp : e->cplan) { cudaFree(cp->d_ent); cudaFree(cp->d_tmp); delete cp; }
+	for (StripPlan *sp : e->splan) { cudaFree(sp->d_cells); cudaFree(sp->d_terms); delete sp; }
 	if (e->mail_h) cudaFreeHost(e->mail_h);
 	cudaFree(e->d_mail_counters); cudaFree(e->d_mail_partial);
 	if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -1362,28 +1367,104 @@ static bool boxes_meet(const Box &A, const Box &B)
 	return A.a0 < B.a0 + B.na && B.a0 < A.a0 + A.na && A.b0 < B.b0 + B.nb && B.b0 < A.b0 + A.nb && A.c0 < B.c0 + B.nc && B.c0 < A.c0 + A.nc;
 }
 
+/* the strips of one TFSF region for this pass (clipped to the planes of the current part) as a list for the list kernels;
+ * false: the faces are large, one launch per strip */
+static bool small_strip_list(alisb_engine *e, const TfsfObj *t, int set, StripList &SL)
+{
+	const alisb_engine *x = t->d.aux;
+	const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
+	memset(&SL, 0, sizeof SL);             /* the list is also the key of its regrouped plan */
+	SL.n = 0; SL.ny = e->ny; SL.pitch = e->pitch; SL.any = x->ny; SL.apitch = x->pitch;
+	for (int m=0; m<=e->g.complex_field; m++) for (const alisb_strip &s : L) {
+		Box B = clipc(mkbox(s.box), e->f_lo, e->f_hi);
+		const size_t n = bcount(B);
+		if (!n) continue;
+		if (n > 16384 || SL.n == ALISB_MAXSTRIPOPS) return false;
+		StripOp &o = SL.op[SL.n++];
+		o.F = e->F[set][m][s.comp]; o.G = x->F[1-set][m][s.aux_comp]; o.C = s.use_eps ? e->eps[s.comp] : 0; o.coef = s.coef; o.B = B;
+		o.alt0 = s.alt[0] + t->d.offset[0]; o.alt1 = s.alt[1] + t->d.offset[1]; o.alt2 = s.alt[2] + t->d.offset[2];
+		o.clampa = t->d.clamp[1-set][s.aux_comp][0]; o.clampb = t->d.clamp[1-set][s.aux_comp][1];
+	}
+	return true;
+}
+
+static StripPlan *build_strip_plan(alisb_engine *e, const alisb_engine *x, const StripList &SL)
+{
+	if ((e->nz + 2)*e->plane >= ((size_t)1 << 31) || (x->nz + 2)*x->plane >= ((size_t)1 << 31)) return 0;
+	RsOp ops[ALISB_MAXSTRIPOPS];
+	for (int q=0; q<SL.n; q++) {
+		const StripOp &o = SL.op[q];
+		ops[q].F = o.F; ops[q].G = o.G; ops[q].C = o.C; ops[q].coef = o.coef;
+		ops[q].a0 = o.B.a0; ops[q].b0 = o.B.b0; ops[q].c0 = o.B.c0; ops[q].na = o.B.na; ops[q].nb = o.B.nb; ops[q].nc = o.B.nc;
+		ops[q].alt0 = o.alt0; ops[q].alt1 = o.alt1; ops[q].alt2 = o.alt2; ops[q].clampa = o.clampa; ops[q].clampb = o.clampb;
+	}
+	RsPlan R;
+	if (!rs_resolve(ops, SL.n, SL.ny, SL.pitch, SL.any, SL.apitch, ALISB_XO, ALISB_RS_ARRAYS, 15, R)) return 0;
+	std::vector<RsCellDev> cells(R.cells.size());
+	std::vector<RsTermDev> terms;
+	for (size_t q=0; q<R.cells.size(); q++) {
+		const RsCell &c = R.cells[q];
+		const RsTerm &t0 = R.terms[c.first];
+		RsCellDev d;
+		d.tgt = c.tgt; d.src = t0.src; d.coef = t0.coef; d.pad = 0;
+		d.meta = c.farr | (t0.garr << 4) | ((t0.carr + 1) << 8) | (c.count << 12);
+		d.more = (int)terms.size();
+		for (int k=1; k<c.count; k++) {
+			const RsTerm &t = R.terms[c.first + k];
+			RsTermDev td; td.src = t.src; td.coef = t.coef; td.meta = t.garr | ((t.carr + 1) << 4); td.pad = 0;
+			terms.push_back(td);
+		}
+		cells[q] = d;
+	}
+	StripPlan *sp = new StripPlan();
+	memset(&sp->P, 0, sizeof sp->P);
+	sp->key = SL; sp->d_cells = 0; sp->d_terms = 0;
+	for (size_t q=0; q<R.F.size(); q++) sp->P.F[q] = (float*)R.F[q];
+	for (size_t q=0; q<R.G.size(); q++) sp->P.G[q] = (const float*)R.G[q];
+	for (size_t q=0; q<R.C.size(); q++) sp->P.C[q] = (const float*)R.C[q];
+	sp->P.n = (int)cells.size();
+	if (sp->P.n) {
+		bool ok = cudaMalloc((void**)&sp->d_cells, sizeof(RsCellDev)*cells.size()) == cudaSuccess
+		       && cudaMemcpy(sp->d_cells, cells.data(), sizeof(RsCellDev)*cells.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+		if (ok && !terms.empty()) ok = cudaMalloc((void**)&sp->d_terms, sizeof(RsTermDev)*terms.size()) == cudaSuccess
+		                            && cudaMemcpy(sp->d_terms, terms.data(), sizeof(RsTermDev)*terms.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+		if (!ok) { cudaGetLastError(); cudaFree(sp->d_cells); cudaFree(sp->d_terms); delete sp; return 0; }
+	}
+	sp->P.cells = sp->d_cells; sp->P.terms = sp->d_terms;
+	return sp;
+}
+
+static StripPlan *strip_plan(alisb_engine *e, const alisb_engine *x, const StripList &SL, bool may_build)
+{
+	if (!e->tune_resolve || e->dbuf || x->dbuf || SL.n < 2) return 0;
+	for (StripPlan *sp : e->splan) if (!memcmp(&sp->key, &SL, sizeof SL)) return sp->P.n >= 0 ? sp : 0;
+	if (!may_build) return 0;
+	if (e->splan.size() >= 16) {
+		cudaStreamSynchronize(e->stream);
+		for (StripPlan *sp : e->splan) { cudaFree(sp->d_cells); cudaFree(sp->d_terms); delete sp; }
+		e->splan.clear(); e->cfg_version++;
+	}
+	StripPlan *sp = build_strip_plan(e, x, SL);
+	if (!sp) { sp = new StripPlan(); sp->key = SL; sp->d_cells = 0; sp->d_terms = 0; memset(&sp->P, 0, sizeof sp->P); sp->P.n = -1; }
+	e->splan.push_back(sp);
+	return sp->P.n >= 0 ? sp : 0;
+}
+
 static int apply_tfsf(alisb_engine *e, int set, bool step_aux)
 {
 	for (TfsfObj *t : e->tf) {
 		alisb_engine *x = t->d.aux;
 		if (step_aux) TRY(pass_launch(x, set, ALISB_PART_ALL));
 		const std::vector<alisb_strip> &L = set == ALISB_SET_E ? t->sE : t->sH;
-		/* small faces: all strips of this TFSF region in one single-CTA launch */
+		/* small faces: all strips of this TFSF region in one launch */
 		{
 			StripList SL;
-			SL.n = 0; SL.ny = e->ny; SL.pitch = e->pitch; SL.any = x->ny; SL.apitch = x->pitch;
-			bool ok = true;
-			for (int m=0; m<=e->g.complex_field && ok; m++) for (const alisb_strip &s : L) {
-				Box B = clipc(mkbox(s.box), e->f_lo, e->f_hi);
-				const size_t n = bcount(B);
-				if (!n) continue;
-				if (n > 16384 || SL.n == ALISB_MAXSTRIPOPS) { ok = false; break; }
-				StripOp &o = SL.op[SL.n++];
-				o.F = e->F[set][m][s.comp]; o.G = x->F[1-set][m][s.aux_comp]; o.C = s.use_eps ? e->eps[s.comp] : 0; o.coef = s.coef; o.B = B;
-				o.alt0 = s.alt[0] + t->d.offset[0]; o.alt1 = s.alt[1] + t->d.offset[1]; o.alt2 = s.alt[2] + t->d.offset[2];
-				o.clampa = t->d.clamp[1-set][s.aux_comp][0]; o.clampb = t->d.clamp[1-set][s.aux_comp][1];
-			}
+			const bool ok = small_strip_list(e, t, set, SL);
 			if (ok) {
+				if (StripPlan *sp = strip_plan(e, x, SL, g_mode != GMODE_CAPTURE)) {
+					if (sp->P.n) { strip_resolved<<<div_up(sp->P.n, 256), 256, 0, e->stream>>>(sp->P); e->launches++; }
+					continue;
+				}
 				if (SL.n) {
 					/* strips that add to the same array keep their order where their boxes meet (float addition is not associative);
 					 * the chains of the three components (and of the complex sets) run side by side */
@@ -1565,7 +1646,11 @@ static int pass_prepare(alisb_engine *e, int set, int part)
 	set_filter(e, set, part);
 	if (ade_in_kernel(e)) TRY(ade_table(e));
 	TRY(prepare_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
-	if (e->tune_resolve && !e->dbuf) { CopyList L; if (small_copy_list(e, set, L)) copy_plan(e, L, true); }   /* the pass may be captured: plans are built here */
+	if (e->tune_resolve && !e->dbuf) {              /* the pass may be captured: plans are built here */
+		CopyList L;
+		if (small_copy_list(e, set, L)) copy_plan(e, L, true);
+		for (TfsfObj *t : e->tf) { StripList SL; if (small_strip_list(e, t, set, SL)) strip_plan(e, t->d.aux, SL, true); }
+	}
 	return ALISB_OK;
 }
 
@@ -1583,16 +1668,18 @@ static int pass_launch(alisb_engine *e, int set, int part)
 	 * (update.c:242-269); the pass as a whole ends when both have finished */
 	const bool aux_aside = part != ALISB_PART_REST && !e->tf.empty() && e->tune_conc > 0 && e->tune_aux_aside && (long)e->nx*e->ny*e->nz < e->tune_small;
 	if (aux_aside) {
-		CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->side[1], e->ev_fork, 0));
+		/* on the stream of the highest priority: this world's volume launch fills every SM (two CTAs take the whole register
+		 * file), so the few CTAs of the auxiliary chain must be first in line whenever a slot frees up */
+		CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->hi, e->ev_fork, 0));
 		int rca = ALISB_OK;
 		for (TfsfObj *t : e->tf) {
 			alisb_engine *x = t->d.aux;
 			cudaStream_t const xs = x->stream;
-			x->stream = e->side[1];
+			x->stream = e->hi;
 			if (rca == ALISB_OK) rca = pass_launch(x, set, ALISB_PART_ALL);
 			x->stream = xs;
 		}
-		CU(cudaEventRecord(e->ev_join[1], e->side[1]));
+		CU(cudaEventRecord(e->ev_hi, e->hi));
 		TRY(rca);
 	}
 	if (pair) { CU(cudaEventRecord(e->ev_fork, main_stream)); CU(cudaStreamWaitEvent(e->side[0], e->ev_fork, 0)); }
@@ -1614,7 +1701,7 @@ static int pass_launch(alisb_engine *e, int set, int part)
 	set_filter(e, set, part);
 	TRY(launch_sources(e, set, set == ALISB_SET_E ? e->tH : e->tE));
 	TRY(apply_copies(e, set));
-	if (aux_aside) CU(cudaStreamWaitEvent(main_stream, e->ev_join[1], 0));
+	if (aux_aside) CU(cudaStreamWaitEvent(main_stream, e->ev_hi, 0));
 	e->f_lo = 0; e->f_hi = e->nz + 1;
 	return ALISB_OK;
 }

@@ -1387,6 +1387,35 @@ template <int CL> static __device__ __forceinline__ void strip_chain(const Strip
 __global__ void __cluster_dims__(ALISB_LIST_CTAS, 1, 1) __launch_bounds__(1024) strip_list(const __grid_constant__ StripList L) { strip_chain<ALISB_LIST_CTAS>(L); }
 __global__ void __launch_bounds__(1024) strip_list1(const __grid_constant__ StripList L) { strip_chain<1>(L); }
 
+/* The strip list regrouped per cell (engine.cu, build_strip_plan; strip_resolve.h): one thread per cell adds the cell's
+ * terms in list order -- the same products and the same sequence of additions as the strips one after the other
+ * (update.c:193-202), no ordering between cells, no barrier.  A cell record carries its first term (most cells have one). */
+#define ALISB_RS_ARRAYS 8
+struct RsCellDev { int tgt, meta, src; float coef; int more, pad; };   /* meta: farr | garr << 4 | (carr+1) << 8 | count << 12; more: index of the 2nd term */
+struct RsTermDev { int src; float coef; int meta, pad; };              /* meta: garr | (carr+1) << 4 */
+struct ResolvedStrips { float *F[ALISB_RS_ARRAYS]; const float *G[ALISB_RS_ARRAYS], *C[ALISB_RS_ARRAYS]; const RsCellDev *cells; const RsTermDev *terms; int n; };
+__global__ void __launch_bounds__(256) strip_resolved(const __grid_constant__ ResolvedStrips P)
+{
+	const int t = blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= P.n) return;
+	const RsCellDev c = P.cells[t];
+	const int farr = c.meta & 15, garr = (c.meta >> 4) & 15, carr = ((c.meta >> 8) & 15) - 1, count = c.meta >> 12;
+	float f = P.F[farr][c.tgt];
+	{
+		const float g = P.G[garr][c.src];
+		if (carr >= 0) f += c.coef*g*P.C[carr][c.tgt];
+		else           f += c.coef*g;
+	}
+	for (int k = 1; k < count; k++) {
+		const RsTermDev tm = P.terms[c.more + k - 1];
+		const int ga = tm.meta & 15, ca = ((tm.meta >> 4) & 15) - 1;
+		const float g = P.G[ga][tm.src];
+		if (ca >= 0) f += tm.coef*g*P.C[ca][c.tgt];
+		else         f += tm.coef*g;
+	}
+	P.F[farr][c.tgt] = f;
+}
+
 /* gather / scatter a box between any engine array (element (a,b,c) at c*sC + b*sB + a + off) and a
  * dense buffer in the HOST order (z fastest, reference makeField layout): the transposition is
  * done here so that the host side is a plain memcpy */

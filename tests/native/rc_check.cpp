@@ -11,6 +11,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "../../alis_b200/csrc/copy_resolve.h"
+#include "../../alis_b200/csrc/strip_resolve.h"
 
 struct Op { int arr; float cosk, sink; RcOp r; };
 static const int XO = 31;
@@ -163,7 +164,70 @@ int main(int argc, char **argv)
 		cases++;
 		if (run_case(L, narr, cplx, resolved, refused, "random list")) { printf("seed %d\n", seed); return 1; }
 	}
+	/* (3) strip lists (strip_resolve.h): overlapping face strips added one after the other (update(), update.c:193-202) against
+	 *     the per-cell regrouping that kernel strip_resolved applies */
+	size_t strip_cells = 0, strip_multi = 0;
+	for (int seed=0; seed<seeds; seed++) {
+		rng_state = 5000 + seed;
+		NX = rint_(4, 12); NY = rint_(4, 9); NZ = rint_(4, 8); PITCH = 64; ELEMS = (size_t)(NZ+2)*(NY+2)*PITCH;
+		const int ANY = rint_(1, NY), APITCH = 64, ANZ = NZ;                 /* auxiliary world: fewer rows, same planes */
+		const size_t AELEMS = (size_t)(ANZ+2)*(ANY+2)*APITCH;
+		const int nf = rint_(1, 3), ng = rint_(1, 3), nc = rint_(1, 2);
+		std::vector<std::vector<float> > F(nf, std::vector<float>(ELEMS)), G(ng, std::vector<float>(AELEMS)), C(nc, std::vector<float>(ELEMS));
+		for (auto &v : F) for (float &x : v) x = rflt();
+		for (auto &v : G) for (float &x : v) x = rflt();
+		for (auto &v : C) for (float &x : v) x = rflt();
+		std::vector<std::vector<float> > F2 = F;
+		const int nops = rint_(2, 30);
+		std::vector<RsOp> ops(nops);
+		for (int q=0; q<nops; q++) {
+			RsOp &o = ops[q];
+			const int N[3] = {NX, NY, NZ};
+			int lo[3], hi[3];
+			const int thin = rint_(0, 2);
+			for (int ax=0; ax<3; ax++) {
+				if (ax == thin) lo[ax] = hi[ax] = rint_(1, N[ax]);
+				else { lo[ax] = rint_(1, N[ax]); hi[ax] = rint_(lo[ax], N[ax]); }
+			}
+			o.F = &F[rint_(0, nf-1)]; o.G = &G[rint_(0, ng-1)]; o.C = (rnd() & 1) ? (const void*)&C[rint_(0, nc-1)] : 0; o.coef = rflt();
+			o.a0 = lo[0]; o.b0 = lo[1]; o.c0 = lo[2]; o.na = hi[0]-lo[0]+1; o.nb = hi[1]-lo[1]+1; o.nc = hi[2]-lo[2]+1;
+			o.alt0 = rint_(0, 1); o.alt1 = rint_(-1, 1); o.alt2 = rint_(-1, 1);
+			o.clampa = rint_(1, 31); o.clampb = ANY;                           /* rows beyond the auxiliary world clamp to its last row */
+			if (o.b0 + o.alt1 < 0) o.alt1 = 0;
+		}
+		/* in order, as kernel strip_list / the reference */
+		for (const RsOp &o : ops) {
+			std::vector<float> &f = *(std::vector<float>*)o.F; const std::vector<float> &g = *(const std::vector<float>*)o.G;
+			for (int c=o.c0; c<o.c0+o.nc; c++) for (int b=o.b0; b<o.b0+o.nb; b++) for (int a=o.a0; a<o.a0+o.na; a++) {
+				const size_t i = idx(a, b, c);
+				const int xa = std::min(a + o.alt0, o.clampa), xb = std::min(b + o.alt1, o.clampb), xc = c + o.alt2;
+				const float gv = g[((size_t)xc*(ANY+2) + xb)*APITCH + XO + xa];
+				if (o.C) f[i] += o.coef*gv*(*(const std::vector<float>*)o.C)[i];
+				else     f[i] += o.coef*gv;
+			}
+		}
+		RsPlan P;
+		cases++;
+		if (!rs_resolve(ops.data(), nops, NY, PITCH, ANY, APITCH, XO, 8, 15, P)) { refused++; continue; }
+		resolved++;
+		for (size_t t=P.cells.size(); t-- > 0; ) {                          /* any order: here from the last cell to the first */
+			const RsCell &cl = P.cells[t];
+			int fa = -1;
+			for (int q=0; q<nf; q++) if (P.F[cl.farr] == (const void*)&F[q]) fa = q;
+			float f = F2[fa][cl.tgt];
+			for (int k=0; k<cl.count; k++) {
+				const RsTerm &tm = P.terms[cl.first + k];
+				const float gv = (*(const std::vector<float>*)P.G[tm.garr])[tm.src];
+				if (tm.carr >= 0) f += tm.coef*gv*(*(const std::vector<float>*)P.C[tm.carr])[cl.tgt];
+				else              f += tm.coef*gv;
+			}
+			F2[fa][cl.tgt] = f;
+			strip_cells++; if (cl.count > 1) strip_multi++;
+		}
+		for (int q=0; q<nf; q++) if (memcmp(F[q].data(), F2[q].data(), ELEMS*sizeof(float))) { printf("strip list seed %d: array %d differs between the ordered strips and the regrouped plan\n", seed, q); return 1; }
+	}
+	if (!strip_multi) { printf("no cell with more than one strip term was exercised\n"); return 1; }
 	if (resolved < cases/2) { printf("only %d of %d lists resolved\n", resolved, cases); return 1; }
-	printf("ok %d %d %d bound %zu of %zu\n", cases, resolved, refused, g_bound, g_entries);
+	printf("ok %d %d %d bound %zu of %zu strips %zu of %zu\n", cases, resolved, refused, g_bound, g_entries, strip_multi, strip_cells);
 	return 0;
 }

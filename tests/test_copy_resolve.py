@@ -2,7 +2,9 @@
 
 CPU part: tests/bin/rc_check (tests/native/rc_check.cpp, built by alis_b200/build_host.sh) applies random ordered copy
 lists, and the periodic / hexagonal H-pass lists of reference update.c:311-339, once copy by copy as the reference does
-(copyBoundary, update.c:182-191) and once through the resolved plan; both must agree bit for bit.
+(copyBoundary, update.c:182-191) and once through the resolved plan; both must agree bit for bit.  The same program checks
+the TFSF strip lists regrouped per cell (alis_b200/csrc/strip_resolve.h, kernel strip_resolved) against the strips added
+one after the other (update(), update.c:193-202).
 GPU part: worlds whose passes end in such lists step identically with the resolved kernel and with the level-by-level
 list kernels (ALISB_RESOLVE=0), and identically to the oracle."""
 import os
@@ -19,10 +21,11 @@ def test_resolved_plan_equals_ordered_copies_on_cpu():
     assert os.path.exists(RC), "tests/bin/rc_check is missing: run __graft_entry__.build()"
     r = subprocess.run([RC, "400"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    word, cases, resolved, refused, _, bound, _, entries = r.stdout.split()
-    assert word == "ok" and int(cases) == 404 and int(resolved) + int(refused) == int(cases)
-    assert int(resolved) >= 350          # the walk must not give up on ordinary lists
+    word, cases, resolved, refused, _, bound, _, entries, _, multi, _, cells = r.stdout.split()
+    assert word == "ok" and int(cases) == 804 and int(resolved) + int(refused) == int(cases)
+    assert int(resolved) >= 700          # the walks must not give up on ordinary lists
     assert 0 < int(bound) < int(entries)  # both kinds of entries (ordered among themselves / free) were exercised
+    assert 0 < int(multi) < int(cells)    # strip cells with one and with several ordered terms
 
 
 class BlochBox:
@@ -91,3 +94,22 @@ def test_resolved_copies_step_like_ordered_copies(oracle_lib, engine_lib, monkey
     helpers.assert_fields_identical(g, o, f"resolved copies vs oracle {shape}")
     helpers.assert_fields_identical(g0, o, f"list kernels vs oracle {shape}")
     assert g.launch_count() <= g0.launch_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["nanoblock", "tfsf_normal", "metasurface", "phc", "focused_tfsf"])
+@pytest.mark.parametrize("knobs", [
+    {"ALISB_RESOLVE": "0"},                                           # the level-by-level list kernels (copy_list, strip_list)
+    {"ALISB_MAILBOX": "0", "ALISB_AUX_ASIDE": "0", "ALISB_CONC": "0"},  # copies + stream sync, auxiliary worlds in line, no side streams
+], ids=["list-kernels", "in-line"])
+def test_named_configs_with_the_launch_bound_knobs_off(cfg, knobs, tmp_path, monkeypatch):
+    """the default path (resolved copies and strips, mailbox, auxiliary worlds on a side stream) is what every other GPU test
+    runs; here the same reference-built worlds step through the paths those replaced and must give the same golden state"""
+    from tests import helpers
+    if not helpers.have_ref_bin("stepdump_bridge_cuda"):
+        pytest.skip("oracle/_ref harness not built")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    out = str(tmp_path / "g.bin")
+    helpers.run_stepdump("stepdump_bridge_cuda", cfg, out, cwd=str(tmp_path))
+    assert helpers.sha256_file(out) == helpers.golden_hashes()[cfg]["sha256"], f"{cfg} with {knobs} differs from the reference golden"
