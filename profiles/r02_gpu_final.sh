@@ -14,8 +14,4 @@ timeout 400 ncu --set full --clock-control none --import-source on --launch-skip
 	-o $O/r02_ncu_fused_$T python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $O/r02_ncu_fused_$T.log 2>&1
 ncu -i $O/r02_ncu_fused_$T.ncu-rep --page raw --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,launch__grid_size > $O/r02_ncu_fused_${T}_raw.csv 2>&1
 cat $O/r02_ncu_fused_${T}_raw.csv | cut -d, -f5,9,12- | tail -3
-mkdir -p /tmp/phc && cp tests/bin/refex_PhC_Band_Diagram_cuda /tmp/phc/PhC_Band_Diagram && ( cd /tmp/phc && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 100000 -c 60 --csv --log-file $O/r02_launches_phc_$T.csv ./PhC_Band_Diagram > /dev/null 2>&1 )
-python - <<'PY'
-import csv,os
-p='gpurun_out/r02_launches_phc_%s.csv' % (os.environ.get('T') or 'final')
-PY
+ls -la $O | tail -15
