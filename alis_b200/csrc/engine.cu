@@ -1986,7 +1986,7 @@ static int mail_open(alisb_engine *e)
 	memset(h, 0, MAIL_BYTES + 64);
 	if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return fail(ALISB_ECUDA, "mailbox: no device pointer for mapped host memory"); }
 	unsigned *cnt = 0; double *part = 0;
-	if (cudaMalloc((void**)&cnt, sizeof(unsigned)*(1 + ALISB_FLUX_MAIL_PLANES)) != cudaSuccess || cudaMalloc((void**)&part, sizeof(double)*2*128*ALISB_FLUX_MAIL_PLANES) != cudaSuccess
+	if (cudaMalloc((void**)&cnt, sizeof(unsigned)*(1 + ALISB_FLUX_MAIL_PLANES)) != cudaSuccess || cudaMalloc((void**)&part, sizeof(double)*2*(128 + 1)*ALISB_FLUX_MAIL_PLANES) != cudaSuccess
 	    || cudaMemset(cnt, 0, sizeof(unsigned)*(1 + ALISB_FLUX_MAIL_PLANES)) != cudaSuccess) {
 		cudaGetLastError(); cudaFree(cnt); cudaFree(part); cudaFreeHost(h); return fail(ALISB_ECUDA, "mailbox: allocation failed");
 	}
@@ -1995,9 +1995,10 @@ static int mail_open(alisb_engine *e)
 }
 /* waits for the kernel that was launched with sequence number `seq`; polls the stream now and then so that a launch
  * that died does not hang the host */
-static int mail_wait(alisb_engine *e, unsigned seq)
+static int mail_wait(alisb_engine *e, unsigned seq, bool pair = false)
 {
-	volatile unsigned *flag = (volatile unsigned*)(e->mail_h + MAIL_BYTES);
+	/* pair: a single value and its sequence number in one 8-byte word (floats 1022, 1023 of the payload: value, number) */
+	volatile unsigned *flag = pair ? (volatile unsigned*)(e->mail_h + 1023*sizeof(float)) : (volatile unsigned*)(e->mail_h + MAIL_BYTES);
 	for (unsigned long spins = 1; *flag != seq; spins++) {
 		if ((spins & 0xffff) == 0) {
 			const cudaError_t st = cudaStreamQuery(e->stream);
@@ -2030,14 +2031,20 @@ static int rw_box_one(alisb_engine *e, int arr, const int32_t ids[6], const int3
 	case 3:  sB = e->pitch; sC = (long long)(e->ny+2)*e->pitch; off = ALISB_XO - (long long)r.dense.c0*sC; break;
 	default: sB = r.dense.na; sC = (long long)r.dense.nb*r.dense.na; off = -((long long)r.dense.c0*sC + (long long)r.dense.b0*sB + r.dense.a0); break;
 	}
-	if (!write && e->tune_mail && n*sizeof(float) <= MAIL_BYTES) {
+	if (!write && e->tune_mail && n*sizeof(float) <= MAIL_BYTES - 2*sizeof(float)) {
 		TRY(mail_open(e));
 		const unsigned seq = ++e->mail_seq;
-		box_gather_mail<<<1, 256, 0, e->stream>>>(r.p, (float*)e->mail_d, B, sC, sB, off, (volatile unsigned*)(e->mail_d + MAIL_BYTES), seq);
+		box_gather_mail<<<1, n == 1 ? 32 : 256, 0, e->stream>>>(r.p, (float*)e->mail_d, B, sC, sB, off, (volatile unsigned*)(e->mail_d + MAIL_BYTES), seq);
 		CU(cudaGetLastError());
 		e->launches++;
-		TRY(mail_wait(e, seq));
-		memcpy(host, e->mail_h, n*sizeof(float));
+		TRY(mail_wait(e, seq, n == 1));
+		if (n == 1) {
+			/* value and number were stored as one 8-byte word; read them the same way */
+			const unsigned long long w = *(volatile unsigned long long*)(e->mail_h + 1022*sizeof(float));
+			if ((unsigned)(w >> 32) != seq) return fail(ALISB_ECUDA, "mailbox: torn probe word");
+			const unsigned bits = (unsigned)w;
+			memcpy(host, &bits, sizeof(float));
+		} else memcpy(host, e->mail_h, n*sizeof(float));
 		return ALISB_OK;
 	}
 	TRY(need_scratch(e, n));

@@ -1438,6 +1438,15 @@ __global__ void box_scatter(float *A, const float *buf, Box B, long long sC, lon
 __global__ void __launch_bounds__(256) box_gather_mail(const float *A, float *host_buf, Box B, long long sC, long long sB, long long off, volatile unsigned *flag, unsigned seq)
 {
 	const size_t n = (size_t)B.na*B.nb*B.nc;
+	if (n == 1) {
+		/* a single value (the probe of a `get`) travels together with its sequence number in ONE aligned 8-byte store,
+		 * which cannot be torn: no fence, no second store (the host reads the pair at host_buf + 1022, see mail_wait) */
+		if (threadIdx.x == 0) {
+			const float v = A[B.c0*sC + B.b0*sB + B.a0 + off];
+			*reinterpret_cast<volatile unsigned long long*>(host_buf + 1022) = ((unsigned long long)seq << 32) | __float_as_uint(v);
+		}
+		return;
+	}
 	for (size_t t = threadIdx.x; t < n; t += blockDim.x) {
 		int a, b, c; size_t q;
 		box_cell(B, t, a, b, c, q);
@@ -1445,7 +1454,7 @@ __global__ void __launch_bounds__(256) box_gather_mail(const float *A, float *ho
 	}
 	__threadfence_system();
 	__syncthreads();
-	if (threadIdx.x == 0) { *flag = seq; __threadfence_system(); }
+	if (threadIdx.x == 0) *flag = seq;           /* the end of the kernel flushes it */
 }
 
 /* reference phaser.c:83-110 (updatePhaser): the running DFT of one call -- every face of the monitor
@@ -1620,10 +1629,19 @@ __global__ void __launch_bounds__(256) flux_mail(const __grid_constant__ FluxPar
 	if (threadIdx.x == 0) {
 		s1 = 0; s2 = 0;
 		for (int k = 0; k < (int)gridDim.x; k++) { s1 += sh[0][k]; s2 += sh[1][k]; }
-		host_out[2*blockIdx.y] = s1; host_out[2*blockIdx.y + 1] = s2;
+		/* the plane's sums stay on the device; the plane that finishes last carries all of them to the host in one go: one
+		 * system-scope fence per request instead of one per plane */
+		double *dev_out = partial + 2*(size_t)gridDim.x*gridDim.y;
+		dev_out[2*blockIdx.y] = s1; dev_out[2*blockIdx.y + 1] = s2;
 		counters[1 + blockIdx.y] = 0;
-		__threadfence_system();
-		if (atomicAdd(&counters[0], 1u) == gridDim.y - 1) { counters[0] = 0; __threadfence_system(); *flag = seq; __threadfence_system(); }
+		__threadfence();
+		if (atomicAdd(&counters[0], 1u) == gridDim.y - 1) {
+			counters[0] = 0;
+			__threadfence();
+			for (int q = 0; q < 2*(int)gridDim.y; q++) host_out[q] = __ldcg(&dev_out[q]);
+			__threadfence_system();
+			*flag = seq;                          /* the end of the kernel flushes it */
+		}
 	}
 }
 
