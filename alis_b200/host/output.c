@@ -9,9 +9,12 @@
  * (cited per function); sums run in index order, i.e. they equal the reference's result with one
  * OpenMP thread (its `omp reduction` makes the last digits thread-count dependent).
  */
+#define _GNU_SOURCE
 #include <sys/time.h>
 #include <sys/stat.h>
 #include <string.h>
+#include <pthread.h>
+#include <sched.h>
 #include "alis_c.h"
 #include "host_internal.h"
 
@@ -177,6 +180,84 @@ void (writeRow)(world W, char *format, ...)
 	va_end(ap);
 }
 
+/* ---- the running DFT of writeSpectrum beside the time loop ------------------------------------------------------
+ * A writeSpectrum call adds one sample to every bin: `bins` complex exponentials, 9 us of host time per call in
+ * PhC_Band_Diagram -- on the critical path of a launch-bound loop, because the sample comes from a `get` that has just
+ * waited for the step and the next step is only enqueued afterwards.  The additions do not have to happen now: the
+ * bins are read once, when the record is complete.  A call therefore only queues (row, sample, phase step); one worker
+ * thread performs the additions, in call order (one consumer, FIFO: every bin receives the same float operations in the
+ * same order as the in-line loop, so the spectrum is bit-identical), while the driver's thread is already waiting for
+ * the next step.  The call that completes a record drains the queue first.  ALIS_SPECTRUM_THREAD=0 / 1: in line / worker
+ * (default: worker with the CUDA engine only). */
+typedef struct { float complex *row; int bins, nMax; float t; double d; } spec_job;
+#define SPEC_RING 4096
+static spec_job spec_ring[SPEC_RING];
+static unsigned long spec_head, spec_tail;          /* jobs queued / jobs finished (monotonic) */
+static pthread_t spec_thread;
+static int spec_mode = -1;                          /* -1 undecided, 0 in line, 1 worker running */
+static pthread_mutex_t spec_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t spec_wake = PTHREAD_COND_INITIALIZER;
+static int spec_asleep;
+
+static void spec_accumulate(const spec_job *j)
+{
+	for (int n=0; n<j->bins; n++) j->row[n] += (float) j->d * cexpf(2*PI*I*j->t*(j->nMax-n));      /* reference output.c:214 */
+}
+
+static void *spec_worker(void *arg)
+{
+	(void)arg;
+	for (;;) {
+		unsigned long idle = 0;
+		unsigned long long since = 0;
+		while (__atomic_load_n(&spec_head, __ATOMIC_ACQUIRE) == spec_tail) {
+			/* stays awake for 300 us after its last job (a time loop that calls every 50..200 us never pays for a wake-up),
+			 * then sleeps on the condition variable so that it does not take a core from anybody */
+			if ((++idle & 31) == 1) {
+				struct timeval tv; gettimeofday(&tv, 0);
+				const unsigned long long now = tv.tv_sec*1000000ULL + tv.tv_usec;
+				if (!since) since = now;
+				if (now - since < 300) { sched_yield(); continue; }
+			} else { sched_yield(); continue; }
+			pthread_mutex_lock(&spec_lock);
+			__atomic_store_n(&spec_asleep, 1, __ATOMIC_SEQ_CST);
+			while (__atomic_load_n(&spec_head, __ATOMIC_SEQ_CST) == spec_tail) pthread_cond_wait(&spec_wake, &spec_lock);
+			__atomic_store_n(&spec_asleep, 0, __ATOMIC_SEQ_CST);
+			pthread_mutex_unlock(&spec_lock);
+			idle = 0; since = 0;
+		}
+		spec_accumulate(&spec_ring[spec_tail % SPEC_RING]);
+		__atomic_store_n(&spec_tail, spec_tail + 1, __ATOMIC_RELEASE);
+	}
+	return 0;
+}
+
+static void spec_drain(void)
+{
+	while (__atomic_load_n(&spec_tail, __ATOMIC_ACQUIRE) != spec_head) sched_yield();
+}
+
+static void spec_submit(const spec_job *j)
+{
+	if (spec_mode < 0) {
+		/* default: on with the CUDA engine (the host cores are idle while the device steps), off with a CPU engine (the
+		 * oracle's OpenMP team owns every core: a spinning worker measured 17 % slower there) */
+		const char *s = getenv("ALIS_SPECTRUM_THREAD");
+		const int want = s ? atoi(s) : !strncmp(alisb_backend(), "cuda", 4);
+		spec_mode = want && pthread_create(&spec_thread, 0, spec_worker, 0) == 0 ? 1 : 0;
+		if (spec_mode) pthread_detach(spec_thread);
+	}
+	if (!spec_mode) { spec_accumulate(j); return; }
+	while (spec_head - __atomic_load_n(&spec_tail, __ATOMIC_ACQUIRE) >= SPEC_RING) sched_yield();     /* ring full: the worker is behind */
+	spec_ring[spec_head % SPEC_RING] = *j;
+	__atomic_store_n(&spec_head, spec_head + 1, __ATOMIC_SEQ_CST);
+	if (__atomic_load_n(&spec_asleep, __ATOMIC_SEQ_CST)) {
+		pthread_mutex_lock(&spec_lock);
+		pthread_cond_signal(&spec_wake);
+		pthread_mutex_unlock(&spec_lock);
+	}
+}
+
 /* Running DFT of scalar samples between wavelengths LMin..LMax with the resolution of an N-step
  * record; normalised by the spectrum of the driving source; written on the N-th call
  * (reference output.c:177-230). */
@@ -223,11 +304,13 @@ void (writeSpectrum)(world W, int N, float LMin, float LMax, char *format, ...)
 	for (int m=1; m<M; m++) {
 		float t = W->t / (dL * nMin * nMax);
 		d = va_arg(ap, double);
-		for (int n=0; n<bins; n++) e->spectrum[m][n] += (float) d * cexpf(2*PI*I*t*(nMax-n));
+		const spec_job job = { e->spectrum[m], bins, nMax, t, d };
+		spec_submit(&job);
 	}
 	va_end(ap);
 
 	if (e->calls == (unsigned long)N) {
+		if (spec_mode > 0) spec_drain();
 		e->file = fopen(strcat(filename, ".txt"), "w");
 		if (!e->file) { printf("alis-b200: cannot open %s\n", filename); exit(0); }
 		for (int n=0; n<bins; n++) {

@@ -3,6 +3,9 @@ validated WITHOUT a GPU: linked against the CPU oracle engine (tests/bin/libalis
 infrastructure) it must reproduce the unmodified reference bit for bit -- the complete field
 state of the 10 configurations (sha256 goldens) and every monitor value of monitors.c (far-field
 values, whose surface sums are engine calls, to 1e-5: helpers.monitor_mismatches)."""
+import os
+import subprocess
+
 import pytest
 
 from tests import helpers
@@ -73,3 +76,29 @@ def test_graded_grid_slices_match_reference_golden(tmp_path):
     want = helpers.golden_graded_slices()
     assert len(want) == 12
     assert helpers.run_graded_slices("graded_slices_mine_oracle", str(tmp_path)) == want
+
+
+def test_spectrum_worker_thread_gives_the_inline_spectrum(tmp_path):
+    """writeSpectrum's running DFT on the worker thread (alis_b200/host/output.c, default with the CUDA engine) against the
+    in-line loop of reference output.c:211-215: same float operations per bin in the same order, so the written spectrum must
+    be byte-identical.  Run here on the CPU engine with the worker forced on."""
+    import shutil
+    exe = os.path.join(helpers.TEST_BIN, "phc_band_diagram_oracle")
+    if not os.path.exists(exe):
+        pytest.skip("tests/bin/phc_band_diagram_oracle not built")
+    outs = []
+    for mode in ("0", "1"):
+        d = tmp_path / f"mode{mode}"
+        d.mkdir()
+        shutil.copy(exe, d / "phc_band_diagram")
+        env = dict(os.environ)
+        env["ALIS_SPECTRUM_THREAD"] = mode
+        env["LD_LIBRARY_PATH"] = helpers.TEST_BIN + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+        env.setdefault("OMP_NUM_THREADS", "4")
+        r = subprocess.run(["./phc_band_diagram", "1.2", "3000"], cwd=d, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        txt = sorted(p for p in d.rglob("*.txt"))
+        assert txt, "no spectrum was written"
+        outs.append([p.read_bytes() for p in txt])
+    assert outs[0] == outs[1], "the worker thread's spectrum differs from the in-line one"
+    assert len(outs[0][0].splitlines()) > 10
