@@ -436,7 +436,7 @@ float SoEE(world W, int i, int j, int k) { return sq(SoEx(W,i,j,k))+sq(SoEy(W,i,
 static float scattered_E(world W, int c, int i, int j, int k)
 {
 	folded r = fold_cos(W, i, j, k, 0.5, SGN(c,0,1), SGN(c,1,1), SGN(c,2,1));
-	NEED(W, r);
+	NEED1(W, 0, c, 0, r);                       /* E component c of the real set is all it reads of this world */
 	i = r.i, j = r.j, k = r.k;
 	float f = e_pair(Ecomp(W,0,c), c, i, j, k);
 	for (tfsf S = W->S; S; S = S->S) {
@@ -474,6 +474,13 @@ unsigned alis_field_arrays(world W, field F)
 	}
 	if (F == EE) return 07;
 	if (F == HH || F == UH) return 070;
+	/* scattered / incident E (fields.c:686-789): one E component of this world (none for the incident field); the
+	 * auxiliary worlds are fetched whole by the functions themselves */
+	if (F == ScEx) return 01;
+	if (F == ScEy) return 02;
+	if (F == ScEz) return 04;
+	if (F == ScEE) return 07;
+	if (F == SoEx || F == SoEy || F == SoEz || F == SoEE) return 0;
 	if (F == RI || F == LogRI || F == ContourRI || F == Contour || F == raweEffx || F == raweEffy || F == raweEffz || F == eEff) return 0;
 	return W->complexField ? 07777 : 077;
 }
@@ -579,8 +586,25 @@ float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0
 	const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
 	for (int a=0; a<3; a++) if (sym[a] && lo[a] < 0) { const int far = MAX(-lo[a], hi[a]); lo[a] = hi[a] < 0 ? -hi[a] : 0; hi[a] = far; }
 	alis_view_need_for(W, F, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
-	size_t q = 0;
-	for (int i=i0; i<=i1; i++) for (int j=j0; j<=j1; j++) for (int k=k0; k<=k1; k++) v[q++] = F(W, i, j, k);
+	/* The reference evaluates a slice under `omp parallel for` (slices.c:262-266), so field functions -- its own and user
+	 * callbacks -- are safe to call concurrently.  Here the region they read has just been fetched; the first cell is
+	 * evaluated alone so that whatever a function fetches lazily (auxiliary worlds of the TFSF source, ADE currents, the
+	 * engine itself) is in place before the team starts, and a fetch that still happens inside the team is serialised
+	 * (view.c).  ALIS_PARALLEL_EVAL=0: one thread. */
+	const size_t total = (size_t)ni*nj*nk;
+	v[0] = F(W, i0, j0, k0);
+	static int team = -1;
+	if (team < 0) { const char *e = getenv("ALIS_PARALLEL_EVAL"); team = e ? atoi(e) != 0 : 1; }
+	if (team && total >= 2048) {
+		#pragma omp parallel for schedule(static)
+		for (long t=1; t<(long)total; t++) {
+			const int k = k0 + (int)(t % nk), j = j0 + (int)((t / nk) % nj), i = i0 + (int)(t / ((long)nk*nj));
+			v[t] = F(W, i, j, k);
+		}
+	} else {
+		size_t q = 0;
+		for (int i=i0; i<=i1; i++) for (int j=j0; j<=j1; j++) for (int k=k0; k<=k1; k++, q++) if (q) v[q] = F(W, i, j, k);
+	}
 	return v;
 }
 

@@ -70,6 +70,13 @@ void alis_view_need_arr(world W, int set, int comp, int m, int i0, int i1, int j
 	if (b[0] > b[1] || b[2] > b[3] || b[4] > b[5]) { view_array(W, set, comp, m); return; }
 	if (a->have && a->synced == v->version &&
 	    a->box[0] <= b[0] && b[1] <= a->box[1] && a->box[2] <= b[2] && b[3] <= a->box[3] && a->box[4] <= b[4] && b[5] <= a->box[5]) return;
+	/* a fetch from inside a team of evaluating threads (alis_eval_region) is rare -- the region was fetched before the team
+	 * started -- but must not run twice at once: one thread at a time, and whoever comes second looks again first */
+	#pragma omp critical(alis_view_fetch)
+	{
+	const int covered = a->have && a->synced == v->version &&
+	    a->box[0] <= b[0] && b[1] <= a->box[1] && a->box[2] <= b[2] && b[3] <= a->box[3] && a->box[4] <= b[4] && b[5] <= a->box[5];
+	if (!covered) {
 	/* grow the working set: monitors called every step (probes, slices) ask for the same regions
 	 * again, so fetch the union with the previous request unless that is wasteful */
 	if (a->have) {
@@ -83,6 +90,8 @@ void alis_view_need_arr(world W, int set, int comp, int m, int i0, int i1, int j
 	pull_box(W, set, comp, m, b);
 	memcpy(a->box, b, sizeof b);
 	a->have = 1; a->synced = v->version;
+	}
+	}
 }
 
 /* all components of both field sets (monitors that mix E and H) */
