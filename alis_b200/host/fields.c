@@ -234,7 +234,7 @@ static float raw_current(world W, int c, int i, int j, int k)
 		           : c==1 ? (C->dtdx[i] * (hz[i][j][k] - hz[i+1][j][k]) + C->dtdz[k] * (hx[i][j][k+1] - hx[i][j][k]))
 		                  : (C->dtdy[j] * (hx[i][j][k] - hx[i][j+1][k]) + C->dtdx[i] * (hy[i+1][j][k] - hy[i][j][k]));
 		f += curl * (1 - inv[i][j][k]);
-		if (C->N) alis_view_need_ade(W);
+		if (C->N) alis_view_need_ade_box(W, i, i, j, j, k, k);       /* the currents of this cell only */
 		for (int n=0; n<C->N; n++) {
 			const int ini = C->iMin[n]<=i && (c==0 ? i<=C->iMax[n] : i<C->iMax[n]);
 			const int inj = C->jMin[n]<=j && (c==1 ? j<=C->jMax[n] : j<C->jMax[n]);
@@ -586,6 +586,8 @@ float *alis_eval_region(world W, field F, int i0, int i1, int j0, int j1, int k0
 	const int sym[3] = { W->xMinSur==SYM, W->yMinSur==SYM, W->zMinSur==SYM };
 	for (int a=0; a<3; a++) if (sym[a] && lo[a] < 0) { const int far = MAX(-lo[a], hi[a]); lo[a] = hi[a] < 0 ? -hi[a] : 0; hi[a] = far; }
 	alis_view_need_for(W, F, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
+	if (alis_field_arrays(W, F) == (W->complexField ? 07777u : 077u))      /* a function this file does not know better: it may read currents */
+		alis_view_need_ade_box(W, lo[0], hi[0]+1, lo[1], hi[1]+1, lo[2], hi[2]+1);
 	/* The reference evaluates a slice under `omp parallel for` (slices.c:262-266), so field functions -- its own and user
 	 * callbacks -- are safe to call concurrently.  Here the region they read has just been fetched; the first cell is
 	 * evaluated alone so that whatever a function fetches lazily (auxiliary worlds of the TFSF source, ADE currents, the

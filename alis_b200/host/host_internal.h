@@ -44,6 +44,7 @@ void alis_view_need_all(world W);
 unsigned alis_field_arrays(world W, field F);   /* bit (m*2+set)*3+comp for every host view F reads */
 void alis_view_need_for(world W, field F, int i0, int i1, int j0, int j1, int k0, int k1);   /* only the arrays F reads */
 void alis_view_need_ade(world W);               /* W->E[m].Jx[n][p] ... host views                */
+void alis_view_need_ade_box(world W, int i0, int i1, int j0, int j1, int k0, int k1);   /* ... over an index box only */
 void alis_view_free(world W);
 /* device twins of the field functions (fields.c) */
 int    alis_host_monitors(void);                       /* env ALIS_HOST_MONITORS=1: host-view path only */

@@ -17,7 +17,7 @@ typedef struct { unsigned long synced; int box[6], have; } arr_state;
 typedef struct {
 	unsigned long version;        /* bumped whenever the device state advances              */
 	arr_state arr[2][2][3];       /* [m][set][comp]: which box of each host view is current  */
-	unsigned long ade_synced; int have_ade;
+	arr_state *ade; int nade;     /* per dispersive object: which box of its current arrays (all poles, components, field sets) is current */
 } view_state;
 
 static view_state *state(world W)
@@ -114,22 +114,72 @@ void alis_view_need_all(world W)
 }
 
 /* host views of the ADE polarisation currents W->E[m].Jx[n][p][i][j][k] (read by rawJ*, jx..jz) */
-void alis_view_need_ade(world W)
+/* The polarisation currents of the dispersive objects over the index box (clipped to every object's own box): what a
+ * function that reads currents at a few cells needs (a `get(W, JE, ...)` every half step used to bring ALL current arrays of
+ * the world back, megabytes per call).  One box per object covers all its poles, components and field sets. */
+void alis_view_need_ade_box(world W, int i0, int i1, int j0, int j1, int k0, int k1)
 {
 	view_state *v = state(W);
 	coeffs *C = W->CE;
 	if (!C->N) return;
-	if (v->have_ade && v->ade_synced == v->version) return;
-	alis_bridge *E = alis_host_bridge(W);
-	for (int m=0; m<=W->complexField; m++) {
-		float *****J[3] = { W->E[m].Jx, W->E[m].Jy, W->E[m].Jz };
-		for (int n=0; n<C->N; n++) for (int p=0; p<C->NK[n]; p++) for (int c=0; c<3; c++) {
-			int32_t ids[6] = { m, n, p, c, 0, 0 };
-			int32_t box[6] = { C->iMin[n]-(W->iMIN-1), C->iMax[n]-(W->iMIN-1), C->jMin[n]-(W->jMIN-1), C->jMax[n]-(W->jMIN-1), C->kMin[n]-(W->kMIN-1), C->kMax[n]-(W->kMIN-1) };
-			if (alis_bridge_read_box(E, ALISB_ARR_ADE_J, ids, box, &J[c][n][p][C->iMin[n]][C->jMin[n]][C->kMin[n]]) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+	if (v->nade < C->N) {
+		#pragma omp critical(alis_view_fetch)
+		if (v->nade < C->N) {
+			arr_state *grown = calloc(C->N, sizeof *grown);
+			if (v->ade) memcpy(grown, v->ade, sizeof(*grown)*v->nade);
+			v->ade = grown;                    /* (the old table, if any, is left to the end of the process: another thread may be reading it) */
+			v->nade = C->N;
 		}
 	}
-	v->have_ade = 1; v->ade_synced = v->version;
+	for (int n=0; n<C->N; n++) {
+		if (!C->NK[n]) continue;
+		arr_state *a = &v->ade[n];
+		int b[6] = { MAX(i0, C->iMin[n]), MIN(i1, C->iMax[n]), MAX(j0, C->jMin[n]), MIN(j1, C->jMax[n]), MAX(k0, C->kMin[n]), MIN(k1, C->kMax[n]) };
+		if (b[0] > b[1] || b[2] > b[3] || b[4] > b[5]) continue;
+		if (a->have && a->synced == v->version &&
+		    a->box[0] <= b[0] && b[1] <= a->box[1] && a->box[2] <= b[2] && b[3] <= a->box[3] && a->box[4] <= b[4] && b[5] <= a->box[5]) continue;
+		#pragma omp critical(alis_view_fetch)
+		{
+		const int covered = a->have && a->synced == v->version &&
+		    a->box[0] <= b[0] && b[1] <= a->box[1] && a->box[2] <= b[2] && b[3] <= a->box[3] && a->box[4] <= b[4] && b[5] <= a->box[5];
+		if (!covered) {
+			if (a->have) {                     /* grow the working set, as alis_view_need_arr does */
+				int u[6];
+				for (int q=0; q<3; q++) u[2*q] = MIN(b[2*q], a->box[2*q]), u[2*q+1] = MAX(b[2*q+1], a->box[2*q+1]);
+				const double vu = (double)(u[1]-u[0]+1)*(u[3]-u[2]+1)*(u[5]-u[4]+1);
+				const double vb = (double)(b[1]-b[0]+1)*(b[3]-b[2]+1)*(b[5]-b[4]+1);
+				const double vo = (double)(a->box[1]-a->box[0]+1)*(a->box[3]-a->box[2]+1)*(a->box[5]-a->box[4]+1);
+				if (vu <= 4*(vb+vo) + 4096) memcpy(b, u, sizeof u);
+			}
+			alis_bridge *E = alis_host_bridge(W);
+			const int nj = b[3]-b[2]+1, nk = b[5]-b[4]+1;
+			const int whole = b[2] == C->jMin[n] && b[3] == C->jMax[n] && b[4] == C->kMin[n] && b[5] == C->kMax[n];   /* whole sheets: contiguous in the host array */
+			float *tmp = whole ? 0 : malloc(sizeof(float)*(size_t)(b[1]-b[0]+1)*nj*nk);
+			for (int m=0; m<=W->complexField; m++) {
+				float *****J[3] = { W->E[m].Jx, W->E[m].Jy, W->E[m].Jz };
+				for (int p=0; p<C->NK[n]; p++) for (int c=0; c<3; c++) {
+					int32_t ids[6] = { m, n, p, c, 0, 0 };
+					int32_t box[6] = { b[0]-(W->iMIN-1), b[1]-(W->iMIN-1), b[2]-(W->jMIN-1), b[3]-(W->jMIN-1), b[4]-(W->kMIN-1), b[5]-(W->kMIN-1) };
+					float ***A = J[c][n][p];
+					if (alis_bridge_read_box(E, ALISB_ARR_ADE_J, ids, box, whole ? &A[b[0]][b[2]][b[4]] : tmp) != ALISB_OK) { printf("alis-b200: %s\n", alisb_last_error()); exit(1); }
+					if (!whole) {
+						size_t q = 0;
+						for (int i=b[0]; i<=b[1]; i++) for (int j=b[2]; j<=b[3]; j++) { memcpy(&A[i][j][b[4]], tmp+q, sizeof(float)*nk); q += nk; }
+					}
+				}
+			}
+			free(tmp);
+			memcpy(a->box, b, sizeof b);
+			a->have = 1; a->synced = v->version;
+		}
+		}
+	}
+}
+
+/* all of them (alisSyncFields, the host path of objectAbsorption) */
+void alis_view_need_ade(world W)
+{
+	alis_view_need_ade_box(W, W->iMIN-1, W->iMAX+1, W->jMIN-1, W->jMAX+1, W->kMIN-1, W->kMAX+1);
 }
 
 void alis_view_free(world W)
@@ -142,6 +192,7 @@ void alis_view_free(world W)
 			if (V[s]->z) removeField(V[s]->z, W->iMIN-1, W->jMIN-1, W->kMIN-1);
 		}
 	}
+	if (W->b200_view) free(((view_state*)W->b200_view)->ade);
 	free(W->b200_view);
 	W->b200_view = 0;
 }
